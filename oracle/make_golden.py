@@ -1,0 +1,134 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (under oracle/ref_shim.py) here.
+
+Run in the build container only (needs /root/reference):   python oracle/make_golden.py
+The fixtures pin `oracle/sttode_oracle.py` and `oracle/pmath_oracle.py` to the reference's own outputs and
+travel to the GPU box, where /root/reference does not exist.  Weights are NOT stored: both sides rebuild
+them with `make_state_dict(seed)`; the reference side loads them with `load_state_dict(strict=True)`,
+which also proves key/shape parity of the 90 parameters + 2 buffers.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_shim                      # noqa: E402
+from oracle import sttode_oracle as O            # noqa: E402
+from sttode_b200 import synth                    # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def ref_model(ref, dataset, tp, tf, seed, dtype=torch.float32):
+    args = ref_shim.make_args(dataset, tp, tf)
+    m = ref.sttode.STTODENet(args, torch.device("cpu")).to(dtype).eval()
+    m.load_state_dict(O.make_state_dict(seed, tp, tf, dtype), strict=True)
+    return m
+
+
+def inject_z(ref, z):
+    ref.sttode.Normal.rsample = lambda self: self.mu + z.to(self.mu.dtype) * self.sigma
+
+
+def np32(t):
+    return t.detach().to(torch.float32).numpy()
+
+
+@torch.no_grad()
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = ref_shim.install()
+    torch.manual_seed(0)
+
+    # ---- MHGSA module: L == S (swap quirk), L != S (cross, transposed), adversarial rows ------------
+    m = ref_model(ref, "eth", 8, 12, seed=1)
+    attn = m.past_encoder.ODE_Encoder.odeblock.odefunc.layers[0].self_attn.temporal_attention_before
+    g = torch.Generator().manual_seed(11)
+    rec = {}
+    for name, (L, S, bsz) in {"sq5": (5, 5, 3), "sq1": (1, 1, 4), "sq33": (33, 33, 2), "x46": (4, 6, 3)}.items():
+        q = torch.randn(L, bsz, 64, generator=g)
+        kv = q if L == S else torch.randn(S, bsz, 64, generator=g)
+        out, w = attn(q, kv, kv)
+        rec[f"{name}_q"], rec[f"{name}_kv"], rec[f"{name}_out"], rec[f"{name}_w"] = map(np32, (q, kv, out, w))
+    np.savez_compressed(os.path.join(OUT, "mhgsa.npz"), **rec)
+
+    # ---- ODE block ---------------------------------------------------------------------------------
+    rec = {}
+    for name, (L, bsz) in {"L1": (1, 7), "L6": (6, 5), "L40": (40, 3)}.items():
+        x = torch.randn(L, bsz, 1, 64, generator=g)
+        m.past_encoder.agent_mask = torch.zeros(1)
+        y = m.past_encoder.ODE_Encoder(x, mask=None, num_agent=bsz)
+        rec[f"{name}_x"], rec[f"{name}_y"] = np32(x), np32(y)
+    np.savez_compressed(os.path.join(OUT, "ode_block.npz"), **rec)
+
+    # ---- full inference: ETH path (set_data + inference) -------------------------------------------
+    rec = {}
+    for idx, n in enumerate((2, 5, 10)):
+        obs, gt = synth.eth_scene(idx, n)
+        ones = torch.ones(n, 8)
+        z = synth.latent(n, seed=7 + idx)
+        inject_z(ref, z)
+        m.set_data(None, obs, gt, ones, torch.ones(n, 12))
+        pred = m.inference(None)                                    # [20,N,12,2]
+        pf = m.past_encoder(torch.cat((m.past_traj, torch.cat([(m.past_traj[:, 1:] - m.past_traj[:, :-1])[:, [0]],
+                            m.past_traj[:, 1:] - m.past_traj[:, :-1]], 1)), -1), 1, n)
+        rec[f"eth{idx}_n"] = np.int64(n)
+        rec[f"eth{idx}_pred"], rec[f"eth{idx}_pf"] = np32(pred), np32(pf)
+        # float64 arbiter of the same reference code
+        m64 = ref_model(ref, "eth", 8, 12, seed=1, dtype=torch.float64)
+        m64.set_data(None, obs.double(), gt.double(), ones.double(), torch.ones(n, 12).double())
+        rec[f"eth{idx}_pred64"] = m64.inference(None).numpy()
+    np.savez_compressed(os.path.join(OUT, "inference_eth.npz"), **rec)
+
+    # ---- full inference: NBA path (set_data_nba + inference), 10/20 and 5/10 -----------------------
+    rec = {}
+    for name, (B, tp, tf) in {"nba1020": (6, 10, 20), "nba0510": (9, 5, 10)}.items():
+        mn = ref_model(ref, "nba", tp, tf, seed=2)
+        data = synth.nba_batch(0, B, 11, tp, tf)
+        z = synth.latent(B * 11, seed=9)
+        inject_z(ref, z)
+        mn.set_data_nba(data)
+        pred = mn.inference(data)
+        rec[f"{name}_pred"] = np32(pred)
+        rec[f"{name}_B"] = np.int64(B)
+    np.savez_compressed(os.path.join(OUT, "inference_nba.npz"), **rec)
+
+    # ---- pmath ---------------------------------------------------------------------------------------
+    P = ref.pmath
+    rec = {}
+    x = torch.randn(16, 8, generator=g) * 0.3
+    y = torch.randn(16, 8, generator=g) * 0.3
+    x[0] = 0; y[1] = 0                                              # zero rows (clamp_min 1e-5 paths)
+    x[2] = x[2] / x[2].norm() * 0.9995                              # beyond the ball margin -> project rescales
+    x[3] = x[3] / x[3].norm() * 5.0                                 # far outside
+    mat = torch.randn(6, 8, generator=g) * 0.5
+    rec.update(x=np32(x), y=np32(y), mat=np32(mat))
+    for c in (1.0, 0.5):
+        t = f"c{c}"
+        px, py = P.project(x, c=c), P.project(y, c=c)
+        rec[f"project_{t}"] = np32(px)
+        rec[f"lambda_x_{t}"] = np32(P.lambda_x(px, c=c))
+        rec[f"mobius_add_{t}"] = np32(P.mobius_add(px, py, c=c))
+        rec[f"dist_{t}"] = np32(P.dist(px, py, c=c))
+        rec[f"dist0_{t}"] = np32(P.dist0(px, c=c))
+        rec[f"expmap0_{t}"] = np32(P.expmap0(x, c=c))
+        rec[f"logmap0_{t}"] = np32(P.logmap0(px, c=c))
+        rec[f"expmap_{t}"] = np32(P.expmap(px, y, c=c))
+        rec[f"logmap_{t}"] = np32(P.logmap(px, py, c=c))
+        rec[f"mobius_matvec_{t}"] = np32(P.mobius_matvec(mat, px, c=c))
+        rec[f"dist_matrix_{t}"] = np32(P.dist_matrix(px, py, c=c))
+        rec[f"poincare_mean_{t}"] = np32(P.poincare_mean(px, dim=0, c=c))
+    s = torch.linspace(-20, 20, 41)
+    rec["tanh"] = np32(P.tanh(s))
+    u = torch.tensor([-1.5, -1.0, -0.99999, -0.5, 0.0, 0.3, 0.99998, 1.0, 2.0])
+    rec["artanh_in"], rec["artanh"] = np32(u), np32(P.artanh(u))
+    rec["arsinh_in"], rec["arsinh"] = np32(s), np32(P.arsinh(s))
+    np.savez_compressed(os.path.join(OUT, "pmath.npz"), **rec)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,145 @@
+"""Pins the CPU oracle to the reference's own outputs (fixtures made by oracle/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sttode_oracle as O
+from oracle import pmath_oracle as PO
+from sttode_b200 import synth
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+@pytest.fixture(scope="module")
+def sd_eth():
+    return O.make_state_dict(1, 8, 12)
+
+
+ATT = "past_encoder.ODE_Encoder.odeblock.odefunc.layers.0.self_attn.temporal_attention_before."
+
+
+@pytest.mark.parametrize("name", ["sq5", "sq1", "sq33", "x46"])
+def test_mhgsa_matches_reference(golden, sd_eth, name):
+    g = golden("mhgsa")
+    q, kv = torch.from_numpy(g[f"{name}_q"]), torch.from_numpy(g[f"{name}_kv"])
+    out, w = O.hyp_mhsa(q, kv, kv, sd_eth[ATT + "in_proj_weight"], sd_eth[ATT + "in_proj_bias"],
+                        sd_eth[ATT + "out_proj.weight"], sd_eth[ATT + "out_proj.bias"])
+    # identical op sequence except the fused 192-wide projection is sliced: <= a few ulp
+    assert rel(out, g[f"{name}_out"]) < 2e-6
+    assert rel(w, g[f"{name}_w"]) < 2e-6
+    assert list(w.shape) == list(g[f"{name}_w"].shape)
+
+
+def test_mhgsa_square_swap_quirk(golden, sd_eth):
+    """L == S uses acos(k_i . q_j) un-transposed (SURVEY finding 4): the textbook orientation must differ."""
+    g = golden("mhgsa")
+    q = torch.from_numpy(g["sq5_q"])
+    st = O.hyp_mhsa_stages(q, sd_eth[ATT + "in_proj_weight"], sd_eth[ATT + "in_proj_bias"])
+    sc = st["scores"]
+    manual = -torch.acos((st["k_hat"] @ st["q_hat"].transpose(1, 2)).clamp(-1 + 1e-4, 1 - 1e-4))
+    assert torch.equal(sc, manual)
+    assert (sc - sc.transpose(1, 2)).abs().max() > 1e-2
+
+
+@pytest.mark.parametrize("name", ["L1", "L6", "L40"])
+def test_ode_block_matches_reference(golden, sd_eth, name):
+    g = golden("ode_block")
+    y = O.ode_encoder(torch.from_numpy(g[f"{name}_x"]), sd_eth, "past_encoder.")
+    assert rel(y, g[f"{name}_y"]) < 2e-6
+
+
+def test_ode_block_is_single_euler_step(sd_eth):
+    x = torch.randn(3, 4, 1, 64, generator=torch.Generator().manual_seed(3))
+    p = "past_encoder.ODE_Encoder.odeblock.odefunc.layers.0."
+    manual = torch.relu(x + 12.0 * O.encoder_layer(x, sd_eth, p))
+    assert torch.equal(O.ode_encoder(x, sd_eth, "past_encoder."), manual)
+
+
+@pytest.mark.parametrize("idx,n", [(0, 2), (1, 5), (2, 10)])
+def test_inference_eth_matches_reference(golden, sd_eth, idx, n):
+    g = golden("inference_eth")
+    obs, _ = synth.eth_scene(idx, n)
+    past, orig = O.eth_scene_normalise(obs)
+    dump = {}
+    pred = O.inference(sd_eth, past, 1, n, synth.latent(n, seed=7 + idx), scene_orig=orig, dump=dump)
+    assert rel(dump["past_feature"], g[f"eth{idx}_pf"]) < 2e-6
+    assert rel(pred, g[f"eth{idx}_pred"]) < 2e-6
+    # fp32 reference vs its own fp64 run: the noise floor every tolerance is judged against
+    assert rel(g[f"eth{idx}_pred"], g[f"eth{idx}_pred64"]) < 1e-5
+
+
+def test_inference_eth_fp64_arbiter(golden):
+    g = golden("inference_eth")
+    sd64 = O.make_state_dict(1, 8, 12, torch.float64)
+    obs, _ = synth.eth_scene(1, 5)
+    past, orig = O.eth_scene_normalise(obs.double())
+    pred = O.inference(sd64, past, 1, 5, synth.latent(5, seed=8).double(), scene_orig=orig)
+    # the reference accumulates `prediction` in a float32 zeros tensor even when the model is double
+    # (model/STTODE.py:333 `torch.zeros(...)` + in-place `+=`), so its own fp64 run carries fp32 rounding
+    assert rel(pred, g["eth1_pred64"]) < 2e-7
+
+
+@pytest.mark.parametrize("name,tp,tf", [("nba1020", 10, 20), ("nba0510", 5, 10)])
+def test_inference_nba_matches_reference(golden, name, tp, tf):
+    g = golden("inference_nba")
+    B = int(g[f"{name}_B"])
+    sd = O.make_state_dict(2, tp, tf)
+    data = synth.nba_batch(0, B, 11, tp, tf)
+    past = data["past_traj"].view(B * 11, tp, 2)
+    pred = O.inference(sd, past, B, 11, synth.latent(B * 11, seed=9))
+    assert rel(pred, g[f"{name}_pred"]) < 2e-6
+
+
+def test_gru_fast_path_equals_loop(sd_eth):
+    p = "decoder.decompose.0.encoder_past."
+    x = torch.randn(13, 8, 32, generator=torch.Generator().manual_seed(5))
+    a = O.gru_last_state(x, sd_eth[p + "weight_ih_l0"], sd_eth[p + "weight_hh_l0"], sd_eth[p + "bias_ih_l0"], sd_eth[p + "bias_hh_l0"])
+    b = O.gru_last_state(x, sd_eth[p + "weight_ih_l0"], sd_eth[p + "weight_hh_l0"], sd_eth[p + "bias_ih_l0"], sd_eth[p + "bias_hh_l0"], fast=True)
+    assert rel(a, b) < 1e-6
+
+
+def test_state_dict_inventory():
+    spec = O.state_dict_spec(8, 12)
+    assert len(spec) == 92
+    n_params = sum(int(np.prod(s)) for k, s, kind in spec if kind != "pe")
+    assert n_params == 1_627_792          # SURVEY.md §8b [measured] at 8/12
+    assert sum(int(np.prod(s)) for k, s, kind in O.state_dict_spec(5, 10) if kind != "pe") == 1_602_172
+    assert sum(int(np.prod(s)) for k, s, kind in O.state_dict_spec(10, 20) if kind != "pe") == 1_679_032
+
+
+# ------------------------------------------------------------------ pmath
+@pytest.mark.parametrize("c", [1.0, 0.5])
+def test_pmath_matches_reference(golden, c):
+    g = golden("pmath")
+    x, y, mat = (torch.from_numpy(g[k]) for k in ("x", "y", "mat"))
+    t = f"c{c}"
+    px, py = PO.project(x, c), PO.project(y, c)
+    got = {
+        "project": px, "lambda_x": PO.lambda_x(px, c), "mobius_add": PO.mobius_add(px, py, c),
+        "dist": PO.dist(px, py, c), "dist0": PO.dist0(px, c), "expmap0": PO.expmap0(x, c),
+        "logmap0": PO.logmap0(px, c), "expmap": PO.expmap(px, y, c), "logmap": PO.logmap(px, py, c),
+        "mobius_matvec": PO.mobius_matvec(mat, px, c), "dist_matrix": PO.dist_matrix(px, py, c),
+        "poincare_mean": PO.poincare_mean(px, 0, c),
+    }
+    for k, v in got.items():
+        ref = g[f"{k}_{t}"]
+        assert v.shape == ref.shape, k
+        np.testing.assert_allclose(v.numpy(), ref, rtol=1e-6, atol=1e-7, err_msg=k, equal_nan=True)
+
+
+def test_pmath_scalar_fns(golden):
+    g = golden("pmath")
+    np.testing.assert_array_equal(PO.tanh(torch.linspace(-20, 20, 41)).numpy(), g["tanh"])
+    np.testing.assert_array_equal(PO.artanh(torch.from_numpy(g["artanh_in"])).numpy(), g["artanh"])
+    np.testing.assert_array_equal(PO.arsinh(torch.from_numpy(g["arsinh_in"])).numpy(), g["arsinh"])
+
+
+def test_dist_matrix_closed_form_fp64():
+    g = torch.Generator().manual_seed(4)
+    x = PO.project(torch.randn(9, 8, generator=g, dtype=torch.float64) * 0.4)
+    y = PO.project(torch.randn(7, 8, generator=g, dtype=torch.float64) * 0.4)
+    for c in (1.0, 0.7):
+        np.testing.assert_allclose(PO.dist_matrix_closed_form(x, y, c).numpy(), PO.dist_matrix(x, y, c).numpy(), rtol=1e-9, atol=1e-9)
