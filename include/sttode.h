@@ -1,0 +1,219 @@
+/* sttode.h — C ABI of libsttode_sm100.so, the B200 (sm_100a) implementation of the STTODE forward hot path.
+ *
+ * The reference (joyecnu/STTODE) is pure Python/PyTorch and has no FFI; its boundary for this path is the
+ * Python module API.  Each entry point below names the reference interface it replaces
+ * (file:line relative to the reference root).  INTEGRATION.md shows the ctypes binding a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only.  All `const float*` / `float*` are DEVICE pointers to contiguous fp32
+ *     unless the name ends in `_host`.  `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - ownership: the caller owns every buffer including the workspace; the library never allocates or frees
+ *     device memory on these calls and keeps no pointer after return (exception: *_host entry points own a
+ *     cached pinned/device staging arena, released by sttode_release_host_arena()).
+ *   - errors: return 0 on success, negative STTODE_E* otherwise; text via sttode_last_error() (thread local).
+ *     Unsupported shapes/options are errors, never fallbacks.  There is no CPU path.
+ *   - work is only enqueued on `stream`; no implicit synchronisation; safe under CUDA-graph capture
+ *     (except *_host, which synchronises the stream before returning).
+ *   - weights use the reference's state_dict tensors as they are (nn.Linear layout W[out][in]).
+ */
+#ifndef STTODE_H_
+#define STTODE_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STTODE_VERSION 100          /* 0.1.0 */
+#define STTODE_D 64                 /* model width  (model/STTODE.py:182, hidden_dim) */
+#define STTODE_H 8                  /* heads        (model/STTODE.py:190) */
+#define STTODE_FF 1024              /* FFN width    (model/STTODE.py:191) */
+#define STTODE_ZDIM 32              /* latent width (train.py:37) */
+#define STTODE_GRU 96               /* GRU state    (model/STTODE.py:26) */
+
+enum {
+    STTODE_OK = 0,
+    STTODE_EINVAL = -1,     /* bad shape / option / null pointer */
+    STTODE_EUNSUPPORTED = -2, /* option the reference accepts but this path does not implement */
+    STTODE_EWORKSPACE = -3, /* workspace too small */
+    STTODE_ECUDA = -4,      /* CUDA runtime error (launch, device mismatch: needs sm_100) */
+};
+
+/* score_mode of the geodesic attention */
+enum {
+    STTODE_SCORE_OBLIQUE_ACOS = 0,  /* -acos(clamp(<k^,q^>)) : the live reference path (core/manifolds/oblique.py:36-45) */
+    STTODE_SCORE_POINCARE_DIST = 1, /* -dist_c(expmap0(q), expmap0(k)) via the Gram closed form (hyptorch/pmath.py:482-493) */
+};
+
+/* explicit fixed-step solvers for the tensor ODE (ode_demo.py:186-190 uses EULER with one step of h = 12) */
+enum { STTODE_ODE_EULER = 0, STTODE_ODE_MIDPOINT = 1, STTODE_ODE_RK4 = 2 /* classic */, STTODE_ODE_RK4_38 = 3 /* torchdiffeq 'rk4' */ };
+
+/* trajectory memory layouts */
+enum { STTODE_TRAJ_RT2 = 0 /* [rows, T, 2]  (NBA: data['past_traj'].view(B*N,T,2)) */,
+       STTODE_TRAJ_R2T = 1 /* [rows, 2, T]  (ETH/SDD loaders: obs_traj [N,2,T]) */ };
+
+/* Hyp_mhsa parameters (hyptransformerlib.py:356-365): in_proj_weight [3E,E], in_proj_bias [3E], out_proj [E,E],[E] */
+typedef struct sttode_mhgsa_weights {
+    const float *in_proj_w, *in_proj_b, *out_proj_w, *out_proj_b;
+} sttode_mhgsa_weights;
+
+/* one TransformerEncoderLayer = the ODE right-hand side (hypertransformer.py:112-127) */
+typedef struct sttode_ode_weights {
+    sttode_mhgsa_weights attn;                  /* self_attn.temporal_attention_before.*            */
+    const float *info_w, *info_b;               /* self_attn.temporal_info   [64,64],[64]           */
+    const float *gate_w, *gate_b;               /* self_attn.temporal_gate   [64,64],[64]           */
+    const float *lin1_w, *lin1_b;               /* linear1 [1024,64],[1024]                         */
+    const float *lin2_w, *lin2_b;               /* linear2 [64,1024],[64]                           */
+    const float *norm1_g, *norm1_b, *norm2_g, *norm2_b; /* LayerNorm(64), eps 1e-5                  */
+} sttode_ode_weights;
+
+/* PastEncoder / FutureEncoder front end (model/STTODE.py:179-197) */
+typedef struct sttode_encoder_weights {
+    const float *fc_w, *fc_b;                   /* input_fc  [64,4],[64]                            */
+    const float *pe;                            /* pos_encoder.pe [200,64]                          */
+    const float *pefc_w, *pefc_b;               /* pos_encoder.fc [64,128],[64]                     */
+    const float *fc2_w, *fc2_b;                 /* input_fc2 [64,64*T],[64]                         */
+    const float *fc3_w, *fc3_b;                 /* input_fc3 [64,67],[64]                           */
+    sttode_ode_weights ode;                     /* ODE_Encoder.odeblock.odefunc.layers.0.*          */
+} sttode_encoder_weights;
+
+/* one DecomposeBlock (model/STTODE.py:16-38) */
+typedef struct sttode_mlp3_weights { const float *w0, *b0, *w1, *b1, *w2, *b2; } sttode_mlp3_weights; /* 256->512->256->out */
+typedef struct sttode_decompose_weights {
+    const float *conv_w, *conv_b;               /* conv_past [32,2,3],[32]                          */
+    const float *gru_w_ih, *gru_w_hh, *gru_b_ih, *gru_b_hh; /* encoder_past [288,32],[288,96],[288],[288] */
+    sttode_mlp3_weights dec_y;                  /* decoder_y -> 2*T_f                               */
+    sttode_mlp3_weights dec_x;                  /* decoder_x -> 2*T_p                               */
+} sttode_decompose_weights;
+
+typedef struct sttode_model_weights {
+    int past_length, future_length;             /* args.past_length / future_length                 */
+    sttode_encoder_weights past;                /* past_encoder.*                                   */
+    sttode_decompose_weights dec[2];            /* decoder.decompose.{0,1}.*  (num_decompose = 2)   */
+} sttode_model_weights;
+
+/* ---- diagnostics ------------------------------------------------------------------------------- */
+int sttode_version(void);
+const char *sttode_last_error(void);
+/* 0 when the current CUDA device is compute capability 10.x, else STTODE_ECUDA (load fails loudly elsewhere) */
+int sttode_device_check(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+unsigned long long sttode_launch_count(void);
+
+/* measurement hook: when enabled, every launch of the dominant kernel (k_dec_pair, the per-(agent,sample)
+ * decoder tile) is bracketed by CUDA events on its own stream; _read waits for them, returns the summed
+ * device time and the number of launches since the last read, and recycles the events. */
+int sttode_profile_enable(int on);
+int sttode_profile_read(double *total_ms, unsigned long long *launches);
+
+/* ---- MHGSA: replaces Hyp_mhsa.forward -> hyp_mhsa (hyptransformerlib.py:403-454 -> :29-311) ------
+ * query [L,bsz,E], key/value [S,bsz,E] (key==value==query pointer for self-attention), out [L,bsz,E],
+ * attn_weights (nullable) [bsz,L,S] = head-averaged softmax (need_weights=True, :306-309).
+ * E must be 64 and H 8.  When L == S the reference's un-transposed score matrix is reproduced
+ * (out_i = sum_j softmax_j(-acos(k^_i . q^_j)) v_j, SURVEY.md finding 4); L != S is textbook. */
+size_t sttode_mhgsa_workspace_bytes(int L, int S, int bsz);
+int sttode_mhgsa_fwd(const float *query, const float *key, const float *value, const sttode_mhgsa_weights *w,
+                     float *out, float *attn_weights, int L, int S, int bsz, int E, int H, int score_mode,
+                     float clamp_eps, float curvature, void *workspace, size_t workspace_bytes, void *stream);
+
+/* `linear` (hyptransformerlib.py:7-26) for the path's shapes: out[rows,out_features] = x[rows,64] . W[out_features,64]^T + b,
+ * out_features a multiple of 64 (QKV 192, out-proj / gates 64). */
+int sttode_linear64(const float *x, const float *weight, const float *bias, float *out, int rows, int out_features, void *stream);
+
+/* ---- tensor-ODE block: replaces ODEG_Encoder.forward (ode_demo.py:217-231) incl. the torchdiffeq solver
+ * loop (ode_demo.py:186-190), TransformerEncoder_ode.forward (:53-72), TransformerEncoderLayer.forward
+ * (hypertransformer.py:134-153) and Hypattention.forward (:55-89).
+ * x [L, bsz, 64] (the reference's [L,bsz,1,64]); y rows have stride ldy floats (>= 64) so the result can
+ * land in past_feature[:, 64:128].  y = relu(solve(x, t in [0, n_steps*h])) when final_relu, else raw.
+ * Reference call: n_steps = 1, h = 12, method = EULER, final_relu = 1. */
+size_t sttode_ode_block_workspace_bytes(int L, int bsz, int method);
+int sttode_ode_block_fwd(const float *x, const sttode_ode_weights *w, float *y, int ldy, int L, int bsz,
+                         int n_steps, float h, int method, int final_relu, void *workspace,
+                         size_t workspace_bytes, void *stream);
+/* one evaluation of the ODE right-hand side f(t, y) (TransformerEncoder_ode.forward, ode_demo.py:53-72) */
+int sttode_ode_rhs_fwd(const float *x, const sttode_ode_weights *w, float *f, int L, int bsz, void *workspace,
+                       size_t workspace_bytes, void *stream);
+
+/* Hypattention.forward on its own (hypertransformer.py:55-89): out = tanh(W_i m + b_i) * sigmoid(W_g m + b_g),
+ * m = MHGSA(x).  Only the attn / info / gate members of `w` are read.  Workspace as for the ODE block. */
+int sttode_hypattention_fwd(const float *x, const sttode_ode_weights *w, float *out, int L, int bsz, void *workspace,
+                            size_t workspace_bytes, void *stream);
+
+/* ---- PastEncoder.forward (model/STTODE.py:214-236), eval mode.
+ * traj: raw positions in `layout`; n_batches groups of (L scenes x agents) rows, rows = n_batches*L*agents
+ * ordered [batch][scene][agent] (NBA: L = B scenes attend to each other per agent).  For ETH/SDD (L = 1)
+ * scenes of different sizes are concatenated: scene_ptr [n_scenes+1] and row_scene [rows] (int32, device)
+ * give the CSR split; the scene origin (mean last-frame position, model/STTODE.py:417) is subtracted and
+ * returned in origin [n_scenes,2].  scene_ptr == NULL means NBA semantics (no normalisation, category flag
+ * on agent index agents-1 of every scene, model/STTODE.py:199-210).
+ * Outputs: past_feature [rows,128], traj_norm [rows,T_p,2] (the reference's self.past_traj). */
+size_t sttode_past_encoder_workspace_bytes(int rows, int L);
+int sttode_past_encoder_fwd(const float *traj, int layout, const int *scene_ptr, const int *row_scene, int n_scenes,
+                            int rows, int L, int agents, const sttode_model_weights *w, float *past_feature,
+                            float *traj_norm, float *origin, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- Decoder.forward (model/STTODE.py:320-347) in 'inference' mode, both DecomposeBlocks (:51-77).
+ * past_feature [rows,128] (one row per agent, NOT repeated K times), traj_norm [rows,T_p,2],
+ * z [rows*K, 32] or NULL to draw z ~ N(0,I) in-kernel from (seed) with Philox (the reference's randn_like,
+ * model/STTODE.py:616).  row_scene/origin (nullable) add the scene origin back (:621-622).
+ * pred [rows, K, T_f, 2]  (== reference output [K,rows,T_f,2].permute(1,0,2,3), test.py:186).
+ * recon (nullable) [rows*K, T_p, 2] = the reconstruction the reference returns as recover_pre_seq. */
+size_t sttode_decoder_workspace_bytes(int rows, int sample_k);
+int sttode_decoder_fwd(const float *past_feature, const float *traj_norm, const float *z, unsigned long long seed,
+                       const int *row_scene, const float *origin, int rows, int sample_k,
+                       const sttode_model_weights *w, float *pred, float *recon, void *workspace,
+                       size_t workspace_bytes, void *stream);
+
+/* ---- STTODENet.inference (model/STTODE.py:574-623) incl. set_data / set_data_nba preprocessing
+ * (:397-486): past encoder + K-sample decoder in one call, device buffers. */
+size_t sttode_forecast_workspace_bytes(int rows, int L, int sample_k, int past_length);
+int sttode_forecast(const float *traj, int layout, const int *scene_ptr, const int *row_scene, int n_scenes,
+                    int rows, int L, int agents, const float *z, unsigned long long seed, int sample_k,
+                    const sttode_model_weights *w, float *pred, float *past_feature_or_null,
+                    float *traj_norm_or_null /* [rows,T_p,2] = self.past_traj */, float *origin_or_null /* [n_scenes,2] = self.scene_orig */,
+                    void *workspace, size_t workspace_bytes, void *stream);
+
+/* Same with HOST trajectory / prediction buffers (the end-to-end call test.py's loop makes per batch:
+ * H2D of the batch, inference, D2H of the K samples; test.py:175-194).  Weights stay device resident.
+ * Stages through an internal pinned + device arena (grown on demand, freed by sttode_release_host_arena). */
+int sttode_forecast_host(const float *traj_host, int layout, const int *scene_ptr_host, int n_scenes, int rows,
+                         int L, int agents, unsigned long long seed, int sample_k, const sttode_model_weights *w,
+                         float *pred_host, void *stream);
+void sttode_release_host_arena(void);
+
+/* ---- min-over-K ADE/FDE on device (utils/metrics.py:7-26; test.py:204-208): sums[0] += sum_agents minADE,
+ * sums[1] += sum_agents minFDE, sums[2] += rows  (double[3], device; AverageMeter numerators). */
+int sttode_min_ade_fde(const float *pred, const float *gt, int gt_layout, int rows, int sample_k, int future_length,
+                       double *sums, void *stream);
+
+/* ---- Oblique manifold stand-alone ops: replace Oblique.proj / Oblique.dist (core/manifolds/oblique.py:15-16, 36-45).
+ * proj: out = x / ||x||_2 over the last dim (no epsilon).  dist(p1 [batch,n1,d], p2 [batch,n2,d]) ->
+ * out [batch,n2,n1] = acos(clamp(p2 @ p1^T, -1+eps, 1-eps)) — note the reference's argument order. */
+int sttode_oblique_proj(const float *x, float *out, int rows, int d, void *stream);
+int sttode_oblique_dist(const float *p1, const float *p2, float *out, int batch, int n1, int n2, int d, float clamp_eps, void *stream);
+
+/* ---- Poincare-ball library: replaces hyptorch/pmath.py (rows = product of leading dims, d = last dim) ---- */
+int sttode_pmath_project(const float *x, float *out, int rows, int d, float c, void *stream);            /* :76-103  */
+int sttode_pmath_lambda_x(const float *x, float *out, int rows, int d, float c, void *stream);           /* :106-129 */
+int sttode_pmath_mobius_add(const float *x, const float *y, float *out, int rows, int d, float c, void *stream); /* :132-177 */
+int sttode_pmath_dist(const float *x, const float *y, float *out, int rows, int d, float c, void *stream);       /* :180-208 */
+int sttode_pmath_dist0(const float *x, float *out, int rows, int d, float c, void *stream);              /* :211-234 */
+int sttode_pmath_expmap0(const float *u, float *out, int rows, int d, float c, void *stream);            /* :280-304 */
+int sttode_pmath_logmap0(const float *y, float *out, int rows, int d, float c, void *stream);            /* :342-368 */
+int sttode_pmath_expmap(const float *x, const float *u, float *out, int rows, int d, float c, void *stream);     /* :237-277 */
+int sttode_pmath_logmap(const float *x, const float *y, float *out, int rows, int d, float c, void *stream);     /* :307-339 */
+/* m [dout, d]; out [rows, dout] */
+int sttode_pmath_mobius_matvec(const float *m, const float *x, float *out, int rows, int d, int dout, float c, void *stream); /* :371-408 */
+/* x [b, d], y [n, d] -> out [b, n]; Gram-epilogue closed form, nothing of size b*n*d is materialised */
+int sttode_pmath_dist_matrix(const float *x, const float *y, float *out, int b, int n, int d, float c, void *stream); /* :482-493 */
+/* elementwise helpers (:11-12, :16-22, :51-55) */
+int sttode_pmath_tanh(const float *x, float *out, size_t n, float clamp, void *stream);
+int sttode_pmath_artanh(const float *x, float *out, size_t n, void *stream);
+int sttode_pmath_arsinh(const float *x, float *out, size_t n, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STTODE_H_ */

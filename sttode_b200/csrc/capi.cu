@@ -1,0 +1,603 @@
+// extern "C" entry points of libsttode_sm100.so (see include/sttode.h for the contract).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <atomic>
+#include <mutex>
+#include <utility>
+#include <vector>
+#include "kernels.cuh"
+
+namespace sttode {
+void launch_pmath_rows(int op, const float* x, const float* y, float* out, int rows, int d, float c, cudaStream_t st);
+void launch_pmath_matvec(const float* m, const float* x, float* out, int rows, int d, int dout, float c, cudaStream_t st);
+void launch_pmath_dist_matrix(const float* x, const float* y, float* out, int b, int n, int d, float c, cudaStream_t st);
+void launch_pmath_elem(int op, const float* x, float* out, size_t n, float clampv, cudaStream_t st);
+void launch_oblique_proj(const float* x, float* out, int rows, int d, cudaStream_t st);
+void launch_oblique_dist(const float* p1, const float* p2, float* out, int batch, int n1, int n2, int d, float lo, float hi, cudaStream_t st);
+}
+using namespace sttode;
+
+namespace {
+thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess) return fail(STTODE_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+#define LAUNCH_CHECK(name)                                                                      \
+    do {                                                                                        \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                     \
+        cudaError_t e_ = cudaGetLastError();                                                    \
+        if (e_ != cudaSuccess) return fail(STTODE_ECUDA, "launch %s: %s", name, cudaGetErrorString(e_)); \
+    } while (0)
+
+// optional CUDA-event bracketing of the dominant kernel (k_dec_pair) for bench.py's roofline leg
+struct Profiler {
+    std::mutex mu;
+    bool on = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> used, pool;
+} g_prof;
+
+inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+template <typename Kern>
+int set_smem(Kern kern, size_t bytes, const char* name) {
+    if (bytes > 227 * 1024) return fail(STTODE_EUNSUPPORTED, "%s needs %zu B of shared memory (> 227 KB): sequence too long", name, bytes);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return fail(STTODE_ECUDA, "cudaFuncSetAttribute(%s, %zu): %s", name, bytes, cudaGetErrorString(e));
+    return 0;
+}
+
+struct Carver {          // bump allocator over the caller's workspace
+    char* base; size_t size, off = 0;
+    Carver(void* p, size_t n) : base((char*)p), size(n) {}
+    template <typename T> T* take(size_t count) {
+        size_t bytes = align_up(count * sizeof(T));
+        if (!base || off + bytes > size) { off = size + 1; return nullptr; }
+        T* r = (T*)(base + off);
+        off += bytes;
+        return r;
+    }
+    bool ok() const { return off <= size; }
+};
+
+// ---- attention core shared by sttode_mhgsa_fwd and the ODE right-hand side ---------------------------
+struct AttnWs { float *q, *kv, *o, *den; };
+size_t attn_ws_floats(int L, int S, int bsz, bool self_attn, bool want_weights) {
+    size_t f = 0;
+    f += align_up((size_t)L * bsz * (self_attn ? 192 : 64) * 4) / 4;
+    if (!self_attn) f += align_up((size_t)S * bsz * 128 * 4) / 4;
+    f += align_up((size_t)L * bsz * 64 * 4) / 4;
+    if (want_weights) f += align_up((size_t)bsz * 8 * L * 4) / 4;
+    return f;
+}
+
+// projected q^ (scaled, on-manifold), k^ (on-manifold), v -> o = attention output before out_proj.
+// self-attention layout: one [rows,192] buffer (q^|k^|v).  nb = number of independent (L x bsz) batches.
+int run_attention(const float* xq, const float* xk, const float* xv, bool self_attn, const sttode_mhgsa_weights& w, int L,
+                  int S, int bsz, int nb, int score_mode, float clamp_eps, float curv, Carver& ws, float** o_out,
+                  float* attn_weights, cudaStream_t st) {
+    const int rows_q = nb * L * bsz, rows_k = nb * S * bsz;
+    float *qb, *kb, *vb;
+    int ldq, ldk;
+    const float scale = 0.35355339059327379f;       // float(head_dim) ** -0.5, head_dim = 8 (hyptransformerlib.py:110)
+    int rc;
+    if ((rc = set_smem(k_proj, proj_smem_bytes(), "k_proj"))) return rc;
+    if (self_attn) {
+        float* qkv = ws.take<float>((size_t)rows_q * 192);
+        if (!qkv) return fail(STTODE_EWORKSPACE, "workspace too small for qkv");
+        k_proj<<<ceil_div(rows_q, BM), NTHREADS, proj_smem_bytes(), st>>>(xq, 64, rows_q, w.in_proj_w, w.in_proj_b, 3, qkv, 192,
+                                                                        0x1u, 0x3u, scale, score_mode, curv);
+        LAUNCH_CHECK("k_proj");
+        qb = qkv; kb = qkv + 64; vb = qkv + 128; ldq = ldk = 192;
+    } else {
+        float* qq = ws.take<float>((size_t)rows_q * 64);
+        float* kv = ws.take<float>((size_t)rows_k * 128);
+        if (!qq || !kv) return fail(STTODE_EWORKSPACE, "workspace too small for q/kv");
+        k_proj<<<ceil_div(rows_q, BM), NTHREADS, proj_smem_bytes(), st>>>(xq, 64, rows_q, w.in_proj_w, w.in_proj_b, 1, qq, 64,
+                                                                        0x1u, 0x1u, scale, score_mode, curv);
+        LAUNCH_CHECK("k_proj(q)");
+        k_proj<<<ceil_div(rows_k, BM), NTHREADS, proj_smem_bytes(), st>>>(xk, 64, rows_k, w.in_proj_w + 64 * 64, w.in_proj_b + 64, 1,
+                                                                        kv, 128, 0x0u, 0x1u, 1.f, score_mode, curv);
+        LAUNCH_CHECK("k_proj(k)");
+        k_proj<<<ceil_div(rows_k, BM), NTHREADS, proj_smem_bytes(), st>>>(xv, 64, rows_k, w.in_proj_w + 128 * 64, w.in_proj_b + 128, 1,
+                                                                        kv + 64, 128, 0x0u, 0x0u, 1.f, score_mode, curv);
+        LAUNCH_CHECK("k_proj(v)");
+        qb = qq; ldq = 64; kb = kv; vb = kv + 64; ldk = 128;
+    }
+    float* o = ws.take<float>((size_t)rows_q * 64);
+    float* den = attn_weights ? ws.take<float>((size_t)nb * bsz * 8 * L) : nullptr;
+    if (!o || (attn_weights && !den)) return fail(STTODE_EWORKSPACE, "workspace too small for attention output");
+    const float lo = (float)(-1.0 + (double)clamp_eps), hi = (float)(1.0 - (double)clamp_eps);
+    // L == S: the reference leaves acos(k^ q^T) un-transposed (hyptransformerlib.py:261-265): rows are keys.
+    const bool swap = (L == S);
+    const float* rowop = swap ? kb : qb;
+    const float* colop = swap ? qb : kb;
+    const int ldr = swap ? ldk : ldq, ldc = swap ? ldq : ldk;
+    const int Lr = L, Lc = S;
+    dim3 grid(nb * bsz * 8, ceil_div(Lr, 128));
+    k_geo_attn<<<grid, 128, 0, st>>>(rowop, ldr, colop, ldc, vb, ldk, o, 64, den, Lr, Lc, bsz, score_mode, lo, hi, curv);
+    LAUNCH_CHECK("k_geo_attn");
+    if (attn_weights) {
+        k_attn_weights<<<dim3(nb * bsz, Lr), 128, 0, st>>>(rowop, ldr, colop, ldc, den, attn_weights, Lr, Lc, bsz, score_mode, lo, hi, curv);
+        LAUNCH_CHECK("k_attn_weights");
+    }
+    *o_out = o;
+    return 0;
+}
+
+int check_ptrs_mhgsa(const sttode_mhgsa_weights* w) {
+    if (!w || !w->in_proj_w || !w->in_proj_b || !w->out_proj_w || !w->out_proj_b)
+        return fail(STTODE_EINVAL, "Hyp_mhsa weights: null pointer (bias=False is not supported)");
+    return 0;
+}
+
+// f = rhs(x) for nb batches of [L, bsz, 64]; out = act(base + coef*f)
+int run_rhs(const float* x, int L, int bsz, int nb, const sttode_ode_weights& w, const float* base, int ldb, float coef, int relu,
+            float* out, int ldout, Carver ws /* by value: scratch is reusable after the call */, cudaStream_t st, int gate_only = 0) {
+    const int rows = nb * L * bsz;
+    float* o = nullptr;
+    int rc;
+    if (L > 1) {
+        if ((rc = run_attention(x, x, x, true, w.attn, L, L, bsz, nb, STTODE_SCORE_OBLIQUE_ACOS, 1e-4f, 1.f, ws, &o, nullptr, st))) return rc;
+    }
+    if ((rc = set_smem(k_ode_tail, ode_tail_smem_bytes(), "k_ode_tail"))) return rc;
+    k_ode_tail<<<ceil_div(rows, BM), NTHREADS, ode_tail_smem_bytes(), st>>>(x, 64, o, 64, base, ldb, coef, relu, out, ldout, rows, w, gate_only);
+    LAUNCH_CHECK("k_ode_tail");
+    return 0;
+}
+
+size_t rhs_ws_bytes(int rows, int L) { return L > 1 ? align_up((size_t)rows * 192 * 4) + align_up((size_t)rows * 64 * 4) : 0; }
+
+int run_ode_block(const float* x, int L, int bsz, int nb, const sttode_ode_weights& w, int n_steps, float h, int method,
+                  int final_relu, float* y, int ldy, Carver ws, cudaStream_t st) {
+    const int rows = nb * L * bsz;
+    int rc;
+    if (n_steps < 1) return fail(STTODE_EINVAL, "n_steps must be >= 1");
+    if (method == STTODE_ODE_EULER) {
+        // y_{k+1} = y_k + h f(y_k); intermediate states ping-pong through the workspace, last step writes y
+        float* tmp[2] = {nullptr, nullptr};
+        if (n_steps > 1) {
+            tmp[0] = ws.take<float>((size_t)rows * 64);
+            tmp[1] = ws.take<float>((size_t)rows * 64);
+            if (!tmp[0] || !tmp[1]) return fail(STTODE_EWORKSPACE, "workspace too small for multi-step Euler");
+        }
+        const float* cur = x;
+        for (int s = 0; s < n_steps; ++s) {
+            const bool last = s == n_steps - 1;
+            float* dst = last ? y : tmp[s & 1];
+            if ((rc = run_rhs(cur, L, bsz, nb, w, cur, 64, h, last && final_relu, dst, last ? ldy : 64, ws, st))) return rc;
+            cur = dst;
+        }
+        return 0;
+    }
+    // explicit Runge-Kutta tableaux (strictly lower triangular a, weights b)
+    int stages;
+    float a[4][4] = {{0}}, b[4] = {0};
+    if (method == STTODE_ODE_MIDPOINT) { stages = 2; a[1][0] = 0.5f; b[1] = 1.f; }
+    else if (method == STTODE_ODE_RK4) { stages = 4; a[1][0] = 0.5f; a[2][1] = 0.5f; a[3][2] = 1.f; b[0] = b[3] = 1.f / 6; b[1] = b[2] = 1.f / 3; }
+    else if (method == STTODE_ODE_RK4_38) { stages = 4; a[1][0] = 1.f / 3; a[2][0] = -1.f / 3; a[2][1] = 1.f; a[3][0] = 1.f; a[3][1] = -1.f; a[3][2] = 1.f;
+                                            b[0] = b[3] = 0.125f; b[1] = b[2] = 0.375f; }
+    else return fail(STTODE_EINVAL, "unknown ODE method %d", method);
+    float* k[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < stages; ++i) if (!(k[i] = ws.take<float>((size_t)rows * 64))) return fail(STTODE_EWORKSPACE, "workspace too small for RK stages");
+    float* stage_in = ws.take<float>((size_t)rows * 64);
+    float* state[2] = {ws.take<float>((size_t)rows * 64), ws.take<float>((size_t)rows * 64)};
+    if (!stage_in || !state[0] || !state[1]) return fail(STTODE_EWORKSPACE, "workspace too small for RK state");
+    const float* cur = x;
+    const int eb = ceil_div(rows * 64, 256);
+    for (int s = 0; s < n_steps; ++s) {
+        for (int i = 0; i < stages; ++i) {
+            const float* in = cur;
+            if (i > 0) {
+                k_lincomb<<<eb, 256, 0, st>>>(cur, 64, k[0], i > 1 ? k[1] : nullptr, i > 2 ? k[2] : nullptr, nullptr, h * a[i][0], h * a[i][1],
+                                              h * a[i][2], 0.f, 0, stage_in, 64, rows);
+                LAUNCH_CHECK("k_lincomb");
+                in = stage_in;
+            }
+            if ((rc = run_rhs(in, L, bsz, nb, w, nullptr, 0, 1.f, 0, k[i], 64, ws, st))) return rc;
+        }
+        const bool last = s == n_steps - 1;
+        float* dst = last ? y : state[s & 1];
+        k_lincomb<<<eb, 256, 0, st>>>(cur, 64, k[0], k[1], stages > 2 ? k[2] : nullptr, stages > 3 ? k[3] : nullptr, h * b[0], h * b[1],
+                                      h * b[2], h * b[3], last && final_relu, dst, last ? ldy : 64, rows);
+        LAUNCH_CHECK("k_lincomb");
+        cur = dst;
+    }
+    return 0;
+}
+
+size_t ode_ws_bytes(int rows, int L, int method) {
+    size_t extra = method == STTODE_ODE_EULER ? 2 : 7;
+    return rhs_ws_bytes(rows, L) + extra * align_up((size_t)rows * 64 * 4);
+}
+
+int check_model(const sttode_model_weights* w, bool need_enc = true, bool need_dec = true) {
+    if (!w) return fail(STTODE_EINVAL, "null model weights");
+    if (w->past_length < 2 || w->future_length < 1) return fail(STTODE_EINVAL, "past_length must be >= 2 and future_length >= 1");
+    if (w->past_length > 200) return fail(STTODE_EINVAL, "past_length exceeds the positional table (200)");
+    const void* const* p = (const void* const*)&w->past;
+    for (size_t i = 0; need_enc && i < sizeof(w->past) / sizeof(void*); ++i) if (!p[i]) return fail(STTODE_EINVAL, "past-encoder weight pointer %zu is null", i);
+    p = (const void* const*)&w->dec[0];
+    for (size_t i = 0; need_dec && i < 2 * sizeof(w->dec[0]) / sizeof(void*); ++i) if (!p[i]) return fail(STTODE_EINVAL, "decoder weight pointer %zu is null", i);
+    return 0;
+}
+
+size_t past_encoder_ws(int rows, int L) { return ode_ws_bytes(rows, L, STTODE_ODE_EULER); }
+size_t decoder_ws(int rows) { return align_up((size_t)rows * ROWPRE_LD * 4); }
+
+int run_past_encoder(const float* traj, int layout, const int* scene_ptr, const int* row_scene, int n_scenes, int rows, int L,
+                     int agents, const sttode_model_weights* w, float* past_feature, float* traj_norm, float* origin, Carver ws,
+                     cudaStream_t st) {
+    int rc;
+    const int T = w->past_length;
+    if (rows <= 0) return fail(STTODE_EINVAL, "rows must be positive");
+    if (scene_ptr) {
+        if (L != 1) return fail(STTODE_EINVAL, "scene_ptr (ETH/SDD semantics) requires L == 1");
+        if (!row_scene || !origin || n_scenes <= 0) return fail(STTODE_EINVAL, "scene_ptr given without row_scene/origin/n_scenes");
+        k_scene_origin<<<ceil_div(n_scenes * 32, 256), 256, 0, st>>>(traj, layout, scene_ptr, n_scenes, T, origin);
+        LAUNCH_CHECK("k_scene_origin");
+    } else {
+        if (L < 1 || agents < 1 || rows % (L * agents) != 0) return fail(STTODE_EINVAL, "rows (%d) must be a multiple of L*agents (%d*%d)", rows, L, agents);
+    }
+    const size_t sm = prologue_smem_bytes(T);
+    if ((rc = set_smem(k_prologue, sm, "k_prologue"))) return rc;
+    k_prologue<<<ceil_div(rows, BM), NTHREADS, sm, st>>>(traj, layout, scene_ptr, row_scene, origin, rows, agents, T, w->past, past_feature, 128, traj_norm);
+    LAUNCH_CHECK("k_prologue");
+    const int nb = scene_ptr ? rows : rows / (L * agents);
+    const int bsz = scene_ptr ? 1 : agents;
+    // ODE block on x0 = past_feature[:, 0:64] (ld 128) -> past_feature[:, 64:128]
+    // k_ode_tail / k_proj read x with ld 64 only through run_rhs: stage x0 contiguously when L > 1
+    if (L == 1) {
+        if ((rc = set_smem(k_ode_tail, ode_tail_smem_bytes(), "k_ode_tail"))) return rc;
+        k_ode_tail<<<ceil_div(rows, BM), NTHREADS, ode_tail_smem_bytes(), st>>>(past_feature, 128, nullptr, 0, past_feature, 128, 12.f, 1,
+                                                                                past_feature + 64, 128, rows, w->past.ode, 0);
+        LAUNCH_CHECK("k_ode_tail");
+        return 0;
+    }
+    float* x0 = ws.take<float>((size_t)rows * 64);
+    if (!x0) return fail(STTODE_EWORKSPACE, "workspace too small for x0");
+    CUDA_TRY(cudaMemcpy2DAsync(x0, 64 * 4, past_feature, 128 * 4, 64 * 4, rows, cudaMemcpyDeviceToDevice, st));
+    return run_ode_block(x0, L, bsz, nb, w->past.ode, 1, 12.f, STTODE_ODE_EULER, 1, past_feature + 64, 128, ws, st);
+}
+
+int run_decoder(const float* past_feature, const float* traj_norm, const float* z, unsigned long long seed, const int* row_scene,
+                const float* origin, int rows, int K, const sttode_model_weights* w, float* pred, float* recon, Carver ws,
+                cudaStream_t st) {
+    int rc;
+    if (K < 1 || K > BM) return fail(STTODE_EINVAL, "sample_k must be in [1, %d]", BM);
+    const int Tp = w->past_length, Tf = w->future_length;
+    float* rowpre = ws.take<float>((size_t)rows * ROWPRE_LD);
+    if (!rowpre) return fail(STTODE_EWORKSPACE, "workspace too small for decoder row precompute");
+    const size_t sm_row = dec_row_smem_bytes(Tp), sm_pair = dec_pair_smem_bytes(Tp, Tf);
+    if ((rc = set_smem(k_dec_row, sm_row, "k_dec_row"))) return rc;
+    if ((rc = set_smem(k_dec_pair, sm_pair, "k_dec_pair"))) return rc;
+    k_dec_row<<<ceil_div(rows, BM), NTHREADS, sm_row, st>>>(past_feature, traj_norm, rows, Tp, w->dec[0], w->dec[1], rowpre);
+    LAUNCH_CHECK("k_dec_row");
+    const int rpt = BM / K;
+    std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+    if (g_prof.on) {
+        std::lock_guard<std::mutex> lock(g_prof.mu);
+        if (!g_prof.pool.empty()) { ev = g_prof.pool.back(); g_prof.pool.pop_back(); }
+        else { CUDA_TRY(cudaEventCreate(&ev.first)); CUDA_TRY(cudaEventCreate(&ev.second)); }
+        CUDA_TRY(cudaEventRecord(ev.first, st));
+    }
+    k_dec_pair<<<ceil_div(rows, rpt), NTHREADS, sm_pair, st>>>(traj_norm, z, seed, rowpre, origin ? row_scene : nullptr, origin, rows, K, rpt, Tp,
+                                                              Tf, w->dec[0], w->dec[1], pred, recon);
+    LAUNCH_CHECK("k_dec_pair");
+    if (ev.first) {
+        std::lock_guard<std::mutex> lock(g_prof.mu);
+        CUDA_TRY(cudaEventRecord(ev.second, st));
+        g_prof.used.push_back(ev);
+    }
+    return 0;
+}
+
+// ---- host staging arena for sttode_forecast_host -----------------------------------------------------
+struct HostArena {
+    std::mutex mu;
+    char *pin_in = nullptr, *pin_out = nullptr, *dev = nullptr;
+    size_t pin_in_sz = 0, pin_out_sz = 0, dev_sz = 0;
+} g_arena;
+
+int grow(char** p, size_t* cur, size_t want, bool pinned) {
+    if (*cur >= want) return 0;
+    if (*p) { if (pinned) cudaFreeHost(*p); else cudaFree(*p); *p = nullptr; *cur = 0; }
+    size_t sz = want + want / 4;
+    cudaError_t e = pinned ? cudaMallocHost((void**)p, sz) : cudaMalloc((void**)p, sz);
+    if (e != cudaSuccess) return fail(STTODE_ECUDA, "arena alloc of %zu B failed: %s", sz, cudaGetErrorString(e));
+    *cur = sz;
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int sttode_version(void) { return STTODE_VERSION; }
+const char* sttode_last_error(void) { return g_err; }
+unsigned long long sttode_launch_count(void) { return g_launches.load(); }
+
+int sttode_profile_enable(int on) {
+    std::lock_guard<std::mutex> lock(g_prof.mu);
+    g_prof.on = on != 0;
+    return 0;
+}
+
+int sttode_profile_read(double* total_ms, unsigned long long* launches) {
+    if (!total_ms || !launches) return fail(STTODE_EINVAL, "null pointer");
+    std::lock_guard<std::mutex> lock(g_prof.mu);
+    double ms = 0;
+    for (auto& e : g_prof.used) {
+        float t = 0;
+        CUDA_TRY(cudaEventSynchronize(e.second));
+        CUDA_TRY(cudaEventElapsedTime(&t, e.first, e.second));
+        ms += t;
+        g_prof.pool.push_back(e);
+    }
+    *total_ms = ms;
+    *launches = g_prof.used.size();
+    g_prof.used.clear();
+    return 0;
+}
+
+int sttode_device_check(void) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    CUDA_TRY(cudaGetDeviceProperties(&p, dev));
+    if (p.major != 10) return fail(STTODE_ECUDA, "libsttode_sm100 needs compute capability 10.x (B200); device %d is %d.%d", dev, p.major, p.minor);
+    return 0;
+}
+
+size_t sttode_mhgsa_workspace_bytes(int L, int S, int bsz) {
+    return 4 * attn_ws_floats(L, S, bsz, false, true) + 4 * attn_ws_floats(L, S, bsz, true, true) + 1024;
+}
+
+int sttode_mhgsa_fwd(const float* query, const float* key, const float* value, const sttode_mhgsa_weights* w, float* out,
+                     float* attn_weights, int L, int S, int bsz, int E, int H, int score_mode, float clamp_eps, float curvature,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if ((rc = check_ptrs_mhgsa(w))) return rc;
+    if (!query || !key || !value || !out) return fail(STTODE_EINVAL, "null tensor pointer");
+    if (E != STTODE_D || H != STTODE_H) return fail(STTODE_EUNSUPPORTED, "only embed_dim=64, num_heads=8 (the STTODE configuration) is implemented, got E=%d H=%d", E, H);
+    if (L < 1 || S < 1 || bsz < 1) return fail(STTODE_EINVAL, "L, S, bsz must be positive");
+    if (score_mode != STTODE_SCORE_OBLIQUE_ACOS && score_mode != STTODE_SCORE_POINCARE_DIST) return fail(STTODE_EINVAL, "unknown score_mode %d", score_mode);
+    if (score_mode == STTODE_SCORE_POINCARE_DIST && !(curvature > 0.f)) return fail(STTODE_EINVAL, "curvature must be > 0");
+    const bool self_attn = (query == key && key == value);
+    if (self_attn && L != S) return fail(STTODE_EINVAL, "self-attention requires L == S");
+    Carver ws(workspace, workspace_bytes);
+    float* o = nullptr;
+    if ((rc = run_attention(query, key, value, self_attn, *w, L, S, bsz, 1, score_mode, clamp_eps, curvature, ws, &o, attn_weights, st))) return rc;
+    // out_proj (hyptransformerlib.py:305): reuse k_proj with a single unscaled, un-normalised block
+    k_proj<<<ceil_div(L * bsz, BM), NTHREADS, proj_smem_bytes(), st>>>(o, 64, L * bsz, w->out_proj_w, w->out_proj_b, 1, out, 64, 0u, 0u, 1.f, 0, 1.f);
+    LAUNCH_CHECK("k_proj(out)");
+    return 0;
+}
+
+int sttode_linear64(const float* x, const float* weight, const float* bias, float* out, int rows, int out_features, void* stream) {
+    int rc;
+    if (!x || !weight || !bias || !out || rows < 1) return fail(STTODE_EINVAL, "linear64: bad argument");
+    if (out_features < 64 || out_features % 64 != 0 || out_features > 64 * 32) return fail(STTODE_EUNSUPPORTED, "linear64: out_features must be a multiple of 64 (<= 2048)");
+    if ((rc = set_smem(k_proj, proj_smem_bytes(), "k_proj"))) return rc;
+    k_proj<<<ceil_div(rows, BM), NTHREADS, proj_smem_bytes(), (cudaStream_t)stream>>>(x, 64, rows, weight, bias, out_features / 64, out, out_features, 0u, 0u, 1.f, 0, 1.f);
+    LAUNCH_CHECK("k_proj(linear64)");
+    return 0;
+}
+
+size_t sttode_ode_block_workspace_bytes(int L, int bsz, int method) { return ode_ws_bytes(L * bsz, L, method) + 1024; }
+
+int sttode_ode_block_fwd(const float* x, const sttode_ode_weights* w, float* y, int ldy, int L, int bsz, int n_steps, float h,
+                         int method, int final_relu, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc;
+    if (!x || !w || !y) return fail(STTODE_EINVAL, "null pointer");
+    if ((rc = check_ptrs_mhgsa(&w->attn))) return rc;
+    if (L < 1 || bsz < 1 || ldy < 64) return fail(STTODE_EINVAL, "bad shape L=%d bsz=%d ldy=%d", L, bsz, ldy);
+    return run_ode_block(x, L, bsz, 1, *w, n_steps, h, method, final_relu, y, ldy, Carver(workspace, workspace_bytes), (cudaStream_t)stream);
+}
+
+int sttode_ode_rhs_fwd(const float* x, const sttode_ode_weights* w, float* f, int L, int bsz, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+    if (!x || !w || !f) return fail(STTODE_EINVAL, "null pointer");
+    if (L < 1 || bsz < 1) return fail(STTODE_EINVAL, "bad shape");
+    return run_rhs(x, L, bsz, 1, *w, nullptr, 0, 1.f, 0, f, 64, Carver(workspace, workspace_bytes), (cudaStream_t)stream);
+}
+
+int sttode_hypattention_fwd(const float* x, const sttode_ode_weights* w, float* out, int L, int bsz, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+    if (!x || !w || !out) return fail(STTODE_EINVAL, "null pointer");
+    if (L < 1 || bsz < 1) return fail(STTODE_EINVAL, "bad shape");
+    return run_rhs(x, L, bsz, 1, *w, nullptr, 0, 1.f, 0, out, 64, Carver(workspace, workspace_bytes), (cudaStream_t)stream, 1);
+}
+
+size_t sttode_past_encoder_workspace_bytes(int rows, int L) { return past_encoder_ws(rows, L) + align_up((size_t)rows * 64 * 4) + 1024; }
+
+int sttode_past_encoder_fwd(const float* traj, int layout, const int* scene_ptr, const int* row_scene, int n_scenes, int rows, int L,
+                            int agents, const sttode_model_weights* w, float* past_feature, float* traj_norm, float* origin,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+    int rc;
+    if ((rc = check_model(w, true, false))) return rc;
+    if (!traj || !past_feature) return fail(STTODE_EINVAL, "null pointer");
+    return run_past_encoder(traj, layout, scene_ptr, row_scene, n_scenes, rows, L, agents, w, past_feature, traj_norm, origin,
+                            Carver(workspace, workspace_bytes), (cudaStream_t)stream);
+}
+
+size_t sttode_decoder_workspace_bytes(int rows, int sample_k) { (void)sample_k; return decoder_ws(rows) + 1024; }
+
+int sttode_decoder_fwd(const float* past_feature, const float* traj_norm, const float* z, unsigned long long seed,
+                       const int* row_scene, const float* origin, int rows, int sample_k, const sttode_model_weights* w,
+                       float* pred, float* recon, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc;
+    if ((rc = check_model(w, false, true))) return rc;
+    if (!past_feature || !traj_norm || !pred) return fail(STTODE_EINVAL, "null pointer");
+    if (origin && !row_scene) return fail(STTODE_EINVAL, "origin given without row_scene");
+    return run_decoder(past_feature, traj_norm, z, seed, row_scene, origin, rows, sample_k, w, pred, recon,
+                       Carver(workspace, workspace_bytes), (cudaStream_t)stream);
+}
+
+size_t sttode_forecast_workspace_bytes(int rows, int L, int sample_k, int past_length) {
+    (void)sample_k;
+    size_t enc = past_encoder_ws(rows, L) + align_up((size_t)rows * 64 * 4), dec = decoder_ws(rows);
+    return align_up((size_t)rows * 128 * 4) + align_up((size_t)rows * past_length * 2 * 4) + align_up((size_t)rows * 2 * 4) + (enc > dec ? enc : dec) + 4096;
+}
+
+int sttode_forecast(const float* traj, int layout, const int* scene_ptr, const int* row_scene, int n_scenes, int rows, int L, int agents,
+                    const float* z, unsigned long long seed, int sample_k, const sttode_model_weights* w, float* pred,
+                    float* past_feature_out, float* traj_norm_out, float* origin_out, void* workspace, size_t workspace_bytes,
+                    void* stream) {
+    int rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = check_model(w))) return rc;
+    if (!traj || !pred) return fail(STTODE_EINVAL, "null pointer");
+    Carver ws(workspace, workspace_bytes);
+    float* pf = past_feature_out ? past_feature_out : ws.take<float>((size_t)rows * 128);
+    float* tn = traj_norm_out ? traj_norm_out : ws.take<float>((size_t)rows * w->past_length * 2);
+    float* org = !scene_ptr ? nullptr : origin_out ? origin_out : ws.take<float>((size_t)n_scenes * 2);
+    if (!pf || !tn || (scene_ptr && !org)) return fail(STTODE_EWORKSPACE, "workspace too small (%zu B given)", workspace_bytes);
+    Carver rest((char*)workspace + ws.off, workspace_bytes - ws.off);
+    if ((rc = run_past_encoder(traj, layout, scene_ptr, row_scene, n_scenes, rows, L, agents, w, pf, tn, org, rest, st))) return rc;
+    return run_decoder(pf, tn, z, seed, row_scene, org, rows, sample_k, w, pred, nullptr, rest, st);
+}
+
+int sttode_forecast_host(const float* traj_host, int layout, const int* scene_ptr_host, int n_scenes, int rows, int L, int agents,
+                         unsigned long long seed, int sample_k, const sttode_model_weights* w, float* pred_host, void* stream) {
+    int rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = check_model(w))) return rc;
+    if (!traj_host || !pred_host || rows <= 0) return fail(STTODE_EINVAL, "null pointer / empty batch");
+    std::lock_guard<std::mutex> lock(g_arena.mu);
+    const int Tp = w->past_length, Tf = w->future_length;
+    const size_t traj_b = (size_t)rows * Tp * 2 * 4, pred_b = (size_t)rows * sample_k * Tf * 2 * 4;
+    const size_t sp_b = scene_ptr_host ? align_up((size_t)(n_scenes + 1) * 4) : 0, rs_b = scene_ptr_host ? align_up((size_t)rows * 4) : 0;
+    const size_t in_b = align_up(traj_b) + sp_b + rs_b;
+    const size_t ws_b = sttode_forecast_workspace_bytes(rows, L, sample_k, Tp);
+    if ((rc = grow(&g_arena.pin_in, &g_arena.pin_in_sz, in_b, true))) return rc;
+    if ((rc = grow(&g_arena.pin_out, &g_arena.pin_out_sz, pred_b, true))) return rc;
+    if ((rc = grow(&g_arena.dev, &g_arena.dev_sz, in_b + align_up(pred_b) + ws_b, false))) return rc;
+    // stage inputs in pinned memory (one H2D), build row->scene map on the host
+    memcpy(g_arena.pin_in, traj_host, traj_b);
+    int *sp_h = nullptr, *rs_h = nullptr;
+    if (scene_ptr_host) {
+        sp_h = (int*)(g_arena.pin_in + align_up(traj_b));
+        rs_h = (int*)(g_arena.pin_in + align_up(traj_b) + sp_b);
+        memcpy(sp_h, scene_ptr_host, (size_t)(n_scenes + 1) * 4);
+        if (sp_h[0] != 0 || sp_h[n_scenes] != rows) return fail(STTODE_EINVAL, "scene_ptr must start at 0 and end at rows");
+        for (int s = 0; s < n_scenes; ++s) {
+            if (sp_h[s + 1] <= sp_h[s]) return fail(STTODE_EINVAL, "scene %d is empty", s);
+            for (int r = sp_h[s]; r < sp_h[s + 1]; ++r) rs_h[r] = s;
+        }
+    }
+    char* d = g_arena.dev;
+    CUDA_TRY(cudaMemcpyAsync(d, g_arena.pin_in, in_b, cudaMemcpyHostToDevice, st));
+    const float* traj_d = (const float*)d;
+    const int* sp_d = scene_ptr_host ? (const int*)(d + align_up(traj_b)) : nullptr;
+    const int* rs_d = scene_ptr_host ? (const int*)(d + align_up(traj_b) + sp_b) : nullptr;
+    float* pred_d = (float*)(d + in_b);
+    void* ws_d = d + in_b + align_up(pred_b);
+    if ((rc = sttode_forecast(traj_d, layout, sp_d, rs_d, n_scenes, rows, L, agents, nullptr, seed, sample_k, w, pred_d, nullptr, nullptr, nullptr, ws_d, ws_b, st))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(g_arena.pin_out, pred_d, pred_b, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    memcpy(pred_host, g_arena.pin_out, pred_b);
+    return 0;
+}
+
+void sttode_release_host_arena(void) {
+    std::lock_guard<std::mutex> lock(g_arena.mu);
+    if (g_arena.pin_in) cudaFreeHost(g_arena.pin_in);
+    if (g_arena.pin_out) cudaFreeHost(g_arena.pin_out);
+    if (g_arena.dev) cudaFree(g_arena.dev);
+    g_arena.pin_in = g_arena.pin_out = g_arena.dev = nullptr;
+    g_arena.pin_in_sz = g_arena.pin_out_sz = g_arena.dev_sz = 0;
+}
+
+int sttode_min_ade_fde(const float* pred, const float* gt, int gt_layout, int rows, int sample_k, int future_length, double* sums,
+                       void* stream) {
+    if (!pred || !gt || !sums || rows <= 0 || sample_k < 1 || future_length < 1) return fail(STTODE_EINVAL, "bad argument");
+    k_min_ade_fde<<<ceil_div(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(pred, gt, gt_layout, rows, sample_k, future_length, sums);
+    LAUNCH_CHECK("k_min_ade_fde");
+    return 0;
+}
+
+// ---- Oblique manifold -------------------------------------------------------------------------------
+int sttode_oblique_proj(const float* x, float* out, int rows, int d, void* stream) {
+    if (!x || !out || rows < 1 || d < 1) return fail(STTODE_EINVAL, "oblique_proj: bad argument");
+    launch_oblique_proj(x, out, rows, d, (cudaStream_t)stream);
+    LAUNCH_CHECK("oblique_proj");
+    return 0;
+}
+int sttode_oblique_dist(const float* p1, const float* p2, float* out, int batch, int n1, int n2, int d, float clamp_eps, void* stream) {
+    if (!p1 || !p2 || !out || batch < 1 || n1 < 1 || n2 < 1 || d < 1) return fail(STTODE_EINVAL, "oblique_dist: bad argument");
+    if (batch > 65535) return fail(STTODE_EUNSUPPORTED, "oblique_dist: batch > 65535");
+    launch_oblique_dist(p1, p2, out, batch, n1, n2, d, (float)(-1.0 + (double)clamp_eps), (float)(1.0 - (double)clamp_eps), (cudaStream_t)stream);
+    LAUNCH_CHECK("oblique_dist");
+    return 0;
+}
+
+// ---- pmath ------------------------------------------------------------------------------------------
+#define PMATH_ROWS(NAME, OP, NEEDY)                                                                               \
+    int NAME(const float* x, PMATH_Y_##NEEDY float* out, int rows, int d, float c, void* stream) {                \
+        if (!x || !out || PMATH_YNULL_##NEEDY rows < 1 || d < 1) return fail(STTODE_EINVAL, #NAME ": bad argument"); \
+        if (!(c > 0.f)) return fail(STTODE_EINVAL, #NAME ": curvature must be > 0");                              \
+        launch_pmath_rows(OP, x, PMATH_YARG_##NEEDY, out, rows, d, c, (cudaStream_t)stream);                      \
+        LAUNCH_CHECK(#NAME);                                                                                      \
+        return 0;                                                                                                 \
+    }
+#define PMATH_Y_0
+#define PMATH_Y_1 const float* y,
+#define PMATH_YNULL_0
+#define PMATH_YNULL_1 !y ||
+#define PMATH_YARG_0 nullptr
+#define PMATH_YARG_1 y
+PMATH_ROWS(sttode_pmath_project, 0, 0)
+PMATH_ROWS(sttode_pmath_lambda_x, 1, 0)
+PMATH_ROWS(sttode_pmath_mobius_add, 2, 1)
+PMATH_ROWS(sttode_pmath_dist, 3, 1)
+PMATH_ROWS(sttode_pmath_dist0, 4, 0)
+PMATH_ROWS(sttode_pmath_expmap0, 5, 0)
+PMATH_ROWS(sttode_pmath_logmap0, 6, 0)
+PMATH_ROWS(sttode_pmath_expmap, 7, 1)
+PMATH_ROWS(sttode_pmath_logmap, 8, 1)
+
+int sttode_pmath_mobius_matvec(const float* m, const float* x, float* out, int rows, int d, int dout, float c, void* stream) {
+    if (!m || !x || !out || rows < 1 || d < 1 || dout < 1) return fail(STTODE_EINVAL, "mobius_matvec: bad argument");
+    if (dout > 1024) return fail(STTODE_EUNSUPPORTED, "mobius_matvec: dout > 1024");
+    if (!(c > 0.f)) return fail(STTODE_EINVAL, "mobius_matvec: curvature must be > 0");
+    launch_pmath_matvec(m, x, out, rows, d, dout, c, (cudaStream_t)stream);
+    LAUNCH_CHECK("mobius_matvec");
+    return 0;
+}
+int sttode_pmath_dist_matrix(const float* x, const float* y, float* out, int b, int n, int d, float c, void* stream) {
+    if (!x || !y || !out || b < 1 || n < 1 || d < 1) return fail(STTODE_EINVAL, "dist_matrix: bad argument");
+    if (!(c > 0.f)) return fail(STTODE_EINVAL, "dist_matrix: curvature must be > 0");
+    launch_pmath_dist_matrix(x, y, out, b, n, d, c, (cudaStream_t)stream);
+    LAUNCH_CHECK("dist_matrix");
+    return 0;
+}
+int sttode_pmath_tanh(const float* x, float* out, size_t n, float clampv, void* stream) {
+    if (!x || !out) return fail(STTODE_EINVAL, "tanh: null pointer");
+    if (n) { launch_pmath_elem(0, x, out, n, clampv, (cudaStream_t)stream); LAUNCH_CHECK("tanh"); }
+    return 0;
+}
+int sttode_pmath_artanh(const float* x, float* out, size_t n, void* stream) {
+    if (!x || !out) return fail(STTODE_EINVAL, "artanh: null pointer");
+    if (n) { launch_pmath_elem(1, x, out, n, 0.f, (cudaStream_t)stream); LAUNCH_CHECK("artanh"); }
+    return 0;
+}
+int sttode_pmath_arsinh(const float* x, float* out, size_t n, void* stream) {
+    if (!x || !out) return fail(STTODE_EINVAL, "arsinh: null pointer");
+    if (n) { launch_pmath_elem(2, x, out, n, 0.f, (cudaStream_t)stream); LAUNCH_CHECK("arsinh"); }
+    return 0;
+}
+
+}  // extern "C"

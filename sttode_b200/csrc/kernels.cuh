@@ -1,0 +1,39 @@
+// Kernel declarations shared between the .cu translation units and the C-ABI layer.
+#pragma once
+#include "../../include/sttode.h"
+#include "common.cuh"
+
+namespace sttode {
+
+// encoder.cu
+__global__ void k_scene_origin(const float* traj, int layout, const int* scene_ptr, int n_scenes, int T, float* origin);
+__global__ void k_prologue(const float* traj, int layout, const int* scene_ptr, const int* row_scene, const float* origin,
+                           int rows, int agents, int T, sttode_encoder_weights w, float* x0, int ldx0, float* traj_norm);
+__global__ void k_proj(const float* X, int ldx, int rows, const float* W, const float* b, int nblk, float* out, int ldo,
+                       unsigned scale_mask, unsigned norm_mask, float scale, int score_mode, float curv);
+__global__ void k_geo_attn(const float* rowop, int ldr, const float* colop, int ldc, const float* vals, int ldv, float* out,
+                           int ldo, float* denom, int Lr, int Lc, int bsz, int score_mode, float lo, float hi, float curv);
+__global__ void k_attn_weights(const float* rowop, int ldr, const float* colop, int ldc, const float* denom, float* wout,
+                               int Lr, int Lc, int bsz, int score_mode, float lo, float hi, float curv);
+__global__ void k_ode_tail(const float* x, int ldx, const float* attn_o, int ldo, const float* base, int ldb, float coef,
+                           int relu, float* out, int ldout, int rows, sttode_ode_weights w, int gate_only);
+__global__ void k_lincomb(const float* base, int ldb, const float* k0, const float* k1, const float* k2, const float* k3,
+                          float c0, float c1, float c2, float c3, int relu, float* out, int ldout, int rows);
+size_t prologue_smem_bytes(int T);
+size_t proj_smem_bytes();
+size_t ode_tail_smem_bytes();
+
+// decoder.cu
+constexpr int ROWPRE_LD = 2048;     // per-row layer-1 partial sums: [P0x | P0y | P1y | P1x], 512 each
+__global__ void k_dec_row(const float* past_feature, const float* traj_norm, int rows, int Tp, sttode_decompose_weights w0,
+                          sttode_decompose_weights w1, float* rowpre);
+__global__ void k_dec_pair(const float* traj_norm, const float* z, unsigned long long seed, const float* rowpre,
+                           const int* row_scene, const float* origin, int rows, int K, int rpt, int Tp, int Tf,
+                           sttode_decompose_weights w0, sttode_decompose_weights w1, float* pred, float* recon);
+size_t dec_row_smem_bytes(int Tp);
+size_t dec_pair_smem_bytes(int Tp, int Tf);
+
+// metrics.cu
+__global__ void k_min_ade_fde(const float* pred, const float* gt, int gt_layout, int rows, int K, int Tf, double* sums);
+
+}  // namespace sttode

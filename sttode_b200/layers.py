@@ -1,0 +1,177 @@
+"""Geodesic transformer layer and tensor-ODE block on B200: drop-ins for the reference's
+`hypertransformer.py` (`Hypattention`, `TransformerEncoderLayer`) and `ode_demo.py`
+(`TransformerEncoder_ode`, `ODEblock_en`, `ODEG_Encoder`).
+
+Same class names, constructor signatures, attribute side effects and state_dict keys
+(`self_attn.temporal_attention_before.*`, `self_attn.temporal_info.*`, `self_attn.temporal_gate.*`,
+`linear1/2.*`, `norm1/2.*`; prefix `odeblock.odefunc.layers.0.`).  One `ODEG_Encoder.forward` is one
+call of `sttode_ode_block_fwd` (csrc/encoder.cu): the torchdiffeq solver loop, the right-hand side and the
+final ReLU all run in the library.  Forward only in round 1.
+"""
+import copy
+import ctypes as C
+
+import torch
+from torch import nn
+
+from . import _lib
+from .mhgsa import Hyp_mhsa, _f32c, _mhgsa_struct
+
+ODE_EULER, ODE_MIDPOINT, ODE_RK4, ODE_RK4_38 = 0, 1, 2, 3
+_METHODS = {"euler": ODE_EULER, "midpoint": ODE_MIDPOINT, "rk4_classic": ODE_RK4, "rk4": ODE_RK4_38}
+
+
+def _ode_struct(layer):
+    """sttode_ode_weights for a TransformerEncoderLayer (or just its Hypattention when `layer` is one)."""
+    s = _lib.OdeWeights()
+    att = layer.self_attn if isinstance(layer, TransformerEncoderLayer) else layer
+    mh = att.temporal_attention_before
+    s.attn = _mhgsa_struct(mh.in_proj_weight, mh.in_proj_bias, mh.out_proj.weight, mh.out_proj.bias)
+    s.info_w, s.info_b = _lib.dptr(att.temporal_info.weight), _lib.dptr(att.temporal_info.bias)
+    s.gate_w, s.gate_b = _lib.dptr(att.temporal_gate.weight), _lib.dptr(att.temporal_gate.bias)
+    if isinstance(layer, TransformerEncoderLayer):
+        if layer.linear1.weight.shape != (1024, 64):
+            raise NotImplementedError("TransformerEncoderLayer on B200: d_model=64, dim_feedforward=1024 only (model/STTODE.py:190-194)")
+        s.lin1_w, s.lin1_b = _lib.dptr(layer.linear1.weight), _lib.dptr(layer.linear1.bias)
+        s.lin2_w, s.lin2_b = _lib.dptr(layer.linear2.weight), _lib.dptr(layer.linear2.bias)
+        s.norm1_g, s.norm1_b = _lib.dptr(layer.norm1.weight), _lib.dptr(layer.norm1.bias)
+        s.norm2_g, s.norm2_b = _lib.dptr(layer.norm2.weight), _lib.dptr(layer.norm2.bias)
+    return s
+
+
+def _check_eval_dropout(p, training, what):
+    if p > 0.0 and training:
+        raise NotImplementedError(f"{what}: dropout > 0 in training mode is not implemented on the B200 path "
+                                  "(the reference builds these layers with dropout = 0, model/STTODE.py:192,251)")
+
+
+class Hypattention(nn.Module):
+    """MHGSA followed by the tanh * sigmoid gate (hypertransformer.py:19-89)."""
+
+    def __init__(self, d_model, nhead, dropout=0., motion_only=True, cross_range=0, num_conv_layer=3):
+        super().__init__()
+        self.model_dim = d_model
+        self.temporal_attention_before = Hyp_mhsa(d_model, nhead, dropout=dropout)
+        self.temporal_info = nn.Linear(d_model, d_model)
+        self.temporal_gate = nn.Linear(d_model, d_model)
+
+    def forward(self, query, key, value, key_padding_mask=None, need_weights=False, attn_mask=None, seq_mask=False):
+        # [T, N, sample_num, D]; the reference ignores every mask argument here (hypertransformer.py:69-79)
+        assert query.dim() == key.dim() == value.dim() == 4
+        assert query.shape[1] == key.shape[1] == value.shape[1] and query.shape[2] == key.shape[2] == value.shape[2]
+        if not (key is query and value is query):
+            raise NotImplementedError("Hypattention on B200: self-attention only (query is key is value), as on the reference path")
+        _check_eval_dropout(self.temporal_attention_before.dropout, self.training, "Hypattention")
+        T, N, sn, D = query.shape
+        x = _f32c(query, "query").reshape(T, N * sn, D)
+        out = torch.empty_like(x)
+        lib = _lib.lib()
+        ws = _lib.workspace(lib.sttode_ode_block_workspace_bytes(T, N * sn, ODE_EULER), x.device)
+        st = _ode_struct(self)
+        _lib.check(lib.sttode_hypattention_fwd(_lib.dptr(x), C.byref(st), _lib.dptr(out), T, N * sn, _lib.dptr(ws), ws.numel(),
+                                               _lib.stream_ptr()))
+        weights = None
+        if need_weights:
+            weights = self.temporal_attention_before(x, x, x, need_weights=True)[1]
+        return out.reshape(T, N, sn, D), weights
+
+
+class TransformerEncoderLayer(nn.Module):
+    """s = LN1(x + Hypattention(x)); LN2(s + W2 relu(W1 s)) (hypertransformer.py:91-153) = the ODE right-hand side."""
+
+    def __init__(self, d_model, nhead, dim_feedforward=2048, dropout=0.1, activation="relu"):
+        super().__init__()
+        if activation != "relu":
+            raise NotImplementedError("TransformerEncoderLayer on B200: relu only (the reference default)")
+        self.self_attn = Hypattention(d_model, nhead, dropout=dropout, motion_only=False, cross_range=2, num_conv_layer=7)
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.dropout = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.dropout1 = nn.Dropout(dropout)
+        self.dropout2 = nn.Dropout(dropout)
+
+    def forward(self, src, src_mask=None, src_key_padding_mask=None):
+        _check_eval_dropout(self.dropout.p, self.training, "TransformerEncoderLayer")
+        shape = src.shape
+        x = _f32c(src, "src").reshape(shape[0], -1, shape[-1])
+        out = torch.empty_like(x)
+        lib = _lib.lib()
+        ws = _lib.workspace(lib.sttode_ode_block_workspace_bytes(x.shape[0], x.shape[1], ODE_EULER), x.device)
+        st = _ode_struct(self)
+        _lib.check(lib.sttode_ode_rhs_fwd(_lib.dptr(x), C.byref(st), _lib.dptr(out), x.shape[0], x.shape[1], _lib.dptr(ws),
+                                          ws.numel(), _lib.stream_ptr()))
+        return out.reshape(shape)
+
+
+class TransformerEncoder_ode(nn.Module):
+    """The ODE function f(t, y): a stack of encoder layers; ignores t and the stored masks (ode_demo.py:25-72)."""
+
+    def __init__(self, encoder_layer, num_layers, norm=None):
+        super().__init__()
+        self.layers = nn.ModuleList([copy.deepcopy(encoder_layer) for _ in range(num_layers)])
+        self.num_layers, self.norm = num_layers, norm
+        self.src = self.mask = self.src_key_padding_mask = None
+        self.num_agent = 1
+
+    def forward(self, t, src):
+        out = src
+        for mod in self.layers:
+            out = mod(out)
+        if self.norm is not None:
+            out = self.norm(out)
+        return out
+
+
+class ODEblock_en(nn.Module):
+    """z = odeint(f, x, t, method)[1] with the solver loop inside the library (ode_demo.py:169-190).
+
+    `n_steps` / `method` generalise the reference's single Euler step over t = [0, time]."""
+
+    def __init__(self, odefunc, t=torch.tensor([0, 1]), method="euler", n_steps=1):
+        super().__init__()
+        self.t, self.odefunc, self.method, self.n_steps = t, odefunc, method, n_steps
+
+    def set_x0(self, tgt):
+        self.odefunc.tgt = tgt.detach()          # the reference clones; nothing reads it (ode_demo.py:175-177)
+
+    def setparrament(self, src, mask, src_key_padding_mask, num_agent=1):
+        self.odefunc.src, self.odefunc.mask = src, (mask,)
+        self.odefunc.src_key_padding_mask, self.odefunc.num_agent = src_key_padding_mask, num_agent
+
+    def solve(self, x, final_relu):
+        if self.odefunc.num_layers != 1 or self.odefunc.norm is not None:
+            raise NotImplementedError("ODEblock_en on B200: one encoder layer, no final norm (model/STTODE.py:193-195)")
+        layer = self.odefunc.layers[0]
+        _check_eval_dropout(layer.dropout.p, layer.training, "ODEblock_en")
+        shape = x.shape
+        xs = _f32c(x, "x").reshape(shape[0], -1, shape[-1])
+        L, bsz = xs.shape[0], xs.shape[1]
+        y = torch.empty_like(xs)
+        span = float(self.t[-1]) - float(self.t[0])
+        lib = _lib.lib()
+        method = _METHODS[self.method]
+        ws = _lib.workspace(lib.sttode_ode_block_workspace_bytes(L, bsz, method), xs.device)
+        st = _ode_struct(layer)
+        _lib.check(lib.sttode_ode_block_fwd(_lib.dptr(xs), C.byref(st), _lib.dptr(y), 64, L, bsz, self.n_steps,
+                                            span / self.n_steps, method, int(final_relu), _lib.dptr(ws), ws.numel(),
+                                            _lib.stream_ptr()))
+        return y.reshape(shape)
+
+    def forward(self, x):
+        return self.solve(x, final_relu=False)
+
+
+class ODEG_Encoder(nn.Module):
+    """relu(ODEblock_en(src)) (ode_demo.py:217-231)."""
+
+    def __init__(self, encoder_layer, nlayer, time, method="euler", n_steps=1):
+        super().__init__()
+        self.odeblock = ODEblock_en(TransformerEncoder_ode(encoder_layer, nlayer), t=torch.tensor([0, time]),
+                                    method=method, n_steps=n_steps)
+
+    def forward(self, src, mask=None, src_key_padding_mask=None, num_agent=1):
+        self.odeblock.set_x0(src)
+        self.odeblock.setparrament(src=src, mask=mask, src_key_padding_mask=src_key_padding_mask, num_agent=num_agent)
+        return self.odeblock.solve(src, final_relu=True)

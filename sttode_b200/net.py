@@ -1,0 +1,368 @@
+"""STTODENet on B200: drop-in for the reference's `model/STTODE.py` model API.
+
+`STTODENet(args, device)` keeps the reference's constructor, parameter names (90 parameters + 2 buffers, so
+reference checkpoints load with `strict=True`), `set_data` / `set_data_nba` / `inference` call sequence
+(test.py:164-199, 495-526) and the attributes callers read (`agent_num`, `scene_orig`, `past_feature`,
+`past_traj`, `cur_location`).  `inference` is one `sttode_forecast` call: scene normalisation, velocity
+features, past encoder (front end + tensor-ODE block with MHGSA), K-sample decoder and the latent draw all
+run inside libsttode_sm100.so.  `forecast_scenes` is the batched form (many ETH/SDD scenes per launch) the
+reference does not have.
+
+Round-1 scope: inference.  `forward()` (the training losses, model/STTODE.py:553-568) needs the backward
+kernels scheduled for round 2 and raises NotImplementedError; FutureEncoder exists for state_dict parity.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+from .layers import ODEG_Encoder, TransformerEncoderLayer, _ode_struct
+from .mhgsa import _f32c
+
+TRAJ_RT2, TRAJ_R2T = 0, 1
+
+
+def initialize_weights(modules):
+    """model/utils.py:11-21 (Linear branch is the only one reached by this model)."""
+    for m in modules:
+        if isinstance(m, nn.Linear):
+            nn.init.normal_(m.weight, 0, 0.01)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+
+
+class MLP(nn.Module):
+    """Linear-ReLU stack, last layer linear (model/utils.py:67-95).  Parameter container: the arithmetic of
+    the decoder MLPs runs inside k_dec_pair."""
+
+    def __init__(self, input_dim, output_dim, hidden_size=(1024, 512), activation="relu", discrim=False, dropout=-1):
+        super().__init__()
+        dims = [input_dim, *hidden_size, output_dim]
+        self.layers = nn.ModuleList(nn.Linear(a, b) for a, b in zip(dims[:-1], dims[1:]))
+
+
+class MLP2(nn.Module):
+    """model/STTODE.py:111-133 (FutureEncoder.out_mlp)."""
+
+    def __init__(self, input_dim, hidden_dims=(128, 128), activation="tanh"):
+        super().__init__()
+        self.out_dim = hidden_dims[-1]
+        self.affine_layers = nn.ModuleList()
+        last = input_dim
+        for nh in hidden_dims:
+            self.affine_layers.append(nn.Linear(last, nh))
+            last = nh
+        initialize_weights(self.affine_layers.modules())
+
+
+class Normal:
+    """Diagonal Gaussian (model/STTODE.py:79-109); used by callers of the sampler stage."""
+
+    def __init__(self, mu=None, logvar=None, params=None):
+        if params is not None:
+            self.mu, self.logvar = torch.chunk(params, chunks=2, dim=-1)
+        else:
+            self.mu, self.logvar = mu, logvar
+        self.sigma = torch.exp(0.5 * self.logvar)
+
+    def rsample(self):
+        return self.mu + torch.randn_like(self.sigma) * self.sigma
+
+    sample = rsample
+
+    def kl(self, p=None):
+        if p is None:
+            return -0.5 * (1 + self.logvar - self.mu.pow(2) - self.logvar.exp())
+        t1 = (self.mu - p.mu) / (p.sigma + 1e-8)
+        t2 = self.sigma / (p.sigma + 1e-8)
+        return 0.5 * (t1 * t1 + t2 * t2) - 0.5 - torch.log(t2)
+
+    def mode(self):
+        return self.mu
+
+
+class PositionalAgentEncoding(nn.Module):
+    """Sinusoid table + Linear(2d -> d) on [x | pe] (model/STTODE.py:137-176)."""
+
+    def __init__(self, d_model, dropout=0.1, max_t_len=200, concat=True):
+        super().__init__()
+        self.dropout = nn.Dropout(p=dropout)
+        self.concat, self.d_model = concat, d_model
+        if concat:
+            self.fc = nn.Linear(2 * d_model, d_model)
+        pe = torch.zeros(max_t_len, d_model)
+        pos = torch.arange(0, max_t_len, dtype=torch.float).unsqueeze(1)
+        div = torch.exp(torch.arange(0, d_model, 2).float() * (-math.log(10000.0) / d_model))
+        pe[:, 0::2] = torch.sin(pos * div)
+        pe[:, 1::2] = torch.cos(pos * div)
+        self.register_buffer("pe", pe)
+
+
+def _encoder_struct(enc):
+    s = _lib.EncoderWeights()
+    s.fc_w, s.fc_b = _lib.dptr(enc.input_fc.weight), _lib.dptr(enc.input_fc.bias)
+    s.pe = _lib.dptr(enc.pos_encoder.pe)
+    s.pefc_w, s.pefc_b = _lib.dptr(enc.pos_encoder.fc.weight), _lib.dptr(enc.pos_encoder.fc.bias)
+    s.fc2_w, s.fc2_b = _lib.dptr(enc.input_fc2.weight), _lib.dptr(enc.input_fc2.bias)
+    s.fc3_w, s.fc3_b = _lib.dptr(enc.input_fc3.weight), _lib.dptr(enc.input_fc3.bias)
+    s.ode = _ode_struct(enc.ODE_Encoder.odeblock.odefunc.layers[0])
+    return s
+
+
+class _EncoderBase(nn.Module):
+    def __init__(self, args, length, in_dim=4):
+        super().__init__()
+        self.args = args
+        self.model_dim = args.hidden_dim
+        if self.model_dim != 64:
+            raise NotImplementedError("B200 path: hidden_dim = 64 only (train.py:38 default)")
+        self.input_fc = nn.Linear(in_dim, self.model_dim)
+        self.input_fc2 = nn.Linear(self.model_dim * length, self.model_dim)
+        self.input_fc3 = nn.Linear(self.model_dim + 3, self.model_dim)
+        self.nhead, self.ff_dim, self.dropout, self.nlayer = 8, 1024, 0., 1
+        self.ODE_Encoder = ODEG_Encoder(TransformerEncoderLayer(self.model_dim, self.nhead, self.ff_dim, self.dropout), self.nlayer, 12)
+        self.pos_encoder = PositionalAgentEncoding(self.model_dim, 0.1, concat=True)
+        self.agent_mask = None
+
+    def get_agent_mask(self, agent_mask):
+        self.agent_mask = agent_mask
+
+
+class PastEncoder(_EncoderBase):
+    """model/STTODE.py:178-236.  forward(inputs [B*N,T_p,4], B, N) -> [B*N,128]."""
+
+    def __init__(self, args, in_dim=4):
+        super().__init__(args, args.past_length, in_dim)
+        self.scale_number = len(args.hyper_scales)
+
+    def forward(self, inputs, batch_size, agent_num):
+        # `inputs` = [positions | velocities]; the library recomputes the velocities from the positions exactly
+        # as STTODENet.inference does (model/STTODE.py:582-596), so only columns 0:2 are read.
+        if self.training:
+            raise NotImplementedError("PastEncoder on B200: eval mode only in round 1 (PE dropout 0.1 is live in training, model/STTODE.py:197)")
+        traj = _f32c(inputs[..., :2], "inputs")
+        rows, T = traj.shape[0], traj.shape[1]
+        mw = _lib.ModelWeights()
+        mw.past_length, mw.future_length = T, 1
+        mw.past = _encoder_struct(self)
+        out = torch.empty(rows, 128, device=traj.device, dtype=torch.float32)
+        lib = _lib.lib()
+        ws = _lib.workspace(lib.sttode_past_encoder_workspace_bytes(rows, batch_size), traj.device)
+        _lib.check(lib.sttode_past_encoder_fwd(_lib.dptr(traj), TRAJ_RT2, None, None, 0, rows, batch_size, agent_num, C.byref(mw),
+                                               _lib.dptr(out), None, None, _lib.dptr(ws), ws.numel(), _lib.stream_ptr()))
+        return out
+
+
+class FutureEncoder(_EncoderBase):
+    """Posterior encoder (model/STTODE.py:238-300): training only.  Parameters are kept for checkpoint parity."""
+
+    def __init__(self, args, in_dim=4):
+        super().__init__(args, args.future_length, in_dim)
+        scale_num = 2 + len(args.hyper_scales)
+        self.out_mlp = MLP2(scale_num * self.model_dim, [128], "relu")
+        self.qz_layer = nn.Linear(self.out_mlp.out_dim, 2 * args.zdim)
+        initialize_weights(self.qz_layer.modules())
+
+    def forward(self, inputs, batch_size, agent_num, past_feature):
+        raise NotImplementedError("FutureEncoder.forward is on the training path (model/STTODE.py:498-525); round 2")
+
+
+class DecomposeBlock(nn.Module):
+    """Conv1d(2->32,k3)+GRU(32->96)+two MLPs (model/STTODE.py:16-77).  Parameter container."""
+
+    def __init__(self, past_len, future_len, input_dim):
+        super().__init__()
+        self.past_len, self.future_len = past_len, future_len
+        self.conv_past = nn.Conv1d(2, 32, 3, stride=1, padding=1)
+        self.encoder_past = nn.GRU(32, 96, 1, batch_first=True)
+        self.decoder_y = MLP(96 + input_dim, future_len * 2, hidden_size=(512, 256))
+        self.decoder_x = MLP(96 + input_dim, past_len * 2, hidden_size=(512, 256))
+        nn.init.kaiming_normal_(self.conv_past.weight)
+        nn.init.kaiming_normal_(self.encoder_past.weight_ih_l0)
+        nn.init.kaiming_normal_(self.encoder_past.weight_hh_l0)
+        nn.init.zeros_(self.conv_past.bias)
+        nn.init.zeros_(self.encoder_past.bias_ih_l0)
+        nn.init.zeros_(self.encoder_past.bias_hh_l0)
+
+
+def _mlp3_struct(mlp):
+    s = _lib.Mlp3Weights()
+    for i in range(3):
+        setattr(s, f"w{i}", _lib.dptr(mlp.layers[i].weight))
+        setattr(s, f"b{i}", _lib.dptr(mlp.layers[i].bias))
+    return s
+
+
+def _decompose_struct(blk):
+    s = _lib.DecomposeWeights()
+    s.conv_w, s.conv_b = _lib.dptr(blk.conv_past.weight), _lib.dptr(blk.conv_past.bias)
+    g = blk.encoder_past
+    s.gru_w_ih, s.gru_w_hh = _lib.dptr(g.weight_ih_l0), _lib.dptr(g.weight_hh_l0)
+    s.gru_b_ih, s.gru_b_hh = _lib.dptr(g.bias_ih_l0), _lib.dptr(g.bias_hh_l0)
+    s.dec_y, s.dec_x = _mlp3_struct(blk.decoder_y), _mlp3_struct(blk.decoder_x)
+    return s
+
+
+class Decoder(nn.Module):
+    """K-sample residual decoder (model/STTODE.py:302-347)."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        self.model_dim = args.hidden_dim
+        self.decode_way = "RES"
+        self.num_decompose = args.num_decompose
+        if self.num_decompose != 2:
+            raise NotImplementedError("B200 path: num_decompose = 2 only (train.py:40 default)")
+        input_dim = 2 * self.model_dim + args.zdim
+        if args.zdim != 32:
+            raise NotImplementedError("B200 path: zdim = 32 only (train.py:37 default)")
+        self.past_length, self.future_length = args.past_length, args.future_length
+        self.decompose = nn.ModuleList(DecomposeBlock(args.past_length, args.future_length, input_dim) for _ in range(2))
+
+    def forward(self, past_feature, z, batch_size_curr, agent_num_perscene, past_traj, cur_location, sample_num, mode="train"):
+        """Reference signature: past_feature / z are [rows*sample_num, .] (already repeated per sample).
+        Returns (out_seq, recover_pre_seq).  Every (agent, sample) pair is treated as its own row (K = 1 inside
+        the library) so arbitrary per-pair features are honoured; STTODENet.inference uses the de-duplicated
+        path instead."""
+        pf = _f32c(past_feature, "past_feature")
+        zz = _f32c(z, "z").reshape(-1, 32)
+        pairs = pf.shape[0]
+        traj = _f32c(past_traj, "past_traj").repeat_interleave(sample_num, dim=0)
+        if not torch.equal(cur_location.reshape(-1, 2), past_traj[:, -1].reshape(-1, 2)):
+            raise NotImplementedError("Decoder on B200: cur_location must be past_traj[:, -1] (as at every reference call site)")
+        mw = _lib.ModelWeights()
+        mw.past_length, mw.future_length = self.past_length, self.future_length
+        mw.dec[0], mw.dec[1] = _decompose_struct(self.decompose[0]), _decompose_struct(self.decompose[1])
+        pred = torch.empty(pairs, 1, self.future_length, 2, device=pf.device, dtype=torch.float32)
+        recon = torch.empty(pairs, self.past_length, 2, device=pf.device, dtype=torch.float32)
+        lib = _lib.lib()
+        ws = _lib.workspace(lib.sttode_decoder_workspace_bytes(pairs, 1), pf.device)
+        _lib.check(lib.sttode_decoder_fwd(_lib.dptr(pf), _lib.dptr(traj), _lib.dptr(zz), 0, None, None, pairs, 1, C.byref(mw),
+                                          _lib.dptr(pred), _lib.dptr(recon), _lib.dptr(ws), ws.numel(), _lib.stream_ptr()))
+        out = pred.view(pairs, self.future_length, 2)
+        if mode == "inference":
+            out = out.view(-1, sample_num, self.future_length, 2)
+        return out, recon
+
+
+class STTODENet(nn.Module):
+    """model/STTODE.py:349-623."""
+
+    def __init__(self, args, device):
+        super().__init__()
+        self.device, self.args = device, args
+        self.max_train_agent = args.max_train_agent
+        self.rand_rot_scene, self.discrete_rot = args.rand_rot_scene, args.discrete_rot
+        scale_num = 2 + len(args.hyper_scales)
+        self.past_encoder = PastEncoder(args)
+        self.pz_layer = nn.Linear(scale_num * args.hidden_dim, 2 * args.zdim)
+        if args.learn_prior:
+            raise NotImplementedError("learn_prior=True crashes in the reference too (pz_layer expects 256 features, gets 128; model/STTODE.py:361,513)")
+        self.future_encoder = FutureEncoder(args)
+        self.decoder = Decoder(args)
+        self.param_annealers = nn.ModuleList()
+        self.z_override = None          # test hook: inject the latent instead of drawing it
+        self._struct_cache = None
+
+    def set_device(self, device):
+        self.device = device
+        self.to(device)
+
+    # ---- weights ---------------------------------------------------------------------------------
+    def _weights(self):
+        mw = _lib.ModelWeights()
+        mw.past_length, mw.future_length = self.args.past_length, self.args.future_length
+        mw.past = _encoder_struct(self.past_encoder)
+        mw.dec[0], mw.dec[1] = _decompose_struct(self.decoder.decompose[0]), _decompose_struct(self.decoder.decompose[1])
+        return mw
+
+    # ---- data staging (reference call sequence) ---------------------------------------------------
+    def set_data(self, batch, pre_motion, fut_motion, pre_motion_mask, fut_motion_mask):
+        """ETH/UCY/SDD: pre_motion [N,2,T_p] as the loaders yield it (model/STTODE.py:397-461), eval mode."""
+        if self.training:
+            raise NotImplementedError("set_data in training mode (random rotation / agent subsampling) is on the training path; round 2")
+        self.batch_size = 1
+        self._obs = _f32c(pre_motion.to(self.device), "pre_motion")
+        self.agent_num = self._obs.shape[0]
+        self.pre_motion_mask, self.fut_motion_mask = pre_motion_mask, fut_motion_mask
+        self.fut_motion_orig = fut_motion.transpose(1, 2) if fut_motion is not None else None
+        self._mode = "scene"
+
+    def set_data_nba(self, data):
+        """NBA: data['past_traj'] [B,N,T_p,2] (model/STTODE.py:463-486)."""
+        self.data = data
+        self.batch_size, self.agent_num = data["past_traj"].shape[0], data["past_traj"].shape[1]
+        self._mode = "nba"
+
+    def _seed(self):
+        return int(torch.randint(0, 2 ** 62, (1,)).item())      # follows torch.manual_seed like the reference's randn_like
+
+    def _forecast(self, traj, layout, scene_ptr, row_scene, n_scenes, rows, L, agents, K):
+        lib = _lib.lib()
+        Tp, Tf = self.args.past_length, self.args.future_length
+        dev = traj.device
+        pred = torch.empty(rows, K, Tf, 2, device=dev, dtype=torch.float32)
+        pf = torch.empty(rows, 128, device=dev, dtype=torch.float32)
+        tn = torch.empty(rows, Tp, 2, device=dev, dtype=torch.float32)
+        org = torch.empty(max(n_scenes, 1), 2, device=dev, dtype=torch.float32)
+        ws = _lib.workspace(lib.sttode_forecast_workspace_bytes(rows, L, K, Tp), dev)
+        z = self.z_override
+        if z is not None:
+            z = _f32c(z.to(dev), "z").reshape(-1, 32)
+            if z.shape[0] != rows * K:
+                raise _lib.SttodeError(f"z_override has {z.shape[0]} rows, expected rows*K = {rows * K}")
+        mw = self._weights()
+        _lib.check(lib.sttode_forecast(_lib.dptr(traj), layout, _lib.dptr(scene_ptr), _lib.dptr(row_scene), n_scenes, rows, L, agents,
+                                       _lib.dptr(z), self._seed() if z is None else 0, K, C.byref(mw), _lib.dptr(pred), _lib.dptr(pf),
+                                       _lib.dptr(tn), _lib.dptr(org), _lib.dptr(ws), ws.numel(), _lib.stream_ptr()))
+        self.past_feature, self.past_traj, self._origin = pf, tn, org
+        return pred
+
+    @torch.no_grad()
+    def inference(self, data=None):
+        """-> [K, B*N, T_f, 2] like the reference (model/STTODE.py:574-623)."""
+        K = self.args.sample_k
+        Tp = self.args.past_length
+        if self.args.dataset == "nba":
+            src = data if data is not None else self.data
+            past = _f32c(src["past_traj"].to(self.device), "past_traj")
+            B, N = past.shape[0], past.shape[1]
+            rows = B * N
+            pred = self._forecast(past.view(rows, Tp, 2), TRAJ_RT2, None, None, 0, rows, B, N, K)
+            self.scene_orig = self.past_traj                               # model/STTODE.py:473
+        else:
+            obs = self._obs
+            n = obs.shape[0]
+            sp = torch.tensor([0, n], dtype=torch.int32, device=obs.device)
+            rs = torch.zeros(n, dtype=torch.int32, device=obs.device)
+            pred = self._forecast(obs, TRAJ_R2T, sp, rs, 1, n, 1, n, K)
+            self.scene_orig = self._origin[0]
+        self.cur_location = self.past_traj[:, [-1]]
+        return pred.permute(1, 0, 2, 3)
+
+    @torch.no_grad()
+    def forecast_scenes(self, obs_traj, scene_ptr, layout=TRAJ_R2T, sample_k=None):
+        """Batched ETH/UCY/SDD inference: many scenes per launch (no reference equivalent; each scene is
+        processed exactly as one `set_data` + `inference` call).  obs_traj [sum N_i, 2, T_p] (or [.., T_p, 2]
+        with layout=TRAJ_RT2), scene_ptr int32 [n_scenes+1] CSR offsets.  -> pred [sum N_i, K, T_f, 2]."""
+        K = self.args.sample_k if sample_k is None else sample_k
+        obs = _f32c(obs_traj.to(self.device), "obs_traj")
+        sp = scene_ptr.to(device=obs.device, dtype=torch.int32).contiguous()
+        n_scenes, rows = sp.numel() - 1, obs.shape[0]
+        counts = (sp[1:] - sp[:-1]).long()
+        rs = torch.repeat_interleave(torch.arange(n_scenes, device=obs.device, dtype=torch.int32), counts).contiguous()
+        if rs.numel() != rows:
+            raise _lib.SttodeError("scene_ptr does not cover obs_traj")
+        return self._forecast(obs, layout, sp, rs, n_scenes, rows, 1, 1, K)
+
+    # ---- training path: round 2 ---------------------------------------------------------------------
+    def forward(self):
+        raise NotImplementedError("STTODENet.forward (training losses, model/STTODE.py:553-568) needs the backward kernels: round 2")
+
+    def step_annealer(self):
+        for anl in self.param_annealers:
+            anl.step()

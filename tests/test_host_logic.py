@@ -1,0 +1,120 @@
+"""CPU-side checks: the C-ABI library loads and exports everything include/sttode.h declares, the Python
+mirror has the reference's state_dict layout and option behaviour, and nothing silently falls back."""
+import os
+import re
+
+import pytest
+import torch
+
+import sttode_b200._lib as L
+from oracle import sttode_oracle as O
+from oracle import ref_shim
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "sttode.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sttode_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = L.load()
+    names = declared_symbols()
+    assert len(names) >= 35
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/sttode.h but not exported"
+        assert n in L.SIGNATURES, f"{n} has no ctypes signature in sttode_b200/_lib.py"
+    assert set(L.SIGNATURES) == set(names)
+    assert lib.sttode_version() == 100
+
+
+def test_struct_sizes_match_header():
+    import ctypes as C
+    assert C.sizeof(L.MhgsaWeights) == 4 * 8
+    assert C.sizeof(L.OdeWeights) == 16 * 8
+    assert C.sizeof(L.EncoderWeights) == (9 + 16) * 8
+    assert C.sizeof(L.DecomposeWeights) == (6 + 12) * 8
+    assert C.sizeof(L.ModelWeights) == 8 + (25 + 36) * 8
+
+
+def make_args(dataset="eth", tp=8, tf=12):
+    return ref_shim.make_args(dataset, tp, tf)
+
+
+@pytest.mark.parametrize("tp,tf", [(8, 12), (5, 10), (10, 20)])
+def test_state_dict_layout_matches_reference_spec(tp, tf):
+    from sttode_b200.net import STTODENet
+    m = STTODENet(make_args("nba", tp, tf), torch.device("cpu"))
+    sd = m.state_dict()
+    spec = O.state_dict_spec(tp, tf)
+    assert list(sd.keys()) == [k for k, _, _ in spec]
+    for k, shape, _ in spec:
+        assert tuple(sd[k].shape) == tuple(shape), k
+    m.load_state_dict(O.make_state_dict(3, tp, tf), strict=True)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present (GPU box)")
+def test_seeded_init_equals_reference():
+    """Same constructor order and init calls => torch.manual_seed(s) gives the reference's initial weights."""
+    from sttode_b200.net import STTODENet
+    ref = ref_shim.install()
+    torch.manual_seed(1)
+    a = ref.sttode.STTODENet(make_args(), torch.device("cpu")).state_dict()
+    torch.manual_seed(1)
+    b = STTODENet(make_args(), torch.device("cpu")).state_dict()
+    assert list(a.keys()) == list(b.keys())
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_no_cpu_fallback():
+    from sttode_b200.mhgsa import Hyp_mhsa
+    from sttode_b200 import pmath
+    m = Hyp_mhsa(64, 8).eval()
+    x = torch.randn(3, 2, 64)
+    with pytest.raises(L.SttodeError):
+        m(x, x, x)
+    with pytest.raises(L.SttodeError):
+        pmath.project(torch.randn(4, 8))
+
+
+def test_unsupported_options_raise():
+    from sttode_b200.mhgsa import Hyp_mhsa, hyp_mhsa
+    with pytest.raises(NotImplementedError):
+        Hyp_mhsa(64, 8, add_bias_kv=True)
+    with pytest.raises(NotImplementedError):
+        Hyp_mhsa(64, 8, kdim=32)
+    m = Hyp_mhsa(64, 8)
+    x = torch.randn(3, 2, 64)
+    with pytest.raises(NotImplementedError):
+        m(x, x, x, attn_mask=torch.zeros(3, 3))
+    with pytest.raises(NotImplementedError):
+        m(x, x, x, key_padding_mask=torch.zeros(2, 3, dtype=torch.bool))
+    from sttode_b200.net import STTODENet
+    a = make_args()
+    a.learn_prior = True
+    with pytest.raises(NotImplementedError):
+        STTODENet(a, torch.device("cpu"))
+    with pytest.raises(NotImplementedError):
+        STTODENet(make_args(), torch.device("cpu")).forward()
+
+
+def test_compat_registers_reference_module_names():
+    import subprocess, sys
+    code = ("import sys; sys.path.insert(0, %r); import sttode_b200.compat as c; c.install();"
+            "from model.STTODE import STTODENet; from hyptransformerlib import Hyp_mhsa; from ode_demo import ODEG_Encoder;"
+            "from core.manifolds import Oblique; import hyptorch.pmath as p; print(STTODENet.__module__, p.__name__)") % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "sttode_b200.net" in out.stdout
+
+
+def test_synth_is_deterministic():
+    from sttode_b200 import synth
+    a, _ = synth.eth_scene(3, 7)
+    b, _ = synth.eth_scene(3, 7)
+    assert torch.equal(a, b) and a.shape == (7, 2, 8)
+    d = synth.nba_batch(1, 4)
+    assert d["past_traj"].shape == (4, 11, 10, 2) and d["future_traj"].shape == (4, 11, 20, 2)
