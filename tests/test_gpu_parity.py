@@ -106,7 +106,8 @@ def test_mhgsa_poincare_score_mode(eth, dev):
     m, sd = eth
     from sttode_b200.mhgsa import hyp_mhsa, SCORE_POINCARE_DIST
     L, bsz, c = 9, 3, 0.7
-    x = torch.randn(L, bsz, 64, generator=torch.Generator().manual_seed(8))
+    # modest activations keep expmap0(q), expmap0(k) inside the ball, where the distance is well conditioned
+    x = torch.randn(L, bsz, 64, generator=torch.Generator().manual_seed(8)) * 0.3
     W, b, Wo, bo = (sd[ATT + k] for k in ("in_proj_weight", "in_proj_bias", "out_proj.weight", "out_proj.bias"))
     # oracle: same pipeline with the score replaced by -dist_matrix(project(expmap0(k)), project(expmap0(q)))
     qkv = O.linear(x, W, b); q, k, v = qkv.chunk(3, -1); q = q * 8 ** -0.5
@@ -336,7 +337,17 @@ def test_pmath_vs_reference_golden(golden, dev, c):
     for k, v in got.items():
         ref = g[f"{k}_{t}"]
         assert tuple(v.shape) == ref.shape, k
-        np.testing.assert_allclose(v.cpu().numpy(), ref, rtol=2e-4, atol=2e-6, err_msg=k, equal_nan=True)
+        got_np = v.cpu().numpy()
+        if k in ("dist", "dist0", "dist_matrix"):
+            # d = 2/sqrt(c) artanh(u): near the ball boundary d'(u) = 1/(1-u^2) ~ 5e4, so one fp32 ulp of u moves d by
+            # ~3e-3 (the reference's own fp32 noise).  Compare the well-conditioned u = tanh(sqrt(c) d / 2) everywhere
+            # and d itself away from the boundary.
+            u_got, u_ref = np.tanh(np.sqrt(c) * got_np / 2), np.tanh(np.sqrt(c) * ref / 2)
+            np.testing.assert_allclose(u_got, u_ref, rtol=0, atol=2e-6, err_msg=k)
+            inner = u_ref < 0.99
+            np.testing.assert_allclose(got_np[inner], ref[inner], rtol=2e-4, atol=2e-6, err_msg=k)
+        else:
+            np.testing.assert_allclose(got_np, ref, rtol=2e-4, atol=2e-6, err_msg=k, equal_nan=True)
 
 
 def test_pmath_scalar_fns_and_large(golden, dev):
