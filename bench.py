@@ -164,9 +164,8 @@ def run_reference(args):
 def run_ours(args):
     import torch.distributed as dist
     import sttode_b200._lib as L
-    from oracle.ref_shim import make_args
     from sttode_b200.net import STTODENet, TRAJ_R2T
-    from oracle import sttode_oracle as O           # weights generator + cpu_baseline leg only
+    from sttode_b200.synth import make_args, make_state_dict
 
     rank, local_rank, world = dist_env()
     if world > 1:
@@ -176,7 +175,7 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     lib = L.lib()
 
-    sd = O.make_state_dict(WEIGHT_SEED, TP, TF)
+    sd = make_state_dict(WEIGHT_SEED, TP, TF)
     model = STTODENet(make_args("eth", TP, TF), dev)
     model.load_state_dict(sd, strict=True)
     model.set_device(dev)

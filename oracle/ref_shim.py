@@ -82,10 +82,4 @@ def install():
                                  metrics=metrics)
 
 
-def make_args(dataset="eth", past_length=8, future_length=12, sample_k=20):
-    """The Namespace `STTODENet(args, device)` reads (train.py:21-52 defaults)."""
-    import argparse
-    return argparse.Namespace(hidden_dim=64, zdim=32, hyper_scales=[5, 11], past_length=past_length,
-                              future_length=future_length, num_decompose=2, learn_prior=False,
-                              ztype="gaussian", sample_k=sample_k, min_clip=2.0, dataset=dataset,
-                              max_train_agent=100, rand_rot_scene=True, discrete_rot=False, traj_scale=1)
+from sttode_b200.synth import make_args          # noqa: E402,F401  (the args Namespace STTODENet reads)
