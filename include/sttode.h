@@ -108,6 +108,10 @@ unsigned long long sttode_launch_count(void);
 int sttode_profile_enable(int on);
 int sttode_profile_read(double *total_ms, unsigned long long *launches);
 
+/* tcgen05 building-block check: c[128,n] = a[128,k] . b[n,k]^T on the tensor cores, passes = 1 (fp16 inputs) or
+ * 3 (fp16 hi/lo split, fp32-accurate).  status (device int) is set to 1 if the MMA never completed. */
+int sttode_umma_selftest(const float *a, const float *b, float *c, int n, int k, int passes, int swap_lbo_sbo, int *status, void *stream);
+
 /* ---- MHGSA: replaces Hyp_mhsa.forward -> hyp_mhsa (hyptransformerlib.py:403-454 -> :29-311) ------
  * query [L,bsz,E], key/value [S,bsz,E] (key==value==query pointer for self-attention), out [L,bsz,E],
  * attn_weights (nullable) [bsz,L,S] = head-averaged softmax (need_weights=True, :306-309).

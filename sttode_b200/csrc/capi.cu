@@ -13,6 +13,7 @@ void launch_pmath_rows(int op, const float* x, const float* y, float* out, int r
 void launch_pmath_matvec(const float* m, const float* x, float* out, int rows, int d, int dout, float c, cudaStream_t st);
 void launch_pmath_dist_matrix(const float* x, const float* y, float* out, int b, int n, int d, float c, cudaStream_t st);
 void launch_pmath_elem(int op, const float* x, float* out, size_t n, float clampv, cudaStream_t st);
+int launch_umma_selftest(const float* A, const float* B, float* C, int N, int K, int passes, int swap, int* status, cudaStream_t st);
 void launch_oblique_proj(const float* x, float* out, int rows, int d, cudaStream_t st);
 void launch_oblique_dist(const float* p1, const float* p2, float* out, int batch, int n1, int n2, int d, float lo, float hi, cudaStream_t st);
 }
@@ -348,6 +349,15 @@ int sttode_profile_read(double* total_ms, unsigned long long* launches) {
     *total_ms = ms;
     *launches = g_prof.used.size();
     g_prof.used.clear();
+    return 0;
+}
+
+int sttode_umma_selftest(const float* a, const float* b, float* c, int n, int k, int passes, int swap_lbo_sbo, int* status, void* stream) {
+    if (!a || !b || !c || !status) return fail(STTODE_EINVAL, "null pointer");
+    if (n < 16 || n > 256 || n % 16 || k < 16 || k > 128 || k % 16 || (passes != 1 && passes != 3)) return fail(STTODE_EINVAL, "selftest: N in [16,256] %%16, K in [16,128] %%16, passes 1|3");
+    int e = launch_umma_selftest(a, b, c, n, k, passes, swap_lbo_sbo, status, (cudaStream_t)stream);
+    g_launches.fetch_add(1);
+    if (e) return fail(STTODE_ECUDA, "selftest launch: %s", cudaGetErrorString((cudaError_t)e));
     return 0;
 }
 
