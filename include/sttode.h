@@ -92,6 +92,8 @@ typedef struct sttode_model_weights {
     int past_length, future_length;             /* args.past_length / future_length                 */
     sttode_encoder_weights past;                /* past_encoder.*                                   */
     sttode_decompose_weights dec[2];            /* decoder.decompose.{0,1}.*  (num_decompose = 2)   */
+    const void *dec_packed;                     /* optional: buffer filled by sttode_decoder_pack -> tensor-core decoder;
+                                                   NULL -> FP32-FFMA decoder kernels                */
 } sttode_model_weights;
 
 /* ---- diagnostics ------------------------------------------------------------------------------- */
@@ -169,6 +171,14 @@ int sttode_decoder_fwd(const float *past_feature, const float *traj_norm, const 
                        const int *row_scene, const float *origin, int rows, int sample_k,
                        const sttode_model_weights *w, float *pred, float *recon, void *workspace,
                        size_t workspace_bytes, void *stream);
+
+/* Tensor-core decoder: split the decoder weights once per weight version into the fp16 hi/lo operand images the
+ * tcgen05 kernel streams (caller-owned buffer of sttode_decoder_pack_bytes).  The last 256 bytes are a status word
+ * (int32, 0 = ok) that the kernel sets if an MMA/copy barrier ever times out; read it with sttode_decoder_pack_status
+ * after synchronising. */
+size_t sttode_decoder_pack_bytes(int past_length, int future_length);
+int sttode_decoder_pack(const sttode_model_weights *w, void *packed, size_t packed_bytes, void *stream);
+int sttode_decoder_pack_status(const void *packed, int past_length, int future_length, int *status_host);
 
 /* ---- STTODENet.inference (model/STTODE.py:574-623) incl. set_data / set_data_nba preprocessing
  * (:397-486): past encoder + K-sample decoder in one call, device buffers. */

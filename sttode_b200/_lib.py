@@ -36,7 +36,8 @@ class DecomposeWeights(C.Structure):
 
 
 class ModelWeights(C.Structure):
-    _fields_ = [("past_length", C.c_int), ("future_length", C.c_int), ("past", EncoderWeights), ("dec", DecomposeWeights * 2)]
+    _fields_ = [("past_length", C.c_int), ("future_length", C.c_int), ("past", EncoderWeights), ("dec", DecomposeWeights * 2),
+                ("dec_packed", C.c_void_p)]
 
 
 # every symbol include/sttode.h declares: name -> (restype, argtypes)
@@ -62,6 +63,9 @@ SIGNATURES = {
     "sttode_past_encoder_fwd": (_I, [_V, _I, _V, _V, _I, _I, _I, _I, C.POINTER(ModelWeights), _V, _V, _V, _V, _Z, _V]),
     "sttode_decoder_workspace_bytes": (_Z, [_I, _I]),
     "sttode_decoder_fwd": (_I, [_V, _V, _V, _U64, _V, _V, _I, _I, C.POINTER(ModelWeights), _V, _V, _V, _Z, _V]),
+    "sttode_decoder_pack_bytes": (_Z, [_I, _I]),
+    "sttode_decoder_pack": (_I, [C.POINTER(ModelWeights), _V, _Z, _V]),
+    "sttode_decoder_pack_status": (_I, [_V, _I, _I, C.POINTER(C.c_int)]),
     "sttode_forecast_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "sttode_forecast": (_I, [_V, _I, _V, _V, _I, _I, _I, _I, _V, _U64, _I, C.POINTER(ModelWeights), _V, _V, _V, _V, _V, _Z, _V]),
     "sttode_forecast_host": (_I, [_V, _I, _V, _I, _I, _I, _I, _U64, _I, C.POINTER(ModelWeights), _V, _V]),

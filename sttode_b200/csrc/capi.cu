@@ -287,6 +287,8 @@ int run_decoder(const float* past_feature, const float* traj_norm, const float* 
     k_dec_row<<<ceil_div(rows, BM), NTHREADS, sm_row, st>>>(past_feature, traj_norm, rows, Tp, w->dec[0], w->dec[1], rowpre);
     LAUNCH_CHECK("k_dec_row");
     const int rpt = BM / K;
+    const size_t sm_tc = dec_pair_tc_smem_bytes(Tp, Tf);
+    if (w->dec_packed && (rc = set_smem(k_dec_pair_tc, sm_tc, "k_dec_pair_tc"))) return rc;
     std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
     if (g_prof.on) {
         std::lock_guard<std::mutex> lock(g_prof.mu);
@@ -294,9 +296,17 @@ int run_decoder(const float* past_feature, const float* traj_norm, const float* 
         else { CUDA_TRY(cudaEventCreate(&ev.first)); CUDA_TRY(cudaEventCreate(&ev.second)); }
         CUDA_TRY(cudaEventRecord(ev.first, st));
     }
-    k_dec_pair<<<ceil_div(rows, rpt), NTHREADS, sm_pair, st>>>(traj_norm, z, seed, rowpre, origin ? row_scene : nullptr, origin, rows, K, rpt, Tp,
-                                                              Tf, w->dec[0], w->dec[1], pred, recon);
-    LAUNCH_CHECK("k_dec_pair");
+    if (w->dec_packed) {
+        const DecPackLayout lay = dec_pack_layout(Tp, Tf);
+        const unsigned char* pk = (const unsigned char*)w->dec_packed;
+        k_dec_pair_tc<<<ceil_div(rows, rpt), NTHREADS, sm_tc, st>>>(traj_norm, z, seed, rowpre, origin ? row_scene : nullptr, origin, rows, K, rpt,
+                                                                    Tp, Tf, w->dec[0], w->dec[1], pk, lay, pred, recon, (int*)(pk + lay.total));
+        LAUNCH_CHECK("k_dec_pair_tc");
+    } else {
+        k_dec_pair<<<ceil_div(rows, rpt), NTHREADS, sm_pair, st>>>(traj_norm, z, seed, rowpre, origin ? row_scene : nullptr, origin, rows, K, rpt, Tp,
+                                                                  Tf, w->dec[0], w->dec[1], pred, recon);
+        LAUNCH_CHECK("k_dec_pair");
+    }
     if (ev.first) {
         std::lock_guard<std::mutex> lock(g_prof.mu);
         CUDA_TRY(cudaEventRecord(ev.second, st));
@@ -454,6 +464,53 @@ int sttode_decoder_fwd(const float* past_feature, const float* traj_norm, const 
     if (origin && !row_scene) return fail(STTODE_EINVAL, "origin given without row_scene");
     return run_decoder(past_feature, traj_norm, z, seed, row_scene, origin, rows, sample_k, w, pred, recon,
                        Carver(workspace, workspace_bytes), (cudaStream_t)stream);
+}
+
+size_t sttode_decoder_pack_bytes(int past_length, int future_length) { return (size_t)dec_pack_layout(past_length, future_length).total + 256; }
+
+int sttode_decoder_pack(const sttode_model_weights* w, void* packed, size_t packed_bytes, void* stream) {
+    int rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = check_model(w, false, true))) return rc;
+    if (!packed) return fail(STTODE_EINVAL, "null packed buffer");
+    const DecPackLayout L = dec_pack_layout(w->past_length, w->future_length);
+    if (packed_bytes < (size_t)L.total + 256) return fail(STTODE_EWORKSPACE, "packed buffer too small: %zu < %u", packed_bytes, L.total + 256);
+    unsigned char* pk = (unsigned char*)packed;
+    auto image = [&](const float* W, int ldw, int row0, int col0, int nvalid, int nrows, int K, size_t hi_off, size_t lo_off) {
+        const int n = (K >> 3) * nrows;
+        k_pack_image<<<ceil_div(n, 128), 128, 0, st>>>(W, ldw, row0, col0, nvalid, nrows, K, pk + hi_off, pk + lo_off);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    };
+    const sttode_mlp3_weights* mlps[4] = {&w->dec[0].dec_x, &w->dec[0].dec_y, &w->dec[1].dec_y, &w->dec[1].dec_x};
+    for (int m = 0; m < 4; ++m) {
+        const int K1 = (int)L.k1[m], n3 = (int)L.n3[m], n3p = (int)L.n3p[m];
+        for (int c = 0; c < TC_NCH; ++c) {
+            const size_t blk = L.mlp_off[m] + (size_t)c * L.mlp_blk[m];
+            image(mlps[m]->w0, 256, c * 16, 128, 16, 16, K1, blk, blk + 16 * K1 * 2);
+            image(mlps[m]->w1, 512, 0, c * 16, 256, 256, 16, blk + 2 * 16 * K1 * 2, blk + 2 * 16 * K1 * 2 + 8192);
+        }
+        for (int p = 0; p < 16; ++p) {
+            const size_t pc = L.l3_off[m] + (size_t)(p >> 3) * L.l3_blk[m] + (size_t)(p & 7) * n3p * 64;
+            image(mlps[m]->w2, 256, 0, p * 16, n3, n3p, 16, pc, pc + n3p * 32);
+        }
+    }
+    for (int g = 0; g < 2; ++g)
+        for (int b = 0; b < 6; ++b) {
+            const size_t blk = L.gru_off[g] + (size_t)b * TC_STAGE;
+            const int row0 = (b >> 1) * 96 + (b & 1) * 48;
+            image(w->dec[g].gru_w_ih, 32, row0, 0, 48, 48, 32, blk, blk + 3072);
+            image(w->dec[g].gru_w_hh, 96, row0, 0, 48, 48, 96, blk + 6144, blk + 6144 + 9216);
+        }
+    CUDA_TRY(cudaMemsetAsync(pk + L.total, 0, 256, st));
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int sttode_decoder_pack_status(const void* packed, int past_length, int future_length, int* status_host) {
+    if (!packed || !status_host) return fail(STTODE_EINVAL, "null pointer");
+    const DecPackLayout L = dec_pack_layout(past_length, future_length);
+    CUDA_TRY(cudaMemcpy(status_host, (const unsigned char*)packed + L.total, sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 size_t sttode_forecast_workspace_bytes(int rows, int L, int sample_k, int past_length) {

@@ -206,6 +206,36 @@ def _decompose_struct(blk):
     return s
 
 
+class _PackedDecoder:
+    """fp16 hi/lo operand images of the decoder weights for the tcgen05 kernel, rebuilt whenever a parameter changes."""
+
+    def __init__(self):
+        self.key, self.buf = None, None
+
+    def get(self, decoder, past_length, future_length):
+        params = [p for blk in decoder.decompose for p in blk.parameters()]
+        key = tuple((p.data_ptr(), p._version) for p in params) + (past_length, future_length)
+        if key != self.key:
+            lib = _lib.lib()
+            dev = params[0].device
+            buf = torch.empty(lib.sttode_decoder_pack_bytes(past_length, future_length), dtype=torch.uint8, device=dev)
+            mw = _lib.ModelWeights()
+            mw.past_length, mw.future_length = past_length, future_length
+            mw.dec[0], mw.dec[1] = _decompose_struct(decoder.decompose[0]), _decompose_struct(decoder.decompose[1])
+            _lib.check(lib.sttode_decoder_pack(C.byref(mw), _lib.dptr(buf), buf.numel(), _lib.stream_ptr()))
+            self.key, self.buf = key, buf
+        return self.buf
+
+    def status(self, past_length, future_length):
+        """0 unless a tensor-core barrier ever timed out (synchronises)."""
+        if self.buf is None:
+            return 0
+        st = C.c_int(0)
+        torch.cuda.synchronize()
+        _lib.check(_lib.lib().sttode_decoder_pack_status(_lib.dptr(self.buf), past_length, future_length, C.byref(st)))
+        return st.value
+
+
 class Decoder(nn.Module):
     """K-sample residual decoder (model/STTODE.py:302-347)."""
 
@@ -222,6 +252,8 @@ class Decoder(nn.Module):
             raise NotImplementedError("B200 path: zdim = 32 only (train.py:37 default)")
         self.past_length, self.future_length = args.past_length, args.future_length
         self.decompose = nn.ModuleList(DecomposeBlock(args.past_length, args.future_length, input_dim) for _ in range(2))
+        self.use_tensor_cores = True        # tcgen05 decoder tile (k_dec_pair_tc); False -> FP32-FFMA kernel
+        self._packed = _PackedDecoder()
 
     def forward(self, past_feature, z, batch_size_curr, agent_num_perscene, past_traj, cur_location, sample_num, mode="train"):
         """Reference signature: past_feature / z are [rows*sample_num, .] (already repeated per sample).
@@ -237,6 +269,7 @@ class Decoder(nn.Module):
         mw = _lib.ModelWeights()
         mw.past_length, mw.future_length = self.past_length, self.future_length
         mw.dec[0], mw.dec[1] = _decompose_struct(self.decompose[0]), _decompose_struct(self.decompose[1])
+        mw.dec_packed = _lib.dptr(self._packed.get(self, self.past_length, self.future_length)) if self.use_tensor_cores else None
         pred = torch.empty(pairs, 1, self.future_length, 2, device=pf.device, dtype=torch.float32)
         recon = torch.empty(pairs, self.past_length, 2, device=pf.device, dtype=torch.float32)
         lib = _lib.lib()
@@ -278,7 +311,12 @@ class STTODENet(nn.Module):
         mw.past_length, mw.future_length = self.args.past_length, self.args.future_length
         mw.past = _encoder_struct(self.past_encoder)
         mw.dec[0], mw.dec[1] = _decompose_struct(self.decoder.decompose[0]), _decompose_struct(self.decoder.decompose[1])
+        if self.decoder.use_tensor_cores:
+            mw.dec_packed = _lib.dptr(self.decoder._packed.get(self.decoder, self.args.past_length, self.args.future_length))
         return mw
+
+    def tc_status(self):
+        return self.decoder._packed.status(self.args.past_length, self.args.future_length)
 
     # ---- data staging (reference call sequence) ---------------------------------------------------
     def set_data(self, batch, pre_motion, fut_motion, pre_motion_mask, fut_motion_mask):

@@ -27,19 +27,23 @@ def dev():
     return torch.device("cuda:0")
 
 
-def build_model(dataset, tp, tf, seed, dev):
+def build_model(dataset, tp, tf, seed, dev, tensor_cores=True):
     from oracle.ref_shim import make_args
     from sttode_b200.net import STTODENet
     sd = O.make_state_dict(seed, tp, tf)
     m = STTODENet(make_args(dataset, tp, tf), dev)
     m.load_state_dict(sd, strict=True)
     m.set_device(dev)
+    m.decoder.use_tensor_cores = tensor_cores
     return m.eval(), sd
 
 
-@pytest.fixture(scope="module")
-def eth(dev):
-    return build_model("eth", 8, 12, 1, dev)
+@pytest.fixture(scope="module", params=["tc", "ffma"])
+def eth(dev, request):
+    """Every test that uses this fixture runs twice: tensor-core (tcgen05) decoder and FP32-FFMA decoder."""
+    m, sd = build_model("eth", 8, 12, 1, dev, tensor_cores=request.param == "tc")
+    yield m, sd
+    assert m.tc_status() == 0, "a tcgen05 barrier timed out"
 
 
 # ------------------------------------------------------------------ MHGSA
@@ -200,11 +204,12 @@ def test_inference_eth_vs_reference_golden(golden, eth, dev, idx, n):
     m.z_override = None
 
 
+@pytest.mark.parametrize("tcores", [True, False])
 @pytest.mark.parametrize("name,tp,tf", [("nba1020", 10, 20), ("nba0510", 5, 10)])
-def test_inference_nba_vs_reference_golden(golden, dev, name, tp, tf):
+def test_inference_nba_vs_reference_golden(golden, dev, name, tp, tf, tcores):
     g = golden("inference_nba")
     B = int(g[f"{name}_B"])
-    m, _ = build_model("nba", tp, tf, 2, dev)
+    m, _ = build_model("nba", tp, tf, 2, dev, tensor_cores=tcores)
     data = synth.nba_batch(0, B, 11, tp, tf)
     m.z_override = synth.latent(B * 11, seed=9)
     m.set_data_nba(data)
@@ -212,6 +217,7 @@ def test_inference_nba_vs_reference_golden(golden, dev, name, tp, tf):
     ref = g[f"{name}_pred"]
     cur = data["past_traj"].view(B * 11, tp, 2)[:, -1].numpy()[None, :, None, :]
     assert rel(pred.cpu().numpy() - cur, ref - cur) < TOL
+    assert m.tc_status() == 0
 
 
 def test_inference_nba_batch128_vs_oracle(dev):
