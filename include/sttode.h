@@ -179,6 +179,9 @@ int sttode_decoder_fwd(const float *past_feature, const float *traj_norm, const 
 size_t sttode_decoder_pack_bytes(int past_length, int future_length);
 int sttode_decoder_pack(const sttode_model_weights *w, void *packed, size_t packed_bytes, void *stream);
 int sttode_decoder_pack_status(const void *packed, int past_length, int future_length, int *status_host);
+/* debug: read (out31_host, nullable) then reset + enable/disable the per-phase cycle counters that CTA 0 of the tensor-core
+ * decoder accumulates in the status tail (31 x int64). */
+int sttode_decoder_timing(void *packed, int past_length, int future_length, int enable, long long *out31_host);
 
 /* ---- STTODENet.inference (model/STTODE.py:574-623) incl. set_data / set_data_nba preprocessing
  * (:397-486): past encoder + K-sample decoder in one call, device buffers. */

@@ -1,8 +1,7 @@
-# tests that failed last time, bench (both arms), ncu launch list + one full capture of the dominant kernel
+# bench (both arms), ncu launch list + one full capture of the dominant kernel
 mkdir -p gpurun_out
 rm -f gpurun_out/summary.txt
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "pmath or poincare" > gpurun_out/t_fix.log 2>&1; echo "tests exit $?" >> gpurun_out/summary.txt
-timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?" >> gpurun_out/summary.txt
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?" >> gpurun_out/summary.txt
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "bench ref exit $?" >> gpurun_out/summary.txt
 CMD="python bench.py --steps 2 --warmup 3 --scenes 384 --cpu-scenes 4"
 timeout 600 $CMD > gpurun_out/plain.log 2>&1 && \

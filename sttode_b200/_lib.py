@@ -66,6 +66,7 @@ SIGNATURES = {
     "sttode_decoder_pack_bytes": (_Z, [_I, _I]),
     "sttode_decoder_pack": (_I, [C.POINTER(ModelWeights), _V, _Z, _V]),
     "sttode_decoder_pack_status": (_I, [_V, _I, _I, C.POINTER(C.c_int)]),
+    "sttode_decoder_timing": (_I, [_V, _I, _I, _I, C.POINTER(C.c_longlong)]),
     "sttode_forecast_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "sttode_forecast": (_I, [_V, _I, _V, _V, _I, _I, _I, _I, _V, _U64, _I, C.POINTER(ModelWeights), _V, _V, _V, _V, _V, _Z, _V]),
     "sttode_forecast_host": (_I, [_V, _I, _V, _I, _I, _I, _I, _U64, _I, C.POINTER(ModelWeights), _V, _V]),

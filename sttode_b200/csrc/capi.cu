@@ -299,7 +299,7 @@ int run_decoder(const float* past_feature, const float* traj_norm, const float* 
     if (w->dec_packed) {
         const DecPackLayout lay = dec_pack_layout(Tp, Tf);
         const unsigned char* pk = (const unsigned char*)w->dec_packed;
-        k_dec_pair_tc<<<ceil_div(rows, rpt), NTHREADS, sm_tc, st>>>(traj_norm, z, seed, rowpre, origin ? row_scene : nullptr, origin, rows, K, rpt,
+        k_dec_pair_tc<<<ceil_div(rows, rpt), dec_pair_tc_threads(), sm_tc, st>>>(traj_norm, z, seed, rowpre, origin ? row_scene : nullptr, origin, rows, K, rpt,
                                                                     Tp, Tf, w->dec[0], w->dec[1], pk, lay, pred, recon, (int*)(pk + lay.total));
         LAUNCH_CHECK("k_dec_pair_tc");
     } else {
@@ -484,25 +484,36 @@ int sttode_decoder_pack(const sttode_model_weights* w, void* packed, size_t pack
     const sttode_mlp3_weights* mlps[4] = {&w->dec[0].dec_x, &w->dec[0].dec_y, &w->dec[1].dec_y, &w->dec[1].dec_x};
     for (int m = 0; m < 4; ++m) {
         const int K1 = (int)L.k1[m], n3 = (int)L.n3[m], n3p = (int)L.n3p[m];
-        for (int c = 0; c < TC_NCH; ++c) {
-            const size_t blk = L.mlp_off[m] + (size_t)c * L.mlp_blk[m];
-            image(mlps[m]->w0, 256, c * 16, 128, 16, 16, K1, blk, blk + 16 * K1 * 2);
-            image(mlps[m]->w1, 512, 0, c * 16, 256, 256, 16, blk + 2 * 16 * K1 * 2, blk + 2 * 16 * K1 * 2 + 8192);
+        for (int c = 0; c < 16; ++c) {          // chunk c = hidden units 32c..32c+31: block 2c holds the hi images, 2c+1 the lo images
+            const size_t ba = L.mlp_off[m] + (size_t)(2 * c) * L.mlp_blk[m], bb = ba + L.mlp_blk[m];
+            image(mlps[m]->w1, 512, 0, c * 32, 256, 256, 32, ba, bb);                       // layer-2 slab W2[:, 32c..]
+            image(mlps[m]->w0, 256, c * 32, 128, 32, 32, K1, ba + 16384, bb + 16384);       // layer-1 rows, pair columns 128..128+K1
         }
-        for (int p = 0; p < 16; ++p) {
-            const size_t pc = L.l3_off[m] + (size_t)(p >> 3) * L.l3_blk[m] + (size_t)(p & 7) * n3p * 64;
-            image(mlps[m]->w2, 256, 0, p * 16, n3, n3p, 16, pc, pc + n3p * 32);
+        for (int p = 0; p < 8; ++p) {
+            const size_t pc = L.l3_off[m] + (size_t)(p >> 2) * L.l3_blk[m] + (size_t)(p & 3) * n3p * 128;
+            image(mlps[m]->w2, 256, 0, p * 32, n3, n3p, 32, pc, pc + n3p * 64);
         }
     }
     for (int g = 0; g < 2; ++g)
-        for (int b = 0; b < 6; ++b) {
-            const size_t blk = L.gru_off[g] + (size_t)b * TC_STAGE;
-            const int row0 = (b >> 1) * 96 + (b & 1) * 48;
-            image(w->dec[g].gru_w_ih, 32, row0, 0, 48, 48, 32, blk, blk + 3072);
-            image(w->dec[g].gru_w_hh, 96, row0, 0, 48, 48, 96, blk + 6144, blk + 6144 + 9216);
+        for (int kb = 0; kb < 8; ++kb) {
+            const size_t blk = L.gru_off[g] + (size_t)kb * TC_GRU_BLK;
+            if (kb < 2) image(w->dec[g].gru_w_ih, 32, 0, kb * 16, 288, 288, 16, blk, blk + 9216);
+            else        image(w->dec[g].gru_w_hh, 96, 0, (kb - 2) * 16, 288, 288, 16, blk, blk + 9216);
         }
     CUDA_TRY(cudaMemsetAsync(pk + L.total, 0, 256, st));
     CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// debug: enable (1) / read the per-phase cycle counters CTA 0 of k_dec_pair_tc accumulates in the status tail
+int sttode_decoder_timing(void* packed, int past_length, int future_length, int enable, long long* out31_host) {
+    if (!packed) return fail(STTODE_EINVAL, "null pointer");
+    const DecPackLayout L = dec_pack_layout(past_length, future_length);
+    unsigned char* tail = (unsigned char*)packed + L.total;
+    if (out31_host) CUDA_TRY(cudaMemcpy(out31_host, tail + 8, 31 * 8, cudaMemcpyDeviceToHost));
+    int flag[2] = {0, enable};
+    CUDA_TRY(cudaMemset(tail, 0, 256));
+    CUDA_TRY(cudaMemcpy(tail, flag, 8, cudaMemcpyHostToDevice));
     return 0;
 }
 

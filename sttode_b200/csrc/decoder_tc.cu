@@ -13,6 +13,7 @@
 // the MMAs; all 256 threads run the TMEM epilogues (warp w reads lanes 32*(w%4).., warps w and w+4 split the columns).
 #include "kernels.cuh"
 #include "tc.cuh"
+#include <cstdio>
 
 namespace sttode {
 
@@ -36,183 +37,254 @@ DecPackLayout dec_pack_layout(int Tp, int Tf) {
         L.k1[m] = k1[m];
         L.n3[m] = n3[m];
         L.n3p[m] = (n3[m] + 15) / 16 * 16;
-        L.mlp_blk[m] = 2 * 16 * k1[m] * 2 + 2 * 256 * 16 * 2;
+        L.mlp_blk[m] = 16384 + 64 * k1[m];      // [W2 chunk image (256 rows x 32 k) | W1 chunk image (32 rows x K1)], hi and lo blocks alternate
         L.mlp_off[m] = off;
         off += TC_NCH * L.mlp_blk[m];
-        L.l3_blk[m] = L.n3p[m] * 512;
+        L.l3_blk[m] = L.n3p[m] * 512;           // 4 pieces of [hi n3p x 32 | lo n3p x 32]
         L.l3_off[m] = off;
         off += 2 * L.l3_blk[m];
     }
-    for (int g = 0; g < 2; ++g) { L.gru_off[g] = off; off += 6 * TC_STAGE; }
+    for (int g = 0; g < 2; ++g) { L.gru_off[g] = off; off += 8 * TC_GRU_BLK; }
     L.total = off;
     return L;
 }
 
 // ------------------------------------------------------------------------------------------------
+// Warp-specialised tile kernel (320 threads):
+//   warps 0..7  epilogue : TMEM -> registers -> bias/ReLU/gates -> fp16 hi/lo operand images in shared memory, outputs
+//   warp  8     issuer   : tcgen05.mma + tcgen05.commit (warp-uniform bookkeeping, one elected lane issues)
+//   warp  9     producer : streams the packed weight blocks L2 -> shared ring with cp.async.bulk
+// The roles talk through mbarriers only.  All phase parities are closed-form functions of the loop indices.
+constexpr int TC_THREADS = 320;
+constexpr int EPI_THREADS = 256;
 constexpr int SM_A1 = 0;                         // [hi 32 KB | lo 32 KB]   A1 = [z (k 0..31) | state (k 32..127)]
-constexpr int SM_H = 65536;                      // 2 x [hi 4 KB | lo 4 KB] (MLP chunk operand)  /  GRU: conv image hi 8 KB | lo 8 KB
-constexpr int SM_RING = SM_H + 16384;
+constexpr int SM_H = 65536;                      // 2 x [hi 8 KB | lo 8 KB] (MLP 32-wide chunk operand)  /  GRU: conv image in H[0]
+constexpr int SM_RING = SM_H + 32768;
 constexpr int SM_XY = SM_RING + TC_NST * TC_STAGE;
-constexpr int COL_D2 = 0, COL_D1 = 256, COL_D3 = 288;     // TMEM columns, MLP phases
-constexpr int COL_GR = 0, COL_GZ = 96, COL_GNI = 192, COL_GNH = 288;   // GRU phase
+constexpr int COL_D2 = 0, COL_D1 = 256, COL_D3 = 320;     // TMEM columns, MLP phases (D1: 2 x 32)
+constexpr int COL_GR = 0, COL_GNI = 192, COL_GNH = 288;   // GRU phase (r|z contiguous at 0..191)
+constexpr int B_WFULL = 0, B_WFREE = 4, B_D1FULL = 8, B_HFULL = 10, B_HFREE = 12, B_ACC = 14, B_XFULL = 15, B_D3FREE = 16, B_COUNT = 17;
 
-struct TcCtx {
-    unsigned char* sm;
-    uint64_t *wfull, *wfree, *d1full, *hfree, *accfull;
-    int* failed;
-    uint32_t tmem;
-    // per-thread (uniform) phase counters
-    uint32_t n_d1[2], n_h[2], n_acc;
-    // producer state (meaningful on thread 0)
-    int ld, total_blocks;
-    const unsigned char* packed;
-    DecPackLayout lay;
-    int Tp, recon;
-};
-
-__device__ __forceinline__ void tc_wait(TcCtx& c, uint64_t* bar, uint32_t parity) {
-    if (*(volatile int*)c.failed) return;
-    if (!tc::mbar_wait(bar, parity)) *(volatile int*)c.failed = 1;
+__device__ __forceinline__ void tc_wait(uint64_t* bars, int bar, uint32_t parity) {
+    if (!tc::mbar_wait(bars + bar, parity)) {      // a protocol bug must fail loudly, never hang the GPU
+        printf("k_dec_pair_tc: mbarrier %d timed out (block %d thread %d)\n", bar, blockIdx.x, threadIdx.x);
+        __trap();
+    }
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\tselp.u32 %0, 1, 0, px;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// epilogue warp: publish generic-proxy smem writes + finished TMEM reads, one arrival per warp
+__device__ __forceinline__ void epi_signal(uint64_t* bars, int bar) {
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bars + bar);
 }
 
-// global block sequence: [mlp x0: 32 chunks, 2 L3] [gru1: 6*Tp] [mlp y0: 34] [mlp y1: 34] [mlp x1: 34 when recon]
-__device__ __forceinline__ void block_src(const TcCtx& c, int i, const unsigned char*& src, uint32_t& bytes) {
-    int m = -1;
+// global block sequence: [mlp x0: 32 chunk blocks, 2 L3] [gru1: 8*Tp] [mlp y0: 34] [mlp y1: 34] [mlp x1: 34 when recon]
+__device__ __forceinline__ void block_src(const DecPackLayout& lay, int Tp, int i, uint32_t& off, uint32_t& bytes) {
+    int m;
     if (i < 34) m = 0;
     else {
         i -= 34;
-        if (i < 6 * c.Tp) { src = c.packed + c.lay.gru_off[1] + (size_t)(i % 6) * TC_STAGE; bytes = TC_STAGE; return; }
-        i -= 6 * c.Tp;
+        if (i < 8 * Tp) { off = lay.gru_off[1] + (uint32_t)(i & 7) * TC_GRU_BLK; bytes = TC_GRU_BLK; return; }
+        i -= 8 * Tp;
         if (i < 34) m = 1;
         else if (i < 68) { m = 2; i -= 34; }
         else { m = 3; i -= 68; }
     }
-    if (i < TC_NCH) { src = c.packed + c.lay.mlp_off[m] + (size_t)i * c.lay.mlp_blk[m]; bytes = c.lay.mlp_blk[m]; }
-    else { src = c.packed + c.lay.l3_off[m] + (size_t)(i - TC_NCH) * c.lay.l3_blk[m]; bytes = c.lay.l3_blk[m]; }
+    if (i < TC_NCH) { off = lay.mlp_off[m] + (uint32_t)i * lay.mlp_blk[m]; bytes = lay.mlp_blk[m]; }
+    else { off = lay.l3_off[m] + (uint32_t)(i - TC_NCH) * lay.l3_blk[m]; bytes = lay.l3_blk[m]; }
 }
 
-__device__ __forceinline__ void ring_load_next(TcCtx& c) {      // thread 0
-    const int s = c.ld % TC_NST;
-    const unsigned char* src; uint32_t bytes;
-    block_src(c, c.ld, src, bytes);
-    tc::mbar_arrive_expect_tx(c.wfull + s, bytes);
-    tc::bulk_g2s(c.sm + SM_RING + s * TC_STAGE, src, bytes, c.wfull + s);
-    ++c.ld;
-}
-__device__ __forceinline__ void ring_refill(TcCtx& c) {         // thread 0, never blocks
-    while (c.ld < c.total_blocks) {
-        const int s = c.ld % TC_NST;
-        if (c.ld >= TC_NST && !tc::mbar_try_wait(c.wfree + s, (uint32_t)((c.ld / TC_NST - 1) & 1))) break;
-        ring_load_next(c);
+// ================================================================ producer warp ============================
+__device__ void producer_main(unsigned char* sm, uint64_t* bars, const unsigned char* __restrict__ packed, const DecPackLayout& lay, int Tp,
+                              int total_blocks) {
+#pragma unroll 1
+    for (int i = 0; i < total_blocks; ++i) {
+        const int s = i & (TC_NST - 1);
+        if (i >= TC_NST) tc_wait(bars, B_WFREE + s, (uint32_t)(((i >> 2) - 1) & 1));
+        uint32_t off, bytes;
+        block_src(lay, Tp, i, off, bytes);
+        if (elect_one()) {
+            tc::mbar_arrive_expect_tx(bars + B_WFULL + s, bytes);
+            tc::bulk_g2s(sm + SM_RING + s * TC_STAGE, packed + off, bytes, bars + B_WFULL + s);
+        }
+        __syncwarp();
     }
 }
-// thread 0: make block i resident and return its stage base (shared-window address)
-__device__ __forceinline__ uint32_t ring_acquire(TcCtx& c, int i) {
-    while (c.ld <= i) {
-        const int s = c.ld % TC_NST;
-        if (c.ld >= TC_NST) tc_wait(c, c.wfree + s, (uint32_t)((c.ld / TC_NST - 1) & 1));
-        ring_load_next(c);
+static_assert(TC_NST == 4, "ring index arithmetic assumes 4 stages");
+
+// ================================================================ issuer warp ==============================
+__device__ __forceinline__ uint32_t ring_wait(unsigned char* sm, uint64_t* bars, int i) {      // block i resident -> stage address
+    tc_wait(bars, B_WFULL + (i & 3), (uint32_t)((i >> 2) & 1));
+    return tc::smem_u32(sm + SM_RING + (i & 3) * TC_STAGE);
+}
+
+// n_acc / n_d3 are running counts kept by the caller (uniform across the warp)
+__device__ void issuer_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int K1, int n3p, int blk0, uint32_t& n_d3) {
+    const uint32_t h_base = tc::smem_u32(sm + SM_H);
+    const uint64_t a1_hi = tc::op_desc(tc::smem_u32(sm + SM_A1), 128), a1_lo = tc::op_desc(tc::smem_u32(sm + SM_A1) + 32768, 128);
+    const uint32_t idesc1 = tc::make_idesc_f16(32), idesc2 = tc::make_idesc_f16(256), idesc3 = tc::make_idesc_f16(n3p);
+    const int nk1 = K1 >> 4;
+#pragma unroll 1
+    for (int ch = 0; ch <= 16; ++ch) {
+        if (ch < 16) {              // layer 1 of chunk ch (D1[ch&1] was released when chunk ch-2 was staged)
+            const uint32_t sa = ring_wait(sm, bars, blk0 + 2 * ch), sb = ring_wait(sm, bars, blk0 + 2 * ch + 1);
+            tc::tc_fence_after();
+            if (elect_one()) {
+                tc::mma_split3_d(tmem + COL_D1 + (ch & 1) * 32, a1_hi, a1_lo, 256, tc::op_desc(sa + 16384, 32), tc::op_desc(sb + 16384, 32), 64,
+                                 idesc1, nk1, false);
+                tc::mma_commit(bars + B_D1FULL + (ch & 1));
+            }
+            __syncwarp();
+        }
+        if (ch >= 1) {              // layer 2 of chunk ch-1 once its operand is staged
+            const int pc = ch - 1, b = pc & 1;
+            tc_wait(bars, B_HFULL + b, (uint32_t)((pc >> 1) & 1));
+            tc::tc_fence_after();
+            const int i0 = blk0 + 2 * pc;
+            const uint32_t sa = tc::smem_u32(sm + SM_RING + (i0 & 3) * TC_STAGE), sb = tc::smem_u32(sm + SM_RING + ((i0 + 1) & 3) * TC_STAGE);
+            if (elect_one()) {
+                tc::mma_split3_d(tmem + COL_D2, tc::op_desc(h_base + b * 16384, 128), tc::op_desc(h_base + b * 16384 + 8192, 128), 256,
+                                 tc::op_desc(sa, 256), tc::op_desc(sb, 256), 512, idesc2, 2, pc > 0);
+                tc::mma_commit(bars + B_WFREE + (i0 & 3));
+                tc::mma_commit(bars + B_WFREE + ((i0 + 1) & 3));
+                tc::mma_commit(bars + B_HFREE + b);
+                if (pc == 15) tc::mma_commit(bars + B_ACC);            // D2 complete
+            }
+            __syncwarp();
+        }
     }
-    tc_wait(c, c.wfull + (i % TC_NST), (uint32_t)((i / TC_NST) & 1));
-    return tc::smem_u32(c.sm + SM_RING + (i % TC_NST) * TC_STAGE);
+    // layer 3: D3 must have been read out by the previous phase's epilogue
+    if (n_d3 >= 1) tc_wait(bars, B_D3FREE, (n_d3 - 1) & 1);
+#pragma unroll 1
+    for (int p = 0; p < 8; ++p) {
+        const int b = p & 1, blk = blk0 + TC_NCH + (p >> 2);
+        const uint32_t st = ring_wait(sm, bars, blk) + (uint32_t)(p & 3) * n3p * 128;
+        tc_wait(bars, B_HFULL + b, (uint32_t)((p >> 1) & 1));          // 8 layer-2 fills per buffer precede: parity unchanged
+        tc::tc_fence_after();
+        if (elect_one()) {
+            tc::mma_split3_d(tmem + COL_D3, tc::op_desc(h_base + b * 16384, 128), tc::op_desc(h_base + b * 16384 + 8192, 128), 256,
+                             tc::op_desc(st, n3p), tc::op_desc(st + n3p * 64, n3p), 2 * n3p, idesc3, 2, p > 0);
+            tc::mma_commit(bars + B_HFREE + b);
+            if ((p & 3) == 3) tc::mma_commit(bars + B_WFREE + (blk & 3));
+            if (p == 7) tc::mma_commit(bars + B_ACC);                  // D3 complete
+        }
+        __syncwarp();
+    }
+    ++n_d3;
 }
 
-// stage 8 values of one row as kchunk `kc` of the chunk operand H[b], after the previous reader of H[b] has finished
-__device__ __forceinline__ void stage_h(TcCtx& c, int b, int m, int kc, const float (&v)[8]) {
-    if (c.n_h[b] >= 1) tc_wait(c, c.hfree + b, (c.n_h[b] - 1) & 1);
-    ++c.n_h[b];
-    tc::store_split8(c.sm + SM_H + b * 8192, c.sm + SM_H + b * 8192 + 4096, 128, m, kc, v);
+__device__ void issuer_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, int blk0, int T, uint32_t n_d3, uint32_t& n_x) {
+    const uint32_t a1 = tc::smem_u32(sm + SM_A1), xh = tc::smem_u32(sm + SM_H);
+    const uint32_t idesc_rz = tc::make_idesc_f16(192), idesc_n = tc::make_idesc_f16(96);
+    if (n_d3 >= 1) tc_wait(bars, B_D3FREE, (n_d3 - 1) & 1);           // the gate accumulators overlap D3
+#pragma unroll 1
+    for (int t = 0; t < T; ++t) {
+        tc_wait(bars, B_XFULL, n_x & 1);            // conv image of step t and state h_t are staged
+        ++n_x;
+        tc::tc_fence_after();
+#pragma unroll 1
+        for (int kb = 0; kb < 8; ++kb) {            // one K = 16 slab of [W_ih | W_hh] (288 rows) per ring block
+            const int bi = blk0 + t * 8 + kb;
+            const uint32_t st = ring_wait(sm, bars, bi);
+            tc::tc_fence_after();
+            // A operand slab: kb < 2 -> conv image (k chunks 2kb, 2kb+1); else state h (A1 k chunks 4 + 2(kb-2) ..)
+            const uint32_t a_off = kb < 2 ? xh + kb * 4096 : a1 + 4 * 2048 + (kb - 2) * 4096;
+            const uint32_t a_lo_off = kb < 2 ? a_off + 8192 : a_off + 32768;
+            if (elect_one()) {
+                const uint64_t ah = tc::op_desc(a_off, 128), al = tc::op_desc(a_lo_off, 128);
+                tc::mma_split3_d(tmem + COL_GR, ah, al, 0, tc::op_desc(st, 288), tc::op_desc(st + 9216, 288), 0, idesc_rz, 1, kb > 0);
+                const uint64_t bnh = tc::op_desc(st + 192 * 16, 288), bnl = tc::op_desc(st + 9216 + 192 * 16, 288);
+                if (kb < 2) tc::mma_split3_d(tmem + COL_GNI, ah, al, 0, bnh, bnl, 0, idesc_n, 1, kb > 0);
+                else        tc::mma_split3_d(tmem + COL_GNH, ah, al, 0, bnh, bnl, 0, idesc_n, 1, kb > 2);
+                tc::mma_commit(bars + B_WFREE + (bi & 3));
+                if (kb == 7) tc::mma_commit(bars + B_ACC);
+            }
+            __syncwarp();
+        }
+    }
+    tc_wait(bars, B_XFULL, n_x & 1);                // final state staged and the last gate read-out finished
+    ++n_x;
+    tc::tc_fence_after();
 }
 
-// One 3-layer MLP on the tile.  blk0 = index of its first ring block.  Result (+=) into xy_s[m][0..n3).
-__device__ void mlp_tc(TcCtx& c, int mi, int blk0, const float* __restrict__ rowpre, int prow, const float* __restrict__ b1,
-                       const float* __restrict__ b2, float* xy_s, int ldxy, bool accumulate) {
+// ================================================================ epilogue (256 threads) ===================
+// stage 16 values (two k chunks) of one row of the 32-wide chunk operand H[b]; `fill` = number of earlier fills of H[b]
+// in this kernel parity-wise (only its low bit matters), `first` = no earlier fill at all
+__device__ __forceinline__ void stage_h16(unsigned char* sm, uint64_t* bars, int b, int m, int wh, const float (&v)[16], bool first, uint32_t prev_parity) {
+    if (!first) tc_wait(bars, B_HFREE + b, prev_parity);
+    float lo8[8], hi8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { lo8[i] = v[i]; hi8[i] = v[8 + i]; }
+    unsigned char* hb = sm + SM_H + b * 16384;
+    tc::store_split8(hb, hb + 8192, 128, m, 2 * wh, lo8);
+    tc::store_split8(hb, hb + 8192, 128, m, 2 * wh + 1, hi8);
+    epi_signal(bars, B_HFULL + b);
+}
+
+__device__ __forceinline__ void load_rowbias16(float (&rb)[16], const float* __restrict__ rowpre, int prow, int ch, int wh) {
+    if (prow >= 0) {
+        const float4* p = reinterpret_cast<const float4*>(rowpre + (size_t)prow * ROWPRE_LD + ch * 32 + wh * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 r = __ldg(p + q);
+            rb[4 * q] = r.x; rb[4 * q + 1] = r.y; rb[4 * q + 2] = r.z; rb[4 * q + 3] = r.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) rb[i] = 0.f;
+    }
+}
+
+// mlp_index = how many MLPs ran before this one in the kernel (12 fills of each H buffer per MLP: parities repeat)
+__device__ void epi_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int n3, int n3p, bool first_mlp, const float* __restrict__ rowpre,
+                        int prow, const float* __restrict__ b1, const float* __restrict__ b2, float* xy_s, int ldxy, bool accumulate,
+                        uint32_t& n_acc) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wq = warp & 3, wh = warp >> 2;
     const int m = wq * 32 + lane;
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
-    const int K1 = c.lay.k1[mi], n3 = c.lay.n3[mi], n3p = c.lay.n3p[mi];
-    const uint32_t a1_hi = tc::smem_u32(c.sm + SM_A1), a1_lo = a1_hi + 32768;
-    const uint32_t h_base = tc::smem_u32(c.sm + SM_H);
-    const uint32_t w1_lo_off = 16 * K1 * 2, w2_off = 2 * w1_lo_off;
-
-    if (tid == 0) {
-        const uint32_t st = ring_acquire(c, blk0);
-        tc::tc_fence_after();
-        tc::mma_split3(c.tmem + COL_D1, a1_hi, a1_lo, st, st + w1_lo_off, 16, 0, 16, K1, false);
-        tc::mma_commit(c.d1full + 0);
-    }
+    float rb[16], rbn[16];
+    load_rowbias16(rb, rowpre, prow, 0, wh);
 #pragma unroll 1
-    for (int ch = 0; ch < TC_NCH; ++ch) {
+    for (int ch = 0; ch < 16; ++ch) {
         const int b = ch & 1;
-        if (tid == 0 && ch + 1 < TC_NCH) {          // look-ahead: keep the tensor pipe fed during this chunk's epilogue
-            const uint32_t st = ring_acquire(c, blk0 + ch + 1);
-            tc::tc_fence_after();
-            tc::mma_split3(c.tmem + COL_D1 + (b ^ 1) * 16, a1_hi, a1_lo, st, st + w1_lo_off, 16, 0, 16, K1, false);
-            tc::mma_commit(c.d1full + (b ^ 1));
-        }
-        float rb[8];
-        if (prow >= 0) {
-            const float4* p = reinterpret_cast<const float4*>(rowpre + (size_t)prow * ROWPRE_LD + ch * 16 + wh * 8);
-            const float4 r0 = __ldg(p), r1 = __ldg(p + 1);
-            rb[0] = r0.x; rb[1] = r0.y; rb[2] = r0.z; rb[3] = r0.w; rb[4] = r1.x; rb[5] = r1.y; rb[6] = r1.z; rb[7] = r1.w;
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) rb[i] = 0.f;
-        }
-        tc_wait(c, c.d1full + b, c.n_d1[b] & 1);
-        ++c.n_d1[b];
+        if (ch + 1 < 16) load_rowbias16(rbn, rowpre, prow, ch + 1, wh);        // hide the L2 latency behind this chunk
+        tc_wait(bars, B_D1FULL + b, (uint32_t)((ch >> 1) & 1));
         tc::tc_fence_after();
-        float v[8];
-        tc::tmem_ld8(c.tmem + lane_base + COL_D1 + b * 16 + wh * 8, v);
+        float v[16];
+        tc::tmem_ld16(tmem + lane_base + COL_D1 + b * 32 + wh * 16, v);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i] + rb[i], 0.f);
-        stage_h(c, b, m, wh, v);
-        tc::fence_proxy_async();
-        tc::tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            tc::tc_fence_after();
-            const uint32_t st = tc::smem_u32(c.sm + SM_RING + ((blk0 + ch) % TC_NST) * TC_STAGE);
-            tc::mma_split3(c.tmem + COL_D2, h_base + b * 8192, h_base + b * 8192 + 4096, st + w2_off, st + w2_off + 8192, 256, 0, 256, 16, ch > 0);
-            tc::mma_commit(c.wfree + (blk0 + ch) % TC_NST);
-            tc::mma_commit(c.hfree + b);
-            ring_refill(c);
-        }
+        for (int i = 0; i < 16; ++i) { v[i] = fmaxf(v[i] + rb[i], 0.f); rb[i] = rbn[i]; }
+        // fill j = 12*k + ch/2 of H[b]: wait for the reader of fill j-1
+        stage_h16(sm, bars, b, m, wh, v, first_mlp && ch < 2, (uint32_t)(((ch >> 1) + 1) & 1));
     }
-    // layer-2 epilogue feeds layer 3 sixteen columns at a time
-    if (tid == 0) tc::mma_commit(c.accfull);
-    tc_wait(c, c.accfull, c.n_acc & 1);
-    ++c.n_acc;
+    tc_wait(bars, B_ACC, n_acc & 1);                // D2 complete
+    ++n_acc;
     tc::tc_fence_after();
 #pragma unroll 1
-    for (int p = 0; p < 16; ++p) {
-        const int b = p & 1;
-        float v[8];
-        tc::tmem_ld8(c.tmem + lane_base + COL_D2 + p * 16 + wh * 8, v);
+    for (int p = 0; p < 8; ++p) {
+        float v[16];
+        tc::tmem_ld16(tmem + lane_base + COL_D2 + p * 32 + wh * 16, v);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i] + __ldg(b1 + p * 16 + wh * 8 + i), 0.f);
-        stage_h(c, b, m, wh, v);
-        tc::fence_proxy_async();
-        tc::tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            const int blk = blk0 + TC_NCH + (p >> 3);
-            const uint32_t st = ring_acquire(c, blk) + (uint32_t)(p & 7) * n3p * 64;
-            tc::tc_fence_after();
-            tc::mma_split3(c.tmem + COL_D3, h_base + b * 8192, h_base + b * 8192 + 4096, st, st + n3p * 32, n3p, 0, n3p, 16, p > 0);
-            tc::mma_commit(c.hfree + b);
-            if ((p & 7) == 7) tc::mma_commit(c.wfree + blk % TC_NST);
-            ring_refill(c);
-        }
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + __ldg(b1 + p * 32 + wh * 16 + i), 0.f);
+        stage_h16(sm, bars, p & 1, m, wh, v, false, (uint32_t)(((p >> 1) + 1) & 1));     // fill 12k + 8 + p/2
     }
-    if (tid == 0) tc::mma_commit(c.accfull);
-    tc_wait(c, c.accfull, c.n_acc & 1);
-    ++c.n_acc;
+    tc_wait(bars, B_ACC, n_acc & 1);                // D3 complete
+    ++n_acc;
     tc::tc_fence_after();
     for (int c0 = 0; c0 < n3p; c0 += 16) {
         if (((c0 >> 4) & 1) != wh) continue;        // warp-uniform: the two column halves alternate 16-wide groups
         float v[16];
-        tc::tmem_ld16(c.tmem + lane_base + COL_D3 + c0, v);
+        tc::tmem_ld16(tmem + lane_base + COL_D3 + c0, v);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const int o = c0 + i;
@@ -222,95 +294,72 @@ __device__ void mlp_tc(TcCtx& c, int mi, int blk0, const float* __restrict__ row
             }
         }
     }
-    tc::tc_fence_before();
-    __syncthreads();
+    epi_signal(bars, B_D3FREE);
+    epi_barrier();
 }
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
 
 // Conv1d+ReLU -> GRU over T steps; conv input d = xy_s; final state left in A1 k 32..127 (fp16 hi/lo images).
-__device__ void gru_tc(TcCtx& c, int blk0, const sttode_decompose_weights& w, const float* xy_s, int ldxy, int T) {
+// gb: shared-memory constants [brz 192 | bin 96 | bhn 96 | conv_w 192 | conv_b 32]
+__device__ void epi_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, const float* gb, const float* xy_s, int ldxy, int T, uint32_t& n_acc) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wq = warp & 3, wh = warp >> 2;
     const int m = wq * 32 + lane;
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
-    unsigned char* a1_hi_p = c.sm + SM_A1;
+    unsigned char* a1_hi_p = sm + SM_A1;
     unsigned char* a1_lo_p = a1_hi_p + 32768;
-    const uint32_t a1_hi = tc::smem_u32(a1_hi_p), a1_lo = a1_hi + 32768;
-    const uint32_t x_hi = tc::smem_u32(c.sm + SM_H), x_lo = x_hi + 8192;
+    const float *brz = gb, *bin = gb + 192, *bhn = gb + 288, *cw = gb + 384, *cb = gb + 576;
     // h0 = 0: clear k chunks 4..15 of both images
-    for (int i = tid; i < 2 * 12 * 128; i += NTHREADS) {
+    for (int i = tid; i < 2 * 12 * 128; i += EPI_THREADS) {
         const int img = i / (12 * 128), r = i - img * 12 * 128;
-        *reinterpret_cast<uint4*>(c.sm + SM_A1 + img * 32768 + 4 * 2048 + r * 16) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(sm + SM_A1 + img * 32768 + 4 * 2048 + r * 16) = make_uint4(0, 0, 0, 0);
     }
     float hreg[48];
 #pragma unroll
     for (int i = 0; i < 48; ++i) hreg[i] = 0.f;
     const int u0 = wh * 48;
-
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
-        // conv channels wh*16 .. +16 of row m at time t -> k chunks 2*wh, 2*wh+1 of the X image
+        // conv channels wh*16 .. +16 of row m at time t -> k chunks 2*wh, 2*wh+1 of the conv image (H[0])
+        float d[6];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int tt = t + k - 1;
+            const bool in = tt >= 0 && tt < T;
+            d[k] = in ? xy_s[m * ldxy + tt * 2] : 0.f;
+            d[3 + k] = in ? xy_s[m * ldxy + tt * 2 + 1] : 0.f;
+        }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             float v[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int chn = wh * 16 + half * 8 + i;
-                float a = __ldg(w.conv_b + chn);
+                float a = cb[chn];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const int tt = t + k - 1;
-                    if (tt >= 0 && tt < T) {
-                        a = fmaf(__ldg(w.conv_w + chn * 6 + k), xy_s[m * ldxy + tt * 2], a);
-                        a = fmaf(__ldg(w.conv_w + chn * 6 + 3 + k), xy_s[m * ldxy + tt * 2 + 1], a);
-                    }
-                }
+                for (int e = 0; e < 6; ++e) a = fmaf(cw[chn * 6 + e], d[e], a);
                 v[i] = fmaxf(a, 0.f);
             }
-            tc::store_split8(c.sm + SM_H, c.sm + SM_H + 8192, 128, m, wh * 2 + half, v);
+            tc::store_split8(sm + SM_H, sm + SM_H + 8192, 128, m, wh * 2 + half, v);
         }
-        tc::fence_proxy_async();
-        tc::tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            tc::tc_fence_after();
-#pragma unroll 1
-            for (int blk = 0; blk < 6; ++blk) {
-                const int g = blk >> 1, hf = blk & 1;
-                const int bi = blk0 + t * 6 + blk;
-                const uint32_t st = ring_acquire(c, bi);
-                tc::tc_fence_after();
-                const uint32_t wih_hi = st, wih_lo = st + 3072, whh_hi = st + 6144, whh_lo = st + 6144 + 9216;
-                if (g < 2) {
-                    const uint32_t d = c.tmem + (g == 0 ? COL_GR : COL_GZ) + hf * 48;
-                    tc::mma_split3(d, x_hi, x_lo, wih_hi, wih_lo, 48, 0, 48, 32, false);
-                    tc::mma_split3(d, a1_hi + 4 * 2048, a1_lo + 4 * 2048, whh_hi, whh_lo, 48, 0, 48, 96, true);
-                } else {
-                    tc::mma_split3(c.tmem + COL_GNI + hf * 48, x_hi, x_lo, wih_hi, wih_lo, 48, 0, 48, 32, false);
-                    tc::mma_split3(c.tmem + COL_GNH + hf * 48, a1_hi + 4 * 2048, a1_lo + 4 * 2048, whh_hi, whh_lo, 48, 0, 48, 96, false);
-                }
-                tc::mma_commit(c.wfree + bi % TC_NST);
-                ring_refill(c);
-            }
-            tc::mma_commit(c.accfull);
-        }
-        tc_wait(c, c.accfull, c.n_acc & 1);
-        ++c.n_acc;
+        epi_signal(bars, B_XFULL);                  // conv image t (+ state h_t written at the end of step t-1)
+        tc_wait(bars, B_ACC, n_acc & 1);
+        ++n_acc;
         tc::tc_fence_after();
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
             const int u = u0 + q * 16;
             float gr[16], gz[16], gni[16], gnh[16];
-            tc::tmem_ld16(c.tmem + lane_base + COL_GR + u, gr);
-            tc::tmem_ld16(c.tmem + lane_base + COL_GZ + u, gz);
-            tc::tmem_ld16(c.tmem + lane_base + COL_GNI + u, gni);
-            tc::tmem_ld16(c.tmem + lane_base + COL_GNH + u, gnh);
+            tc::tmem_ld16(tmem + lane_base + COL_GR + u, gr);
+            tc::tmem_ld16(tmem + lane_base + COL_GR + 96 + u, gz);
+            tc::tmem_ld16(tmem + lane_base + COL_GNI + u, gni);
+            tc::tmem_ld16(tmem + lane_base + COL_GNH + u, gnh);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-                const float r = fast_sigmoid(gr[i] + (__ldg(w.gru_b_ih + u + i) + __ldg(w.gru_b_hh + u + i)));
-                const float zg = fast_sigmoid(gz[i] + (__ldg(w.gru_b_ih + 96 + u + i) + __ldg(w.gru_b_hh + 96 + u + i)));
-                const float n = fast_tanh((gni[i] + __ldg(w.gru_b_ih + 192 + u + i)) + r * (gnh[i] + __ldg(w.gru_b_hh + 192 + u + i)));
+                const float r = fast_sigmoid(gr[i] + brz[u + i]);
+                const float zg = fast_sigmoid(gz[i] + brz[96 + u + i]);
+                const float n = fast_tanh((gni[i] + bin[u + i]) + r * (gnh[i] + bhn[u + i]));
                 const float hp = hreg[q * 16 + i];
                 hreg[q * 16 + i] = (hp - n) * zg + n;
             }
@@ -322,121 +371,134 @@ __device__ void gru_tc(TcCtx& c, int blk0, const sttode_decompose_weights& w, co
                 tc::store_split8(a1_hi_p, a1_lo_p, 128, m, 4 + (u >> 3) + j, v);
             }
         }
-        // the next step's barrier (after its conv image is written) orders these writes before the next MMAs
     }
-    tc::fence_proxy_async();
-    tc::tc_fence_before();
-    __syncthreads();
+    epi_signal(bars, B_XFULL);                      // final state staged, gate accumulators read out
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, unsigned long long seed,
               const float* __restrict__ rowpre, const int* __restrict__ row_scene, const float* __restrict__ origin, int rows, int K,
               int rpt, int Tp, int Tf, sttode_decompose_weights w0, sttode_decompose_weights w1,
-              const unsigned char* __restrict__ packed, DecPackLayout lay, float* __restrict__ pred, float* __restrict__ recon,
-              int* __restrict__ status) {
+              const unsigned char* __restrict__ packed, const __grid_constant__ DecPackLayout lay, float* __restrict__ pred,
+              float* __restrict__ recon, int* __restrict__ status) {
     extern __shared__ __align__(128) unsigned char sm[];
     const int Tm = Tp > Tf ? Tp : Tf;
     const int ldxy = 2 * Tm + 1;
     float* xy_s = reinterpret_cast<float*>(sm + SM_XY);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM_XY + ((BM * ldxy * 4 + 15) / 16) * 16);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
-    int* failed = reinterpret_cast<int*>(tmem_slot + 1);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT + 1);
+    float* gb = reinterpret_cast<float*>(bars + B_COUNT + 3);          // GRU/conv constants of block 1 (608 floats)
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wq = warp & 3, wh = warp >> 2;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wq = warp & 3, wh = (warp >> 2) & 1;
     const int m = wq * 32 + lane;
     const int row0 = blockIdx.x * rpt;
     const int nrow = min(rpt, rows - row0);
     const int np = nrow * K;
     const int prow = m < np ? row0 + m / K : -1;
     const size_t pair0 = (size_t)row0 * K;
-
-    TcCtx c;
-    c.sm = sm;
-    c.wfull = bars; c.wfree = bars + 4; c.d1full = bars + 8; c.hfree = bars + 10; c.accfull = bars + 12;
-    c.failed = failed;
-    c.n_d1[0] = c.n_d1[1] = c.n_h[0] = c.n_h[1] = c.n_acc = 0;
-    c.ld = 0;
-    c.total_blocks = 34 * 3 + 6 * Tp + (recon ? 34 : 0);
-    c.packed = packed; c.lay = lay; c.Tp = Tp; c.recon = recon != nullptr;
+    const int total_blocks = 34 * 3 + 8 * Tp + (recon ? 34 : 0);
+    const int by0 = 34 + 8 * Tp;
+    (void)status;
 
     if (tid == 0) {
-        for (int i = 0; i < 13; ++i) tc::mbar_init(bars + i, 1);
-        tc::fence_mbar_init();
-        *failed = 0;
-    }
-    if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
-    // latent z -> A1 k chunks 0..3 (this thread: chunks 2*wh, 2*wh+1 of row m)
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const int kc = wh * 2 + j;
-        float v[8];
-        if (m < np) {
-            const size_t pair = pair0 + m;
-            float4 lo4, hi4;
-            if (z) {
-                lo4 = *reinterpret_cast<const float4*>(z + pair * 32 + kc * 8);
-                hi4 = *reinterpret_cast<const float4*>(z + pair * 32 + kc * 8 + 4);
-            } else {
-                lo4 = latent_normal4(seed, pair, kc * 2);
-                hi4 = latent_normal4(seed, pair, kc * 2 + 1);
-            }
-            v[0] = lo4.x; v[1] = lo4.y; v[2] = lo4.z; v[3] = lo4.w; v[4] = hi4.x; v[5] = hi4.y; v[6] = hi4.z; v[7] = hi4.w;
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        for (int i = 0; i < B_COUNT; ++i) {
+            const bool warp_counted = (i == B_HFULL || i == B_HFULL + 1 || i == B_XFULL || i == B_D3FREE);
+            tc::mbar_init(bars + i, warp_counted ? 8 : 1);
         }
-        tc::store_split8(sm + SM_A1, sm + SM_A1 + 32768, 128, m, kc, v);
+        tc::fence_mbar_init();
+    }
+    if (warp == 8) tc::tmem_alloc(tmem_slot, 512);
+    if (warp < 8) {
+        for (int i = tid; i < 608; i += EPI_THREADS) {
+            float v;
+            if (i < 192) v = w1.gru_b_ih[i] + w1.gru_b_hh[i];
+            else if (i < 288) v = w1.gru_b_ih[i];                      // b_in
+            else if (i < 384) v = w1.gru_b_hh[i - 96];                 // b_hn
+            else if (i < 576) v = w1.conv_w[i - 384];
+            else v = w1.conv_b[i - 576];
+            gb[i] = v;
+        }
+        // latent z -> A1 k chunks 0..3 (this thread: chunks 2*wh, 2*wh+1 of row m)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int kc = wh * 2 + j;
+            float v[8];
+            if (m < np) {
+                const size_t pair = pair0 + m;
+                float4 lo4, hi4;
+                if (z) {
+                    lo4 = *reinterpret_cast<const float4*>(z + pair * 32 + kc * 8);
+                    hi4 = *reinterpret_cast<const float4*>(z + pair * 32 + kc * 8 + 4);
+                } else {
+                    lo4 = latent_normal4(seed, pair, kc * 2);
+                    hi4 = latent_normal4(seed, pair, kc * 2 + 1);
+                }
+                v[0] = lo4.x; v[1] = lo4.y; v[2] = lo4.z; v[3] = lo4.w; v[4] = hi4.x; v[5] = hi4.y; v[6] = hi4.z; v[7] = hi4.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = 0.f;
+            }
+            tc::store_split8(sm + SM_A1, sm + SM_A1 + 32768, 128, m, kc, v);
+        }
     }
     tc::fence_proxy_async();
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
-    c.tmem = *tmem_slot;
-    if (tid == 0) ring_refill(c);
+    const uint32_t tmem = *tmem_slot;
 
-    // ---- block 0 decoder_x -> x_hat0
-    mlp_tc(c, 0, 0, rowpre + 0, prow, w0.dec_x.b1, w0.dec_x.b2, xy_s, ldxy, false);
-    if (recon)
-        for (int idx = tid; idx < np * 2 * Tp; idx += NTHREADS) {
+    if (warp == 9) {                                // ---------------- producer
+        producer_main(sm, bars, packed, lay, Tp, total_blocks);
+    } else if (warp == 8) {                         // ---------------- issuer
+        uint32_t n_d3 = 0, n_x = 0;
+        issuer_mlp(sm, bars, tmem, 32, (int)lay.n3p[0], 0, n_d3);
+        issuer_gru(sm, bars, tmem, 34, Tp, n_d3, n_x);
+        issuer_mlp(sm, bars, tmem, 32, (int)lay.n3p[1], by0, n_d3);
+        issuer_mlp(sm, bars, tmem, 128, (int)lay.n3p[2], by0 + 34, n_d3);
+        if (recon) issuer_mlp(sm, bars, tmem, 128, (int)lay.n3p[3], by0 + 68, n_d3);
+    } else {                                        // ---------------- epilogue warps
+        uint32_t n_acc = 0;
+        epi_mlp(sm, bars, tmem, 2 * Tp, (int)lay.n3p[0], true, rowpre + 0, prow, w0.dec_x.b1, w0.dec_x.b2, xy_s, ldxy, false, n_acc);
+        if (recon)
+            for (int idx = tid; idx < np * 2 * Tp; idx += EPI_THREADS) {
+                const int mm = idx / (2 * Tp), e = idx - mm * 2 * Tp;
+                recon[(pair0 + mm) * 2 * Tp + e] = xy_s[mm * ldxy + e];
+            }
+        for (int idx = tid; idx < BM * 2 * Tp; idx += EPI_THREADS) {      // conv input of block 1: x_true - x_hat0
             const int mm = idx / (2 * Tp), e = idx - mm * 2 * Tp;
-            recon[(pair0 + mm) * 2 * Tp + e] = xy_s[mm * ldxy + e];
+            const int r = mm < np ? row0 + mm / K : -1;
+            xy_s[mm * ldxy + e] = r >= 0 ? traj_norm[(size_t)r * 2 * Tp + e] - xy_s[mm * ldxy + e] : 0.f;
         }
-    for (int idx = tid; idx < BM * 2 * Tp; idx += NTHREADS) {
-        const int mm = idx / (2 * Tp), e = idx - mm * 2 * Tp;
-        const int r = mm < np ? row0 + mm / K : -1;
-        xy_s[mm * ldxy + e] = r >= 0 ? traj_norm[(size_t)r * 2 * Tp + e] - xy_s[mm * ldxy + e] : 0.f;
-    }
-    __syncthreads();
-    // ---- block 1 Conv1d + GRU -> state1 (A1 k 32..127)
-    gru_tc(c, 34, w1, xy_s, ldxy, Tp);
-    // ---- decoder_y of both blocks
-    const int by0 = 34 + 6 * Tp;
-    mlp_tc(c, 1, by0, rowpre + 512, prow, w0.dec_y.b1, w0.dec_y.b2, xy_s, ldxy, false);
-    mlp_tc(c, 2, by0 + 34, rowpre + 1024, prow, w1.dec_y.b1, w1.dec_y.b2, xy_s, ldxy, true);
-    for (int idx = tid; idx < np * 2 * Tf; idx += NTHREADS) {
-        const int mm = idx / (2 * Tf), e = idx - mm * 2 * Tf, cc = e & 1;
-        const int r = row0 + mm / K;
-        float v = xy_s[mm * ldxy + e] + traj_norm[((size_t)r * Tp + Tp - 1) * 2 + cc];
-        if (origin) v += origin[row_scene[r] * 2 + cc];
-        pred[(pair0 + mm) * 2 * Tf + e] = v;
-    }
-    if (recon) {
-        __syncthreads();
-        mlp_tc(c, 3, by0 + 68, rowpre + 1536, prow, w1.dec_x.b1, w1.dec_x.b2, xy_s, ldxy, false);
-        for (int idx = tid; idx < np * 2 * Tp; idx += NTHREADS) {
-            const int mm = idx / (2 * Tp), e = idx - mm * 2 * Tp;
-            recon[(pair0 + mm) * 2 * Tp + e] += xy_s[mm * ldxy + e];
+        epi_barrier();
+        epi_gru(sm, bars, tmem, gb, xy_s, ldxy, Tp, n_acc);
+        epi_barrier();                              // every thread is done reading the conv input before y0 overwrites xy_s
+        epi_mlp(sm, bars, tmem, 2 * Tf, (int)lay.n3p[1], false, rowpre + 512, prow, w0.dec_y.b1, w0.dec_y.b2, xy_s, ldxy, false, n_acc);
+        epi_mlp(sm, bars, tmem, 2 * Tf, (int)lay.n3p[2], false, rowpre + 1024, prow, w1.dec_y.b1, w1.dec_y.b2, xy_s, ldxy, true, n_acc);
+        for (int idx = tid; idx < np * 2 * Tf; idx += EPI_THREADS) {
+            const int mm = idx / (2 * Tf), e = idx - mm * 2 * Tf, cc = e & 1;
+            const int r = row0 + mm / K;
+            float v = xy_s[mm * ldxy + e] + traj_norm[((size_t)r * Tp + Tp - 1) * 2 + cc];
+            if (origin) v += origin[row_scene[r] * 2 + cc];
+            pred[(pair0 + mm) * 2 * Tf + e] = v;
+        }
+        if (recon) {
+            epi_barrier();
+            epi_mlp(sm, bars, tmem, 2 * Tp, (int)lay.n3p[3], false, rowpre + 1536, prow, w1.dec_x.b1, w1.dec_x.b2, xy_s, ldxy, false, n_acc);
+            for (int idx = tid; idx < np * 2 * Tp; idx += EPI_THREADS) {
+                const int mm = idx / (2 * Tp), e = idx - mm * 2 * Tp;
+                recon[(pair0 + mm) * 2 * Tp + e] += xy_s[mm * ldxy + e];
+            }
         }
     }
+    tc::tc_fence_before();
     __syncthreads();
-    if (tid == 0 && *failed) *status = 1;
-    if (warp == 1) tc::tmem_dealloc(c.tmem, 512);
+    if (warp == 8) tc::tmem_dealloc(tmem, 512);
 }
 
 size_t dec_pair_tc_smem_bytes(int Tp, int Tf) {
     const int Tm = Tp > Tf ? Tp : Tf;
-    return (size_t)SM_XY + ((size_t)(BM * (2 * Tm + 1) * 4 + 15) / 16) * 16 + 16 * 8 + 16;
+    return (size_t)SM_XY + ((size_t)(BM * (2 * Tm + 1) * 4 + 15) / 16) * 16 + (B_COUNT + 3) * 8 + 608 * 4;
 }
+int dec_pair_tc_threads() { return TC_THREADS; }
 
 }  // namespace sttode

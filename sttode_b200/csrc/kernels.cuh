@@ -36,7 +36,8 @@ size_t dec_pair_smem_bytes(int Tp, int Tf);
 // decoder_tc.cu — tensor-core decoder tile + weight packing
 constexpr int TC_NST = 4;            // weight ring stages
 constexpr int TC_STAGE = 24576;      // bytes per ring stage
-constexpr int TC_NCH = 32;           // 16-unit hidden chunks per MLP (512 / 16)
+constexpr int TC_NCH = 32;           // ring blocks per MLP layer-1/2 sweep: 16 chunks of 32 hidden units x (hi block, lo block)
+constexpr int TC_GRU_BLK = 18432;    // one K = 16 slab of [W_ih | W_hh]: 288 rows, hi 9216 B | lo 9216 B
 struct DecPackLayout {               // byte offsets inside the packed weight buffer; MLP order: x0, y0, y1, x1
     uint32_t mlp_off[4], mlp_blk[4], l3_off[4], l3_blk[4], n3p[4], n3[4], k1[4];
     uint32_t gru_off[2];             // decompose[0], decompose[1]: 6 blocks of TC_STAGE bytes (gate x half)
@@ -48,8 +49,9 @@ __global__ void k_pack_image(const float* W, int ldw, int row0, int col0, int nv
 __global__ void k_dec_pair_tc(const float* traj_norm, const float* z, unsigned long long seed, const float* rowpre,
                               const int* row_scene, const float* origin, int rows, int K, int rpt, int Tp, int Tf,
                               sttode_decompose_weights w0, sttode_decompose_weights w1, const unsigned char* packed,
-                              DecPackLayout lay, float* pred, float* recon, int* status);
+                              const __grid_constant__ DecPackLayout lay, float* pred, float* recon, int* status);
 size_t dec_pair_tc_smem_bytes(int Tp, int Tf);
+int dec_pair_tc_threads();
 
 // metrics.cu
 __global__ void k_min_ade_fde(const float* pred, const float* gt, int gt_layout, int rows, int K, int Tf, double* sums);

@@ -147,6 +147,30 @@ __device__ __forceinline__ void mma_split3(uint32_t d_tmem, uint32_t a_hi, uint3
     }
 }
 
+// Descriptor-based variant for hot issue loops: operand descriptors are built once; advancing by one K = 16 step adds
+// `a_step` / `b_step` (in 16-byte units: 2 * rows of the operand image) to the 14-bit start-address field.
+__device__ __forceinline__ void mma_f16_nc(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate));
+}
+__device__ __forceinline__ void mma_split3_d(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint32_t a_step, uint64_t b_hi, uint64_t b_lo,
+                                             uint32_t b_step, uint32_t idesc, int nk, bool accumulate_first) {
+    uint32_t acc = accumulate_first ? 1u : 0u;
+#pragma unroll 2
+    for (int k = 0; k < nk; ++k) {
+        mma_f16_nc(d_tmem, a_lo, b_hi, idesc, acc);      // small terms first
+        mma_f16_nc(d_tmem, a_hi, b_lo, idesc, 1u);
+        mma_f16_nc(d_tmem, a_hi, b_hi, idesc, 1u);
+        acc = 1u;
+        a_hi += a_step; a_lo += a_step; b_hi += b_step; b_lo += b_step;
+    }
+}
+// descriptor of an R-row operand image starting at shared-window address `addr`
+__device__ __forceinline__ uint64_t op_desc(uint32_t addr, int rows) { return make_desc(addr, (uint32_t)rows * 16, 128); }
+
 // ---- fp16 hi/lo split --------------------------------------------------------------------------------------
 __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
     hi = __float2half_rn(x);
