@@ -34,7 +34,7 @@ sys.path.insert(0, ROOT)
 TP, TF, K = 8, 12, 20
 CYCLE = (10, 20, 30, 40, 50, 60)
 WEIGHT_SEED = 1
-DRAM_BYTES_PER_PAIR = 97.5e6 / 268800      # ncu --set full, k_dec_pair (profiles/r01_ncu_full_k_dec_pair_ffma.md)
+DRAM_BYTES_PER_PAIR = 100.2e6 / 268800     # ncu --set full of the dominant kernel (profiles/r01_ncu_full_k_dec_pair_tc.md)
 
 
 # ---------------------------------------------------------------------------------- FLOP accounting
@@ -164,6 +164,7 @@ def run_reference(args):
 def run_ours(args):
     import torch.distributed as dist
     import sttode_b200._lib as L
+    from sttode_b200 import parallel
     from sttode_b200.net import STTODENet, TRAJ_R2T
     from sttode_b200.synth import make_args, make_state_dict
 
@@ -180,6 +181,7 @@ def run_ours(args):
     model.load_state_dict(sd, strict=True)
     model.set_device(dev)
     model.eval()
+    model.decoder.use_tensor_cores = not args.ffma
     mw = model._weights()
 
     S = args.scenes
@@ -225,8 +227,7 @@ def run_ours(args):
     e0.record()
     for i in range(args.steps):
         step_device(1000 + i)
-    if world > 1:
-        dist.all_reduce(sums)                                          # the final metric gather (3 doubles)
+    ade, fde, nrow = parallel.reduce_metric_sums(sums)                 # the final metric gather: one all-reduce of 3 doubles
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -239,8 +240,6 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    ade, fde, nrow = (float(x) for x in sums.cpu())
-    ade, fde = ade / max(nrow, 1), fde / max(nrow, 1)
 
     # ---- end-to-end leg (host buffers through the C ABI) ------------------------------------------------
     for i in range(max(1, args.warmup // 2)):
@@ -273,12 +272,14 @@ def run_ours(args):
     pairs = rows * K
     ker_ms = tot_ms.value / max(n_l.value, 1)
     ach = issued_flops_dec_pair(TP, TF) * pairs / (ker_ms * 1e-3) / 1e12
-    roofline = {"kernel": "k_dec_pair", "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                "traffic": DRAM_BYTES_PER_PAIR * pairs, "traffic_source": "profiles/r01_ncu_full_k_dec_pair_ffma.md: 97.5 MB per 268 800-pair launch (dram read+write), scaled by pairs",
+    tc = bool(model.decoder.use_tensor_cores)
+    roofline = {"kernel": "k_dec_pair_tc" if tc else "k_dec_pair", "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                "traffic": DRAM_BYTES_PER_PAIR * pairs, "traffic_source": "profiles/r01_ncu_full_k_dec_pair_tc.md: dram read+write per 268 800-pair launch, scaled by pairs",
                 "peak_source": peak_src, "kernel_ms": ker_ms, "kernel_share_of_step": ker_ms / (ms / args.steps),
                 "flops_per_launch_issued": issued_flops_dec_pair(TP, TF) * pairs,
-                "note": "FP32 FFMA kernel (fp32 accuracy is required: SURVEY finding 9); FLOPs are those ISSUED after exact de-duplication, "
-                        "not the reference's op list; FFMA peak is 148 SM x 128 lanes x 2 x clk ~= 72 TFLOP/s"}
+                "note": ("tcgen05 kind::f16 with the 3xFP16 hi/lo split (fp32-accurate; SURVEY finding 9 rules out single-pass 16/19-bit inputs): "
+                         "3 tensor-core MACs per algorithmic MAC, so the attainable ceiling is peak/3; " if tc else "FP32 FFMA kernel; ") +
+                        "FLOPs are the ALGORITHMIC ones this kernel issues after exact de-duplication (csrc/decoder.cu header), not the reference's op list"}
     step_flops_ref = reference_flops_per_row(TP, TF) * rows
     step_flops_issued = issued_flops_per_row(TP) * rows + issued_flops_dec_pair(TP, TF) * pairs
 
@@ -309,6 +310,7 @@ def run_ours(args):
         "roofline": roofline,
         "cpu_baseline": {"value": cpu_val, "unit": "scenes/s", "cores": threads, "kind": "port",
                          "sample": f"first {nsmp} scenes of the same workload, one scene per call, PyTorch-CPU oracle port, {threads} threads, {cpu_s:.1f} s"},
+        "tc_status": model.tc_status(),
         "quality": {"min_ade": ade, "min_fde": fde, "agents": nrow, "note": "synthetic weights: parity is checked in tests/, not here"},
     }
     print(json.dumps(line), flush=True)
@@ -326,6 +328,7 @@ def main():
     ap.add_argument("--scenes", type=int, default=1536, help="scenes per GPU per step")
     ap.add_argument("--cpu-scenes", type=int, default=192, help="bounded CPU-baseline sample (scenes)")
     ap.add_argument("--ref-scenes", type=int, default=96, help="scenes per step of the --impl reference arm")
+    ap.add_argument("--ffma", action="store_true", help="use the FP32-FFMA decoder tile instead of the tcgen05 one")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -14,21 +14,20 @@ for _ in range(2): m.forecast_scenes(obs, sp)
 torch.cuda.synchronize()
 buf = m.decoder._packed.buf
 lib = L.lib()
-L.check(lib.sttode_decoder_timing(L.dptr(buf), 8, 12, 1, None))
-m.forecast_scenes(obs, sp); torch.cuda.synchronize()
 out = (C.c_longlong * 31)()
-L.check(lib.sttode_decoder_timing(L.dptr(buf), 8, 12, 0, out))
-names = {0: "issuer: L1 mma issue code", 1: "issuer: wait wfree", 2: "issuer: wait wfull", 3: "issuer: wait hfull", 4: "issuer: wait xfull", 5: "issuer: wait d3free",
-         6: "issuer: mlp x0", 7: "issuer: gru", 8: "issuer: mlp y0", 9: "issuer: mlp y1", 10: "epi: wait d1full", 11: "epi: wait hfree", 12: "epi: wait acc",
-         13: "epi: gru gate math", 20: "issuer: L2 mma issue code", 21: "issuer: gru mma issue code", 16: "epi: mlp x0", 17: "epi: gru", 18: "epi: mlp y0", 19: "epi: mlp y1", 29: "epi thread total", 30: "other waits"}
-for i in range(31):
-    if out[i]: print(f"{i:2d} {names.get(i, ''):28s} {out[i]:>10d}")
-
-# timeline of chunks 4,5 of MLP y0
 L.check(lib.sttode_decoder_timing(L.dptr(buf), 8, 12, 2, None))
 m.forecast_scenes(obs, sp); torch.cuda.synchronize()
+m.forecast_scenes(obs, sp); torch.cuda.synchronize()
 L.check(lib.sttode_decoder_timing(L.dptr(buf), 8, 12, 0, out))
-ev = ["I0 iter start", "I1 acquired", "I2 MMA1 issued", "I3 hfull(pc) done", "I4 MMA2(pc) issued", "I5 refilled", "E6 before d1full", "E7 d1full done", "E8 tmem ld done", "E9 -", "E10 staged+signalled"]
-t0 = min(v for v in out[:22] if v)
-for ch in range(2):
-    print("chunk", 4 + ch, {ev[e]: out[ch * 11 + e] - t0 for e in range(11) if out[ch * 11 + e]})
+v = list(out)
+def rel(idx, names):
+    base = min(v[i] for i in idx if v[i])
+    return {n: v[i] - base for i, n in zip(idx, names) if v[i]}
+base = min(x for x in v[0:29] if x)
+R = lambda xs: [x - base if x else None for x in xs]
+print("issuer ch4 [iter start, hfull(3) ok, MMA2(3) issued, ring(4) ok, MMA1(4) issued]:", R(v[0:5]))
+print("issuer ch5 [iter start, hfull(4) ok, MMA2(4) issued, ring(5) ok, MMA1(5) issued]:", R(v[5:10]))
+print("epi ch4 grp0 [before d1full, d1full ok, tmem ld done, staged+signalled]:", R(v[10:14]))
+print("epi ch5 grp1 [before d1full, d1full ok, tmem ld done, staged+signalled]:", R(v[15:19]))
+print("producer blk A of chunk 5:", [x - base if x else None for x in v[23:26]], "(loop top, wfree ok, arrived)")
+print("producer blk B of chunk 5:", [x - base if x else None for x in v[26:29]])

@@ -560,8 +560,15 @@ int sttode_forecast_host(const float* traj_host, int layout, const int* scene_pt
     const size_t sp_b = scene_ptr_host ? align_up((size_t)(n_scenes + 1) * 4) : 0, rs_b = scene_ptr_host ? align_up((size_t)rows * 4) : 0;
     const size_t in_b = align_up(traj_b) + sp_b + rs_b;
     const size_t ws_b = sttode_forecast_workspace_bytes(rows, L, sample_k, Tp);
+    // page-locked caller buffers are DMA targets as they are; pageable ones are staged through the pinned arena
+    auto is_pinned = [](const void* p) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeHost;
+    };
+    const bool out_pinned = is_pinned(pred_host);
     if ((rc = grow(&g_arena.pin_in, &g_arena.pin_in_sz, in_b, true))) return rc;
-    if ((rc = grow(&g_arena.pin_out, &g_arena.pin_out_sz, pred_b, true))) return rc;
+    if (!out_pinned && (rc = grow(&g_arena.pin_out, &g_arena.pin_out_sz, pred_b, true))) return rc;
     if ((rc = grow(&g_arena.dev, &g_arena.dev_sz, in_b + align_up(pred_b) + ws_b, false))) return rc;
     // stage inputs in pinned memory (one H2D), build row->scene map on the host
     memcpy(g_arena.pin_in, traj_host, traj_b);
@@ -584,9 +591,9 @@ int sttode_forecast_host(const float* traj_host, int layout, const int* scene_pt
     float* pred_d = (float*)(d + in_b);
     void* ws_d = d + in_b + align_up(pred_b);
     if ((rc = sttode_forecast(traj_d, layout, sp_d, rs_d, n_scenes, rows, L, agents, nullptr, seed, sample_k, w, pred_d, nullptr, nullptr, nullptr, ws_d, ws_b, st))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(g_arena.pin_out, pred_d, pred_b, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out_pinned ? (void*)pred_host : (void*)g_arena.pin_out, pred_d, pred_b, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    memcpy(pred_host, g_arena.pin_out, pred_b);
+    if (!out_pinned) memcpy(pred_host, g_arena.pin_out, pred_b);
     return 0;
 }
 

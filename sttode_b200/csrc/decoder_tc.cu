@@ -65,6 +65,15 @@ constexpr int COL_D2 = 0, COL_D1 = 256, COL_D3 = 320;     // TMEM columns, MLP p
 constexpr int COL_GR = 0, COL_GNI = 192, COL_GNH = 288;   // GRU phase (r|z contiguous at 0..191)
 constexpr int B_WFULL = 0, B_WFREE = 4, B_D1FULL = 8, B_HFULL = 10, B_HFREE = 12, B_ACC = 14, B_XFULL = 15, B_D3FREE = 16, B_COUNT = 17;
 
+// debug timeline: absolute clock64 stamps into the status tail (CTA 0 only, when status[1] == 2)
+// compiled in only with -DSTTODE_TC_TIMELINE (scripts/tc_timing.py); the release build has no trace of it
+#ifdef STTODE_TC_TIMELINE
+__device__ long long* g_tl = nullptr;
+#define TLOG(cond, slot) do { if (g_tl && blockIdx.x == 0 && (cond)) g_tl[slot] = clock64(); } while (0)
+#else
+#define TLOG(cond, slot) do { (void)(cond); } while (0)
+#endif
+
 __device__ __forceinline__ void tc_wait(uint64_t* bars, int bar, uint32_t parity) {
     if (!tc::mbar_wait(bars + bar, parity)) {      // a protocol bug must fail loudly, never hang the GPU
         printf("k_dec_pair_tc: mbarrier %d timed out (block %d thread %d)\n", bar, blockIdx.x, threadIdx.x);
@@ -106,18 +115,25 @@ __device__ __forceinline__ void block_src(const DecPackLayout& lay, int Tp, int 
 
 // ================================================================ producer warp ============================
 __device__ void producer_main(unsigned char* sm, uint64_t* bars, const unsigned char* __restrict__ packed, const DecPackLayout& lay, int Tp,
-                              int total_blocks) {
+                              int total_blocks, int dbg_nocopy) {
 #pragma unroll 1
     for (int i = 0; i < total_blocks; ++i) {
         const int s = i & (TC_NST - 1);
+        const int tli = i - (34 + 8 * Tp + 10);        // debug timeline: blocks of chunk 5 of MLP y0
+        TLOG((tli == 0 || tli == 1) && (threadIdx.x & 31) == 0, 23 + tli * 3);
         if (i >= TC_NST) tc_wait(bars, B_WFREE + s, (uint32_t)(((i >> 2) - 1) & 1));
+        TLOG((tli == 0 || tli == 1) && (threadIdx.x & 31) == 0, 24 + tli * 3);
         uint32_t off, bytes;
         block_src(lay, Tp, i, off, bytes);
         if (elect_one()) {
-            tc::mbar_arrive_expect_tx(bars + B_WFULL + s, bytes);
-            tc::bulk_g2s(sm + SM_RING + s * TC_STAGE, packed + off, bytes, bars + B_WFULL + s);
+            if (dbg_nocopy) mbar_arrive(bars + B_WFULL + s);          // debug: timing without the weight stream (results invalid)
+            else {
+                tc::mbar_arrive_expect_tx(bars + B_WFULL + s, bytes);
+                tc::bulk_g2s(sm + SM_RING + s * TC_STAGE, packed + off, bytes, bars + B_WFULL + s);
+            }
         }
         __syncwarp();
+        TLOG((tli == 0 || tli == 1) && (threadIdx.x & 31) == 0, 25 + tli * 3);
     }
 }
 static_assert(TC_NST == 4, "ring index arithmetic assumes 4 stages");
@@ -136,20 +152,15 @@ __device__ void issuer_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int
     const int nk1 = K1 >> 4;
 #pragma unroll 1
     for (int ch = 0; ch <= 16; ++ch) {
-        if (ch < 16) {              // layer 1 of chunk ch (D1[ch&1] was released when chunk ch-2 was staged)
-            const uint32_t sa = ring_wait(sm, bars, blk0 + 2 * ch), sb = ring_wait(sm, bars, blk0 + 2 * ch + 1);
-            tc::tc_fence_after();
-            if (elect_one()) {
-                tc::mma_split3_d(tmem + COL_D1 + (ch & 1) * 32, a1_hi, a1_lo, 256, tc::op_desc(sa + 16384, 32), tc::op_desc(sb + 16384, 32), 64,
-                                 idesc1, nk1, false);
-                tc::mma_commit(bars + B_D1FULL + (ch & 1));
-            }
-            __syncwarp();
-        }
-        if (ch >= 1) {              // layer 2 of chunk ch-1 once its operand is staged
+        // layer 2 of chunk ch-1 first: its commit releases two ring stages, so the producer can refill them while this warp
+        // waits for the blocks of chunk ch
+        const bool tl = (K1 == 32 && blk0 != 0 && (ch == 4 || ch == 5) && (threadIdx.x & 31) == 0);
+        TLOG(tl, (ch - 4) * 5 + 0);
+        if (ch >= 1) {
             const int pc = ch - 1, b = pc & 1;
             tc_wait(bars, B_HFULL + b, (uint32_t)((pc >> 1) & 1));
             tc::tc_fence_after();
+            TLOG(tl, (ch - 4) * 5 + 1);
             const int i0 = blk0 + 2 * pc;
             const uint32_t sa = tc::smem_u32(sm + SM_RING + (i0 & 3) * TC_STAGE), sb = tc::smem_u32(sm + SM_RING + ((i0 + 1) & 3) * TC_STAGE);
             if (elect_one()) {
@@ -161,6 +172,19 @@ __device__ void issuer_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int
                 if (pc == 15) tc::mma_commit(bars + B_ACC);            // D2 complete
             }
             __syncwarp();
+            TLOG(tl, (ch - 4) * 5 + 2);
+        }
+        if (ch < 16) {              // layer 1 of chunk ch (D1[ch&1] was released when chunk ch-2 was staged)
+            const uint32_t sa = ring_wait(sm, bars, blk0 + 2 * ch), sb = ring_wait(sm, bars, blk0 + 2 * ch + 1);
+            tc::tc_fence_after();
+            TLOG(tl, (ch - 4) * 5 + 3);
+            if (elect_one()) {
+                tc::mma_split3_d(tmem + COL_D1 + (ch & 1) * 32, a1_hi, a1_lo, 256, tc::op_desc(sa + 16384, 32), tc::op_desc(sb + 16384, 32), 64,
+                                 idesc1, nk1, false);
+                tc::mma_commit(bars + B_D1FULL + (ch & 1));
+            }
+            __syncwarp();
+            TLOG(tl, (ch - 4) * 5 + 4);
         }
     }
     // layer 3: D3 must have been read out by the previous phase's epilogue
@@ -189,9 +213,12 @@ __device__ void issuer_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, int
     if (n_d3 >= 1) tc_wait(bars, B_D3FREE, (n_d3 - 1) & 1);           // the gate accumulators overlap D3
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
+        const bool tl = (t == 2 && (threadIdx.x & 31) == 0);
+        TLOG(tl, 20);
         tc_wait(bars, B_XFULL, n_x & 1);            // conv image of step t and state h_t are staged
         ++n_x;
         tc::tc_fence_after();
+        TLOG(tl, 21);
 #pragma unroll 1
         for (int kb = 0; kb < 8; ++kb) {            // one K = 16 slab of [W_ih | W_hh] (288 rows) per ring block
             const int bi = blk0 + t * 8 + kb;
@@ -211,6 +238,7 @@ __device__ void issuer_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, int
             }
             __syncwarp();
         }
+        TLOG(tl, 22);
     }
     tc_wait(bars, B_XFULL, n_x & 1);                // final state staged and the last gate read-out finished
     ++n_x;
@@ -218,71 +246,77 @@ __device__ void issuer_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, int
 }
 
 // ================================================================ epilogue (256 threads) ===================
-// stage 16 values (two k chunks) of one row of the 32-wide chunk operand H[b]; `fill` = number of earlier fills of H[b]
-// in this kernel parity-wise (only its low bit matters), `first` = no earlier fill at all
-__device__ __forceinline__ void stage_h16(unsigned char* sm, uint64_t* bars, int b, int m, int wh, const float (&v)[16], bool first, uint32_t prev_parity) {
+// stage the 32 values (four k chunks) of one row of the chunk operand H[b]; prev_parity = phase of the MMA that read
+// the previous contents of H[b]
+__device__ __forceinline__ void stage_h32(unsigned char* sm, uint64_t* bars, int b, int m, const float (&v)[32], bool first, uint32_t prev_parity) {
     if (!first) tc_wait(bars, B_HFREE + b, prev_parity);
-    float lo8[8], hi8[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { lo8[i] = v[i]; hi8[i] = v[8 + i]; }
     unsigned char* hb = sm + SM_H + b * 16384;
-    tc::store_split8(hb, hb + 8192, 128, m, 2 * wh, lo8);
-    tc::store_split8(hb, hb + 8192, 128, m, 2 * wh + 1, hi8);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float t8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t8[i] = v[q * 8 + i];
+        tc::store_split8(hb, hb + 8192, 128, m, q, t8);
+    }
     epi_signal(bars, B_HFULL + b);
 }
 
-__device__ __forceinline__ void load_rowbias16(float (&rb)[16], const float* __restrict__ rowpre, int prow, int ch, int wh) {
+__device__ __forceinline__ void load_rowbias32(float (&rb)[32], const float* __restrict__ rowpre, int prow, int ch) {
     if (prow >= 0) {
-        const float4* p = reinterpret_cast<const float4*>(rowpre + (size_t)prow * ROWPRE_LD + ch * 32 + wh * 16);
+        const float4* p = reinterpret_cast<const float4*>(rowpre + (size_t)prow * ROWPRE_LD + ch * 32);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 8; ++q) {
             const float4 r = __ldg(p + q);
             rb[4 * q] = r.x; rb[4 * q + 1] = r.y; rb[4 * q + 2] = r.z; rb[4 * q + 3] = r.w;
         }
     } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) rb[i] = 0.f;
+        for (int i = 0; i < 32; ++i) rb[i] = 0.f;
     }
 }
 
-// mlp_index = how many MLPs ran before this one in the kernel (12 fills of each H buffer per MLP: parities repeat)
+// The two epilogue warp groups (wh = 0: warps 0-3, wh = 1: warps 4-7) each own one of the double buffers: group wh handles
+// the chunks / pieces with index parity wh, all 32 columns, so two chunks are in flight in the epilogue at any time.
 __device__ void epi_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int n3, int n3p, bool first_mlp, const float* __restrict__ rowpre,
                         int prow, const float* __restrict__ b1, const float* __restrict__ b2, float* xy_s, int ldxy, bool accumulate,
                         uint32_t& n_acc) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wq = warp & 3, wh = warp >> 2;
     const int m = wq * 32 + lane;
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
-    float rb[16], rbn[16];
-    load_rowbias16(rb, rowpre, prow, 0, wh);
+    float rb[32];
 #pragma unroll 1
-    for (int ch = 0; ch < 16; ++ch) {
-        const int b = ch & 1;
-        if (ch + 1 < 16) load_rowbias16(rbn, rowpre, prow, ch + 1, wh);        // hide the L2 latency behind this chunk
-        tc_wait(bars, B_D1FULL + b, (uint32_t)((ch >> 1) & 1));
+    for (int ch = wh; ch < 16; ch += 2) {
+        const bool tl = (!first_mlp && !accumulate && n3 != 0 && (ch == 4 || ch == 5) && lane == 0 && wq == 0 && n_acc >= 8);
+        load_rowbias32(rb, rowpre, prow, ch);
+        TLOG(tl, 10 + (ch - 4) * 5 + 0);
+        tc_wait(bars, B_D1FULL + wh, (uint32_t)((ch >> 1) & 1));
         tc::tc_fence_after();
-        float v[16];
-        tc::tmem_ld16(tmem + lane_base + COL_D1 + b * 32 + wh * 16, v);
+        TLOG(tl, 10 + (ch - 4) * 5 + 1);
+        float v[32];
+        tc::tmem_ld32(tmem + lane_base + COL_D1 + wh * 32, v);
+        TLOG(tl, 10 + (ch - 4) * 5 + 2);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { v[i] = fmaxf(v[i] + rb[i], 0.f); rb[i] = rbn[i]; }
-        // fill j = 12*k + ch/2 of H[b]: wait for the reader of fill j-1
-        stage_h16(sm, bars, b, m, wh, v, first_mlp && ch < 2, (uint32_t)(((ch >> 1) + 1) & 1));
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + rb[i], 0.f);
+        // fill j = 12*k + ch/2 of H[wh]: wait for the reader of fill j-1
+        stage_h32(sm, bars, wh, m, v, first_mlp && ch < 2, (uint32_t)(((ch >> 1) + 1) & 1));
+        TLOG(tl, 10 + (ch - 4) * 5 + 3);
     }
     tc_wait(bars, B_ACC, n_acc & 1);                // D2 complete
     ++n_acc;
     tc::tc_fence_after();
 #pragma unroll 1
-    for (int p = 0; p < 8; ++p) {
-        float v[16];
-        tc::tmem_ld16(tmem + lane_base + COL_D2 + p * 32 + wh * 16, v);
+    for (int p = wh; p < 8; p += 2) {
+        float v[32];
+        tc::tmem_ld32(tmem + lane_base + COL_D2 + p * 32, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + __ldg(b1 + p * 32 + wh * 16 + i), 0.f);
-        stage_h16(sm, bars, p & 1, m, wh, v, false, (uint32_t)(((p >> 1) + 1) & 1));     // fill 12k + 8 + p/2
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + __ldg(b1 + p * 32 + i), 0.f);
+        stage_h32(sm, bars, wh, m, v, false, (uint32_t)(((p >> 1) + 1) & 1));             // fill 12k + 8 + p/2
     }
     tc_wait(bars, B_ACC, n_acc & 1);                // D3 complete
     ++n_acc;
     tc::tc_fence_after();
     for (int c0 = 0; c0 < n3p; c0 += 16) {
-        if (((c0 >> 4) & 1) != wh) continue;        // warp-uniform: the two column halves alternate 16-wide groups
+        if (((c0 >> 4) & 1) != wh) continue;        // warp-uniform: the two groups alternate 16-wide column groups
         float v[16];
         tc::tmem_ld16(tmem + lane_base + COL_D3 + c0, v);
 #pragma unroll
@@ -343,6 +377,7 @@ __device__ void epi_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, const 
             }
             tc::store_split8(sm + SM_H, sm + SM_H + 8192, 128, m, wh * 2 + half, v);
         }
+        const bool tl = (t == 2 && tid == 0);
         epi_signal(bars, B_XFULL);                  // conv image t (+ state h_t written at the end of step t-1)
         tc_wait(bars, B_ACC, n_acc & 1);
         ++n_acc;
@@ -357,8 +392,11 @@ __device__ void epi_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, const 
             tc::tmem_ld16(tmem + lane_base + COL_GNH + u, gnh);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-                const float r = fast_sigmoid(gr[i] + brz[u + i]);
-                const float zg = fast_sigmoid(gz[i] + brz[96 + u + i]);
+                // r = 1/(1+ea), z = 1/(1+eb) with one reciprocal of the product (pre-activations clamped so it stays finite)
+                const float da = 1.f + __expf(-fminf(fmaxf(gr[i] + brz[u + i], -30.f), 30.f));
+                const float db = 1.f + __expf(-fminf(fmaxf(gz[i] + brz[96 + u + i], -30.f), 30.f));
+                const float inv = __fdividef(1.f, da * db);
+                const float r = inv * db, zg = inv * da;
                 const float n = fast_tanh((gni[i] + bin[u + i]) + r * (gnh[i] + bhn[u + i]));
                 const float hp = hreg[q * 16 + i];
                 hreg[q * 16 + i] = (hp - n) * zg + n;
@@ -398,12 +436,14 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
     const size_t pair0 = (size_t)row0 * K;
     const int total_blocks = 34 * 3 + 8 * Tp + (recon ? 34 : 0);
     const int by0 = 34 + 8 * Tp;
-    (void)status;
+#ifdef STTODE_TC_TIMELINE
+    if (blockIdx.x == 0 && tid == 0) g_tl = status[1] == 2 ? reinterpret_cast<long long*>(status + 2) : nullptr;
+#endif
 
     if (tid == 0) {
         for (int i = 0; i < B_COUNT; ++i) {
-            const bool warp_counted = (i == B_HFULL || i == B_HFULL + 1 || i == B_XFULL || i == B_D3FREE);
-            tc::mbar_init(bars + i, warp_counted ? 8 : 1);
+            const int cnt = (i == B_HFULL || i == B_HFULL + 1) ? 4 : (i == B_XFULL || i == B_D3FREE) ? 8 : 1;
+            tc::mbar_init(bars + i, cnt);
         }
         tc::fence_mbar_init();
     }
@@ -448,7 +488,7 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 9) {                                // ---------------- producer
-        producer_main(sm, bars, packed, lay, Tp, total_blocks);
+        producer_main(sm, bars, packed, lay, Tp, total_blocks, status[1] == 3);
     } else if (warp == 8) {                         // ---------------- issuer
         uint32_t n_d3 = 0, n_x = 0;
         issuer_mlp(sm, bars, tmem, 32, (int)lay.n3p[0], 0, n_d3);
