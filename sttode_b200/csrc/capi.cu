@@ -284,8 +284,15 @@ int run_decoder(const float* past_feature, const float* traj_norm, const float* 
     const size_t sm_row = dec_row_smem_bytes(Tp), sm_pair = dec_pair_smem_bytes(Tp, Tf);
     if ((rc = set_smem(k_dec_row, sm_row, "k_dec_row"))) return rc;
     if ((rc = set_smem(k_dec_pair, sm_pair, "k_dec_pair"))) return rc;
-    k_dec_row<<<ceil_div(rows, BM), NTHREADS, sm_row, st>>>(past_feature, traj_norm, rows, Tp, w->dec[0], w->dec[1], rowpre);
-    LAUNCH_CHECK("k_dec_row");
+    if (w->dec_packed) {
+        if ((rc = set_smem(k_dec_row_tc, dec_row_tc_smem_bytes(), "k_dec_row_tc"))) return rc;
+        k_dec_row_tc<<<ceil_div(rows, BM), dec_pair_tc_threads(), dec_row_tc_smem_bytes(), st>>>(past_feature, traj_norm, rows, Tp, w->dec[0], w->dec[1],
+                                                                                                   (const unsigned char*)w->dec_packed, dec_pack_layout(Tp, Tf), rowpre);
+        LAUNCH_CHECK("k_dec_row_tc");
+    } else {
+        k_dec_row<<<ceil_div(rows, BM), NTHREADS, sm_row, st>>>(past_feature, traj_norm, rows, Tp, w->dec[0], w->dec[1], rowpre);
+        LAUNCH_CHECK("k_dec_row");
+    }
     const int rpt = BM / K;
     const size_t sm_tc = dec_pair_tc_smem_bytes(Tp, Tf);
     if (w->dec_packed && (rc = set_smem(k_dec_pair_tc, sm_tc, "k_dec_pair_tc"))) return rc;
@@ -500,6 +507,15 @@ int sttode_decoder_pack(const sttode_model_weights* w, void* packed, size_t pack
             if (kb < 2) image(w->dec[g].gru_w_ih, 32, 0, kb * 16, 288, 288, 16, blk, blk + 9216);
             else        image(w->dec[g].gru_w_hh, 96, 0, (kb - 2) * 16, 288, 288, 16, blk, blk + 9216);
         }
+    {   // row kernel: tile j = (product p = j/2, columns (j&1)*256..): K slabs over [pf 0..127 | state 160..255] (p < 2) or pf only
+        const sttode_mlp3_weights* prod[4] = {&w->dec[0].dec_x, &w->dec[0].dec_y, &w->dec[1].dec_y, &w->dec[1].dec_x};
+        size_t blk = L.rowp_off;
+        for (int j = 0; j < 8; ++j) {
+            const int p = j >> 1, nb = j & 1, nks = j < 4 ? 14 : 8;
+            for (int ks = 0; ks < nks; ++ks, blk += 16384)
+                image(prod[p]->w0, 256, nb * 256, ks < 8 ? ks * 16 : 160 + (ks - 8) * 16, 256, 256, 16, blk, blk + 8192);
+        }
+    }
     CUDA_TRY(cudaMemsetAsync(pk + L.total, 0, 256, st));
     CUDA_TRY(cudaGetLastError());
     return 0;

@@ -45,6 +45,8 @@ DecPackLayout dec_pack_layout(int Tp, int Tf) {
         off += 2 * L.l3_blk[m];
     }
     for (int g = 0; g < 2; ++g) { L.gru_off[g] = off; off += 8 * TC_GRU_BLK; }
+    L.rowp_off = off;                           // row kernel: 88 slabs of [256 rows x 16 k] hi 8 KB | lo 8 KB
+    off += 88 * 16384;
     L.total = off;
     return L;
 }
@@ -337,7 +339,8 @@ __device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.
 
 // Conv1d+ReLU -> GRU over T steps; conv input d = xy_s; final state left in A1 k 32..127 (fp16 hi/lo images).
 // gb: shared-memory constants [brz 192 | bin 96 | bhn 96 | conv_w 192 | conv_b 32]
-__device__ void epi_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, const float* gb, const float* xy_s, int ldxy, int T, uint32_t& n_acc) {
+__device__ void epi_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, const float* gb, const float* xy_s, int ldxy, int valid_rows, int T,
+                        uint32_t& n_acc) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wq = warp & 3, wh = warp >> 2;
     const int m = wq * 32 + lane;
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
@@ -360,7 +363,7 @@ __device__ void epi_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, const 
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const int tt = t + k - 1;
-            const bool in = tt >= 0 && tt < T;
+            const bool in = tt >= 0 && tt < T && m < valid_rows;
             d[k] = in ? xy_s[m * ldxy + tt * 2] : 0.f;
             d[3 + k] = in ? xy_s[m * ldxy + tt * 2 + 1] : 0.f;
         }
@@ -510,7 +513,7 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
             xy_s[mm * ldxy + e] = r >= 0 ? traj_norm[(size_t)r * 2 * Tp + e] - xy_s[mm * ldxy + e] : 0.f;
         }
         epi_barrier();
-        epi_gru(sm, bars, tmem, gb, xy_s, ldxy, Tp, n_acc);
+        epi_gru(sm, bars, tmem, gb, xy_s, ldxy, BM, Tp, n_acc);
         epi_barrier();                              // every thread is done reading the conv input before y0 overwrites xy_s
         epi_mlp(sm, bars, tmem, 2 * Tf, (int)lay.n3p[1], false, rowpre + 512, prow, w0.dec_y.b1, w0.dec_y.b2, xy_s, ldxy, false, n_acc);
         epi_mlp(sm, bars, tmem, 2 * Tf, (int)lay.n3p[2], false, rowpre + 1024, prow, w1.dec_y.b1, w1.dec_y.b2, xy_s, ldxy, true, n_acc);
@@ -534,6 +537,152 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
     __syncthreads();
     if (warp == 8) tc::tmem_dealloc(tmem, 512);
 }
+
+
+// ================================================================ per-agent-row kernel on tensor cores ======
+// k_dec_row_tc: block-0 Conv1d+GRU on the past trajectory (sample independent) and the four layer-1 partial products
+//   rowpre[r] = [ W0x[:, pf|st].[pf|st0]+b | W0y[:, pf|st].[pf|st0]+b | W1y[:, pf].pf+b | W1x[:, pf].pf+b ]   (512 each)
+// for a tile of 128 agent rows.  Same roles / ring / GRU code as the pair kernel; the P phase runs 8 output tiles of
+// [128 x 256] (double buffered in TMEM), K = 224 or 128 in 16-wide slabs streamed through the ring.
+constexpr int SMR_PFHI = SM_H;                   // P phase: past_feature image hi (32 KB) overlays the conv-image / chunk buffers
+constexpr int SMR_PFLO = SM_RING + TC_NST * TC_STAGE;     // past_feature image lo (32 KB)
+constexpr int SMR_BARS = SMR_PFLO + 32768;
+
+__device__ __forceinline__ void row_block_src(const DecPackLayout& lay, int Tp, int i, uint32_t& off, uint32_t& bytes) {
+    if (i < 8 * Tp) { off = lay.gru_off[0] + (uint32_t)(i & 7) * TC_GRU_BLK; bytes = TC_GRU_BLK; return; }
+    off = lay.rowp_off + (uint32_t)(i - 8 * Tp) * 16384;
+    bytes = 16384;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_dec_row_tc(const float* __restrict__ past_feature, const float* __restrict__ traj_norm, int rows, int Tp, sttode_decompose_weights w0,
+             sttode_decompose_weights w1, const unsigned char* __restrict__ packed, const __grid_constant__ DecPackLayout lay,
+             float* __restrict__ rowpre) {
+    extern __shared__ __align__(128) unsigned char sm[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SMR_BARS);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT + 1);
+    float* gb = reinterpret_cast<float*>(bars + B_COUNT + 3);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wq = warp & 3, wh = (warp >> 2) & 1;
+    const int m = wq * 32 + lane;
+    const int row0 = blockIdx.x * BM;
+    const int nrow = min(BM, rows - row0);
+    const int total_blocks = 8 * Tp + 88;
+
+    if (tid == 0) {
+        for (int i = 0; i < B_COUNT; ++i) tc::mbar_init(bars + i, (i == B_HFULL || i == B_HFULL + 1 || i == B_XFULL || i == B_D3FREE) ? 8 : 1);
+        tc::fence_mbar_init();
+    }
+    if (warp == 8) tc::tmem_alloc(tmem_slot, 512);
+    if (warp < 8)
+        for (int i = tid; i < 608; i += EPI_THREADS) {
+            float v;
+            if (i < 192) v = w0.gru_b_ih[i] + w0.gru_b_hh[i];
+            else if (i < 288) v = w0.gru_b_ih[i];
+            else if (i < 384) v = w0.gru_b_hh[i - 96];
+            else if (i < 576) v = w0.conv_w[i - 384];
+            else v = w0.conv_b[i - 576];
+            gb[i] = v;
+        }
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 9) {                                // ---------------- producer
+#pragma unroll 1
+        for (int i = 0; i < total_blocks; ++i) {
+            const int s = i & 3;
+            if (i >= TC_NST) tc_wait(bars, B_WFREE + s, (uint32_t)(((i >> 2) - 1) & 1));
+            uint32_t off, bytes;
+            row_block_src(lay, Tp, i, off, bytes);
+            if (elect_one()) {
+                tc::mbar_arrive_expect_tx(bars + B_WFULL + s, bytes);
+                tc::bulk_g2s(sm + SM_RING + s * TC_STAGE, packed + off, bytes, bars + B_WFULL + s);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 8) {                         // ---------------- issuer
+        uint32_t n_x = 0;
+        issuer_gru(sm, bars, tmem, 0, Tp, 0, n_x);
+        tc_wait(bars, B_XFULL, n_x & 1);            // past_feature images staged
+        tc::tc_fence_after();
+        const uint32_t pf_hi = tc::smem_u32(sm + SMR_PFHI), pf_lo = tc::smem_u32(sm + SMR_PFLO);
+        const uint32_t st_hi = tc::smem_u32(sm + SM_A1) + 4 * 2048, st_lo = st_hi + 32768;
+        const uint32_t idesc = tc::make_idesc_f16(256);
+        int blk = 8 * Tp;
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) {               // output tile j: product p = j/2, columns (j&1)*256 ..
+            const int b = j & 1, nks = j < 4 ? 14 : 8;
+            if (j >= 2) { tc_wait(bars, B_HFULL + b, (uint32_t)(((j >> 1) + 1) & 1)); tc::tc_fence_after(); }     // D[b] read out
+#pragma unroll 1
+            for (int ks = 0; ks < nks; ++ks, ++blk) {
+                const uint32_t st = ring_wait(sm, bars, blk);
+                tc::tc_fence_after();
+                const uint32_t ah = ks < 8 ? pf_hi + ks * 4096 : st_hi + (ks - 8) * 4096;
+                const uint32_t al = ks < 8 ? pf_lo + ks * 4096 : st_lo + (ks - 8) * 4096;
+                if (elect_one()) {
+                    tc::mma_split3_d(tmem + b * 256, tc::op_desc(ah, 128), tc::op_desc(al, 128), 0, tc::op_desc(st, 256), tc::op_desc(st + 8192, 256), 0,
+                                     idesc, 1, ks > 0);
+                    tc::mma_commit(bars + B_WFREE + (blk & 3));
+                    if (ks == nks - 1) tc::mma_commit(bars + B_D1FULL + b);
+                }
+                __syncwarp();
+            }
+        }
+    } else {                                        // ---------------- epilogue warps
+        uint32_t n_acc = 0;
+        epi_gru(sm, bars, tmem, gb, traj_norm + (size_t)row0 * 2 * Tp, 2 * Tp, nrow, Tp, n_acc);
+        // past_feature tile -> fp16 hi/lo images (k chunks 8*wh .. 8*wh+7 of row m); safe: every GRU MMA has completed
+        {
+            const int r = row0 + m;
+#pragma unroll 1
+            for (int q = 0; q < 8; ++q) {
+                const int kc = wh * 8 + q;
+                float v[8];
+                if (m < nrow) {
+                    const float4 a = *reinterpret_cast<const float4*>(past_feature + (size_t)r * 128 + kc * 8);
+                    const float4 bb = *reinterpret_cast<const float4*>(past_feature + (size_t)r * 128 + kc * 8 + 4);
+                    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = bb.x; v[5] = bb.y; v[6] = bb.z; v[7] = bb.w;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+                }
+                tc::store_split8(sm + SMR_PFHI, sm + SMR_PFLO, 128, m, kc, v);
+            }
+        }
+        epi_signal(bars, B_XFULL);
+        const float* bias[4] = {w0.dec_x.b0, w0.dec_y.b0, w1.dec_y.b0, w1.dec_x.b0};
+        const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) {
+            const int b = j & 1, p = j >> 1, nb = j & 1;
+            tc_wait(bars, B_D1FULL + b, (uint32_t)((j >> 1) & 1));
+            tc::tc_fence_after();
+            const float* bp = bias[p] + nb * 256 + wh * 128;
+            float* dst = rowpre + (size_t)(row0 + m) * ROWPRE_LD + p * 512 + nb * 256 + wh * 128;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+                float v[32];
+                tc::tmem_ld32(tmem + lane_base + b * 256 + wh * 128 + c0, v);
+                if (m < nrow) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        *reinterpret_cast<float4*>(dst + c0 + q * 4) = make_float4(v[q * 4] + __ldg(bp + c0 + q * 4), v[q * 4 + 1] + __ldg(bp + c0 + q * 4 + 1),
+                                                                                   v[q * 4 + 2] + __ldg(bp + c0 + q * 4 + 2), v[q * 4 + 3] + __ldg(bp + c0 + q * 4 + 3));
+                }
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + B_HFULL + b);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tc::tmem_dealloc(tmem, 512);
+}
+
+size_t dec_row_tc_smem_bytes() { return (size_t)SMR_BARS + (B_COUNT + 3) * 8 + 608 * 4; }
 
 size_t dec_pair_tc_smem_bytes(int Tp, int Tf) {
     const int Tm = Tp > Tf ? Tp : Tf;

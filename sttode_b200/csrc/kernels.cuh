@@ -40,7 +40,8 @@ constexpr int TC_NCH = 32;           // ring blocks per MLP layer-1/2 sweep: 16 
 constexpr int TC_GRU_BLK = 18432;    // one K = 16 slab of [W_ih | W_hh]: 288 rows, hi 9216 B | lo 9216 B
 struct DecPackLayout {               // byte offsets inside the packed weight buffer; MLP order: x0, y0, y1, x1
     uint32_t mlp_off[4], mlp_blk[4], l3_off[4], l3_blk[4], n3p[4], n3[4], k1[4];
-    uint32_t gru_off[2];             // decompose[0], decompose[1]: 6 blocks of TC_STAGE bytes (gate x half)
+    uint32_t gru_off[2];             // decompose[0], decompose[1]: 8 K-slabs of TC_GRU_BLK bytes
+    uint32_t rowp_off;               // k_dec_row_tc layer-1 partial-product slabs
     uint32_t total;                  // bytes of images; a 256-byte status tail follows
 };
 DecPackLayout dec_pack_layout(int Tp, int Tf);
@@ -50,6 +51,9 @@ __global__ void k_dec_pair_tc(const float* traj_norm, const float* z, unsigned l
                               const int* row_scene, const float* origin, int rows, int K, int rpt, int Tp, int Tf,
                               sttode_decompose_weights w0, sttode_decompose_weights w1, const unsigned char* packed,
                               const __grid_constant__ DecPackLayout lay, float* pred, float* recon, int* status);
+__global__ void k_dec_row_tc(const float* past_feature, const float* traj_norm, int rows, int Tp, sttode_decompose_weights w0,
+                             sttode_decompose_weights w1, const unsigned char* packed, const __grid_constant__ DecPackLayout lay, float* rowpre);
+size_t dec_row_tc_smem_bytes();
 size_t dec_pair_tc_smem_bytes(int Tp, int Tf);
 int dec_pair_tc_threads();
 
