@@ -88,12 +88,23 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thr = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "20",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
+
+            def pump():
+                for ln in self.proc.stdout:
+                    self.lines.append((time.perf_counter(), ln))
+            self.thr = threading.Thread(target=pump, daemon=True)
             self.thr.start()
+            t0 = time.perf_counter()
+            while not self.lines and time.perf_counter() - t0 < 5.0:      # nvidia-smi takes a moment to come up
+                time.sleep(0.01)
         except Exception:
             self.proc = None
+
+    def mark(self):
+        """Start of the timed region: only samples taken after this count."""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if not self.proc:
@@ -101,7 +112,10 @@ class ClockSampler:
         self.proc.terminate()
         self.thr.join(timeout=2)
         sm, smax, reasons = [], None, set()
-        for ln in self.lines:
+        t_mark = getattr(self, "t_mark", 0.0)
+        for ts, ln in self.lines:
+            if ts < t_mark:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -224,6 +238,7 @@ def run_ours(args):
     launches0 = L.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark()
     e0.record()
     for i in range(args.steps):
         step_device(1000 + i)

@@ -25,9 +25,11 @@ def rel(idx, names):
     return {n: v[i] - base for i, n in zip(idx, names) if v[i]}
 base = min(x for x in v[0:29] if x)
 R = lambda xs: [x - base if x else None for x in xs]
-print("issuer ch4 [iter start, hfull(3) ok, MMA2(3) issued, ring(4) ok, MMA1(4) issued]:", R(v[0:5]))
-print("issuer ch5 [iter start, hfull(4) ok, MMA2(4) issued, ring(5) ok, MMA1(5) issued]:", R(v[5:10]))
+print("issuer ch4 [L1 start, ring(4) ok, MMA1(4) issued, hfull(3) ok, MMA2(3) issued]:", R(v[0:5]))
+print("issuer ch5 [L1 start, ring(5) ok, MMA1(5) issued, hfull(4) ok, MMA2(4) issued]:", R(v[5:10]))
 print("epi ch4 grp0 [before d1full, d1full ok, tmem ld done, staged+signalled]:", R(v[10:14]))
 print("epi ch5 grp1 [before d1full, d1full ok, tmem ld done, staged+signalled]:", R(v[15:19]))
 print("producer blk A of chunk 5:", [x - base if x else None for x in v[23:26]], "(loop top, wfree ok, arrived)")
 print("producer blk B of chunk 5:", [x - base if x else None for x in v[26:29]])
+ph = [v[14], v[19], v[20], v[21], v[22], v[29]]
+print("epilogue phases (cycles): x0+prep", ph[1] - ph[0], " gru", ph[2] - ph[1], " y0", ph[3] - ph[2], " y1", ph[4] - ph[3], " output", ph[5] - ph[4], " total", ph[5] - ph[0])
