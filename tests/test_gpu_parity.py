@@ -370,3 +370,96 @@ def test_pmath_scalar_fns_and_large(golden, dev):
     u = torch.randn(4096, 64, generator=gen).to(dev) * 0.05
     back = P.logmap0(P.expmap0(u, c=1.0), c=1.0)
     assert rel(back, u) < 1e-4
+
+
+# ------------------------------------------------------------------ edge cases (ragged, extreme sizes, option errors)
+def test_single_agent_scene_and_ragged_batch(eth, dev):
+    """A scene with one agent (tile of 20 pairs), ragged scene sizes that do not fill row / pair tiles."""
+    m, sd = eth
+    scenes = [synth.eth_scene(100 + i, n) for i, n in enumerate((1, 4, 1, 13, 2))]
+    counts = [o.shape[0] for o, _ in scenes]
+    obs = torch.cat([o for o, _ in scenes])
+    sp = torch.tensor(np.concatenate([[0], np.cumsum(counts)]), dtype=torch.int32)
+    z = synth.latent(sum(counts), seed=31)
+    m.z_override = z
+    pred = m.forecast_scenes(obs.to(dev), sp)
+    r0 = 0
+    for (o, _), n in zip(scenes, counts):
+        past, orig = O.eth_scene_normalise(o)
+        ref = O.inference(sd, past, 1, n, z[r0 * 20:(r0 + n) * 20], scene_orig=orig, fast=True)
+        cur = (past[:, -1] + orig)[:, None, None, :]
+        assert rel(pred[r0:r0 + n].cpu() - cur, ref.permute(1, 0, 2, 3) - cur) < TOL
+        r0 += n
+    m.z_override = None
+
+
+def test_sdd_large_scene_512_agents(eth, dev):
+    """SDD-shape sweep end point (BASELINE.json configs[3]): one scene with 512 agents, coordinates U(0,1500)/50."""
+    m, sd = eth
+    g = torch.Generator().manual_seed(77)
+    n = 512
+    p0 = torch.rand(n, 1, 2, generator=g) * 30.0
+    traj = p0 + torch.cumsum(torch.randn(n, 8, 2, generator=g) * 0.4, dim=1)
+    obs = traj.permute(0, 2, 1).contiguous()
+    z = synth.latent(n, seed=5)
+    m.z_override = z
+    m.set_data(None, obs.to(dev), None, None, None)
+    pred = m.inference(None)
+    past, orig = O.eth_scene_normalise(obs)
+    ref = O.inference(sd, past, 1, n, z, scene_orig=orig, fast=True)
+    cur = (past[:, -1] + orig)[None, :, None, :]
+    assert rel(pred.cpu() - cur, ref - cur) < TOL
+    m.z_override = None
+
+
+@pytest.mark.parametrize("k", [1, 7])
+def test_other_sample_counts(eth, dev, k):
+    """sample_k other than 20 through the C ABI (the reference hard-codes 20 in `inference`, model/STTODE.py:600, but
+    `Decoder.forward` takes any sample_num, e.g. 1 in decoder_future_0)."""
+    m, sd = eth
+    n = 9
+    obs, _ = synth.eth_scene(55, n)
+    past, orig = O.eth_scene_normalise(obs)
+    pf = O.past_encoder(O.velocity_features(past), 1, n, sd)
+    z = synth.latent(n, sample_k=k, seed=4)
+    out_ref, rec_ref = O.decoder(pf.repeat_interleave(k, 0), z, past, past[:, [-1]], k, sd, mode="inference")
+    m.z_override = z
+    sp = torch.tensor([0, n], dtype=torch.int32)
+    pred = m.forecast_scenes(obs.to(dev), sp, sample_k=k)
+    cur = (past[:, -1])[:, None, None, :]
+    assert pred.shape == (n, k, 12, 2)
+    assert rel(pred.cpu() - orig - cur, out_ref - cur) < TOL
+    m.z_override = None
+
+
+def test_ode_encoder_large_attention_axis(eth, dev):
+    """Gram-tile stress of SURVEY §8d C4(ii): L = S = 256 with 64 agents through the whole ODE block."""
+    m, sd = eth
+    x = torch.randn(256, 64, 1, 64, generator=torch.Generator().manual_seed(12)) * 0.7
+    y = m.past_encoder.ODE_Encoder(x.to(dev))
+    assert rel(y, O.ode_encoder(x, sd, "past_encoder.")) < TOL
+
+
+def test_c_abi_error_paths(eth, dev):
+    import ctypes as C
+    import sttode_b200._lib as L
+    m, _ = eth
+    lib = L.lib()
+    x = torch.randn(4, 2, 64, device=dev)
+    out = torch.empty_like(x)
+    st = m.past_encoder.ODE_Encoder.odeblock.odefunc.layers[0]
+    from sttode_b200.layers import _ode_struct
+    w = _ode_struct(st)
+    ws = torch.empty(1024, dtype=torch.uint8, device=dev)
+    # workspace too small
+    rc = lib.sttode_ode_block_fwd(L.dptr(x), C.byref(w), L.dptr(out), 64, 4, 2, 1, 12.0, 0, 1, L.dptr(ws), 16, L.stream_ptr())
+    assert rc == -3 and b"workspace" in lib.sttode_last_error()
+    # bad method / bad shape / unsupported head config
+    big = L.workspace(lib.sttode_ode_block_workspace_bytes(4, 2, 3), dev)
+    assert lib.sttode_ode_block_fwd(L.dptr(x), C.byref(w), L.dptr(out), 64, 4, 2, 1, 12.0, 9, 1, L.dptr(big), big.numel(), L.stream_ptr()) == -1
+    assert lib.sttode_ode_block_fwd(L.dptr(x), C.byref(w), L.dptr(out), 32, 4, 2, 1, 12.0, 0, 1, L.dptr(big), big.numel(), L.stream_ptr()) == -1
+    mh = w.attn
+    assert lib.sttode_mhgsa_fwd(L.dptr(x), L.dptr(x), L.dptr(x), C.byref(mh), L.dptr(out), None, 4, 4, 2, 64, 4, 0, 1e-4, 1.0, L.dptr(big), big.numel(), L.stream_ptr()) == -2
+    # the stream is still healthy afterwards
+    y = m.past_encoder.ODE_Encoder(x.unsqueeze(2))
+    assert torch.isfinite(y).all()
