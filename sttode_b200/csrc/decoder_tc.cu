@@ -116,33 +116,34 @@ __device__ __forceinline__ void block_src(const DecPackLayout& lay, int Tp, int 
 }
 
 // ================================================================ producer warp ============================
-__device__ void producer_main(unsigned char* sm, uint64_t* bars, const unsigned char* __restrict__ packed, const DecPackLayout& lay, int Tp,
-                              int total_blocks, int dbg_nocopy) {
+// The ring is managed in PAIRS of stages (every phase starts at an even block index and uses blocks two at a time):
+// one full / one free mbarrier per pair halves the number of barrier hand-offs on the issuer's critical path.
+template <typename SrcFn>
+__device__ void producer_loop(unsigned char* sm, uint64_t* bars, const unsigned char* __restrict__ packed, int total_blocks, int dbg_nocopy,
+                              SrcFn src_of) {
 #pragma unroll 1
-    for (int i = 0; i < total_blocks; ++i) {
-        const int s = i & (TC_NST - 1);
-        const int tli = i - (34 + 8 * Tp + 10);        // debug timeline: blocks of chunk 5 of MLP y0
-        TLOG((tli == 0 || tli == 1) && (threadIdx.x & 31) == 0, 23 + tli * 3);
-        if (i >= TC_NST) tc_wait(bars, B_WFREE + s, (uint32_t)(((i >> 2) - 1) & 1));
-        TLOG((tli == 0 || tli == 1) && (threadIdx.x & 31) == 0, 24 + tli * 3);
-        uint32_t off, bytes;
-        block_src(lay, Tp, i, off, bytes);
+    for (int j = 0; j < (total_blocks >> 1); ++j) {
+        const int d = j & 1;
+        uint32_t off0, bytes0, off1, bytes1;
+        src_of(2 * j, off0, bytes0);                // address arithmetic first: nothing but the copies follows the wait
+        src_of(2 * j + 1, off1, bytes1);
+        if (j >= 2) tc_wait(bars, B_WFREE + d, (uint32_t)(((j >> 1) - 1) & 1));
         if (elect_one()) {
-            if (dbg_nocopy) mbar_arrive(bars + B_WFULL + s);          // debug: timing without the weight stream (results invalid)
+            if (dbg_nocopy) mbar_arrive(bars + B_WFULL + d);          // debug: timing without the weight stream (results invalid)
             else {
-                tc::mbar_arrive_expect_tx(bars + B_WFULL + s, bytes);
-                tc::bulk_g2s(sm + SM_RING + s * TC_STAGE, packed + off, bytes, bars + B_WFULL + s);
+                tc::mbar_arrive_expect_tx(bars + B_WFULL + d, bytes0 + bytes1);
+                tc::bulk_g2s(sm + SM_RING + (2 * d) * TC_STAGE, packed + off0, bytes0, bars + B_WFULL + d);
+                tc::bulk_g2s(sm + SM_RING + (2 * d + 1) * TC_STAGE, packed + off1, bytes1, bars + B_WFULL + d);
             }
         }
         __syncwarp();
-        TLOG((tli == 0 || tli == 1) && (threadIdx.x & 31) == 0, 25 + tli * 3);
     }
 }
 static_assert(TC_NST == 4, "ring index arithmetic assumes 4 stages");
 
 // ================================================================ issuer warp ==============================
 __device__ __forceinline__ uint32_t ring_wait(unsigned char* sm, uint64_t* bars, int i) {      // block i resident -> stage address
-    tc_wait(bars, B_WFULL + (i & 3), (uint32_t)((i >> 2) & 1));
+    if (!(i & 1)) tc_wait(bars, B_WFULL + ((i >> 1) & 1), (uint32_t)((i >> 2) & 1));           // the pair's barrier covers block i+1 too
     return tc::smem_u32(sm + SM_RING + (i & 3) * TC_STAGE);
 }
 
@@ -168,8 +169,7 @@ __device__ void issuer_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int
             if (elect_one()) {
                 tc::mma_split3_d(tmem + COL_D2, tc::op_desc(h_base + b * 16384, 128), tc::op_desc(h_base + b * 16384 + 8192, 128), 256,
                                  tc::op_desc(sa, 256), tc::op_desc(sb, 256), 512, idesc2, 2, pc > 0);
-                tc::mma_commit(bars + B_WFREE + (i0 & 3));
-                tc::mma_commit(bars + B_WFREE + ((i0 + 1) & 3));
+                tc::mma_commit(bars + B_WFREE + ((i0 >> 1) & 1));
                 tc::mma_commit(bars + B_HFREE + b);
                 if (pc == 15) tc::mma_commit(bars + B_ACC);            // D2 complete
             }
@@ -201,7 +201,7 @@ __device__ void issuer_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int
             tc::mma_split3_d(tmem + COL_D3, tc::op_desc(h_base + b * 16384, 128), tc::op_desc(h_base + b * 16384 + 8192, 128), 256,
                              tc::op_desc(st, n3p), tc::op_desc(st + n3p * 64, n3p), 2 * n3p, idesc3, 2, p > 0);
             tc::mma_commit(bars + B_HFREE + b);
-            if ((p & 3) == 3) tc::mma_commit(bars + B_WFREE + (blk & 3));
+            if (p == 7) tc::mma_commit(bars + B_WFREE + ((blk >> 1) & 1));
             if (p == 7) tc::mma_commit(bars + B_ACC);                  // D3 complete
         }
         __syncwarp();
@@ -235,7 +235,7 @@ __device__ void issuer_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, int
                 const uint64_t bnh = tc::op_desc(st + 192 * 16, 288), bnl = tc::op_desc(st + 9216 + 192 * 16, 288);
                 if (kb < 2) tc::mma_split3_d(tmem + COL_GNI, ah, al, 0, bnh, bnl, 0, idesc_n, 1, kb > 0);
                 else        tc::mma_split3_d(tmem + COL_GNH, ah, al, 0, bnh, bnl, 0, idesc_n, 1, kb > 2);
-                tc::mma_commit(bars + B_WFREE + (bi & 3));
+                if (bi & 1) tc::mma_commit(bars + B_WFREE + ((bi >> 1) & 1));
                 if (kb == 7) tc::mma_commit(bars + B_ACC);
             }
             __syncwarp();
@@ -491,7 +491,7 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 9) {                                // ---------------- producer
-        producer_main(sm, bars, packed, lay, Tp, total_blocks, status[1] == 3);
+        producer_loop(sm, bars, packed, total_blocks, status[1] == 3, [&](int i, uint32_t& off, uint32_t& bytes) { block_src(lay, Tp, i, off, bytes); });
     } else if (warp == 8) {                         // ---------------- issuer
         uint32_t n_d3 = 0, n_x = 0;
         issuer_mlp(sm, bars, tmem, 32, (int)lay.n3p[0], 0, n_d3);
@@ -590,18 +590,7 @@ k_dec_row_tc(const float* __restrict__ past_feature, const float* __restrict__ t
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 9) {                                // ---------------- producer
-#pragma unroll 1
-        for (int i = 0; i < total_blocks; ++i) {
-            const int s = i & 3;
-            if (i >= TC_NST) tc_wait(bars, B_WFREE + s, (uint32_t)(((i >> 2) - 1) & 1));
-            uint32_t off, bytes;
-            row_block_src(lay, Tp, i, off, bytes);
-            if (elect_one()) {
-                tc::mbar_arrive_expect_tx(bars + B_WFULL + s, bytes);
-                tc::bulk_g2s(sm + SM_RING + s * TC_STAGE, packed + off, bytes, bars + B_WFULL + s);
-            }
-            __syncwarp();
-        }
+        producer_loop(sm, bars, packed, total_blocks, 0, [&](int i, uint32_t& off, uint32_t& bytes) { row_block_src(lay, Tp, i, off, bytes); });
     } else if (warp == 8) {                         // ---------------- issuer
         uint32_t n_x = 0;
         issuer_gru(sm, bars, tmem, 0, Tp, 0, n_x);
@@ -624,7 +613,7 @@ k_dec_row_tc(const float* __restrict__ past_feature, const float* __restrict__ t
                 if (elect_one()) {
                     tc::mma_split3_d(tmem + b * 256, tc::op_desc(ah, 128), tc::op_desc(al, 128), 0, tc::op_desc(st, 256), tc::op_desc(st + 8192, 256), 0,
                                      idesc, 1, ks > 0);
-                    tc::mma_commit(bars + B_WFREE + (blk & 3));
+                    if (blk & 1) tc::mma_commit(bars + B_WFREE + ((blk >> 1) & 1));
                     if (ks == nks - 1) tc::mma_commit(bars + B_D1FULL + b);
                 }
                 __syncwarp();
