@@ -305,6 +305,40 @@ def run_ours(args):
     cpu_s = time_cpu_port(sd, scenes[:nsmp], threads)
     cpu_val = nsmp / cpu_s
 
+    # ---- other configs of BASELINE.json, measured briefly for DESIGN.md (not the headline): rank 0 only -----------------
+    extra = {}
+    if not args.no_extra:
+        from sttode_b200 import synth
+        with torch.no_grad():
+            # configs[0] shape: one ETH scene (N = 7) per call, the way test.py drives the model; eager C-ABI call vs one CUDA-graph launch
+            obs7, _ = synth.eth_scene(3, 7)
+            obs7 = obs7.to(dev)
+            sp7 = torch.tensor([0, 7], dtype=torch.int32, device=dev)
+
+            def lat(fn, n=200):
+                for _ in range(20):
+                    fn()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(n):
+                    fn()
+                torch.cuda.synchronize()
+                return 1e6 * (time.perf_counter() - t0) / n
+            g7 = model.capture_forecast(rows=7, L=1, agents=1, n_scenes=1)
+            extra["eth_single_scene_N7"] = {"eager_us_per_call": lat(lambda: model.forecast_scenes(obs7, sp7)),
+                                            "cuda_graph_us_per_call": lat(lambda: g7(obs7, sp7)), "kernels_per_call": 5}
+            # configs[2]: NBA shape, 11 agents, obs 10 / pred 20, reference test batch B = 128 (scenes of a batch attend to each other: MHGSA L = S = 128)
+            nba = STTODENet(make_args("nba", 10, 20), dev)
+            nba.load_state_dict(make_state_dict(2, 10, 20), strict=True)
+            nba.set_device(dev)
+            nba.eval()
+            nb = 16
+            batches = torch.stack([synth.nba_batch(i, 128, 11, 10, 20)["past_traj"] for i in range(nb)]).to(dev)      # [nb,128,11,10,2]
+            gnba = nba.capture_forecast(rows=nb * 128 * 11, L=128, agents=11, n_scenes=0, layout=0)
+            us = lat(lambda: gnba(batches.view(-1, 10, 2)), n=20)
+            extra["nba_B128_10_20"] = {"scenes_per_s": nb * 128 / (us * 1e-6), "batches_per_launch": nb, "us_per_launch": us,
+                                       "note": "16 reference batches per launch, each batch = one MHGSA group of L = S = 128 scenes x 11 agents"}
+
     total_scenes = S * world * args.steps
     value = total_scenes / (ms_max * 1e-3)
     line = {
@@ -326,6 +360,7 @@ def run_ours(args):
         "cpu_baseline": {"value": cpu_val, "unit": "scenes/s", "cores": threads, "kind": "port",
                          "sample": f"first {nsmp} scenes of the same workload, one scene per call, PyTorch-CPU oracle port, {threads} threads, {cpu_s:.1f} s"},
         "tc_status": model.tc_status(),
+        "extra": extra,
         "quality": {"min_ade": ade, "min_fde": fde, "agents": nrow, "note": "synthetic weights: parity is checked in tests/, not here"},
     }
     print(json.dumps(line), flush=True)
@@ -343,6 +378,7 @@ def main():
     ap.add_argument("--scenes", type=int, default=1536, help="scenes per GPU per step")
     ap.add_argument("--cpu-scenes", type=int, default=192, help="bounded CPU-baseline sample (scenes)")
     ap.add_argument("--ref-scenes", type=int, default=96, help="scenes per step of the --impl reference arm")
+    ap.add_argument("--no-extra", action="store_true", help="skip the brief single-scene-latency and NBA-shape measurements")
     ap.add_argument("--ffma", action="store_true", help="use the FP32-FFMA decoder tile instead of the tcgen05 one")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

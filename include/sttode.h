@@ -94,6 +94,9 @@ typedef struct sttode_model_weights {
     sttode_decompose_weights dec[2];            /* decoder.decompose.{0,1}.*  (num_decompose = 2)   */
     const void *dec_packed;                     /* optional: buffer filled by sttode_decoder_pack -> tensor-core decoder;
                                                    NULL -> FP32-FFMA decoder kernels                */
+    unsigned long long *rng_state;              /* optional device counter for CUDA-graph replay: when set and z == NULL the
+                                                   in-kernel latent draw uses seed + *rng_state and the call bumps *rng_state
+                                                   by one in-stream, so every replay of a captured call draws fresh samples   */
 } sttode_model_weights;
 
 /* ---- diagnostics ------------------------------------------------------------------------------- */

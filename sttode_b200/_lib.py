@@ -37,7 +37,7 @@ class DecomposeWeights(C.Structure):
 
 class ModelWeights(C.Structure):
     _fields_ = [("past_length", C.c_int), ("future_length", C.c_int), ("past", EncoderWeights), ("dec", DecomposeWeights * 2),
-                ("dec_packed", C.c_void_p)]
+                ("dec_packed", C.c_void_p), ("rng_state", C.c_void_p)]
 
 
 # every symbol include/sttode.h declares: name -> (restype, argtypes)

@@ -306,13 +306,17 @@ int run_decoder(const float* past_feature, const float* traj_norm, const float* 
     if (w->dec_packed) {
         const DecPackLayout lay = dec_pack_layout(Tp, Tf);
         const unsigned char* pk = (const unsigned char*)w->dec_packed;
-        k_dec_pair_tc<<<ceil_div(rows, rpt), dec_pair_tc_threads(), sm_tc, st>>>(traj_norm, z, seed, rowpre, origin ? row_scene : nullptr, origin, rows, K, rpt,
+        k_dec_pair_tc<<<ceil_div(rows, rpt), dec_pair_tc_threads(), sm_tc, st>>>(traj_norm, z, seed, z ? nullptr : w->rng_state, rowpre, origin ? row_scene : nullptr, origin, rows, K, rpt,
                                                                     Tp, Tf, w->dec[0], w->dec[1], pk, lay, pred, recon, (int*)(pk + lay.total));
         LAUNCH_CHECK("k_dec_pair_tc");
     } else {
-        k_dec_pair<<<ceil_div(rows, rpt), NTHREADS, sm_pair, st>>>(traj_norm, z, seed, rowpre, origin ? row_scene : nullptr, origin, rows, K, rpt, Tp,
+        k_dec_pair<<<ceil_div(rows, rpt), NTHREADS, sm_pair, st>>>(traj_norm, z, seed, z ? nullptr : w->rng_state, rowpre, origin ? row_scene : nullptr, origin, rows, K, rpt, Tp,
                                                                   Tf, w->dec[0], w->dec[1], pred, recon);
         LAUNCH_CHECK("k_dec_pair");
+    }
+    if (!z && w->rng_state) {
+        k_bump_counter<<<1, 1, 0, st>>>(w->rng_state);
+        LAUNCH_CHECK("k_bump_counter");
     }
     if (ev.first) {
         std::lock_guard<std::mutex> lock(g_prof.mu);

@@ -263,7 +263,7 @@ __device__ void mlp_phase(const float* A1, int lda, const sttode_mlp3_weights& w
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-k_dec_pair(const float* __restrict__ traj_norm, const float* __restrict__ z, unsigned long long seed,
+k_dec_pair(const float* __restrict__ traj_norm, const float* __restrict__ z, unsigned long long seed, const unsigned long long* __restrict__ rng_state,
            const float* __restrict__ rowpre, const int* __restrict__ row_scene, const float* __restrict__ origin, int rows,
            int K, int rpt, int Tp, int Tf, sttode_decompose_weights w0, sttode_decompose_weights w1,
            float* __restrict__ pred, float* __restrict__ recon) {
@@ -282,6 +282,7 @@ k_dec_pair(const float* __restrict__ traj_norm, const float* __restrict__ z, uns
     int* prow_s = reinterpret_cast<int*>(xy_s + BM * ldxy);   // [BM]
 
     const int tid = threadIdx.x;
+    if (rng_state) seed += *rng_state;
     const int row0 = blockIdx.x * rpt;
     const int nrow = min(rpt, rows - row0);
     const int np = nrow * K;                        // valid pairs in this tile
@@ -335,6 +336,8 @@ k_dec_pair(const float* __restrict__ traj_norm, const float* __restrict__ z, uns
         }
     }
 }
+
+__global__ void k_bump_counter(unsigned long long* p) { *p += 1ull; }
 
 size_t dec_pair_smem_bytes(int Tp, int Tf) {
     const int Tm = Tp > Tf ? Tp : Tf;

@@ -417,7 +417,7 @@ __device__ void epi_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, const 
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, unsigned long long seed,
+k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, unsigned long long seed, const unsigned long long* __restrict__ rng_state,
               const float* __restrict__ rowpre, const int* __restrict__ row_scene, const float* __restrict__ origin, int rows, int K,
               int rpt, int Tp, int Tf, sttode_decompose_weights w0, sttode_decompose_weights w1,
               const unsigned char* __restrict__ packed, const __grid_constant__ DecPackLayout lay, float* __restrict__ pred,
@@ -437,6 +437,7 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
     const int np = nrow * K;
     const int prow = m < np ? row0 + m / K : -1;
     const size_t pair0 = (size_t)row0 * K;
+    if (rng_state) seed += *rng_state;
     const int total_blocks = 34 * 3 + 8 * Tp + (recon ? 34 : 0);
     const int by0 = 34 + 8 * Tp;
 #ifdef STTODE_TC_TIMELINE

@@ -27,7 +27,8 @@ size_t ode_tail_smem_bytes();
 constexpr int ROWPRE_LD = 2048;     // per-row layer-1 partial sums: [P0x | P0y | P1y | P1x], 512 each
 __global__ void k_dec_row(const float* past_feature, const float* traj_norm, int rows, int Tp, sttode_decompose_weights w0,
                           sttode_decompose_weights w1, float* rowpre);
-__global__ void k_dec_pair(const float* traj_norm, const float* z, unsigned long long seed, const float* rowpre,
+__global__ void k_dec_pair(const float* traj_norm, const float* z, unsigned long long seed, const unsigned long long* rng_state,
+                           const float* rowpre,
                            const int* row_scene, const float* origin, int rows, int K, int rpt, int Tp, int Tf,
                            sttode_decompose_weights w0, sttode_decompose_weights w1, float* pred, float* recon);
 size_t dec_row_smem_bytes(int Tp);
@@ -47,7 +48,8 @@ struct DecPackLayout {               // byte offsets inside the packed weight bu
 DecPackLayout dec_pack_layout(int Tp, int Tf);
 __global__ void k_pack_image(const float* W, int ldw, int row0, int col0, int nvalid, int nrows, int K, unsigned char* hi,
                              unsigned char* lo);
-__global__ void k_dec_pair_tc(const float* traj_norm, const float* z, unsigned long long seed, const float* rowpre,
+__global__ void k_dec_pair_tc(const float* traj_norm, const float* z, unsigned long long seed, const unsigned long long* rng_state,
+                              const float* rowpre,
                               const int* row_scene, const float* origin, int rows, int K, int rpt, int Tp, int Tf,
                               sttode_decompose_weights w0, sttode_decompose_weights w1, const unsigned char* packed,
                               const __grid_constant__ DecPackLayout lay, float* pred, float* recon, int* status);
@@ -56,6 +58,8 @@ __global__ void k_dec_row_tc(const float* past_feature, const float* traj_norm, 
 size_t dec_row_tc_smem_bytes();
 size_t dec_pair_tc_smem_bytes(int Tp, int Tf);
 int dec_pair_tc_threads();
+
+__global__ void k_bump_counter(unsigned long long* p);
 
 // metrics.cu
 __global__ void k_min_ade_fde(const float* pred, const float* gt, int gt_layout, int rows, int K, int Tf, double* sums);

@@ -282,6 +282,63 @@ class Decoder(nn.Module):
         return out, recon
 
 
+class ForecastGraph:
+    """One `sttode_forecast` call captured as a CUDA graph for a fixed shape (the whole K-sample inference is then a single
+    graph launch: no per-kernel launch latency, no host work between kernels).  Inputs are copied into static buffers; the
+    latent draw reads a device counter that the graph itself bumps, so every replay samples fresh z (sttode.h: rng_state)."""
+
+    def __init__(self, model, rows, L, agents, n_scenes=0, layout=TRAJ_R2T, sample_k=None):
+        self.model, self.rows, self.L, self.agents, self.n_scenes, self.layout = model, rows, L, agents, n_scenes, layout
+        self.K = model.args.sample_k if sample_k is None else sample_k
+        dev = next(model.parameters()).device
+        Tp, Tf = model.args.past_length, model.args.future_length
+        lib = _lib.lib()
+        self.traj = torch.zeros(rows, 2, Tp, device=dev) if layout == TRAJ_R2T else torch.zeros(rows, Tp, 2, device=dev)
+        self.scene_ptr = torch.zeros(n_scenes + 1, dtype=torch.int32, device=dev) if n_scenes else None
+        self.row_scene = torch.zeros(rows, dtype=torch.int32, device=dev) if n_scenes else None
+        self.pred = torch.empty(rows, self.K, Tf, 2, device=dev)
+        self.past_feature = torch.empty(rows, 128, device=dev)
+        self.traj_norm = torch.empty(rows, Tp, 2, device=dev)
+        self.origin = torch.empty(max(n_scenes, 1), 2, device=dev)
+        self.ws = _lib.workspace(lib.sttode_forecast_workspace_bytes(rows, L, self.K, Tp), dev)
+        self.rng_state = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.seed = model._seed()
+        self.graph = None
+
+    def _launch(self):
+        mw = self.model._weights()
+        mw.rng_state = self.rng_state.data_ptr()
+        self._mw = mw
+        _lib.check(_lib.lib().sttode_forecast(_lib.dptr(self.traj), self.layout, _lib.dptr(self.scene_ptr), _lib.dptr(self.row_scene),
+                                              self.n_scenes, self.rows, self.L, self.agents, None, self.seed, self.K, C.byref(mw),
+                                              _lib.dptr(self.pred), _lib.dptr(self.past_feature), _lib.dptr(self.traj_norm),
+                                              _lib.dptr(self.origin), _lib.dptr(self.ws), self.ws.numel(), _lib.stream_ptr()))
+
+    def capture(self):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._launch()                       # warm-up outside the capture (packs the decoder weights, sets smem attributes)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._launch()
+        return self
+
+    @torch.no_grad()
+    def __call__(self, traj, scene_ptr=None):
+        self.traj.copy_(traj.reshape(self.traj.shape), non_blocking=True)
+        if self.n_scenes:
+            sp = scene_ptr.to(device=self.traj.device, dtype=torch.int32)
+            self.scene_ptr.copy_(sp, non_blocking=True)
+            counts = (sp[1:] - sp[:-1]).long()
+            self.row_scene.copy_(torch.repeat_interleave(torch.arange(self.n_scenes, device=sp.device, dtype=torch.int32), counts,
+                                                         output_size=self.rows))
+        self.graph.replay()
+        return self.pred
+
+
 class STTODENet(nn.Module):
     """model/STTODE.py:349-623."""
 
@@ -396,6 +453,10 @@ class STTODENet(nn.Module):
         if rs.numel() != rows:
             raise _lib.SttodeError("scene_ptr does not cover obs_traj")
         return self._forecast(obs, layout, sp, rs, n_scenes, rows, 1, 1, K)
+
+    def capture_forecast(self, rows, L, agents, n_scenes=0, layout=TRAJ_R2T, sample_k=None):
+        """CUDA-graph version of `forecast_scenes` (n_scenes > 0, L = 1) or of NBA-style inference (n_scenes = 0) for a fixed shape."""
+        return ForecastGraph(self, rows, L, agents, n_scenes, layout, sample_k).capture()
 
     # ---- training path: round 2 ---------------------------------------------------------------------
     def forward(self):

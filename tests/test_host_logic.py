@@ -36,7 +36,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(L.OdeWeights) == 16 * 8
     assert C.sizeof(L.EncoderWeights) == (9 + 16) * 8
     assert C.sizeof(L.DecomposeWeights) == (6 + 12) * 8
-    assert C.sizeof(L.ModelWeights) == 8 + (25 + 36 + 1) * 8
+    assert C.sizeof(L.ModelWeights) == 8 + (25 + 36 + 2) * 8
 
 
 def make_args(dataset="eth", tp=8, tf=12):
