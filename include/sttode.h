@@ -52,7 +52,9 @@ enum { STTODE_ODE_EULER = 0, STTODE_ODE_MIDPOINT = 1, STTODE_ODE_RK4 = 2 /* clas
 
 /* trajectory memory layouts */
 enum { STTODE_TRAJ_RT2 = 0 /* [rows, T, 2]  (NBA: data['past_traj'].view(B*N,T,2)) */,
-       STTODE_TRAJ_R2T = 1 /* [rows, 2, T]  (ETH/SDD loaders: obs_traj [N,2,T]) */ };
+       STTODE_TRAJ_R2T = 1 /* [rows, 2, T]  (ETH/SDD loaders: obs_traj [N,2,T]) */,
+       STTODE_FEAT_RT4 = 2 /* [rows, T, 4]  explicit [x, y, vx, vy] features (self.inputs / self.inputs_for_posterior):
+                               used as they are, no centring and no velocity recomputation */ };
 
 /* Hyp_mhsa parameters (hyptransformerlib.py:356-365): in_proj_weight [3E,E], in_proj_bias [3E], out_proj [E,E],[E] */
 typedef struct sttode_mhgsa_weights {
@@ -162,6 +164,15 @@ size_t sttode_past_encoder_workspace_bytes(int rows, int L);
 int sttode_past_encoder_fwd(const float *traj, int layout, const int *scene_ptr, const int *row_scene, int n_scenes,
                             int rows, int L, int agents, const sttode_model_weights *w, float *past_feature,
                             float *traj_norm, float *origin, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Generic encoder on explicit features: PastEncoder.forward (model/STTODE.py:214-236) or the shared front half of
+ * FutureEncoder.forward (:276-295) — input_fc, positional fc, flatten-T fc, category fc, tensor-ODE block, concat.
+ * feat4 [rows, T, 4]; rows ordered [batch][scene(L)][agent]; feature [rows,128] = [pre-ODE | ODE output]. */
+int sttode_encoder_fwd(const float *feat4, int rows, int L, int agents, int T, const sttode_encoder_weights *w, float *feature,
+                       void *workspace, size_t workspace_bytes, void *stream);
+/* y[rows,N] = act(x[rows,K] . W[N,K]^T + b): the two small heads of FutureEncoder (out_mlp 256->128 ReLU, qz_layer 128->64;
+ * model/STTODE.py:297-300).  K % 4 == 0, K <= 256, N % 64 == 0. */
+int sttode_linear(const float *x, const float *weight, const float *bias, float *y, int rows, int K, int N, int relu, void *stream);
 
 /* ---- Decoder.forward (model/STTODE.py:320-347) in 'inference' mode, both DecomposeBlocks (:51-77).
  * past_feature [rows,128] (one row per agent, NOT repeated K times), traj_norm [rows,T_p,2],

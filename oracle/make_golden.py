@@ -95,6 +95,21 @@ def main():
         rec[f"{name}_B"] = np.int64(B)
     np.savez_compressed(os.path.join(OUT, "inference_nba.npz"), **rec)
 
+    # ---- training objective (forward of train.py's step, eval mode so PE dropout is off): NBA shape, B = 4 -------------------
+    rec = {}
+    B, tp, tf = 4, 10, 20
+    mn = ref_model(ref, "nba", tp, tf, seed=2)
+    data = synth.nba_batch(1, B, 11, tp, tf)
+    gq = torch.Generator().manual_seed(21)
+    eps_q, eps_mid, eps_p = torch.randn(B * 11, 32, generator=gq), torch.randn(B * 11, 32, generator=gq), torch.randn(B * 11 * 20, 32, generator=gq)
+    queue = [eps_q, eps_mid, eps_p]
+    ref.sttode.Normal.rsample = lambda self: self.mu + queue.pop(0) * self.sigma
+    mn.set_data_nba(data)
+    total, lp, lr, lk, ld = mn.forward()
+    rec.update(total=np.float64(float(total)), pred=np.float64(lp), recover=np.float64(lr), kl=np.float64(lk), diverse=np.float64(ld),
+               qz=np32(mn.qz_param), B=np.int64(B))
+    np.savez_compressed(os.path.join(OUT, "training_objective.npz"), **rec)
+
     # ---- pmath ---------------------------------------------------------------------------------------
     P = ref.pmath
     rec = {}

@@ -184,6 +184,44 @@ def past_encoder(inputs, B, N, sd, prefix="past_encoder."):
     return torch.cat((x0, y), dim=-1).view(B * N, -1)
 
 
+def future_encoder(inputs_post, B, N, past_feature, sd, prefix="future_encoder."):
+    """FutureEncoder.forward (model/STTODE.py:276-300), eval mode -> q(z) parameters [B*N, 2*zdim]."""
+    x0 = encoder_prologue(inputs_post, B, N, sd, prefix)
+    y = ode_encoder(x0.unsqueeze(2), sd, prefix).squeeze(2)
+    ff = torch.cat((x0, y), dim=-1).view(B * N, -1)
+    h = torch.relu(F.linear(torch.cat((past_feature, ff), dim=-1), sd[prefix + "out_mlp.affine_layers.0.weight"],
+                            sd[prefix + "out_mlp.affine_layers.0.bias"]))
+    return F.linear(h, sd[prefix + "qz_layer.weight"], sd[prefix + "qz_layer.bias"])
+
+
+def posterior_inputs(past_traj, future_traj):
+    """inputs_for_posterior (model/STTODE.py:477-481): future positions and their velocities (first step from the last past position)."""
+    vel = future_traj - torch.cat([past_traj[:, [-1]], future_traj[:, :-1, :]], dim=1)
+    return torch.cat((future_traj, vel), dim=-1)
+
+
+def training_objective(sd, past_traj, future_traj, B, N, eps_q, eps_p, min_clip=2.0):
+    """STTODENet.forward (model/STTODE.py:553-568) in eval mode with the two live rsample draws injected
+    (eps_q [R,32] for q(z|x,y); eps_p [R*20,32] for the prior samples of the best-of-20 term).
+    Returns (total, pred, recover, kl, diverse) as python floats plus the q(z) parameters."""
+    R = B * N
+    pf = past_encoder(velocity_features(past_traj), B, N, sd)
+    qz = future_encoder(posterior_inputs(past_traj, future_traj), B, N, pf, sd)
+    mu, logvar = torch.chunk(qz, 2, dim=-1)
+    zq = mu + eps_q * torch.exp(0.5 * logvar)
+    cur = past_traj[:, [-1]]
+    pred, rec = decoder(pf, zq, past_traj, cur, 1, sd, mode="train")
+    Tf, Tp = future_traj.shape[1], past_traj.shape[1]
+    loss_pred = (future_traj - pred).pow(2).sum() / B / Tf
+    loss_rec = (past_traj - rec).pow(2).sum() / B / Tp
+    kl = 0.5 * ((mu / (1 + 1e-8)) ** 2 + (torch.exp(0.5 * logvar) / (1 + 1e-8)) ** 2) - 0.5 - torch.log(torch.exp(0.5 * logvar) / (1 + 1e-8))
+    loss_kl = (kl.sum() / (B * N)).clamp_min(min_clip)
+    div, _ = decoder(pf.repeat_interleave(20, dim=0), eps_p, past_traj, cur, 20, sd, mode="inference")      # [R,20,Tf,2]
+    loss_div = (future_traj.unsqueeze(1) - div).pow(2).sum(dim=-1).sum(dim=-1).min(dim=1)[0].mean()
+    total = loss_pred + loss_rec + loss_kl + loss_div
+    return dict(total=float(total), pred=float(loss_pred), recover=float(loss_rec), kl=float(loss_kl), diverse=float(loss_div), qz=qz)
+
+
 # --------------------------------------------------------------------------------------------------
 # decoder  (model/STTODE.py:16-77, 302-347; model/utils.py:67-95)
 # --------------------------------------------------------------------------------------------------

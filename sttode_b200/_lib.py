@@ -61,6 +61,8 @@ SIGNATURES = {
     "sttode_hypattention_fwd": (_I, [_V, C.POINTER(OdeWeights), _V, _I, _I, _V, _Z, _V]),
     "sttode_past_encoder_workspace_bytes": (_Z, [_I, _I]),
     "sttode_past_encoder_fwd": (_I, [_V, _I, _V, _V, _I, _I, _I, _I, C.POINTER(ModelWeights), _V, _V, _V, _V, _Z, _V]),
+    "sttode_encoder_fwd": (_I, [_V, _I, _I, _I, _I, C.POINTER(EncoderWeights), _V, _V, _Z, _V]),
+    "sttode_linear": (_I, [_V, _V, _V, _V, _I, _I, _I, _I, _V]),
     "sttode_decoder_workspace_bytes": (_Z, [_I, _I]),
     "sttode_decoder_fwd": (_I, [_V, _V, _V, _U64, _V, _V, _I, _I, C.POINTER(ModelWeights), _V, _V, _V, _Z, _V]),
     "sttode_decoder_pack_bytes": (_Z, [_I, _I]),

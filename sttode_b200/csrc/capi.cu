@@ -236,13 +236,20 @@ int check_model(const sttode_model_weights* w, bool need_enc = true, bool need_d
 }
 
 size_t past_encoder_ws(int rows, int L) { return ode_ws_bytes(rows, L, STTODE_ODE_EULER); }
-size_t decoder_ws(int rows) { return align_up((size_t)rows * ROWPRE_LD * 4); }
+size_t decoder_ws(int rows) { return align_up((size_t)rows * ROWPRE_LD * 4) + align_up(((size_t)rows / 1 + 256) * 4); }
+
+int run_encoder(const float* traj, int layout, const int* scene_ptr, const int* row_scene, int n_scenes, int rows, int L, int agents, int T,
+                const sttode_encoder_weights& ew, float* past_feature, float* traj_norm, float* origin, Carver ws, cudaStream_t st);
 
 int run_past_encoder(const float* traj, int layout, const int* scene_ptr, const int* row_scene, int n_scenes, int rows, int L,
                      int agents, const sttode_model_weights* w, float* past_feature, float* traj_norm, float* origin, Carver ws,
                      cudaStream_t st) {
+    return run_encoder(traj, layout, scene_ptr, row_scene, n_scenes, rows, L, agents, w->past_length, w->past, past_feature, traj_norm, origin, ws, st);
+}
+
+int run_encoder(const float* traj, int layout, const int* scene_ptr, const int* row_scene, int n_scenes, int rows, int L, int agents, int T,
+                const sttode_encoder_weights& ew, float* past_feature, float* traj_norm, float* origin, Carver ws, cudaStream_t st) {
     int rc;
-    const int T = w->past_length;
     if (rows <= 0) return fail(STTODE_EINVAL, "rows must be positive");
     if (scene_ptr) {
         if (L != 1) return fail(STTODE_EINVAL, "scene_ptr (ETH/SDD semantics) requires L == 1");
@@ -254,7 +261,7 @@ int run_past_encoder(const float* traj, int layout, const int* scene_ptr, const 
     }
     const size_t sm = prologue_smem_bytes(T);
     if ((rc = set_smem(k_prologue, sm, "k_prologue"))) return rc;
-    k_prologue<<<ceil_div(rows, BM), NTHREADS, sm, st>>>(traj, layout, scene_ptr, row_scene, origin, rows, agents, T, w->past, past_feature, 128, traj_norm);
+    k_prologue<<<ceil_div(rows, BM), NTHREADS, sm, st>>>(traj, layout, scene_ptr, row_scene, origin, rows, agents, T, ew, past_feature, 128, traj_norm);
     LAUNCH_CHECK("k_prologue");
     const int nb = scene_ptr ? rows : rows / (L * agents);
     const int bsz = scene_ptr ? 1 : agents;
@@ -263,14 +270,14 @@ int run_past_encoder(const float* traj, int layout, const int* scene_ptr, const 
     if (L == 1) {
         if ((rc = set_smem(k_ode_tail, ode_tail_smem_bytes(), "k_ode_tail"))) return rc;
         k_ode_tail<<<ceil_div(rows, BM), NTHREADS, ode_tail_smem_bytes(), st>>>(past_feature, 128, nullptr, 0, past_feature, 128, 12.f, 1,
-                                                                                past_feature + 64, 128, rows, w->past.ode, 0);
+                                                                                past_feature + 64, 128, rows, ew.ode, 0);
         LAUNCH_CHECK("k_ode_tail");
         return 0;
     }
     float* x0 = ws.take<float>((size_t)rows * 64);
     if (!x0) return fail(STTODE_EWORKSPACE, "workspace too small for x0");
     CUDA_TRY(cudaMemcpy2DAsync(x0, 64 * 4, past_feature, 128 * 4, 64 * 4, rows, cudaMemcpyDeviceToDevice, st));
-    return run_ode_block(x0, L, bsz, nb, w->past.ode, 1, 12.f, STTODE_ODE_EULER, 1, past_feature + 64, 128, ws, st);
+    return run_ode_block(x0, L, bsz, nb, ew.ode, 1, 12.f, STTODE_ODE_EULER, 1, past_feature + 64, 128, ws, st);
 }
 
 int run_decoder(const float* past_feature, const float* traj_norm, const float* z, unsigned long long seed, const int* row_scene,
@@ -279,49 +286,57 @@ int run_decoder(const float* past_feature, const float* traj_norm, const float* 
     int rc;
     if (K < 1 || K > BM) return fail(STTODE_EINVAL, "sample_k must be in [1, %d]", BM);
     const int Tp = w->past_length, Tf = w->future_length;
+    const int rpt = BM / K, row_tiles = ceil_div(rows, BM), pair_tiles = ceil_div(rows, rpt);
     float* rowpre = ws.take<float>((size_t)rows * ROWPRE_LD);
     if (!rowpre) return fail(STTODE_EWORKSPACE, "workspace too small for decoder row precompute");
     const size_t sm_row = dec_row_smem_bytes(Tp), sm_pair = dec_pair_smem_bytes(Tp, Tf);
     if ((rc = set_smem(k_dec_row, sm_row, "k_dec_row"))) return rc;
     if ((rc = set_smem(k_dec_pair, sm_pair, "k_dec_pair"))) return rc;
-    if (w->dec_packed) {
-        if ((rc = set_smem(k_dec_row_tc, dec_row_tc_smem_bytes(), "k_dec_row_tc"))) return rc;
-        k_dec_row_tc<<<ceil_div(rows, BM), dec_pair_tc_threads(), dec_row_tc_smem_bytes(), st>>>(past_feature, traj_norm, rows, Tp, w->dec[0], w->dec[1],
-                                                                                                   (const unsigned char*)w->dec_packed, dec_pack_layout(Tp, Tf), rowpre);
-        LAUNCH_CHECK("k_dec_row_tc");
-    } else {
-        k_dec_row<<<ceil_div(rows, BM), NTHREADS, sm_row, st>>>(past_feature, traj_norm, rows, Tp, w->dec[0], w->dec[1], rowpre);
+    const unsigned long long* rng = z ? nullptr : w->rng_state;
+    const int* rs = origin ? row_scene : nullptr;
+    if (!w->dec_packed) {                           // FP32-FFMA decoder
+        k_dec_row<<<row_tiles, NTHREADS, sm_row, st>>>(past_feature, traj_norm, rows, Tp, w->dec[0], w->dec[1], rowpre, nullptr);
         LAUNCH_CHECK("k_dec_row");
-    }
-    const int rpt = BM / K;
-    const size_t sm_tc = dec_pair_tc_smem_bytes(Tp, Tf);
-    if (w->dec_packed && (rc = set_smem(k_dec_pair_tc, sm_tc, "k_dec_pair_tc"))) return rc;
-    std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
-    if (g_prof.on) {
-        std::lock_guard<std::mutex> lock(g_prof.mu);
-        if (!g_prof.pool.empty()) { ev = g_prof.pool.back(); g_prof.pool.pop_back(); }
-        else { CUDA_TRY(cudaEventCreate(&ev.first)); CUDA_TRY(cudaEventCreate(&ev.second)); }
-        CUDA_TRY(cudaEventRecord(ev.first, st));
-    }
-    if (w->dec_packed) {
+        k_dec_pair<<<pair_tiles, NTHREADS, sm_pair, st>>>(traj_norm, z, seed, rng, rowpre, rs, origin, rows, K, rpt, Tp, Tf, w->dec[0], w->dec[1], pred,
+                                                          recon, nullptr);
+        LAUNCH_CHECK("k_dec_pair");
+    } else {
+        // Tensor-core decoder.  Its fp16 hi/lo operands cover |v| < 65504; a tile that stages anything larger raises its flag and is
+        // recomputed by the FP32 kernel right after (a CTA of the redo launch exits at once when its flag is clear).
         const DecPackLayout lay = dec_pack_layout(Tp, Tf);
         const unsigned char* pk = (const unsigned char*)w->dec_packed;
-        k_dec_pair_tc<<<ceil_div(rows, rpt), dec_pair_tc_threads(), sm_tc, st>>>(traj_norm, z, seed, z ? nullptr : w->rng_state, rowpre, origin ? row_scene : nullptr, origin, rows, K, rpt,
-                                                                    Tp, Tf, w->dec[0], w->dec[1], pk, lay, pred, recon, (int*)(pk + lay.total));
+        const size_t sm_tc = dec_pair_tc_smem_bytes(Tp, Tf), sm_rtc = dec_row_tc_smem_bytes();
+        if ((rc = set_smem(k_dec_row_tc, sm_rtc, "k_dec_row_tc"))) return rc;
+        if ((rc = set_smem(k_dec_pair_tc, sm_tc, "k_dec_pair_tc"))) return rc;
+        int* flags = ws.take<int>((size_t)row_tiles + pair_tiles);
+        if (!flags) return fail(STTODE_EWORKSPACE, "workspace too small for decoder tile flags");
+        CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int) * ((size_t)row_tiles + pair_tiles), st));
+        k_dec_row_tc<<<row_tiles, dec_pair_tc_threads(), sm_rtc, st>>>(past_feature, traj_norm, rows, Tp, w->dec[0], w->dec[1], pk, lay, rowpre, flags);
+        LAUNCH_CHECK("k_dec_row_tc");
+        k_dec_row<<<row_tiles, NTHREADS, sm_row, st>>>(past_feature, traj_norm, rows, Tp, w->dec[0], w->dec[1], rowpre, flags);
+        LAUNCH_CHECK("k_dec_row(redo)");
+        std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+        if (g_prof.on) {
+            std::lock_guard<std::mutex> lock(g_prof.mu);
+            if (!g_prof.pool.empty()) { ev = g_prof.pool.back(); g_prof.pool.pop_back(); }
+            else { CUDA_TRY(cudaEventCreate(&ev.first)); CUDA_TRY(cudaEventCreate(&ev.second)); }
+            CUDA_TRY(cudaEventRecord(ev.first, st));
+        }
+        k_dec_pair_tc<<<pair_tiles, dec_pair_tc_threads(), sm_tc, st>>>(traj_norm, z, seed, rng, rowpre, rs, origin, rows, K, rpt, Tp, Tf, w->dec[0],
+                                                                        w->dec[1], pk, lay, pred, recon, (int*)(pk + lay.total), flags + row_tiles);
         LAUNCH_CHECK("k_dec_pair_tc");
-    } else {
-        k_dec_pair<<<ceil_div(rows, rpt), NTHREADS, sm_pair, st>>>(traj_norm, z, seed, z ? nullptr : w->rng_state, rowpre, origin ? row_scene : nullptr, origin, rows, K, rpt, Tp,
-                                                                  Tf, w->dec[0], w->dec[1], pred, recon);
-        LAUNCH_CHECK("k_dec_pair");
+        if (ev.first) {
+            std::lock_guard<std::mutex> lock(g_prof.mu);
+            CUDA_TRY(cudaEventRecord(ev.second, st));
+            g_prof.used.push_back(ev);
+        }
+        k_dec_pair<<<pair_tiles, NTHREADS, sm_pair, st>>>(traj_norm, z, seed, rng, rowpre, rs, origin, rows, K, rpt, Tp, Tf, w->dec[0], w->dec[1], pred,
+                                                          recon, flags + row_tiles);
+        LAUNCH_CHECK("k_dec_pair(redo)");
     }
-    if (!z && w->rng_state) {
+    if (rng) {
         k_bump_counter<<<1, 1, 0, st>>>(w->rng_state);
         LAUNCH_CHECK("k_bump_counter");
-    }
-    if (ev.first) {
-        std::lock_guard<std::mutex> lock(g_prof.mu);
-        CUDA_TRY(cudaEventRecord(ev.second, st));
-        g_prof.used.push_back(ev);
     }
     return 0;
 }
@@ -462,6 +477,26 @@ int sttode_past_encoder_fwd(const float* traj, int layout, const int* scene_ptr,
     if (!traj || !past_feature) return fail(STTODE_EINVAL, "null pointer");
     return run_past_encoder(traj, layout, scene_ptr, row_scene, n_scenes, rows, L, agents, w, past_feature, traj_norm, origin,
                             Carver(workspace, workspace_bytes), (cudaStream_t)stream);
+}
+
+int sttode_encoder_fwd(const float* feat4, int rows, int L, int agents, int T, const sttode_encoder_weights* w, float* feature, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+    if (!feat4 || !w || !feature) return fail(STTODE_EINVAL, "null pointer");
+    if (T < 1 || T > 200) return fail(STTODE_EINVAL, "T must be in [1, 200]");
+    const void* const* p = (const void* const*)w;
+    for (size_t i = 0; i < sizeof(*w) / sizeof(void*); ++i) if (!p[i]) return fail(STTODE_EINVAL, "encoder weight pointer %zu is null", i);
+    return run_encoder(feat4, STTODE_FEAT_RT4, nullptr, nullptr, 0, rows, L, agents, T, *w, feature, nullptr, nullptr, Carver(workspace, workspace_bytes),
+                       (cudaStream_t)stream);
+}
+
+int sttode_linear(const float* x, const float* weight, const float* bias, float* y, int rows, int K, int N, int relu, void* stream) {
+    int rc;
+    if (!x || !weight || !bias || !y || rows < 1) return fail(STTODE_EINVAL, "linear: bad argument");
+    if (K < 4 || K > 256 || K % 4 || N < 64 || N % 64) return fail(STTODE_EUNSUPPORTED, "linear: K %% 4 == 0, K <= 256, N %% 64 == 0 (got K=%d N=%d)", K, N);
+    if ((rc = set_smem(k_linear, linear_smem_bytes(K), "k_linear"))) return rc;
+    k_linear<<<ceil_div(rows, BM), NTHREADS, linear_smem_bytes(K), (cudaStream_t)stream>>>(x, rows, K, weight, bias, N, relu, y);
+    LAUNCH_CHECK("k_linear");
+    return 0;
 }
 
 size_t sttode_decoder_workspace_bytes(int rows, int sample_k) { (void)sample_k; return decoder_ws(rows) + 1024; }

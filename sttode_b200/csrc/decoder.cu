@@ -119,8 +119,9 @@ __device__ void gru_phase(const float* d_s, int ldd, int T, const sttode_decompo
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_dec_row(const float* __restrict__ past_feature, const float* __restrict__ traj_norm, int rows, int Tp,
-          sttode_decompose_weights w0, sttode_decompose_weights w1, float* __restrict__ rowpre) {
+          sttode_decompose_weights w0, sttode_decompose_weights w1, float* __restrict__ rowpre, const int* __restrict__ only_flagged) {
     extern __shared__ __align__(16) float smem[];
+    if (only_flagged && !only_flagged[blockIdx.x]) return;      // fp32 redo of the tiles the tensor-core kernel flagged (fp16 range)
     const int ldd = 2 * Tp + 1;
     float* hA = smem;                          // [BM][LDH]  final state
     float* scratch = hA + BM * LDH;            // GRU: hB | xt | wch      P-phase: pf_s | wbuf
@@ -266,8 +267,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 k_dec_pair(const float* __restrict__ traj_norm, const float* __restrict__ z, unsigned long long seed, const unsigned long long* __restrict__ rng_state,
            const float* __restrict__ rowpre, const int* __restrict__ row_scene, const float* __restrict__ origin, int rows,
            int K, int rpt, int Tp, int Tf, sttode_decompose_weights w0, sttode_decompose_weights w1,
-           float* __restrict__ pred, float* __restrict__ recon) {
+           float* __restrict__ pred, float* __restrict__ recon, const int* __restrict__ only_flagged) {
     extern __shared__ __align__(16) float smem[];
+    if (only_flagged && !only_flagged[blockIdx.x]) return;
     const int Tm = Tp > Tf ? Tp : Tf;
     const int ldxy = 2 * Tm + 1;
     float* zA = smem;                               // [BM][LDZ]: z | block-1 GRU state

@@ -248,9 +248,21 @@ __device__ void issuer_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, int
 }
 
 // ================================================================ epilogue (256 threads) ===================
+// fp16 operands overflow at 65504: any staged activation beyond FP16_SAFE marks the tile, and the FP32-FFMA kernel redoes it
+constexpr float FP16_SAFE = 60000.f;
+template <int N>
+__device__ __forceinline__ void track_range(const float (&v)[N], int& ovf) {
+    float mx = 0.f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) mx = fmaxf(mx, fabsf(v[i]));
+    ovf |= !(mx <= FP16_SAFE);                      // also true for NaN/inf
+}
+
 // stage the 32 values (four k chunks) of one row of the chunk operand H[b]; prev_parity = phase of the MMA that read
 // the previous contents of H[b]
-__device__ __forceinline__ void stage_h32(unsigned char* sm, uint64_t* bars, int b, int m, const float (&v)[32], bool first, uint32_t prev_parity) {
+__device__ __forceinline__ void stage_h32(unsigned char* sm, uint64_t* bars, int b, int m, const float (&v)[32], bool first, uint32_t prev_parity,
+                                          int& ovf) {
+    track_range(v, ovf);
     if (!first) tc_wait(bars, B_HFREE + b, prev_parity);
     unsigned char* hb = sm + SM_H + b * 16384;
 #pragma unroll
@@ -281,7 +293,7 @@ __device__ __forceinline__ void load_rowbias32(float (&rb)[32], const float* __r
 // the chunks / pieces with index parity wh, all 32 columns, so two chunks are in flight in the epilogue at any time.
 __device__ void epi_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int n3, int n3p, bool first_mlp, const float* __restrict__ rowpre,
                         int prow, const float* __restrict__ b1, const float* __restrict__ b2, float* xy_s, int ldxy, bool accumulate,
-                        uint32_t& n_acc) {
+                        uint32_t& n_acc, int& ovf) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wq = warp & 3, wh = warp >> 2;
     const int m = wq * 32 + lane;
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
@@ -300,7 +312,7 @@ __device__ void epi_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int n3
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + rb[i], 0.f);
         // fill j = 12*k + ch/2 of H[wh]: wait for the reader of fill j-1
-        stage_h32(sm, bars, wh, m, v, first_mlp && ch < 2, (uint32_t)(((ch >> 1) + 1) & 1));
+        stage_h32(sm, bars, wh, m, v, first_mlp && ch < 2, (uint32_t)(((ch >> 1) + 1) & 1), ovf);
         TLOG(tl, 10 + (ch - 4) * 5 + 3);
     }
     tc_wait(bars, B_ACC, n_acc & 1);                // D2 complete
@@ -312,7 +324,7 @@ __device__ void epi_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int n3
         tc::tmem_ld32(tmem + lane_base + COL_D2 + p * 32, v);
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + __ldg(b1 + p * 32 + i), 0.f);
-        stage_h32(sm, bars, wh, m, v, false, (uint32_t)(((p >> 1) + 1) & 1));             // fill 12k + 8 + p/2
+        stage_h32(sm, bars, wh, m, v, false, (uint32_t)(((p >> 1) + 1) & 1), ovf);        // fill 12k + 8 + p/2
     }
     tc_wait(bars, B_ACC, n_acc & 1);                // D3 complete
     ++n_acc;
@@ -340,7 +352,7 @@ __device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.
 // Conv1d+ReLU -> GRU over T steps; conv input d = xy_s; final state left in A1 k 32..127 (fp16 hi/lo images).
 // gb: shared-memory constants [brz 192 | bin 96 | bhn 96 | conv_w 192 | conv_b 32]
 __device__ void epi_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, const float* gb, const float* xy_s, int ldxy, int valid_rows, int T,
-                        uint32_t& n_acc) {
+                        uint32_t& n_acc, int& ovf) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wq = warp & 3, wh = warp >> 2;
     const int m = wq * 32 + lane;
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
@@ -378,6 +390,7 @@ __device__ void epi_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, const 
                 for (int e = 0; e < 6; ++e) a = fmaf(cw[chn * 6 + e], d[e], a);
                 v[i] = fmaxf(a, 0.f);
             }
+            track_range(v, ovf);
             tc::store_split8(sm + SM_H, sm + SM_H + 8192, 128, m, wh * 2 + half, v);
         }
         const bool tl = (t == 2 && tid == 0);
@@ -421,7 +434,7 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
               const float* __restrict__ rowpre, const int* __restrict__ row_scene, const float* __restrict__ origin, int rows, int K,
               int rpt, int Tp, int Tf, sttode_decompose_weights w0, sttode_decompose_weights w1,
               const unsigned char* __restrict__ packed, const __grid_constant__ DecPackLayout lay, float* __restrict__ pred,
-              float* __restrict__ recon, int* __restrict__ status) {
+              float* __restrict__ recon, int* __restrict__ status, int* __restrict__ tile_flags) {
     extern __shared__ __align__(128) unsigned char sm[];
     const int Tm = Tp > Tf ? Tp : Tf;
     const int ldxy = 2 * Tm + 1;
@@ -437,6 +450,7 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
     const int np = nrow * K;
     const int prow = m < np ? row0 + m / K : -1;
     const size_t pair0 = (size_t)row0 * K;
+    int ovf = 0;                                    // set when a staged fp16 operand would leave the fp16 range
     if (rng_state) seed += *rng_state;
     const int total_blocks = 34 * 3 + 8 * Tp + (recon ? 34 : 0);
     const int by0 = 34 + 8 * Tp;
@@ -482,6 +496,7 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = 0.f;
             }
+            track_range(v, ovf);
             tc::store_split8(sm + SM_A1, sm + SM_A1 + 32768, 128, m, kc, v);
         }
     }
@@ -502,7 +517,7 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
         if (recon) issuer_mlp(sm, bars, tmem, 128, (int)lay.n3p[3], by0 + 68, n_d3);
     } else {                                        // ---------------- epilogue warps
         uint32_t n_acc = 0;
-        epi_mlp(sm, bars, tmem, 2 * Tp, (int)lay.n3p[0], true, rowpre + 0, prow, w0.dec_x.b1, w0.dec_x.b2, xy_s, ldxy, false, n_acc);
+        epi_mlp(sm, bars, tmem, 2 * Tp, (int)lay.n3p[0], true, rowpre + 0, prow, w0.dec_x.b1, w0.dec_x.b2, xy_s, ldxy, false, n_acc, ovf);
         if (recon)
             for (int idx = tid; idx < np * 2 * Tp; idx += EPI_THREADS) {
                 const int mm = idx / (2 * Tp), e = idx - mm * 2 * Tp;
@@ -514,10 +529,10 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
             xy_s[mm * ldxy + e] = r >= 0 ? traj_norm[(size_t)r * 2 * Tp + e] - xy_s[mm * ldxy + e] : 0.f;
         }
         epi_barrier();
-        epi_gru(sm, bars, tmem, gb, xy_s, ldxy, BM, Tp, n_acc);
+        epi_gru(sm, bars, tmem, gb, xy_s, ldxy, BM, Tp, n_acc, ovf);
         epi_barrier();                              // every thread is done reading the conv input before y0 overwrites xy_s
-        epi_mlp(sm, bars, tmem, 2 * Tf, (int)lay.n3p[1], false, rowpre + 512, prow, w0.dec_y.b1, w0.dec_y.b2, xy_s, ldxy, false, n_acc);
-        epi_mlp(sm, bars, tmem, 2 * Tf, (int)lay.n3p[2], false, rowpre + 1024, prow, w1.dec_y.b1, w1.dec_y.b2, xy_s, ldxy, true, n_acc);
+        epi_mlp(sm, bars, tmem, 2 * Tf, (int)lay.n3p[1], false, rowpre + 512, prow, w0.dec_y.b1, w0.dec_y.b2, xy_s, ldxy, false, n_acc, ovf);
+        epi_mlp(sm, bars, tmem, 2 * Tf, (int)lay.n3p[2], false, rowpre + 1024, prow, w1.dec_y.b1, w1.dec_y.b2, xy_s, ldxy, true, n_acc, ovf);
         for (int idx = tid; idx < np * 2 * Tf; idx += EPI_THREADS) {
             const int mm = idx / (2 * Tf), e = idx - mm * 2 * Tf, cc = e & 1;
             const int r = row0 + mm / K;
@@ -527,13 +542,14 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
         }
         if (recon) {
             epi_barrier();
-            epi_mlp(sm, bars, tmem, 2 * Tp, (int)lay.n3p[3], false, rowpre + 1536, prow, w1.dec_x.b1, w1.dec_x.b2, xy_s, ldxy, false, n_acc);
+            epi_mlp(sm, bars, tmem, 2 * Tp, (int)lay.n3p[3], false, rowpre + 1536, prow, w1.dec_x.b1, w1.dec_x.b2, xy_s, ldxy, false, n_acc, ovf);
             for (int idx = tid; idx < np * 2 * Tp; idx += EPI_THREADS) {
                 const int mm = idx / (2 * Tp), e = idx - mm * 2 * Tp;
                 recon[(pair0 + mm) * 2 * Tp + e] += xy_s[mm * ldxy + e];
             }
         }
     }
+    if (ovf) tile_flags[blockIdx.x] = 1;
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 8) tc::tmem_dealloc(tmem, 512);
@@ -558,8 +574,9 @@ __device__ __forceinline__ void row_block_src(const DecPackLayout& lay, int Tp, 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_dec_row_tc(const float* __restrict__ past_feature, const float* __restrict__ traj_norm, int rows, int Tp, sttode_decompose_weights w0,
              sttode_decompose_weights w1, const unsigned char* __restrict__ packed, const __grid_constant__ DecPackLayout lay,
-             float* __restrict__ rowpre) {
+             float* __restrict__ rowpre, int* __restrict__ tile_flags) {
     extern __shared__ __align__(128) unsigned char sm[];
+    int ovf = 0;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SMR_BARS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT + 1);
     float* gb = reinterpret_cast<float*>(bars + B_COUNT + 3);
@@ -622,7 +639,7 @@ k_dec_row_tc(const float* __restrict__ past_feature, const float* __restrict__ t
         }
     } else {                                        // ---------------- epilogue warps
         uint32_t n_acc = 0;
-        epi_gru(sm, bars, tmem, gb, traj_norm + (size_t)row0 * 2 * Tp, 2 * Tp, nrow, Tp, n_acc);
+        epi_gru(sm, bars, tmem, gb, traj_norm + (size_t)row0 * 2 * Tp, 2 * Tp, nrow, Tp, n_acc, ovf);
         // past_feature tile -> fp16 hi/lo images (k chunks 8*wh .. 8*wh+7 of row m); safe: every GRU MMA has completed
         {
             const int r = row0 + m;
@@ -638,6 +655,7 @@ k_dec_row_tc(const float* __restrict__ past_feature, const float* __restrict__ t
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] = 0.f;
                 }
+                track_range(v, ovf);
                 tc::store_split8(sm + SMR_PFHI, sm + SMR_PFLO, 128, m, kc, v);
             }
         }
@@ -667,6 +685,7 @@ k_dec_row_tc(const float* __restrict__ past_feature, const float* __restrict__ t
             if (lane == 0) mbar_arrive(bars + B_HFULL + b);
         }
     }
+    if (ovf) tile_flags[blockIdx.x] = 1;
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 8) tc::tmem_dealloc(tmem, 512);

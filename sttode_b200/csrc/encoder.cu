@@ -58,6 +58,14 @@ k_prologue(const float* __restrict__ traj, int layout, const int* __restrict__ s
     const int row0 = blockIdx.x * BM;
 
     // positions (scene-normalised) and the category flag
+    if (layout == STTODE_FEAT_RT4) {       // explicit [x, y, vx, vy] features: copy the tile as it is
+        for (int idx = tid; idx < BM * T; idx += NTHREADS) {
+            const int m = idx / T, t = idx - m * T, r = row0 + m;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < rows) v = *reinterpret_cast<const float4*>(traj + ((size_t)r * T + t) * 4);
+            *reinterpret_cast<float4*>(in_s + m * ldin + t * 4) = v;
+        }
+    } else
     for (int idx = tid; idx < BM * T; idx += NTHREADS) {
         const int m = idx / T, t = idx - m * T, r = row0 + m;
         float px = 0.f, py = 0.f;
@@ -85,6 +93,7 @@ k_prologue(const float* __restrict__ traj, int layout, const int* __restrict__ s
     }
     __syncthreads();
     // velocities from the normalised positions, first step duplicated (model/STTODE.py:588-589)
+    if (layout != STTODE_FEAT_RT4)
     for (int idx = tid; idx < BM * T; idx += NTHREADS) {
         const int m = idx / T, t = idx - m * T;
         const int t1 = t == 0 ? 1 : t, t0 = t1 - 1;
@@ -431,6 +440,41 @@ k_ode_tail(const float* __restrict__ x, int ldx, const float* __restrict__ attn_
 }
 
 size_t ode_tail_smem_bytes() { return sizeof(float) * ((size_t)3 * BM * LDS64 + 2 * 64 * LDS64); }
+
+// y[rows,N] = act(x[rows,K] . W[N,K]^T + b): small dense heads (K <= 256, K % 4 == 0, N % 64 == 0)
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_linear(const float* __restrict__ X, int rows, int K, const float* __restrict__ W, const float* __restrict__ b, int N, int relu,
+         float* __restrict__ Y) {
+    extern __shared__ __align__(16) float smem[];
+    const int lda = K + PAD;
+    float* xs = smem;                      // [BM][K+4]
+    float* wbuf = xs + BM * lda;           // [2][64][36]
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int row0 = blockIdx.x * BM, kv = K >> 2;
+    for (int idx = tid; idx < BM * kv; idx += NTHREADS) {
+        const int m = idx / kv, c4 = (idx - m * kv) << 2, r = row0 + m;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < rows) v = *reinterpret_cast<const float4*>(X + (size_t)r * K + c4);
+        *reinterpret_cast<float4*>(xs + m * lda + c4) = v;
+    }
+    for (int nb = 0; nb < N / 64; ++nb) {
+        float acc[8][4];
+        zero_acc(acc);
+        gemm_step<4, 32>(acc, xs, lda, W + (size_t)nb * 64 * K, K, K, wbuf);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = row0 + i * 16 + ty;
+            if (r >= rows) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = nb * 64 + j * 16 + tx;
+                const float v = acc[i][j] + __ldg(b + n);
+                Y[(size_t)r * N + n] = relu ? fmaxf(v, 0.f) : v;
+            }
+        }
+    }
+}
+size_t linear_smem_bytes(int K) { return sizeof(float) * ((size_t)BM * (K + PAD) + 2 * 64 * (32 + PAD)); }
 
 // out = base + sum_i coef[i] * k_i  (explicit Runge-Kutta stage combinations), optional relu.
 __global__ void k_lincomb(const float* __restrict__ base, int ldb, const float* __restrict__ k0, const float* __restrict__ k1,

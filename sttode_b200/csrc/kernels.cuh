@@ -19,6 +19,8 @@ __global__ void k_ode_tail(const float* x, int ldx, const float* attn_o, int ldo
                            int relu, float* out, int ldout, int rows, sttode_ode_weights w, int gate_only);
 __global__ void k_lincomb(const float* base, int ldb, const float* k0, const float* k1, const float* k2, const float* k3,
                           float c0, float c1, float c2, float c3, int relu, float* out, int ldout, int rows);
+__global__ void k_linear(const float* X, int rows, int K, const float* W, const float* b, int N, int relu, float* Y);
+size_t linear_smem_bytes(int K);
 size_t prologue_smem_bytes(int T);
 size_t proj_smem_bytes();
 size_t ode_tail_smem_bytes();
@@ -26,11 +28,11 @@ size_t ode_tail_smem_bytes();
 // decoder.cu
 constexpr int ROWPRE_LD = 2048;     // per-row layer-1 partial sums: [P0x | P0y | P1y | P1x], 512 each
 __global__ void k_dec_row(const float* past_feature, const float* traj_norm, int rows, int Tp, sttode_decompose_weights w0,
-                          sttode_decompose_weights w1, float* rowpre);
+                          sttode_decompose_weights w1, float* rowpre, const int* only_flagged);
 __global__ void k_dec_pair(const float* traj_norm, const float* z, unsigned long long seed, const unsigned long long* rng_state,
                            const float* rowpre,
                            const int* row_scene, const float* origin, int rows, int K, int rpt, int Tp, int Tf,
-                           sttode_decompose_weights w0, sttode_decompose_weights w1, float* pred, float* recon);
+                           sttode_decompose_weights w0, sttode_decompose_weights w1, float* pred, float* recon, const int* only_flagged);
 size_t dec_row_smem_bytes(int Tp);
 size_t dec_pair_smem_bytes(int Tp, int Tf);
 
@@ -52,9 +54,9 @@ __global__ void k_dec_pair_tc(const float* traj_norm, const float* z, unsigned l
                               const float* rowpre,
                               const int* row_scene, const float* origin, int rows, int K, int rpt, int Tp, int Tf,
                               sttode_decompose_weights w0, sttode_decompose_weights w1, const unsigned char* packed,
-                              const __grid_constant__ DecPackLayout lay, float* pred, float* recon, int* status);
+                              const __grid_constant__ DecPackLayout lay, float* pred, float* recon, int* status, int* tile_flags);
 __global__ void k_dec_row_tc(const float* past_feature, const float* traj_norm, int rows, int Tp, sttode_decompose_weights w0,
-                             sttode_decompose_weights w1, const unsigned char* packed, const __grid_constant__ DecPackLayout lay, float* rowpre);
+                             sttode_decompose_weights w1, const unsigned char* packed, const __grid_constant__ DecPackLayout lay, float* rowpre, int* tile_flags);
 size_t dec_row_tc_smem_bytes();
 size_t dec_pair_tc_smem_bytes(int Tp, int Tf);
 int dec_pair_tc_threads();

@@ -139,25 +139,35 @@ class PastEncoder(_EncoderBase):
         self.scale_number = len(args.hyper_scales)
 
     def forward(self, inputs, batch_size, agent_num):
-        # `inputs` = [positions | velocities]; the library recomputes the velocities from the positions exactly
-        # as STTODENet.inference does (model/STTODE.py:582-596), so only columns 0:2 are read.
-        if self.training:
-            raise NotImplementedError("PastEncoder on B200: eval mode only in round 1 (PE dropout 0.1 is live in training, model/STTODE.py:197)")
-        traj = _f32c(inputs[..., :2], "inputs")
-        rows, T = traj.shape[0], traj.shape[1]
-        mw = _lib.ModelWeights()
-        mw.past_length, mw.future_length = T, 1
-        mw.past = _encoder_struct(self)
-        out = torch.empty(rows, 128, device=traj.device, dtype=torch.float32)
-        lib = _lib.lib()
-        ws = _lib.workspace(lib.sttode_past_encoder_workspace_bytes(rows, batch_size), traj.device)
-        _lib.check(lib.sttode_past_encoder_fwd(_lib.dptr(traj), TRAJ_RT2, None, None, 0, rows, batch_size, agent_num, C.byref(mw),
-                                               _lib.dptr(out), None, None, _lib.dptr(ws), ws.numel(), _lib.stream_ptr()))
-        return out
+        return _encoder_forward(self, inputs, batch_size, agent_num)
+
+
+def _encoder_forward(enc, inputs, batch_size, agent_num):
+    """Front end + tensor-ODE block on explicit [x, y, vx, vy] features -> [B*N, 128] (sttode_encoder_fwd)."""
+    if enc.training:
+        raise NotImplementedError("encoders on B200: eval mode only in round 1 (PE dropout 0.1 is live in training, model/STTODE.py:197,256)")
+    feat = _f32c(inputs, "inputs")
+    rows, T = feat.shape[0], feat.shape[1]
+    if feat.shape[-1] != 4 or rows != batch_size * agent_num:
+        raise _lib.SttodeError("encoder inputs must be [batch_size*agent_num, T, 4]")
+    st = _encoder_struct(enc)
+    out = torch.empty(rows, 128, device=feat.device, dtype=torch.float32)
+    lib = _lib.lib()
+    ws = _lib.workspace(lib.sttode_past_encoder_workspace_bytes(rows, batch_size), feat.device)
+    _lib.check(lib.sttode_encoder_fwd(_lib.dptr(feat), rows, batch_size, agent_num, T, C.byref(st), _lib.dptr(out), _lib.dptr(ws), ws.numel(),
+                                      _lib.stream_ptr()))
+    return out
+
+
+def _linear(x, layer, relu):
+    out = torch.empty(x.shape[0], layer.out_features, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().sttode_linear(_lib.dptr(x), _lib.dptr(layer.weight), _lib.dptr(layer.bias), _lib.dptr(out), x.shape[0],
+                                        layer.in_features, layer.out_features, int(relu), _lib.stream_ptr()))
+    return out
 
 
 class FutureEncoder(_EncoderBase):
-    """Posterior encoder (model/STTODE.py:238-300): training only.  Parameters are kept for checkpoint parity."""
+    """Posterior encoder (model/STTODE.py:238-300)."""
 
     def __init__(self, args, in_dim=4):
         super().__init__(args, args.future_length, in_dim)
@@ -167,7 +177,11 @@ class FutureEncoder(_EncoderBase):
         initialize_weights(self.qz_layer.modules())
 
     def forward(self, inputs, batch_size, agent_num, past_feature):
-        raise NotImplementedError("FutureEncoder.forward is on the training path (model/STTODE.py:498-525); round 2")
+        """-> q(z | past, future) parameters [B*N, 2*zdim] (model/STTODE.py:276-300); forward only."""
+        ff = _encoder_forward(self, inputs, batch_size, agent_num)
+        h = torch.cat((_f32c(past_feature, "past_feature"), ff), dim=-1)
+        h = _linear(h, self.out_mlp.affine_layers[0], relu=True)
+        return _linear(h, self.qz_layer, relu=False)
 
 
 class DecomposeBlock(nn.Module):
@@ -458,9 +472,45 @@ class STTODENet(nn.Module):
         """CUDA-graph version of `forecast_scenes` (n_scenes > 0, L = 1) or of NBA-style inference (n_scenes = 0) for a fixed shape."""
         return ForecastGraph(self, rows, L, agents, n_scenes, layout, sample_k).capture()
 
-    # ---- training path: round 2 ---------------------------------------------------------------------
+    # ---- training objective (forward only; the backward kernels are round-2 work) -----------------------------
+    @torch.no_grad()
     def forward(self):
-        raise NotImplementedError("STTODENet.forward (training losses, model/STTODE.py:553-568) needs the backward kernels: round 2")
+        """The reference's training objective (model/STTODE.py:553-568) evaluated forward-only on the staged batch:
+        returns (total_loss tensor WITHOUT autograd history, loss_pred, loss_recover, loss_kl, loss_diverse).
+        Needs eval() mode (PE dropout and the random scene rotation are train-mode only) and `set_data_nba`.
+        `self.eps_override = (eps_q [R,zdim], eps_p [R*20,zdim])` injects the two live rsample draws."""
+        if self.training:
+            raise NotImplementedError("STTODENet.forward in train() mode needs the backward kernels (round 2); call it under eval() for the loss values")
+        if getattr(self, "_mode", None) != "nba":
+            raise NotImplementedError("STTODENet.forward on B200: stage the batch with set_data_nba (ETH staging with rotation is train-mode only)")
+        args, dev = self.args, self.device
+        B, N, Tp, Tf = self.batch_size, self.agent_num, args.past_length, args.future_length
+        R = B * N
+        past = _f32c(self.data["past_traj"].to(dev), "past_traj").view(R, Tp, 2)
+        fut = _f32c(self.data["future_traj"].to(dev), "future_traj").view(R, Tf, 2)
+        vel = past[:, 1:] - past[:, :-1]
+        inputs = torch.cat((past, torch.cat([vel[:, [0]], vel], dim=1)), dim=-1)
+        fvel = fut - torch.cat([past[:, [-1]], fut[:, :-1]], dim=1)
+        self.past_feature = self.past_encoder(inputs, B, N)
+        self.qz_param = self.future_encoder(torch.cat((fut, fvel), dim=-1), B, N, self.past_feature)
+        mu, logvar = torch.chunk(self.qz_param, 2, dim=-1)
+        sigma = torch.exp(0.5 * logvar)
+        eps = getattr(self, "eps_override", None)
+        eps_q = eps[0].to(dev) if eps is not None else torch.randn_like(sigma)
+        eps_p = eps[1].to(dev) if eps is not None else torch.randn(R * 20, args.zdim, device=dev)
+        self.qz_sampled = mu + eps_q * sigma
+        cur = past[:, [-1]]
+        self.pred_traj, self.recover_traj = self.decoder(self.past_feature, self.qz_sampled, B, N, past, cur, sample_num=1)
+        loss_pred = (fut - self.pred_traj).pow(2).sum() / B / Tf
+        loss_recover = (past - self.recover_traj).pow(2).sum() / B / Tp
+        kl = 0.5 * ((mu / (1 + 1e-8)) ** 2 + (sigma / (1 + 1e-8)) ** 2) - 0.5 - torch.log(sigma / (1 + 1e-8))      # KL(q || N(0, I)), Normal.kl
+        loss_kl = (kl.sum() / (B * N)).clamp_min(args.min_clip)
+        self.past_feature_repeat = self.past_feature.repeat_interleave(20, dim=0)
+        self.diverse_pred_traj, _ = self.decoder(self.past_feature_repeat, eps_p, B, N, past, cur, sample_num=20, mode="inference")
+        diff = fut.unsqueeze(1) - self.diverse_pred_traj
+        loss_diverse = diff.pow(2).sum(dim=-1).sum(dim=-1).min(dim=1)[0].mean()
+        total = loss_pred + loss_recover + loss_kl + loss_diverse
+        return total, loss_pred.item(), loss_recover.item(), loss_kl.item(), loss_diverse.item()
 
     def step_annealer(self):
         for anl in self.param_annealers:

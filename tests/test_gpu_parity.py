@@ -277,6 +277,31 @@ def test_module_level_apis_vs_oracle(eth, dev):
     assert rel(rec, rec_ref) < TOL
 
 
+@pytest.mark.parametrize("what", ["latent", "past_feature", "one_agent"])
+def test_decoder_beyond_fp16_range_falls_back_to_fp32(dev, what):
+    """The tensor-core decoder splits operands into fp16 hi/lo pairs (|v| < 65504).  Tiles that stage larger
+    values must be recomputed by the FP32 kernel, so the result still matches the oracle (the training path
+    feeds posterior latents of magnitude ~1e5 through the decoder with random-init weights)."""
+    m, sd = build_model("eth", 8, 12, 1, dev, tensor_cores=True)
+    n = 9
+    obs, _ = synth.eth_scene(41, n)
+    past, _ = O.eth_scene_normalise(obs)
+    pf = O.past_encoder(O.velocity_features(past), 1, n, sd)
+    z = synth.latent(n, seed=4)
+    if what == "latent":
+        z = z * 9.0e4
+    elif what == "past_feature":
+        pf = pf * 3.0e5
+    else:                                  # a single (agent, sample) pair out of range: only its tile is redone
+        z[3 * 20 + 7] *= 2.0e5
+    out, rec = m.decoder(pf.repeat_interleave(20, 0).to(dev), z.to(dev), 1, n, past.to(dev), past[:, [-1]].to(dev), sample_num=20, mode="inference")
+    out_ref, rec_ref = O.decoder(pf.repeat_interleave(20, 0), z, past, past[:, [-1]], 20, sd, mode="inference")
+    assert torch.isfinite(out).all()
+    assert rel(out, out_ref) < TOL
+    assert rel(rec, rec_ref) < TOL
+    assert m.tc_status() == 0
+
+
 def test_in_kernel_latent_is_standard_normal_and_seeded(eth, dev):
     """With z not injected the decoder draws z ~ N(0, I) itself (the reference's randn_like): check the
     draw through its effect — deterministic per seed, different across seeds — and the raw moments."""
@@ -496,3 +521,24 @@ def test_cuda_graph_forecast(eth, dev):
                                     C.byref(mw), L.dptr(pred), None, None, None, L.dptr(ws), ws.numel(), L.stream_ptr()))
     torch.cuda.synchronize()
     assert torch.equal(pred, b)          # warm-up used counter 0, capture does not execute, replays use 1 and 2
+
+
+def test_future_encoder_and_training_objective_vs_reference(golden, dev):
+    """FutureEncoder.forward and the training objective STTODENet.forward() (forward only) against the reference's own
+    forward() output (tests/golden/training_objective.npz: eval mode, injected rsample draws)."""
+    g = golden("training_objective")
+    B, tp, tf = int(g["B"]), 10, 20
+    m, sd = build_model("nba", tp, tf, 2, dev)
+    data = synth.nba_batch(1, B, 11, tp, tf)
+    gq = torch.Generator().manual_seed(21)
+    eps_q, _, eps_p = torch.randn(B * 11, 32, generator=gq), torch.randn(B * 11, 32, generator=gq), torch.randn(B * 11 * 20, 32, generator=gq)
+    m.eps_override = (eps_q, eps_p)
+    m.set_data_nba(data)
+    total, lp, lr, lk, ld = m.forward()
+    assert rel(m.qz_param, g["qz"]) < TOL
+    for got, key in ((float(total), "total"), (lp, "pred"), (lr, "recover"), (lk, "kl"), (ld, "diverse")):
+        assert abs(got - float(g[key])) <= TOL * abs(float(g[key])), key
+    # the Decoder K = 1 path returns the reconstruction the reference calls recover_pre_seq
+    past = data["past_traj"].view(B * 11, tp, 2)
+    ref = O.training_objective(sd, past, data["future_traj"].view(B * 11, tf, 2), B, 11, eps_q, eps_p)
+    assert abs(float(total) - ref["total"]) <= TOL * abs(ref["total"])

@@ -98,7 +98,7 @@ def test_unsupported_options_raise():
     with pytest.raises(NotImplementedError):
         STTODENet(a, torch.device("cpu"))
     with pytest.raises(NotImplementedError):
-        STTODENet(make_args(), torch.device("cpu")).forward()
+        STTODENet(make_args(), torch.device("cpu")).train().forward()
 
 
 def test_compat_registers_reference_module_names():

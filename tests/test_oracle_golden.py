@@ -93,6 +93,19 @@ def test_inference_nba_matches_reference(golden, name, tp, tf):
     assert rel(pred, g[f"{name}_pred"]) < 2e-6
 
 
+def test_training_objective_matches_reference(golden):
+    g = golden("training_objective")
+    B, tp, tf = int(g["B"]), 10, 20
+    sd = O.make_state_dict(2, tp, tf)
+    data = synth.nba_batch(1, B, 11, tp, tf)
+    gq = torch.Generator().manual_seed(21)
+    eps_q, _, eps_p = torch.randn(B * 11, 32, generator=gq), torch.randn(B * 11, 32, generator=gq), torch.randn(B * 11 * 20, 32, generator=gq)
+    out = O.training_objective(sd, data["past_traj"].view(B * 11, tp, 2), data["future_traj"].view(B * 11, tf, 2), B, 11, eps_q, eps_p)
+    assert rel(out["qz"], g["qz"]) < 2e-6
+    for k in ("total", "pred", "recover", "kl", "diverse"):
+        assert abs(out[k] - float(g[k])) <= 2e-6 * abs(float(g[k])), k
+
+
 def test_gru_fast_path_equals_loop(sd_eth):
     p = "decoder.decompose.0.encoder_past."
     x = torch.randn(13, 8, 32, generator=torch.Generator().manual_seed(5))
