@@ -152,6 +152,37 @@ int sttode_ode_rhs_fwd(const float *x, const sttode_ode_weights *w, float *f, in
 int sttode_hypattention_fwd(const float *x, const sttode_ode_weights *w, float *out, int L, int bsz, void *workspace,
                             size_t workspace_bytes, void *stream);
 
+/* ---- backward of the MHGSA / tensor-ODE block (training config: "forward+backward through ODE and MHGSA").
+ * The reference obtains these from torch autograd over hyp_mhsa (hyptransformerlib.py:29-311), Hypattention.forward
+ * (hypertransformer.py:55-89), TransformerEncoderLayer.forward (:134-153) and the Euler step (ode_demo.py:186-190,231);
+ * here they are explicit entry points an autograd.Function calls.  Every backward call re-materialises the forward
+ * intermediates from the block INPUT, so the forward saves nothing.  Parameter gradients are ACCUMULATED (+=) into the
+ * buffers of the grads struct (same shapes as the weights; the struct or any member may be NULL to skip it); input
+ * gradients are overwritten.  Summation order is fixed (no atomics): results are run-to-run deterministic. */
+typedef struct sttode_mhgsa_grads { float *in_proj_w, *in_proj_b, *out_proj_w, *out_proj_b; } sttode_mhgsa_grads;
+typedef struct sttode_ode_grads {
+    sttode_mhgsa_grads attn;
+    float *info_w, *info_b, *gate_w, *gate_b, *lin1_w, *lin1_b, *lin2_w, *lin2_b, *norm1_g, *norm1_b, *norm2_g, *norm2_b;
+} sttode_ode_grads;
+
+/* dout [L,bsz,E] -> dquery [L,bsz,E] (+ dkey, dvalue [S,bsz,E] when key/value are separate tensors; with
+ * query == key == value the self-attention branch is differentiated and dquery receives the whole gradient, as in the
+ * reference where only `query` feeds the packed projection, hyptransformerlib.py:113-115).  Oblique acos score only.
+ * The head-averaged attention weights output is not differentiated. */
+size_t sttode_mhgsa_bwd_workspace_bytes(int L, int S, int bsz);
+int sttode_mhgsa_bwd(const float *query, const float *key, const float *value, const sttode_mhgsa_weights *w, const float *dout,
+                     float *dquery, float *dkey, float *dvalue, const sttode_mhgsa_grads *grads, int L, int S, int bsz, int E, int H,
+                     int score_mode, float clamp_eps, void *workspace, size_t workspace_bytes, void *stream);
+/* df [L,bsz,64] = gradient of sttode_ode_rhs_fwd's output (gate_only = 0) or of sttode_hypattention_fwd's (gate_only = 1) */
+size_t sttode_ode_rhs_bwd_workspace_bytes(int L, int bsz);
+int sttode_ode_rhs_bwd(const float *x, const float *df, const sttode_ode_weights *w, float *dx, const sttode_ode_grads *grads, int L, int bsz,
+                       int gate_only, void *workspace, size_t workspace_bytes, void *stream);
+/* dy rows have stride lddy floats (>= 64): gradient of sttode_ode_block_fwd's y.  method must be STTODE_ODE_EULER. */
+size_t sttode_ode_block_bwd_workspace_bytes(int L, int bsz, int n_steps);
+int sttode_ode_block_bwd(const float *x, const float *dy, int lddy, const sttode_ode_weights *w, float *dx, const sttode_ode_grads *grads,
+                         int L, int bsz, int n_steps, float h, int method, int final_relu, void *workspace, size_t workspace_bytes,
+                         void *stream);
+
 /* ---- PastEncoder.forward (model/STTODE.py:214-236), eval mode.
  * traj: raw positions in `layout`; n_batches groups of (L scenes x agents) rows, rows = n_batches*L*agents
  * ordered [batch][scene][agent] (NBA: L = B scenes attend to each other per agent).  For ETH/SDD (L = 1)

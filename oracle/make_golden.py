@@ -1,6 +1,6 @@
 """Generate tests/golden/*.npz by running the UNMODIFIED reference (under oracle/ref_shim.py) here.
 
-Run in the build container only (needs /root/reference):   python oracle/make_golden.py
+Run in the build container only (needs /root/reference):   python oracle/make_golden.py [forward|backward|all]
 The fixtures pin `oracle/sttode_oracle.py` and `oracle/pmath_oracle.py` to the reference's own outputs and
 travel to the GPU box, where /root/reference does not exist.  Weights are NOT stored: both sides rebuild
 them with `make_state_dict(seed)`; the reference side loads them with `load_state_dict(strict=True)`,
@@ -145,5 +145,49 @@ def main():
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
+def grads_of(mod):
+    return {n: np32(p.grad) for n, p in mod.named_parameters() if p.grad is not None}
+
+
+def backward_golden():
+    """Gradients of the reference itself (torch autograd over the unmodified modules) for the MHGSA module and the
+    tensor-ODE block on the inputs of mhgsa.npz / ode_block.npz, with seeded upstream gradients."""
+    ref = ref_shim.install()
+    m = ref_model(ref, "eth", 8, 12, seed=1)
+    attn = m.past_encoder.ODE_Encoder.odeblock.odefunc.layers[0].self_attn.temporal_attention_before
+    gi = np.load(os.path.join(OUT, "mhgsa.npz"))
+    g = torch.Generator().manual_seed(31)
+    rec = {}
+    for name in ("sq5", "x46"):
+        q = torch.from_numpy(gi[f"{name}_q"]).requires_grad_(True)
+        square = gi[f"{name}_q"].shape == gi[f"{name}_kv"].shape
+        kv = q if square else torch.from_numpy(gi[f"{name}_kv"]).requires_grad_(True)
+        dout = torch.randn(*q.shape, generator=g)
+        m.zero_grad(set_to_none=True)
+        attn(q, kv, kv)[0].backward(dout)
+        rec[f"mhgsa_{name}_dout"], rec[f"mhgsa_{name}_dq"] = np32(dout), np32(q.grad)
+        if not square:
+            rec[f"mhgsa_{name}_dkv"] = np32(kv.grad)
+        for n, v in grads_of(attn).items():
+            rec[f"mhgsa_{name}_g_{n}"] = v
+    go = np.load(os.path.join(OUT, "ode_block.npz"))
+    enc = m.past_encoder.ODE_Encoder
+    for name in ("L1", "L6"):
+        x = torch.from_numpy(go[f"{name}_x"]).requires_grad_(True)
+        dy = torch.randn(*x.shape, generator=g)
+        m.zero_grad(set_to_none=True)
+        m.past_encoder.agent_mask = torch.zeros(1)
+        enc(x, mask=None, num_agent=x.shape[1]).backward(dy)
+        rec[f"ode_{name}_dy"], rec[f"ode_{name}_dx"] = np32(dy), np32(x.grad)
+        for n, p in enc.named_parameters():      # L == 1: q/k projections receive no gradient at all (softmax over one key)
+            rec[f"ode_{name}_g_{n}"] = np32(p.grad if p.grad is not None else torch.zeros_like(p))
+    np.savez_compressed(os.path.join(OUT, "backward.npz"), **rec)
+    print("backward.npz", os.path.getsize(os.path.join(OUT, "backward.npz")))
+
+
 if __name__ == "__main__":
-    main()
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("forward", "all"):
+        main()
+    if what in ("backward", "all"):
+        backward_golden()

@@ -22,6 +22,16 @@ class OdeWeights(C.Structure):
         "norm1_g", "norm1_b", "norm2_g", "norm2_b")]
 
 
+class MhgsaGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("in_proj_w", "in_proj_b", "out_proj_w", "out_proj_b")]
+
+
+class OdeGrads(C.Structure):
+    _fields_ = [("attn", MhgsaGrads)] + [(n, C.c_void_p) for n in (
+        "info_w", "info_b", "gate_w", "gate_b", "lin1_w", "lin1_b", "lin2_w", "lin2_b",
+        "norm1_g", "norm1_b", "norm2_g", "norm2_b")]
+
+
 class EncoderWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("fc_w", "fc_b", "pe", "pefc_w", "pefc_b", "fc2_w", "fc2_b", "fc3_w", "fc3_b")] + [("ode", OdeWeights)]
 
@@ -59,6 +69,12 @@ SIGNATURES = {
     "sttode_ode_block_fwd": (_I, [_V, C.POINTER(OdeWeights), _V, _I, _I, _I, _I, _F, _I, _I, _V, _Z, _V]),
     "sttode_ode_rhs_fwd": (_I, [_V, C.POINTER(OdeWeights), _V, _I, _I, _V, _Z, _V]),
     "sttode_hypattention_fwd": (_I, [_V, C.POINTER(OdeWeights), _V, _I, _I, _V, _Z, _V]),
+    "sttode_mhgsa_bwd_workspace_bytes": (_Z, [_I, _I, _I]),
+    "sttode_mhgsa_bwd": (_I, [_V, _V, _V, C.POINTER(MhgsaWeights), _V, _V, _V, _V, C.POINTER(MhgsaGrads), _I, _I, _I, _I, _I, _I, _F, _V, _Z, _V]),
+    "sttode_ode_rhs_bwd_workspace_bytes": (_Z, [_I, _I]),
+    "sttode_ode_rhs_bwd": (_I, [_V, _V, C.POINTER(OdeWeights), _V, C.POINTER(OdeGrads), _I, _I, _I, _V, _Z, _V]),
+    "sttode_ode_block_bwd_workspace_bytes": (_Z, [_I, _I, _I]),
+    "sttode_ode_block_bwd": (_I, [_V, _V, _I, C.POINTER(OdeWeights), _V, C.POINTER(OdeGrads), _I, _I, _I, _F, _I, _I, _V, _Z, _V]),
     "sttode_past_encoder_workspace_bytes": (_Z, [_I, _I]),
     "sttode_past_encoder_fwd": (_I, [_V, _I, _V, _V, _I, _I, _I, _I, C.POINTER(ModelWeights), _V, _V, _V, _V, _Z, _V]),
     "sttode_encoder_fwd": (_I, [_V, _I, _I, _I, _I, C.POINTER(EncoderWeights), _V, _V, _Z, _V]),

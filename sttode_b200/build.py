@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsttode_sm100.so")
-SOURCES = ["encoder.cu", "decoder.cu", "decoder_tc.cu", "pmath.cu", "tc_selftest.cu", "capi.cu"]
+SOURCES = ["encoder.cu", "backward.cu", "decoder.cu", "decoder_tc.cu", "pmath.cu", "tc_selftest.cu", "capi.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "kernels.cuh"), os.path.join(CSRC, "tc.cuh"),
            os.path.join(os.path.dirname(HERE), "include", "sttode.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

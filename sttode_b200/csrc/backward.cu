@@ -1,0 +1,298 @@
+// Backward of the MHGSA + tensor-ODE right-hand side (training config), sm_100a, FP32.
+//
+// What is differentiated (file:line relative to the reference root, forward semantics in encoder.cu):
+//   k_geo_attn_bwd   Oblique.proj / Oblique.dist / clamp / acos / softmax / bmm     core/manifolds/oblique.py:15-16,36-45;
+//                                                                                  hyptransformerlib.py:252-300
+//   k_gate_ln_fwd    tanh(info) * sigmoid(gate), residual, LayerNorm (recompute)   hypertransformer.py:81-83,148
+//   k_gate_bwd       d tanh * sigmoid                                              hypertransformer.py:81-83
+//   k_ln_bwd         LayerNorm(64) input gradient (+ x^ * dy for the gamma sum)    hypertransformer.py:148,152
+//   k_gemm           every dense product of the chain (y = x W^T, dx = dy W, dW += dy^T x)
+//   k_colsum         bias / LayerNorm parameter gradients (deterministic column sums)
+// The reference gets these from torch autograd; the chain below is the hand derivation of the same graph.
+// The training shapes are small (NBA: 32 x 11 rows, ETH: one scene), so this round's kernels favour a
+// deterministic, launch-by-launch decomposition over fusion; the forward they re-materialise is bit-identical
+// in structure to k_proj / k_geo_attn and within rounding of k_ode_tail.
+#include "kernels.cuh"
+
+namespace sttode {
+
+// ------------------------------------------------------------------------------------------------
+// C[M,N] = epi(sum_k A(m,k) B(k,n)),  A(m,k) = A[m*sam + k*sak],  B(k,n) = B[k*sbk + n*sbn]
+// epi(v) = ((relu? max(v + bias[n], 0) : v + bias[n]) * (mask[m,n] > 0 ? 1 : 0 if mask)) + res[m,n] (+ C[m,n] if accumulate)
+// 64 x 64 output tile per CTA, 256 threads x (4 x 4) register tile, K in slabs of 16.
+// ------------------------------------------------------------------------------------------------
+constexpr int GT = 64, GK = 16;
+
+__global__ void __launch_bounds__(256)
+k_gemm(int M, int N, int K, const float* __restrict__ A, long sam, long sak, const float* __restrict__ B, long sbk, long sbn,
+       float* __restrict__ C, long ldc, const float* __restrict__ bias, const float* __restrict__ res, long ldres,
+       const float* __restrict__ mask, long ldmask, int relu, int accumulate) {
+    __shared__ float As[GK][GT + 4];
+    __shared__ float Bs[GK][GT + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const bool a_kfast = sak == 1, b_nfast = sbn == 1;
+    for (int k0 = 0; k0 < K; k0 += GK) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int idx = tid + e * 256;
+            int mm, kk;
+            if (a_kfast) { kk = idx & 15; mm = idx >> 4; } else { mm = idx & 63; kk = idx >> 6; }
+            As[kk][mm] = (m0 + mm < M && k0 + kk < K) ? A[(long)(m0 + mm) * sam + (long)(k0 + kk) * sak] : 0.f;
+            int nn, kb;
+            if (b_nfast) { nn = idx & 63; kb = idx >> 6; } else { kb = idx & 15; nn = idx >> 4; }
+            Bs[kb][nn] = (n0 + nn < N && k0 + kb < K) ? B[(long)(k0 + kb) * sbk + (long)(n0 + nn) * sbn] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < GK; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty + 16 * i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty + 16 * i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx + 16 * j;
+            if (n >= N) continue;
+            float v = acc[i][j];
+            if (bias) v += __ldg(bias + n);
+            if (relu) v = fmaxf(v, 0.f);
+            if (mask && !(mask[(long)m * ldmask + n] > 0.f)) v = 0.f;
+            if (res) v += res[(long)m * ldres + n];
+            if (accumulate) v += C[(long)m * ldc + n];
+            C[(long)m * ldc + n] = v;
+        }
+    }
+}
+
+// out[n] += sum_r X[r, n]     (one CTA owns 32 columns: no atomics, fixed summation order)
+__global__ void __launch_bounds__(256)
+k_colsum(const float* __restrict__ X, long ldx, int rows, int N, float* __restrict__ out) {
+    __shared__ float part[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + tx;
+    float s = 0.f;
+    if (n < N)
+        for (int r = ty; r < rows; r += 8) s += X[(long)r * ldx + n];
+    part[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && n < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += part[k][tx];
+        out[n] += t;
+    }
+}
+
+// z1 = x + tanh(ui) * sigmoid(ug);  s1 = LayerNorm(z1).  One warp per row, two features per lane.
+__global__ void __launch_bounds__(256)
+k_gate_ln_fwd(const float* __restrict__ x, const float* __restrict__ ui, const float* __restrict__ ug,
+              const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ z1, float* __restrict__ s1,
+              int rows) {
+    const int r = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const size_t o = (size_t)r * 64;
+    const float v0 = x[o + lane] + tanhf(ui[o + lane]) * sigmoidf_(ug[o + lane]);
+    const float v1 = x[o + lane + 32] + tanhf(ui[o + lane + 32]) * sigmoidf_(ug[o + lane + 32]);
+    const float mean = warp_sum(v0 + v1) * (1.f / 64.f);
+    const float d0 = v0 - mean, d1 = v1 - mean;
+    const float rstd = 1.f / sqrtf(warp_sum(d0 * d0 + d1 * d1) * (1.f / 64.f) + 1e-5f);
+    z1[o + lane] = v0;
+    z1[o + lane + 32] = v1;
+    s1[o + lane] = d0 * rstd * __ldg(gamma + lane) + __ldg(beta + lane);
+    s1[o + lane + 32] = d1 * rstd * __ldg(gamma + lane + 32) + __ldg(beta + lane + 32);
+}
+
+// LayerNorm(64) backward for the input: z = pre-norm rows, ds = gradient of the normalised output.
+//   dz = rstd * (g - mean(g) - x^ * mean(g * x^)),  g = ds * gamma;   xhat_ds = x^ * ds  (column-summed into d gamma)
+__global__ void __launch_bounds__(256)
+k_ln_bwd(const float* __restrict__ z, const float* __restrict__ gamma, const float* __restrict__ ds, long ldds,
+         float* __restrict__ dz, float* __restrict__ xhat_ds, int rows) {
+    const int r = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const size_t o = (size_t)r * 64;
+    const float v0 = z[o + lane], v1 = z[o + lane + 32];
+    const float mean = warp_sum(v0 + v1) * (1.f / 64.f);
+    const float d0 = v0 - mean, d1 = v1 - mean;
+    const float rstd = 1.f / sqrtf(warp_sum(d0 * d0 + d1 * d1) * (1.f / 64.f) + 1e-5f);
+    const float h0 = d0 * rstd, h1 = d1 * rstd;
+    const float e0 = ds[(long)r * ldds + lane], e1 = ds[(long)r * ldds + lane + 32];
+    const float g0 = e0 * __ldg(gamma + lane), g1 = e1 * __ldg(gamma + lane + 32);
+    const float m1 = warp_sum(g0 + g1) * (1.f / 64.f);
+    const float m2 = warp_sum(g0 * h0 + g1 * h1) * (1.f / 64.f);
+    dz[o + lane] = rstd * (g0 - m1 - h0 * m2);
+    dz[o + lane + 32] = rstd * (g1 - m1 - h1 * m2);
+    if (xhat_ds) {
+        xhat_ds[o + lane] = h0 * e0;
+        xhat_ds[o + lane + 32] = h1 * e1;
+    }
+}
+
+// g = tanh(ui) * sigmoid(ug):  dui = dg * s * (1 - t^2),  dug = dg * t * s * (1 - s)
+__global__ void k_gate_bwd(const float* __restrict__ ui, const float* __restrict__ ug, const float* __restrict__ dg, long lddg,
+                           float* __restrict__ dui, float* __restrict__ dug, int rows) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)rows * 64) return;
+    const int r = (int)(idx >> 6), n = (int)(idx & 63);
+    const float t = tanhf(ui[idx]), s = sigmoidf_(ug[idx]), d = dg[(long)r * lddg + n];
+    dui[idx] = d * s * (1.f - t * t);
+    dug[idx] = d * t * s * (1.f - s);
+}
+
+// out[r, 0:64] = alpha * a[r] * (gate[r] > 0 if gate) + (b ? b[r] : 0)       (row strides in floats)
+__global__ void k_rows_axpb(const float* __restrict__ a, long lda, float alpha, const float* __restrict__ gate, long ldg,
+                            const float* __restrict__ b, long ldb, float* __restrict__ out, long ldo, int rows) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)rows * 64) return;
+    const long r = (long)(idx >> 6), n = (long)(idx & 63);
+    float v = alpha * a[r * lda + n];
+    if (gate && !(gate[r * ldg + n] > 0.f)) v = 0.f;
+    if (b) v += b[r * ldb + n];
+    out[r * ldo + n] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Geodesic attention backward for one (group, head).  Forward (k_geo_attn):
+//   s_ij = -acos(clamp(<row_i, col_j>, lo, hi)),  P_ij = softmax_j(s_ij),  o_i = sum_j P_ij v_j
+// with row = k^, col = q^ when L == S (the reference's un-transposed matrix) and row = q^, col = k^ otherwise.
+// Given d o_i:   delta_i = <do_i, o_i>,  dS_ij = P_ij (<do_i, v_j> - delta_i),
+//   dG_ij = dS_ij / sqrt(1 - g_ij^2) inside the clamp range (torch.clamp passes the gradient on [lo, hi]), 0 outside,
+//   d row_i = sum_j dG_ij col_j,  d col_j = sum_i dG_ij row_i,  d v_j = sum_i P_ij do_i,
+// then through p^ = p / |p| (oblique.py:16):  dp = (dp^ - p^ <p^, dp^>) / |p|   (times the q scaling for q).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ld8(float (&d)[8], const float* p) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+}
+__device__ __forceinline__ void st8(float* p, const float (&d)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(d[0], d[1], d[2], d[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(d[4], d[5], d[6], d[7]);
+}
+__device__ __forceinline__ float dot8(const float (&a)[8], const float (&b)[8]) {
+    float g = a[0] * b[0];
+#pragma unroll
+    for (int d = 1; d < 8; ++d) g = fmaf(a[d], b[d], g);
+    return g;
+}
+// gradient w.r.t. the un-normalised head vector from the gradient w.r.t. the unit vector
+__device__ __forceinline__ void unnormalise_grad(float (&g)[8], const float (&unit)[8], float norm, float scale) {
+    const float t = dot8(unit, g), inv = scale / norm;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) g[d] = (g[d] - unit[d] * t) * inv;
+}
+
+__global__ void __launch_bounds__(128)
+k_geo_attn_bwd(const float* __restrict__ qh, int ldq, const float* __restrict__ kh, int ldk, const float* __restrict__ v, int ldv,
+               const float* __restrict__ nq, const float* __restrict__ nk, int ldn, const float* __restrict__ dout, int ldo,
+               float* __restrict__ dq, int lddq, float* __restrict__ dk, int lddk, float* __restrict__ dv, int lddv,
+               int L, int S, int bsz, int swap, float lo, float hi, float qscale) {
+    extern __shared__ __align__(16) float sm[];
+    const int Lr = L, Lc = S;
+    float* rowv = sm;                    // [Lr][8]
+    float* dov = rowv + Lr * 8;          // [Lr][8]
+    float* colv = dov + Lr * 8;          // [Lc][8]
+    float* vv = colv + Lc * 8;           // [Lc][8]
+    float* den = vv + Lc * 8;            // [Lr]
+    float* delta = den + Lr;             // [Lr]
+    const int head = blockIdx.x & 7, g = blockIdx.x >> 3;
+    const int kb = g / bsz, n = g - kb * bsz;
+    const size_t qbase = (size_t)kb * L * bsz + n, kbase = (size_t)kb * S * bsz + n;
+    const float* rowsrc = swap ? kh : qh;  const int ldr = swap ? ldk : ldq;  const size_t rbase = swap ? kbase : qbase;
+    const float* colsrc = swap ? qh : kh;  const int ldc = swap ? ldq : ldk;  const size_t cbase = swap ? qbase : kbase;
+    for (int i = threadIdx.x; i < Lr; i += 128) {
+        float t[8];
+        ld8(t, rowsrc + (rbase + (size_t)i * bsz) * ldr + head * 8);  st8(rowv + i * 8, t);
+        ld8(t, dout + (qbase + (size_t)i * bsz) * ldo + head * 8);    st8(dov + i * 8, t);
+    }
+    for (int j = threadIdx.x; j < Lc; j += 128) {
+        float t[8];
+        ld8(t, colsrc + (cbase + (size_t)j * bsz) * ldc + head * 8);  st8(colv + j * 8, t);
+        ld8(t, v + (kbase + (size_t)j * bsz) * ldv + head * 8);       st8(vv + j * 8, t);
+    }
+    __syncthreads();
+    // ---- row pass: softmax statistics, delta, d row
+    for (int i = threadIdx.x; i < Lr; i += 128) {
+        float a[8], d_o[8], o[8], dr[8];
+        ld8(a, rowv + i * 8);
+        ld8(d_o, dov + i * 8);
+        float dn = 0.f;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) { o[d] = 0.f; dr[d] = 0.f; }
+        for (int j = 0; j < Lc; ++j) {
+            float c[8], w[8];
+            ld8(c, colv + j * 8);
+            ld8(w, vv + j * 8);
+            const float p = expf(-acosf(clamp_nan(dot8(a, c), lo, hi)));
+            dn += p;
+#pragma unroll
+            for (int d = 0; d < 8; ++d) o[d] = fmaf(p, w[d], o[d]);
+        }
+        const float dl = dot8(d_o, o) / dn;
+        for (int j = 0; j < Lc; ++j) {
+            float c[8], w[8];
+            ld8(c, colv + j * 8);
+            ld8(w, vv + j * 8);
+            const float gij = dot8(a, c);
+            if (gij >= lo && gij <= hi) {
+                const float p = expf(-acosf(gij)) / dn;
+                const float dg = p * (dot8(d_o, w) - dl) / sqrtf(1.f - gij * gij);
+#pragma unroll
+                for (int d = 0; d < 8; ++d) dr[d] = fmaf(dg, c[d], dr[d]);
+            }
+        }
+        den[i] = dn;
+        delta[i] = dl;
+        const size_t r = rbase + (size_t)i * bsz;
+        unnormalise_grad(dr, a, (swap ? nk : nq)[r * ldn + head], swap ? 1.f : qscale);
+        st8((swap ? dk : dq) + r * (swap ? lddk : lddq) + head * 8, dr);
+    }
+    __syncthreads();
+    // ---- column pass: d col, d v
+    for (int j = threadIdx.x; j < Lc; j += 128) {
+        float c[8], w[8], dc[8], dw[8];
+        ld8(c, colv + j * 8);
+        ld8(w, vv + j * 8);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) { dc[d] = 0.f; dw[d] = 0.f; }
+        for (int i = 0; i < Lr; ++i) {
+            float a[8], d_o[8];
+            ld8(a, rowv + i * 8);
+            ld8(d_o, dov + i * 8);
+            const float gij = dot8(a, c);
+            const float p = expf(-acosf(clamp_nan(gij, lo, hi))) / den[i];
+#pragma unroll
+            for (int d = 0; d < 8; ++d) dw[d] = fmaf(p, d_o[d], dw[d]);
+            if (gij >= lo && gij <= hi) {
+                const float dg = p * (dot8(d_o, w) - delta[i]) / sqrtf(1.f - gij * gij);
+#pragma unroll
+                for (int d = 0; d < 8; ++d) dc[d] = fmaf(dg, a[d], dc[d]);
+            }
+        }
+        const size_t rk = kbase + (size_t)j * bsz;
+        st8(dv + rk * lddv + head * 8, dw);
+        const size_t r = cbase + (size_t)j * bsz;
+        unnormalise_grad(dc, c, (swap ? nq : nk)[r * ldn + head], swap ? qscale : 1.f);
+        st8((swap ? dq : dk) + r * (swap ? lddq : lddk) + head * 8, dc);
+    }
+}
+
+size_t geo_attn_bwd_smem_bytes(int L, int S) { return sizeof(float) * ((size_t)L * 18 + (size_t)S * 16); }
+
+}  // namespace sttode

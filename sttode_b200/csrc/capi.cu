@@ -6,6 +6,7 @@
 #include <mutex>
 #include <utility>
 #include <vector>
+#include <algorithm>
 #include "kernels.cuh"
 
 namespace sttode {
@@ -84,11 +85,15 @@ size_t attn_ws_floats(int L, int S, int bsz, bool self_attn, bool want_weights) 
     return f;
 }
 
+struct AttnBufs { float *q, *k, *v; int ldq, ldk; };   // where run_attention left q^, k^, v (k and v share ldk)
+
 // projected q^ (scaled, on-manifold), k^ (on-manifold), v -> o = attention output before out_proj.
+// norms (nullable): |q| and |k| per (row, head) for the backward — [rows,16] (q | k) for self-attention,
+// [rows_q,8] followed by [rows_k,8] otherwise.
 // self-attention layout: one [rows,192] buffer (q^|k^|v).  nb = number of independent (L x bsz) batches.
 int run_attention(const float* xq, const float* xk, const float* xv, bool self_attn, const sttode_mhgsa_weights& w, int L,
                   int S, int bsz, int nb, int score_mode, float clamp_eps, float curv, Carver& ws, float** o_out,
-                  float* attn_weights, cudaStream_t st) {
+                  float* attn_weights, cudaStream_t st, float* norms = nullptr, AttnBufs* bufs = nullptr) {
     const int rows_q = nb * L * bsz, rows_k = nb * S * bsz;
     float *qb, *kb, *vb;
     int ldq, ldk;
@@ -99,7 +104,7 @@ int run_attention(const float* xq, const float* xk, const float* xv, bool self_a
         float* qkv = ws.take<float>((size_t)rows_q * 192);
         if (!qkv) return fail(STTODE_EWORKSPACE, "workspace too small for qkv");
         k_proj<<<ceil_div(rows_q, BM), NTHREADS, proj_smem_bytes(), st>>>(xq, 64, rows_q, w.in_proj_w, w.in_proj_b, 3, qkv, 192,
-                                                                        0x1u, 0x3u, scale, score_mode, curv);
+                                                                        0x1u, 0x3u, scale, score_mode, curv, norms, 16);
         LAUNCH_CHECK("k_proj");
         qb = qkv; kb = qkv + 64; vb = qkv + 128; ldq = ldk = 192;
     } else {
@@ -107,13 +112,13 @@ int run_attention(const float* xq, const float* xk, const float* xv, bool self_a
         float* kv = ws.take<float>((size_t)rows_k * 128);
         if (!qq || !kv) return fail(STTODE_EWORKSPACE, "workspace too small for q/kv");
         k_proj<<<ceil_div(rows_q, BM), NTHREADS, proj_smem_bytes(), st>>>(xq, 64, rows_q, w.in_proj_w, w.in_proj_b, 1, qq, 64,
-                                                                        0x1u, 0x1u, scale, score_mode, curv);
+                                                                        0x1u, 0x1u, scale, score_mode, curv, norms, 8);
         LAUNCH_CHECK("k_proj(q)");
         k_proj<<<ceil_div(rows_k, BM), NTHREADS, proj_smem_bytes(), st>>>(xk, 64, rows_k, w.in_proj_w + 64 * 64, w.in_proj_b + 64, 1,
-                                                                        kv, 128, 0x0u, 0x1u, 1.f, score_mode, curv);
+                                                                        kv, 128, 0x0u, 0x1u, 1.f, score_mode, curv, norms ? norms + (size_t)rows_q * 8 : nullptr, 8);
         LAUNCH_CHECK("k_proj(k)");
         k_proj<<<ceil_div(rows_k, BM), NTHREADS, proj_smem_bytes(), st>>>(xv, 64, rows_k, w.in_proj_w + 128 * 64, w.in_proj_b + 128, 1,
-                                                                        kv + 64, 128, 0x0u, 0x0u, 1.f, score_mode, curv);
+                                                                        kv + 64, 128, 0x0u, 0x0u, 1.f, score_mode, curv, nullptr, 0);
         LAUNCH_CHECK("k_proj(v)");
         qb = qq; ldq = 64; kb = kv; vb = kv + 64; ldk = 128;
     }
@@ -135,6 +140,7 @@ int run_attention(const float* xq, const float* xk, const float* xv, bool self_a
         LAUNCH_CHECK("k_attn_weights");
     }
     *o_out = o;
+    if (bufs) *bufs = AttnBufs{qb, kb, vb, ldq, ldk};
     return 0;
 }
 
@@ -222,6 +228,219 @@ int run_ode_block(const float* x, int L, int bsz, int nb, const sttode_ode_weigh
 size_t ode_ws_bytes(int rows, int L, int method) {
     size_t extra = method == STTODE_ODE_EULER ? 2 : 7;
     return rhs_ws_bytes(rows, L) + extra * align_up((size_t)rows * 64 * 4);
+}
+
+// ---- backward of the MHGSA / ODE right-hand side (kernels in backward.cu) ----------------------------------
+// C[M,N] = epi(A . B) with arbitrary strides; see k_gemm.
+int gemm(cudaStream_t st, int M, int N, int K, const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C, long ldc,
+         const float* bias = nullptr, const float* res = nullptr, long ldres = 0, const float* mask = nullptr, long ldmask = 0,
+         int relu = 0, int accumulate = 0) {
+    k_gemm<<<dim3(ceil_div(N, 64), ceil_div(M, 64)), 256, 0, st>>>(M, N, K, A, sam, sak, B, sbk, sbn, C, ldc, bias, res, ldres, mask, ldmask,
+                                                                  relu, accumulate);
+    LAUNCH_CHECK("k_gemm");
+    return 0;
+}
+// y[rows,N] = x[rows,K] . W[N,K]^T + b
+int gemm_nt(cudaStream_t st, int rows, int N, int K, const float* x, long ldx, const float* W, const float* b, float* y, long ldy,
+            int relu = 0, const float* res = nullptr, long ldres = 0) {
+    return gemm(st, rows, N, K, x, ldx, 1, W, 1, K, y, ldy, b, res, ldres, nullptr, 0, relu, 0);
+}
+// dx[rows,K] = dy[rows,N] . W[N,K]  (+ res) (* mask)
+int gemm_nn(cudaStream_t st, int rows, int K, int N, const float* dy, long lddy, const float* W, float* dx, long lddx,
+            const float* res = nullptr, long ldres = 0, const float* mask = nullptr, long ldmask = 0, int accumulate = 0) {
+    return gemm(st, rows, K, N, dy, lddy, 1, W, K, 1, dx, lddx, nullptr, res, ldres, mask, ldmask, 0, accumulate);
+}
+// dW[N,K] += dy[rows,N]^T . x[rows,K];  db[N] += column sums of dy   (either may be null)
+int weight_grad(cudaStream_t st, int rows, int N, int K, const float* dy, long lddy, const float* x, long ldx, float* dW, float* db) {
+    int rc;
+    if (dW && (rc = gemm(st, N, K, rows, dy, 1, lddy, x, ldx, 1, dW, K, nullptr, nullptr, 0, nullptr, 0, 0, 1))) return rc;
+    if (db) {
+        k_colsum<<<ceil_div(N, 32), 256, 0, st>>>(dy, lddy, rows, N, db);
+        LAUNCH_CHECK("k_colsum");
+    }
+    return 0;
+}
+
+size_t attn_bwd_ws_bytes(int rows_q, int rows_k, bool self_attn) {
+    // forward buffers (q^|k^|v, o, norms) + d o + d(q|k|v)
+    size_t b = self_attn ? align_up((size_t)rows_q * 192 * 4) : align_up((size_t)rows_q * 64 * 4) + align_up((size_t)rows_k * 128 * 4);
+    b += align_up((size_t)rows_q * 64 * 4);                               // o
+    b += align_up(((size_t)rows_q + rows_k) * 8 * 4);                     // norms
+    b += align_up((size_t)rows_q * 64 * 4);                               // d o
+    b += align_up((size_t)rows_q * 64 * 4) + 2 * align_up((size_t)rows_k * 64 * 4);   // d q, d k, d v (raw projections)
+    return b;
+}
+
+// Backward through in-projection + geodesic attention, given d o (gradient of the pre-out_proj attention output).
+// Recomputes q^, k^, v, o; writes gradients w.r.t. the three inputs (dxq always; dxk/dxv only when !self_attn —
+// self-attention sums the three into dxq) and accumulates the in_proj parameter gradients.
+// res (nullable) is added to dxq (the residual branch of the caller).
+struct AttnFwd { float *o, *norms; AttnBufs b; };
+int attention_recompute(const float* xq, const float* xk, const float* xv, bool self_attn, const sttode_mhgsa_weights& w, int L, int S, int bsz,
+                        int nb, float clamp_eps, Carver& ws, AttnFwd* f, cudaStream_t st) {
+    const int rows_q = nb * L * bsz, rows_k = nb * S * bsz;
+    f->norms = ws.take<float>(((size_t)rows_q + rows_k) * 8);
+    if (!f->norms) return fail(STTODE_EWORKSPACE, "workspace too small for the head norms");
+    return run_attention(xq, xk, xv, self_attn, w, L, S, bsz, nb, STTODE_SCORE_OBLIQUE_ACOS, clamp_eps, 1.f, ws, &f->o, nullptr, st, f->norms, &f->b);
+}
+int attention_bwd(const float* xq, const float* xk, const float* xv, bool self_attn, const sttode_mhgsa_weights& w, const sttode_mhgsa_grads* gw,
+                  const AttnFwd& f, const float* d_o, int L, int S, int bsz, int nb, float clamp_eps, const float* res, long ldres, float* dxq,
+                  float* dxk, float* dxv, Carver& ws, cudaStream_t st) {
+    int rc;
+    const int rows_q = nb * L * bsz, rows_k = nb * S * bsz;
+    float* dq = ws.take<float>((size_t)rows_q * 64);
+    float* dk = ws.take<float>((size_t)rows_k * 64);
+    float* dv = ws.take<float>((size_t)rows_k * 64);
+    if (!dq || !dk || !dv) return fail(STTODE_EWORKSPACE, "workspace too small for the attention gradients");
+    const size_t sm = geo_attn_bwd_smem_bytes(L, S);
+    if ((rc = set_smem(k_geo_attn_bwd, sm, "k_geo_attn_bwd"))) return rc;
+    const float lo = (float)(-1.0 + (double)clamp_eps), hi = (float)(1.0 - (double)clamp_eps);
+    const float* nq = f.norms;
+    const float* nk = self_attn ? f.norms + 8 : f.norms + (size_t)rows_q * 8;
+    k_geo_attn_bwd<<<nb * bsz * 8, 128, sm, st>>>(f.b.q, f.b.ldq, f.b.k, f.b.ldk, f.b.v, f.b.ldk, nq, nk, self_attn ? 16 : 8, d_o, 64, dq, 64, dk, 64,
+                                                  dv, 64, L, S, bsz, L == S, lo, hi, 0.35355339059327379f);
+    LAUNCH_CHECK("k_geo_attn_bwd");
+    const float* W = w.in_proj_w;
+    if (gw) {
+        if ((rc = weight_grad(st, rows_q, 64, 64, dq, 64, xq, 64, gw->in_proj_w, gw->in_proj_b))) return rc;
+        if ((rc = weight_grad(st, rows_k, 64, 64, dk, 64, xk, 64, gw->in_proj_w ? gw->in_proj_w + 64 * 64 : nullptr, gw->in_proj_b ? gw->in_proj_b + 64 : nullptr))) return rc;
+        if ((rc = weight_grad(st, rows_k, 64, 64, dv, 64, xv, 64, gw->in_proj_w ? gw->in_proj_w + 128 * 64 : nullptr, gw->in_proj_b ? gw->in_proj_b + 128 : nullptr))) return rc;
+    }
+    if ((rc = gemm_nn(st, rows_q, 64, 64, dq, 64, W, dxq, 64, res, ldres))) return rc;
+    if (self_attn) {
+        if ((rc = gemm_nn(st, rows_k, 64, 64, dk, 64, W + 64 * 64, dxq, 64, nullptr, 0, nullptr, 0, 1))) return rc;
+        if ((rc = gemm_nn(st, rows_k, 64, 64, dv, 64, W + 128 * 64, dxq, 64, nullptr, 0, nullptr, 0, 1))) return rc;
+    } else {
+        if ((rc = gemm_nn(st, rows_k, 64, 64, dk, 64, W + 64 * 64, dxk, 64))) return rc;
+        if ((rc = gemm_nn(st, rows_k, 64, 64, dv, 64, W + 128 * 64, dxv, 64))) return rc;
+    }
+    return 0;
+}
+
+size_t rhs_bwd_ws_bytes(int rows, int L) {
+    const size_t r64 = align_up((size_t)rows * 64 * 4), rff = align_up((size_t)rows * STTODE_FF * 4);
+    return attn_bwd_ws_bytes(rows, rows, true) + 14 * r64 + 2 * rff + (L > 1 ? 0 : align_up((size_t)rows * 192 * 4));
+}
+
+// dx = J_f(x)^T df for f = TransformerEncoder_ode.forward (or Hypattention.forward when gate_only), parameter gradients
+// accumulated into gw (nullable, members nullable).  Re-materialises the forward intermediates of x first.
+int run_rhs_bwd(const float* x, const float* df, long lddf, int L, int bsz, int nb, const sttode_ode_weights& w, const sttode_ode_grads* gw,
+                float* dx, int gate_only, Carver ws, cudaStream_t st) {
+    int rc;
+    const int R = nb * L * bsz;
+    const int eb = ceil_div(R * 64, 256), wb = ceil_div(R, 8);
+    // ---- forward re-materialisation
+    AttnFwd f{};
+    const float* o;
+    long ldo;
+    float* vraw = nullptr;
+    if (L > 1) {
+        if ((rc = attention_recompute(x, x, x, true, w.attn, L, L, bsz, nb, 1e-4f, ws, &f, st))) return rc;
+        o = f.o; ldo = 64;
+    } else {                                    // one key: o is the value projection
+        vraw = ws.take<float>((size_t)R * 64);
+        if (!vraw) return fail(STTODE_EWORKSPACE, "workspace too small (value projection)");
+        if ((rc = gemm_nt(st, R, 64, 64, x, 64, w.attn.in_proj_w + 128 * 64, w.attn.in_proj_b + 128, vraw, 64))) return rc;
+        o = vraw; ldo = 64;
+    }
+    float* a = ws.take<float>((size_t)R * 64);
+    float* ui = ws.take<float>((size_t)R * 64);
+    float* ug = ws.take<float>((size_t)R * 64);
+    float* dui = ws.take<float>((size_t)R * 64);
+    float* dug = ws.take<float>((size_t)R * 64);
+    float* da = ws.take<float>((size_t)R * 64);
+    float* d_o = ws.take<float>((size_t)R * 64);
+    if (!a || !ui || !ug || !dui || !dug || !da || !d_o) return fail(STTODE_EWORKSPACE, "workspace too small for the gate chain");
+    if ((rc = gemm_nt(st, R, 64, 64, o, ldo, w.attn.out_proj_w, w.attn.out_proj_b, a, 64))) return rc;
+    if ((rc = gemm_nt(st, R, 64, 64, a, 64, w.info_w, w.info_b, ui, 64))) return rc;
+    if ((rc = gemm_nt(st, R, 64, 64, a, 64, w.gate_w, w.gate_b, ug, 64))) return rc;
+    const float* dg = df;                       // gradient w.r.t. the gate output
+    long lddg = lddf;
+    float* dz1 = nullptr;
+    if (!gate_only) {
+        float* z1 = ws.take<float>((size_t)R * 64);
+        float* s1 = ws.take<float>((size_t)R * 64);
+        float* h1 = ws.take<float>((size_t)R * STTODE_FF);
+        float* z2 = ws.take<float>((size_t)R * 64);
+        float* dz2 = ws.take<float>((size_t)R * 64);
+        float* tmp = ws.take<float>((size_t)R * 64);
+        float* dpre = ws.take<float>((size_t)R * STTODE_FF);
+        float* ds1 = ws.take<float>((size_t)R * 64);
+        dz1 = ws.take<float>((size_t)R * 64);
+        if (!z1 || !s1 || !h1 || !z2 || !dz2 || !tmp || !dpre || !ds1 || !dz1) return fail(STTODE_EWORKSPACE, "workspace too small for the FFN chain");
+        k_gate_ln_fwd<<<wb, 256, 0, st>>>(x, ui, ug, w.norm1_g, w.norm1_b, z1, s1, R);
+        LAUNCH_CHECK("k_gate_ln_fwd");
+        if ((rc = gemm_nt(st, R, STTODE_FF, 64, s1, 64, w.lin1_w, w.lin1_b, h1, STTODE_FF, 1))) return rc;
+        if ((rc = gemm_nt(st, R, 64, STTODE_FF, h1, STTODE_FF, w.lin2_w, w.lin2_b, z2, 64, 0, s1, 64))) return rc;
+        // ---- backward: LN2, FFN, LN1
+        k_ln_bwd<<<wb, 256, 0, st>>>(z2, w.norm2_g, df, lddf, dz2, tmp, R);
+        LAUNCH_CHECK("k_ln_bwd");
+        if (gw) {
+            if ((rc = weight_grad(st, R, 64, 64, tmp, 64, nullptr, 0, nullptr, gw->norm2_g))) return rc;
+            if ((rc = weight_grad(st, R, 64, 64, df, lddf, nullptr, 0, nullptr, gw->norm2_b))) return rc;
+            if ((rc = weight_grad(st, R, 64, STTODE_FF, dz2, 64, h1, STTODE_FF, gw->lin2_w, gw->lin2_b))) return rc;
+        }
+        if ((rc = gemm_nn(st, R, STTODE_FF, 64, dz2, 64, w.lin2_w, dpre, STTODE_FF, nullptr, 0, h1, STTODE_FF))) return rc;   // * relu'
+        if (gw && (rc = weight_grad(st, R, STTODE_FF, 64, dpre, STTODE_FF, s1, 64, gw->lin1_w, gw->lin1_b))) return rc;
+        if ((rc = gemm_nn(st, R, 64, STTODE_FF, dpre, STTODE_FF, w.lin1_w, ds1, 64, dz2, 64))) return rc;
+        k_ln_bwd<<<wb, 256, 0, st>>>(z1, w.norm1_g, ds1, 64, dz1, tmp, R);
+        LAUNCH_CHECK("k_ln_bwd");
+        if (gw) {
+            if ((rc = weight_grad(st, R, 64, 64, tmp, 64, nullptr, 0, nullptr, gw->norm1_g))) return rc;
+            if ((rc = weight_grad(st, R, 64, 64, ds1, 64, nullptr, 0, nullptr, gw->norm1_b))) return rc;
+        }
+        dg = dz1; lddg = 64;
+    }
+    // ---- gate, out_proj
+    k_gate_bwd<<<eb, 256, 0, st>>>(ui, ug, dg, lddg, dui, dug, R);
+    LAUNCH_CHECK("k_gate_bwd");
+    if (gw) {
+        if ((rc = weight_grad(st, R, 64, 64, dui, 64, a, 64, gw->info_w, gw->info_b))) return rc;
+        if ((rc = weight_grad(st, R, 64, 64, dug, 64, a, 64, gw->gate_w, gw->gate_b))) return rc;
+    }
+    if ((rc = gemm_nn(st, R, 64, 64, dui, 64, w.info_w, da, 64))) return rc;
+    if ((rc = gemm_nn(st, R, 64, 64, dug, 64, w.gate_w, da, 64, nullptr, 0, nullptr, 0, 1))) return rc;
+    if (gw && (rc = weight_grad(st, R, 64, 64, da, 64, o, ldo, gw->attn.out_proj_w, gw->attn.out_proj_b))) return rc;
+    if ((rc = gemm_nn(st, R, 64, 64, da, 64, w.attn.out_proj_w, d_o, 64))) return rc;
+    // ---- attention + in-projection; the residual x -> z1 joins here (dz1), Hypattention alone has none
+    if (L > 1) return attention_bwd(x, x, x, true, w.attn, gw ? &gw->attn : nullptr, f, d_o, L, L, bsz, nb, 1e-4f, dz1, 64, dx, nullptr, nullptr, ws, st);
+    if (gw && (rc = weight_grad(st, R, 64, 64, d_o, 64, x, 64, gw->attn.in_proj_w ? gw->attn.in_proj_w + 128 * 64 : nullptr,
+                                gw->attn.in_proj_b ? gw->attn.in_proj_b + 128 : nullptr))) return rc;
+    return gemm_nn(st, R, 64, 64, d_o, 64, w.attn.in_proj_w + 128 * 64, dx, 64, dz1, 64);
+}
+
+size_t ode_bwd_ws_bytes(int rows, int L, int n_steps) {
+    return ((size_t)n_steps + 3) * align_up((size_t)rows * 64 * 4) + std::max(rhs_bwd_ws_bytes(rows, L), rhs_ws_bytes(rows, L));
+}
+
+// Backward of run_ode_block for the explicit Euler grid: states are recomputed forward, then
+//   g_n = dy * [x_n > 0]  (final relu),   g_s = g_{s+1} + J_f(x_s)^T (h g_{s+1}),   dx = g_0.
+int run_ode_block_bwd(const float* x, const float* dy, long lddy, int L, int bsz, int nb, const sttode_ode_weights& w, const sttode_ode_grads* gw,
+                      int n_steps, float h, int final_relu, float* dx, Carver ws, cudaStream_t st) {
+    int rc;
+    const int R = nb * L * bsz, eb = ceil_div(R * 64, 256);
+    std::vector<const float*> state(n_steps + 1);
+    state[0] = x;
+    for (int s = 1; s <= n_steps; ++s) {
+        float* p = ws.take<float>((size_t)R * 64);
+        if (!p) return fail(STTODE_EWORKSPACE, "workspace too small for the solver states");
+        if ((rc = run_rhs(state[s - 1], L, bsz, nb, w, state[s - 1], 64, h, 0, p, 64, ws, st))) return rc;
+        state[s] = p;
+    }
+    float* g = ws.take<float>((size_t)R * 64);
+    float* hg = ws.take<float>((size_t)R * 64);
+    float* dxs = ws.take<float>((size_t)R * 64);
+    if (!g || !hg || !dxs) return fail(STTODE_EWORKSPACE, "workspace too small for the adjoint state");
+    k_rows_axpb<<<eb, 256, 0, st>>>(dy, lddy, 1.f, final_relu ? state[n_steps] : nullptr, 64, nullptr, 0, n_steps == 0 ? dx : g, 64, R);
+    LAUNCH_CHECK("k_rows_axpb");
+    for (int s = n_steps - 1; s >= 0; --s) {
+        k_rows_axpb<<<eb, 256, 0, st>>>(g, 64, h, nullptr, 0, nullptr, 0, hg, 64, R);
+        LAUNCH_CHECK("k_rows_axpb");
+        if ((rc = run_rhs_bwd(state[s], hg, 64, L, bsz, nb, w, gw, dxs, 0, ws, st))) return rc;
+        k_rows_axpb<<<eb, 256, 0, st>>>(g, 64, 1.f, nullptr, 0, dxs, 64, s == 0 ? dx : g, 64, R);
+        LAUNCH_CHECK("k_rows_axpb");
+    }
+    return 0;
 }
 
 int check_model(const sttode_model_weights* w, bool need_enc = true, bool need_dec = true) {
@@ -427,7 +646,7 @@ int sttode_mhgsa_fwd(const float* query, const float* key, const float* value, c
     float* o = nullptr;
     if ((rc = run_attention(query, key, value, self_attn, *w, L, S, bsz, 1, score_mode, clamp_eps, curvature, ws, &o, attn_weights, st))) return rc;
     // out_proj (hyptransformerlib.py:305): reuse k_proj with a single unscaled, un-normalised block
-    k_proj<<<ceil_div(L * bsz, BM), NTHREADS, proj_smem_bytes(), st>>>(o, 64, L * bsz, w->out_proj_w, w->out_proj_b, 1, out, 64, 0u, 0u, 1.f, 0, 1.f);
+    k_proj<<<ceil_div(L * bsz, BM), NTHREADS, proj_smem_bytes(), st>>>(o, 64, L * bsz, w->out_proj_w, w->out_proj_b, 1, out, 64, 0u, 0u, 1.f, 0, 1.f, nullptr, 0);
     LAUNCH_CHECK("k_proj(out)");
     return 0;
 }
@@ -437,7 +656,7 @@ int sttode_linear64(const float* x, const float* weight, const float* bias, floa
     if (!x || !weight || !bias || !out || rows < 1) return fail(STTODE_EINVAL, "linear64: bad argument");
     if (out_features < 64 || out_features % 64 != 0 || out_features > 64 * 32) return fail(STTODE_EUNSUPPORTED, "linear64: out_features must be a multiple of 64 (<= 2048)");
     if ((rc = set_smem(k_proj, proj_smem_bytes(), "k_proj"))) return rc;
-    k_proj<<<ceil_div(rows, BM), NTHREADS, proj_smem_bytes(), (cudaStream_t)stream>>>(x, 64, rows, weight, bias, out_features / 64, out, out_features, 0u, 0u, 1.f, 0, 1.f);
+    k_proj<<<ceil_div(rows, BM), NTHREADS, proj_smem_bytes(), (cudaStream_t)stream>>>(x, 64, rows, weight, bias, out_features / 64, out, out_features, 0u, 0u, 1.f, 0, 1.f, nullptr, 0);
     LAUNCH_CHECK("k_proj(linear64)");
     return 0;
 }
@@ -465,6 +684,57 @@ int sttode_hypattention_fwd(const float* x, const sttode_ode_weights* w, float* 
     if (!x || !w || !out) return fail(STTODE_EINVAL, "null pointer");
     if (L < 1 || bsz < 1) return fail(STTODE_EINVAL, "bad shape");
     return run_rhs(x, L, bsz, 1, *w, nullptr, 0, 1.f, 0, out, 64, Carver(workspace, workspace_bytes), (cudaStream_t)stream, 1);
+}
+
+// ---- backward entry points -------------------------------------------------------------------------------
+size_t sttode_mhgsa_bwd_workspace_bytes(int L, int S, int bsz) {
+    return attn_bwd_ws_bytes(L * bsz, S * bsz, false) + align_up((size_t)L * bsz * 192 * 4) + 1024;
+}
+
+int sttode_mhgsa_bwd(const float* query, const float* key, const float* value, const sttode_mhgsa_weights* w, const float* dout,
+                     float* dquery, float* dkey, float* dvalue, const sttode_mhgsa_grads* grads, int L, int S, int bsz, int E, int H,
+                     int score_mode, float clamp_eps, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = check_ptrs_mhgsa(w))) return rc;
+    if (!query || !key || !value || !dout || !dquery) return fail(STTODE_EINVAL, "null pointer");
+    if (E != STTODE_D || H != STTODE_H) return fail(STTODE_EUNSUPPORTED, "embed_dim/num_heads must be 64/8 (got %d/%d)", E, H);
+    if (score_mode != STTODE_SCORE_OBLIQUE_ACOS) return fail(STTODE_EUNSUPPORTED, "backward is implemented for the Oblique acos score only");
+    if (L < 1 || S < 1 || bsz < 1) return fail(STTODE_EINVAL, "bad shape L=%d S=%d bsz=%d", L, S, bsz);
+    const bool self_attn = (query == key && key == value);
+    if (self_attn && L != S) return fail(STTODE_EINVAL, "self-attention requires L == S");
+    if (!self_attn && (!dkey || !dvalue)) return fail(STTODE_EINVAL, "dkey/dvalue are required when key/value are separate tensors");
+    Carver ws(workspace, workspace_bytes);
+    AttnFwd f{};
+    if ((rc = attention_recompute(query, key, value, self_attn, *w, L, S, bsz, 1, clamp_eps, ws, &f, st))) return rc;
+    float* d_o = ws.take<float>((size_t)L * bsz * 64);
+    if (!d_o) return fail(STTODE_EWORKSPACE, "workspace too small");
+    if (grads && (rc = weight_grad(st, L * bsz, 64, 64, dout, 64, f.o, 64, grads->out_proj_w, grads->out_proj_b))) return rc;
+    if ((rc = gemm_nn(st, L * bsz, 64, 64, dout, 64, w->out_proj_w, d_o, 64))) return rc;
+    return attention_bwd(query, key, value, self_attn, *w, grads, f, d_o, L, S, bsz, 1, clamp_eps, nullptr, 0, dquery, dkey, dvalue, ws, st);
+}
+
+size_t sttode_ode_rhs_bwd_workspace_bytes(int L, int bsz) { return rhs_bwd_ws_bytes(L * bsz, L) + 1024; }
+
+int sttode_ode_rhs_bwd(const float* x, const float* df, const sttode_ode_weights* w, float* dx, const sttode_ode_grads* grads, int L, int bsz,
+                       int gate_only, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc;
+    if (!x || !df || !w || !dx) return fail(STTODE_EINVAL, "null pointer");
+    if ((rc = check_ptrs_mhgsa(&w->attn))) return rc;
+    if (L < 1 || bsz < 1) return fail(STTODE_EINVAL, "bad shape");
+    return run_rhs_bwd(x, df, 64, L, bsz, 1, *w, grads, dx, gate_only, Carver(workspace, workspace_bytes), (cudaStream_t)stream);
+}
+
+size_t sttode_ode_block_bwd_workspace_bytes(int L, int bsz, int n_steps) { return ode_bwd_ws_bytes(L * bsz, L, n_steps < 1 ? 1 : n_steps) + 1024; }
+
+int sttode_ode_block_bwd(const float* x, const float* dy, int lddy, const sttode_ode_weights* w, float* dx, const sttode_ode_grads* grads, int L,
+                         int bsz, int n_steps, float h, int method, int final_relu, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc;
+    if (!x || !dy || !w || !dx) return fail(STTODE_EINVAL, "null pointer");
+    if ((rc = check_ptrs_mhgsa(&w->attn))) return rc;
+    if (L < 1 || bsz < 1 || lddy < 64 || n_steps < 1) return fail(STTODE_EINVAL, "bad shape L=%d bsz=%d lddy=%d n_steps=%d", L, bsz, lddy, n_steps);
+    if (method != STTODE_ODE_EULER) return fail(STTODE_EUNSUPPORTED, "backward is implemented for the Euler grid only (method %d)", method);
+    return run_ode_block_bwd(x, dy, lddy, L, bsz, 1, *w, grads, n_steps, h, final_relu, dx, Carver(workspace, workspace_bytes), (cudaStream_t)stream);
 }
 
 size_t sttode_past_encoder_workspace_bytes(int rows, int L) { return past_encoder_ws(rows, L) + align_up((size_t)rows * 64 * 4) + 1024; }

@@ -193,7 +193,8 @@ __device__ __forceinline__ float group8_sum(float v) {
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_proj(const float* __restrict__ X, int ldx, int rows, const float* __restrict__ W, const float* __restrict__ b, int nblk,
-       float* __restrict__ out, int ldo, unsigned scale_mask, unsigned norm_mask, float scale, int score_mode, float curv) {
+       float* __restrict__ out, int ldo, unsigned scale_mask, unsigned norm_mask, float scale, int score_mode, float curv,
+       float* __restrict__ norms, int ldn) {
     extern __shared__ __align__(16) float smem[];
     float* xs = smem;                      // [BM][68]
     float* wbuf = xs + BM * LDS64;         // [2][64][68]
@@ -221,6 +222,7 @@ k_proj(const float* __restrict__ X, int ldx, int rows, const float* __restrict__
                 if (do_scale) v *= scale;
                 if (do_norm) {   // a head is 8 consecutive columns = 8 consecutive lanes
                     float nrm = sqrtf(group8_sum(v * v));
+                    if (norms && r < rows && (tx & 7) == 0) norms[(size_t)r * ldn + blk * 8 + (n >> 3)] = nrm;   // saved for the backward
                     if (score_mode == STTODE_SCORE_OBLIQUE_ACOS) {
                         v = v / nrm;                                   // oblique.py:16, no epsilon: 0/0 -> NaN as in the reference
                     } else {                                           // expmap0 (pmath.py:300-304) then project (:98-103)

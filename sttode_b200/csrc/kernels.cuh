@@ -10,7 +10,7 @@ __global__ void k_scene_origin(const float* traj, int layout, const int* scene_p
 __global__ void k_prologue(const float* traj, int layout, const int* scene_ptr, const int* row_scene, const float* origin,
                            int rows, int agents, int T, sttode_encoder_weights w, float* x0, int ldx0, float* traj_norm);
 __global__ void k_proj(const float* X, int ldx, int rows, const float* W, const float* b, int nblk, float* out, int ldo,
-                       unsigned scale_mask, unsigned norm_mask, float scale, int score_mode, float curv);
+                       unsigned scale_mask, unsigned norm_mask, float scale, int score_mode, float curv, float* norms, int ldn);
 __global__ void k_geo_attn(const float* rowop, int ldr, const float* colop, int ldc, const float* vals, int ldv, float* out,
                            int ldo, float* denom, int Lr, int Lc, int bsz, int score_mode, float lo, float hi, float curv);
 __global__ void k_attn_weights(const float* rowop, int ldr, const float* colop, int ldc, const float* denom, float* wout,
@@ -24,6 +24,21 @@ size_t linear_smem_bytes(int K);
 size_t prologue_smem_bytes(int T);
 size_t proj_smem_bytes();
 size_t ode_tail_smem_bytes();
+
+// backward.cu
+__global__ void k_gemm(int M, int N, int K, const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C, long ldc,
+                       const float* bias, const float* res, long ldres, const float* mask, long ldmask, int relu, int accumulate);
+__global__ void k_colsum(const float* X, long ldx, int rows, int N, float* out);
+__global__ void k_gate_ln_fwd(const float* x, const float* ui, const float* ug, const float* gamma, const float* beta, float* z1,
+                              float* s1, int rows);
+__global__ void k_ln_bwd(const float* z, const float* gamma, const float* ds, long ldds, float* dz, float* xhat_ds, int rows);
+__global__ void k_gate_bwd(const float* ui, const float* ug, const float* dg, long lddg, float* dui, float* dug, int rows);
+__global__ void k_rows_axpb(const float* a, long lda, float alpha, const float* gate, long ldg, const float* b, long ldb, float* out,
+                            long ldo, int rows);
+__global__ void k_geo_attn_bwd(const float* qh, int ldq, const float* kh, int ldk, const float* v, int ldv, const float* nq,
+                               const float* nk, int ldn, const float* dout, int ldo, float* dq, int lddq, float* dk, int lddk,
+                               float* dv, int lddv, int L, int S, int bsz, int swap, float lo, float hi, float qscale);
+size_t geo_attn_bwd_smem_bytes(int L, int S);
 
 // decoder.cu
 constexpr int ROWPRE_LD = 2048;     // per-row layer-1 partial sums: [P0x | P0y | P1y | P1x], 512 each

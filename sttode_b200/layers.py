@@ -6,7 +6,8 @@ Same class names, constructor signatures, attribute side effects and state_dict 
 (`self_attn.temporal_attention_before.*`, `self_attn.temporal_info.*`, `self_attn.temporal_gate.*`,
 `linear1/2.*`, `norm1/2.*`; prefix `odeblock.odefunc.layers.0.`).  One `ODEG_Encoder.forward` is one
 call of `sttode_ode_block_fwd` (csrc/encoder.cu): the torchdiffeq solver loop, the right-hand side and the
-final ReLU all run in the library.  Forward only in round 1.
+final ReLU all run in the library; each forward is one autograd node whose backward is the library's
+`sttode_ode_rhs_bwd` / `sttode_ode_block_bwd`.
 """
 import copy
 import ctypes as C
@@ -21,22 +22,110 @@ ODE_EULER, ODE_MIDPOINT, ODE_RK4, ODE_RK4_38 = 0, 1, 2, 3
 _METHODS = {"euler": ODE_EULER, "midpoint": ODE_MIDPOINT, "rk4_classic": ODE_RK4, "rk4": ODE_RK4_38}
 
 
-def _ode_struct(layer):
-    """sttode_ode_weights for a TransformerEncoderLayer (or just its Hypattention when `layer` is one)."""
-    s = _lib.OdeWeights()
+_ODE_FIELDS = ("info_w", "info_b", "gate_w", "gate_b", "lin1_w", "lin1_b", "lin2_w", "lin2_b", "norm1_g", "norm1_b", "norm2_g", "norm2_b")
+
+
+def _ode_params(layer):
+    """The 16 tensors of sttode_ode_weights in struct order (only the first 8 exist for a bare Hypattention)."""
     att = layer.self_attn if isinstance(layer, TransformerEncoderLayer) else layer
     mh = att.temporal_attention_before
-    s.attn = _mhgsa_struct(mh.in_proj_weight, mh.in_proj_bias, mh.out_proj.weight, mh.out_proj.bias)
-    s.info_w, s.info_b = _lib.dptr(att.temporal_info.weight), _lib.dptr(att.temporal_info.bias)
-    s.gate_w, s.gate_b = _lib.dptr(att.temporal_gate.weight), _lib.dptr(att.temporal_gate.bias)
+    ps = [mh.in_proj_weight, mh.in_proj_bias, mh.out_proj.weight, mh.out_proj.bias,
+          att.temporal_info.weight, att.temporal_info.bias, att.temporal_gate.weight, att.temporal_gate.bias]
     if isinstance(layer, TransformerEncoderLayer):
         if layer.linear1.weight.shape != (1024, 64):
             raise NotImplementedError("TransformerEncoderLayer on B200: d_model=64, dim_feedforward=1024 only (model/STTODE.py:190-194)")
-        s.lin1_w, s.lin1_b = _lib.dptr(layer.linear1.weight), _lib.dptr(layer.linear1.bias)
-        s.lin2_w, s.lin2_b = _lib.dptr(layer.linear2.weight), _lib.dptr(layer.linear2.bias)
-        s.norm1_g, s.norm1_b = _lib.dptr(layer.norm1.weight), _lib.dptr(layer.norm1.bias)
-        s.norm2_g, s.norm2_b = _lib.dptr(layer.norm2.weight), _lib.dptr(layer.norm2.bias)
+        ps += [layer.linear1.weight, layer.linear1.bias, layer.linear2.weight, layer.linear2.bias,
+               layer.norm1.weight, layer.norm1.bias, layer.norm2.weight, layer.norm2.bias]
+    return ps
+
+
+def _ode_struct_from(tensors, cls=_lib.OdeWeights):
+    """sttode_ode_weights (or sttode_ode_grads) over a list laid out like `_ode_params`."""
+    s = cls()
+    s.attn.in_proj_w, s.attn.in_proj_b, s.attn.out_proj_w, s.attn.out_proj_b = (_lib.dptr(t) for t in tensors[:4])
+    for name, t in zip(_ODE_FIELDS, tensors[4:]):
+        setattr(s, name, _lib.dptr(t))
     return s
+
+
+def _ode_struct(layer):
+    """sttode_ode_weights for a TransformerEncoderLayer (or just its Hypattention when `layer` is one)."""
+    return _ode_struct_from(_ode_params(layer))
+
+
+class _OdeRhsFn(torch.autograd.Function):
+    """f(x) = TransformerEncoderLayer.forward (gate_only = 0) or Hypattention.forward (gate_only = 1) with its backward
+    (sttode_ode_rhs_fwd / sttode_hypattention_fwd / sttode_ode_rhs_bwd).  x [L, bsz, 64]."""
+
+    @staticmethod
+    def forward(ctx, x, gate_only, *params):
+        L, bsz = x.shape[0], x.shape[1]
+        params = [_f32c(p, "parameter") for p in params]
+        out = torch.empty_like(x)
+        lib = _lib.lib()
+        ws = _lib.workspace(lib.sttode_ode_block_workspace_bytes(L, bsz, ODE_EULER), x.device)
+        st = _ode_struct_from(params)
+        fn = lib.sttode_hypattention_fwd if gate_only else lib.sttode_ode_rhs_fwd
+        _lib.check(fn(_lib.dptr(x), C.byref(st), _lib.dptr(out), L, bsz, _lib.dptr(ws), ws.numel(), _lib.stream_ptr()))
+        ctx.save_for_backward(x, *params)
+        ctx.gate_only = gate_only
+        return out
+
+    @staticmethod
+    def backward(ctx, df):
+        x, *params = ctx.saved_tensors
+        L, bsz = x.shape[0], x.shape[1]
+        df = _f32c(df, "grad_output")
+        dx = torch.empty_like(x)
+        grads = [torch.zeros_like(p) for p in params]                # the library accumulates (+=)
+        lib = _lib.lib()
+        ws = _lib.workspace(lib.sttode_ode_rhs_bwd_workspace_bytes(L, bsz), x.device)
+        st, gs = _ode_struct_from(params), _ode_struct_from(grads, _lib.OdeGrads)
+        _lib.check(lib.sttode_ode_rhs_bwd(_lib.dptr(x), _lib.dptr(df), C.byref(st), _lib.dptr(dx), C.byref(gs), L, bsz, int(ctx.gate_only),
+                                          _lib.dptr(ws), ws.numel(), _lib.stream_ptr()))
+        return (dx, None, *grads)
+
+
+class _OdeBlockFn(torch.autograd.Function):
+    """y = [relu](odeint(f, x, grid)[-1]) with its backward (sttode_ode_block_fwd / sttode_ode_block_bwd): the reference
+    back-propagates through torchdiffeq's unrolled solver (adjoint=False, ode_demo.py:7); the library recomputes the
+    solver states and runs the discrete adjoint of the same grid.  x [L, bsz, 64]."""
+
+    @staticmethod
+    def forward(ctx, x, n_steps, h, method, final_relu, *params):
+        L, bsz = x.shape[0], x.shape[1]
+        params = [_f32c(p, "parameter") for p in params]
+        y = torch.empty_like(x)
+        lib = _lib.lib()
+        ws = _lib.workspace(lib.sttode_ode_block_workspace_bytes(L, bsz, method), x.device)
+        st = _ode_struct_from(params)
+        _lib.check(lib.sttode_ode_block_fwd(_lib.dptr(x), C.byref(st), _lib.dptr(y), 64, L, bsz, n_steps, h, method, int(final_relu),
+                                            _lib.dptr(ws), ws.numel(), _lib.stream_ptr()))
+        ctx.save_for_backward(x, *params)
+        ctx.cfg = (n_steps, h, method, final_relu)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, *params = ctx.saved_tensors
+        n_steps, h, method, final_relu = ctx.cfg
+        L, bsz = x.shape[0], x.shape[1]
+        dy = _f32c(dy, "grad_output")
+        dx = torch.empty_like(x)
+        grads = [torch.zeros_like(p) for p in params]
+        lib = _lib.lib()
+        ws = _lib.workspace(lib.sttode_ode_block_bwd_workspace_bytes(L, bsz, n_steps), x.device)
+        st, gs = _ode_struct_from(params), _ode_struct_from(grads, _lib.OdeGrads)
+        _lib.check(lib.sttode_ode_block_bwd(_lib.dptr(x), _lib.dptr(dy), 64, C.byref(st), _lib.dptr(dx), C.byref(gs), L, bsz, n_steps, h, method,
+                                            int(final_relu), _lib.dptr(ws), ws.numel(), _lib.stream_ptr()))
+        return (dx, None, None, None, None, *grads)
+
+
+def _grad_view(t, name):
+    """Contiguous fp32 view that keeps the autograd history (unlike `_f32c`, which detaches)."""
+    if t.dtype != torch.float32:
+        raise _lib.SttodeError(f"{name}: only float32 is implemented on the B200 path (got {t.dtype})")
+    return t.contiguous()
 
 
 def _check_eval_dropout(p, training, what):
@@ -63,13 +152,8 @@ class Hypattention(nn.Module):
             raise NotImplementedError("Hypattention on B200: self-attention only (query is key is value), as on the reference path")
         _check_eval_dropout(self.temporal_attention_before.dropout, self.training, "Hypattention")
         T, N, sn, D = query.shape
-        x = _f32c(query, "query").reshape(T, N * sn, D)
-        out = torch.empty_like(x)
-        lib = _lib.lib()
-        ws = _lib.workspace(lib.sttode_ode_block_workspace_bytes(T, N * sn, ODE_EULER), x.device)
-        st = _ode_struct(self)
-        _lib.check(lib.sttode_hypattention_fwd(_lib.dptr(x), C.byref(st), _lib.dptr(out), T, N * sn, _lib.dptr(ws), ws.numel(),
-                                               _lib.stream_ptr()))
+        x = _grad_view(query, "query").reshape(T, N * sn, D)
+        out = _OdeRhsFn.apply(x, True, *_ode_params(self))
         weights = None
         if need_weights:
             weights = self.temporal_attention_before(x, x, x, need_weights=True)[1]
@@ -95,13 +179,8 @@ class TransformerEncoderLayer(nn.Module):
     def forward(self, src, src_mask=None, src_key_padding_mask=None):
         _check_eval_dropout(self.dropout.p, self.training, "TransformerEncoderLayer")
         shape = src.shape
-        x = _f32c(src, "src").reshape(shape[0], -1, shape[-1])
-        out = torch.empty_like(x)
-        lib = _lib.lib()
-        ws = _lib.workspace(lib.sttode_ode_block_workspace_bytes(x.shape[0], x.shape[1], ODE_EULER), x.device)
-        st = _ode_struct(self)
-        _lib.check(lib.sttode_ode_rhs_fwd(_lib.dptr(x), C.byref(st), _lib.dptr(out), x.shape[0], x.shape[1], _lib.dptr(ws),
-                                          ws.numel(), _lib.stream_ptr()))
+        x = _grad_view(src, "src").reshape(shape[0], -1, shape[-1])
+        out = _OdeRhsFn.apply(x, False, *_ode_params(self))
         return out.reshape(shape)
 
 
@@ -146,17 +225,10 @@ class ODEblock_en(nn.Module):
         layer = self.odefunc.layers[0]
         _check_eval_dropout(layer.dropout.p, layer.training, "ODEblock_en")
         shape = x.shape
-        xs = _f32c(x, "x").reshape(shape[0], -1, shape[-1])
-        L, bsz = xs.shape[0], xs.shape[1]
-        y = torch.empty_like(xs)
+        xs = _grad_view(x, "x").reshape(shape[0], -1, shape[-1])
         span = float(self.t[-1]) - float(self.t[0])
-        lib = _lib.lib()
         method = _METHODS[self.method]
-        ws = _lib.workspace(lib.sttode_ode_block_workspace_bytes(L, bsz, method), xs.device)
-        st = _ode_struct(layer)
-        _lib.check(lib.sttode_ode_block_fwd(_lib.dptr(xs), C.byref(st), _lib.dptr(y), 64, L, bsz, self.n_steps,
-                                            span / self.n_steps, method, int(final_relu), _lib.dptr(ws), ws.numel(),
-                                            _lib.stream_ptr()))
+        y = _OdeBlockFn.apply(xs, self.n_steps, span / self.n_steps, method, bool(final_relu), *_ode_params(layer))
         return y.reshape(shape)
 
     def forward(self, x):

@@ -5,7 +5,7 @@ Same names, argument meaning, state_dict keys (`in_proj_weight`, `in_proj_bias`,
 `out_proj.bias`) and error behaviour; the arithmetic runs in libsttode_sm100.so (csrc/encoder.cu:
 k_proj -> k_geo_attn -> k_proj).  Options the reference accepts but whose code path is dead or
 commented out there (masks, bias_kv, zero_attn, dropout > 0 in training) raise instead of silently
-differing.  Forward only in round 1: tensors returned do not carry autograd history.
+differing.  Differentiable: forward and backward are one autograd node over sttode_mhgsa_fwd / sttode_mhgsa_bwd.
 """
 import ctypes as C
 
@@ -105,20 +105,66 @@ def hyp_mhsa(query, key, value, embed_dim_to_check, num_heads, in_proj_weight, i
     if in_proj_bias is None or out_proj_bias is None:
         raise NotImplementedError("hyp_mhsa on B200: bias=False is not implemented")
     S = key.shape[0]
-    q = _f32c(query, "query")
     self_attn = (key is query or (key.data_ptr() == query.data_ptr() and key.shape == query.shape)) and \
                 (value is key or (value.data_ptr() == key.data_ptr() and value.shape == key.shape))
-    k = q if self_attn else _f32c(key, "key")
-    v = q if self_attn else _f32c(value, "value")
-    out = torch.empty(L, bsz, E, device=q.device, dtype=torch.float32)
-    w = torch.empty(bsz, L, S, device=q.device, dtype=torch.float32) if need_weights else None
-    lib = _lib.lib()
-    ws = _lib.workspace(lib.sttode_mhgsa_workspace_bytes(L, S, bsz), q.device)
-    st = _mhgsa_struct(in_proj_weight, in_proj_bias, out_proj_weight, out_proj_bias)
-    _lib.check(lib.sttode_mhgsa_fwd(_lib.dptr(q), _lib.dptr(k), _lib.dptr(v), C.byref(st), _lib.dptr(out), _lib.dptr(w),
-                                    L, S, bsz, E, num_heads, score_mode, float(np.float32(OBLIQUE_EPS[torch.float32])),
-                                    float(curvature), _lib.dptr(ws), ws.numel(), _lib.stream_ptr()))
-    return out, w
+    out, w = _MhgsaFn.apply(query, None if self_attn else key, None if self_attn else value, in_proj_weight, in_proj_bias,
+                            out_proj_weight, out_proj_bias, num_heads, bool(need_weights), score_mode, float(curvature))
+    return out, (w if need_weights else None)
+
+
+def _clamp_eps():
+    return float(np.float32(OBLIQUE_EPS[torch.float32]))
+
+
+class _MhgsaFn(torch.autograd.Function):
+    """sttode_mhgsa_fwd / sttode_mhgsa_bwd as one autograd node (the reference differentiates hyptransformerlib.py:29-311
+    with torch autograd).  key/value None = the self-attention branch (:113-115).  The backward re-materialises the forward
+    from the inputs, so nothing but the inputs is saved.  The head-averaged weights output is not differentiable here."""
+
+    @staticmethod
+    def forward(ctx, query, key, value, in_w, in_b, out_w, out_b, num_heads, need_weights, score_mode, curvature):
+        L, bsz, E = query.shape
+        q = _f32c(query, "query")
+        self_attn = key is None
+        k = q if self_attn else _f32c(key, "key")
+        v = q if self_attn else _f32c(value, "value")
+        S = k.shape[0]
+        out = torch.empty(L, bsz, E, device=q.device, dtype=torch.float32)
+        w = torch.empty(bsz, L, S, device=q.device, dtype=torch.float32) if need_weights else None
+        lib = _lib.lib()
+        ws = _lib.workspace(lib.sttode_mhgsa_workspace_bytes(L, S, bsz), q.device)
+        params = [_f32c(t, n) for t, n in ((in_w, "in_proj_weight"), (in_b, "in_proj_bias"), (out_w, "out_proj.weight"), (out_b, "out_proj.bias"))]
+        st = _mhgsa_struct(*params)
+        _lib.check(lib.sttode_mhgsa_fwd(_lib.dptr(q), _lib.dptr(k), _lib.dptr(v), C.byref(st), _lib.dptr(out), _lib.dptr(w),
+                                        L, S, bsz, E, num_heads, score_mode, _clamp_eps(), curvature, _lib.dptr(ws), ws.numel(),
+                                        _lib.stream_ptr()))
+        ctx.save_for_backward(q, k, v, *params)
+        ctx.cfg = (self_attn, num_heads, score_mode)
+        if w is None:
+            w = out.new_empty(0)
+        ctx.mark_non_differentiable(w)
+        return out, w
+
+    @staticmethod
+    def backward(ctx, dout, _dw):
+        q, k, v, in_w, in_b, out_w, out_b = ctx.saved_tensors
+        self_attn, num_heads, score_mode = ctx.cfg
+        L, bsz, E = q.shape
+        S = k.shape[0]
+        dout = _f32c(dout, "grad_output")
+        dq = torch.empty_like(q)
+        dk = None if self_attn else torch.empty_like(k)
+        dv = None if self_attn else torch.empty_like(v)
+        grads = [torch.zeros_like(t) for t in (in_w, in_b, out_w, out_b)]       # the library accumulates (+=)
+        gs = _lib.MhgsaGrads()
+        gs.in_proj_w, gs.in_proj_b, gs.out_proj_w, gs.out_proj_b = (_lib.dptr(g) for g in grads)
+        lib = _lib.lib()
+        ws = _lib.workspace(lib.sttode_mhgsa_bwd_workspace_bytes(L, S, bsz), q.device)
+        st = _mhgsa_struct(in_w, in_b, out_w, out_b)
+        _lib.check(lib.sttode_mhgsa_bwd(_lib.dptr(q), _lib.dptr(k), _lib.dptr(v), C.byref(st), _lib.dptr(dout), _lib.dptr(dq), _lib.dptr(dk),
+                                        _lib.dptr(dv), C.byref(gs), L, S, bsz, E, num_heads, score_mode, _clamp_eps(), _lib.dptr(ws),
+                                        ws.numel(), _lib.stream_ptr()))
+        return (dq, dk, dv, *grads, None, None, None, None)
 
 
 class Hyp_mhsa(nn.Module):

@@ -156,3 +156,43 @@ def test_dist_matrix_closed_form_fp64():
     y = PO.project(torch.randn(7, 8, generator=g, dtype=torch.float64) * 0.4)
     for c in (1.0, 0.7):
         np.testing.assert_allclose(PO.dist_matrix_closed_form(x, y, c).numpy(), PO.dist_matrix(x, y, c).numpy(), rtol=1e-9, atol=1e-9)
+
+
+# ------------------------------------------------------------------ gradients (training config): oracle autograd vs the reference's
+def _leaf_sd(sd, prefix):
+    sd = dict(sd)
+    leaves = {}
+    for k in sd:
+        if k.startswith(prefix) and sd[k].is_floating_point():
+            sd[k] = sd[k].clone().requires_grad_(True)
+            leaves[k[len(prefix):]] = sd[k]
+    return sd, leaves
+
+
+@pytest.mark.parametrize("name", ["sq5", "x46"])
+def test_mhgsa_gradients_match_reference(golden, sd_eth, name):
+    gi, gb = golden("mhgsa"), golden("backward")
+    sd, leaves = _leaf_sd(sd_eth, ATT)
+    q = torch.from_numpy(gi[f"{name}_q"]).requires_grad_(True)
+    square = gi[f"{name}_q"].shape == gi[f"{name}_kv"].shape
+    kv = q if square else torch.from_numpy(gi[f"{name}_kv"]).requires_grad_(True)
+    out, _ = O.hyp_mhsa(q, kv, kv, sd[ATT + "in_proj_weight"], sd[ATT + "in_proj_bias"], sd[ATT + "out_proj.weight"], sd[ATT + "out_proj.bias"])
+    out.backward(torch.from_numpy(gb[f"mhgsa_{name}_dout"]))
+    assert rel(q.grad, gb[f"mhgsa_{name}_dq"]) < 5e-6
+    if not square:
+        assert rel(kv.grad, gb[f"mhgsa_{name}_dkv"]) < 5e-6
+    for n, leaf in leaves.items():
+        assert rel(leaf.grad, gb[f"mhgsa_{name}_g_{n}"]) < 5e-6, n
+
+
+@pytest.mark.parametrize("name", ["L1", "L6"])
+def test_ode_block_gradients_match_reference(golden, sd_eth, name):
+    gi, gb = golden("ode_block"), golden("backward")
+    prefix = "past_encoder.ODE_Encoder."
+    sd, leaves = _leaf_sd(sd_eth, prefix)
+    x = torch.from_numpy(gi[f"{name}_x"]).requires_grad_(True)
+    O.ode_encoder(x, sd, "past_encoder.").backward(torch.from_numpy(gb[f"ode_{name}_dy"]))
+    assert rel(x.grad, gb[f"ode_{name}_dx"]) < 5e-6
+    for n, leaf in leaves.items():
+        got = leaf.grad if leaf.grad is not None else torch.zeros_like(leaf)
+        assert rel(got, gb[f"ode_{name}_g_{n}"]) < 5e-6 or np.abs(gb[f"ode_{name}_g_{n}"]).max() == 0, n
