@@ -1,6 +1,6 @@
 """Generate tests/golden/*.npz by running the UNMODIFIED reference (under oracle/ref_shim.py) here.
 
-Run in the build container only (needs /root/reference):   python oracle/make_golden.py [forward|backward|all]
+Run in the build container only (needs /root/reference):   python oracle/make_golden.py [forward|backward|training|all]
 The fixtures pin `oracle/sttode_oracle.py` and `oracle/pmath_oracle.py` to the reference's own outputs and
 travel to the GPU box, where /root/reference does not exist.  Weights are NOT stored: both sides rebuild
 them with `make_state_dict(seed)`; the reference side loads them with `load_state_dict(strict=True)`,
@@ -185,8 +185,72 @@ def backward_golden():
     print("backward.npz", os.path.getsize(os.path.join(OUT, "backward.npz")))
 
 
+class _MaskDropout(torch.nn.Module):
+    """Stands in for PositionalAgentEncoding.dropout (nn.Dropout(0.1), model/STTODE.py:140): same arithmetic
+    (x * mask / (1 - p)) with the Bernoulli mask injected so both sides use the same draw."""
+
+    def __init__(self, mask, p=0.1):
+        super().__init__()
+        self.mask, self.p = mask, p
+
+    def forward(self, x):
+        return x * (self.mask.to(x.dtype) / (1.0 - self.p))
+
+
+def training_draws(R, tp, tf, seed):
+    """Every random draw of one training step, from one seeded generator (shared with tests/test_gpu_training.py)."""
+    g = torch.Generator().manual_seed(seed)
+    return dict(mask_past=(torch.rand(R, tp, 64, generator=g) >= 0.1).float(), mask_future=(torch.rand(R, tf, 64, generator=g) >= 0.1).float(),
+                eps_q=torch.randn(R, 32, generator=g), eps_mid=torch.randn(R, 32, generator=g), eps_p=torch.randn(R * 20, 32, generator=g),
+                theta_u=torch.rand(1, generator=g))
+
+
+def grad_sample_index(numel, count=512):
+    return torch.linspace(0, numel - 1, min(numel, count)).round().long()
+
+
+def training_golden():
+    """One training step of the reference itself in train() mode (train.py:61-65: set_data* -> forward -> backward) with every
+    random draw injected: loss tuple + the gradient of all parameters.  Weights are the reference's own default init under
+    torch.manual_seed(3) (sttode_b200.net.STTODENet reproduces it bit for bit, tests/test_host_logic.py)."""
+    ref = ref_shim.install()
+    rec = {}
+    for name, dataset, tp, tf, B, N in (("nba", "nba", 10, 20, 8, 11), ("eth", "eth", 8, 12, 1, 7)):
+        torch.manual_seed(3)
+        m = ref.sttode.STTODENet(ref_shim.make_args(dataset, tp, tf), torch.device("cpu")).train()
+        R = B * N
+        d = training_draws(R, tp, tf, seed=40 + B)
+        m.past_encoder.pos_encoder.dropout = _MaskDropout(d["mask_past"])
+        m.future_encoder.pos_encoder.dropout = _MaskDropout(d["mask_future"])
+        queue = [d["eps_q"], d["eps_mid"], d["eps_p"]]
+        ref.sttode.Normal.rsample = lambda self: self.mu + queue.pop(0) * self.sigma
+        if dataset == "nba":
+            m.set_data_nba(synth.nba_batch(2, B, N, tp, tf))
+        else:
+            obs, gt = synth.eth_scene(3, N)
+            orig_rand = torch.rand
+            torch.rand = lambda *a, **k: d["theta_u"].clone()        # the uniform draw behind the rotation angle (model/STTODE.py:423)
+            try:
+                m.set_data(None, obs, gt, torch.ones(N, tp), torch.ones(N, tf))
+            finally:
+                torch.rand = orig_rand
+        m.zero_grad(set_to_none=True)
+        total, lp, lr, lk, ld = m.forward()
+        total.backward()
+        rec[f"{name}_losses"] = np.array([float(total), lp, lr, lk, ld], np.float64)
+        for n, p_ in m.named_parameters():           # fixtures stay small: <= 512 evenly spaced entries + norm + max per tensor
+            g_ = (p_.grad if p_.grad is not None else torch.zeros_like(p_)).detach().flatten()
+            rec[f"{name}_g_{n}"] = np32(g_[grad_sample_index(g_.numel())])
+            rec[f"{name}_gstat_{n}"] = np.array([float(g_.double().norm()), float(g_.abs().max())], np.float64)
+        rec[f"{name}_has_grad"] = np.array([p_.grad is not None for _, p_ in m.named_parameters()])
+    np.savez_compressed(os.path.join(OUT, "training_step.npz"), **rec)
+    print("training_step.npz", os.path.getsize(os.path.join(OUT, "training_step.npz")))
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("training", "all"):
+        training_golden()
     if what in ("forward", "all"):
         main()
     if what in ("backward", "all"):

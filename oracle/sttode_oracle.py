@@ -166,27 +166,30 @@ def add_category(x):
     return torch.cat((x, cat.repeat(B, 1, 1)), dim=-1)
 
 
-def encoder_prologue(inputs, B, N, sd, prefix):
-    """PastEncoder.forward up to the ODE block (model/STTODE.py:214-223), eval mode (PE dropout off)."""
+def encoder_prologue(inputs, B, N, sd, prefix, drop_mask=None):
+    """PastEncoder.forward up to the ODE block (model/STTODE.py:214-223).  drop_mask None = eval mode (PE dropout off);
+    a 0/1 mask [B*N,T,64] = train mode with that Bernoulli draw (nn.Dropout(0.1): x * mask / 0.9, :140,176)."""
     T = inputs.shape[1]
     tf_in = F.linear(inputs, sd[prefix + "input_fc.weight"], sd[prefix + "input_fc.bias"]).view(B * N, T, D_MODEL)
     pe = sd[prefix + "pos_encoder.pe"][:T][None].repeat(B * N, 1, 1)
     tf_pos = F.linear(torch.cat([tf_in, pe], dim=-1), sd[prefix + "pos_encoder.fc.weight"], sd[prefix + "pos_encoder.fc.bias"])
+    if drop_mask is not None:
+        tf_pos = tf_pos * (drop_mask.to(tf_pos.dtype) / (1.0 - 0.1))
     tf_pos = tf_pos.view(B, N, T, D_MODEL)
     x = F.linear(tf_pos.contiguous().view(B, N, T * D_MODEL), sd[prefix + "input_fc2.weight"], sd[prefix + "input_fc2.bias"])
     return F.linear(add_category(x), sd[prefix + "input_fc3.weight"], sd[prefix + "input_fc3.bias"])   # [B,N,64]
 
 
-def past_encoder(inputs, B, N, sd, prefix="past_encoder."):
+def past_encoder(inputs, B, N, sd, prefix="past_encoder.", drop_mask=None):
     """model/STTODE.py:214-236 -> [B*N, 128] = cat(pre-ODE feature, ODE output)."""
-    x0 = encoder_prologue(inputs, B, N, sd, prefix)
+    x0 = encoder_prologue(inputs, B, N, sd, prefix, drop_mask)
     y = ode_encoder(x0.unsqueeze(2), sd, prefix).squeeze(2)
     return torch.cat((x0, y), dim=-1).view(B * N, -1)
 
 
-def future_encoder(inputs_post, B, N, past_feature, sd, prefix="future_encoder."):
-    """FutureEncoder.forward (model/STTODE.py:276-300), eval mode -> q(z) parameters [B*N, 2*zdim]."""
-    x0 = encoder_prologue(inputs_post, B, N, sd, prefix)
+def future_encoder(inputs_post, B, N, past_feature, sd, prefix="future_encoder.", drop_mask=None):
+    """FutureEncoder.forward (model/STTODE.py:276-300) -> q(z) parameters [B*N, 2*zdim]."""
+    x0 = encoder_prologue(inputs_post, B, N, sd, prefix, drop_mask)
     y = ode_encoder(x0.unsqueeze(2), sd, prefix).squeeze(2)
     ff = torch.cat((x0, y), dim=-1).view(B * N, -1)
     h = torch.relu(F.linear(torch.cat((past_feature, ff), dim=-1), sd[prefix + "out_mlp.affine_layers.0.weight"],
@@ -200,13 +203,17 @@ def posterior_inputs(past_traj, future_traj):
     return torch.cat((future_traj, vel), dim=-1)
 
 
-def training_objective(sd, past_traj, future_traj, B, N, eps_q, eps_p, min_clip=2.0):
-    """STTODENet.forward (model/STTODE.py:553-568) in eval mode with the two live rsample draws injected
-    (eps_q [R,32] for q(z|x,y); eps_p [R*20,32] for the prior samples of the best-of-20 term).
-    Returns (total, pred, recover, kl, diverse) as python floats plus the q(z) parameters."""
-    R = B * N
-    pf = past_encoder(velocity_features(past_traj), B, N, sd)
-    qz = future_encoder(posterior_inputs(past_traj, future_traj), B, N, pf, sd)
+def training_objective(sd, past_traj, future_traj, B, N, eps_q, eps_p, min_clip=2.0, masks=None, features=None, tensors=False):
+    """STTODENet.forward (model/STTODE.py:553-568) with the two live rsample draws injected (eps_q [R,32] for q(z|x,y);
+    eps_p [R*20,32] for the prior samples of the best-of-20 term).  masks None = eval mode; (mask_past, mask_future) = train
+    mode with those PE-dropout draws.  features = (inputs, inputs_for_posterior) when they are not the NBA-style ones derived
+    from the trajectories (ETH staging keeps un-normalised velocities, model/STTODE.py:432-457).
+    Returns (total, pred, recover, kl, diverse) as python floats plus the q(z) parameters; tensors=True keeps `total` a
+    tensor with autograd history (sd entries that require grad receive the reference's gradients)."""
+    inputs, inputs_post = features if features is not None else (velocity_features(past_traj), posterior_inputs(past_traj, future_traj))
+    mp_, mf_ = masks if masks is not None else (None, None)
+    pf = past_encoder(inputs, B, N, sd, drop_mask=mp_)
+    qz = future_encoder(inputs_post, B, N, pf, sd, drop_mask=mf_)
     mu, logvar = torch.chunk(qz, 2, dim=-1)
     zq = mu + eps_q * torch.exp(0.5 * logvar)
     cur = past_traj[:, [-1]]
@@ -219,7 +226,8 @@ def training_objective(sd, past_traj, future_traj, B, N, eps_q, eps_p, min_clip=
     div, _ = decoder(pf.repeat_interleave(20, dim=0), eps_p, past_traj, cur, 20, sd, mode="inference")      # [R,20,Tf,2]
     loss_div = (future_traj.unsqueeze(1) - div).pow(2).sum(dim=-1).sum(dim=-1).min(dim=1)[0].mean()
     total = loss_pred + loss_rec + loss_kl + loss_div
-    return dict(total=float(total), pred=float(loss_pred), recover=float(loss_rec), kl=float(loss_kl), diverse=float(loss_div), qz=qz)
+    return dict(total=total if tensors else float(total.detach()), pred=float(loss_pred.detach()), recover=float(loss_rec.detach()), kl=float(loss_kl.detach()),
+                diverse=float(loss_div.detach()), qz=qz)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -294,6 +302,27 @@ def eth_scene_normalise(obs_traj):
     pre_motion = obs_traj.permute(2, 0, 1)                      # [T,N,2]
     scene_orig = pre_motion[[-1]].view(-1, 2).mean(dim=0)
     return (pre_motion - scene_orig).permute(1, 0, 2), scene_orig
+
+
+def eth_train_staging(obs_traj, gt_traj, theta):
+    """STTODENet.set_data in train() mode (model/STTODE.py:397-461) without agent subsampling: rotation by `theta` about the
+    scene origin (rotation_2d_torch, :6-14).  obs [N,2,T_p], gt [N,2,T_f] -> (inputs, inputs_for_posterior, past, future)."""
+    pre, fut = obs_traj.permute(2, 0, 1), gt_traj.permute(2, 0, 1)
+    orig = pre[[-1]].view(-1, 2).mean(dim=0)
+
+    def rot(x):
+        nx = x - orig
+        out = torch.zeros_like(x)
+        out[..., 0] = nx[..., 0] * torch.cos(theta) - nx[..., 1] * torch.sin(theta)
+        out[..., 1] = nx[..., 0] * torch.sin(theta) + nx[..., 1] * torch.cos(theta)
+        return out + orig, out
+    pre, pre_n = rot(pre)
+    fut, fut_n = rot(fut)
+    pre_vel = pre[1:] - pre[:-1]
+    pre_vel = torch.cat([pre_vel[[0]], pre_vel], dim=0)
+    fut_vel = fut - torch.cat([pre[[-1]], fut[:-1]])
+    return (torch.cat([pre_n, pre_vel], dim=-1).permute(1, 0, 2), torch.cat([fut_n, fut_vel], dim=-1).permute(1, 0, 2),
+            pre_n.permute(1, 0, 2), fut_n.permute(1, 0, 2))
 
 
 def velocity_features(past_traj):

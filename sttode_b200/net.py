@@ -8,8 +8,11 @@ features, past encoder (front end + tensor-ODE block with MHGSA), K-sample decod
 run inside libsttode_sm100.so.  `forecast_scenes` is the batched form (many ETH/SDD scenes per launch) the
 reference does not have.
 
-Round-1 scope: inference.  `forward()` (the training losses, model/STTODE.py:553-568) needs the backward
-kernels scheduled for round 2 and raises NotImplementedError; FutureEncoder exists for state_dict parity.
+Training (`train()` mode; train.py:55-95): `forward()` returns the reference's loss tuple with autograd history.  The
+MHGSA / tensor-ODE blocks of both encoders run forward and backward in libsttode_sm100 (autograd nodes over
+sttode_ode_block_fwd / _bwd); the thin layers around them and the decoder are torch ops in train() mode so that autograd
+reaches their parameters (their fused inference kernels are the eval() path).  `eval()` + `forward()` evaluates the same
+objective forward-only, entirely in the library.
 """
 import ctypes as C
 import math
@@ -17,6 +20,7 @@ import math
 import numpy as np
 import torch
 from torch import nn
+import torch.nn.functional as F
 
 from . import _lib
 from .layers import ODEG_Encoder, TransformerEncoderLayer, _ode_struct
@@ -42,6 +46,13 @@ class MLP(nn.Module):
         super().__init__()
         dims = [input_dim, *hidden_size, output_dim]
         self.layers = nn.ModuleList(nn.Linear(a, b) for a, b in zip(dims[:-1], dims[1:]))
+
+    def forward(self, x):                        # train() mode only (model/utils.py:88-95)
+        for i, layer in enumerate(self.layers):
+            x = layer(x)
+            if i != len(self.layers) - 1:
+                x = torch.relu(x)
+        return x
 
 
 class MLP2(nn.Module):
@@ -143,9 +154,10 @@ class PastEncoder(_EncoderBase):
 
 
 def _encoder_forward(enc, inputs, batch_size, agent_num):
-    """Front end + tensor-ODE block on explicit [x, y, vx, vy] features -> [B*N, 128] (sttode_encoder_fwd)."""
+    """Front end + tensor-ODE block on explicit [x, y, vx, vy] features -> [B*N, 128].
+    eval(): one library call (sttode_encoder_fwd), no autograd history.  train(): differentiable (see `_encoder_forward_train`)."""
     if enc.training:
-        raise NotImplementedError("encoders on B200: eval mode only in round 1 (PE dropout 0.1 is live in training, model/STTODE.py:197,256)")
+        return _encoder_forward_train(enc, inputs, batch_size, agent_num)
     feat = _f32c(inputs, "inputs")
     rows, T = feat.shape[0], feat.shape[1]
     if feat.shape[-1] != 4 or rows != batch_size * agent_num:
@@ -157,6 +169,31 @@ def _encoder_forward(enc, inputs, batch_size, agent_num):
     _lib.check(lib.sttode_encoder_fwd(_lib.dptr(feat), rows, batch_size, agent_num, T, C.byref(st), _lib.dptr(out), _lib.dptr(ws), ws.numel(),
                                       _lib.stream_ptr()))
     return out
+
+
+def _encoder_forward_train(enc, inputs, batch_size, agent_num):
+    """train() mode (model/STTODE.py:214-236 with the PE dropout of :140,176 live).  The MHGSA / tensor-ODE block — the
+    path this library exists for — runs forward AND backward in libsttode_sm100 (one autograd node, sttode_ode_block_fwd/_bwd).
+    The thin front end around it (input_fc, PE fc, dropout, flatten fc, category fc; 2 % of the step) is expressed with
+    torch ops so autograd can reach its parameters; its fused forward kernel (k_prologue) is the eval() path.
+    `enc.dropout_mask_override` ([R,T,64] of 0/1) replaces the Bernoulli draw (tests)."""
+    rows, T = inputs.shape[0], inputs.shape[1]
+    if inputs.shape[-1] != 4 or rows != batch_size * agent_num:
+        raise _lib.SttodeError("encoder inputs must be [batch_size*agent_num, T, 4]")
+    if not inputs.is_cuda:
+        raise _lib.SttodeError("encoder inputs must be CUDA tensors; this path has no CPU implementation")
+    h = F.linear(inputs, enc.input_fc.weight, enc.input_fc.bias)
+    pe = enc.pos_encoder.pe[:T].unsqueeze(0).expand(rows, T, 64)
+    h = F.linear(torch.cat((h, pe), dim=-1), enc.pos_encoder.fc.weight, enc.pos_encoder.fc.bias)
+    mask = getattr(enc, "dropout_mask_override", None)
+    p = enc.pos_encoder.dropout.p
+    h = F.dropout(h, p, True) if mask is None else h * (mask.to(h) / (1.0 - p))
+    h = F.linear(h.reshape(batch_size, agent_num, T * 64), enc.input_fc2.weight, enc.input_fc2.bias)
+    cat = torch.zeros(agent_num, 3, device=h.device, dtype=h.dtype)
+    cat[agent_num - 1, 2] = 1                                                   # model/STTODE.py:199-210
+    x0 = F.linear(torch.cat((h, cat.expand(batch_size, agent_num, 3)), dim=-1), enc.input_fc3.weight, enc.input_fc3.bias)
+    y = enc.ODE_Encoder(x0.unsqueeze(2), mask=None, num_agent=agent_num).squeeze(2)
+    return torch.cat((x0, y), dim=-1).view(rows, 128)
 
 
 def _linear(x, layer, relu):
@@ -177,8 +214,11 @@ class FutureEncoder(_EncoderBase):
         initialize_weights(self.qz_layer.modules())
 
     def forward(self, inputs, batch_size, agent_num, past_feature):
-        """-> q(z | past, future) parameters [B*N, 2*zdim] (model/STTODE.py:276-300); forward only."""
+        """-> q(z | past, future) parameters [B*N, 2*zdim] (model/STTODE.py:276-300)."""
         ff = _encoder_forward(self, inputs, batch_size, agent_num)
+        if self.training:
+            h = torch.relu(self.out_mlp.affine_layers[0](torch.cat((past_feature, ff), dim=-1)))
+            return self.qz_layer(h)
         h = torch.cat((_f32c(past_feature, "past_feature"), ff), dim=-1)
         h = _linear(h, self.out_mlp.affine_layers[0], relu=True)
         return _linear(h, self.qz_layer, relu=False)
@@ -200,6 +240,23 @@ class DecomposeBlock(nn.Module):
         nn.init.zeros_(self.conv_past.bias)
         nn.init.zeros_(self.encoder_past.bias_ih_l0)
         nn.init.zeros_(self.encoder_past.bias_hh_l0)
+
+    def forward(self, x_true, x_hat, f):
+        """Differentiable form used in train() mode (model/STTODE.py:51-77); inference runs k_dec_row_tc / k_dec_pair_tc.
+        The GRU recurrence is unrolled with fp32 matmuls (cuDNN's RNN path drops to TF32 on sm_100, which costs ~2e-4 in the
+        gradients); same gate order and arithmetic as nn.GRU (r, z, n; n = tanh(W_in x + b_in + r * (W_hn h + b_hn)))."""
+        emb = torch.relu(F.conv1d((x_true - x_hat).transpose(1, 2), self.conv_past.weight, self.conv_past.bias, padding=1)).transpose(1, 2)
+        g = self.encoder_past
+        gi_all = F.linear(emb, g.weight_ih_l0, g.bias_ih_l0)                      # [rows, T, 288]
+        h = emb.new_zeros(emb.shape[0], 96)
+        for t in range(emb.shape[1]):
+            gi, gh = gi_all[:, t], F.linear(h, g.weight_hh_l0, g.bias_hh_l0)
+            r = torch.sigmoid(gi[:, :96] + gh[:, :96])
+            zt = torch.sigmoid(gi[:, 96:192] + gh[:, 96:192])
+            n = torch.tanh(gi[:, 192:] + r * gh[:, 192:])
+            h = (1 - zt) * n + zt * h
+        feat = torch.cat((f, h), dim=1)
+        return self.decoder_x(feat).view(-1, self.past_len, 2), self.decoder_y(feat).view(-1, self.future_len, 2)
 
 
 def _mlp3_struct(mlp):
@@ -274,6 +331,8 @@ class Decoder(nn.Module):
         Returns (out_seq, recover_pre_seq).  Every (agent, sample) pair is treated as its own row (K = 1 inside
         the library) so arbitrary per-pair features are honoured; STTODENet.inference uses the de-duplicated
         path instead."""
+        if self.training:
+            return self._forward_train(past_feature, z, past_traj, cur_location, sample_num, mode)
         pf = _f32c(past_feature, "past_feature")
         zz = _f32c(z, "z").reshape(-1, 32)
         pairs = pf.shape[0]
@@ -294,6 +353,36 @@ class Decoder(nn.Module):
         if mode == "inference":
             out = out.view(-1, sample_num, self.future_length, 2)
         return out, recon
+
+
+def _decoder_forward_train(self, past_feature, z, past_traj, cur_location, sample_num, mode):
+    """train() mode: the reference's op sequence (model/STTODE.py:320-347) with autograd history."""
+    if not past_feature.is_cuda:
+        raise _lib.SttodeError("Decoder inputs must be CUDA tensors; this path has no CPU implementation")
+    x_true = past_traj.repeat_interleave(sample_num, dim=0)
+    hidden = torch.cat((past_feature.view(-1, sample_num, past_feature.shape[-1]), z.view(-1, sample_num, z.shape[-1])), dim=-1)
+    hidden = hidden.view(x_true.shape[0], -1)
+    x_hat = torch.zeros_like(x_true)
+    pred, rec = 0, 0
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):       # fp32 Conv1d: TF32 would break the 1e-4 budget
+        for blk in self.decompose:
+            x_hat, y_hat = blk(x_true, x_hat, hidden)
+            pred, rec = pred + y_hat, rec + x_hat
+    out = pred + cur_location.repeat_interleave(sample_num, dim=0)
+    if mode == "inference":
+        out = out.view(-1, sample_num, *out.shape[1:])
+    return out, rec
+
+
+Decoder._forward_train = _decoder_forward_train
+
+
+def _rotation_2d(x, theta, origin):
+    """model/STTODE.py:6-14: rotate about `origin`; returns (rotated, rotated - origin)."""
+    nx = x - origin
+    c, sn = torch.cos(theta), torch.sin(theta)
+    rot = torch.stack((nx[..., 0] * c - nx[..., 1] * sn, nx[..., 0] * sn + nx[..., 1] * c), dim=-1)
+    return rot + origin, rot
 
 
 class ForecastGraph:
@@ -391,15 +480,47 @@ class STTODENet(nn.Module):
 
     # ---- data staging (reference call sequence) ---------------------------------------------------
     def set_data(self, batch, pre_motion, fut_motion, pre_motion_mask, fut_motion_mask):
-        """ETH/UCY/SDD: pre_motion [N,2,T_p] as the loaders yield it (model/STTODE.py:397-461), eval mode."""
-        if self.training:
-            raise NotImplementedError("set_data in training mode (random rotation / agent subsampling) is on the training path; round 2")
+        """ETH/UCY/SDD: pre_motion [N,2,T_p], fut_motion [N,2,T_f] as the loaders yield them (model/STTODE.py:397-461).
+        eval(): staging only (normalisation and velocities run inside sttode_forecast).  train(): the reference's agent
+        subsampling (np.random.choice, > max_train_agent) and random scene rotation, then the explicit feature tensors."""
         self.batch_size = 1
-        self._obs = _f32c(pre_motion.to(self.device), "pre_motion")
-        self.agent_num = self._obs.shape[0]
-        self.pre_motion_mask, self.fut_motion_mask = pre_motion_mask, fut_motion_mask
-        self.fut_motion_orig = fut_motion.transpose(1, 2) if fut_motion is not None else None
         self._mode = "scene"
+        pre = pre_motion.to(self.device)
+        if not self.training:
+            self._obs = _f32c(pre, "pre_motion")
+            self.agent_num = self._obs.shape[0]
+            self.pre_motion_mask, self.fut_motion_mask = pre_motion_mask, fut_motion_mask
+            self.fut_motion_orig = fut_motion.transpose(1, 2) if fut_motion is not None else None
+            return
+        dev = self.device
+        fut = fut_motion.to(dev)
+        fut_orig = fut.transpose(1, 2)
+        pre, fut = pre.permute(2, 0, 1), fut.permute(2, 0, 1)                         # [T,N,2]
+        if pre.shape[1] > self.max_train_agent:                                       # model/STTODE.py:405-413
+            ind = torch.tensor(np.random.choice(pre.shape[1], self.max_train_agent).tolist(), device=dev)
+            pre, fut = pre.index_select(1, ind).contiguous(), fut.index_select(1, ind).contiguous()
+            pre_motion_mask, fut_motion_mask = pre_motion_mask.to(dev).index_select(0, ind), fut_motion_mask.to(dev).index_select(0, ind)
+            fut_orig = fut_orig.index_select(0, ind).contiguous()
+        self.agent_num = pre.shape[1]
+        self.scene_orig = pre[[-1]].view(-1, 2).mean(dim=0)
+        if self.rand_rot_scene:                                                       # :419-426
+            theta = getattr(self, "theta_override", None)
+            if theta is None:
+                theta = (torch.randint(high=24, size=(1,)).to(dev) * (np.pi / 12)) if self.discrete_rot else torch.rand(1).to(dev) * np.pi * 2
+            pre, pre_norm = _rotation_2d(pre, theta, self.scene_orig)
+            fut, fut_norm = _rotation_2d(fut, theta, self.scene_orig)
+            fut_orig, _ = _rotation_2d(fut_orig, theta, self.scene_orig)
+        else:
+            pre_norm, fut_norm = pre - self.scene_orig, fut - self.scene_orig
+        pre_vel = pre[1:] - pre[:-1]
+        pre_vel = torch.cat([pre_vel[[0]], pre_vel], dim=0)
+        fut_vel = fut - torch.cat([pre[[-1]], fut[:-1]])
+        self.pre_motion_mask, self.fut_motion_mask, self.fut_motion_orig = pre_motion_mask, fut_motion_mask, fut_orig
+        self.inputs = torch.cat([pre_norm, pre_vel], dim=-1).permute(1, 0, 2).contiguous()
+        self.inputs_for_posterior = torch.cat([fut_norm, fut_vel], dim=-1).permute(1, 0, 2).contiguous()
+        self.past_traj = pre_norm.permute(1, 0, 2).contiguous()
+        self.future_traj = fut_norm.permute(1, 0, 2).contiguous()
+        self.cur_location = self.past_traj[:, [-1]]
 
     def set_data_nba(self, data):
         """NBA: data['past_traj'] [B,N,T_p,2] (model/STTODE.py:463-486)."""
@@ -472,44 +593,56 @@ class STTODENet(nn.Module):
         """CUDA-graph version of `forecast_scenes` (n_scenes > 0, L = 1) or of NBA-style inference (n_scenes = 0) for a fixed shape."""
         return ForecastGraph(self, rows, L, agents, n_scenes, layout, sample_k).capture()
 
-    # ---- training objective (forward only; the backward kernels are round-2 work) -----------------------------
-    @torch.no_grad()
+    # ---- training objective -----------------------------------------------------------------------------------------------
+    def _stage_features(self):
+        """(inputs [R,T_p,4], inputs_for_posterior [R,T_f,4], past [R,T_p,2], future [R,T_f,2]) of the staged batch."""
+        if getattr(self, "_mode", None) == "nba":                                   # model/STTODE.py:463-481
+            dev, B, N = self.device, self.batch_size, self.agent_num
+            past = _f32c(self.data["past_traj"].to(dev), "past_traj").view(B * N, self.args.past_length, 2)
+            fut = _f32c(self.data["future_traj"].to(dev), "future_traj").view(B * N, self.args.future_length, 2)
+            vel = past[:, 1:] - past[:, :-1]
+            inputs = torch.cat((past, torch.cat([vel[:, [0]], vel], dim=1)), dim=-1)
+            fvel = fut - torch.cat([past[:, [-1]], fut[:, :-1]], dim=1)
+            self.scene_orig = self.past_traj = past
+            self.future_traj, self.cur_location = fut, past[:, [-1]]
+            return inputs, torch.cat((fut, fvel), dim=-1), past, fut
+        if getattr(self, "_mode", None) == "scene" and self.training:
+            return self.inputs, self.inputs_for_posterior, self.past_traj, self.future_traj
+        raise NotImplementedError("STTODENet.forward: stage the batch with set_data_nba, or with set_data in train() mode "
+                                  "(eval-mode set_data keeps only what inference needs)")
+
     def forward(self):
-        """The reference's training objective (model/STTODE.py:553-568) evaluated forward-only on the staged batch:
-        returns (total_loss tensor WITHOUT autograd history, loss_pred, loss_recover, loss_kl, loss_diverse).
-        Needs eval() mode (PE dropout and the random scene rotation are train-mode only) and `set_data_nba`.
-        `self.eps_override = (eps_q [R,zdim], eps_p [R*20,zdim])` injects the two live rsample draws."""
-        if self.training:
-            raise NotImplementedError("STTODENet.forward in train() mode needs the backward kernels (round 2); call it under eval() for the loss values")
-        if getattr(self, "_mode", None) != "nba":
-            raise NotImplementedError("STTODENet.forward on B200: stage the batch with set_data_nba (ETH staging with rotation is train-mode only)")
+        """The reference's training objective (model/STTODE.py:553-568) on the staged batch:
+        (total_loss, loss_pred, loss_recover, loss_kl, loss_diverse).  train(): total_loss carries autograd history (call
+        .backward() on it as train.py:65 does).  eval(): forward-only, every stage inside the library.
+        `self.eps_override = (eps_q [R,zdim], eps_p [R*20,zdim])` injects the two live rsample draws (tests)."""
         args, dev = self.args, self.device
-        B, N, Tp, Tf = self.batch_size, self.agent_num, args.past_length, args.future_length
-        R = B * N
-        past = _f32c(self.data["past_traj"].to(dev), "past_traj").view(R, Tp, 2)
-        fut = _f32c(self.data["future_traj"].to(dev), "future_traj").view(R, Tf, 2)
-        vel = past[:, 1:] - past[:, :-1]
-        inputs = torch.cat((past, torch.cat([vel[:, [0]], vel], dim=1)), dim=-1)
-        fvel = fut - torch.cat([past[:, [-1]], fut[:, :-1]], dim=1)
-        self.past_feature = self.past_encoder(inputs, B, N)
-        self.qz_param = self.future_encoder(torch.cat((fut, fvel), dim=-1), B, N, self.past_feature)
-        mu, logvar = torch.chunk(self.qz_param, 2, dim=-1)
-        sigma = torch.exp(0.5 * logvar)
-        eps = getattr(self, "eps_override", None)
-        eps_q = eps[0].to(dev) if eps is not None else torch.randn_like(sigma)
-        eps_p = eps[1].to(dev) if eps is not None else torch.randn(R * 20, args.zdim, device=dev)
-        self.qz_sampled = mu + eps_q * sigma
-        cur = past[:, [-1]]
-        self.pred_traj, self.recover_traj = self.decoder(self.past_feature, self.qz_sampled, B, N, past, cur, sample_num=1)
-        loss_pred = (fut - self.pred_traj).pow(2).sum() / B / Tf
-        loss_recover = (past - self.recover_traj).pow(2).sum() / B / Tp
-        kl = 0.5 * ((mu / (1 + 1e-8)) ** 2 + (sigma / (1 + 1e-8)) ** 2) - 0.5 - torch.log(sigma / (1 + 1e-8))      # KL(q || N(0, I)), Normal.kl
-        loss_kl = (kl.sum() / (B * N)).clamp_min(args.min_clip)
-        self.past_feature_repeat = self.past_feature.repeat_interleave(20, dim=0)
-        self.diverse_pred_traj, _ = self.decoder(self.past_feature_repeat, eps_p, B, N, past, cur, sample_num=20, mode="inference")
-        diff = fut.unsqueeze(1) - self.diverse_pred_traj
-        loss_diverse = diff.pow(2).sum(dim=-1).sum(dim=-1).min(dim=1)[0].mean()
-        total = loss_pred + loss_recover + loss_kl + loss_diverse
+        with torch.set_grad_enabled(self.training and torch.is_grad_enabled()):
+            inputs, inputs_post, past, fut = self._stage_features()
+            B, N, Tp, Tf = self.batch_size, self.agent_num, args.past_length, args.future_length
+            R = B * N
+            self.past_feature = self.past_encoder(inputs, B, N)
+            self.qz_param = self.future_encoder(inputs_post, B, N, self.past_feature)
+            self.qz_distribution = Normal(params=self.qz_param)
+            mu, sigma = self.qz_distribution.mu, self.qz_distribution.sigma
+            eps = getattr(self, "eps_override", None)
+            eps_q = eps[0].to(dev) if eps is not None else torch.randn_like(sigma)
+            self.qz_sampled = mu + eps_q * sigma
+            self.pz_distribution = Normal(mu=torch.zeros(R, args.zdim, device=dev), logvar=torch.zeros(R, args.zdim, device=dev))
+            if eps is None:
+                torch.randn_like(sigma)          # the reference draws pz_distribution.rsample() here and discards it (:525)
+            cur = past[:, [-1]]
+            self.pred_traj, self.recover_traj = self.decoder(self.past_feature, self.qz_sampled, B, N, past, cur, sample_num=1)
+            eps_p = eps[1].to(dev) if eps is not None else torch.randn(R * 20, args.zdim, device=dev)
+            self.pz_sampled = eps_p
+            loss_pred = (fut - self.pred_traj).pow(2).sum() / B / Tf                  # :372-376
+            loss_recover = (past - self.recover_traj).pow(2).sum() / B / Tp          # :384-387
+            loss_kl = (self.qz_distribution.kl(self.pz_distribution).sum() / (B * N)).clamp_min(args.min_clip)     # :378-382
+            self.past_feature_repeat = self.past_feature.repeat_interleave(20, dim=0)
+            self.diverse_pred_traj, _ = self.decoder(self.past_feature_repeat, eps_p, B, N, past, cur, sample_num=20, mode="inference")
+            diff = fut.unsqueeze(1) - self.diverse_pred_traj                          # :389-395
+            loss_diverse = diff.pow(2).sum(dim=-1).sum(dim=-1).min(dim=1)[0].mean()
+            total = loss_pred + loss_recover + loss_kl + loss_diverse
         return total, loss_pred.item(), loss_recover.item(), loss_kl.item(), loss_diverse.item()
 
     def step_annealer(self):

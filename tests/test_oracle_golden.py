@@ -196,3 +196,28 @@ def test_ode_block_gradients_match_reference(golden, sd_eth, name):
     for n, leaf in leaves.items():
         got = leaf.grad if leaf.grad is not None else torch.zeros_like(leaf)
         assert rel(got, gb[f"ode_{name}_g_{n}"]) < 5e-6 or np.abs(gb[f"ode_{name}_g_{n}"]).max() == 0, n
+
+
+# ------------------------------------------------------------------ one whole training step of the reference (train() mode)
+@pytest.mark.parametrize("name", ["nba", "eth"])
+def test_training_step_matches_reference(golden, name):
+    """Oracle objective + torch autograd vs the reference's own train()-mode step: loss tuple and the gradient of every
+    parameter (PE-dropout masks, rsample draws and the rotation angle injected on both sides)."""
+    from training_common import CASES, case_inputs, check_against_golden, theta_of
+    from sttode_b200.net import STTODENet
+    dataset, tp, tf, B, N = CASES[name]
+    torch.manual_seed(3)
+    sd = {k: v.clone() for k, v in STTODENet(synth.make_args(dataset, tp, tf), torch.device("cpu")).state_dict().items()}
+    names = [k for k in sd if not k.endswith("pos_encoder.pe")]
+    for k in names:
+        sd[k].requires_grad_(True)
+    d, data = case_inputs(name)
+    if dataset == "nba":
+        past, fut, feats = data["past_traj"].view(B * N, tp, 2), data["future_traj"].view(B * N, tf, 2), None
+    else:
+        inputs, inputs_post, past, fut = O.eth_train_staging(data[0], data[1], theta_of(d))
+        feats = (inputs, inputs_post)
+    out = O.training_objective(sd, past, fut, B, N, d["eps_q"], d["eps_p"], masks=(d["mask_past"], d["mask_future"]), features=feats, tensors=True)
+    out["total"].backward()
+    losses = (out["total"], out["pred"], out["recover"], out["kl"], out["diverse"])
+    check_against_golden(golden("training_step"), name, losses, [(k, sd[k].grad) for k in names], 2e-5)
