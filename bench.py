@@ -369,6 +369,67 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """BASELINE.json configs[4] (not the headline metric): STTODE training step — forward + backward through both MHGSA /
+    tensor-ODE blocks in libsttode_sm100, data-parallel, one NCCL all-reduce of the flat 6.4 MB gradient buffer per step.
+    NBA shape (B = 32 scenes x 11 agents per rank, obs 10 / pred 20, train.py:24), synthetic batches, reference default init."""
+    import torch.distributed as dist
+    import sttode_b200._lib as L
+    from sttode_b200 import parallel, synth
+    from sttode_b200.net import STTODENet
+    rank, local_rank, world = dist_env()
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    L.lib()
+    B, N, tp, tf = args.train_batch, 11, 10, 20
+    torch.manual_seed(1)                                         # train.py:110: identical initial weights on every rank
+    model = STTODENet(synth.make_args("nba", tp, tf), torch.device("cpu"))
+    model.set_device(dev)
+    model.train()
+    reducer = parallel.FlatGradReducer(model)
+    opt, sched = parallel.make_optimizer(model)
+    torch.manual_seed(1000 + rank)                               # per-rank dropout / rsample streams
+    batches = [{k: v.to(dev) for k, v in synth.nba_batch(100 + rank * 64 + i, B, N, tp, tf).items()} for i in range(8)]
+    it = [0]
+
+    def stage():
+        model.set_data_nba(batches[it[0] % len(batches)])
+        it[0] += 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(max(args.warmup, 3)):
+        out = parallel.train_step(model, opt, reducer, stage)
+    barrier()
+    l0 = L.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = parallel.train_step(model, opt, reducer, stage)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / args.steps
+    if rank == 0:
+        print(json.dumps({"metric": "training scenes/sec (DP, forward+backward+Adam)", "value": B * world / (ms * 1e-3), "unit": "scenes/s", "n_gpus": world,
+                          "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                          "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "STTODE training step (BASELINE.json configs[4]), NBA shape obs 10 / pred 20", "batch_per_gpu": B,
+                                     "agents": N, "parallelism": f"dp{world}: one all-reduce of {reducer.nbytes} B per step (pz_layer excluded)"},
+                          "gpu_launches": int(L.launch_count() - l0), "last_loss": float(out[0].detach()),
+                          "note": "MHGSA / tensor-ODE forward+backward in libsttode_sm100; thin front end and decoder run as torch ops in train() mode"}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -379,11 +440,15 @@ def main():
     ap.add_argument("--cpu-scenes", type=int, default=192, help="bounded CPU-baseline sample (scenes)")
     ap.add_argument("--ref-scenes", type=int, default=96, help="scenes per step of the --impl reference arm")
     ap.add_argument("--no-extra", action="store_true", help="skip the brief single-scene-latency and NBA-shape measurements")
+    ap.add_argument("--train", action="store_true", help="time the data-parallel training step (configs[4]) instead of the headline inference metric")
+    ap.add_argument("--train-batch", type=int, default=32, help="scenes per GPU per training step (train.py:24)")
     ap.add_argument("--ffma", action="store_true", help="use the FP32-FFMA decoder tile instead of the tcgen05 one")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.train:
+        run_train(args)
     else:
         run_ours(args)
 

@@ -36,3 +36,70 @@ def reduce_metric_sums(sums):
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
     n = float(sums[2])
     return float(sums[0]) / max(n, 1.0), float(sums[1]) / max(n, 1.0), n
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Data-parallel training (BASELINE.json configs[4]): every rank draws its own batch (train.py:24, B = 32), so
+# the global batch is 32 x world; gradients are summed over ranks in ONE all_reduce of a flat fp32 buffer and divided by
+# world (the mean of the per-rank objectives).  `pz_layer` never receives a gradient (learn_prior = False, train.py:28) and is
+# left out of the buffer so the collective carries no dead bytes.
+# ---------------------------------------------------------------------------------------------------------------------
+class FlatGradReducer:
+    """Owns one contiguous fp32 gradient buffer; every participating parameter's `.grad` is a view into it, so autograd
+    accumulates straight into the buffer and the data-parallel exchange is a single all_reduce(SUM) + one scale."""
+
+    def __init__(self, module, exclude=("pz_layer",), group=None):
+        self.group = group
+        self.params = [(n, p) for n, p in module.named_parameters() if p.requires_grad and not any(n.startswith(e) or ("." + e) in n for e in exclude)]
+        self.excluded = [n for n, p in module.named_parameters() if p.requires_grad and (n, p) not in [(a, b) for a, b in self.params]]
+        if not self.params:
+            raise ValueError("no parameters to reduce")
+        p0 = self.params[0][1]
+        if any(p.dtype != torch.float32 or p.device != p0.device for _, p in self.params):
+            raise ValueError("FlatGradReducer: all parameters must be float32 on one device")
+        total = sum(p.numel() for _, p in self.params)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=p0.device)
+        off = 0
+        for _, p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    @property
+    def nbytes(self):
+        return self.flat.numel() * 4
+
+    def zero(self):
+        """Replaces optimizer.zero_grad(): keeps the views alive (set_to_none would detach them from the buffer)."""
+        self.flat.zero_()
+
+    def world(self):
+        return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+
+    def reduce(self):
+        """Sum over ranks, then mean.  Call after backward(), before optimizer.step()."""
+        for n, p in self.params:
+            if p.grad is None or p.grad.data_ptr() < self.flat.data_ptr() or p.grad.data_ptr() >= self.flat.data_ptr() + self.nbytes:
+                raise RuntimeError(f"{n}.grad no longer aliases the flat buffer (use reducer.zero(), not zero_grad(set_to_none=True))")
+        w = self.world()
+        if w > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat.mul_(1.0 / w)
+        return self.flat
+
+
+def make_optimizer(module, lr=1e-4, decay_step=10, decay_gamma=0.5):
+    """train.py:122-123: Adam(lr) + StepLR(decay_step, decay_gamma)."""
+    opt = torch.optim.Adam(module.parameters(), lr=lr)
+    return opt, torch.optim.lr_scheduler.StepLR(opt, step_size=decay_step, gamma=decay_gamma)
+
+
+def train_step(model, optimizer, reducer, stage):
+    """One data-parallel step of train.py:61-66: stage() -> forward -> zero -> backward -> (all-reduce) -> Adam.
+    `stage` puts this rank's batch into the model (set_data_nba / set_data).  Returns the reference's loss tuple."""
+    stage()
+    out = model.forward()
+    reducer.zero()
+    out[0].backward()
+    reducer.reduce()
+    optimizer.step()
+    return out
