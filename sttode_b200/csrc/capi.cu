@@ -790,6 +790,10 @@ int sttode_decoder_pack(const sttode_model_weights* w, void* packed, size_t pack
     if ((rc = check_model(w, false, true))) return rc;
     if (!packed) return fail(STTODE_EINVAL, "null packed buffer");
     const DecPackLayout L = dec_pack_layout(w->past_length, w->future_length);
+    for (int m = 0; m < 4; ++m)
+        if (L.l3_blk[m] > (uint32_t)TC_STAGE || L.n3p[m] > 128)
+            return fail(STTODE_EUNSUPPORTED, "tensor-core decoder: 2 * max(past_length, future_length) must be <= 48 (got %d / %d); use the FP32 decoder (dec_packed = NULL)",
+                        w->past_length, w->future_length);
     if (packed_bytes < (size_t)L.total + 256) return fail(STTODE_EWORKSPACE, "packed buffer too small: %zu < %u", packed_bytes, L.total + 256);
     unsigned char* pk = (unsigned char*)packed;
     auto image = [&](const float* W, int ldw, int row0, int col0, int nvalid, int nrows, int K, size_t hi_off, size_t lo_off) {
@@ -800,10 +804,20 @@ int sttode_decoder_pack(const sttode_model_weights* w, void* packed, size_t pack
     const sttode_mlp3_weights* mlps[4] = {&w->dec[0].dec_x, &w->dec[0].dec_y, &w->dec[1].dec_y, &w->dec[1].dec_x};
     for (int m = 0; m < 4; ++m) {
         const int K1 = (int)L.k1[m], n3 = (int)L.n3[m], n3p = (int)L.n3p[m];
-        for (int c = 0; c < 16; ++c) {          // chunk c = hidden units 32c..32c+31: block 2c holds the hi images, 2c+1 the lo images
-            const size_t ba = L.mlp_off[m] + (size_t)(2 * c) * L.mlp_blk[m], bb = ba + L.mlp_blk[m];
-            image(mlps[m]->w1, 512, 0, c * 32, 256, 256, 32, ba, bb);                       // layer-2 slab W2[:, 32c..]
-            image(mlps[m]->w0, 256, c * 32, 128, 32, 32, K1, ba + 16384, bb + 16384);       // layer-1 rows, pair columns 128..128+K1
+        const size_t w1sz = 64 * (size_t)K1, lead_hi = L.mlp_off[m], lead_lo = lead_hi + L.lead_blk[m], chunk0 = lead_hi + 2 * (size_t)L.lead_blk[m];
+        auto layer1_rows = [&](int c, size_t hi, size_t lo) {     // layer-1 rows of chunk c (hidden units 32c..32c+31), pair columns 128..128+K1
+            image(mlps[m]->w0, 256, c * 32, 128, 32, 32, K1, hi, lo);
+        };
+        layer1_rows(0, lead_hi, lead_lo);
+        layer1_rows(1, lead_hi + w1sz, lead_lo + w1sz);
+        for (int c = 0; c < 16; ++c) {          // chunk c: block 2c holds the hi images, 2c+1 the lo images of [W2[:, 32c..] | W1 rows of chunk c+2]
+            const size_t ba = chunk0 + (size_t)(2 * c) * L.mlp_blk[m], bb = ba + L.mlp_blk[m];
+            image(mlps[m]->w1, 512, 0, c * 32, 256, 256, 32, ba, bb);
+            if (c < 14) layer1_rows(c + 2, ba + 16384, bb + 16384);
+            else {
+                CUDA_TRY(cudaMemsetAsync(pk + ba + 16384, 0, w1sz, st));
+                CUDA_TRY(cudaMemsetAsync(pk + bb + 16384, 0, w1sz, st));
+            }
         }
         for (int p = 0; p < 8; ++p) {
             const size_t pc = L.l3_off[m] + (size_t)(p >> 2) * L.l3_blk[m] + (size_t)(p & 3) * n3p * 128;

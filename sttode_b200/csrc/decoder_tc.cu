@@ -3,7 +3,7 @@
 // Same algebra as k_dec_pair (decoder.cu): decoder_x0 -> Conv1d+GRU1 -> decoder_y0 + decoder_y1 -> pred, for a tile of
 // 128 pairs resident on one SM.  Every dense contraction runs as tcgen05.mma kind::f16 with the 3xFP16 split of
 // tc.cuh (fp32-accurate), accumulators in TMEM:
-//   MLP layer 1 : D1[128x16]   = [z|state](K1) . W1c^T          per 16-unit hidden chunk (double buffered in TMEM)
+//   MLP layer 1 : D1[128x32]   = [z|state](K1) . W1c^T          per 32-unit hidden chunk (4 TMEM buffers, issued 2 chunks ahead)
 //   MLP layer 2 : D2[128x256] += relu(D1 + rowpre) . W2c^T      (the register epilogue of layer 1 re-stages the chunk as A)
 //   MLP layer 3 : D3[128xn3p] += relu(D2 + b1)[:,16p..] . W3p^T
 //   GRU step    : D_r|D_z|D_ni|D_nh [128x96 each] = conv(x)_t . W_ih^T (+) h . W_hh^T ; gates in the register epilogue
@@ -37,9 +37,12 @@ DecPackLayout dec_pack_layout(int Tp, int Tf) {
         L.k1[m] = k1[m];
         L.n3[m] = n3[m];
         L.n3p[m] = (n3[m] + 15) / 16 * 16;
-        L.mlp_blk[m] = 16384 + 64 * k1[m];      // [W2 chunk image (256 rows x 32 k) | W1 chunk image (32 rows x K1)], hi and lo blocks alternate
+        // stream of one MLP: lead pair [W1 rows of chunk 0 | chunk 1] (hi block, lo block), then per chunk c a (hi, lo) pair of
+        // [W2 chunk c image (256 rows x 32 k) | W1 chunk c+2 image (32 rows x K1)]: layer 1 runs two chunks ahead of layer 2
+        L.lead_blk[m] = 2 * 64 * k1[m];
+        L.mlp_blk[m] = 16384 + 64 * k1[m];
         L.mlp_off[m] = off;
-        off += TC_NCH * L.mlp_blk[m];
+        off += 2 * L.lead_blk[m] + TC_NCH * L.mlp_blk[m];
         L.l3_blk[m] = L.n3p[m] * 512;           // 4 pieces of [hi n3p x 32 | lo n3p x 32]
         L.l3_off[m] = off;
         off += 2 * L.l3_blk[m];
@@ -63,9 +66,9 @@ constexpr int SM_A1 = 0;                         // [hi 32 KB | lo 32 KB]   A1 =
 constexpr int SM_H = 65536;                      // 2 x [hi 8 KB | lo 8 KB] (MLP 32-wide chunk operand)  /  GRU: conv image in H[0]
 constexpr int SM_RING = SM_H + 32768;
 constexpr int SM_XY = SM_RING + TC_NST * TC_STAGE;
-constexpr int COL_D2 = 0, COL_D1 = 256, COL_D3 = 320;     // TMEM columns, MLP phases (D1: 2 x 32)
-constexpr int COL_GR = 0, COL_GNI = 192, COL_GNH = 288;   // GRU phase (r|z contiguous at 0..191)
-constexpr int B_WFULL = 0, B_WFREE = 4, B_D1FULL = 8, B_HFULL = 10, B_HFREE = 12, B_ACC = 14, B_XFULL = 15, B_D3FREE = 16, B_COUNT = 17;
+constexpr int COL_D2 = 0, COL_D1 = 256, COL_D3 = 384;     // TMEM columns, MLP phases (D1: 4 x 32; D3 <= 128 columns)
+constexpr int COL_GR = 0, COL_GNI = 192, COL_GNH = 288;   // GRU phase (r|z contiguous at 0..191); overlaps D2/D1, not D3
+constexpr int B_WFULL = 0, B_WFREE = 4, B_D1FULL = 8, B_HFULL = 12, B_HFREE = 14, B_ACC = 16, B_XFULL = 17, B_D3FREE = 18, B_COUNT = 19;
 
 // debug timeline: absolute clock64 stamps into the status tail (CTA 0 only, when status[1] == 2)
 // compiled in only with -DSTTODE_TC_TIMELINE (scripts/tc_timing.py); the release build has no trace of it
@@ -99,20 +102,22 @@ __device__ __forceinline__ void epi_signal(uint64_t* bars, int bar) {
     if ((threadIdx.x & 31) == 0) mbar_arrive(bars + bar);
 }
 
-// global block sequence: [mlp x0: 32 chunk blocks, 2 L3] [gru1: 8*Tp] [mlp y0: 34] [mlp y1: 34] [mlp x1: 34 when recon]
+// global block sequence: [mlp x0: 36 blocks] [gru1: 8*Tp] [mlp y0: 36] [mlp y1: 36] [mlp x1: 36 when recon]
+// one MLP = lead pair, 32 chunk blocks, layer-3 pair
 __device__ __forceinline__ void block_src(const DecPackLayout& lay, int Tp, int i, uint32_t& off, uint32_t& bytes) {
     int m;
-    if (i < 34) m = 0;
+    if (i < TC_MLP_BLOCKS) m = 0;
     else {
-        i -= 34;
+        i -= TC_MLP_BLOCKS;
         if (i < 8 * Tp) { off = lay.gru_off[1] + (uint32_t)(i & 7) * TC_GRU_BLK; bytes = TC_GRU_BLK; return; }
         i -= 8 * Tp;
-        if (i < 34) m = 1;
-        else if (i < 68) { m = 2; i -= 34; }
-        else { m = 3; i -= 68; }
+        if (i < TC_MLP_BLOCKS) m = 1;
+        else if (i < 2 * TC_MLP_BLOCKS) { m = 2; i -= TC_MLP_BLOCKS; }
+        else { m = 3; i -= 2 * TC_MLP_BLOCKS; }
     }
-    if (i < TC_NCH) { off = lay.mlp_off[m] + (uint32_t)i * lay.mlp_blk[m]; bytes = lay.mlp_blk[m]; }
-    else { off = lay.l3_off[m] + (uint32_t)(i - TC_NCH) * lay.l3_blk[m]; bytes = lay.l3_blk[m]; }
+    if (i < 2) { off = lay.mlp_off[m] + (uint32_t)i * lay.lead_blk[m]; bytes = lay.lead_blk[m]; }
+    else if (i < 2 + TC_NCH) { off = lay.mlp_off[m] + 2 * lay.lead_blk[m] + (uint32_t)(i - 2) * lay.mlp_blk[m]; bytes = lay.mlp_blk[m]; }
+    else { off = lay.l3_off[m] + (uint32_t)(i - 2 - TC_NCH) * lay.l3_blk[m]; bytes = lay.l3_blk[m]; }
 }
 
 // ================================================================ producer warp ============================
@@ -147,53 +152,57 @@ __device__ __forceinline__ uint32_t ring_wait(unsigned char* sm, uint64_t* bars,
     return tc::smem_u32(sm + SM_RING + (i & 3) * TC_STAGE);
 }
 
-// n_acc / n_d3 are running counts kept by the caller (uniform across the warp)
+// n_d3 is a running count kept by the caller (uniform across the warp).
+// Layer 1 runs TWO chunks ahead of layer 2: L1(ch+2) is issued before the issuer waits for the staged operand of chunk ch, so
+// the two epilogue groups always have a finished D1 to work on while the tensor pipe runs layer 2 (4 D1 buffers in TMEM; the
+// weight stream carries W1 of chunk ch+2 next to W2 of chunk ch, so both operands of an iteration arrive in one ring pair).
 __device__ void issuer_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int K1, int n3p, int blk0, uint32_t& n_d3) {
     const uint32_t h_base = tc::smem_u32(sm + SM_H);
     const uint64_t a1_hi = tc::op_desc(tc::smem_u32(sm + SM_A1), 128), a1_lo = tc::op_desc(tc::smem_u32(sm + SM_A1) + 32768, 128);
     const uint32_t idesc1 = tc::make_idesc_f16(32), idesc2 = tc::make_idesc_f16(256), idesc3 = tc::make_idesc_f16(n3p);
     const int nk1 = K1 >> 4;
+    const uint32_t w1sz = 64u * (uint32_t)K1;
+    {   // lead pair: layer 1 of chunks 0 and 1 (D1[0], D1[1]: their previous readers finished phases ago)
+        const uint32_t sa = ring_wait(sm, bars, blk0), sb = ring_wait(sm, bars, blk0 + 1);
+        tc::tc_fence_after();
+        if (elect_one()) {
+            tc::mma_split3_d(tmem + COL_D1, a1_hi, a1_lo, 256, tc::op_desc(sa, 32), tc::op_desc(sb, 32), 64, idesc1, nk1, false);
+            tc::mma_commit(bars + B_D1FULL);
+            tc::mma_split3_d(tmem + COL_D1 + 32, a1_hi, a1_lo, 256, tc::op_desc(sa + w1sz, 32), tc::op_desc(sb + w1sz, 32), 64, idesc1, nk1, false);
+            tc::mma_commit(bars + B_D1FULL + 1);
+            tc::mma_commit(bars + B_WFREE + ((blk0 >> 1) & 1));
+        }
+        __syncwarp();
+    }
 #pragma unroll 1
-    for (int ch = 0; ch <= 16; ++ch) {
-        // layer 2 of chunk ch-1 first: its commit releases two ring stages, so the producer can refill them while this warp
-        // waits for the blocks of chunk ch
-        const bool tl = (K1 == 32 && blk0 != 0 && (ch == 4 || ch == 5) && (threadIdx.x & 31) == 0);
-        TLOG(tl, (ch - 4) * 5 + 0);
-        if (ch >= 1) {
-            const int pc = ch - 1, b = pc & 1;
-            tc_wait(bars, B_HFULL + b, (uint32_t)((pc >> 1) & 1));
-            tc::tc_fence_after();
-            TLOG(tl, (ch - 4) * 5 + 1);
-            const int i0 = blk0 + 2 * pc;
-            const uint32_t sa = tc::smem_u32(sm + SM_RING + (i0 & 3) * TC_STAGE), sb = tc::smem_u32(sm + SM_RING + ((i0 + 1) & 3) * TC_STAGE);
+    for (int ch = 0; ch < 16; ++ch) {
+        const int i0 = blk0 + 2 + 2 * ch, b = ch & 1;
+        const uint32_t sa = ring_wait(sm, bars, i0), sb = ring_wait(sm, bars, i0 + 1);
+        tc::tc_fence_after();
+        if (ch < 14) {              // layer 1 of chunk ch+2 into D1[(ch+2)&3] (chunk ch-2 was read out before HFULL(ch-2), waited two iterations ago)
             if (elect_one()) {
-                tc::mma_split3_d(tmem + COL_D2, tc::op_desc(h_base + b * 16384, 128), tc::op_desc(h_base + b * 16384 + 8192, 128), 256,
-                                 tc::op_desc(sa, 256), tc::op_desc(sb, 256), 512, idesc2, 2, pc > 0);
-                tc::mma_commit(bars + B_WFREE + ((i0 >> 1) & 1));
-                tc::mma_commit(bars + B_HFREE + b);
-                if (pc == 15) tc::mma_commit(bars + B_ACC);            // D2 complete
-            }
-            __syncwarp();
-            TLOG(tl, (ch - 4) * 5 + 2);
-        }
-        if (ch < 16) {              // layer 1 of chunk ch (D1[ch&1] was released when chunk ch-2 was staged)
-            const uint32_t sa = ring_wait(sm, bars, blk0 + 2 * ch), sb = ring_wait(sm, bars, blk0 + 2 * ch + 1);
-            tc::tc_fence_after();
-            TLOG(tl, (ch - 4) * 5 + 3);
-            if (elect_one()) {
-                tc::mma_split3_d(tmem + COL_D1 + (ch & 1) * 32, a1_hi, a1_lo, 256, tc::op_desc(sa + 16384, 32), tc::op_desc(sb + 16384, 32), 64,
+                tc::mma_split3_d(tmem + COL_D1 + ((ch + 2) & 3) * 32, a1_hi, a1_lo, 256, tc::op_desc(sa + 16384, 32), tc::op_desc(sb + 16384, 32), 64,
                                  idesc1, nk1, false);
-                tc::mma_commit(bars + B_D1FULL + (ch & 1));
+                tc::mma_commit(bars + B_D1FULL + ((ch + 2) & 3));
             }
             __syncwarp();
-            TLOG(tl, (ch - 4) * 5 + 4);
         }
+        tc_wait(bars, B_HFULL + b, (uint32_t)((ch >> 1) & 1));          // relu(D1(ch) + rowpre) staged as the A operand
+        tc::tc_fence_after();
+        if (elect_one()) {
+            tc::mma_split3_d(tmem + COL_D2, tc::op_desc(h_base + b * 16384, 128), tc::op_desc(h_base + b * 16384 + 8192, 128), 256,
+                             tc::op_desc(sa, 256), tc::op_desc(sb, 256), 512, idesc2, 2, ch > 0);
+            tc::mma_commit(bars + B_WFREE + ((i0 >> 1) & 1));
+            tc::mma_commit(bars + B_HFREE + b);
+            if (ch == 15) tc::mma_commit(bars + B_ACC);            // D2 complete
+        }
+        __syncwarp();
     }
     // layer 3: D3 must have been read out by the previous phase's epilogue
     if (n_d3 >= 1) tc_wait(bars, B_D3FREE, (n_d3 - 1) & 1);
 #pragma unroll 1
     for (int p = 0; p < 8; ++p) {
-        const int b = p & 1, blk = blk0 + TC_NCH + (p >> 2);
+        const int b = p & 1, blk = blk0 + 2 + TC_NCH + (p >> 2);
         const uint32_t st = ring_wait(sm, bars, blk) + (uint32_t)(p & 3) * n3p * 128;
         tc_wait(bars, B_HFULL + b, (uint32_t)((p >> 1) & 1));          // 8 layer-2 fills per buffer precede: parity unchanged
         tc::tc_fence_after();
@@ -212,7 +221,7 @@ __device__ void issuer_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int
 __device__ void issuer_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, int blk0, int T, uint32_t n_d3, uint32_t& n_x) {
     const uint32_t a1 = tc::smem_u32(sm + SM_A1), xh = tc::smem_u32(sm + SM_H);
     const uint32_t idesc_rz = tc::make_idesc_f16(192), idesc_n = tc::make_idesc_f16(96);
-    if (n_d3 >= 1) tc_wait(bars, B_D3FREE, (n_d3 - 1) & 1);           // the gate accumulators overlap D3
+    (void)n_d3;                                     // the gate accumulators (columns 0..383) overlap D2 / D1 (all read out), not D3
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
         const bool tl = (t == 2 && (threadIdx.x & 31) == 0);
@@ -303,11 +312,11 @@ __device__ void epi_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int n3
         const bool tl = (!first_mlp && !accumulate && n3 != 0 && (ch == 4 || ch == 5) && lane == 0 && wq == 0 && n_acc >= 8);
         load_rowbias32(rb, rowpre, prow, ch);
         TLOG(tl, 10 + (ch - 4) * 5 + 0);
-        tc_wait(bars, B_D1FULL + wh, (uint32_t)((ch >> 1) & 1));
+        tc_wait(bars, B_D1FULL + (ch & 3), (uint32_t)((ch >> 2) & 1));      // 4 completions per buffer per MLP: parity restarts at 0
         tc::tc_fence_after();
         TLOG(tl, 10 + (ch - 4) * 5 + 1);
         float v[32];
-        tc::tmem_ld32(tmem + lane_base + COL_D1 + wh * 32, v);
+        tc::tmem_ld32(tmem + lane_base + COL_D1 + (ch & 3) * 32, v);
         TLOG(tl, 10 + (ch - 4) * 5 + 2);
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + rb[i], 0.f);
@@ -452,8 +461,8 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
     const size_t pair0 = (size_t)row0 * K;
     int ovf = 0;                                    // set when a staged fp16 operand would leave the fp16 range
     if (rng_state) seed += *rng_state;
-    const int total_blocks = 34 * 3 + 8 * Tp + (recon ? 34 : 0);
-    const int by0 = 34 + 8 * Tp;
+    const int total_blocks = TC_MLP_BLOCKS * 3 + 8 * Tp + (recon ? TC_MLP_BLOCKS : 0);
+    const int by0 = TC_MLP_BLOCKS + 8 * Tp;
 #ifdef STTODE_TC_TIMELINE
     if (blockIdx.x == 0 && tid == 0) g_tl = status[1] == 2 ? reinterpret_cast<long long*>(status + 2) : nullptr;
 #endif
@@ -511,10 +520,10 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
     } else if (warp == 8) {                         // ---------------- issuer
         uint32_t n_d3 = 0, n_x = 0;
         issuer_mlp(sm, bars, tmem, 32, (int)lay.n3p[0], 0, n_d3);
-        issuer_gru(sm, bars, tmem, 34, Tp, n_d3, n_x);
+        issuer_gru(sm, bars, tmem, TC_MLP_BLOCKS, Tp, n_d3, n_x);
         issuer_mlp(sm, bars, tmem, 32, (int)lay.n3p[1], by0, n_d3);
-        issuer_mlp(sm, bars, tmem, 128, (int)lay.n3p[2], by0 + 34, n_d3);
-        if (recon) issuer_mlp(sm, bars, tmem, 128, (int)lay.n3p[3], by0 + 68, n_d3);
+        issuer_mlp(sm, bars, tmem, 128, (int)lay.n3p[2], by0 + TC_MLP_BLOCKS, n_d3);
+        if (recon) issuer_mlp(sm, bars, tmem, 128, (int)lay.n3p[3], by0 + 2 * TC_MLP_BLOCKS, n_d3);
     } else {                                        // ---------------- epilogue warps
         uint32_t n_acc = 0;
         epi_mlp(sm, bars, tmem, 2 * Tp, (int)lay.n3p[0], true, rowpre + 0, prow, w0.dec_x.b1, w0.dec_x.b2, xy_s, ldxy, false, n_acc, ovf);
