@@ -20,16 +20,12 @@ m.forecast_scenes(obs, sp); torch.cuda.synchronize()
 m.forecast_scenes(obs, sp); torch.cuda.synchronize()
 L.check(lib.sttode_decoder_timing(L.dptr(buf), 8, 12, 0, out))
 v = list(out)
-def rel(idx, names):
-    base = min(v[i] for i in idx if v[i])
-    return {n: v[i] - base for i, n in zip(idx, names) if v[i]}
-base = min(x for x in v[0:29] if x)
-R = lambda xs: [x - base if x else None for x in xs]
-print("issuer ch4 [L1 start, ring(4) ok, MMA1(4) issued, hfull(3) ok, MMA2(3) issued]:", R(v[0:5]))
-print("issuer ch5 [L1 start, ring(5) ok, MMA1(5) issued, hfull(4) ok, MMA2(4) issued]:", R(v[5:10]))
-print("epi ch4 grp0 [before d1full, d1full ok, tmem ld done, staged+signalled]:", R(v[10:14]))
-print("epi ch5 grp1 [before d1full, d1full ok, tmem ld done, staged+signalled]:", R(v[15:19]))
-print("producer blk A of chunk 5:", [x - base if x else None for x in v[23:26]], "(loop top, wfree ok, arrived)")
-print("producer blk B of chunk 5:", [x - base if x else None for x in v[26:29]])
-ph = [v[14], v[19], v[20], v[21], v[22], v[29]]
-print("epilogue phases (cycles): x0+prep", ph[1] - ph[0], " gru", ph[2] - ph[1], " y0", ph[3] - ph[2], " y1", ph[4] - ph[3], " output", ph[5] - ph[4], " total", ph[5] - ph[0])
+d = lambda a, b: (v[b] - v[a]) if v[a] and v[b] else None
+print("epilogue phases (cycles): x0", d(24, 25), " prep+gru", d(25, 26), " y0", d(26, 27), " y1", d(27, 28), " output", d(28, 29), " total", d(24, 29))
+print("gru step t=2, epilogue thread 0: conv image", d(0, 1), " wait for gates (MMA)", d(1, 2), " gate math + restage", d(2, 3))
+print("gru step t=2, issuer lane 0: wait xfull", d(20, 21), " issue 8 slabs", d(21, 22))
+print("epi mlp ch4 grp0 [before d1full, d1full ok, tmem ld done, staged+signalled]:", [d(10, 10 + i) for i in range(1, 4)])
+print("epi mlp ch5 grp1 [before d1full, d1full ok, tmem ld done, staged+signalled]:", [d(15, 15 + i) for i in range(1, 4)])
+print("epi mlp ch4 stage_h32 from tmem-ld-done: [relu+range", d(12, 4), " wait hfree", d(4, 5), " split+store", d(5, 6), " fence+arrive", d(6, 7), "]")
+base = v[24]
+print("absolute (from phase start): epi ch4", [v[i] - base for i in range(10, 14)], " epi ch5", [v[i] - base for i in range(15, 19)], " stage ch4", [v[i] - base for i in range(4, 8)])

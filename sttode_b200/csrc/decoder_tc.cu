@@ -55,13 +55,16 @@ DecPackLayout dec_pack_layout(int Tp, int Tf) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Warp-specialised tile kernel (320 threads):
-//   warps 0..7  epilogue : TMEM -> registers -> bias/ReLU/gates -> fp16 hi/lo operand images in shared memory, outputs
-//   warp  8     issuer   : tcgen05.mma + tcgen05.commit (warp-uniform bookkeeping, one elected lane issues)
-//   warp  9     producer : streams the packed weight blocks L2 -> shared ring with cp.async.bulk
+// Warp-specialised tile kernel (576 threads):
+//   warps 0..15 epilogue : TMEM -> registers -> bias/ReLU/gates -> fp16 hi/lo operand images in shared memory, outputs
+//   warp  16    issuer   : tcgen05.mma + tcgen05.commit (warp-uniform bookkeeping, one elected lane issues)
+//   warp  17    producer : streams the packed weight blocks L2 -> shared ring with cp.async.bulk
 // The roles talk through mbarriers only.  All phase parities are closed-form functions of the loop indices.
-constexpr int TC_THREADS = 320;
-constexpr int EPI_THREADS = 256;
+// Epilogue warp w reads TMEM lanes 32*(w & 3)..; sub = w >> 2 (0..3) selects its share of the columns: four epilogue warps per
+// scheduler keep the ALU / MUFU pipes fed while one of them waits on TMEM or shared memory.
+constexpr int ISSUER_WARP = 16, PRODUCER_WARP = 17;
+constexpr int TC_THREADS = 576;
+constexpr int EPI_THREADS = 512;
 constexpr int SM_A1 = 0;                         // [hi 32 KB | lo 32 KB]   A1 = [z (k 0..31) | state (k 32..127)]
 constexpr int SM_H = 65536;                      // 2 x [hi 8 KB | lo 8 KB] (MLP 32-wide chunk operand)  /  GRU: conv image in H[0]
 constexpr int SM_RING = SM_H + 32768;
@@ -93,7 +96,7 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\tselp.u32 %0, 1, 0, px;\n\t}" : "=r"(pred));
     return pred != 0;
 }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 // epilogue warp: publish generic-proxy smem writes + finished TMEM reads, one arrival per warp
 __device__ __forceinline__ void epi_signal(uint64_t* bars, int bar) {
     tc::fence_proxy_async();
@@ -267,61 +270,65 @@ __device__ __forceinline__ void track_range(const float (&v)[N], int& ovf) {
     ovf |= !(mx <= FP16_SAFE);                      // also true for NaN/inf
 }
 
-// stage the 32 values (four k chunks) of one row of the chunk operand H[b]; prev_parity = phase of the MMA that read
+// stage 16 values (k chunks 2*half, 2*half+1) of one row of the chunk operand H[b]; prev_parity = phase of the MMA that read
 // the previous contents of H[b]
-__device__ __forceinline__ void stage_h32(unsigned char* sm, uint64_t* bars, int b, int m, const float (&v)[32], bool first, uint32_t prev_parity,
-                                          int& ovf) {
+__device__ __forceinline__ void stage_h16(unsigned char* sm, uint64_t* bars, int b, int half, int m, const float (&v)[16], bool first,
+                                          uint32_t prev_parity, int& ovf, bool tl = false) {
     track_range(v, ovf);
+    TLOG(tl, 4);
     if (!first) tc_wait(bars, B_HFREE + b, prev_parity);
+    TLOG(tl, 5);
     unsigned char* hb = sm + SM_H + b * 16384;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < 2; ++q) {
         float t8[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) t8[i] = v[q * 8 + i];
-        tc::store_split8(hb, hb + 8192, 128, m, q, t8);
+        tc::store_split8(hb, hb + 8192, 128, m, half * 2 + q, t8);
     }
+    TLOG(tl, 6);
     epi_signal(bars, B_HFULL + b);
+    TLOG(tl, 7);
 }
 
-__device__ __forceinline__ void load_rowbias32(float (&rb)[32], const float* __restrict__ rowpre, int prow, int ch) {
+__device__ __forceinline__ void load_rowbias16(float (&rb)[16], const float* __restrict__ rowpre, int prow, int col) {
     if (prow >= 0) {
-        const float4* p = reinterpret_cast<const float4*>(rowpre + (size_t)prow * ROWPRE_LD + ch * 32);
+        const float4* p = reinterpret_cast<const float4*>(rowpre + (size_t)prow * ROWPRE_LD + col);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < 4; ++q) {
             const float4 r = __ldg(p + q);
             rb[4 * q] = r.x; rb[4 * q + 1] = r.y; rb[4 * q + 2] = r.z; rb[4 * q + 3] = r.w;
         }
     } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) rb[i] = 0.f;
+        for (int i = 0; i < 16; ++i) rb[i] = 0.f;
     }
 }
 
-// The two epilogue warp groups (wh = 0: warps 0-3, wh = 1: warps 4-7) each own one of the double buffers: group wh handles
-// the chunks / pieces with index parity wh, all 32 columns, so two chunks are in flight in the epilogue at any time.
+// Epilogue warp groups: sub = warp >> 2.  wh = sub & 1 owns the chunks / pieces of index parity wh (one of the double buffers),
+// half = sub >> 1 owns columns 16*half..16*half+15 of each 32-wide chunk, so two chunks are in flight and each is staged by 8 warps.
 __device__ void epi_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int n3, int n3p, bool first_mlp, const float* __restrict__ rowpre,
                         int prow, const float* __restrict__ b1, const float* __restrict__ b2, float* xy_s, int ldxy, bool accumulate,
                         uint32_t& n_acc, int& ovf) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wq = warp & 3, wh = warp >> 2;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wq = warp & 3, sub = warp >> 2, wh = sub & 1, half = sub >> 1;
     const int m = wq * 32 + lane;
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
-    float rb[32];
+    float rb[16];
 #pragma unroll 1
     for (int ch = wh; ch < 16; ch += 2) {
-        const bool tl = (!first_mlp && !accumulate && n3 != 0 && (ch == 4 || ch == 5) && lane == 0 && wq == 0 && n_acc >= 8);
-        load_rowbias32(rb, rowpre, prow, ch);
+        const bool tl = (!first_mlp && !accumulate && n3 != 0 && (ch == 4 || ch == 5) && lane == 0 && wq == 0 && half == 0 && n_acc >= 8);
+        load_rowbias16(rb, rowpre, prow, ch * 32 + half * 16);
         TLOG(tl, 10 + (ch - 4) * 5 + 0);
         tc_wait(bars, B_D1FULL + (ch & 3), (uint32_t)((ch >> 2) & 1));      // 4 completions per buffer per MLP: parity restarts at 0
         tc::tc_fence_after();
         TLOG(tl, 10 + (ch - 4) * 5 + 1);
-        float v[32];
-        tc::tmem_ld32(tmem + lane_base + COL_D1 + (ch & 3) * 32, v);
+        float v[16];
+        tc::tmem_ld16(tmem + lane_base + COL_D1 + (ch & 3) * 32 + half * 16, v);
         TLOG(tl, 10 + (ch - 4) * 5 + 2);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + rb[i], 0.f);
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + rb[i], 0.f);
         // fill j = 12*k + ch/2 of H[wh]: wait for the reader of fill j-1
-        stage_h32(sm, bars, wh, m, v, first_mlp && ch < 2, (uint32_t)(((ch >> 1) + 1) & 1), ovf);
+        stage_h16(sm, bars, wh, half, m, v, first_mlp && ch < 2, (uint32_t)(((ch >> 1) + 1) & 1), ovf, tl && ch == 4);
         TLOG(tl, 10 + (ch - 4) * 5 + 3);
     }
     tc_wait(bars, B_ACC, n_acc & 1);                // D2 complete
@@ -329,17 +336,17 @@ __device__ void epi_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int n3
     tc::tc_fence_after();
 #pragma unroll 1
     for (int p = wh; p < 8; p += 2) {
-        float v[32];
-        tc::tmem_ld32(tmem + lane_base + COL_D2 + p * 32, v);
+        float v[16];
+        tc::tmem_ld16(tmem + lane_base + COL_D2 + p * 32 + half * 16, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + __ldg(b1 + p * 32 + i), 0.f);
-        stage_h32(sm, bars, wh, m, v, false, (uint32_t)(((p >> 1) + 1) & 1), ovf);        // fill 12k + 8 + p/2
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + __ldg(b1 + p * 32 + half * 16 + i), 0.f);
+        stage_h16(sm, bars, wh, half, m, v, false, (uint32_t)(((p >> 1) + 1) & 1), ovf);        // fill 12k + 8 + p/2
     }
     tc_wait(bars, B_ACC, n_acc & 1);                // D3 complete
     ++n_acc;
     tc::tc_fence_after();
     for (int c0 = 0; c0 < n3p; c0 += 16) {
-        if (((c0 >> 4) & 1) != wh) continue;        // warp-uniform: the two groups alternate 16-wide column groups
+        if (((c0 >> 4) & 3) != sub) continue;       // warp-uniform: the four groups take 16-wide column groups in turn
         float v[16];
         tc::tmem_ld16(tmem + lane_base + COL_D3 + c0, v);
 #pragma unroll
@@ -362,7 +369,7 @@ __device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.
 // gb: shared-memory constants [brz 192 | bin 96 | bhn 96 | conv_w 192 | conv_b 32]
 __device__ void epi_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, const float* gb, const float* xy_s, int ldxy, int valid_rows, int T,
                         uint32_t& n_acc, int& ovf) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wq = warp & 3, wh = warp >> 2;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wq = warp & 3, sub = warp >> 2;
     const int m = wq * 32 + lane;
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
     unsigned char* a1_hi_p = sm + SM_A1;
@@ -373,13 +380,13 @@ __device__ void epi_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, const 
         const int img = i / (12 * 128), r = i - img * 12 * 128;
         *reinterpret_cast<uint4*>(sm + SM_A1 + img * 32768 + 4 * 2048 + r * 16) = make_uint4(0, 0, 0, 0);
     }
-    float hreg[48];
+    float hreg[24];                                 // this thread's 24 hidden units (sub*24 ..) of row m, fp32 across the recurrence
 #pragma unroll
-    for (int i = 0; i < 48; ++i) hreg[i] = 0.f;
-    const int u0 = wh * 48;
+    for (int i = 0; i < 24; ++i) hreg[i] = 0.f;
+    const int u0 = sub * 24;
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
-        // conv channels wh*16 .. +16 of row m at time t -> k chunks 2*wh, 2*wh+1 of the conv image (H[0])
+        // conv channels sub*8 .. +8 of row m at time t -> k chunk `sub` of the conv image (H[0])
         float d[6];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -388,52 +395,50 @@ __device__ void epi_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, const 
             d[k] = in ? xy_s[m * ldxy + tt * 2] : 0.f;
             d[3 + k] = in ? xy_s[m * ldxy + tt * 2 + 1] : 0.f;
         }
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        {
             float v[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int chn = wh * 16 + half * 8 + i;
+                const int chn = sub * 8 + i;
                 float a = cb[chn];
 #pragma unroll
                 for (int e = 0; e < 6; ++e) a = fmaf(cw[chn * 6 + e], d[e], a);
                 v[i] = fmaxf(a, 0.f);
             }
             track_range(v, ovf);
-            tc::store_split8(sm + SM_H, sm + SM_H + 8192, 128, m, wh * 2 + half, v);
+            tc::store_split8(sm + SM_H, sm + SM_H + 8192, 128, m, sub, v);
         }
         const bool tl = (t == 2 && tid == 0);
+        TLOG(tl, 0);
         epi_signal(bars, B_XFULL);                  // conv image t (+ state h_t written at the end of step t-1)
+        TLOG(tl, 1);
         tc_wait(bars, B_ACC, n_acc & 1);
         ++n_acc;
         tc::tc_fence_after();
+        TLOG(tl, 2);
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-            const int u = u0 + q * 16;
-            float gr[16], gz[16], gni[16], gnh[16];
-            tc::tmem_ld16(tmem + lane_base + COL_GR + u, gr);
-            tc::tmem_ld16(tmem + lane_base + COL_GR + 96 + u, gz);
-            tc::tmem_ld16(tmem + lane_base + COL_GNI + u, gni);
-            tc::tmem_ld16(tmem + lane_base + COL_GNH + u, gnh);
+            const int u = u0 + q * 8;
+            float gr[8], gz[8], gni[8], gnh[8];
+            tc::tmem_ld8(tmem + lane_base + COL_GR + u, gr);
+            tc::tmem_ld8(tmem + lane_base + COL_GR + 96 + u, gz);
+            tc::tmem_ld8(tmem + lane_base + COL_GNI + u, gni);
+            tc::tmem_ld8(tmem + lane_base + COL_GNH + u, gnh);
+            float v[8];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
+            for (int i = 0; i < 8; ++i) {
                 // r = 1/(1+ea), z = 1/(1+eb) with one reciprocal of the product (pre-activations clamped so it stays finite)
                 const float da = 1.f + __expf(-fminf(fmaxf(gr[i] + brz[u + i], -30.f), 30.f));
                 const float db = 1.f + __expf(-fminf(fmaxf(gz[i] + brz[96 + u + i], -30.f), 30.f));
                 const float inv = __fdividef(1.f, da * db);
                 const float r = inv * db, zg = inv * da;
                 const float n = fast_tanh((gni[i] + bin[u + i]) + r * (gnh[i] + bhn[u + i]));
-                const float hp = hreg[q * 16 + i];
-                hreg[q * 16 + i] = (hp - n) * zg + n;
+                const float hp = hreg[q * 8 + i];
+                v[i] = hreg[q * 8 + i] = (hp - n) * zg + n;
             }
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                float v[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = hreg[q * 16 + j * 8 + i];
-                tc::store_split8(a1_hi_p, a1_lo_p, 128, m, 4 + (u >> 3) + j, v);
-            }
+            tc::store_split8(a1_hi_p, a1_lo_p, 128, m, 4 + (u >> 3), v);
         }
+        TLOG(tl, 3);
     }
     epi_signal(bars, B_XFULL);                      // final state staged, gate accumulators read out
 }
@@ -452,7 +457,7 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT + 1);
     float* gb = reinterpret_cast<float*>(bars + B_COUNT + 3);          // GRU/conv constants of block 1 (608 floats)
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wq = warp & 3, wh = (warp >> 2) & 1;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wq = warp & 3, sub = (warp >> 2) & 3;
     const int m = wq * 32 + lane;
     const int row0 = blockIdx.x * rpt;
     const int nrow = min(rpt, rows - row0);
@@ -469,13 +474,13 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
 
     if (tid == 0) {
         for (int i = 0; i < B_COUNT; ++i) {
-            const int cnt = (i == B_HFULL || i == B_HFULL + 1) ? 4 : (i == B_XFULL || i == B_D3FREE) ? 8 : 1;
+            const int cnt = (i == B_HFULL || i == B_HFULL + 1) ? 8 : (i == B_XFULL || i == B_D3FREE) ? 16 : 1;     // arrivals: one per epilogue warp
             tc::mbar_init(bars + i, cnt);
         }
         tc::fence_mbar_init();
     }
-    if (warp == 8) tc::tmem_alloc(tmem_slot, 512);
-    if (warp < 8) {
+    if (warp == ISSUER_WARP) tc::tmem_alloc(tmem_slot, 512);
+    if (warp < ISSUER_WARP) {
         for (int i = tid; i < 608; i += EPI_THREADS) {
             float v;
             if (i < 192) v = w1.gru_b_ih[i] + w1.gru_b_hh[i];
@@ -485,10 +490,9 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
             else v = w1.conv_b[i - 576];
             gb[i] = v;
         }
-        // latent z -> A1 k chunks 0..3 (this thread: chunks 2*wh, 2*wh+1 of row m)
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int kc = wh * 2 + j;
+        // latent z -> A1 k chunks 0..3 (this thread: chunk `sub` of row m)
+        {
+            const int kc = sub;
             float v[8];
             if (m < np) {
                 const size_t pair = pair0 + m;
@@ -515,9 +519,9 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == 9) {                                // ---------------- producer
+    if (warp == PRODUCER_WARP) {                    // ---------------- producer
         producer_loop(sm, bars, packed, total_blocks, status[1] == 3, [&](int i, uint32_t& off, uint32_t& bytes) { block_src(lay, Tp, i, off, bytes); });
-    } else if (warp == 8) {                         // ---------------- issuer
+    } else if (warp == ISSUER_WARP) {               // ---------------- issuer
         uint32_t n_d3 = 0, n_x = 0;
         issuer_mlp(sm, bars, tmem, 32, (int)lay.n3p[0], 0, n_d3);
         issuer_gru(sm, bars, tmem, TC_MLP_BLOCKS, Tp, n_d3, n_x);
@@ -526,7 +530,9 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
         if (recon) issuer_mlp(sm, bars, tmem, 128, (int)lay.n3p[3], by0 + 2 * TC_MLP_BLOCKS, n_d3);
     } else {                                        // ---------------- epilogue warps
         uint32_t n_acc = 0;
+        TLOG(tid == 0, 24);
         epi_mlp(sm, bars, tmem, 2 * Tp, (int)lay.n3p[0], true, rowpre + 0, prow, w0.dec_x.b1, w0.dec_x.b2, xy_s, ldxy, false, n_acc, ovf);
+        TLOG(tid == 0, 25);
         if (recon)
             for (int idx = tid; idx < np * 2 * Tp; idx += EPI_THREADS) {
                 const int mm = idx / (2 * Tp), e = idx - mm * 2 * Tp;
@@ -540,8 +546,11 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
         epi_barrier();
         epi_gru(sm, bars, tmem, gb, xy_s, ldxy, BM, Tp, n_acc, ovf);
         epi_barrier();                              // every thread is done reading the conv input before y0 overwrites xy_s
+        TLOG(tid == 0, 26);
         epi_mlp(sm, bars, tmem, 2 * Tf, (int)lay.n3p[1], false, rowpre + 512, prow, w0.dec_y.b1, w0.dec_y.b2, xy_s, ldxy, false, n_acc, ovf);
+        TLOG(tid == 0, 27);
         epi_mlp(sm, bars, tmem, 2 * Tf, (int)lay.n3p[2], false, rowpre + 1024, prow, w1.dec_y.b1, w1.dec_y.b2, xy_s, ldxy, true, n_acc, ovf);
+        TLOG(tid == 0, 28);
         for (int idx = tid; idx < np * 2 * Tf; idx += EPI_THREADS) {
             const int mm = idx / (2 * Tf), e = idx - mm * 2 * Tf, cc = e & 1;
             const int r = row0 + mm / K;
@@ -559,9 +568,10 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
         }
     }
     if (ovf) tile_flags[blockIdx.x] = 1;
+    TLOG(tid == 0, 29);
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 8) tc::tmem_dealloc(tmem, 512);
+    if (warp == ISSUER_WARP) tc::tmem_dealloc(tmem, 512);
 }
 
 
@@ -589,18 +599,18 @@ k_dec_row_tc(const float* __restrict__ past_feature, const float* __restrict__ t
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SMR_BARS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT + 1);
     float* gb = reinterpret_cast<float*>(bars + B_COUNT + 3);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wq = warp & 3, wh = (warp >> 2) & 1;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wq = warp & 3, sub = (warp >> 2) & 3;
     const int m = wq * 32 + lane;
     const int row0 = blockIdx.x * BM;
     const int nrow = min(BM, rows - row0);
     const int total_blocks = 8 * Tp + 88;
 
     if (tid == 0) {
-        for (int i = 0; i < B_COUNT; ++i) tc::mbar_init(bars + i, (i == B_HFULL || i == B_HFULL + 1 || i == B_XFULL || i == B_D3FREE) ? 8 : 1);
+        for (int i = 0; i < B_COUNT; ++i) tc::mbar_init(bars + i, (i == B_HFULL || i == B_HFULL + 1 || i == B_XFULL || i == B_D3FREE) ? 16 : 1);
         tc::fence_mbar_init();
     }
-    if (warp == 8) tc::tmem_alloc(tmem_slot, 512);
-    if (warp < 8)
+    if (warp == ISSUER_WARP) tc::tmem_alloc(tmem_slot, 512);
+    if (warp < ISSUER_WARP)
         for (int i = tid; i < 608; i += EPI_THREADS) {
             float v;
             if (i < 192) v = w0.gru_b_ih[i] + w0.gru_b_hh[i];
@@ -616,9 +626,9 @@ k_dec_row_tc(const float* __restrict__ past_feature, const float* __restrict__ t
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == 9) {                                // ---------------- producer
+    if (warp == PRODUCER_WARP) {                    // ---------------- producer
         producer_loop(sm, bars, packed, total_blocks, 0, [&](int i, uint32_t& off, uint32_t& bytes) { row_block_src(lay, Tp, i, off, bytes); });
-    } else if (warp == 8) {                         // ---------------- issuer
+    } else if (warp == ISSUER_WARP) {               // ---------------- issuer
         uint32_t n_x = 0;
         issuer_gru(sm, bars, tmem, 0, Tp, 0, n_x);
         tc_wait(bars, B_XFULL, n_x & 1);            // past_feature images staged
@@ -649,12 +659,12 @@ k_dec_row_tc(const float* __restrict__ past_feature, const float* __restrict__ t
     } else {                                        // ---------------- epilogue warps
         uint32_t n_acc = 0;
         epi_gru(sm, bars, tmem, gb, traj_norm + (size_t)row0 * 2 * Tp, 2 * Tp, nrow, Tp, n_acc, ovf);
-        // past_feature tile -> fp16 hi/lo images (k chunks 8*wh .. 8*wh+7 of row m); safe: every GRU MMA has completed
+        // past_feature tile -> fp16 hi/lo images (k chunks 4*sub .. 4*sub+3 of row m); safe: every GRU MMA has completed
         {
             const int r = row0 + m;
 #pragma unroll 1
-            for (int q = 0; q < 8; ++q) {
-                const int kc = wh * 8 + q;
+            for (int q = 0; q < 4; ++q) {
+                const int kc = sub * 4 + q;
                 float v[8];
                 if (m < nrow) {
                     const float4 a = *reinterpret_cast<const float4*>(past_feature + (size_t)r * 128 + kc * 8);
@@ -676,12 +686,12 @@ k_dec_row_tc(const float* __restrict__ past_feature, const float* __restrict__ t
             const int b = j & 1, p = j >> 1, nb = j & 1;
             tc_wait(bars, B_D1FULL + b, (uint32_t)((j >> 1) & 1));
             tc::tc_fence_after();
-            const float* bp = bias[p] + nb * 256 + wh * 128;
-            float* dst = rowpre + (size_t)(row0 + m) * ROWPRE_LD + p * 512 + nb * 256 + wh * 128;
+            const float* bp = bias[p] + nb * 256 + sub * 64;
+            float* dst = rowpre + (size_t)(row0 + m) * ROWPRE_LD + p * 512 + nb * 256 + sub * 64;
 #pragma unroll 1
-            for (int c0 = 0; c0 < 128; c0 += 32) {
+            for (int c0 = 0; c0 < 64; c0 += 32) {
                 float v[32];
-                tc::tmem_ld32(tmem + lane_base + b * 256 + wh * 128 + c0, v);
+                tc::tmem_ld32(tmem + lane_base + b * 256 + sub * 64 + c0, v);
                 if (m < nrow) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
@@ -697,7 +707,7 @@ k_dec_row_tc(const float* __restrict__ past_feature, const float* __restrict__ t
     if (ovf) tile_flags[blockIdx.x] = 1;
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 8) tc::tmem_dealloc(tmem, 512);
+    if (warp == ISSUER_WARP) tc::tmem_dealloc(tmem, 512);
 }
 
 size_t dec_row_tc_smem_bytes() { return (size_t)SMR_BARS + (B_COUNT + 3) * 8 + 608 * 4; }
