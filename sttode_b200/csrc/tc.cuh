@@ -179,16 +179,22 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
 __device__ __forceinline__ uint32_t pack_half2(__half a, __half b) {
     return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
 }
-// 8 consecutive-k values of one row -> one 16-byte chunk each of the hi and lo operand images
+// packed conversion of two floats to f16x2 (one F2FP instruction; `lo_elem` lands in the low half)
+__device__ __forceinline__ uint32_t cvt_f16x2(float lo_elem, float hi_elem) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+    return r;
+}
+// 8 consecutive-k values of one row -> one 16-byte chunk each of the hi and lo operand images.
+// Same roundings as split_f16 (hi = rn(x), lo = rn(x - hi)), two values per conversion instruction: the scalar F2F
+// conversions share the 16-lane XU pipe with MUFU and were the epilogue's bottleneck.
 __device__ __forceinline__ void store_split8(unsigned char* hi_base, unsigned char* lo_base, int rows, int row, int kchunk, const float (&v)[8]) {
     uint32_t hw[4], lw[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        __half h0, l0, h1, l1;
-        split_f16(v[2 * i], h0, l0);
-        split_f16(v[2 * i + 1], h1, l1);
-        hw[i] = pack_half2(h0, h1);
-        lw[i] = pack_half2(l0, l1);
+        hw[i] = cvt_f16x2(v[2 * i], v[2 * i + 1]);
+        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
+        lw[i] = cvt_f16x2(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
     }
     const size_t off = (size_t)kchunk * rows * 16 + (size_t)row * 16;
     *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
