@@ -499,9 +499,18 @@ int run_encoder(const float* traj, int layout, const int* scene_ptr, const int* 
     return run_ode_block(x0, L, bsz, nb, ew.ode, 1, 12.f, STTODE_ODE_EULER, 1, past_feature + 64, 128, ws, st);
 }
 
+// Device -> host copy-out of the predictions, overlapped with the pair kernels: the pair tiles are launched in `nch` slices
+// and slice i's predictions are copied on `stream` while slice i+1 computes (sttode_forecast_host).
+struct CopyOut {
+    char* host;                 // pinned destination, same layout as pred
+    cudaStream_t stream;
+    cudaEvent_t* done;          // >= nch events
+    int nch;
+};
+
 int run_decoder(const float* past_feature, const float* traj_norm, const float* z, unsigned long long seed, const int* row_scene,
                 const float* origin, int rows, int K, const sttode_model_weights* w, float* pred, float* recon, Carver ws,
-                cudaStream_t st) {
+                cudaStream_t st, const CopyOut* co = nullptr) {
     int rc;
     if (K < 1 || K > BM) return fail(STTODE_EINVAL, "sample_k must be in [1, %d]", BM);
     const int Tp = w->past_length, Tf = w->future_length;
@@ -513,45 +522,68 @@ int run_decoder(const float* past_feature, const float* traj_norm, const float* 
     if ((rc = set_smem(k_dec_pair, sm_pair, "k_dec_pair"))) return rc;
     const unsigned long long* rng = z ? nullptr : w->rng_state;
     const int* rs = origin ? row_scene : nullptr;
-    if (!w->dec_packed) {                           // FP32-FFMA decoder
+    const bool tcores = w->dec_packed != nullptr;
+    DecPackLayout lay{};
+    const unsigned char* pk = (const unsigned char*)w->dec_packed;
+    int* flags = nullptr;
+    if (!tcores) {                                  // FP32-FFMA decoder
         k_dec_row<<<row_tiles, NTHREADS, sm_row, st>>>(past_feature, traj_norm, rows, Tp, w->dec[0], w->dec[1], rowpre, nullptr);
         LAUNCH_CHECK("k_dec_row");
-        k_dec_pair<<<pair_tiles, NTHREADS, sm_pair, st>>>(traj_norm, z, seed, rng, rowpre, rs, origin, rows, K, rpt, Tp, Tf, w->dec[0], w->dec[1], pred,
-                                                          recon, nullptr);
-        LAUNCH_CHECK("k_dec_pair");
     } else {
         // Tensor-core decoder.  Its fp16 hi/lo operands cover |v| < 65504; a tile that stages anything larger raises its flag and is
         // recomputed by the FP32 kernel right after (a CTA of the redo launch exits at once when its flag is clear).
-        const DecPackLayout lay = dec_pack_layout(Tp, Tf);
-        const unsigned char* pk = (const unsigned char*)w->dec_packed;
+        lay = dec_pack_layout(Tp, Tf);
         const size_t sm_tc = dec_pair_tc_smem_bytes(Tp, Tf), sm_rtc = dec_row_tc_smem_bytes();
         if ((rc = set_smem(k_dec_row_tc, sm_rtc, "k_dec_row_tc"))) return rc;
         if ((rc = set_smem(k_dec_pair_tc, sm_tc, "k_dec_pair_tc"))) return rc;
-        int* flags = ws.take<int>((size_t)row_tiles + pair_tiles);
+        flags = ws.take<int>((size_t)row_tiles + pair_tiles);
         if (!flags) return fail(STTODE_EWORKSPACE, "workspace too small for decoder tile flags");
         CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int) * ((size_t)row_tiles + pair_tiles), st));
         k_dec_row_tc<<<row_tiles, dec_pair_tc_threads(), sm_rtc, st>>>(past_feature, traj_norm, rows, Tp, w->dec[0], w->dec[1], pk, lay, rowpre, flags);
         LAUNCH_CHECK("k_dec_row_tc");
         k_dec_row<<<row_tiles, NTHREADS, sm_row, st>>>(past_feature, traj_norm, rows, Tp, w->dec[0], w->dec[1], rowpre, flags);
         LAUNCH_CHECK("k_dec_row(redo)");
-        std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
-        if (g_prof.on) {
-            std::lock_guard<std::mutex> lock(g_prof.mu);
-            if (!g_prof.pool.empty()) { ev = g_prof.pool.back(); g_prof.pool.pop_back(); }
-            else { CUDA_TRY(cudaEventCreate(&ev.first)); CUDA_TRY(cudaEventCreate(&ev.second)); }
-            CUDA_TRY(cudaEventRecord(ev.first, st));
+    }
+    // ---- pair tiles, in nch slices of whole tiles (one slice unless the caller overlaps the copy-out)
+    const int nch = co ? std::max(1, std::min(co->nch, pair_tiles)) : 1;
+    const size_t row_out = (size_t)K * Tf * 2;      // floats of pred per agent row
+    std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+    if (tcores && g_prof.on) {
+        std::lock_guard<std::mutex> lock(g_prof.mu);
+        if (!g_prof.pool.empty()) { ev = g_prof.pool.back(); g_prof.pool.pop_back(); }
+        else { CUDA_TRY(cudaEventCreate(&ev.first)); CUDA_TRY(cudaEventCreate(&ev.second)); }
+        CUDA_TRY(cudaEventRecord(ev.first, st));
+    }
+    for (int c = 0; c < nch; ++c) {
+        const int t0 = (int)((long long)pair_tiles * c / nch), t1 = (int)((long long)pair_tiles * (c + 1) / nch);
+        if (t1 <= t0) continue;
+        const int r0 = t0 * rpt, nr = std::min(rows, t1 * rpt) - r0;
+        const float* tn_c = traj_norm + (size_t)r0 * Tp * 2;
+        const float* z_c = z ? z + (size_t)r0 * K * 32 : nullptr;
+        const float* rp_c = rowpre + (size_t)r0 * ROWPRE_LD;
+        const int* rs_c = rs ? rs + r0 : nullptr;
+        float* pred_c = pred + (size_t)r0 * row_out;
+        float* recon_c = recon ? recon + (size_t)r0 * K * Tp * 2 : nullptr;
+        const unsigned long long pb = (unsigned long long)r0 * K;       // the latent draw is keyed by the pair's index in the whole batch
+        if (tcores) {
+            k_dec_pair_tc<<<t1 - t0, dec_pair_tc_threads(), dec_pair_tc_smem_bytes(Tp, Tf), st>>>(tn_c, z_c, seed, pb, rng, rp_c, rs_c, origin, nr, K, rpt, Tp, Tf,
+                                                                                               w->dec[0], w->dec[1], pk, lay, pred_c, recon_c,
+                                                                                               (int*)(pk + lay.total), flags + row_tiles + t0);
+            LAUNCH_CHECK("k_dec_pair_tc");
+            if (c == nch - 1 && ev.first) {
+                std::lock_guard<std::mutex> lock(g_prof.mu);
+                CUDA_TRY(cudaEventRecord(ev.second, st));
+                g_prof.used.push_back(ev);
+            }
         }
-        k_dec_pair_tc<<<pair_tiles, dec_pair_tc_threads(), sm_tc, st>>>(traj_norm, z, seed, rng, rowpre, rs, origin, rows, K, rpt, Tp, Tf, w->dec[0],
-                                                                        w->dec[1], pk, lay, pred, recon, (int*)(pk + lay.total), flags + row_tiles);
-        LAUNCH_CHECK("k_dec_pair_tc");
-        if (ev.first) {
-            std::lock_guard<std::mutex> lock(g_prof.mu);
-            CUDA_TRY(cudaEventRecord(ev.second, st));
-            g_prof.used.push_back(ev);
+        k_dec_pair<<<t1 - t0, NTHREADS, sm_pair, st>>>(tn_c, z_c, seed, pb, rng, rp_c, rs_c, origin, nr, K, rpt, Tp, Tf, w->dec[0], w->dec[1], pred_c, recon_c,
+                                                       tcores ? flags + row_tiles + t0 : nullptr);
+        LAUNCH_CHECK(tcores ? "k_dec_pair(redo)" : "k_dec_pair");
+        if (co) {
+            CUDA_TRY(cudaEventRecord(co->done[c], st));
+            CUDA_TRY(cudaStreamWaitEvent(co->stream, co->done[c], 0));
+            CUDA_TRY(cudaMemcpyAsync(co->host + (size_t)r0 * row_out * 4, pred_c, (size_t)nr * row_out * 4, cudaMemcpyDeviceToHost, co->stream));
         }
-        k_dec_pair<<<pair_tiles, NTHREADS, sm_pair, st>>>(traj_norm, z, seed, rng, rowpre, rs, origin, rows, K, rpt, Tp, Tf, w->dec[0], w->dec[1], pred,
-                                                          recon, flags + row_tiles);
-        LAUNCH_CHECK("k_dec_pair(redo)");
     }
     if (rng) {
         k_bump_counter<<<1, 1, 0, st>>>(w->rng_state);
@@ -560,11 +592,32 @@ int run_decoder(const float* past_feature, const float* traj_norm, const float* 
     return 0;
 }
 
+constexpr int HOST_MAX_CHUNKS = 8;
+
+// one forecast over `rows` agent rows; co != nullptr overlaps the copy-out of the predictions with the pair kernels
+int forecast_impl(const float* traj, int layout, const int* scene_ptr, const int* row_scene, int n_scenes, int rows, int L, int agents,
+                  const float* z, unsigned long long seed, int sample_k, const sttode_model_weights* w, float* pred, float* past_feature_out,
+                  float* traj_norm_out, float* origin_out, void* workspace, size_t workspace_bytes, cudaStream_t st, const CopyOut* co) {
+    int rc;
+    if ((rc = check_model(w))) return rc;
+    if (!traj || !pred) return fail(STTODE_EINVAL, "null pointer");
+    Carver ws(workspace, workspace_bytes);
+    float* pf = past_feature_out ? past_feature_out : ws.take<float>((size_t)rows * 128);
+    float* tn = traj_norm_out ? traj_norm_out : ws.take<float>((size_t)rows * w->past_length * 2);
+    float* org = !scene_ptr ? nullptr : origin_out ? origin_out : ws.take<float>((size_t)n_scenes * 2);
+    if (!pf || !tn || (scene_ptr && !org)) return fail(STTODE_EWORKSPACE, "workspace too small (%zu B given)", workspace_bytes);
+    Carver rest((char*)workspace + ws.off, workspace_bytes - ws.off);
+    if ((rc = run_past_encoder(traj, layout, scene_ptr, row_scene, n_scenes, rows, L, agents, w, pf, tn, org, rest, st))) return rc;
+    return run_decoder(pf, tn, z, seed, row_scene, org, rows, sample_k, w, pred, nullptr, rest, st, co);
+}
+
 // ---- host staging arena for sttode_forecast_host -----------------------------------------------------
 struct HostArena {
     std::mutex mu;
     char *pin_in = nullptr, *pin_out = nullptr, *dev = nullptr;
     size_t pin_in_sz = 0, pin_out_sz = 0, dev_sz = 0;
+    cudaStream_t copy_stream = nullptr;             // D2H of chunk i overlaps the kernels of chunk i+1
+    cudaEvent_t done[HOST_MAX_CHUNKS] = {}, copied = nullptr;
 } g_arena;
 
 int grow(char** p, size_t* cur, size_t want, bool pinned) {
@@ -873,18 +926,8 @@ int sttode_forecast(const float* traj, int layout, const int* scene_ptr, const i
                     const float* z, unsigned long long seed, int sample_k, const sttode_model_weights* w, float* pred,
                     float* past_feature_out, float* traj_norm_out, float* origin_out, void* workspace, size_t workspace_bytes,
                     void* stream) {
-    int rc;
-    cudaStream_t st = (cudaStream_t)stream;
-    if ((rc = check_model(w))) return rc;
-    if (!traj || !pred) return fail(STTODE_EINVAL, "null pointer");
-    Carver ws(workspace, workspace_bytes);
-    float* pf = past_feature_out ? past_feature_out : ws.take<float>((size_t)rows * 128);
-    float* tn = traj_norm_out ? traj_norm_out : ws.take<float>((size_t)rows * w->past_length * 2);
-    float* org = !scene_ptr ? nullptr : origin_out ? origin_out : ws.take<float>((size_t)n_scenes * 2);
-    if (!pf || !tn || (scene_ptr && !org)) return fail(STTODE_EWORKSPACE, "workspace too small (%zu B given)", workspace_bytes);
-    Carver rest((char*)workspace + ws.off, workspace_bytes - ws.off);
-    if ((rc = run_past_encoder(traj, layout, scene_ptr, row_scene, n_scenes, rows, L, agents, w, pf, tn, org, rest, st))) return rc;
-    return run_decoder(pf, tn, z, seed, row_scene, org, rows, sample_k, w, pred, nullptr, rest, st);
+    return forecast_impl(traj, layout, scene_ptr, row_scene, n_scenes, rows, L, agents, z, seed, sample_k, w, pred, past_feature_out, traj_norm_out,
+                         origin_out, workspace, workspace_bytes, (cudaStream_t)stream, nullptr);
 }
 
 int sttode_forecast_host(const float* traj_host, int layout, const int* scene_ptr_host, int n_scenes, int rows, int L, int agents,
@@ -909,6 +952,11 @@ int sttode_forecast_host(const float* traj_host, int layout, const int* scene_pt
     if ((rc = grow(&g_arena.pin_in, &g_arena.pin_in_sz, in_b, true))) return rc;
     if (!out_pinned && (rc = grow(&g_arena.pin_out, &g_arena.pin_out_sz, pred_b, true))) return rc;
     if ((rc = grow(&g_arena.dev, &g_arena.dev_sz, in_b + align_up(pred_b) + ws_b, false))) return rc;
+    if (!g_arena.copy_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&g_arena.copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < HOST_MAX_CHUNKS; ++i) CUDA_TRY(cudaEventCreateWithFlags(&g_arena.done[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&g_arena.copied, cudaEventDisableTiming));
+    }
     // stage inputs in pinned memory (one H2D), build row->scene map on the host
     memcpy(g_arena.pin_in, traj_host, traj_b);
     int *sp_h = nullptr, *rs_h = nullptr;
@@ -929,8 +977,15 @@ int sttode_forecast_host(const float* traj_host, int layout, const int* scene_pt
     const int* rs_d = scene_ptr_host ? (const int*)(d + align_up(traj_b) + sp_b) : nullptr;
     float* pred_d = (float*)(d + in_b);
     void* ws_d = d + in_b + align_up(pred_b);
-    if ((rc = sttode_forecast(traj_d, layout, sp_d, rs_d, n_scenes, rows, L, agents, nullptr, seed, sample_k, w, pred_d, nullptr, nullptr, nullptr, ws_d, ws_b, st))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(out_pinned ? (void*)pred_host : (void*)g_arena.pin_out, pred_d, pred_b, cudaMemcpyDeviceToHost, st));
+    // the pair kernels run in slices of whole tiles; the D2H copy of slice i overlaps the kernels of slice i+1 (one slice per ~12 MB of output,
+    // each slice a whole number of 148-SM waves is not required: slices are large)
+    CopyOut co{out_pinned ? (char*)pred_host : g_arena.pin_out, g_arena.copy_stream, g_arena.done,
+               (int)std::max<size_t>(1, std::min<size_t>(HOST_MAX_CHUNKS, pred_b / (12u << 20)))};
+    if ((rc = forecast_impl(traj_d, layout, sp_d, rs_d, n_scenes, rows, L, agents, nullptr, seed, sample_k, w, pred_d, nullptr, nullptr, nullptr, ws_d, ws_b,
+                            st, &co)))
+        return rc;
+    CUDA_TRY(cudaEventRecord(g_arena.copied, g_arena.copy_stream));
+    CUDA_TRY(cudaStreamWaitEvent(st, g_arena.copied, 0));                         // the caller's stream stays the single completion point
     CUDA_TRY(cudaStreamSynchronize(st));
     if (!out_pinned) memcpy(pred_host, g_arena.pin_out, pred_b);
     return 0;
@@ -941,6 +996,12 @@ void sttode_release_host_arena(void) {
     if (g_arena.pin_in) cudaFreeHost(g_arena.pin_in);
     if (g_arena.pin_out) cudaFreeHost(g_arena.pin_out);
     if (g_arena.dev) cudaFree(g_arena.dev);
+    if (g_arena.copy_stream) {
+        cudaStreamDestroy(g_arena.copy_stream);
+        for (int i = 0; i < HOST_MAX_CHUNKS; ++i) cudaEventDestroy(g_arena.done[i]);
+        cudaEventDestroy(g_arena.copied);
+        g_arena.copy_stream = nullptr;
+    }
     g_arena.pin_in = g_arena.pin_out = g_arena.dev = nullptr;
     g_arena.pin_in_sz = g_arena.pin_out_sz = g_arena.dev_sz = 0;
 }

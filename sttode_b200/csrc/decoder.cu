@@ -264,7 +264,8 @@ __device__ void mlp_phase(const float* A1, int lda, const sttode_mlp3_weights& w
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-k_dec_pair(const float* __restrict__ traj_norm, const float* __restrict__ z, unsigned long long seed, const unsigned long long* __restrict__ rng_state,
+k_dec_pair(const float* __restrict__ traj_norm, const float* __restrict__ z, unsigned long long seed, unsigned long long pair_base,
+           const unsigned long long* __restrict__ rng_state,
            const float* __restrict__ rowpre, const int* __restrict__ row_scene, const float* __restrict__ origin, int rows,
            int K, int rpt, int Tp, int Tf, sttode_decompose_weights w0, sttode_decompose_weights w1,
            float* __restrict__ pred, float* __restrict__ recon, const int* __restrict__ only_flagged) {
@@ -295,7 +296,7 @@ k_dec_pair(const float* __restrict__ traj_norm, const float* __restrict__ z, uns
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (m < np) {
             const size_t pair = (size_t)row0 * K + m;
-            v = z ? *reinterpret_cast<const float4*>(z + pair * 32 + q * 4) : latent_normal4(seed, pair, q);
+            v = z ? *reinterpret_cast<const float4*>(z + pair * 32 + q * 4) : latent_normal4(seed, pair_base + pair, q);      // pair_base: index of this launch's first pair in the caller's batch
         }
         *reinterpret_cast<float4*>(zA + m * LDZ + q * 4) = v;
     }

@@ -444,7 +444,8 @@ __device__ void epi_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, const 
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, unsigned long long seed, const unsigned long long* __restrict__ rng_state,
+k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, unsigned long long seed, unsigned long long pair_base,
+              const unsigned long long* __restrict__ rng_state,
               const float* __restrict__ rowpre, const int* __restrict__ row_scene, const float* __restrict__ origin, int rows, int K,
               int rpt, int Tp, int Tf, sttode_decompose_weights w0, sttode_decompose_weights w1,
               const unsigned char* __restrict__ packed, const __grid_constant__ DecPackLayout lay, float* __restrict__ pred,
@@ -501,8 +502,8 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
                     lo4 = *reinterpret_cast<const float4*>(z + pair * 32 + kc * 8);
                     hi4 = *reinterpret_cast<const float4*>(z + pair * 32 + kc * 8 + 4);
                 } else {
-                    lo4 = latent_normal4(seed, pair, kc * 2);
-                    hi4 = latent_normal4(seed, pair, kc * 2 + 1);
+                    lo4 = latent_normal4(seed, pair_base + pair, kc * 2);
+                    hi4 = latent_normal4(seed, pair_base + pair, kc * 2 + 1);
                 }
                 v[0] = lo4.x; v[1] = lo4.y; v[2] = lo4.z; v[3] = lo4.w; v[4] = hi4.x; v[5] = hi4.y; v[6] = hi4.z; v[7] = hi4.w;
             } else {

@@ -44,7 +44,7 @@ size_t geo_attn_bwd_smem_bytes(int L, int S);
 constexpr int ROWPRE_LD = 2048;     // per-row layer-1 partial sums: [P0x | P0y | P1y | P1x], 512 each
 __global__ void k_dec_row(const float* past_feature, const float* traj_norm, int rows, int Tp, sttode_decompose_weights w0,
                           sttode_decompose_weights w1, float* rowpre, const int* only_flagged);
-__global__ void k_dec_pair(const float* traj_norm, const float* z, unsigned long long seed, const unsigned long long* rng_state,
+__global__ void k_dec_pair(const float* traj_norm, const float* z, unsigned long long seed, unsigned long long pair_base, const unsigned long long* rng_state,
                            const float* rowpre,
                            const int* row_scene, const float* origin, int rows, int K, int rpt, int Tp, int Tf,
                            sttode_decompose_weights w0, sttode_decompose_weights w1, float* pred, float* recon, const int* only_flagged);
@@ -66,7 +66,7 @@ struct DecPackLayout {               // byte offsets inside the packed weight bu
 DecPackLayout dec_pack_layout(int Tp, int Tf);
 __global__ void k_pack_image(const float* W, int ldw, int row0, int col0, int nvalid, int nrows, int K, unsigned char* hi,
                              unsigned char* lo);
-__global__ void k_dec_pair_tc(const float* traj_norm, const float* z, unsigned long long seed, const unsigned long long* rng_state,
+__global__ void k_dec_pair_tc(const float* traj_norm, const float* z, unsigned long long seed, unsigned long long pair_base, const unsigned long long* rng_state,
                               const float* rowpre,
                               const int* row_scene, const float* origin, int rows, int K, int rpt, int Tp, int Tf,
                               sttode_decompose_weights w0, sttode_decompose_weights w1, const unsigned char* packed,

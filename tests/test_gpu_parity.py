@@ -351,6 +351,43 @@ def test_host_buffer_entry_point(eth, dev):
     assert torch.equal(pred_h, pred_d.cpu())
 
 
+def test_host_entry_point_chunked_copy_overlap(dev):
+    """Large batches are forecast in several launches so the D2H copy of one chunk overlaps the kernels of the next; the latent
+    draw is keyed by the pair's index in the WHOLE batch, so the result is bit-identical to the single-launch device entry point.
+    ETH mode (ragged scenes, chunk cuts on scene boundaries) and NBA mode (cuts on whole attention groups), pageable and pinned output."""
+    import ctypes as C
+    import sttode_b200._lib as L
+    m, _ = build_model("eth", 8, 12, 1, dev)
+    scenes = synth.eth_scenes(460, cycle=(10, 20, 30, 40, 50, 60, 7))
+    counts = [o.shape[0] for o, _ in scenes]
+    obs = torch.cat([o for o, _ in scenes]).contiguous()
+    sp = torch.tensor(np.concatenate([[0], np.cumsum(counts)]), dtype=torch.int32)
+    rows = obs.shape[0]
+    assert rows * 20 * 12 * 2 * 4 > 2 * (12 << 20)            # at least two chunks
+    mw = m._weights()
+    m._seed = lambda: 77
+    want = m.forecast_scenes(obs.to(dev), sp).cpu()
+    for pinned in (False, True):
+        pred_h = torch.empty(rows, 20, 12, 2).pin_memory() if pinned else torch.empty(rows, 20, 12, 2)
+        L.check(L.lib().sttode_forecast_host(obs.data_ptr(), 1, sp.data_ptr(), len(counts), rows, 1, 1, 77, 20, C.byref(mw), pred_h.data_ptr(), L.stream_ptr()))
+        assert torch.equal(pred_h, want)
+    # NBA mode: 48 groups of (L = 16 scenes x 11 agents), 10/20 frames
+    mn, _ = build_model("nba", 10, 20, 2, dev)
+    Lg, groups = 16, 48
+    past = torch.cat([synth.nba_batch(i, Lg, 11, 10, 20)["past_traj"] for i in range(groups)]).contiguous()      # [groups*L, 11, 10, 2]
+    rows = groups * Lg * 11
+    mwn = mn._weights()
+    pred_h = torch.empty(rows, 20, 20, 2)
+    L.check(L.lib().sttode_forecast_host(past.data_ptr(), 0, None, 0, rows, Lg, 11, 5, 20, C.byref(mwn), pred_h.data_ptr(), L.stream_ptr()))
+    pred_d = torch.empty(rows, 20, 20, 2, device=dev)
+    ws = L.workspace(L.lib().sttode_forecast_workspace_bytes(rows, Lg, 20, 10), dev)
+    pd = past.to(dev)
+    L.check(L.lib().sttode_forecast(L.dptr(pd), 0, None, None, 0, rows, Lg, 11, None, 5, 20, C.byref(mwn), L.dptr(pred_d), None, None, None,
+                                    L.dptr(ws), ws.numel(), L.stream_ptr()))
+    assert torch.equal(pred_h, pred_d.cpu())
+    assert m.tc_status() == 0 and mn.tc_status() == 0
+
+
 # ------------------------------------------------------------------ pmath
 @pytest.mark.parametrize("c", [1.0, 0.5])
 def test_pmath_vs_reference_golden(golden, dev, c):
