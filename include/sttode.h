@@ -118,6 +118,9 @@ int sttode_profile_read(double *total_ms, unsigned long long *launches);
 /* tcgen05 building-block check: c[128,n] = a[128,k] . b[n,k]^T on the tensor cores, passes = 1 (fp16 inputs) or
  * 3 (fp16 hi/lo split, fp32-accurate).  status (device int) is set to 1 if the MMA never completed. */
 int sttode_umma_selftest(const float *a, const float *b, float *c, int n, int k, int passes, int swap_lbo_sbo, int *status, void *stream);
+/* Diagnostic: issue `reps` back-to-back tcgen05.mma (M = 128, K = 16, kind::f16, width n) on resident operands; cycles2_dev[0] = clock64 cycles from
+ * first issue to completion, [1] = cycles spent in the issue loop (device pointer to two long long). */
+int sttode_umma_bench(int n, int reps, long long *cycles2_dev, void *stream);
 
 /* ---- MHGSA: replaces Hyp_mhsa.forward -> hyp_mhsa (hyptransformerlib.py:403-454 -> :29-311) ------
  * query [L,bsz,E], key/value [S,bsz,E] (key==value==query pointer for self-attention), out [L,bsz,E],

@@ -1,0 +1,13 @@
+"""Cycles per tcgen05.mma (M=128, K=16, kind::f16, no-swizzle K-major operands) as a function of N: run on the GPU box."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import sttode_b200._lib as L
+lib = L.lib()
+out = torch.zeros(2, dtype=torch.int64, device="cuda")
+for n in (16, 32, 48, 64, 96, 128, 192, 256):
+    for reps in (64, 256):
+        L.check(lib.sttode_umma_bench(n, reps, out.data_ptr(), L.stream_ptr()))
+        torch.cuda.synchronize()
+        tot, iss = out.tolist()
+        print(f"N={n:3d} reps={reps:3d}: total {tot:7d} cyc = {tot / reps:6.1f}/mma   issue loop {iss:7d} = {iss / reps:6.1f}/mma   (ideal {n / 2:.0f})")

@@ -15,6 +15,7 @@ void launch_pmath_matvec(const float* m, const float* x, float* out, int rows, i
 void launch_pmath_dist_matrix(const float* x, const float* y, float* out, int b, int n, int d, float c, cudaStream_t st);
 void launch_pmath_elem(int op, const float* x, float* out, size_t n, float clampv, cudaStream_t st);
 int launch_umma_selftest(const float* A, const float* B, float* C, int N, int K, int passes, int swap, int* status, cudaStream_t st);
+int launch_umma_bench(int N, int reps, long long* cycles, cudaStream_t st);
 void launch_oblique_proj(const float* x, float* out, int rows, int d, cudaStream_t st);
 void launch_oblique_dist(const float* p1, const float* p2, float* out, int batch, int n1, int n2, int d, float lo, float hi, cudaStream_t st);
 }
@@ -666,6 +667,14 @@ int sttode_umma_selftest(const float* a, const float* b, float* c, int n, int k,
     int e = launch_umma_selftest(a, b, c, n, k, passes, swap_lbo_sbo, status, (cudaStream_t)stream);
     g_launches.fetch_add(1);
     if (e) return fail(STTODE_ECUDA, "selftest launch: %s", cudaGetErrorString((cudaError_t)e));
+    return 0;
+}
+
+int sttode_umma_bench(int n, int reps, long long* cycles2_dev, void* stream) {
+    if (!cycles2_dev || n < 16 || n > 256 || n % 16 || reps < 1) return fail(STTODE_EINVAL, "umma_bench: N in [16,256] %%16, reps >= 1");
+    int e = launch_umma_bench(n, reps, cycles2_dev, (cudaStream_t)stream);
+    g_launches.fetch_add(1);
+    if (e) return fail(STTODE_ECUDA, "umma_bench launch: %s", cudaGetErrorString((cudaError_t)e));
     return 0;
 }
 

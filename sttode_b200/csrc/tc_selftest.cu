@@ -76,6 +76,44 @@ k_umma_selftest(const float* __restrict__ A, const float* __restrict__ B, float*
     if (warp == 0) tc::tmem_dealloc(tmem, 256);
 }
 
+// Issue-rate probe: `reps` back-to-back tcgen05.mma (M = 128, K = 16, kind::f16) of width N on resident zero operands, timed with
+// clock64 from the first issue to the mbarrier completion of the trailing commit.  cycles[0] = total, cycles[1] = issue loop only.
+__global__ void __launch_bounds__(128, 1) k_umma_bench(int N, int reps, long long* __restrict__ cycles) {
+    extern __shared__ __align__(128) unsigned char sm[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + (128 + 256) * 32);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (128 + 256) * 32 / 4; i += 128) reinterpret_cast<uint32_t*>(sm)[i] = 0;
+    if (warp == 0) tc::tmem_alloc(tmem_slot, 256);
+    if (tid == 0) { tc::mbar_init(bar, 1); tc::fence_mbar_init(); }
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    if (tid == 0) {
+        const uint32_t idesc = tc::make_idesc_f16(N);
+        const uint64_t da = tc::op_desc(tc::smem_u32(sm), 128), db = tc::op_desc(tc::smem_u32(sm) + 128 * 32, N);
+        const long long t0 = clock64();
+        for (int i = 0; i < reps; ++i) tc::mma_f16_nc(tmem, da, db, idesc, 1u);
+        const long long t1 = clock64();
+        tc::mma_commit(bar);
+        tc::mbar_wait(bar, 0);
+        const long long t2 = clock64();
+        cycles[0] = t2 - t0;
+        cycles[1] = t1 - t0;
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 256);
+}
+
+int launch_umma_bench(int N, int reps, long long* cycles, cudaStream_t st) {
+    const size_t smem = (128 + 256) * 32 + 64;
+    k_umma_bench<<<1, 128, smem, st>>>(N, reps, cycles);
+    return (int)cudaGetLastError();
+}
+
 int launch_umma_selftest(const float* A, const float* B, float* C, int N, int K, int passes, int swap, int* status, cudaStream_t st) {
     const size_t smem = (size_t)(128 + N) * K * 2 * 2 + 64;
     cudaError_t e = cudaFuncSetAttribute(k_umma_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
