@@ -1,6 +1,6 @@
 """Generate tests/golden/*.npz by running the UNMODIFIED reference (under oracle/ref_shim.py) here.
 
-Run in the build container only (needs /root/reference):   python oracle/make_golden.py [forward|backward|training|all]
+Run in the build container only (needs /root/reference):   python oracle/make_golden.py [forward|backward|training|sampler|all]
 The fixtures pin `oracle/sttode_oracle.py` and `oracle/pmath_oracle.py` to the reference's own outputs and
 travel to the GPU box, where /root/reference does not exist.  Weights are NOT stored: both sides rebuild
 them with `make_state_dict(seed)`; the reference side loads them with `load_state_dict(strict=True)`,
@@ -247,8 +247,71 @@ def training_golden():
     print("training_step.npz", os.path.getsize(os.path.join(OUT, "training_step.npz")))
 
 
+def sampler_args(dataset, tp, tf):
+    a = ref_shim.make_args(dataset, tp, tf)
+    a.nz, a.qnet_mlp, a.share_eps, a.train_w_mean = 32, [512, 256], True, True
+    a.kld_weight, a.kld_min_clamp, a.recon_weight = 0.1, 10, 5.0        # trainsampler.py:59-62,90-92
+    return a
+
+
+def sampler_golden():
+    """One step of the reference's second stage (trainsampler.py:133-149): Sampler.forward over the frozen STTODENet with only
+    the decoder in train() mode, compute_sampler_loss_nba, backward: dec_motion, loss terms and the sampler's gradients.
+    Both mean=True (the reference's default) and mean=False (eps injected)."""
+    ref = ref_shim.install()
+    import sampler as ref_sampler
+    import samplerloss as ref_loss
+    rec = {}
+    g = torch.Generator().manual_seed(51)
+    eps1 = torch.randn(1, 32, generator=g)
+    # case "mean": NBA, B = 4, mean=True (the reference's default; its mean=False branch only shape-checks when batch_size == 1)
+    # case "eps":  ETH scene of 7 agents, mean=False with the shared eps row injected
+    for t, dataset, tp, tf, B, N, mean in (("mean", "nba", 5, 10, 4, 11, True), ("eps", "eth", 8, 12, 1, 7, False)):
+        torch.manual_seed(3)
+        net = ref.sttode.STTODENet(ref_shim.make_args(dataset, tp, tf), torch.device("cpu")).eval()
+        torch.manual_seed(4)
+        smp = ref_sampler.Sampler(sampler_args(dataset, tp, tf))
+        d = training_draws(B * N, tp, tf, seed=50)
+        queue = [d["eps_q"], d["eps_mid"], d["eps_p"]]
+        ref.sttode.Normal.rsample = lambda self: self.mu + queue.pop(0) * self.sigma
+        net.decoder.train()
+        if dataset == "nba":
+            data = synth.nba_batch(3, B, N, tp, tf)
+            net.set_data_nba(data)
+            fut = data["future_traj"].view(B * N, tf, 2)
+        else:
+            obs, gt = synth.eth_scene(5, N)
+            net.set_data(None, obs, gt, torch.ones(N, tp), torch.ones(N, tf))
+            fut = gt.transpose(1, 2)
+        orig_randn = torch.randn
+        torch.randn = lambda *a, **k: eps1.clone()             # Sampler's own draw (share_eps: one [1, nz] row, sampler.py:42-43)
+        try:
+            smp.zero_grad(set_to_none=True)
+            dec_motion, sdist, vdist, _ = smp.forward(net, mean=mean)
+        finally:
+            torch.randn = orig_randn
+        div_cfg = {"weight": 1, "scale": 1.0}                  # trainsampler.py:106-111 (eth and nba)
+        if dataset == "nba":
+            dm = dec_motion.permute(1, 0, 2, 3).reshape([-1, 20, 10, 2])       # the reference's reshuffle, kept as is (trainsampler.py:141-143)
+            total, ld, _ = ref_loss.compute_sampler_loss_nba(sampler_args(dataset, tp, tf), fut, dm, 1, vdist, sdist, div_cfg)
+        else:
+            total, ld, _ = ref_loss.compute_sampler_loss(sampler_args(dataset, tp, tf), fut, dec_motion, 1, torch.ones(N, tf), vdist, sdist, div_cfg)
+        total.backward()
+        rec[f"{t}_dec_motion"] = np32(dec_motion)
+        rec[f"{t}_losses"] = np.array([float(total), float(ld["kld"]), float(ld["diverse"])], np.float64)
+        for n, p_ in smp.named_parameters():
+            g_ = (p_.grad if p_.grad is not None else torch.zeros_like(p_)).detach().flatten()
+            rec[f"{t}_g_{n}"] = np32(g_[grad_sample_index(g_.numel())])
+            rec[f"{t}_gstat_{n}"] = np.array([float(g_.double().norm()), float(g_.abs().max())], np.float64)
+    rec["eps1"] = np32(eps1)
+    np.savez_compressed(os.path.join(OUT, "sampler_step.npz"), **rec)
+    print("sampler_step.npz", os.path.getsize(os.path.join(OUT, "sampler_step.npz")))
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("sampler", "all"):
+        sampler_golden()
     if what in ("training", "all"):
         training_golden()
     if what in ("forward", "all"):

@@ -481,46 +481,53 @@ class STTODENet(nn.Module):
     # ---- data staging (reference call sequence) ---------------------------------------------------
     def set_data(self, batch, pre_motion, fut_motion, pre_motion_mask, fut_motion_mask):
         """ETH/UCY/SDD: pre_motion [N,2,T_p], fut_motion [N,2,T_f] as the loaders yield them (model/STTODE.py:397-461).
-        eval(): staging only (normalisation and velocities run inside sttode_forecast).  train(): the reference's agent
-        subsampling (np.random.choice, > max_train_agent) and random scene rotation, then the explicit feature tensors."""
+        Stages the explicit tensors the reference stages (`inputs`, `inputs_for_posterior`, `past_traj`, `future_traj`,
+        `cur_location`, `scene_orig`); in train() mode with the reference's agent subsampling (np.random.choice, > max_train_agent)
+        and random scene rotation.  `inference()` itself only needs the raw scene (normalisation and velocities run inside
+        sttode_forecast), so fut_motion may be None there."""
         self.batch_size = 1
         self._mode = "scene"
-        pre = pre_motion.to(self.device)
-        if not self.training:
-            self._obs = _f32c(pre, "pre_motion")
-            self.agent_num = self._obs.shape[0]
-            self.pre_motion_mask, self.fut_motion_mask = pre_motion_mask, fut_motion_mask
-            self.fut_motion_orig = fut_motion.transpose(1, 2) if fut_motion is not None else None
-            return
         dev = self.device
+        pre = pre_motion.to(dev)
+        self._obs = _f32c(pre, "pre_motion")                       # inference() hands the raw scene to sttode_forecast
+        self.pre_motion_mask, self.fut_motion_mask = pre_motion_mask, fut_motion_mask
+        if fut_motion is None:                                     # inference-only staging
+            self.agent_num = self._obs.shape[0]
+            self.fut_motion_orig = None
+            self._features_staged = False
+            return
         fut = fut_motion.to(dev)
         fut_orig = fut.transpose(1, 2)
         pre, fut = pre.permute(2, 0, 1), fut.permute(2, 0, 1)                         # [T,N,2]
-        if pre.shape[1] > self.max_train_agent:                                       # model/STTODE.py:405-413
+        if self.training and pre.shape[1] > self.max_train_agent:                     # model/STTODE.py:405-413
             ind = torch.tensor(np.random.choice(pre.shape[1], self.max_train_agent).tolist(), device=dev)
             pre, fut = pre.index_select(1, ind).contiguous(), fut.index_select(1, ind).contiguous()
             pre_motion_mask, fut_motion_mask = pre_motion_mask.to(dev).index_select(0, ind), fut_motion_mask.to(dev).index_select(0, ind)
+            self.pre_motion_mask, self.fut_motion_mask = pre_motion_mask, fut_motion_mask
             fut_orig = fut_orig.index_select(0, ind).contiguous()
+            self._obs = pre.permute(1, 2, 0).contiguous()
         self.agent_num = pre.shape[1]
         self.scene_orig = pre[[-1]].view(-1, 2).mean(dim=0)
-        if self.rand_rot_scene:                                                       # :419-426
+        if self.rand_rot_scene and self.training:                                     # :419-426
             theta = getattr(self, "theta_override", None)
             if theta is None:
                 theta = (torch.randint(high=24, size=(1,)).to(dev) * (np.pi / 12)) if self.discrete_rot else torch.rand(1).to(dev) * np.pi * 2
             pre, pre_norm = _rotation_2d(pre, theta, self.scene_orig)
             fut, fut_norm = _rotation_2d(fut, theta, self.scene_orig)
             fut_orig, _ = _rotation_2d(fut_orig, theta, self.scene_orig)
+            self._obs = pre.permute(1, 2, 0).contiguous()
         else:
             pre_norm, fut_norm = pre - self.scene_orig, fut - self.scene_orig
         pre_vel = pre[1:] - pre[:-1]
         pre_vel = torch.cat([pre_vel[[0]], pre_vel], dim=0)
         fut_vel = fut - torch.cat([pre[[-1]], fut[:-1]])
-        self.pre_motion_mask, self.fut_motion_mask, self.fut_motion_orig = pre_motion_mask, fut_motion_mask, fut_orig
+        self.fut_motion_orig = fut_orig
         self.inputs = torch.cat([pre_norm, pre_vel], dim=-1).permute(1, 0, 2).contiguous()
         self.inputs_for_posterior = torch.cat([fut_norm, fut_vel], dim=-1).permute(1, 0, 2).contiguous()
         self.past_traj = pre_norm.permute(1, 0, 2).contiguous()
         self.future_traj = fut_norm.permute(1, 0, 2).contiguous()
         self.cur_location = self.past_traj[:, [-1]]
+        self._features_staged = True
 
     def set_data_nba(self, data):
         """NBA: data['past_traj'] [B,N,T_p,2] (model/STTODE.py:463-486)."""
@@ -593,54 +600,83 @@ class STTODENet(nn.Module):
         """CUDA-graph version of `forecast_scenes` (n_scenes > 0, L = 1) or of NBA-style inference (n_scenes = 0) for a fixed shape."""
         return ForecastGraph(self, rows, L, agents, n_scenes, layout, sample_k).capture()
 
-    # ---- training objective -----------------------------------------------------------------------------------------------
+    # ---- training objective: the reference's stage methods (model/STTODE.py:488-568), also driven by sampler.py ------------------
     def _stage_features(self):
-        """(inputs [R,T_p,4], inputs_for_posterior [R,T_f,4], past [R,T_p,2], future [R,T_f,2]) of the staged batch."""
+        """Make `inputs`, `inputs_for_posterior`, `past_traj`, `future_traj`, `cur_location` current for the staged batch."""
         if getattr(self, "_mode", None) == "nba":                                   # model/STTODE.py:463-481
             dev, B, N = self.device, self.batch_size, self.agent_num
             past = _f32c(self.data["past_traj"].to(dev), "past_traj").view(B * N, self.args.past_length, 2)
             fut = _f32c(self.data["future_traj"].to(dev), "future_traj").view(B * N, self.args.future_length, 2)
             vel = past[:, 1:] - past[:, :-1]
-            inputs = torch.cat((past, torch.cat([vel[:, [0]], vel], dim=1)), dim=-1)
+            self.inputs = torch.cat((past, torch.cat([vel[:, [0]], vel], dim=1)), dim=-1)
             fvel = fut - torch.cat([past[:, [-1]], fut[:, :-1]], dim=1)
+            self.inputs_for_posterior = torch.cat((fut, fvel), dim=-1)
             self.scene_orig = self.past_traj = past
             self.future_traj, self.cur_location = fut, past[:, [-1]]
-            return inputs, torch.cat((fut, fvel), dim=-1), past, fut
-        if getattr(self, "_mode", None) == "scene" and self.training:
-            return self.inputs, self.inputs_for_posterior, self.past_traj, self.future_traj
-        raise NotImplementedError("STTODENet.forward: stage the batch with set_data_nba, or with set_data in train() mode "
-                                  "(eval-mode set_data keeps only what inference needs)")
+        elif not (getattr(self, "_mode", None) == "scene" and getattr(self, "_features_staged", False)):
+            raise NotImplementedError("STTODENet: stage the batch with set_data_nba, or with set_data(..., fut_motion) first")
+
+    def _grad_ctx(self):
+        # autograd history exists wherever a sub-module is in train() mode (train.py trains everything; trainsampler.py:135 puts
+        # only the decoder in train() so gradients reach the sampler through z)
+        on = self.training or self.decoder.training
+        return torch.set_grad_enabled(on and torch.is_grad_enabled())
+
+    def encode_history(self):
+        """model/STTODE.py:488-496."""
+        with self._grad_ctx():
+            self._stage_features()
+            self.past_feature = self.past_encoder(self.inputs, self.batch_size, self.agent_num)
+
+    def fu_encoder(self):
+        """model/STTODE.py:498-527: q(z | past, future), its sample, and the N(0, I) prior with its (discarded) sample."""
+        args, dev = self.args, self.device
+        with self._grad_ctx():
+            self.qz_param = self.future_encoder(self.inputs_for_posterior, self.batch_size, self.agent_num, self.past_feature)
+            self.qz_dis = Normal(params=self.qz_param.repeat_interleave(20, dim=0))
+            self.qz_distribution = Normal(params=self.qz_param)
+            eps = getattr(self, "eps_override", None)
+            sigma = self.qz_distribution.sigma
+            self.qz_sampled = self.qz_distribution.mu + (eps[0].to(dev) if eps is not None else torch.randn_like(sigma)) * sigma
+            R = self.past_feature.shape[0]
+            self.pz_distribution = Normal(mu=torch.zeros(R, args.zdim, device=dev), logvar=torch.zeros(R, args.zdim, device=dev))
+            self.pz_sampled = torch.randn_like(sigma) if eps is None else None       # drawn and overwritten in the reference too (:525,549)
+
+    def decoder_future_0(self, qz_sampled):
+        """model/STTODE.py:534-551: K = 1 decode (prediction + reconstruction), then the prior samples of the best-of-20 term."""
+        args, dev = self.args, self.device
+        with self._grad_ctx():
+            self.pred_traj, self.recover_traj = self.decoder(self.past_feature, qz_sampled, self.batch_size, self.agent_num, self.past_traj,
+                                                             self.cur_location, sample_num=1)
+            self.past_feature_repeat = self.past_feature.repeat_interleave(20, dim=0)
+            R20 = self.past_feature_repeat.shape[0]
+            self.pz_dis = Normal(mu=torch.zeros(R20, args.zdim, device=dev), logvar=torch.zeros(R20, args.zdim, device=dev))
+            eps = getattr(self, "eps_override", None)
+            self.pz_sampled = eps[1].to(dev) if eps is not None else torch.randn(R20, args.zdim, device=dev)
+
+    def decoder_future_1(self, pz_sampled):
+        """model/STTODE.py:529-532: the K = 20 decode."""
+        with self._grad_ctx():
+            self.diverse_pred_traj, self.attn_weights = self.decoder(self.past_feature_repeat, pz_sampled, self.batch_size, self.agent_num,
+                                                                     self.past_traj, self.cur_location, sample_num=20, mode="inference")
 
     def forward(self):
         """The reference's training objective (model/STTODE.py:553-568) on the staged batch:
         (total_loss, loss_pred, loss_recover, loss_kl, loss_diverse).  train(): total_loss carries autograd history (call
         .backward() on it as train.py:65 does).  eval(): forward-only, every stage inside the library.
         `self.eps_override = (eps_q [R,zdim], eps_p [R*20,zdim])` injects the two live rsample draws (tests)."""
-        args, dev = self.args, self.device
-        with torch.set_grad_enabled(self.training and torch.is_grad_enabled()):
-            inputs, inputs_post, past, fut = self._stage_features()
+        args = self.args
+        self.encode_history()
+        self.fu_encoder()
+        self.decoder_future_0(self.qz_sampled)
+        with self._grad_ctx():
             B, N, Tp, Tf = self.batch_size, self.agent_num, args.past_length, args.future_length
-            R = B * N
-            self.past_feature = self.past_encoder(inputs, B, N)
-            self.qz_param = self.future_encoder(inputs_post, B, N, self.past_feature)
-            self.qz_distribution = Normal(params=self.qz_param)
-            mu, sigma = self.qz_distribution.mu, self.qz_distribution.sigma
-            eps = getattr(self, "eps_override", None)
-            eps_q = eps[0].to(dev) if eps is not None else torch.randn_like(sigma)
-            self.qz_sampled = mu + eps_q * sigma
-            self.pz_distribution = Normal(mu=torch.zeros(R, args.zdim, device=dev), logvar=torch.zeros(R, args.zdim, device=dev))
-            if eps is None:
-                torch.randn_like(sigma)          # the reference draws pz_distribution.rsample() here and discards it (:525)
-            cur = past[:, [-1]]
-            self.pred_traj, self.recover_traj = self.decoder(self.past_feature, self.qz_sampled, B, N, past, cur, sample_num=1)
-            eps_p = eps[1].to(dev) if eps is not None else torch.randn(R * 20, args.zdim, device=dev)
-            self.pz_sampled = eps_p
-            loss_pred = (fut - self.pred_traj).pow(2).sum() / B / Tf                  # :372-376
-            loss_recover = (past - self.recover_traj).pow(2).sum() / B / Tp          # :384-387
+            loss_pred = (self.future_traj - self.pred_traj).pow(2).sum() / B / Tf                  # :372-376
+            loss_recover = (self.past_traj - self.recover_traj).pow(2).sum() / B / Tp              # :384-387
             loss_kl = (self.qz_distribution.kl(self.pz_distribution).sum() / (B * N)).clamp_min(args.min_clip)     # :378-382
-            self.past_feature_repeat = self.past_feature.repeat_interleave(20, dim=0)
-            self.diverse_pred_traj, _ = self.decoder(self.past_feature_repeat, eps_p, B, N, past, cur, sample_num=20, mode="inference")
-            diff = fut.unsqueeze(1) - self.diverse_pred_traj                          # :389-395
+        self.decoder_future_1(self.pz_sampled)
+        with self._grad_ctx():
+            diff = self.future_traj.unsqueeze(1) - self.diverse_pred_traj                          # :389-395
             loss_diverse = diff.pow(2).sum(dim=-1).sum(dim=-1).min(dim=1)[0].mean()
             total = loss_pred + loss_recover + loss_kl + loss_diverse
         return total, loss_pred.item(), loss_recover.item(), loss_kl.item(), loss_diverse.item()

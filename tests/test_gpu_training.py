@@ -71,7 +71,7 @@ def test_training_step_batch32_vs_oracle_float64(dev):
     out = O.training_objective(sd64, data["past_traj"].view(B * N, tp, 2).double(), data["future_traj"].view(B * N, tf, 2).double(), B, N,
                                d["eps_q"].double(), d["eps_p"].double(), masks=(d["mask_past"], d["mask_future"]), tensors=True)
     out["total"].backward()
-    assert abs(float(total) - float(out["total"])) <= TOL * abs(float(out["total"]))
+    assert abs(float(total.detach()) - float(out["total"].detach())) <= TOL * abs(float(out["total"].detach()))
     for got, key in zip(parts, ("pred", "recover", "kl", "diverse")):
         assert abs(got - out[key]) <= TOL * abs(out[key]), key
     for n, p in m.named_parameters():
