@@ -220,6 +220,22 @@ int sttode_decoder_fwd(const float *past_feature, const float *traj_norm, const 
                        const sttode_model_weights *w, float *pred, float *recon, void *workspace,
                        size_t workspace_bytes, void *stream);
 
+/* ---- backward of Decoder.forward in 'train' mode (model/STTODE.py:320-347, both DecomposeBlocks :51-77); the reference gets it from
+ * torch autograd (train.py:65).  One row per (agent, sample) pair: past_feature [pairs,128], z [pairs,32], traj_norm [pairs,T_p,2] (x_true,
+ * already repeated per sample), d_pred [pairs,T_f,2] = gradient of out_seq, d_recon [pairs,T_p,2] = gradient of recover_pre_seq (NULL when
+ * the reconstruction is unused, as in decoder_future_1).  The forward is re-materialised from the inputs (Conv1d as a GEMM over im2col,
+ * the GRU recurrence step by step), then back-propagated through time; d_past_feature [pairs,128] and d_z [pairs,32] are overwritten,
+ * parameter gradients are ACCUMULATED (+=) into `grads` (same shapes as the weights; member blocks may not be NULL). */
+typedef struct sttode_mlp3_grads { float *w0, *b0, *w1, *b1, *w2, *b2; } sttode_mlp3_grads;
+typedef struct sttode_decompose_grads {
+    float *conv_w, *conv_b, *gru_w_ih, *gru_w_hh, *gru_b_ih, *gru_b_hh;
+    sttode_mlp3_grads dec_y, dec_x;
+} sttode_decompose_grads;
+size_t sttode_decoder_bwd_workspace_bytes(int pairs, int past_length, int future_length);
+int sttode_decoder_bwd(const float *past_feature, const float *z, const float *traj_norm, const float *d_pred, const float *d_recon,
+                       int pairs, const sttode_model_weights *w, const sttode_decompose_grads *grads2, float *d_past_feature, float *d_z,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
 /* Tensor-core decoder: split the decoder weights once per weight version into the fp16 hi/lo operand images the
  * tcgen05 kernel streams (caller-owned buffer of sttode_decoder_pack_bytes).  The last 256 bytes are a status word
  * (int32, 0 = ok) that the kernel sets if an MMA/copy barrier ever times out; read it with sttode_decoder_pack_status

@@ -45,6 +45,15 @@ class DecomposeWeights(C.Structure):
                [("dec_y", Mlp3Weights), ("dec_x", Mlp3Weights)]
 
 
+class Mlp3Grads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("w0", "b0", "w1", "b1", "w2", "b2")]
+
+
+class DecomposeGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("conv_w", "conv_b", "gru_w_ih", "gru_w_hh", "gru_b_ih", "gru_b_hh")] + \
+               [("dec_y", Mlp3Grads), ("dec_x", Mlp3Grads)]
+
+
 class ModelWeights(C.Structure):
     _fields_ = [("past_length", C.c_int), ("future_length", C.c_int), ("past", EncoderWeights), ("dec", DecomposeWeights * 2),
                 ("dec_packed", C.c_void_p), ("rng_state", C.c_void_p)]
@@ -82,6 +91,8 @@ SIGNATURES = {
     "sttode_linear": (_I, [_V, _V, _V, _V, _I, _I, _I, _I, _V]),
     "sttode_decoder_workspace_bytes": (_Z, [_I, _I]),
     "sttode_decoder_fwd": (_I, [_V, _V, _V, _U64, _V, _V, _I, _I, C.POINTER(ModelWeights), _V, _V, _V, _Z, _V]),
+    "sttode_decoder_bwd_workspace_bytes": (_Z, [_I, _I, _I]),
+    "sttode_decoder_bwd": (_I, [_V, _V, _V, _V, _V, _I, C.POINTER(ModelWeights), C.POINTER(DecomposeGrads), _V, _V, _V, _Z, _V]),
     "sttode_decoder_pack_bytes": (_Z, [_I, _I]),
     "sttode_decoder_pack": (_I, [C.POINTER(ModelWeights), _V, _Z, _V]),
     "sttode_decoder_pack_status": (_I, [_V, _I, _I, C.POINTER(C.c_int)]),

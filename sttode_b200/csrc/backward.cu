@@ -293,6 +293,100 @@ k_geo_attn_bwd(const float* __restrict__ qh, int ldq, const float* __restrict__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Decoder backward helpers (DecomposeBlock: Conv1d(2->32,k3,pad1)+ReLU -> GRU(32->96) -> two 3-layer MLPs; model/STTODE.py:51-77).
+// ------------------------------------------------------------------------------------------------
+// col[(p*T + t), c*3 + k] = x[p, t + k - 1, c] (zero outside [0, T)), x = x_true - x_hat (x_hat nullable): the conv as a GEMM with
+// conv_past.weight viewed as [32, 6] (c-major, k-minor = its memory order).  Also writes xin = x_true - x_hat when xin != null.
+__global__ void k_conv_im2col(const float* __restrict__ x_true, const float* __restrict__ x_hat, int P, int T, float* __restrict__ col) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)P * T * 6) return;
+    const int e = (int)(idx % 6), c = e / 3, k = e - c * 3;
+    const size_t pt = idx / 6;
+    const int t = (int)(pt % T);
+    const size_t p = pt / T;
+    const int tt = t + k - 1;
+    float v = 0.f;
+    if (tt >= 0 && tt < T) {
+        const size_t o = (p * T + tt) * 2 + c;
+        v = x_true[o] - (x_hat ? x_hat[o] : 0.f);
+    }
+    col[idx] = v;
+}
+// dxin[p, t, c] = sum_k dcol[(p*T + t - k + 1), c*3 + k]  (transpose of im2col);  out = base (nullable) - dxin
+// (block 1 sees x_true - x_hat0, so d x_hat0 = d recon - d xin1)
+__global__ void k_conv_col2im_neg(const float* __restrict__ dcol, const float* __restrict__ base, int P, int T, float* __restrict__ out) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)P * T * 2) return;
+    const int c = (int)(idx & 1);
+    const size_t pt = idx >> 1;
+    const int t = (int)(pt % T);
+    const size_t p = pt / T;
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int ts = t - k + 1;                   // source time whose tap k reads x[t]
+        if (ts >= 0 && ts < T) s += dcol[((p * T + ts) * 6) + c * 3 + k];
+    }
+    out[idx] = (base ? base[idx] : 0.f) - s;
+}
+// One GRU step (PyTorch gate order r, z, n):  gi = W_ih x_t + b_ih (row stride ldgi), gh = W_hh h + b_hh.
+//   r = s(gi_r + gh_r), z = s(gi_z + gh_z), n = tanh(gi_n + r * gh_n), h' = (1 - z) n + z h.   Saves r | z | n and gh_n for the backward.
+__global__ void k_gru_step_fwd(const float* __restrict__ gi, long ldgi, const float* __restrict__ gh, const float* __restrict__ h, int P,
+                               float* __restrict__ rzn, float* __restrict__ ghn, float* __restrict__ hout) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)P * 96) return;
+    const size_t p = idx / 96;
+    const int u = (int)(idx - p * 96);
+    const float* gip = gi + p * ldgi;
+    const float* ghp = gh + p * 288;
+    const float r = sigmoidf_(gip[u] + ghp[u]), z = sigmoidf_(gip[96 + u] + ghp[96 + u]);
+    const float gn = ghp[192 + u];
+    const float n = tanhf(gip[192 + u] + r * gn);
+    rzn[p * 288 + u] = r;
+    rzn[p * 288 + 96 + u] = z;
+    rzn[p * 288 + 192 + u] = n;
+    ghn[idx] = gn;
+    hout[idx] = (1.f - z) * n + z * h[idx];
+}
+// Backward of one step.  dh = gradient of h'.  Writes d gi (row stride lddgi), d gh [P,288] and the direct carry dh * z into dh_prev.
+__global__ void k_gru_step_bwd(const float* __restrict__ dh, const float* __restrict__ rzn, const float* __restrict__ ghn,
+                               const float* __restrict__ hprev, int P, float* __restrict__ dgi, long lddgi, float* __restrict__ dgh,
+                               float* __restrict__ dh_prev) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)P * 96) return;
+    const size_t p = idx / 96;
+    const int u = (int)(idx - p * 96);
+    const float r = rzn[p * 288 + u], z = rzn[p * 288 + 96 + u], n = rzn[p * 288 + 192 + u];
+    const float d = dh[idx], gn = ghn[idx];
+    const float dn = d * (1.f - z) * (1.f - n * n);         // through tanh
+    const float dz = d * (hprev[idx] - n) * z * (1.f - z);
+    const float dr = dn * gn * r * (1.f - r);
+    float* gp = dgi + p * lddgi;
+    gp[u] = dr; gp[96 + u] = dz; gp[192 + u] = dn;
+    float* hp = dgh + p * 288;
+    hp[u] = dr; hp[96 + u] = dz; hp[192 + u] = dn * r;
+    dh_prev[idx] = d * z;
+}
+// dst[r, 0:n] = src[r, 0:n]   (row strides in floats)
+__global__ void k_rows_copy(const float* __restrict__ src, long lds, float* __restrict__ dst, long ldd, int rows, int n) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)rows * n) return;
+    const size_t r = idx / n;
+    const int c = (int)(idx - r * n);
+    dst[r * ldd + c] = src[r * lds + c];
+}
+
+// out[r, 0:n] = a[r, 0:n] + b[r, 0:n]
+__global__ void k_rows_add(const float* __restrict__ a, long lda, const float* __restrict__ b, long ldb, float* __restrict__ out, long ldo, int rows,
+                           int n) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)rows * n) return;
+    const size_t r = idx / n;
+    const int c = (int)(idx - r * n);
+    out[r * ldo + c] = a[r * lda + c] + b[r * ldb + c];
+}
+
 size_t geo_attn_bwd_smem_bytes(int L, int S) { return sizeof(float) * ((size_t)L * 18 + (size_t)S * 16); }
 
 }  // namespace sttode

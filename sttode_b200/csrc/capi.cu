@@ -461,6 +461,147 @@ size_t decoder_ws(int rows) { return align_up((size_t)rows * ROWPRE_LD * 4) + al
 int run_encoder(const float* traj, int layout, const int* scene_ptr, const int* row_scene, int n_scenes, int rows, int L, int agents, int T,
                 const sttode_encoder_weights& ew, float* past_feature, float* traj_norm, float* origin, Carver ws, cudaStream_t st);
 
+// ---- backward of the K-sample decoder (kernels in backward.cu) ------------------------------------------------------
+struct DecBlockSaved {      // forward intermediates of one DecomposeBlock over P pair rows
+    float *col, *c, *gi, *h, *rzn, *ghn, *feat, *ax1, *ax2, *xh, *ay1, *ay2;
+};
+size_t dec_block_saved_floats(size_t P, int Tp) {
+    return P * Tp * (6 + 32 + 288) + (size_t)(Tp + 1) * P * 96 + (size_t)Tp * P * (288 + 96) + P * (256 + 512 + 256 + 2 * Tp + 512 + 256);
+}
+size_t dec_bwd_ws_bytes(size_t P, int Tp, int Tf) {
+    const size_t tmax = (size_t)std::max(Tp, Tf);
+    size_t f = 2 * dec_block_saved_floats(P, Tp);                                   // two blocks
+    f += P * 288;                                                                   // gh scratch
+    f += 2 * P * 256 + P * (512 + 256) + 2 * P * 96;                                // dfeat x 2, da1, da2, dh ping-pong
+    f += P * Tp * 288 + (size_t)Tp * P * 288 + P * Tp * (32 + 6) + P * 2 * tmax;    // dgi, dgh, dc, dcol, dxh
+    return f * 4 + 64 * 256;                                                        // + alignment slack of the carver
+}
+
+int take_block(Carver& ws, size_t P, int Tp, DecBlockSaved* b) {
+    b->col = ws.take<float>(P * Tp * 6);    b->c = ws.take<float>(P * Tp * 32);     b->gi = ws.take<float>(P * Tp * 288);
+    b->h = ws.take<float>((size_t)(Tp + 1) * P * 96);
+    b->rzn = ws.take<float>((size_t)Tp * P * 288);  b->ghn = ws.take<float>((size_t)Tp * P * 96);
+    b->feat = ws.take<float>(P * 256);
+    b->ax1 = ws.take<float>(P * 512);  b->ax2 = ws.take<float>(P * 256);  b->xh = ws.take<float>(P * 2 * Tp);
+    b->ay1 = ws.take<float>(P * 512);  b->ay2 = ws.take<float>(P * 256);
+    return ws.ok() && b->ay2 ? 0 : fail(STTODE_EWORKSPACE, "workspace too small for the decoder backward");
+}
+
+// a1 = relu(feat W0^T + b0), a2 = relu(a1 W1^T + b1), out = a2 W2^T + b2 (out nullable: only the activations are needed)
+int mlp3_fwd(cudaStream_t st, int P, const sttode_mlp3_weights& w, int n3, const float* feat, float* a1, float* a2, float* out) {
+    int rc;
+    if ((rc = gemm_nt(st, P, 512, 256, feat, 256, w.w0, w.b0, a1, 512, 1))) return rc;
+    if ((rc = gemm_nt(st, P, 256, 512, a1, 512, w.w1, w.b1, a2, 256, 1))) return rc;
+    if (out && (rc = gemm_nt(st, P, n3, 256, a2, 256, w.w2, w.b2, out, n3))) return rc;
+    return 0;
+}
+// dfeat (+)= J^T dout through the 3-layer MLP; parameter gradients accumulated into g
+int mlp3_bwd(cudaStream_t st, int P, const sttode_mlp3_weights& w, const sttode_mlp3_grads& g, int n3, const float* dout, const float* feat,
+             const float* a1, const float* a2, float* da1, float* da2, float* dfeat, int accumulate) {
+    int rc;
+    if ((rc = weight_grad(st, P, n3, 256, dout, n3, a2, 256, g.w2, g.b2))) return rc;
+    if ((rc = gemm_nn(st, P, 256, n3, dout, n3, w.w2, da2, 256, nullptr, 0, a2, 256))) return rc;           // * relu'
+    if ((rc = weight_grad(st, P, 256, 512, da2, 256, a1, 512, g.w1, g.b1))) return rc;
+    if ((rc = gemm_nn(st, P, 512, 256, da2, 256, w.w1, da1, 512, nullptr, 0, a1, 512))) return rc;
+    if ((rc = weight_grad(st, P, 512, 256, da1, 512, feat, 256, g.w0, g.b0))) return rc;
+    return gemm_nn(st, P, 256, 512, da1, 512, w.w0, dfeat, 256, nullptr, 0, nullptr, 0, accumulate);
+}
+
+// Conv1d+ReLU -> GRU -> feat = [pf | z | h_T] for one block; x_hat (nullable) = previous block's reconstruction
+int dec_block_fwd(cudaStream_t st, int P, int Tp, const sttode_decompose_weights& w, const float* pf, const float* z, const float* x_true,
+                  const float* x_hat, float* gh, DecBlockSaved& b) {
+    int rc;
+    const int PT = P * Tp;
+    k_conv_im2col<<<ceil_div(PT * 6, 256), 256, 0, st>>>(x_true, x_hat, P, Tp, b.col);
+    LAUNCH_CHECK("k_conv_im2col");
+    if ((rc = gemm_nt(st, PT, 32, 6, b.col, 6, w.conv_w, w.conv_b, b.c, 32, 1))) return rc;
+    if ((rc = gemm_nt(st, PT, 288, 32, b.c, 32, w.gru_w_ih, w.gru_b_ih, b.gi, 288))) return rc;
+    CUDA_TRY(cudaMemsetAsync(b.h, 0, (size_t)P * 96 * 4, st));
+    for (int t = 0; t < Tp; ++t) {
+        const float* ht = b.h + (size_t)t * P * 96;
+        if ((rc = gemm_nt(st, P, 288, 96, ht, 96, w.gru_w_hh, w.gru_b_hh, gh, 288))) return rc;
+        k_gru_step_fwd<<<ceil_div(P * 96, 256), 256, 0, st>>>(b.gi + (size_t)t * 288, (long)Tp * 288, gh, ht, P, b.rzn + (size_t)t * P * 288,
+                                                              b.ghn + (size_t)t * P * 96, b.h + (size_t)(t + 1) * P * 96);
+        LAUNCH_CHECK("k_gru_step_fwd");
+    }
+    k_rows_copy<<<ceil_div(P * 128, 256), 256, 0, st>>>(pf, 128, b.feat, 256, P, 128);
+    LAUNCH_CHECK("k_rows_copy");
+    k_rows_copy<<<ceil_div(P * 32, 256), 256, 0, st>>>(z, 32, b.feat + 128, 256, P, 32);
+    LAUNCH_CHECK("k_rows_copy");
+    k_rows_copy<<<ceil_div(P * 96, 256), 256, 0, st>>>(b.h + (size_t)Tp * P * 96, 96, b.feat + 160, 256, P, 96);
+    LAUNCH_CHECK("k_rows_copy");
+    return 0;
+}
+
+// BPTT through the GRU and the conv of one block, starting from dfeat[:, 160:256] = d h_T.  dcol (nullable) receives d im2col(x).
+int dec_block_bwd(cudaStream_t st, int P, int Tp, const sttode_decompose_weights& w, const sttode_decompose_grads& g, const DecBlockSaved& b,
+                  const float* dfeat, float* dh, float* dh2, float* dgi, float* dgh, float* dc, float* dcol) {
+    int rc;
+    const int PT = P * Tp;
+    k_rows_copy<<<ceil_div(P * 96, 256), 256, 0, st>>>(dfeat + 160, 256, dh, 96, P, 96);
+    LAUNCH_CHECK("k_rows_copy");
+    for (int t = Tp - 1; t >= 0; --t) {
+        float* dght = dgh + (size_t)t * P * 288;
+        k_gru_step_bwd<<<ceil_div(P * 96, 256), 256, 0, st>>>(dh, b.rzn + (size_t)t * P * 288, b.ghn + (size_t)t * P * 96, b.h + (size_t)t * P * 96, P,
+                                                              dgi + (size_t)t * 288, (long)Tp * 288, dght, dh2);
+        LAUNCH_CHECK("k_gru_step_bwd");
+        if ((rc = gemm_nn(st, P, 96, 288, dght, 288, w.gru_w_hh, dh2, 96, nullptr, 0, nullptr, 0, 1))) return rc;      // += d gh W_hh
+        std::swap(dh, dh2);
+    }
+    // h_0 .. h_{T-1} and d gh_0 .. d gh_{T-1} are contiguous [T*P, .] stacks: one product for the recurrent weight
+    if ((rc = weight_grad(st, Tp * P, 288, 96, dgh, 288, b.h, 96, g.gru_w_hh, g.gru_b_hh))) return rc;
+    if ((rc = weight_grad(st, PT, 288, 32, dgi, 288, b.c, 32, g.gru_w_ih, g.gru_b_ih))) return rc;
+    if ((rc = gemm_nn(st, PT, 32, 288, dgi, 288, w.gru_w_ih, dc, 32, nullptr, 0, b.c, 32))) return rc;                 // * relu'(conv)
+    if ((rc = weight_grad(st, PT, 32, 6, dc, 32, b.col, 6, g.conv_w, g.conv_b))) return rc;
+    if (dcol && (rc = gemm_nn(st, PT, 6, 32, dc, 32, w.conv_w, dcol, 6))) return rc;
+    return 0;
+}
+
+int run_decoder_bwd(const float* pf, const float* z, const float* x_true, const float* d_pred, const float* d_recon, int P,
+                    const sttode_model_weights* w, const sttode_decompose_grads* g, float* d_pf, float* d_z, Carver ws, cudaStream_t st) {
+    int rc;
+    const int Tp = w->past_length, Tf = w->future_length;
+    DecBlockSaved b0{}, b1{};
+    if ((rc = take_block(ws, P, Tp, &b0)) || (rc = take_block(ws, P, Tp, &b1))) return rc;
+    float* gh = ws.take<float>((size_t)P * 288);
+    float* dfeat0 = ws.take<float>((size_t)P * 256);
+    float* dfeat1 = ws.take<float>((size_t)P * 256);
+    float* da1 = ws.take<float>((size_t)P * 512);
+    float* da2 = ws.take<float>((size_t)P * 256);
+    float* dh = ws.take<float>((size_t)P * 96);
+    float* dh2 = ws.take<float>((size_t)P * 96);
+    float* dgi = ws.take<float>((size_t)P * Tp * 288);
+    float* dgh = ws.take<float>((size_t)Tp * P * 288);
+    float* dc = ws.take<float>((size_t)P * Tp * 32);
+    float* dcol = ws.take<float>((size_t)P * Tp * 6);
+    float* dxh0 = ws.take<float>((size_t)P * 2 * Tp);
+    if (!ws.ok() || !dxh0) return fail(STTODE_EWORKSPACE, "workspace too small for the decoder backward (%zu B given)", ws.size);
+    // ---- forward re-materialisation (model/STTODE.py:336-339)
+    if ((rc = dec_block_fwd(st, P, Tp, w->dec[0], pf, z, x_true, nullptr, gh, b0))) return rc;
+    if ((rc = mlp3_fwd(st, P, w->dec[0].dec_x, 2 * Tp, b0.feat, b0.ax1, b0.ax2, b0.xh))) return rc;
+    if ((rc = mlp3_fwd(st, P, w->dec[0].dec_y, 2 * Tf, b0.feat, b0.ay1, b0.ay2, nullptr))) return rc;
+    if ((rc = dec_block_fwd(st, P, Tp, w->dec[1], pf, z, x_true, b0.xh, gh, b1))) return rc;
+    if ((rc = mlp3_fwd(st, P, w->dec[1].dec_y, 2 * Tf, b1.feat, b1.ay1, b1.ay2, nullptr))) return rc;
+    if (d_recon && (rc = mlp3_fwd(st, P, w->dec[1].dec_x, 2 * Tp, b1.feat, b1.ax1, b1.ax2, nullptr))) return rc;
+    // ---- block 1: prediction += y_hat1, reconstruction += x_hat1 (train mode)
+    if ((rc = mlp3_bwd(st, P, w->dec[1].dec_y, g[1].dec_y, 2 * Tf, d_pred, b1.feat, b1.ay1, b1.ay2, da1, da2, dfeat1, 0))) return rc;
+    if (d_recon && (rc = mlp3_bwd(st, P, w->dec[1].dec_x, g[1].dec_x, 2 * Tp, d_recon, b1.feat, b1.ax1, b1.ax2, da1, da2, dfeat1, 1))) return rc;
+    if ((rc = dec_block_bwd(st, P, Tp, w->dec[1], g[1], b1, dfeat1, dh, dh2, dgi, dgh, dc, dcol))) return rc;
+    // block 1 saw x_true - x_hat0: d x_hat0 = d recon - col2im(d col)
+    k_conv_col2im_neg<<<ceil_div(P * Tp * 2, 256), 256, 0, st>>>(dcol, d_recon, P, Tp, dxh0);
+    LAUNCH_CHECK("k_conv_col2im_neg");
+    // ---- block 0
+    if ((rc = mlp3_bwd(st, P, w->dec[0].dec_y, g[0].dec_y, 2 * Tf, d_pred, b0.feat, b0.ay1, b0.ay2, da1, da2, dfeat0, 0))) return rc;
+    if ((rc = mlp3_bwd(st, P, w->dec[0].dec_x, g[0].dec_x, 2 * Tp, dxh0, b0.feat, b0.ax1, b0.ax2, da1, da2, dfeat0, 1))) return rc;
+    if ((rc = dec_block_bwd(st, P, Tp, w->dec[0], g[0], b0, dfeat0, dh, dh2, dgi, dgh, dc, nullptr))) return rc;
+    // ---- hidden = [past_feature | z] feeds both blocks
+    k_rows_add<<<ceil_div(P * 128, 256), 256, 0, st>>>(dfeat0, 256, dfeat1, 256, d_pf, 128, P, 128);
+    LAUNCH_CHECK("k_rows_add");
+    k_rows_add<<<ceil_div(P * 32, 256), 256, 0, st>>>(dfeat0 + 128, 256, dfeat1 + 128, 256, d_z, 32, P, 32);
+    LAUNCH_CHECK("k_rows_add");
+    return 0;
+}
+
 int run_past_encoder(const float* traj, int layout, const int* scene_ptr, const int* row_scene, int n_scenes, int rows, int L,
                      int agents, const sttode_model_weights* w, float* past_feature, float* traj_norm, float* origin, Carver ws,
                      cudaStream_t st) {
@@ -842,6 +983,27 @@ int sttode_decoder_fwd(const float* past_feature, const float* traj_norm, const 
     if (origin && !row_scene) return fail(STTODE_EINVAL, "origin given without row_scene");
     return run_decoder(past_feature, traj_norm, z, seed, row_scene, origin, rows, sample_k, w, pred, recon,
                        Carver(workspace, workspace_bytes), (cudaStream_t)stream);
+}
+
+size_t sttode_decoder_bwd_workspace_bytes(int pairs, int past_length, int future_length) {
+    return dec_bwd_ws_bytes((size_t)(pairs < 1 ? 1 : pairs), past_length, future_length);
+}
+
+int sttode_decoder_bwd(const float* past_feature, const float* z, const float* traj_norm, const float* d_pred, const float* d_recon, int pairs,
+                       const sttode_model_weights* w, const sttode_decompose_grads* grads2, float* d_past_feature, float* d_z, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+    int rc;
+    if ((rc = check_model(w, false, true))) return rc;
+    if (!past_feature || !z || !traj_norm || !d_pred || !grads2 || !d_past_feature || !d_z || pairs < 1) return fail(STTODE_EINVAL, "decoder_bwd: bad argument");
+    for (int b = 0; b < 2; ++b) {
+        const sttode_decompose_grads& g = grads2[b];
+        const float* all[18] = {g.conv_w, g.conv_b, g.gru_w_ih, g.gru_w_hh, g.gru_b_ih, g.gru_b_hh, g.dec_y.w0, g.dec_y.b0, g.dec_y.w1, g.dec_y.b1,
+                                g.dec_y.w2, g.dec_y.b2, g.dec_x.w0, g.dec_x.b0, g.dec_x.w1, g.dec_x.b1, g.dec_x.w2, g.dec_x.b2};
+        for (const float* p : all)
+            if (!p) return fail(STTODE_EINVAL, "decoder_bwd: null gradient buffer in block %d", b);
+    }
+    return run_decoder_bwd(past_feature, z, traj_norm, d_pred, d_recon, pairs, w, grads2, d_past_feature, d_z, Carver(workspace, workspace_bytes),
+                           (cudaStream_t)stream);
 }
 
 size_t sttode_decoder_pack_bytes(int past_length, int future_length) { return (size_t)dec_pack_layout(past_length, future_length).total + 256; }

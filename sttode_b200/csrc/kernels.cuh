@@ -39,6 +39,13 @@ __global__ void k_geo_attn_bwd(const float* qh, int ldq, const float* kh, int ld
                                const float* nk, int ldn, const float* dout, int ldo, float* dq, int lddq, float* dk, int lddk,
                                float* dv, int lddv, int L, int S, int bsz, int swap, float lo, float hi, float qscale);
 size_t geo_attn_bwd_smem_bytes(int L, int S);
+__global__ void k_conv_im2col(const float* x_true, const float* x_hat, int P, int T, float* col);
+__global__ void k_conv_col2im_neg(const float* dcol, const float* base, int P, int T, float* out);
+__global__ void k_gru_step_fwd(const float* gi, long ldgi, const float* gh, const float* h, int P, float* rzn, float* ghn, float* hout);
+__global__ void k_gru_step_bwd(const float* dh, const float* rzn, const float* ghn, const float* hprev, int P, float* dgi, long lddgi, float* dgh,
+                               float* dh_prev);
+__global__ void k_rows_copy(const float* src, long lds, float* dst, long ldd, int rows, int n);
+__global__ void k_rows_add(const float* a, long lda, const float* b, long ldb, float* out, long ldo, int rows, int n);
 
 // decoder.cu
 constexpr int ROWPRE_LD = 2048;     // per-row layer-1 partial sums: [P0x | P0y | P1y | P1x], 512 each

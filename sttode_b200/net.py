@@ -355,20 +355,79 @@ class Decoder(nn.Module):
         return out, recon
 
 
+def _decompose_params(decoder):
+    """The 36 decoder tensors in sttode_decompose_weights order, block 0 then block 1."""
+    ps = []
+    for blk in decoder.decompose:
+        g = blk.encoder_past
+        ps += [blk.conv_past.weight, blk.conv_past.bias, g.weight_ih_l0, g.weight_hh_l0, g.bias_ih_l0, g.bias_hh_l0]
+        for mlp in (blk.decoder_y, blk.decoder_x):
+            for layer in mlp.layers:
+                ps += [layer.weight, layer.bias]
+    return ps
+
+
+def _decompose_struct_from(t18, cls):
+    """sttode_decompose_weights / sttode_decompose_grads over 18 tensors laid out like `_decompose_params`."""
+    s = cls()
+    s.conv_w, s.conv_b, s.gru_w_ih, s.gru_w_hh, s.gru_b_ih, s.gru_b_hh = (_lib.dptr(t) for t in t18[:6])
+    for mlp, off in ((s.dec_y, 6), (s.dec_x, 12)):
+        mlp.w0, mlp.b0, mlp.w1, mlp.b1, mlp.w2, mlp.b2 = (_lib.dptr(t) for t in t18[off:off + 6])
+    return s
+
+
+class _DecoderTrainFn(torch.autograd.Function):
+    """Decoder.forward in train() mode as one autograd node over sttode_decoder_fwd (FP32 kernels, every pair its own row) and
+    sttode_decoder_bwd (Conv1d / GRU-through-time / MLP backward in libsttode_sm100).  past_feature [P,128], z [P,32],
+    traj [P,T_p,2] = x_true per pair -> (out_seq [P,T_f,2] incl. the current position, recover_pre_seq [P,T_p,2])."""
+
+    @staticmethod
+    def forward(ctx, past_feature, z, traj, Tp, Tf, *params):
+        pf, zz, tj = _f32c(past_feature, "past_feature"), _f32c(z, "z"), _f32c(traj, "past_traj")
+        params = [_f32c(p, "parameter") for p in params]
+        P = pf.shape[0]
+        mw = _lib.ModelWeights()
+        mw.past_length, mw.future_length = Tp, Tf
+        mw.dec[0], mw.dec[1] = _decompose_struct_from(params[:18], _lib.DecomposeWeights), _decompose_struct_from(params[18:], _lib.DecomposeWeights)
+        pred = torch.empty(P, 1, Tf, 2, device=pf.device, dtype=torch.float32)
+        recon = torch.empty(P, Tp, 2, device=pf.device, dtype=torch.float32)
+        lib = _lib.lib()
+        ws = _lib.workspace(lib.sttode_decoder_workspace_bytes(P, 1), pf.device)
+        _lib.check(lib.sttode_decoder_fwd(_lib.dptr(pf), _lib.dptr(tj), _lib.dptr(zz), 0, None, None, P, 1, C.byref(mw), _lib.dptr(pred),
+                                          _lib.dptr(recon), _lib.dptr(ws), ws.numel(), _lib.stream_ptr()))
+        ctx.save_for_backward(pf, zz, tj, *params)
+        ctx.shape = (Tp, Tf)
+        return pred.view(P, Tf, 2), recon
+
+    @staticmethod
+    def backward(ctx, d_pred, d_recon):
+        pf, zz, tj, *params = ctx.saved_tensors
+        Tp, Tf = ctx.shape
+        P = pf.shape[0]
+        d_pred = _f32c(d_pred, "grad_output")
+        d_recon = None if d_recon is None else _f32c(d_recon, "grad_output")
+        mw = _lib.ModelWeights()
+        mw.past_length, mw.future_length = Tp, Tf
+        mw.dec[0], mw.dec[1] = _decompose_struct_from(params[:18], _lib.DecomposeWeights), _decompose_struct_from(params[18:], _lib.DecomposeWeights)
+        grads = [torch.zeros_like(p) for p in params]                                  # the library accumulates (+=)
+        gs = (_lib.DecomposeGrads * 2)(_decompose_struct_from(grads[:18], _lib.DecomposeGrads), _decompose_struct_from(grads[18:], _lib.DecomposeGrads))
+        d_pf, d_z = torch.empty_like(pf), torch.empty_like(zz)
+        lib = _lib.lib()
+        ws = _lib.workspace(lib.sttode_decoder_bwd_workspace_bytes(P, Tp, Tf), pf.device)
+        _lib.check(lib.sttode_decoder_bwd(_lib.dptr(pf), _lib.dptr(zz), _lib.dptr(tj), _lib.dptr(d_pred), _lib.dptr(d_recon), P, C.byref(mw), gs,
+                                          _lib.dptr(d_pf), _lib.dptr(d_z), _lib.dptr(ws), ws.numel(), _lib.stream_ptr()))
+        return (d_pf, d_z, None, None, None, *grads)
+
+
 def _decoder_forward_train(self, past_feature, z, past_traj, cur_location, sample_num, mode):
-    """train() mode: the reference's op sequence (model/STTODE.py:320-347) with autograd history."""
+    """train() mode (model/STTODE.py:320-347) with autograd history: forward and backward both run in libsttode_sm100."""
     if not past_feature.is_cuda:
         raise _lib.SttodeError("Decoder inputs must be CUDA tensors; this path has no CPU implementation")
-    x_true = past_traj.repeat_interleave(sample_num, dim=0)
-    hidden = torch.cat((past_feature.view(-1, sample_num, past_feature.shape[-1]), z.view(-1, sample_num, z.shape[-1])), dim=-1)
-    hidden = hidden.view(x_true.shape[0], -1)
-    x_hat = torch.zeros_like(x_true)
-    pred, rec = 0, 0
-    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):       # fp32 Conv1d: TF32 would break the 1e-4 budget
-        for blk in self.decompose:
-            x_hat, y_hat = blk(x_true, x_hat, hidden)
-            pred, rec = pred + y_hat, rec + x_hat
-    out = pred + cur_location.repeat_interleave(sample_num, dim=0)
+    if not torch.equal(cur_location.reshape(-1, 2), past_traj[:, -1].reshape(-1, 2)):
+        raise NotImplementedError("Decoder on B200: cur_location must be past_traj[:, -1] (as at every reference call site)")
+    x_true = past_traj.detach().repeat_interleave(sample_num, dim=0)
+    pf = past_feature.reshape(x_true.shape[0], -1)
+    out, rec = _DecoderTrainFn.apply(pf, z.reshape(-1, 32), x_true, self.past_length, self.future_length, *_decompose_params(self))
     if mode == "inference":
         out = out.view(-1, sample_num, *out.shape[1:])
     return out, rec

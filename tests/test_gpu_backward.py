@@ -257,3 +257,47 @@ def test_ode_block_backward_vs_reference_golden(model, dev, golden, name):
     assert rel(x.grad, gb[f"ode_{name}_dx"]) < TOL
     for pname, p in enc.named_parameters():
         assert rel(p.grad, gb[f"ode_{name}_g_{pname}"]) < TOL, pname
+
+
+# ------------------------------------------------------------------ decoder (Conv1d + GRU through time + MLPs)
+@pytest.mark.parametrize("tp,tf,R,K,with_recon", [(8, 12, 7, 1, True), (10, 20, 6, 20, False), (5, 10, 3, 4, True)])
+def test_decoder_backward_vs_torch_autograd(dev, tp, tf, R, K, with_recon):
+    """sttode_decoder_bwd (through the train()-mode Decoder) against torch autograd over the same blocks written with torch ops
+    (DecomposeBlock.forward: F.conv1d, an unrolled fp32 GRU, nn.Linear), in float64 on the CPU."""
+    from oracle.ref_shim import make_args
+    from sttode_b200.net import Decoder
+    torch.manual_seed(11)
+    dec = Decoder(make_args("nba", tp, tf)).to(dev).train()
+    g = torch.Generator().manual_seed(12)
+    P = R * K
+    pf, z = torch.randn(R, 128, generator=g), torch.randn(P, 32, generator=g)
+    traj = torch.cumsum(torch.randn(R, tp, 2, generator=g) * 0.3, dim=1)
+    d_out, d_rec = torch.randn(P, tf, 2, generator=g), torch.randn(P, tp, 2, generator=g)
+    # float64 CPU reference: the same module's torch-op blocks
+    ref = Decoder(make_args("nba", tp, tf)).double()
+    ref.load_state_dict({k: v.detach().cpu().double() for k, v in dec.state_dict().items()})
+    pf64, z64 = pf.double().requires_grad_(True), z.double().requires_grad_(True)
+    x_true = traj.double().repeat_interleave(K, dim=0)
+    hidden = torch.cat((pf64.repeat_interleave(K, dim=0), z64), dim=-1)
+    x_hat, pred, rec = torch.zeros_like(x_true), 0, 0
+    for blk in ref.decompose:
+        x_hat, y_hat = blk(x_true, x_hat, hidden)
+        pred, rec = pred + y_hat, rec + x_hat
+    out64 = pred + x_true[:, [-1]]
+    loss64 = (out64 * d_out.double()).sum() + ((rec * d_rec.double()).sum() if with_recon else 0)
+    loss64.backward()
+    # CUDA
+    pfd, zd = pf.to(dev).requires_grad_(True), z.to(dev).requires_grad_(True)
+    trajd = traj.to(dev)
+    out, rec_d = dec(pfd.repeat_interleave(K, dim=0), zd, 1, R, trajd, trajd[:, [-1]], sample_num=K, mode="inference" if K > 1 else "train")
+    assert rel(out.reshape(P, tf, 2), out64) < TOL and rel(rec_d, rec) < TOL
+    loss = (out.reshape(P, tf, 2) * d_out.to(dev)).sum() + ((rec_d * d_rec.to(dev)).sum() if with_recon else 0)
+    loss.backward()
+    assert rel(pfd.grad, pf64.grad) < TOL and rel(zd.grad, z64.grad) < TOL
+    refp = dict(ref.named_parameters())
+    for n, p in dec.named_parameters():
+        if refp[n].grad is None:                      # block-1 decoder_x without the reconstruction: no gradient on either side
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, n
+            continue
+        e = rel(p.grad, refp[n].grad)
+        assert e < TOL, (n, e)
