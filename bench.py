@@ -424,7 +424,7 @@ def run_train(args):
                           "config": {"workload": "STTODE training step (BASELINE.json configs[4]), NBA shape obs 10 / pred 20", "batch_per_gpu": B,
                                      "agents": N, "parallelism": f"dp{world}: one all-reduce of {reducer.nbytes} B per step (pz_layer excluded)"},
                           "gpu_launches": int(L.launch_count() - l0), "last_loss": float(out[0].detach()),
-                          "note": "MHGSA / tensor-ODE forward+backward in libsttode_sm100; thin front end and decoder run as torch ops in train() mode"}), flush=True)
+                          "note": "every layer forward+backward in libsttode_sm100 (ODE blocks, dense layers, decoder incl. GRU through time); torch: autograd bookkeeping, losses, Adam"}), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -220,6 +220,15 @@ int sttode_decoder_fwd(const float *past_feature, const float *traj_norm, const 
                        const sttode_model_weights *w, float *pred, float *recon, void *workspace,
                        size_t workspace_bytes, void *stream);
 
+/* ---- generic dense layer with its backward: the thin layers around the tensor-ODE block in train() mode (input_fc 4->64, PE fc 128->64,
+ * input_fc2 64T->64, input_fc3 67->64: model/STTODE.py:214-223; FutureEncoder head 256->128->64: :297-300).  Any K, N; x rows have stride ldx.
+ *   fwd: y[rows,N] = act(x[rows,K] . W[N,K]^T + b)          (relu != 0 -> ReLU)
+ *   bwd: dx[rows,K] = dy . W (dx nullable, row stride lddx);  dW[N,K] += dy^T . x;  db[N] += column sums of dy   (dW / db nullable).
+ * The caller masks dy with the ReLU derivative beforehand when the forward used one.  Deterministic summation order. */
+int sttode_dense_fwd(const float *x, int ldx, const float *weight, const float *bias, float *y, int rows, int K, int N, int relu, void *stream);
+int sttode_dense_bwd(const float *x, int ldx, const float *weight, const float *dy, float *dx, int lddx, float *dweight, float *dbias, int rows,
+                     int K, int N, void *stream);
+
 /* ---- backward of Decoder.forward in 'train' mode (model/STTODE.py:320-347, both DecomposeBlocks :51-77); the reference gets it from
  * torch autograd (train.py:65).  One row per (agent, sample) pair: past_feature [pairs,128], z [pairs,32], traj_norm [pairs,T_p,2] (x_true,
  * already repeated per sample), d_pred [pairs,T_f,2] = gradient of out_seq, d_recon [pairs,T_p,2] = gradient of recover_pre_seq (NULL when

@@ -91,6 +91,8 @@ SIGNATURES = {
     "sttode_linear": (_I, [_V, _V, _V, _V, _I, _I, _I, _I, _V]),
     "sttode_decoder_workspace_bytes": (_Z, [_I, _I]),
     "sttode_decoder_fwd": (_I, [_V, _V, _V, _U64, _V, _V, _I, _I, C.POINTER(ModelWeights), _V, _V, _V, _Z, _V]),
+    "sttode_dense_fwd": (_I, [_V, _I, _V, _V, _V, _I, _I, _I, _I, _V]),
+    "sttode_dense_bwd": (_I, [_V, _I, _V, _V, _V, _I, _V, _V, _I, _I, _I, _V]),
     "sttode_decoder_bwd_workspace_bytes": (_Z, [_I, _I, _I]),
     "sttode_decoder_bwd": (_I, [_V, _V, _V, _V, _V, _I, C.POINTER(ModelWeights), C.POINTER(DecomposeGrads), _V, _V, _V, _Z, _V]),
     "sttode_decoder_pack_bytes": (_Z, [_I, _I]),

@@ -26,7 +26,7 @@ constexpr int GT = 64, GK = 16;
 __global__ void __launch_bounds__(256)
 k_gemm(int M, int N, int K, const float* __restrict__ A, long sam, long sak, const float* __restrict__ B, long sbk, long sbn,
        float* __restrict__ C, long ldc, const float* __restrict__ bias, const float* __restrict__ res, long ldres,
-       const float* __restrict__ mask, long ldmask, int relu, int accumulate) {
+       const float* __restrict__ mask, long ldmask, int relu, int accumulate, int kchunk, long slice_stride) {
     __shared__ float As[GK][GT + 4];
     __shared__ float Bs[GK][GT + 4];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -37,7 +37,11 @@ k_gemm(int M, int N, int K, const float* __restrict__ A, long sam, long sak, con
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     const bool a_kfast = sak == 1, b_nfast = sbn == 1;
-    for (int k0 = 0; k0 < K; k0 += GK) {
+    // split-K: slice blockIdx.z owns k in [z * kchunk, (z+1) * kchunk) and writes its partial product to C + z * slice_stride
+    const int kbeg = blockIdx.z * kchunk;
+    K = min(K, kbeg + kchunk);
+    C += (size_t)blockIdx.z * slice_stride;
+    for (int k0 = kbeg; k0 < K; k0 += GK) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int idx = tid + e * 256;
@@ -79,6 +83,43 @@ k_gemm(int M, int N, int K, const float* __restrict__ A, long sam, long sak, con
             if (accumulate) v += C[(long)m * ldc + n];
             C[(long)m * ldc + n] = v;
         }
+    }
+}
+
+// out[i] += sum_s part[s * stride + i], s ascending (fixed order: the split-K weight gradients stay deterministic)
+__global__ void k_sum_slices(const float* __restrict__ part, int slices, long stride, long count, float* __restrict__ out) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    float s = 0.f;
+    for (int z = 0; z < slices; ++z) s += part[(long)z * stride + i];
+    out[i] += s;
+}
+
+// part[z * N + n] = sum over rows [z * rchunk, (z+1) * rchunk) of X[r, n]   (tall inputs: many CTAs, summed later in slice order)
+__global__ void __launch_bounds__(256)
+k_colsum_part(const float* __restrict__ X, long ldx, int rows, int N, int rchunk, float* __restrict__ part) {
+    __shared__ float sh[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + tx;
+    const int r0 = blockIdx.y * rchunk, r1 = min(rows, r0 + rchunk);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (n < N) {
+        int r = r0 + ty;
+        for (; r + 24 < r1; r += 32) {              // four independent loads in flight per thread
+            s0 += X[(long)r * ldx + n];
+            s1 += X[(long)(r + 8) * ldx + n];
+            s2 += X[(long)(r + 16) * ldx + n];
+            s3 += X[(long)(r + 24) * ldx + n];
+        }
+        for (; r < r1; r += 8) s0 += X[(long)r * ldx + n];
+    }
+    sh[ty][tx] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (ty == 0 && n < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sh[k][tx];
+        part[(long)blockIdx.y * N + n] = t;
     }
 }
 

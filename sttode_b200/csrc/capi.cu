@@ -237,10 +237,13 @@ int gemm(cudaStream_t st, int M, int N, int K, const float* A, long sam, long sa
          const float* bias = nullptr, const float* res = nullptr, long ldres = 0, const float* mask = nullptr, long ldmask = 0,
          int relu = 0, int accumulate = 0) {
     k_gemm<<<dim3(ceil_div(N, 64), ceil_div(M, 64)), 256, 0, st>>>(M, N, K, A, sam, sak, B, sbk, sbn, C, ldc, bias, res, ldres, mask, ldmask,
-                                                                  relu, accumulate);
+                                                                  relu, accumulate, K, 0);
     LAUNCH_CHECK("k_gemm");
     return 0;
 }
+// Scratch for split-K weight gradients (tall products: few output tiles, thousands of rows): SPLITK_MAX slices of the largest dW.
+constexpr int SPLITK_MAX = 64;
+constexpr size_t SPLITK_FLOATS = (size_t)SPLITK_MAX * 512 * 256;
 // y[rows,N] = x[rows,K] . W[N,K]^T + b
 int gemm_nt(cudaStream_t st, int rows, int N, int K, const float* x, long ldx, const float* W, const float* b, float* y, long ldy,
             int relu = 0, const float* res = nullptr, long ldres = 0) {
@@ -252,10 +255,28 @@ int gemm_nn(cudaStream_t st, int rows, int K, int N, const float* dy, long lddy,
     return gemm(st, rows, K, N, dy, lddy, 1, W, K, 1, dx, lddx, nullptr, res, ldres, mask, ldmask, 0, accumulate);
 }
 // dW[N,K] += dy[rows,N]^T . x[rows,K];  db[N] += column sums of dy   (either may be null)
-int weight_grad(cudaStream_t st, int rows, int N, int K, const float* dy, long lddy, const float* x, long ldx, float* dW, float* db) {
+int weight_grad(cudaStream_t st, int rows, int N, int K, const float* dy, long lddy, const float* x, long ldx, float* dW, float* db,
+                float* splitk = nullptr) {
     int rc;
-    if (dW && (rc = gemm(st, N, K, rows, dy, 1, lddy, x, ldx, 1, dW, K, nullptr, nullptr, 0, nullptr, 0, 0, 1))) return rc;
-    if (db) {
+    const int tiles = ceil_div(N, 64) * ceil_div(K, 64);
+    if (dW && splitk && rows >= 2048 && tiles < 296 && (size_t)N * K <= 512 * 256) {
+        // rows split over gridDim.z so the launch fills the GPU; partial products summed in slice order (deterministic)
+        const int slices = std::min(SPLITK_MAX, std::min(ceil_div(rows, 256), ceil_div(592, tiles)));
+        const int kchunk = ceil_div(ceil_div(rows, slices), 16) * 16;
+        const int nz = ceil_div(rows, kchunk);
+        k_gemm<<<dim3(ceil_div(K, 64), ceil_div(N, 64), nz), 256, 0, st>>>(N, K, rows, dy, 1, lddy, x, ldx, 1, splitk, K, nullptr, nullptr, 0, nullptr, 0,
+                                                                          0, 0, kchunk, (long)N * K);
+        LAUNCH_CHECK("k_gemm(split-K)");
+        k_sum_slices<<<ceil_div(N * K, 256), 256, 0, st>>>(splitk, nz, (long)N * K, (long)N * K, dW);
+        LAUNCH_CHECK("k_sum_slices");
+    } else if (dW && (rc = gemm(st, N, K, rows, dy, 1, lddy, x, ldx, 1, dW, K, nullptr, nullptr, 0, nullptr, 0, 0, 1))) return rc;
+    if (db && splitk && rows >= 2048) {
+        const int nz = std::min(SPLITK_MAX * 4, ceil_div(rows, 256)), rchunk = ceil_div(rows, nz);
+        k_colsum_part<<<dim3(ceil_div(N, 32), ceil_div(rows, rchunk)), 256, 0, st>>>(dy, lddy, rows, N, rchunk, splitk);
+        LAUNCH_CHECK("k_colsum_part");
+        k_sum_slices<<<ceil_div(N, 256), 256, 0, st>>>(splitk, ceil_div(rows, rchunk), (long)N, (long)N, db);
+        LAUNCH_CHECK("k_sum_slices");
+    } else if (db) {
         k_colsum<<<ceil_div(N, 32), 256, 0, st>>>(dy, lddy, rows, N, db);
         LAUNCH_CHECK("k_colsum");
     }
@@ -474,6 +495,7 @@ size_t dec_bwd_ws_bytes(size_t P, int Tp, int Tf) {
     f += P * 288;                                                                   // gh scratch
     f += 2 * P * 256 + P * (512 + 256) + 2 * P * 96;                                // dfeat x 2, da1, da2, dh ping-pong
     f += P * Tp * 288 + (size_t)Tp * P * 288 + P * Tp * (32 + 6) + P * 2 * tmax;    // dgi, dgh, dc, dcol, dxh
+    f += SPLITK_FLOATS;                                                             // split-K partial weight gradients
     return f * 4 + 64 * 256;                                                        // + alignment slack of the carver
 }
 
@@ -497,13 +519,13 @@ int mlp3_fwd(cudaStream_t st, int P, const sttode_mlp3_weights& w, int n3, const
 }
 // dfeat (+)= J^T dout through the 3-layer MLP; parameter gradients accumulated into g
 int mlp3_bwd(cudaStream_t st, int P, const sttode_mlp3_weights& w, const sttode_mlp3_grads& g, int n3, const float* dout, const float* feat,
-             const float* a1, const float* a2, float* da1, float* da2, float* dfeat, int accumulate) {
+             const float* a1, const float* a2, float* da1, float* da2, float* dfeat, int accumulate, float* splitk) {
     int rc;
-    if ((rc = weight_grad(st, P, n3, 256, dout, n3, a2, 256, g.w2, g.b2))) return rc;
+    if ((rc = weight_grad(st, P, n3, 256, dout, n3, a2, 256, g.w2, g.b2, splitk))) return rc;
     if ((rc = gemm_nn(st, P, 256, n3, dout, n3, w.w2, da2, 256, nullptr, 0, a2, 256))) return rc;           // * relu'
-    if ((rc = weight_grad(st, P, 256, 512, da2, 256, a1, 512, g.w1, g.b1))) return rc;
+    if ((rc = weight_grad(st, P, 256, 512, da2, 256, a1, 512, g.w1, g.b1, splitk))) return rc;
     if ((rc = gemm_nn(st, P, 512, 256, da2, 256, w.w1, da1, 512, nullptr, 0, a1, 512))) return rc;
-    if ((rc = weight_grad(st, P, 512, 256, da1, 512, feat, 256, g.w0, g.b0))) return rc;
+    if ((rc = weight_grad(st, P, 512, 256, da1, 512, feat, 256, g.w0, g.b0, splitk))) return rc;
     return gemm_nn(st, P, 256, 512, da1, 512, w.w0, dfeat, 256, nullptr, 0, nullptr, 0, accumulate);
 }
 
@@ -535,7 +557,7 @@ int dec_block_fwd(cudaStream_t st, int P, int Tp, const sttode_decompose_weights
 
 // BPTT through the GRU and the conv of one block, starting from dfeat[:, 160:256] = d h_T.  dcol (nullable) receives d im2col(x).
 int dec_block_bwd(cudaStream_t st, int P, int Tp, const sttode_decompose_weights& w, const sttode_decompose_grads& g, const DecBlockSaved& b,
-                  const float* dfeat, float* dh, float* dh2, float* dgi, float* dgh, float* dc, float* dcol) {
+                  const float* dfeat, float* dh, float* dh2, float* dgi, float* dgh, float* dc, float* dcol, float* splitk) {
     int rc;
     const int PT = P * Tp;
     k_rows_copy<<<ceil_div(P * 96, 256), 256, 0, st>>>(dfeat + 160, 256, dh, 96, P, 96);
@@ -549,10 +571,10 @@ int dec_block_bwd(cudaStream_t st, int P, int Tp, const sttode_decompose_weights
         std::swap(dh, dh2);
     }
     // h_0 .. h_{T-1} and d gh_0 .. d gh_{T-1} are contiguous [T*P, .] stacks: one product for the recurrent weight
-    if ((rc = weight_grad(st, Tp * P, 288, 96, dgh, 288, b.h, 96, g.gru_w_hh, g.gru_b_hh))) return rc;
-    if ((rc = weight_grad(st, PT, 288, 32, dgi, 288, b.c, 32, g.gru_w_ih, g.gru_b_ih))) return rc;
+    if ((rc = weight_grad(st, Tp * P, 288, 96, dgh, 288, b.h, 96, g.gru_w_hh, g.gru_b_hh, splitk))) return rc;
+    if ((rc = weight_grad(st, PT, 288, 32, dgi, 288, b.c, 32, g.gru_w_ih, g.gru_b_ih, splitk))) return rc;
     if ((rc = gemm_nn(st, PT, 32, 288, dgi, 288, w.gru_w_ih, dc, 32, nullptr, 0, b.c, 32))) return rc;                 // * relu'(conv)
-    if ((rc = weight_grad(st, PT, 32, 6, dc, 32, b.col, 6, g.conv_w, g.conv_b))) return rc;
+    if ((rc = weight_grad(st, PT, 32, 6, dc, 32, b.col, 6, g.conv_w, g.conv_b, splitk))) return rc;
     if (dcol && (rc = gemm_nn(st, PT, 6, 32, dc, 32, w.conv_w, dcol, 6))) return rc;
     return 0;
 }
@@ -575,7 +597,8 @@ int run_decoder_bwd(const float* pf, const float* z, const float* x_true, const 
     float* dc = ws.take<float>((size_t)P * Tp * 32);
     float* dcol = ws.take<float>((size_t)P * Tp * 6);
     float* dxh0 = ws.take<float>((size_t)P * 2 * Tp);
-    if (!ws.ok() || !dxh0) return fail(STTODE_EWORKSPACE, "workspace too small for the decoder backward (%zu B given)", ws.size);
+    float* splitk = ws.take<float>(SPLITK_FLOATS);
+    if (!ws.ok() || !dxh0 || !splitk) return fail(STTODE_EWORKSPACE, "workspace too small for the decoder backward (%zu B given)", ws.size);
     // ---- forward re-materialisation (model/STTODE.py:336-339)
     if ((rc = dec_block_fwd(st, P, Tp, w->dec[0], pf, z, x_true, nullptr, gh, b0))) return rc;
     if ((rc = mlp3_fwd(st, P, w->dec[0].dec_x, 2 * Tp, b0.feat, b0.ax1, b0.ax2, b0.xh))) return rc;
@@ -584,16 +607,16 @@ int run_decoder_bwd(const float* pf, const float* z, const float* x_true, const 
     if ((rc = mlp3_fwd(st, P, w->dec[1].dec_y, 2 * Tf, b1.feat, b1.ay1, b1.ay2, nullptr))) return rc;
     if (d_recon && (rc = mlp3_fwd(st, P, w->dec[1].dec_x, 2 * Tp, b1.feat, b1.ax1, b1.ax2, nullptr))) return rc;
     // ---- block 1: prediction += y_hat1, reconstruction += x_hat1 (train mode)
-    if ((rc = mlp3_bwd(st, P, w->dec[1].dec_y, g[1].dec_y, 2 * Tf, d_pred, b1.feat, b1.ay1, b1.ay2, da1, da2, dfeat1, 0))) return rc;
-    if (d_recon && (rc = mlp3_bwd(st, P, w->dec[1].dec_x, g[1].dec_x, 2 * Tp, d_recon, b1.feat, b1.ax1, b1.ax2, da1, da2, dfeat1, 1))) return rc;
-    if ((rc = dec_block_bwd(st, P, Tp, w->dec[1], g[1], b1, dfeat1, dh, dh2, dgi, dgh, dc, dcol))) return rc;
+    if ((rc = mlp3_bwd(st, P, w->dec[1].dec_y, g[1].dec_y, 2 * Tf, d_pred, b1.feat, b1.ay1, b1.ay2, da1, da2, dfeat1, 0, splitk))) return rc;
+    if (d_recon && (rc = mlp3_bwd(st, P, w->dec[1].dec_x, g[1].dec_x, 2 * Tp, d_recon, b1.feat, b1.ax1, b1.ax2, da1, da2, dfeat1, 1, splitk))) return rc;
+    if ((rc = dec_block_bwd(st, P, Tp, w->dec[1], g[1], b1, dfeat1, dh, dh2, dgi, dgh, dc, dcol, splitk))) return rc;
     // block 1 saw x_true - x_hat0: d x_hat0 = d recon - col2im(d col)
     k_conv_col2im_neg<<<ceil_div(P * Tp * 2, 256), 256, 0, st>>>(dcol, d_recon, P, Tp, dxh0);
     LAUNCH_CHECK("k_conv_col2im_neg");
     // ---- block 0
-    if ((rc = mlp3_bwd(st, P, w->dec[0].dec_y, g[0].dec_y, 2 * Tf, d_pred, b0.feat, b0.ay1, b0.ay2, da1, da2, dfeat0, 0))) return rc;
-    if ((rc = mlp3_bwd(st, P, w->dec[0].dec_x, g[0].dec_x, 2 * Tp, dxh0, b0.feat, b0.ax1, b0.ax2, da1, da2, dfeat0, 1))) return rc;
-    if ((rc = dec_block_bwd(st, P, Tp, w->dec[0], g[0], b0, dfeat0, dh, dh2, dgi, dgh, dc, nullptr))) return rc;
+    if ((rc = mlp3_bwd(st, P, w->dec[0].dec_y, g[0].dec_y, 2 * Tf, d_pred, b0.feat, b0.ay1, b0.ay2, da1, da2, dfeat0, 0, splitk))) return rc;
+    if ((rc = mlp3_bwd(st, P, w->dec[0].dec_x, g[0].dec_x, 2 * Tp, dxh0, b0.feat, b0.ax1, b0.ax2, da1, da2, dfeat0, 1, splitk))) return rc;
+    if ((rc = dec_block_bwd(st, P, Tp, w->dec[0], g[0], b0, dfeat0, dh, dh2, dgi, dgh, dc, nullptr, splitk))) return rc;
     // ---- hidden = [past_feature | z] feeds both blocks
     k_rows_add<<<ceil_div(P * 128, 256), 256, 0, st>>>(dfeat0, 256, dfeat1, 256, d_pf, 128, P, 128);
     LAUNCH_CHECK("k_rows_add");
@@ -983,6 +1006,21 @@ int sttode_decoder_fwd(const float* past_feature, const float* traj_norm, const 
     if (origin && !row_scene) return fail(STTODE_EINVAL, "origin given without row_scene");
     return run_decoder(past_feature, traj_norm, z, seed, row_scene, origin, rows, sample_k, w, pred, recon,
                        Carver(workspace, workspace_bytes), (cudaStream_t)stream);
+}
+
+int sttode_dense_fwd(const float* x, int ldx, const float* weight, const float* bias, float* y, int rows, int K, int N, int relu, void* stream) {
+    if (!x || !weight || !y || rows < 1 || K < 1 || N < 1 || ldx < K) return fail(STTODE_EINVAL, "dense_fwd: bad argument");
+    return gemm_nt((cudaStream_t)stream, rows, N, K, x, ldx, weight, bias, y, N, relu ? 1 : 0);
+}
+
+int sttode_dense_bwd(const float* x, int ldx, const float* weight, const float* dy, float* dx, int lddx, float* dweight, float* dbias, int rows, int K,
+                     int N, void* stream) {
+    int rc;
+    if (!x || !weight || !dy || rows < 1 || K < 1 || N < 1 || ldx < K || (dx && lddx < K)) return fail(STTODE_EINVAL, "dense_bwd: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = weight_grad(st, rows, N, K, dy, N, x, ldx, dweight, dbias))) return rc;
+    if (dx && (rc = gemm_nn(st, rows, K, N, dy, N, weight, dx, lddx))) return rc;
+    return 0;
 }
 
 size_t sttode_decoder_bwd_workspace_bytes(int pairs, int past_length, int future_length) {

@@ -8,11 +8,11 @@ features, past encoder (front end + tensor-ODE block with MHGSA), K-sample decod
 run inside libsttode_sm100.so.  `forecast_scenes` is the batched form (many ETH/SDD scenes per launch) the
 reference does not have.
 
-Training (`train()` mode; train.py:55-95): `forward()` returns the reference's loss tuple with autograd history.  The
-MHGSA / tensor-ODE blocks of both encoders run forward and backward in libsttode_sm100 (autograd nodes over
-sttode_ode_block_fwd / _bwd); the thin layers around them and the decoder are torch ops in train() mode so that autograd
-reaches their parameters (their fused inference kernels are the eval() path).  `eval()` + `forward()` evaluates the same
-objective forward-only, entirely in the library.
+Training (`train()` mode; train.py:55-95): `forward()` returns the reference's loss tuple with autograd history.  Every layer of
+the step runs forward and backward in libsttode_sm100 behind autograd nodes: the MHGSA / tensor-ODE blocks of both encoders
+(sttode_ode_block_fwd / _bwd), the thin Linear layers around them (sttode_dense_fwd / _bwd) and the whole decoder
+(sttode_decoder_fwd / _bwd: Conv1d, GRU through time, MLPs).  torch supplies the graph bookkeeping, concatenations, the
+Bernoulli / Gaussian draws and the scalar loss arithmetic.  `eval()` + `forward()` evaluates the same objective forward-only.
 """
 import ctypes as C
 import math
@@ -171,27 +171,59 @@ def _encoder_forward(enc, inputs, batch_size, agent_num):
     return out
 
 
+class _DenseFn(torch.autograd.Function):
+    """y = act(x W^T + b) with its backward, both in libsttode_sm100 (sttode_dense_fwd / sttode_dense_bwd): the train()-mode form of the
+    thin Linear layers around the tensor-ODE block.  x [..., K] (any leading shape), W [N, K], b [N]."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        if not x.is_cuda:
+            raise _lib.SttodeError("dense layer input must be a CUDA tensor; this path has no CPU implementation")
+        xs = _f32c(x, "x").reshape(-1, x.shape[-1])
+        w, b = _f32c(weight, "weight"), _f32c(bias, "bias")
+        rows, K, N = xs.shape[0], xs.shape[1], w.shape[0]
+        y = torch.empty(rows, N, device=xs.device, dtype=torch.float32)
+        _lib.check(_lib.lib().sttode_dense_fwd(_lib.dptr(xs), K, _lib.dptr(w), _lib.dptr(b), _lib.dptr(y), rows, K, N, int(relu), _lib.stream_ptr()))
+        ctx.save_for_backward(xs, w, y if relu else None)
+        ctx.meta = (x.shape, bool(relu), ctx.needs_input_grad[0])
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xs, w, y = ctx.saved_tensors
+        shape, relu, need_dx = ctx.meta
+        rows, K, N = xs.shape[0], xs.shape[1], w.shape[0]
+        dy = dy.reshape(rows, N)
+        dy = (dy * (y > 0)).contiguous() if relu else _f32c(dy, "grad_output")
+        dx = torch.empty_like(xs) if need_dx else None
+        dw, db = torch.zeros_like(w), torch.zeros(N, device=w.device, dtype=torch.float32)          # the library accumulates (+=)
+        _lib.check(_lib.lib().sttode_dense_bwd(_lib.dptr(xs), K, _lib.dptr(w), _lib.dptr(dy), _lib.dptr(dx), K, _lib.dptr(dw), _lib.dptr(db), rows, K, N,
+                                               _lib.stream_ptr()))
+        return (dx.view(shape) if need_dx else None), dw, db, None
+
+
+def _dense(x, layer, relu=False):
+    return _DenseFn.apply(x, layer.weight, layer.bias, relu)
+
+
 def _encoder_forward_train(enc, inputs, batch_size, agent_num):
-    """train() mode (model/STTODE.py:214-236 with the PE dropout of :140,176 live).  The MHGSA / tensor-ODE block — the
-    path this library exists for — runs forward AND backward in libsttode_sm100 (one autograd node, sttode_ode_block_fwd/_bwd).
-    The thin front end around it (input_fc, PE fc, dropout, flatten fc, category fc; 2 % of the step) is expressed with
-    torch ops so autograd can reach its parameters; its fused forward kernel (k_prologue) is the eval() path.
-    `enc.dropout_mask_override` ([R,T,64] of 0/1) replaces the Bernoulli draw (tests)."""
+    """train() mode (model/STTODE.py:214-236 with the PE dropout of :140,176 live).  Every layer runs forward AND backward in
+    libsttode_sm100: the thin Linear layers as `_DenseFn` nodes (sttode_dense_fwd / _bwd), the MHGSA / tensor-ODE block as one node
+    (sttode_ode_block_fwd / _bwd).  torch only concatenates, reshapes and applies the Bernoulli mask.
+    `enc.dropout_mask_override` ([R,T,64] of 0/1) replaces the draw (tests)."""
     rows, T = inputs.shape[0], inputs.shape[1]
     if inputs.shape[-1] != 4 or rows != batch_size * agent_num:
         raise _lib.SttodeError("encoder inputs must be [batch_size*agent_num, T, 4]")
-    if not inputs.is_cuda:
-        raise _lib.SttodeError("encoder inputs must be CUDA tensors; this path has no CPU implementation")
-    h = F.linear(inputs, enc.input_fc.weight, enc.input_fc.bias)
+    h = _dense(inputs, enc.input_fc)
     pe = enc.pos_encoder.pe[:T].unsqueeze(0).expand(rows, T, 64)
-    h = F.linear(torch.cat((h, pe), dim=-1), enc.pos_encoder.fc.weight, enc.pos_encoder.fc.bias)
+    h = _dense(torch.cat((h, pe), dim=-1), enc.pos_encoder.fc)
     mask = getattr(enc, "dropout_mask_override", None)
     p = enc.pos_encoder.dropout.p
     h = F.dropout(h, p, True) if mask is None else h * (mask.to(h) / (1.0 - p))
-    h = F.linear(h.reshape(batch_size, agent_num, T * 64), enc.input_fc2.weight, enc.input_fc2.bias)
+    h = _dense(h.reshape(batch_size, agent_num, T * 64), enc.input_fc2)
     cat = torch.zeros(agent_num, 3, device=h.device, dtype=h.dtype)
     cat[agent_num - 1, 2] = 1                                                   # model/STTODE.py:199-210
-    x0 = F.linear(torch.cat((h, cat.expand(batch_size, agent_num, 3)), dim=-1), enc.input_fc3.weight, enc.input_fc3.bias)
+    x0 = _dense(torch.cat((h, cat.expand(batch_size, agent_num, 3)), dim=-1), enc.input_fc3)
     y = enc.ODE_Encoder(x0.unsqueeze(2), mask=None, num_agent=agent_num).squeeze(2)
     return torch.cat((x0, y), dim=-1).view(rows, 128)
 
@@ -217,8 +249,8 @@ class FutureEncoder(_EncoderBase):
         """-> q(z | past, future) parameters [B*N, 2*zdim] (model/STTODE.py:276-300)."""
         ff = _encoder_forward(self, inputs, batch_size, agent_num)
         if self.training:
-            h = torch.relu(self.out_mlp.affine_layers[0](torch.cat((past_feature, ff), dim=-1)))
-            return self.qz_layer(h)
+            h = _dense(torch.cat((past_feature, ff), dim=-1), self.out_mlp.affine_layers[0], relu=True)
+            return _dense(h, self.qz_layer)
         h = torch.cat((_f32c(past_feature, "past_feature"), ff), dim=-1)
         h = _linear(h, self.out_mlp.affine_layers[0], relu=True)
         return _linear(h, self.qz_layer, relu=False)
