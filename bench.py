@@ -338,6 +338,21 @@ def run_ours(args):
             us = lat(lambda: gnba(batches.view(-1, 10, 2)), n=20)
             extra["nba_B128_10_20"] = {"scenes_per_s": nb * 128 / (us * 1e-6), "batches_per_launch": nb, "us_per_launch": us,
                                        "note": "16 reference batches per launch, each batch = one MHGSA group of L = S = 128 scenes x 11 agents"}
+            # configs[3]: SDD-shape large-scene sweep.  (i) end to end: one scene of N agents per call (S stays 1: stresses rows);
+            # (ii) Gram-tile stress: the MHGSA module alone on [L, bsz, 64] with L = S up to 512 (one 128-query tile per (agent, head) CTA)
+            sweep = {}
+            for n_ag in (16, 64, 256, 512):
+                obs_n = (torch.rand(n_ag, 2, TP, generator=torch.Generator().manual_seed(n_ag)) * 30.0).to(dev)
+                sp_n = torch.tensor([0, n_ag], dtype=torch.int32, device=dev)
+                gn = model.capture_forecast(rows=n_ag, L=1, agents=1, n_scenes=1)
+                sweep[f"N{n_ag}"] = {"cuda_graph_us_per_scene": lat(lambda: gn(obs_n, sp_n), n=50)}
+            attn = model.past_encoder.ODE_Encoder.odeblock.odefunc.layers[0].self_attn.temporal_attention_before
+            for Lg in (128, 256, 512):
+                xg = torch.randn(Lg, 64, 64, generator=torch.Generator().manual_seed(Lg)).to(dev)
+                us_g = lat(lambda: attn(xg, xg, xg, need_weights=False), n=50)
+                pairs_g = 64 * 8 * Lg * Lg                       # (agent, head, i, j) score entries
+                sweep[f"mhgsa_L{Lg}_bsz64"] = {"us_per_call": us_g, "score_entries_per_s": pairs_g / (us_g * 1e-6)}
+            extra["sdd_sweep"] = sweep
 
     total_scenes = S * world * args.steps
     value = total_scenes / (ms_max * 1e-3)
@@ -417,8 +432,31 @@ def run_train(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item()) / args.steps
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_extra:
+        # CPU baseline: the oracle port of the reference's step (forward + torch autograd backward), all host threads, one timed step
+        from oracle import sttode_oracle as O
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+        for k in sd:
+            if not k.endswith("pos_encoder.pe"):
+                sd[k].requires_grad_(True)
+        data = synth.nba_batch(100, B, N, tp, tf)
+        g = torch.Generator().manual_seed(5)
+        eps_q, eps_p = torch.randn(B * N, 32, generator=g), torch.randn(B * N * 20, 32, generator=g)
+        masks = ((torch.rand(B * N, tp, 64, generator=g) >= 0.1).float(), (torch.rand(B * N, tf, 64, generator=g) >= 0.1).float())
+        secs = []
+        for _ in range(2):
+            t0 = time.perf_counter()
+            out_cpu = O.training_objective(sd, data["past_traj"].view(B * N, tp, 2), data["future_traj"].view(B * N, tf, 2), B, N, eps_q, eps_p, masks=masks,
+                                           tensors=True)
+            out_cpu["total"].backward()
+            secs.append(time.perf_counter() - t0)
+        cpu = {"value": B / secs[-1], "unit": "scenes/s", "cores": threads, "kind": "port",
+               "sample": f"one training step (B = {B}) of the PyTorch-CPU oracle port: forward + autograd backward, no optimizer, {secs[-1]:.2f} s"}
     if rank == 0:
-        print(json.dumps({"metric": "training scenes/sec (DP, forward+backward+Adam)", "value": B * world / (ms * 1e-3), "unit": "scenes/s", "n_gpus": world,
+        print(json.dumps({"metric": "training scenes/sec (DP, forward+backward+Adam)", "cpu_baseline": cpu, "value": B * world / (ms * 1e-3), "unit": "scenes/s", "n_gpus": world,
                           "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                           "dtype": "f32", "data": "synthetic",
                           "config": {"workload": "STTODE training step (BASELINE.json configs[4]), NBA shape obs 10 / pred 20", "batch_per_gpu": B,

@@ -9,7 +9,7 @@ import types
 
 
 def install():
-    from . import layers, mhgsa, net, pmath
+    from . import layers, mhgsa, net, pmath, sampler
     mods = {}
 
     def mod(name, **attrs):
@@ -34,5 +34,8 @@ def install():
                                                              "Normal", "MLP2", "PositionalAgentEncoding")})
     ut = mod("model.utils", MLP=net.MLP, initialize_weights=net.initialize_weights)
     model.STTODE, model.utils = st, ut
+    mod("sampler", Sampler=sampler.Sampler)                     # trainsampler.py:9-10, test_sampler.py
+    mod("samplerloss", compute_sampler_loss=sampler.compute_sampler_loss, compute_sampler_loss_nba=sampler.compute_sampler_loss_nba,
+        compute_z_kld=sampler.compute_z_kld, diversity_loss=sampler.diversity_loss, recon_loss=sampler.recon_loss)
     sys.modules.update(mods)
     return mods
