@@ -355,7 +355,9 @@ class Decoder(nn.Module):
             raise NotImplementedError("B200 path: zdim = 32 only (train.py:37 default)")
         self.past_length, self.future_length = args.past_length, args.future_length
         self.decompose = nn.ModuleList(DecomposeBlock(args.past_length, args.future_length, input_dim) for _ in range(2))
-        self.use_tensor_cores = True        # tcgen05 decoder tile (k_dec_pair_tc); False -> FP32-FFMA kernel
+        # tcgen05 decoder tile (k_dec_pair_tc); False -> FP32-FFMA kernels (also chosen for horizons whose layer-3 block does not fit
+        # a ring stage / the TMEM column budget: 2 * max(T_p, T_f) > 48)
+        self.use_tensor_cores = 2 * max(args.past_length, args.future_length) <= 48
         self._packed = _PackedDecoder()
 
     def forward(self, past_feature, z, batch_size_curr, agent_num_perscene, past_traj, cur_location, sample_num, mode="train"):
