@@ -121,6 +121,10 @@ int sttode_umma_selftest(const float *a, const float *b, float *c, int n, int k,
 /* Diagnostic: issue `reps` back-to-back tcgen05.mma (M = 128, K = 16, kind::f16, width n) on resident operands; cycles2_dev[0] = clock64 cycles from
  * first issue to completion, [1] = cycles spent in the issue loop (device pointer to two long long). */
 int sttode_umma_bench(int n, int reps, long long *cycles2_dev, void *stream);
+/* Diagnostic: `reps` GRU-slab-like groups of MMAs (mode 0: 3 x N=192 then 3 x N=96 with distinct hi/lo images, the decoder's order; 1: interleaved;
+ * 2 / 3: only the N=192 / N=96 triples; 4: identical operands) with B images of b_rows rows; same outputs as sttode_umma_bench.
+ * poll_mode > 0 adds 16 bystander warps waiting on an mbarrier meanwhile (1: every lane polls, 2: one lane per warp, 3: one lane + nanosleep). */
+int sttode_umma_pattern(int mode, int b_rows, int reps, int poll_mode, long long *cycles2_dev, void *stream);
 
 /* ---- MHGSA: replaces Hyp_mhsa.forward -> hyp_mhsa (hyptransformerlib.py:403-454 -> :29-311) ------
  * query [L,bsz,E], key/value [S,bsz,E] (key==value==query pointer for self-attention), out [L,bsz,E],

@@ -72,6 +72,7 @@ SIGNATURES = {
     "sttode_profile_read": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),
     "sttode_umma_selftest": (_I, [_V, _V, _V, _I, _I, _I, _I, _V, _V]),
     "sttode_umma_bench": (_I, [_I, _I, _V, _V]),
+    "sttode_umma_pattern": (_I, [_I, _I, _I, _I, _V, _V]),
     "sttode_mhgsa_workspace_bytes": (_Z, [_I, _I, _I]),
     "sttode_mhgsa_fwd": (_I, [_V, _V, _V, C.POINTER(MhgsaWeights), _V, _V, _I, _I, _I, _I, _I, _I, _F, _F, _V, _Z, _V]),
     "sttode_linear64": (_I, [_V, _V, _V, _V, _I, _I, _V]),

@@ -16,6 +16,7 @@ void launch_pmath_dist_matrix(const float* x, const float* y, float* out, int b,
 void launch_pmath_elem(int op, const float* x, float* out, size_t n, float clampv, cudaStream_t st);
 int launch_umma_selftest(const float* A, const float* B, float* C, int N, int K, int passes, int swap, int* status, cudaStream_t st);
 int launch_umma_bench(int N, int reps, long long* cycles, cudaStream_t st);
+int launch_umma_pattern(int mode, int brows, int reps, long long* cycles, cudaStream_t st, int poll_mode);
 void launch_oblique_proj(const float* x, float* out, int rows, int d, cudaStream_t st);
 void launch_oblique_dist(const float* p1, const float* p2, float* out, int batch, int n1, int n2, int d, float lo, float hi, cudaStream_t st);
 }
@@ -839,6 +840,15 @@ int sttode_umma_bench(int n, int reps, long long* cycles2_dev, void* stream) {
     int e = launch_umma_bench(n, reps, cycles2_dev, (cudaStream_t)stream);
     g_launches.fetch_add(1);
     if (e) return fail(STTODE_ECUDA, "umma_bench launch: %s", cudaGetErrorString((cudaError_t)e));
+    return 0;
+}
+
+int sttode_umma_pattern(int mode, int b_rows, int reps, int poll_mode, long long* cycles2_dev, void* stream) {
+    if (!cycles2_dev || mode < 0 || mode > 4 || b_rows < 288 || b_rows > 320 || b_rows % 8 || reps < 1 || poll_mode < 0 || poll_mode > 3)
+        return fail(STTODE_EINVAL, "umma_pattern: bad argument");
+    int e = launch_umma_pattern(mode, b_rows, reps, cycles2_dev, (cudaStream_t)stream, poll_mode);
+    g_launches.fetch_add(1);
+    if (e) return fail(STTODE_ECUDA, "umma_pattern launch: %s", cudaGetErrorString((cudaError_t)e));
     return 0;
 }
 

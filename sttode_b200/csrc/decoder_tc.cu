@@ -222,7 +222,7 @@ __device__ void issuer_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int
 }
 
 __device__ void issuer_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, int blk0, int T, uint32_t n_d3, uint32_t& n_x) {
-    const uint32_t a1 = tc::smem_u32(sm + SM_A1), xh = tc::smem_u32(sm + SM_H);
+    const uint32_t a1 = tc::smem_u32(sm + SM_A1), xh = tc::smem_u32(sm + SM_H), ring0 = tc::smem_u32(sm + SM_RING);
     const uint32_t idesc_rz = tc::make_idesc_f16(192), idesc_n = tc::make_idesc_f16(96);
     (void)n_d3;                                     // the gate accumulators (columns 0..383) overlap D2 / D1 (all read out), not D3
 #pragma unroll 1
@@ -233,25 +233,29 @@ __device__ void issuer_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, int
         ++n_x;
         tc::tc_fence_after();
         TLOG(tl, 21);
-#pragma unroll 1
-        for (int kb = 0; kb < 8; ++kb) {            // one K = 16 slab of [W_ih | W_hh] (288 rows) per ring block
-            const int bi = blk0 + t * 8 + kb;
-            const uint32_t st = ring_wait(sm, bars, bi);
-            tc::tc_fence_after();
-            // A operand slab: kb < 2 -> conv image (k chunks 2kb, 2kb+1); else state h (A1 k chunks 4 + 2(kb-2) ..)
-            const uint32_t a_off = kb < 2 ? xh + kb * 4096 : a1 + 4 * 2048 + (kb - 2) * 4096;
-            const uint32_t a_lo_off = kb < 2 ? a_off + 8192 : a_off + 32768;
-            if (elect_one()) {
+        // one elected lane issues the whole step (8 K = 16 slabs of [W_ih | W_hh], 288 rows each): no reconvergence between slabs
+        if (elect_one()) {
+#pragma unroll
+            for (int kb = 0; kb < 8; ++kb) {
+                const int bi = blk0 + t * 8 + kb;
+                const uint32_t st = ring0 + (uint32_t)(bi & 3) * TC_STAGE;
+                if (!(kb & 1)) {                    // blk0 is even: the pair's barrier covers slab kb + 1 too
+                    tc_wait(bars, B_WFULL + ((bi >> 1) & 1), (uint32_t)((bi >> 2) & 1));
+                    tc::tc_fence_after();
+                }
+                // A operand slab: kb < 2 -> conv image (k chunks 2kb, 2kb+1); else state h (A1 k chunks 4 + 2(kb-2) ..)
+                const uint32_t a_off = kb < 2 ? xh + kb * 4096 : a1 + 4 * 2048 + (kb - 2) * 4096;
+                const uint32_t a_lo_off = kb < 2 ? a_off + 8192 : a_off + 32768;
                 const uint64_t ah = tc::op_desc(a_off, 128), al = tc::op_desc(a_lo_off, 128);
                 tc::mma_split3_d(tmem + COL_GR, ah, al, 0, tc::op_desc(st, 288), tc::op_desc(st + 9216, 288), 0, idesc_rz, 1, kb > 0);
                 const uint64_t bnh = tc::op_desc(st + 192 * 16, 288), bnl = tc::op_desc(st + 9216 + 192 * 16, 288);
                 if (kb < 2) tc::mma_split3_d(tmem + COL_GNI, ah, al, 0, bnh, bnl, 0, idesc_n, 1, kb > 0);
                 else        tc::mma_split3_d(tmem + COL_GNH, ah, al, 0, bnh, bnl, 0, idesc_n, 1, kb > 2);
-                if (bi & 1) tc::mma_commit(bars + B_WFREE + ((bi >> 1) & 1));
+                if (kb & 1) tc::mma_commit(bars + B_WFREE + ((bi >> 1) & 1));
                 if (kb == 7) tc::mma_commit(bars + B_ACC);
             }
-            __syncwarp();
         }
+        __syncwarp();
         TLOG(tl, 22);
     }
     tc_wait(bars, B_XFULL, n_x & 1);                // final state staged and the last gate read-out finished

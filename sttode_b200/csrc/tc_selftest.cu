@@ -108,6 +108,71 @@ __global__ void __launch_bounds__(128, 1) k_umma_bench(int N, int reps, long lon
     if (warp == 0) tc::tmem_dealloc(tmem, 256);
 }
 
+// Pattern probe: `reps` GRU-like slabs of 6 MMAs (3 x N = 192 into D0, 3 x N = 96 into D1) with distinct hi/lo operand images, B images of
+// `brows` rows (the decoder uses 288).  mode 0: rz rz rz n n n (the decoder's order); 1: interleaved rz n rz n rz n; 2: only the three N = 192;
+// 3: only the three N = 96; 4: one N = 256 + ... (unused).  cycles[0] = total, cycles[1] = issue loop.
+__global__ void __launch_bounds__(640, 1) k_umma_pattern(int mode, int brows, int reps, long long* __restrict__ cycles, int poll_mode) {
+    extern __shared__ __align__(128) unsigned char sm[];
+    const int a_bytes = 2 * 128 * 32, b_bytes = 2 * 320 * 32;        // hi + lo images, K = 16
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + a_bytes + b_bytes);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (a_bytes + b_bytes) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = 0;
+    if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
+    if (tid == 0) { tc::mbar_init(bar, 1); tc::mbar_init(bar + 2, 1); tc::fence_mbar_init(); }
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    if (tid == 0) {
+        const uint32_t i192 = tc::make_idesc_f16(192), i96 = tc::make_idesc_f16(96);
+        const uint32_t a0 = tc::smem_u32(sm), b0 = a0 + a_bytes;
+        const uint64_t ah = tc::op_desc(a0, 128), al = tc::op_desc(a0 + 128 * 32, 128);
+        const uint64_t bh = tc::op_desc(b0, brows), bl = tc::op_desc(b0 + brows * 32, brows);
+        const uint64_t nh = tc::op_desc(b0 + 192 * 16, brows), nl = tc::op_desc(b0 + brows * 32 + 192 * 16, brows);
+        const long long t0 = clock64();
+        for (int i = 0; i < reps; ++i) {
+            if (mode == 0) {
+                tc::mma_f16_nc(tmem, al, bh, i192, 1u); tc::mma_f16_nc(tmem, ah, bl, i192, 1u); tc::mma_f16_nc(tmem, ah, bh, i192, 1u);
+                tc::mma_f16_nc(tmem + 192, al, nh, i96, 1u); tc::mma_f16_nc(tmem + 192, ah, nl, i96, 1u); tc::mma_f16_nc(tmem + 192, ah, nh, i96, 1u);
+            } else if (mode == 1) {
+                tc::mma_f16_nc(tmem, al, bh, i192, 1u); tc::mma_f16_nc(tmem + 192, al, nh, i96, 1u);
+                tc::mma_f16_nc(tmem, ah, bl, i192, 1u); tc::mma_f16_nc(tmem + 192, ah, nl, i96, 1u);
+                tc::mma_f16_nc(tmem, ah, bh, i192, 1u); tc::mma_f16_nc(tmem + 192, ah, nh, i96, 1u);
+            } else if (mode == 2) {
+                tc::mma_f16_nc(tmem, al, bh, i192, 1u); tc::mma_f16_nc(tmem, ah, bl, i192, 1u); tc::mma_f16_nc(tmem, ah, bh, i192, 1u);
+            } else if (mode == 3) {
+                tc::mma_f16_nc(tmem + 192, al, nh, i96, 1u); tc::mma_f16_nc(tmem + 192, ah, nl, i96, 1u); tc::mma_f16_nc(tmem + 192, ah, nh, i96, 1u);
+            } else {    // same A / B / D every time at N = 192 (the plain issue-rate probe's pattern)
+                tc::mma_f16_nc(tmem, ah, bh, i192, 1u); tc::mma_f16_nc(tmem, ah, bh, i192, 1u); tc::mma_f16_nc(tmem, ah, bh, i192, 1u);
+            }
+        }
+        const long long t1 = clock64();
+        tc::mma_commit(bar);
+        tc::mbar_wait(bar, 0);
+        const long long t2 = clock64();
+        cycles[0] = t2 - t0;
+        cycles[1] = t1 - t0;
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar + 2)) : "memory");     // release the pollers
+    } else if (warp >= 4) {
+        // bystander warps waiting on an mbarrier while the MMAs run, the way the epilogue warps wait for the accumulators:
+        // poll_mode 1 = every lane polls (mbar_wait), 2 = one lane per warp polls, 3 = one lane polls with a nanosleep back-off
+        if (poll_mode == 1) tc::mbar_wait(bar + 2, 0);
+        else if (poll_mode == 2) { if ((tid & 31) == 0) tc::mbar_wait(bar + 2, 0); __syncwarp(); }
+        else if (poll_mode == 3) { if ((tid & 31) == 0) while (!tc::mbar_try_wait(bar + 2, 0)) __nanosleep(100); __syncwarp(); }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+int launch_umma_pattern(int mode, int brows, int reps, long long* cycles, cudaStream_t st, int poll_mode) {
+    const size_t smem = 2 * 128 * 32 + 2 * 320 * 32 + 64;
+    k_umma_pattern<<<1, poll_mode ? 640 : 128, smem, st>>>(mode, brows, reps, cycles, poll_mode);
+    return (int)cudaGetLastError();
+}
+
 int launch_umma_bench(int N, int reps, long long* cycles, cudaStream_t st) {
     const size_t smem = (128 + 256) * 32 + 64;
     k_umma_bench<<<1, 128, smem, st>>>(N, reps, cycles);
