@@ -177,30 +177,29 @@ __device__ void issuer_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int
         }
         __syncwarp();
     }
+    // one elected lane runs the whole chunk loop (waits included): no reconvergence between the layer-1 and layer-2 groups
+    if (elect_one()) {
 #pragma unroll 1
-    for (int ch = 0; ch < 16; ++ch) {
-        const int i0 = blk0 + 2 + 2 * ch, b = ch & 1;
-        const uint32_t sa = ring_wait(sm, bars, i0), sb = ring_wait(sm, bars, i0 + 1);
-        tc::tc_fence_after();
-        if (ch < 14) {              // layer 1 of chunk ch+2 into D1[(ch+2)&3] (chunk ch-2 was read out before HFULL(ch-2), waited two iterations ago)
-            if (elect_one()) {
+        for (int ch = 0; ch < 16; ++ch) {
+            const int i0 = blk0 + 2 + 2 * ch, b = ch & 1;
+            tc_wait(bars, B_WFULL + ((i0 >> 1) & 1), (uint32_t)((i0 >> 2) & 1));      // the pair's barrier covers block i0 + 1 too
+            const uint32_t sa = tc::smem_u32(sm + SM_RING + (i0 & 3) * TC_STAGE), sb = tc::smem_u32(sm + SM_RING + ((i0 + 1) & 3) * TC_STAGE);
+            tc::tc_fence_after();
+            if (ch < 14) {          // layer 1 of chunk ch+2 into D1[(ch+2)&3] (chunk ch-2 was read out before HFULL(ch-2), waited two iterations ago)
                 tc::mma_split3_d(tmem + COL_D1 + ((ch + 2) & 3) * 32, a1_hi, a1_lo, 256, tc::op_desc(sa + 16384, 32), tc::op_desc(sb + 16384, 32), 64,
                                  idesc1, nk1, false);
                 tc::mma_commit(bars + B_D1FULL + ((ch + 2) & 3));
             }
-            __syncwarp();
-        }
-        tc_wait(bars, B_HFULL + b, (uint32_t)((ch >> 1) & 1));          // relu(D1(ch) + rowpre) staged as the A operand
-        tc::tc_fence_after();
-        if (elect_one()) {
+            tc_wait(bars, B_HFULL + b, (uint32_t)((ch >> 1) & 1));          // relu(D1(ch) + rowpre) staged as the A operand
+            tc::tc_fence_after();
             tc::mma_split3_d(tmem + COL_D2, tc::op_desc(h_base + b * 16384, 128), tc::op_desc(h_base + b * 16384 + 8192, 128), 256,
                              tc::op_desc(sa, 256), tc::op_desc(sb, 256), 512, idesc2, 2, ch > 0);
             tc::mma_commit(bars + B_WFREE + ((i0 >> 1) & 1));
             tc::mma_commit(bars + B_HFREE + b);
             if (ch == 15) tc::mma_commit(bars + B_ACC);            // D2 complete
         }
-        __syncwarp();
     }
+    __syncwarp();
     // layer 3: D3 must have been read out by the previous phase's epilogue
     if (n_d3 >= 1) tc_wait(bars, B_D3FREE, (n_d3 - 1) & 1);
 #pragma unroll 1
