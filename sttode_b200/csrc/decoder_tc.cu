@@ -201,22 +201,23 @@ __device__ void issuer_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int
     }
     __syncwarp();
     // layer 3: D3 must have been read out by the previous phase's epilogue
-    if (n_d3 >= 1) tc_wait(bars, B_D3FREE, (n_d3 - 1) & 1);
+    if (elect_one()) {
+        if (n_d3 >= 1) tc_wait(bars, B_D3FREE, (n_d3 - 1) & 1);
 #pragma unroll 1
-    for (int p = 0; p < 8; ++p) {
-        const int b = p & 1, blk = blk0 + 2 + TC_NCH + (p >> 2);
-        const uint32_t st = ring_wait(sm, bars, blk) + (uint32_t)(p & 3) * n3p * 128;
-        tc_wait(bars, B_HFULL + b, (uint32_t)((p >> 1) & 1));          // 8 layer-2 fills per buffer precede: parity unchanged
-        tc::tc_fence_after();
-        if (elect_one()) {
+        for (int p = 0; p < 8; ++p) {
+            const int b = p & 1, blk = blk0 + 2 + TC_NCH + (p >> 2);
+            if (!(p & 3)) tc_wait(bars, B_WFULL + ((blk >> 1) & 1), (uint32_t)((blk >> 2) & 1));     // the pair's barrier covers both layer-3 blocks
+            const uint32_t st = tc::smem_u32(sm + SM_RING + (blk & 3) * TC_STAGE) + (uint32_t)(p & 3) * n3p * 128;
+            tc_wait(bars, B_HFULL + b, (uint32_t)((p >> 1) & 1));          // 8 layer-2 fills per buffer precede: parity unchanged
+            tc::tc_fence_after();
             tc::mma_split3_d(tmem + COL_D3, tc::op_desc(h_base + b * 16384, 128), tc::op_desc(h_base + b * 16384 + 8192, 128), 256,
                              tc::op_desc(st, n3p), tc::op_desc(st + n3p * 64, n3p), 2 * n3p, idesc3, 2, p > 0);
             tc::mma_commit(bars + B_HFREE + b);
             if (p == 7) tc::mma_commit(bars + B_WFREE + ((blk >> 1) & 1));
             if (p == 7) tc::mma_commit(bars + B_ACC);                  // D3 complete
         }
-        __syncwarp();
     }
+    __syncwarp();
     ++n_d3;
 }
 
