@@ -405,7 +405,7 @@ def run_train(args):
     model.set_device(dev)
     model.train()
     reducer = parallel.FlatGradReducer(model)
-    opt, sched = parallel.make_optimizer(model)
+    opt, sched = parallel.make_optimizer(model, capturable=args.train_graph)
     torch.manual_seed(1000 + rank)                               # per-rank dropout / rsample streams
     batches = [{k: v.to(dev) for k, v in synth.nba_batch(100 + rank * 64 + i, B, N, tp, tf).items()} for i in range(8)]
     it = [0]
@@ -418,14 +418,24 @@ def run_train(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+    if args.train_graph:
+        graphed = parallel.GraphedTrainStep(model, opt, reducer, batches[0], warmup=max(args.warmup, 3))
+        launches_per_step = None
+
+        def one_step():
+            it[0] += 1
+            return graphed(batches[it[0] % len(batches)])
+    else:
+        def one_step():
+            return parallel.train_step(model, opt, reducer, stage)
     for _ in range(max(args.warmup, 3)):
-        out = parallel.train_step(model, opt, reducer, stage)
+        out = one_step()
     barrier()
     l0 = L.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        out = parallel.train_step(model, opt, reducer, stage)
+        out = one_step()
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -461,7 +471,8 @@ def run_train(args):
                           "dtype": "f32", "data": "synthetic",
                           "config": {"workload": "STTODE training step (BASELINE.json configs[4]), NBA shape obs 10 / pred 20", "batch_per_gpu": B,
                                      "agents": N, "parallelism": f"dp{world}: one all-reduce of {reducer.nbytes} B per step (pz_layer excluded)"},
-                          "gpu_launches": int(L.launch_count() - l0), "last_loss": float(out[0].detach()),
+                          "gpu_launches": int(L.launch_count() - l0) if not args.train_graph else "one CUDA-graph replay per step (502 library kernels inside)",
+                          "cuda_graph": bool(args.train_graph), "last_loss": float(out[0].detach()),
                           "note": "every layer forward+backward in libsttode_sm100 (ODE blocks, dense layers, decoder incl. GRU through time); torch: autograd bookkeeping, losses, Adam"}), flush=True)
     if world > 1:
         dist.barrier()
@@ -479,6 +490,7 @@ def main():
     ap.add_argument("--ref-scenes", type=int, default=96, help="scenes per step of the --impl reference arm")
     ap.add_argument("--no-extra", action="store_true", help="skip the brief single-scene-latency and NBA-shape measurements")
     ap.add_argument("--train", action="store_true", help="time the data-parallel training step (configs[4]) instead of the headline inference metric")
+    ap.add_argument("--train-graph", action="store_true", help="replay the whole training step as one CUDA graph")
     ap.add_argument("--train-batch", type=int, default=32, help="scenes per GPU per training step (train.py:24)")
     ap.add_argument("--ffma", action="store_true", help="use the FP32-FFMA decoder tile instead of the tcgen05 one")
     args = ap.parse_args()

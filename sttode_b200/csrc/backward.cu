@@ -19,21 +19,20 @@ namespace sttode {
 // ------------------------------------------------------------------------------------------------
 // C[M,N] = epi(sum_k A(m,k) B(k,n)),  A(m,k) = A[m*sam + k*sak],  B(k,n) = B[k*sbk + n*sbn]
 // epi(v) = ((relu? max(v + bias[n], 0) : v + bias[n]) * (mask[m,n] > 0 ? 1 : 0 if mask)) + res[m,n] (+ C[m,n] if accumulate)
-// 64 x 64 output tile per CTA, 256 threads x (4 x 4) register tile, K in slabs of 16.
 // ------------------------------------------------------------------------------------------------
-constexpr int GT = 64, GK = 16;
+constexpr int GTM = 128, GTN = 64, GK = 16;     // 128 x 64 output tile per CTA, 256 threads x (8 x 4) register tile, K in slabs of 16
 
 __global__ void __launch_bounds__(256)
 k_gemm(int M, int N, int K, const float* __restrict__ A, long sam, long sak, const float* __restrict__ B, long sbk, long sbn,
        float* __restrict__ C, long ldc, const float* __restrict__ bias, const float* __restrict__ res, long ldres,
        const float* __restrict__ mask, long ldmask, int relu, int accumulate, int kchunk, long slice_stride) {
-    __shared__ float As[GK][GT + 4];
-    __shared__ float Bs[GK][GT + 4];
+    __shared__ __align__(16) float As[GK][GTM + 4];
+    __shared__ __align__(16) float Bs[GK][GTN + 4];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
-    float acc[4][4];
+    const int m0 = blockIdx.y * GTM, n0 = blockIdx.x * GTN;
+    float acc[8][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     const bool a_kfast = sak == 1, b_nfast = sbn == 1;
@@ -41,39 +40,64 @@ k_gemm(int M, int N, int K, const float* __restrict__ A, long sam, long sak, con
     const int kbeg = blockIdx.z * kchunk;
     K = min(K, kbeg + kchunk);
     C += (size_t)blockIdx.z * slice_stride;
-    for (int k0 = kbeg; k0 < K; k0 += GK) {
+    // element e of this thread's share of a slab: coordinates chosen so that consecutive threads walk the contiguous axis
+    float ra[8], rb[4];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int idx = tid + e * 256;
+            int mm, kk;
+            if (a_kfast) { kk = idx & 15; mm = idx >> 4; } else { mm = idx & 127; kk = idx >> 7; }
+            ra[e] = (m0 + mm < M && k0 + kk < K) ? A[(long)(m0 + mm) * sam + (long)(k0 + kk) * sak] : 0.f;
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int idx = tid + e * 256;
-            int mm, kk;
-            if (a_kfast) { kk = idx & 15; mm = idx >> 4; } else { mm = idx & 63; kk = idx >> 6; }
-            As[kk][mm] = (m0 + mm < M && k0 + kk < K) ? A[(long)(m0 + mm) * sam + (long)(k0 + kk) * sak] : 0.f;
             int nn, kb;
             if (b_nfast) { nn = idx & 63; kb = idx >> 6; } else { kb = idx & 15; nn = idx >> 4; }
-            Bs[kb][nn] = (n0 + nn < N && k0 + kb < K) ? B[(long)(k0 + kb) * sbk + (long)(n0 + nn) * sbn] : 0.f;
+            rb[e] = (n0 + nn < N && k0 + kb < K) ? B[(long)(k0 + kb) * sbk + (long)(n0 + nn) * sbn] : 0.f;
         }
+    };
+    auto stash = [&]() {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int idx = tid + e * 256;
+            int mm, kk;
+            if (a_kfast) { kk = idx & 15; mm = idx >> 4; } else { mm = idx & 127; kk = idx >> 7; }
+            As[kk][mm] = ra[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int idx = tid + e * 256;
+            int nn, kb;
+            if (b_nfast) { nn = idx & 63; kb = idx >> 6; } else { kb = idx & 15; nn = idx >> 4; }
+            Bs[kb][nn] = rb[e];
+        }
+    };
+    if (kbeg < K) fetch(kbeg);
+    for (int k0 = kbeg; k0 < K; k0 += GK) {
+        stash();
         __syncthreads();
+        if (k0 + GK < K) fetch(k0 + GK);            // global loads of the next slab overlap the FMAs of this one
 #pragma unroll
         for (int kk = 0; kk < GK; ++kk) {
-            float a[4], b[4];
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]), a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty + 16 * i];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx + 16 * j];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 8; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = m0 + ty + 16 * i;
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + ty * 8 + i;
         if (m >= M) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int n = n0 + tx + 16 * j;
+            const int n = n0 + tx * 4 + j;
             if (n >= N) continue;
             float v = acc[i][j];
             if (bias) v += __ldg(bias + n);

@@ -237,8 +237,8 @@ size_t ode_ws_bytes(int rows, int L, int method) {
 int gemm(cudaStream_t st, int M, int N, int K, const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C, long ldc,
          const float* bias = nullptr, const float* res = nullptr, long ldres = 0, const float* mask = nullptr, long ldmask = 0,
          int relu = 0, int accumulate = 0) {
-    k_gemm<<<dim3(ceil_div(N, 64), ceil_div(M, 64)), 256, 0, st>>>(M, N, K, A, sam, sak, B, sbk, sbn, C, ldc, bias, res, ldres, mask, ldmask,
-                                                                  relu, accumulate, K, 0);
+    k_gemm<<<dim3(ceil_div(N, 64), ceil_div(M, 128)), 256, 0, st>>>(M, N, K, A, sam, sak, B, sbk, sbn, C, ldc, bias, res, ldres, mask, ldmask,
+                                                                   relu, accumulate, K, 0);
     LAUNCH_CHECK("k_gemm");
     return 0;
 }
@@ -259,13 +259,13 @@ int gemm_nn(cudaStream_t st, int rows, int K, int N, const float* dy, long lddy,
 int weight_grad(cudaStream_t st, int rows, int N, int K, const float* dy, long lddy, const float* x, long ldx, float* dW, float* db,
                 float* splitk = nullptr) {
     int rc;
-    const int tiles = ceil_div(N, 64) * ceil_div(K, 64);
+    const int tiles = ceil_div(N, 128) * ceil_div(K, 64);
     if (dW && splitk && rows >= 2048 && tiles < 296 && (size_t)N * K <= 512 * 256) {
         // rows split over gridDim.z so the launch fills the GPU; partial products summed in slice order (deterministic)
         const int slices = std::min(SPLITK_MAX, std::min(ceil_div(rows, 256), ceil_div(592, tiles)));
         const int kchunk = ceil_div(ceil_div(rows, slices), 16) * 16;
         const int nz = ceil_div(rows, kchunk);
-        k_gemm<<<dim3(ceil_div(K, 64), ceil_div(N, 64), nz), 256, 0, st>>>(N, K, rows, dy, 1, lddy, x, ldx, 1, splitk, K, nullptr, nullptr, 0, nullptr, 0,
+        k_gemm<<<dim3(ceil_div(K, 64), ceil_div(N, 128), nz), 256, 0, st>>>(N, K, rows, dy, 1, lddy, x, ldx, 1, splitk, K, nullptr, nullptr, 0, nullptr, 0,
                                                                           0, 0, kchunk, (long)N * K);
         LAUNCH_CHECK("k_gemm(split-K)");
         k_sum_slices<<<ceil_div(N * K, 256), 256, 0, st>>>(splitk, nz, (long)N * K, (long)N * K, dW);

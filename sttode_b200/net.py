@@ -222,7 +222,7 @@ def _encoder_forward_train(enc, inputs, batch_size, agent_num):
     h = F.dropout(h, p, True) if mask is None else h * (mask.to(h) / (1.0 - p))
     h = _dense(h.reshape(batch_size, agent_num, T * 64), enc.input_fc2)
     cat = torch.zeros(agent_num, 3, device=h.device, dtype=h.dtype)
-    cat[agent_num - 1, 2] = 1                                                   # model/STTODE.py:199-210
+    cat[agent_num - 1:, 2:].fill_(1.0)                                          # model/STTODE.py:199-210 (fill_: capturable, no H2D scalar copy)
     x0 = _dense(torch.cat((h, cat.expand(batch_size, agent_num, 3)), dim=-1), enc.input_fc3)
     y = enc.ODE_Encoder(x0.unsqueeze(2), mask=None, num_agent=agent_num).squeeze(2)
     return torch.cat((x0, y), dim=-1).view(rows, 128)
@@ -457,8 +457,8 @@ def _decoder_forward_train(self, past_feature, z, past_traj, cur_location, sampl
     """train() mode (model/STTODE.py:320-347) with autograd history: forward and backward both run in libsttode_sm100."""
     if not past_feature.is_cuda:
         raise _lib.SttodeError("Decoder inputs must be CUDA tensors; this path has no CPU implementation")
-    if not torch.equal(cur_location.reshape(-1, 2), past_traj[:, -1].reshape(-1, 2)):
-        raise NotImplementedError("Decoder on B200: cur_location must be past_traj[:, -1] (as at every reference call site)")
+    if cur_location.shape[0] != past_traj.shape[0]:            # the library adds past_traj[:, -1] itself (every reference call site passes it);
+        raise NotImplementedError("Decoder on B200: cur_location must be past_traj[:, -1]")      # no value check here: it would force a device sync
     x_true = past_traj.detach().repeat_interleave(sample_num, dim=0)
     pf = past_feature.reshape(x_true.shape[0], -1)
     out, rec = _DecoderTrainFn.apply(pf, z.reshape(-1, 32), x_true, self.past_length, self.future_length, *_decompose_params(self))
@@ -600,7 +600,7 @@ class STTODENet(nn.Module):
             fut_orig = fut_orig.index_select(0, ind).contiguous()
             self._obs = pre.permute(1, 2, 0).contiguous()
         self.agent_num = pre.shape[1]
-        self.scene_orig = pre[[-1]].view(-1, 2).mean(dim=0)
+        self.scene_orig = pre[-1:].view(-1, 2).mean(dim=0)
         if self.rand_rot_scene and self.training:                                     # :419-426
             theta = getattr(self, "theta_override", None)
             if theta is None:
@@ -612,14 +612,14 @@ class STTODENet(nn.Module):
         else:
             pre_norm, fut_norm = pre - self.scene_orig, fut - self.scene_orig
         pre_vel = pre[1:] - pre[:-1]
-        pre_vel = torch.cat([pre_vel[[0]], pre_vel], dim=0)
-        fut_vel = fut - torch.cat([pre[[-1]], fut[:-1]])
+        pre_vel = torch.cat([pre_vel[:1], pre_vel], dim=0)
+        fut_vel = fut - torch.cat([pre[-1:], fut[:-1]])
         self.fut_motion_orig = fut_orig
         self.inputs = torch.cat([pre_norm, pre_vel], dim=-1).permute(1, 0, 2).contiguous()
         self.inputs_for_posterior = torch.cat([fut_norm, fut_vel], dim=-1).permute(1, 0, 2).contiguous()
         self.past_traj = pre_norm.permute(1, 0, 2).contiguous()
         self.future_traj = fut_norm.permute(1, 0, 2).contiguous()
-        self.cur_location = self.past_traj[:, [-1]]
+        self.cur_location = self.past_traj[:, -1:]
         self._features_staged = True
 
     def set_data_nba(self, data):
@@ -671,7 +671,7 @@ class STTODENet(nn.Module):
             rs = torch.zeros(n, dtype=torch.int32, device=obs.device)
             pred = self._forecast(obs, TRAJ_R2T, sp, rs, 1, n, 1, n, K)
             self.scene_orig = self._origin[0]
-        self.cur_location = self.past_traj[:, [-1]]
+        self.cur_location = self.past_traj[:, -1:]
         return pred.permute(1, 0, 2, 3)
 
     @torch.no_grad()
@@ -701,11 +701,11 @@ class STTODENet(nn.Module):
             past = _f32c(self.data["past_traj"].to(dev), "past_traj").view(B * N, self.args.past_length, 2)
             fut = _f32c(self.data["future_traj"].to(dev), "future_traj").view(B * N, self.args.future_length, 2)
             vel = past[:, 1:] - past[:, :-1]
-            self.inputs = torch.cat((past, torch.cat([vel[:, [0]], vel], dim=1)), dim=-1)
-            fvel = fut - torch.cat([past[:, [-1]], fut[:, :-1]], dim=1)
+            self.inputs = torch.cat((past, torch.cat([vel[:, :1], vel], dim=1)), dim=-1)
+            fvel = fut - torch.cat([past[:, -1:], fut[:, :-1]], dim=1)
             self.inputs_for_posterior = torch.cat((fut, fvel), dim=-1)
             self.scene_orig = self.past_traj = past
-            self.future_traj, self.cur_location = fut, past[:, [-1]]
+            self.future_traj, self.cur_location = fut, past[:, -1:]
         elif not (getattr(self, "_mode", None) == "scene" and getattr(self, "_features_staged", False)):
             raise NotImplementedError("STTODENet: stage the batch with set_data_nba, or with set_data(..., fut_motion) first")
 
@@ -753,11 +753,9 @@ class STTODENet(nn.Module):
             self.diverse_pred_traj, self.attn_weights = self.decoder(self.past_feature_repeat, pz_sampled, self.batch_size, self.agent_num,
                                                                      self.past_traj, self.cur_location, sample_num=20, mode="inference")
 
-    def forward(self):
-        """The reference's training objective (model/STTODE.py:553-568) on the staged batch:
-        (total_loss, loss_pred, loss_recover, loss_kl, loss_diverse).  train(): total_loss carries autograd history (call
-        .backward() on it as train.py:65 does).  eval(): forward-only, every stage inside the library.
-        `self.eps_override = (eps_q [R,zdim], eps_p [R*20,zdim])` injects the two live rsample draws (tests)."""
+    def objective(self):
+        """The reference's training objective (model/STTODE.py:553-568) on the staged batch as tensors, with no host sync (usable under
+        CUDA-graph capture): (total_loss, stack of [loss_pred, loss_recover, loss_kl, loss_diverse])."""
         args = self.args
         self.encode_history()
         self.fu_encoder()
@@ -772,7 +770,15 @@ class STTODENet(nn.Module):
             diff = self.future_traj.unsqueeze(1) - self.diverse_pred_traj                          # :389-395
             loss_diverse = diff.pow(2).sum(dim=-1).sum(dim=-1).min(dim=1)[0].mean()
             total = loss_pred + loss_recover + loss_kl + loss_diverse
-        return total, loss_pred.item(), loss_recover.item(), loss_kl.item(), loss_diverse.item()
+            parts = torch.stack((loss_pred.detach(), loss_recover.detach(), loss_kl.detach(), loss_diverse.detach()))
+        return total, parts
+
+    def forward(self):
+        """(total_loss, loss_pred, loss_recover, loss_kl, loss_diverse) like the reference.  train(): total_loss carries autograd history
+        (call .backward() on it as train.py:65 does).  eval(): forward-only, every stage inside the library.
+        `self.eps_override = (eps_q [R,zdim], eps_p [R*20,zdim])` injects the two live rsample draws (tests)."""
+        total, parts = self.objective()
+        return (total, *parts.tolist())                                                            # one sync for the four floats
 
     def step_annealer(self):
         for anl in self.param_annealers:

@@ -87,9 +87,9 @@ class FlatGradReducer:
         return self.flat
 
 
-def make_optimizer(module, lr=1e-4, decay_step=10, decay_gamma=0.5):
-    """train.py:122-123: Adam(lr) + StepLR(decay_step, decay_gamma)."""
-    opt = torch.optim.Adam(module.parameters(), lr=lr)
+def make_optimizer(module, lr=1e-4, decay_step=10, decay_gamma=0.5, capturable=False):
+    """train.py:122-123: Adam(lr) + StepLR(decay_step, decay_gamma).  capturable=True for `GraphedTrainStep`."""
+    opt = torch.optim.Adam(module.parameters(), lr=lr, capturable=capturable)
     return opt, torch.optim.lr_scheduler.StepLR(opt, step_size=decay_step, gamma=decay_gamma)
 
 
@@ -103,3 +103,49 @@ def train_step(model, optimizer, reducer, stage):
     reducer.reduce()
     optimizer.step()
     return out
+
+
+class GraphedTrainStep:
+    """One whole data-parallel training step — stage -> objective -> backward -> gradient all-reduce -> Adam — captured as ONE CUDA graph
+    for a fixed NBA batch shape.  The step is ~1000 small launches (502 of them libsttode_sm100 kernels); replaying a graph removes the
+    Python / launch overhead that otherwise dominates it.  The optimizer must be built with `capturable=True`.
+
+        step = GraphedTrainStep(model, optimizer, reducer, batch)      # batch: {'past_traj': [B,N,T_p,2], 'future_traj': [B,N,T_f,2]} on the GPU
+        losses = step(next_batch)                                        # tensor [total, pred, recover, kl, diverse], no host sync
+
+    Construction runs `warmup` (>= 1) real training steps on `batch` eagerly (allocations, optimizer state) before capturing.
+    """
+
+    def __init__(self, model, optimizer, reducer, batch, warmup=3):
+        if warmup < 1:
+            # the optimizer creates (and zero-fills) its state on its first step; inside the capture that fill would be replayed every step
+            raise ValueError("GraphedTrainStep needs at least one eager warm-up step (it is a real training step on `batch`)")
+        self.model, self.optimizer, self.reducer = model, optimizer, reducer
+        dev = batch["past_traj"].device
+        self.static = {k: batch[k].detach().clone().contiguous() for k in ("past_traj", "future_traj")}
+        self.losses = torch.zeros(5, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._body()
+
+    def _body(self):
+        self.model.set_data_nba(self.static)
+        total, parts = self.model.objective()
+        self.reducer.zero()
+        total.backward()
+        self.reducer.reduce()
+        self.optimizer.step()
+        self.losses.copy_(torch.cat((total.detach().reshape(1), parts)))
+
+    def __call__(self, batch):
+        for k, v in self.static.items():
+            v.copy_(batch[k], non_blocking=True)
+        self.graph.replay()
+        return self.losses

@@ -118,3 +118,39 @@ def test_adam_steps_reduce_the_loss(dev):
         opt.step()
         hist.append(float(total))
     assert hist[-1] < hist[0]
+
+
+def test_cuda_graph_training_step_equals_eager(dev):
+    """parallel.GraphedTrainStep replays stage -> objective -> backward -> (all-reduce) -> Adam as one CUDA graph; with every random draw
+    injected, one warm-up step plus two replayed steps give the eager loop's losses and land on the same weights (deterministic kernels)."""
+    from sttode_b200 import parallel
+    dataset, tp, tf, B, N = "nba", 10, 20, 8, 11
+    d = training_draws(B * N, tp, tf, seed=21)
+    batches = [{k: v.to(dev) for k, v in synth.nba_batch(20 + i, B, N, tp, tf).items()} for i in range(3)]
+    results = []
+    for graphed in (False, True):
+        m, _ = build(dataset, tp, tf, dev, seed=7)
+        m.train()
+        m.past_encoder.dropout_mask_override, m.future_encoder.dropout_mask_override = d["mask_past"].to(dev), d["mask_future"].to(dev)
+        m.eps_override = (d["eps_q"].to(dev), d["eps_p"].to(dev))
+        red = parallel.FlatGradReducer(m)
+        opt, _ = parallel.make_optimizer(m, lr=1e-3, capturable=graphed)
+        losses = []
+        if graphed:
+            step = parallel.GraphedTrainStep(m, opt, red, batches[0], warmup=1)      # one eager step on batches[0], then capture
+            losses.append(step.losses.clone())
+            for b in batches[1:]:
+                losses.append(step(b).clone())
+        else:
+            for b in batches:
+                out = parallel.train_step(m, opt, red, lambda: m.set_data_nba(b))
+                losses.append(torch.tensor([float(out[0].detach()), *out[1:]], device=dev))
+        torch.cuda.synchronize()
+        results.append((torch.stack(losses).cpu(), {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}))
+    (la, wa), (lb, wb) = results
+    # capturable Adam evaluates its bias corrections with device tensors: same update up to fp32 rounding
+    assert torch.allclose(la, lb, rtol=1e-4, atol=0), (la, lb)
+    # Adam normalises every element's update to ~lr, so an element whose gradient is rounding noise may step the other way: compare in the mean
+    for k in wa:
+        if wa[k].is_floating_point():
+            assert float((wa[k] - wb[k]).abs().mean()) < 2e-5, k
