@@ -34,7 +34,7 @@ sys.path.insert(0, ROOT)
 TP, TF, K = 8, 12, 20
 CYCLE = (10, 20, 30, 40, 50, 60)
 WEIGHT_SEED = 1
-DRAM_BYTES_PER_PAIR = 100.2e6 / 268800     # ncu --set full of the dominant kernel (profiles/r01_ncu_full_k_dec_pair_tc.md)
+DRAM_BYTES_PER_PAIR = 97.0e6 / 268800     # ncu --set full of the dominant kernel (profiles/r01_ncu_full_k_dec_pair_tc.md)
 
 
 # ---------------------------------------------------------------------------------- FLOP accounting
