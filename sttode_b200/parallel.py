@@ -106,13 +106,16 @@ def train_step(model, optimizer, reducer, stage):
 
 
 class GraphedTrainStep:
-    """One whole data-parallel training step — stage -> objective -> backward -> gradient all-reduce -> Adam — captured as ONE CUDA graph
+    """One whole data-parallel training step — stage -> objective -> backward -> gradient all-reduce -> Adam — replayed from CUDA graphs
     for a fixed NBA batch shape.  The step is ~1000 small launches (502 of them libsttode_sm100 kernels); replaying a graph removes the
     Python / launch overhead that otherwise dominates it.  The optimizer must be built with `capturable=True`.
 
         step = GraphedTrainStep(model, optimizer, reducer, batch)      # batch: {'past_traj': [B,N,T_p,2], 'future_traj': [B,N,T_f,2]} on the GPU
         losses = step(next_batch)                                        # tensor [total, pred, recover, kl, diverse], no host sync
 
+    World size 1: one graph holds the whole step.  World size > 1: the NCCL all-reduce stays OUTSIDE the graphs (graph 1 = stage ..
+    backward, eager all-reduce of the flat buffer, graph 2 = Adam): a collective captured into a graph ties every rank's replay to
+    the communicator's internal stream state, and a rank that falls out of step deadlocks the job instead of raising.
     Construction runs `warmup` (>= 1) real training steps on `batch` eagerly (allocations, optimizer state) before capturing.
     """
 
@@ -124,28 +127,44 @@ class GraphedTrainStep:
         dev = batch["past_traj"].device
         self.static = {k: batch[k].detach().clone().contiguous() for k in ("past_traj", "future_traj")}
         self.losses = torch.zeros(5, device=dev)
+        self.split = reducer.world() > 1
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                self._body()
+                self._forward_backward()
+                self.reducer.reduce()
+                self._update()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self._body()
+        if not self.split:
+            with torch.cuda.graph(self.graph):
+                self._forward_backward()
+                self._update()
+            self.graph_update = None
+        else:
+            with torch.cuda.graph(self.graph):
+                self._forward_backward()
+            self.graph_update = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_update, pool=self.graph.pool()):
+                self._update()
 
-    def _body(self):
+    def _forward_backward(self):
         self.model.set_data_nba(self.static)
         total, parts = self.model.objective()
         self.reducer.zero()
         total.backward()
-        self.reducer.reduce()
-        self.optimizer.step()
         self.losses.copy_(torch.cat((total.detach().reshape(1), parts)))
+
+    def _update(self):
+        self.optimizer.step()
 
     def __call__(self, batch):
         for k, v in self.static.items():
             v.copy_(batch[k], non_blocking=True)
         self.graph.replay()
+        if self.split:
+            self.reducer.reduce()             # eager NCCL all-reduce of the flat gradient buffer on the current stream
+            self.graph_update.replay()
         return self.losses
