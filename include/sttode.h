@@ -1,4 +1,4 @@
-/* sttode.h — C ABI of libsttode_sm100.so, the B200 (sm_100a) implementation of the STTODE forward hot path.
+/* sttode.h — C ABI of libsttode_sm100.so, the B200 (sm_100a) implementation of the STTODE hot path (forward and backward).
  *
  * The reference (joyecnu/STTODE) is pure Python/PyTorch and has no FFI; its boundary for this path is the
  * Python module API.  Each entry point below names the reference interface it replaces

@@ -561,7 +561,7 @@ def test_cuda_graph_forecast(eth, dev):
 
 
 def test_future_encoder_and_training_objective_vs_reference(golden, dev):
-    """FutureEncoder.forward and the training objective STTODENet.forward() (forward only) against the reference's own
+    """FutureEncoder.forward and the training objective STTODENet.forward() in eval() mode (no autograd history) against the reference's own
     forward() output (tests/golden/training_objective.npz: eval mode, injected rsample draws)."""
     g = golden("training_objective")
     B, tp, tf = int(g["B"]), 10, 20
