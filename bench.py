@@ -486,7 +486,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scenes", type=int, default=1536, help="scenes per GPU per step")
-    ap.add_argument("--cpu-scenes", type=int, default=192, help="bounded CPU-baseline sample (scenes)")
+    ap.add_argument("--cpu-scenes", type=int, default=1536, help="bounded CPU-baseline sample (scenes; ~10 s of host time at ~150 scenes/s)")
     ap.add_argument("--ref-scenes", type=int, default=96, help="scenes per step of the --impl reference arm")
     ap.add_argument("--no-extra", action="store_true", help="skip the brief single-scene-latency and NBA-shape measurements")
     ap.add_argument("--train", action="store_true", help="time the data-parallel training step (configs[4]) instead of the headline inference metric")
