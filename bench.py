@@ -305,6 +305,32 @@ def run_ours(args):
     cpu_s = time_cpu_port(sd, scenes[:nsmp], threads)
     cpu_val = nsmp / cpu_s
 
+    # ---- ADE/FDE delta vs the reference (second half of BASELINE.json's metric): same scenes, same injected latent, GPU path vs CPU oracle port ---
+    from oracle import sttode_oracle as O
+    from sttode_b200 import synth as _synth
+    npar = 24
+    with torch.no_grad():
+        zs, ade_ref, fde_ref, n_ref = [], 0.0, 0.0, 0
+        for i, (obs, gt) in enumerate(scenes[:npar]):
+            n = obs.shape[0]
+            z = _synth.latent(n, seed=500 + i)
+            zs.append(z)
+            past, orig = O.eth_scene_normalise(obs)
+            pr = O.inference(sd, past, 1, n, z, sample_k=K, scene_orig=orig, fast=True)            # [K, n, T_f, 2]
+            a, f = O.min_ade_fde(pr.permute(1, 0, 2, 3), gt.permute(0, 2, 1))
+            ade_ref, fde_ref, n_ref = ade_ref + a * n, fde_ref + f * n, n_ref + n
+        obs_p = torch.cat([o for o, _ in scenes[:npar]]).to(dev)
+        gt_p = torch.cat([g for _, g in scenes[:npar]])
+        sp_p = torch.tensor(np.concatenate([[0], np.cumsum([o.shape[0] for o, _ in scenes[:npar]])]), dtype=torch.int32)
+        model.z_override = torch.cat(zs)
+        pr_g = model.forecast_scenes(obs_p, sp_p).cpu()                                            # [rows, K, T_f, 2]
+        model.z_override = None
+        ade_g, fde_g = O.min_ade_fde(pr_g, gt_p.permute(0, 2, 1))
+    ade_ref, fde_ref = ade_ref / n_ref, fde_ref / n_ref
+    parity = {"scenes": npar, "agents": n_ref, "min_ade_reference": ade_ref, "min_ade_ours": ade_g, "min_fde_reference": fde_ref, "min_fde_ours": fde_g,
+              "rel_delta_ade": abs(ade_g - ade_ref) / ade_ref, "rel_delta_fde": abs(fde_g - fde_ref) / fde_ref,
+              "note": "same scenes, same injected latent z; reference = PyTorch-CPU oracle port (pinned to the reference's outputs in tests/golden); tolerance 1e-4"}
+
     # ---- other configs of BASELINE.json, measured briefly for DESIGN.md (not the headline): rank 0 only -----------------
     extra = {}
     if not args.no_extra:
@@ -375,6 +401,7 @@ def run_ours(args):
         "cpu_baseline": {"value": cpu_val, "unit": "scenes/s", "cores": threads, "kind": "port",
                          "sample": f"first {nsmp} scenes of the same workload, one scene per call, PyTorch-CPU oracle port, {threads} threads, {cpu_s:.1f} s"},
         "tc_status": model.tc_status(),
+        "ade_fde_delta_vs_reference": parity,
         "extra": extra,
         "quality": {"min_ade": ade, "min_fde": fde, "agents": nrow, "note": "synthetic weights: parity is checked in tests/, not here"},
     }
