@@ -411,18 +411,19 @@ def _decompose_struct_from(t18, cls):
 
 
 class _DecoderTrainFn(torch.autograd.Function):
-    """Decoder.forward in train() mode as one autograd node over sttode_decoder_fwd (FP32 kernels, every pair its own row) and
+    """Decoder.forward in train() mode as one autograd node over sttode_decoder_fwd (tcgen05 kernels, every pair its own row) and
     sttode_decoder_bwd (Conv1d / GRU-through-time / MLP backward in libsttode_sm100).  past_feature [P,128], z [P,32],
     traj [P,T_p,2] = x_true per pair -> (out_seq [P,T_f,2] incl. the current position, recover_pre_seq [P,T_p,2])."""
 
     @staticmethod
-    def forward(ctx, past_feature, z, traj, Tp, Tf, *params):
+    def forward(ctx, past_feature, z, traj, Tp, Tf, packed, *params):
         pf, zz, tj = _f32c(past_feature, "past_feature"), _f32c(z, "z"), _f32c(traj, "past_traj")
         params = [_f32c(p, "parameter") for p in params]
         P = pf.shape[0]
         mw = _lib.ModelWeights()
         mw.past_length, mw.future_length = Tp, Tf
         mw.dec[0], mw.dec[1] = _decompose_struct_from(params[:18], _lib.DecomposeWeights), _decompose_struct_from(params[18:], _lib.DecomposeWeights)
+        mw.dec_packed = _lib.dptr(packed)              # fp16 hi/lo images of the CURRENT weights -> tcgen05 forward; None -> FP32 kernels
         pred = torch.empty(P, 1, Tf, 2, device=pf.device, dtype=torch.float32)
         recon = torch.empty(P, Tp, 2, device=pf.device, dtype=torch.float32)
         lib = _lib.lib()
@@ -450,7 +451,7 @@ class _DecoderTrainFn(torch.autograd.Function):
         ws = _lib.workspace(lib.sttode_decoder_bwd_workspace_bytes(P, Tp, Tf), pf.device)
         _lib.check(lib.sttode_decoder_bwd(_lib.dptr(pf), _lib.dptr(zz), _lib.dptr(tj), _lib.dptr(d_pred), _lib.dptr(d_recon), P, C.byref(mw), gs,
                                           _lib.dptr(d_pf), _lib.dptr(d_z), _lib.dptr(ws), ws.numel(), _lib.stream_ptr()))
-        return (d_pf, d_z, None, None, None, *grads)
+        return (d_pf, d_z, None, None, None, None, *grads)
 
 
 def _decoder_forward_train(self, past_feature, z, past_traj, cur_location, sample_num, mode):
@@ -461,7 +462,10 @@ def _decoder_forward_train(self, past_feature, z, past_traj, cur_location, sampl
         raise NotImplementedError("Decoder on B200: cur_location must be past_traj[:, -1]")      # no value check here: it would force a device sync
     x_true = past_traj.detach().repeat_interleave(sample_num, dim=0)
     pf = past_feature.reshape(x_true.shape[0], -1)
-    out, rec = _DecoderTrainFn.apply(pf, z.reshape(-1, 32), x_true, self.past_length, self.future_length, *_decompose_params(self))
+    # the tensor-core forward needs the weights re-split into fp16 hi/lo images whenever they change (every optimizer step): one
+    # repack serves both decoder passes of a step (the cache is keyed on the parameters' version counters)
+    packed = self._packed.get(self, self.past_length, self.future_length) if self.use_tensor_cores else None
+    out, rec = _DecoderTrainFn.apply(pf, z.reshape(-1, 32), x_true, self.past_length, self.future_length, packed, *_decompose_params(self))
     if mode == "inference":
         out = out.view(-1, sample_num, *out.shape[1:])
     return out, rec
