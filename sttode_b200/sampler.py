@@ -56,36 +56,33 @@ class Sampler(nn.Module):
         self.device = device
         self.to(device)
 
+    def _noise(self, agent_num):
+        """The N(0, I) draw of the non-mean path (sampler.py:40-46): one row shared by every (agent, sample) when `share_eps`, else one per agent."""
+        if self.eps_override is not None:
+            return self.eps_override.to(self.device)
+        if self.share_eps:
+            return torch.randn([1, self.nz]).to(self.device).repeat((agent_num * self.nk, 1))
+        return torch.randn([agent_num, self.nz]).to(self.device).repeat_interleave(self.nk, dim=0)
+
     def forward(self, net, mean=True, need_weights=False):
-        """-> (dec_motion [R, nk, T_f, 2], sampler_dist, vae_dist, net.pred_traj) (sampler.py:32-73)."""
-        agent_num = net.agent_num
+        """-> (dec_motion [R, nk, T_f, 2], sampler_dist, vae_dist, net.pred_traj) (sampler.py:32-73).
+
+        Drives the frozen STTODENet stage by stage: both encoders, then the K = 1 decode from the merged latent `q_c(.)` and the K = nk
+        decode from the nk per-agent latents themselves."""
         net.encode_history()
         net.fu_encoder()
-        history_enc = self.linear(net.past_feature)
-        if not mean:
-            if self.eps_override is not None:
-                eps = self.eps_override.to(self.device)
-            elif self.share_eps:
-                eps = torch.randn([1, self.nz]).to(self.device).repeat((agent_num * self.nk, 1))
-            else:
-                eps = torch.randn([agent_num, self.nz]).to(self.device).repeat_interleave(self.nk, dim=0)
-        qnet_h = self.q_mlp(history_enc)
-        A = self.q_A(qnet_h).view(-1, self.nz)
-        b = self.q_b(qnet_h).view(-1, self.nz)
-        z = b if mean else A * eps + b
-        z = self.q_c(z.view(-1, self.nk * self.nz)).view(-1, self.nz)
-        logvar = (A ** 2 + 1e-8).log()
-        sampler_dist = Normal(mu=b, logvar=logvar)
-        net.decoder_future_0(z)
-        p_z_s = b if mean else A * eps + b
-        net.decoder_future_1(p_z_s)
-        vae_dist = net.pz_dis
-        if self.args.dataset == "nba":
-            dec_motion = net.diverse_pred_traj
-        else:
+        hidden = self.q_mlp(self.linear(net.past_feature))
+        scale, shift = (head(hidden).view(-1, self.nz) for head in (self.q_A, self.q_b))              # A, b of z = A * eps + b
+        latents = shift if mean else scale * self._noise(net.agent_num) + shift                      # [R * nk, nz]
+        merged = self.q_c(latents.view(-1, self.nk * self.nz)).view(-1, self.nz)                      # [R, nz]
+        sampler_dist = Normal(mu=shift, logvar=(scale ** 2 + 1e-8).log())
+        net.decoder_future_0(merged)
+        net.decoder_future_1(latents)
+        dec_motion = net.diverse_pred_traj
+        if self.args.dataset != "nba":
             self.scene_orig = net.scene_orig
-            dec_motion = net.diverse_pred_traj + self.scene_orig
-        return dec_motion, sampler_dist, vae_dist, net.pred_traj
+            dec_motion = dec_motion + self.scene_orig
+        return dec_motion, sampler_dist, net.pz_dis, net.pred_traj
 
     def step_annealer(self):
         pass
