@@ -1176,8 +1176,10 @@ int sttode_forecast_host(const float* traj_host, int layout, const int* scene_pt
         for (int i = 0; i < HOST_MAX_CHUNKS; ++i) CUDA_TRY(cudaEventCreateWithFlags(&g_arena.done[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&g_arena.copied, cudaEventDisableTiming));
     }
-    // stage inputs in pinned memory (one H2D), build row->scene map on the host
-    memcpy(g_arena.pin_in, traj_host, traj_b);
+    // inputs: a page-locked trajectory buffer is the DMA source as it is; a pageable one is staged through the pinned arena.
+    // The CSR offsets and the row -> scene map (built here) always go through the arena.
+    const bool in_pinned = is_pinned(traj_host);
+    if (!in_pinned) memcpy(g_arena.pin_in, traj_host, traj_b);
     int *sp_h = nullptr, *rs_h = nullptr;
     if (scene_ptr_host) {
         sp_h = (int*)(g_arena.pin_in + align_up(traj_b));
@@ -1190,7 +1192,13 @@ int sttode_forecast_host(const float* traj_host, int layout, const int* scene_pt
         }
     }
     char* d = g_arena.dev;
-    CUDA_TRY(cudaMemcpyAsync(d, g_arena.pin_in, in_b, cudaMemcpyHostToDevice, st));
+    if (!in_pinned) {
+        CUDA_TRY(cudaMemcpyAsync(d, g_arena.pin_in, in_b, cudaMemcpyHostToDevice, st));
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(d, traj_host, traj_b, cudaMemcpyHostToDevice, st));
+        if (in_b > align_up(traj_b))
+            CUDA_TRY(cudaMemcpyAsync(d + align_up(traj_b), g_arena.pin_in + align_up(traj_b), in_b - align_up(traj_b), cudaMemcpyHostToDevice, st));
+    }
     const float* traj_d = (const float*)d;
     const int* sp_d = scene_ptr_host ? (const int*)(d + align_up(traj_b)) : nullptr;
     const int* rs_d = scene_ptr_host ? (const int*)(d + align_up(traj_b) + sp_b) : nullptr;
