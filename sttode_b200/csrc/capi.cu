@@ -720,8 +720,16 @@ int run_decoder(const float* past_feature, const float* traj_norm, const float* 
         else { CUDA_TRY(cudaEventCreate(&ev.first)); CUDA_TRY(cudaEventCreate(&ev.second)); }
         CUDA_TRY(cudaEventRecord(ev.first, st));
     }
+    // slices are whole waves of one CTA per SM, so only the last slice ends on a partial wave (as the unsliced launch does)
+    int sms = 148;
+    if (nch > 1) {
+        int dev = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int slice_tiles = nch > 1 ? ceil_div(ceil_div(pair_tiles, nch), sms) * sms : pair_tiles;
     for (int c = 0; c < nch; ++c) {
-        const int t0 = (int)((long long)pair_tiles * c / nch), t1 = (int)((long long)pair_tiles * (c + 1) / nch);
+        const int t0 = std::min(pair_tiles, c * slice_tiles), t1 = std::min(pair_tiles, (c + 1) * slice_tiles);
         if (t1 <= t0) continue;
         const int r0 = t0 * rpt, nr = std::min(rows, t1 * rpt) - r0;
         const float* tn_c = traj_norm + (size_t)r0 * Tp * 2;
