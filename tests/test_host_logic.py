@@ -123,3 +123,21 @@ def test_synth_is_deterministic():
     assert torch.equal(a, b) and a.shape == (7, 2, 8)
     d = synth.nba_batch(1, 4)
     assert d["past_traj"].shape == (4, 11, 10, 2) and d["future_traj"].shape == (4, 11, 20, 2)
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/sttode.h is a C ABI: it must compile as C99 (no C++ types, no default arguments), and a C translation unit that
+    references every declared entry point must link against the library."""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "sttode.h")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr], check=True)
+    src = tmp_path / "link_all.c"
+    names = declared_symbols()
+    src.write_text('#include "sttode.h"\n#include <stdio.h>\nint main(void) {\n  const void *p[] = {' + ", ".join(f"(const void *)&{n}" for n in names) +
+                   '};\n  printf("%d %d\\n", (int)(sizeof p / sizeof p[0]), sttode_version());\n  return 0;\n}\n')
+    exe = tmp_path / "link_all"
+    libdir = os.path.dirname(L.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", libdir, "-lsttode_sm100",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert int(out[0]) == len(names) and int(out[1]) == 100
