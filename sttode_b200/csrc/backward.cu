@@ -110,6 +110,24 @@ k_gemm(int M, int N, int K, const float* __restrict__ A, long sam, long sak, con
     }
 }
 
+// C[m,n] = epi(sum_z part[z][m][n]), z ascending, with k_gemm's epilogue (bias, ReLU, mask, residual, accumulate): second pass of a split-K product
+// whose output is too small to fill the GPU in one pass (a few hundred rows x K = 1024 in the ODE-block backward)
+__global__ void k_splitk_epilogue(const float* __restrict__ part, int slices, int M, int N, float* __restrict__ C, long ldc,
+                                  const float* __restrict__ bias, const float* __restrict__ res, long ldres, const float* __restrict__ mask,
+                                  long ldmask, int relu, int accumulate) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)M * N) return;
+    const int m = (int)(i / N), n = (int)(i - (long)m * N);
+    float v = 0.f;
+    for (int z = 0; z < slices; ++z) v += part[(long)z * M * N + i];
+    if (bias) v += __ldg(bias + n);
+    if (relu) v = fmaxf(v, 0.f);
+    if (mask && !(mask[(long)m * ldmask + n] > 0.f)) v = 0.f;
+    if (res) v += res[(long)m * ldres + n];
+    if (accumulate) v += C[(long)m * ldc + n];
+    C[(long)m * ldc + n] = v;
+}
+
 // out[i] += sum_s part[s * stride + i], s ascending (fixed order: the split-K weight gradients stay deterministic)
 __global__ void k_sum_slices(const float* __restrict__ part, int slices, long stride, long count, float* __restrict__ out) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;

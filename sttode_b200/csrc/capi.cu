@@ -234,35 +234,51 @@ size_t ode_ws_bytes(int rows, int L, int method) {
 
 // ---- backward of the MHGSA / ODE right-hand side (kernels in backward.cu) ----------------------------------
 // C[M,N] = epi(A . B) with arbitrary strides; see k_gemm.
+// Scratch for split-K products (few output tiles, long reduction): SPLITK_MAX slices of the largest weight gradient.
+constexpr int SPLITK_MAX = 64;
+constexpr size_t SPLITK_FLOATS = (size_t)SPLITK_MAX * 512 * 256;
+
 int gemm(cudaStream_t st, int M, int N, int K, const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C, long ldc,
          const float* bias = nullptr, const float* res = nullptr, long ldres = 0, const float* mask = nullptr, long ldmask = 0,
-         int relu = 0, int accumulate = 0) {
+         int relu = 0, int accumulate = 0, float* splitk = nullptr) {
+    const int tiles = ceil_div(N, 64) * ceil_div(M, 128);
+    if (splitk && tiles < 74 && K >= 256 && C != splitk) {
+        // too few output tiles to fill 148 SMs and a long reduction: split K over gridDim.z, then sum the slices in order and apply the epilogue
+        int slices = std::min(std::min(16, K / 64), ceil_div(296, tiles));
+        while (slices > 1 && (size_t)slices * M * N > SPLITK_FLOATS) --slices;
+        if (slices > 1) {
+            const int kchunk = ceil_div(ceil_div(K, slices), 16) * 16, nz = ceil_div(K, kchunk);
+            k_gemm<<<dim3(ceil_div(N, 64), ceil_div(M, 128), nz), 256, 0, st>>>(M, N, K, A, sam, sak, B, sbk, sbn, splitk, N, nullptr, nullptr, 0, nullptr, 0, 0, 0,
+                                                                              kchunk, (long)M * N);
+            LAUNCH_CHECK("k_gemm(split-K)");
+            k_splitk_epilogue<<<ceil_div(M * N, 256), 256, 0, st>>>(splitk, nz, M, N, C, ldc, bias, res, ldres, mask, ldmask, relu, accumulate);
+            LAUNCH_CHECK("k_splitk_epilogue");
+            return 0;
+        }
+    }
     k_gemm<<<dim3(ceil_div(N, 64), ceil_div(M, 128)), 256, 0, st>>>(M, N, K, A, sam, sak, B, sbk, sbn, C, ldc, bias, res, ldres, mask, ldmask,
                                                                    relu, accumulate, K, 0);
     LAUNCH_CHECK("k_gemm");
     return 0;
 }
-// Scratch for split-K weight gradients (tall products: few output tiles, thousands of rows): SPLITK_MAX slices of the largest dW.
-constexpr int SPLITK_MAX = 64;
-constexpr size_t SPLITK_FLOATS = (size_t)SPLITK_MAX * 512 * 256;
 // y[rows,N] = x[rows,K] . W[N,K]^T + b
 int gemm_nt(cudaStream_t st, int rows, int N, int K, const float* x, long ldx, const float* W, const float* b, float* y, long ldy,
-            int relu = 0, const float* res = nullptr, long ldres = 0) {
-    return gemm(st, rows, N, K, x, ldx, 1, W, 1, K, y, ldy, b, res, ldres, nullptr, 0, relu, 0);
+            int relu = 0, const float* res = nullptr, long ldres = 0, float* splitk = nullptr) {
+    return gemm(st, rows, N, K, x, ldx, 1, W, 1, K, y, ldy, b, res, ldres, nullptr, 0, relu, 0, splitk);
 }
 // dx[rows,K] = dy[rows,N] . W[N,K]  (+ res) (* mask)
 int gemm_nn(cudaStream_t st, int rows, int K, int N, const float* dy, long lddy, const float* W, float* dx, long lddx,
-            const float* res = nullptr, long ldres = 0, const float* mask = nullptr, long ldmask = 0, int accumulate = 0) {
-    return gemm(st, rows, K, N, dy, lddy, 1, W, K, 1, dx, lddx, nullptr, res, ldres, mask, ldmask, 0, accumulate);
+            const float* res = nullptr, long ldres = 0, const float* mask = nullptr, long ldmask = 0, int accumulate = 0, float* splitk = nullptr) {
+    return gemm(st, rows, K, N, dy, lddy, 1, W, K, 1, dx, lddx, nullptr, res, ldres, mask, ldmask, 0, accumulate, splitk);
 }
 // dW[N,K] += dy[rows,N]^T . x[rows,K];  db[N] += column sums of dy   (either may be null)
 int weight_grad(cudaStream_t st, int rows, int N, int K, const float* dy, long lddy, const float* x, long ldx, float* dW, float* db,
                 float* splitk = nullptr) {
     int rc;
     const int tiles = ceil_div(N, 128) * ceil_div(K, 64);
-    if (dW && splitk && rows >= 2048 && tiles < 296 && (size_t)N * K <= 512 * 256) {
+    if (dW && splitk && rows >= 256 && tiles < 148 && (size_t)N * K <= 512 * 256) {
         // rows split over gridDim.z so the launch fills the GPU; partial products summed in slice order (deterministic)
-        const int slices = std::min(SPLITK_MAX, std::min(ceil_div(rows, 256), ceil_div(592, tiles)));
+        const int slices = std::min(SPLITK_MAX, std::min(ceil_div(rows, 64), ceil_div(592, tiles)));
         const int kchunk = ceil_div(ceil_div(rows, slices), 16) * 16;
         const int nz = ceil_div(rows, kchunk);
         k_gemm<<<dim3(ceil_div(K, 64), ceil_div(N, 128), nz), 256, 0, st>>>(N, K, rows, dy, 1, lddy, x, ldx, 1, splitk, K, nullptr, nullptr, 0, nullptr, 0,
@@ -342,7 +358,7 @@ int attention_bwd(const float* xq, const float* xk, const float* xv, bool self_a
 
 size_t rhs_bwd_ws_bytes(int rows, int L) {
     const size_t r64 = align_up((size_t)rows * 64 * 4), rff = align_up((size_t)rows * STTODE_FF * 4);
-    return attn_bwd_ws_bytes(rows, rows, true) + 14 * r64 + 2 * rff + (L > 1 ? 0 : align_up((size_t)rows * 192 * 4));
+    return attn_bwd_ws_bytes(rows, rows, true) + 14 * r64 + 2 * rff + (L > 1 ? 0 : align_up((size_t)rows * 192 * 4)) + align_up(SPLITK_FLOATS * 4);
 }
 
 // dx = J_f(x)^T df for f = TransformerEncoder_ode.forward (or Hypattention.forward when gate_only), parameter gradients
@@ -352,6 +368,8 @@ int run_rhs_bwd(const float* x, const float* df, long lddf, int L, int bsz, int 
     int rc;
     const int R = nb * L * bsz;
     const int eb = ceil_div(R * 64, 256), wb = ceil_div(R, 8);
+    float* splitk = ws.take<float>(SPLITK_FLOATS);       // split-K partials: a few hundred rows leave most products with < 10 output tiles
+    if (!splitk) return fail(STTODE_EWORKSPACE, "workspace too small (split-K scratch)");
     // ---- forward re-materialisation
     AttnFwd f{};
     const float* o;
@@ -394,18 +412,18 @@ int run_rhs_bwd(const float* x, const float* df, long lddf, int L, int bsz, int 
         k_gate_ln_fwd<<<wb, 256, 0, st>>>(x, ui, ug, w.norm1_g, w.norm1_b, z1, s1, R);
         LAUNCH_CHECK("k_gate_ln_fwd");
         if ((rc = gemm_nt(st, R, STTODE_FF, 64, s1, 64, w.lin1_w, w.lin1_b, h1, STTODE_FF, 1))) return rc;
-        if ((rc = gemm_nt(st, R, 64, STTODE_FF, h1, STTODE_FF, w.lin2_w, w.lin2_b, z2, 64, 0, s1, 64))) return rc;
+        if ((rc = gemm_nt(st, R, 64, STTODE_FF, h1, STTODE_FF, w.lin2_w, w.lin2_b, z2, 64, 0, s1, 64, splitk))) return rc;
         // ---- backward: LN2, FFN, LN1
         k_ln_bwd<<<wb, 256, 0, st>>>(z2, w.norm2_g, df, lddf, dz2, tmp, R);
         LAUNCH_CHECK("k_ln_bwd");
         if (gw) {
             if ((rc = weight_grad(st, R, 64, 64, tmp, 64, nullptr, 0, nullptr, gw->norm2_g))) return rc;
             if ((rc = weight_grad(st, R, 64, 64, df, lddf, nullptr, 0, nullptr, gw->norm2_b))) return rc;
-            if ((rc = weight_grad(st, R, 64, STTODE_FF, dz2, 64, h1, STTODE_FF, gw->lin2_w, gw->lin2_b))) return rc;
+            if ((rc = weight_grad(st, R, 64, STTODE_FF, dz2, 64, h1, STTODE_FF, gw->lin2_w, gw->lin2_b, splitk))) return rc;
         }
         if ((rc = gemm_nn(st, R, STTODE_FF, 64, dz2, 64, w.lin2_w, dpre, STTODE_FF, nullptr, 0, h1, STTODE_FF))) return rc;   // * relu'
-        if (gw && (rc = weight_grad(st, R, STTODE_FF, 64, dpre, STTODE_FF, s1, 64, gw->lin1_w, gw->lin1_b))) return rc;
-        if ((rc = gemm_nn(st, R, 64, STTODE_FF, dpre, STTODE_FF, w.lin1_w, ds1, 64, dz2, 64))) return rc;
+        if (gw && (rc = weight_grad(st, R, STTODE_FF, 64, dpre, STTODE_FF, s1, 64, gw->lin1_w, gw->lin1_b, splitk))) return rc;
+        if ((rc = gemm_nn(st, R, 64, STTODE_FF, dpre, STTODE_FF, w.lin1_w, ds1, 64, dz2, 64, nullptr, 0, 0, splitk))) return rc;
         k_ln_bwd<<<wb, 256, 0, st>>>(z1, w.norm1_g, ds1, 64, dz1, tmp, R);
         LAUNCH_CHECK("k_ln_bwd");
         if (gw) {
@@ -418,12 +436,12 @@ int run_rhs_bwd(const float* x, const float* df, long lddf, int L, int bsz, int 
     k_gate_bwd<<<eb, 256, 0, st>>>(ui, ug, dg, lddg, dui, dug, R);
     LAUNCH_CHECK("k_gate_bwd");
     if (gw) {
-        if ((rc = weight_grad(st, R, 64, 64, dui, 64, a, 64, gw->info_w, gw->info_b))) return rc;
-        if ((rc = weight_grad(st, R, 64, 64, dug, 64, a, 64, gw->gate_w, gw->gate_b))) return rc;
+        if ((rc = weight_grad(st, R, 64, 64, dui, 64, a, 64, gw->info_w, gw->info_b, splitk))) return rc;
+        if ((rc = weight_grad(st, R, 64, 64, dug, 64, a, 64, gw->gate_w, gw->gate_b, splitk))) return rc;
     }
     if ((rc = gemm_nn(st, R, 64, 64, dui, 64, w.info_w, da, 64))) return rc;
     if ((rc = gemm_nn(st, R, 64, 64, dug, 64, w.gate_w, da, 64, nullptr, 0, nullptr, 0, 1))) return rc;
-    if (gw && (rc = weight_grad(st, R, 64, 64, da, 64, o, ldo, gw->attn.out_proj_w, gw->attn.out_proj_b))) return rc;
+    if (gw && (rc = weight_grad(st, R, 64, 64, da, 64, o, ldo, gw->attn.out_proj_w, gw->attn.out_proj_b, splitk))) return rc;
     if ((rc = gemm_nn(st, R, 64, 64, da, 64, w.attn.out_proj_w, d_o, 64))) return rc;
     // ---- attention + in-projection; the residual x -> z1 joins here (dz1), Hypattention alone has none
     if (L > 1) return attention_bwd(x, x, x, true, w.attn, gw ? &gw->attn : nullptr, f, d_o, L, L, bsz, nb, 1e-4f, dz1, 64, dx, nullptr, nullptr, ws, st);

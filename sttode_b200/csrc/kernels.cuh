@@ -30,6 +30,8 @@ __global__ void k_gemm(int M, int N, int K, const float* A, long sam, long sak, 
                        const float* bias, const float* res, long ldres, const float* mask, long ldmask, int relu, int accumulate, int kchunk,
                        long slice_stride);
 __global__ void k_colsum_part(const float* X, long ldx, int rows, int N, int rchunk, float* part);
+__global__ void k_splitk_epilogue(const float* part, int slices, int M, int N, float* C, long ldc, const float* bias, const float* res, long ldres,
+                                  const float* mask, long ldmask, int relu, int accumulate);
 __global__ void k_sum_slices(const float* part, int slices, long stride, long count, float* out);
 __global__ void k_colsum(const float* X, long ldx, int rows, int N, float* out);
 __global__ void k_gate_ln_fwd(const float* x, const float* ui, const float* ug, const float* gamma, const float* beta, float* z1,
