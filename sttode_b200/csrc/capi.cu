@@ -529,11 +529,11 @@ int take_block(Carver& ws, size_t P, int Tp, DecBlockSaved* b) {
 }
 
 // a1 = relu(feat W0^T + b0), a2 = relu(a1 W1^T + b1), out = a2 W2^T + b2 (out nullable: only the activations are needed)
-int mlp3_fwd(cudaStream_t st, int P, const sttode_mlp3_weights& w, int n3, const float* feat, float* a1, float* a2, float* out) {
+int mlp3_fwd(cudaStream_t st, int P, const sttode_mlp3_weights& w, int n3, const float* feat, float* a1, float* a2, float* out, float* splitk) {
     int rc;
-    if ((rc = gemm_nt(st, P, 512, 256, feat, 256, w.w0, w.b0, a1, 512, 1))) return rc;
-    if ((rc = gemm_nt(st, P, 256, 512, a1, 512, w.w1, w.b1, a2, 256, 1))) return rc;
-    if (out && (rc = gemm_nt(st, P, n3, 256, a2, 256, w.w2, w.b2, out, n3))) return rc;
+    if ((rc = gemm_nt(st, P, 512, 256, feat, 256, w.w0, w.b0, a1, 512, 1, nullptr, 0, splitk))) return rc;
+    if ((rc = gemm_nt(st, P, 256, 512, a1, 512, w.w1, w.b1, a2, 256, 1, nullptr, 0, splitk))) return rc;
+    if (out && (rc = gemm_nt(st, P, n3, 256, a2, 256, w.w2, w.b2, out, n3, 0, nullptr, 0, splitk))) return rc;
     return 0;
 }
 // dfeat (+)= J^T dout through the 3-layer MLP; parameter gradients accumulated into g
@@ -543,9 +543,9 @@ int mlp3_bwd(cudaStream_t st, int P, const sttode_mlp3_weights& w, const sttode_
     if ((rc = weight_grad(st, P, n3, 256, dout, n3, a2, 256, g.w2, g.b2, splitk))) return rc;
     if ((rc = gemm_nn(st, P, 256, n3, dout, n3, w.w2, da2, 256, nullptr, 0, a2, 256))) return rc;           // * relu'
     if ((rc = weight_grad(st, P, 256, 512, da2, 256, a1, 512, g.w1, g.b1, splitk))) return rc;
-    if ((rc = gemm_nn(st, P, 512, 256, da2, 256, w.w1, da1, 512, nullptr, 0, a1, 512))) return rc;
+    if ((rc = gemm_nn(st, P, 512, 256, da2, 256, w.w1, da1, 512, nullptr, 0, a1, 512, 0, splitk))) return rc;
     if ((rc = weight_grad(st, P, 512, 256, da1, 512, feat, 256, g.w0, g.b0, splitk))) return rc;
-    return gemm_nn(st, P, 256, 512, da1, 512, w.w0, dfeat, 256, nullptr, 0, nullptr, 0, accumulate);
+    return gemm_nn(st, P, 256, 512, da1, 512, w.w0, dfeat, 256, nullptr, 0, nullptr, 0, accumulate, splitk);
 }
 
 // Conv1d+ReLU -> GRU -> feat = [pf | z | h_T] for one block; x_hat (nullable) = previous block's reconstruction
@@ -586,13 +586,13 @@ int dec_block_bwd(cudaStream_t st, int P, int Tp, const sttode_decompose_weights
         k_gru_step_bwd<<<ceil_div(P * 96, 256), 256, 0, st>>>(dh, b.rzn + (size_t)t * P * 288, b.ghn + (size_t)t * P * 96, b.h + (size_t)t * P * 96, P,
                                                               dgi + (size_t)t * 288, (long)Tp * 288, dght, dh2);
         LAUNCH_CHECK("k_gru_step_bwd");
-        if ((rc = gemm_nn(st, P, 96, 288, dght, 288, w.gru_w_hh, dh2, 96, nullptr, 0, nullptr, 0, 1))) return rc;      // += d gh W_hh
+        if ((rc = gemm_nn(st, P, 96, 288, dght, 288, w.gru_w_hh, dh2, 96, nullptr, 0, nullptr, 0, 1, splitk))) return rc;      // += d gh W_hh
         std::swap(dh, dh2);
     }
     // h_0 .. h_{T-1} and d gh_0 .. d gh_{T-1} are contiguous [T*P, .] stacks: one product for the recurrent weight
     if ((rc = weight_grad(st, Tp * P, 288, 96, dgh, 288, b.h, 96, g.gru_w_hh, g.gru_b_hh, splitk))) return rc;
     if ((rc = weight_grad(st, PT, 288, 32, dgi, 288, b.c, 32, g.gru_w_ih, g.gru_b_ih, splitk))) return rc;
-    if ((rc = gemm_nn(st, PT, 32, 288, dgi, 288, w.gru_w_ih, dc, 32, nullptr, 0, b.c, 32))) return rc;                 // * relu'(conv)
+    if ((rc = gemm_nn(st, PT, 32, 288, dgi, 288, w.gru_w_ih, dc, 32, nullptr, 0, b.c, 32, 0, splitk))) return rc;      // * relu'(conv)
     if ((rc = weight_grad(st, PT, 32, 6, dc, 32, b.col, 6, g.conv_w, g.conv_b, splitk))) return rc;
     if (dcol && (rc = gemm_nn(st, PT, 6, 32, dc, 32, w.conv_w, dcol, 6))) return rc;
     return 0;
@@ -620,11 +620,11 @@ int run_decoder_bwd(const float* pf, const float* z, const float* x_true, const 
     if (!ws.ok() || !dxh0 || !splitk) return fail(STTODE_EWORKSPACE, "workspace too small for the decoder backward (%zu B given)", ws.size);
     // ---- forward re-materialisation (model/STTODE.py:336-339)
     if ((rc = dec_block_fwd(st, P, Tp, w->dec[0], pf, z, x_true, nullptr, gh, b0))) return rc;
-    if ((rc = mlp3_fwd(st, P, w->dec[0].dec_x, 2 * Tp, b0.feat, b0.ax1, b0.ax2, b0.xh))) return rc;
-    if ((rc = mlp3_fwd(st, P, w->dec[0].dec_y, 2 * Tf, b0.feat, b0.ay1, b0.ay2, nullptr))) return rc;
+    if ((rc = mlp3_fwd(st, P, w->dec[0].dec_x, 2 * Tp, b0.feat, b0.ax1, b0.ax2, b0.xh, splitk))) return rc;
+    if ((rc = mlp3_fwd(st, P, w->dec[0].dec_y, 2 * Tf, b0.feat, b0.ay1, b0.ay2, nullptr, splitk))) return rc;
     if ((rc = dec_block_fwd(st, P, Tp, w->dec[1], pf, z, x_true, b0.xh, gh, b1))) return rc;
-    if ((rc = mlp3_fwd(st, P, w->dec[1].dec_y, 2 * Tf, b1.feat, b1.ay1, b1.ay2, nullptr))) return rc;
-    if (d_recon && (rc = mlp3_fwd(st, P, w->dec[1].dec_x, 2 * Tp, b1.feat, b1.ax1, b1.ax2, nullptr))) return rc;
+    if ((rc = mlp3_fwd(st, P, w->dec[1].dec_y, 2 * Tf, b1.feat, b1.ay1, b1.ay2, nullptr, splitk))) return rc;
+    if (d_recon && (rc = mlp3_fwd(st, P, w->dec[1].dec_x, 2 * Tp, b1.feat, b1.ax1, b1.ax2, nullptr, splitk))) return rc;
     // ---- block 1: prediction += y_hat1, reconstruction += x_hat1 (train mode)
     if ((rc = mlp3_bwd(st, P, w->dec[1].dec_y, g[1].dec_y, 2 * Tf, d_pred, b1.feat, b1.ay1, b1.ay2, da1, da2, dfeat1, 0, splitk))) return rc;
     if (d_recon && (rc = mlp3_bwd(st, P, w->dec[1].dec_x, g[1].dec_x, 2 * Tp, d_recon, b1.feat, b1.ax1, b1.ax2, da1, da2, dfeat1, 1, splitk))) return rc;
