@@ -291,6 +291,10 @@ def run_ours(args):
     roofline = {"kernel": "k_dec_pair_tc" if tc else "k_dec_pair", "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                 "traffic": DRAM_BYTES_PER_PAIR * pairs, "traffic_source": "profiles/r01_ncu_full_k_dec_pair_tc.md: dram read+write per 268 800-pair launch, scaled by pairs",
                 "peak_source": peak_src, "kernel_ms": ker_ms, "kernel_share_of_step": ker_ms / (ms / args.steps),
+                "hbm": {"achieved_gbs": DRAM_BYTES_PER_PAIR * pairs / (ker_ms * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs", 6548.2),
+                        "frac": DRAM_BYTES_PER_PAIR * pairs / (ker_ms * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6548.2),
+                        "note": "shown to document that HBM is not the limiter of this kernel (SURVEY.md §8d)"},
+                "tensor_ops_issued_frac": 3 * ach / peak_tf,        # 3 tensor-core MACs per algorithmic MAC: share of the tensor pipe's sustained rate
                 "flops_per_launch_issued": issued_flops_dec_pair(TP, TF) * pairs,
                 "note": ("tcgen05 kind::f16 with the 3xFP16 hi/lo split (fp32-accurate; SURVEY finding 9 rules out single-pass 16/19-bit inputs): "
                          "3 tensor-core MACs per algorithmic MAC, so the attainable ceiling is peak/3; " if tc else "FP32 FFMA kernel; ") +
