@@ -3,7 +3,8 @@
 Same function names and keyword-only curvature `c`; each call is one kernel of csrc/pmath.cu through the
 C ABI.  The reference never calls these on a live path (SURVEY.md finding 3); they are provided as the
 parity-checked library `north_star` names plus the optional Poincare score mode of the MHGSA kernel.
-float32 CUDA tensors only; no autograd in round 1.
+float32 CUDA tensors only.  `artanh` / `arsinh` carry the reference's custom autograd rules (`Artanh`, `Arsinh`, pmath.py:16-27,51-60) and
+`RiemannianGradient` (:30-45) is provided; the other functions are forward-only.
 """
 import numpy as np
 import torch
@@ -44,12 +45,56 @@ def tanh(x, clamp=15):
     return _elem("sttode_pmath_tanh", x, float(clamp))
 
 
+class Artanh(torch.autograd.Function):
+    """artanh(clamp(x, +-(1 - 1e-5))) with the reference's backward g / (1 - x_clamped^2) (pmath.py:16-27): the gradient passes through the
+    clamp, unlike torch.clamp's own rule."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x.detach().clamp(-1 + 1e-5, 1 - 1e-5))
+        return _elem("sttode_pmath_artanh", x)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        (xc,) = ctx.saved_tensors
+        return grad_output / (1 - xc ** 2)
+
+
+class Arsinh(torch.autograd.Function):
+    """log(clamp_min(x + sqrt(1 + x^2), 1e-5)) with backward g / sqrt(1 + x^2) (pmath.py:51-60)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x.detach())
+        return _elem("sttode_pmath_arsinh", x)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        (x,) = ctx.saved_tensors
+        return grad_output / (1 + x ** 2) ** 0.5
+
+
+class RiemannianGradient(torch.autograd.Function):
+    """Identity whose backward rescales the Euclidean gradient to the Riemannian one: g * (1 - c |x|^2)^2 / 4 (pmath.py:30-45)."""
+    c = 1
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        (x,) = ctx.saved_tensors
+        return grad_output * ((1 - RiemannianGradient.c * x.pow(2).sum(-1, keepdim=True)).pow(2) / 4)
+
+
 def artanh(x):
-    return _elem("sttode_pmath_artanh", x)
+    return Artanh.apply(x)
 
 
 def arsinh(x):
-    return _elem("sttode_pmath_arsinh", x)
+    return Arsinh.apply(x)
 
 
 def project(x, *, c=1.0):

@@ -579,3 +579,21 @@ def test_future_encoder_and_training_objective_vs_reference(golden, dev):
     past = data["past_traj"].view(B * 11, tp, 2)
     ref = O.training_objective(sd, past, data["future_traj"].view(B * 11, tf, 2), B, 11, eps_q, eps_p)
     assert abs(float(total) - ref["total"]) <= TOL * abs(ref["total"])
+
+
+def test_pmath_autograd_rules(dev):
+    """Artanh / Arsinh / RiemannianGradient carry the reference's custom backward rules (hyptorch/pmath.py:16-60)."""
+    from sttode_b200 import pmath as P
+    u = torch.tensor([-1.5, -0.99999, -0.5, 0.0, 0.3, 0.99998, 2.0], device=dev, requires_grad=True)
+    g = torch.linspace(0.5, 2.0, 7, device=dev)
+    P.artanh(u).backward(g)
+    uc = u.detach().clamp(-1 + 1e-5, 1 - 1e-5)
+    assert torch.allclose(u.grad, g / (1 - uc ** 2), rtol=1e-6)             # passes through the clamp, as upstream
+    s = torch.linspace(-20, 20, 9, device=dev, requires_grad=True)
+    gs = torch.ones(9, device=dev)
+    P.arsinh(s).backward(gs)
+    assert torch.allclose(s.grad, 1 / torch.sqrt(1 + s.detach() ** 2), rtol=1e-6)
+    x = (torch.randn(5, 8, generator=torch.Generator().manual_seed(2)) * 0.2).to(dev).requires_grad_(True)
+    w = torch.randn(5, 8, generator=torch.Generator().manual_seed(3)).to(dev)
+    (P.RiemannianGradient.apply(x) * w).sum().backward()
+    assert torch.allclose(x.grad, w * (1 - x.detach().pow(2).sum(-1, keepdim=True)).pow(2) / 4, rtol=1e-6)
