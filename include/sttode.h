@@ -277,6 +277,13 @@ int sttode_forecast_host(const float *traj_host, int layout, const int *scene_pt
                          float *pred_host, void *stream);
 void sttode_release_host_arena(void);
 
+/* The latent the decoder kernels draw when `z` is NULL (the reference's `torch.randn_like`, model/STTODE.py:609-616), written out:
+ * z[n_pairs, 32] for pairs pair_base .. pair_base + n_pairs - 1 of a batch, seed as passed to sttode_forecast / sttode_decoder_fwd
+ * (plus *rng_state when given).  Same device function as the decoder kernels, so the un-injected path is verifiable:
+ * forecast(z = NULL, seed) == forecast(z = this output), and the draw's statistics can be tested directly. */
+int sttode_latent_draw(unsigned long long seed, unsigned long long pair_base, const unsigned long long *rng_state_or_null,
+                       size_t n_pairs, float *z, void *stream);
+
 /* ---- min-over-K ADE/FDE on device (utils/metrics.py:7-26; test.py:204-208): sums[0] += sum_agents minADE,
  * sums[1] += sum_agents minFDE, sums[2] += rows  (double[3], device; AverageMeter numerators). */
 int sttode_min_ade_fde(const float *pred, const float *gt, int gt_layout, int rows, int sample_k, int future_length,

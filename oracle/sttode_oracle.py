@@ -236,10 +236,10 @@ def training_objective(sd, past_traj, future_traj, B, N, eps_q, eps_p, min_clip=
 def gru_last_state(x, w_ih, w_hh, b_ih, b_hh, fast=False):
     """nn.GRU(batch_first=True) final hidden state, h0 = 0 (model/STTODE.py:31,68-69).  x [rows,T,C]."""
     if fast:       # the ATen entry point nn.GRU itself dispatches to (used for CPU-baseline timing)
-        h0 = torch.zeros(1, x.shape[0], w_hh.shape[1], dtype=x.dtype)
+        h0 = torch.zeros(1, x.shape[0], w_hh.shape[1], dtype=x.dtype, device=x.device)
         return torch._VF.gru(x, h0, [w_ih, w_hh, b_ih, b_hh], True, 1, 0.0, False, False, True)[1].squeeze(0)
     Hn = w_hh.shape[1]
-    h = torch.zeros(x.shape[0], Hn, dtype=x.dtype)
+    h = torch.zeros(x.shape[0], Hn, dtype=x.dtype, device=x.device)
     for t in range(x.shape[1]):
         gi = F.linear(x[:, t], w_ih, b_ih)
         gh = F.linear(h, w_hh, b_hh)
@@ -279,8 +279,8 @@ def decoder(past_feature_rep, z, past_traj, cur_location, sample_num, sd, mode="
     hidden = torch.cat((past_feature_rep.view(-1, sample_num, past_feature_rep.shape[-1]),
                         z.view(-1, sample_num, z.shape[-1])), dim=-1).view(rows_k, -1)
     x_hat = torch.zeros_like(x_true)
-    pred = torch.zeros(rows_k, future_len, 2, dtype=x_true.dtype)
-    rec = torch.zeros(rows_k, past_len, 2, dtype=x_true.dtype)
+    pred = torch.zeros(rows_k, future_len, 2, dtype=x_true.dtype, device=x_true.device)
+    rec = torch.zeros(rows_k, past_len, 2, dtype=x_true.dtype, device=x_true.device)
     for i in range(2):
         x_hat, y_hat, state = decompose_block(x_true, x_hat, hidden, sd, f"decoder.decompose.{i}.",
                                               past_len, future_len, fast=fast)

@@ -104,6 +104,7 @@ SIGNATURES = {
     "sttode_forecast": (_I, [_V, _I, _V, _V, _I, _I, _I, _I, _V, _U64, _I, C.POINTER(ModelWeights), _V, _V, _V, _V, _V, _Z, _V]),
     "sttode_forecast_host": (_I, [_V, _I, _V, _I, _I, _I, _I, _U64, _I, C.POINTER(ModelWeights), _V, _V]),
     "sttode_release_host_arena": (None, []),
+    "sttode_latent_draw": (_I, [_U64, _U64, _V, _Z, _V, _V]),
     "sttode_min_ade_fde": (_I, [_V, _V, _I, _I, _I, _I, _V, _V]),
     "sttode_oblique_proj": (_I, [_V, _V, _I, _I, _V]),
     "sttode_oblique_dist": (_I, [_V, _V, _V, _I, _I, _I, _I, _F, _V]),

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsttode_sm100.so")
-SOURCES = ["encoder.cu", "backward.cu", "decoder.cu", "decoder_tc.cu", "pmath.cu", "tc_selftest.cu", "capi.cu"]
+SOURCES = ["encoder.cu", "backward.cu", "decoder.cu", "decoder_tc.cu", "pmath.cu", "tc_selftest.cu", "capi.cu"]      # + new files: keep in sync with csrc/
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "kernels.cuh"), os.path.join(CSRC, "tc.cuh"),
            os.path.join(os.path.dirname(HERE), "include", "sttode.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -24,12 +24,29 @@ def _nvcc():
     return "nvcc"
 
 
+HASH_PATH = LIB_PATH + ".srchash"
+
+
+def source_hash():
+    """sha256 over every source, header and compiler flag that goes into the library."""
+    import hashlib
+    h = hashlib.sha256()
+    for path in [os.path.join(CSRC, s) for s in SOURCES] + HEADERS:
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(os.environ.get("STTODE_TC_TIMELINE", "").encode())
+    return h.hexdigest()
+
+
 def is_stale():
-    if not os.path.isfile(LIB_PATH):
+    """True when the .so is missing or was built from other sources (recorded source hash differs; mtimes are not trusted —
+    the .so is git-ignored and ships prebuilt with the snapshot)."""
+    if not os.path.isfile(LIB_PATH) or not os.path.isfile(HASH_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(HASH_PATH) as f:
+        return f.read().strip() != source_hash()
 
 
 def build(force=False, verbose=False):
@@ -43,6 +60,8 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
+    with open(HASH_PATH, "w") as f:
+        f.write(source_hash() + "\n")
     return LIB_PATH
 
 

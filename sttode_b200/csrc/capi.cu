@@ -1093,52 +1093,9 @@ int sttode_decoder_pack(const sttode_model_weights* w, void* packed, size_t pack
             return fail(STTODE_EUNSUPPORTED, "tensor-core decoder: 2 * max(past_length, future_length) must be <= 48 (got %d / %d); use the FP32 decoder (dec_packed = NULL)",
                         w->past_length, w->future_length);
     if (packed_bytes < (size_t)L.total + 256) return fail(STTODE_EWORKSPACE, "packed buffer too small: %zu < %u", packed_bytes, L.total + 256);
-    unsigned char* pk = (unsigned char*)packed;
-    auto image = [&](const float* W, int ldw, int row0, int col0, int nvalid, int nrows, int K, size_t hi_off, size_t lo_off) {
-        const int n = (K >> 3) * nrows;
-        k_pack_image<<<ceil_div(n, 128), 128, 0, st>>>(W, ldw, row0, col0, nvalid, nrows, K, pk + hi_off, pk + lo_off);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-    };
-    const sttode_mlp3_weights* mlps[4] = {&w->dec[0].dec_x, &w->dec[0].dec_y, &w->dec[1].dec_y, &w->dec[1].dec_x};
-    for (int m = 0; m < 4; ++m) {
-        const int K1 = (int)L.k1[m], n3 = (int)L.n3[m], n3p = (int)L.n3p[m];
-        const size_t w1sz = 64 * (size_t)K1, lead_hi = L.mlp_off[m], lead_lo = lead_hi + L.lead_blk[m], chunk0 = lead_hi + 2 * (size_t)L.lead_blk[m];
-        auto layer1_rows = [&](int c, size_t hi, size_t lo) {     // layer-1 rows of chunk c (hidden units 32c..32c+31), pair columns 128..128+K1
-            image(mlps[m]->w0, 256, c * 32, 128, 32, 32, K1, hi, lo);
-        };
-        layer1_rows(0, lead_hi, lead_lo);
-        layer1_rows(1, lead_hi + w1sz, lead_lo + w1sz);
-        for (int c = 0; c < 16; ++c) {          // chunk c: block 2c holds the hi images, 2c+1 the lo images of [W2[:, 32c..] | W1 rows of chunk c+2]
-            const size_t ba = chunk0 + (size_t)(2 * c) * L.mlp_blk[m], bb = ba + L.mlp_blk[m];
-            image(mlps[m]->w1, 512, 0, c * 32, 256, 256, 32, ba, bb);
-            if (c < 14) layer1_rows(c + 2, ba + 16384, bb + 16384);
-            else {
-                CUDA_TRY(cudaMemsetAsync(pk + ba + 16384, 0, w1sz, st));
-                CUDA_TRY(cudaMemsetAsync(pk + bb + 16384, 0, w1sz, st));
-            }
-        }
-        for (int p = 0; p < 8; ++p) {
-            const size_t pc = L.l3_off[m] + (size_t)(p >> 2) * L.l3_blk[m] + (size_t)(p & 3) * n3p * 128;
-            image(mlps[m]->w2, 256, 0, p * 32, n3, n3p, 32, pc, pc + n3p * 64);
-        }
-    }
-    for (int g = 0; g < 2; ++g)
-        for (int kb = 0; kb < 8; ++kb) {
-            const size_t blk = L.gru_off[g] + (size_t)kb * TC_GRU_BLK;
-            if (kb < 2) image(w->dec[g].gru_w_ih, 32, 0, kb * 16, 288, 288, 16, blk, blk + 9216);
-            else        image(w->dec[g].gru_w_hh, 96, 0, (kb - 2) * 16, 288, 288, 16, blk, blk + 9216);
-        }
-    {   // row kernel: tile j = (product p = j/2, columns (j&1)*256..): K slabs over [pf 0..127 | state 160..255] (p < 2) or pf only
-        const sttode_mlp3_weights* prod[4] = {&w->dec[0].dec_x, &w->dec[0].dec_y, &w->dec[1].dec_y, &w->dec[1].dec_x};
-        size_t blk = L.rowp_off;
-        for (int j = 0; j < 8; ++j) {
-            const int p = j >> 1, nb = j & 1, nks = j < 4 ? 14 : 8;
-            for (int ks = 0; ks < nks; ++ks, blk += 16384)
-                image(prod[p]->w0, 256, nb * 256, ks < 8 ? ks * 16 : 160 + (ks - 8) * 16, 256, 256, 16, blk, blk + 8192);
-        }
-    }
-    CUDA_TRY(cudaMemsetAsync(pk + L.total, 0, 256, st));
-    CUDA_TRY(cudaGetLastError());
+    // every operand image of the pack in ONE launch (job list derived in-kernel from the layout): graph-capturable, no memsets
+    launch_pack_all(w->dec[0], w->dec[1], L, (unsigned char*)packed, st);
+    LAUNCH_CHECK("k_pack_all");
     return 0;
 }
 
@@ -1211,11 +1168,13 @@ int sttode_forecast_host(const float* traj_host, int layout, const int* scene_pt
         sp_h = (int*)(g_arena.pin_in + align_up(traj_b));
         rs_h = (int*)(g_arena.pin_in + align_up(traj_b) + sp_b);
         memcpy(sp_h, scene_ptr_host, (size_t)(n_scenes + 1) * 4);
-        if (sp_h[0] != 0 || sp_h[n_scenes] != rows) return fail(STTODE_EINVAL, "scene_ptr must start at 0 and end at rows");
-        for (int s = 0; s < n_scenes; ++s) {
-            if (sp_h[s + 1] <= sp_h[s]) return fail(STTODE_EINVAL, "scene %d is empty", s);
+        // validate every offset BEFORE the fill loop below writes rs_h[r]: an interior offset above `rows` would write past the arena
+        if (n_scenes <= 0 || sp_h[0] != 0 || sp_h[n_scenes] != rows) return fail(STTODE_EINVAL, "scene_ptr must start at 0 and end at rows");
+        for (int s = 0; s < n_scenes; ++s)
+            if (sp_h[s] < 0 || sp_h[s + 1] <= sp_h[s] || sp_h[s + 1] > rows)
+                return fail(STTODE_EINVAL, "scene_ptr[%d..%d] = %d..%d is not strictly increasing within [0, rows = %d]", s, s + 1, sp_h[s], sp_h[s + 1], rows);
+        for (int s = 0; s < n_scenes; ++s)
             for (int r = sp_h[s]; r < sp_h[s + 1]; ++r) rs_h[r] = s;
-        }
     }
     char* d = g_arena.dev;
     if (!in_pinned) {
@@ -1235,12 +1194,22 @@ int sttode_forecast_host(const float* traj_host, int layout, const int* scene_pt
     CopyOut co{out_pinned ? (char*)pred_host : g_arena.pin_out, g_arena.copy_stream, g_arena.done,
                (int)std::max<size_t>(1, std::min<size_t>(HOST_MAX_CHUNKS, pred_b / (12u << 20)))};
     if ((rc = forecast_impl(traj_d, layout, sp_d, rs_d, n_scenes, rows, L, agents, nullptr, seed, sample_k, w, pred_d, nullptr, nullptr, nullptr, ws_d, ws_b,
-                            st, &co)))
+                            st, &co))) {
+        cudaStreamSynchronize(st);                  // the H2D copies above read the shared arena: drain them before the lock is released
+        cudaStreamSynchronize(g_arena.copy_stream);
         return rc;
+    }
     CUDA_TRY(cudaEventRecord(g_arena.copied, g_arena.copy_stream));
     CUDA_TRY(cudaStreamWaitEvent(st, g_arena.copied, 0));                         // the caller's stream stays the single completion point
     CUDA_TRY(cudaStreamSynchronize(st));
     if (!out_pinned) memcpy(pred_host, g_arena.pin_out, pred_b);
+    return 0;
+}
+
+int sttode_latent_draw(unsigned long long seed, unsigned long long pair_base, const unsigned long long* rng_state, size_t n_pairs, float* z, void* stream) {
+    if (!z || n_pairs == 0) return fail(STTODE_EINVAL, "latent_draw: null pointer / no pairs");
+    k_latent_draw<<<(unsigned)((n_pairs * 8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(seed, pair_base, rng_state, n_pairs, z);
+    LAUNCH_CHECK("k_latent_draw");
     return 0;
 }
 

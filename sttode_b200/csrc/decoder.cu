@@ -342,6 +342,18 @@ k_dec_pair(const float* __restrict__ traj_norm, const float* __restrict__ z, uns
 
 __global__ void k_bump_counter(unsigned long long* p) { *p += 1ull; }
 
+// The latent z the decoder kernels draw for (seed, pair) when no z is injected, written out: z[pair][4q..4q+3] = latent_normal4(seed', pair_base + pair, q),
+// seed' = seed + *rng_state.  Same device function as k_dec_pair / k_dec_pair_tc call, so a test can check the draw itself (moments, independence)
+// and feed exactly these values to the oracle (sttode_latent_draw).
+__global__ void k_latent_draw(unsigned long long seed, unsigned long long pair_base, const unsigned long long* __restrict__ rng_state, size_t n_pairs,
+                              float* __restrict__ z) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pairs * 8) return;
+    if (rng_state) seed += *rng_state;
+    const size_t pair = i >> 3;
+    *reinterpret_cast<float4*>(z + i * 4) = latent_normal4(seed, pair_base + pair, (unsigned)(i & 7));
+}
+
 size_t dec_pair_smem_bytes(int Tp, int Tf) {
     const int Tm = Tp > Tf ? Tp : Tf;
     return sizeof(float) * ((size_t)BM * LDZ + PAIR_REGION + (size_t)BM * (2 * Tm + 1)) + sizeof(int) * BM;

@@ -54,6 +54,77 @@ DecPackLayout dec_pack_layout(int Tp, int Tf) {
     return L;
 }
 
+// ---- all weight images of one pack in ONE launch ------------------------------------------------------------------------------
+// Job j (blockIdx.y) is one operand image; the job list is a closed-form function of the layout, so nothing but the weight pointers
+// and the layout travels to the device (round 1 issued 264 single-image launches + 8 memsets per pack).
+struct PackJob { const float* W; int ldw, row0, col0, nvalid, nrows, K; uint32_t hi, lo; };
+constexpr int PACK_JOBS_MLP = 42, PACK_JOBS = 4 * PACK_JOBS_MLP + 16 + 88 + 1;
+
+__device__ __forceinline__ PackJob pack_job(int j, const sttode_decompose_weights& w0, const sttode_decompose_weights& w1, const DecPackLayout& L) {
+    PackJob J{};
+    if (j < 4 * PACK_JOBS_MLP) {
+        const int m = j / PACK_JOBS_MLP, i = j - m * PACK_JOBS_MLP;
+        const sttode_mlp3_weights& mw = m == 0 ? w0.dec_x : m == 1 ? w0.dec_y : m == 2 ? w1.dec_y : w1.dec_x;
+        const int K1 = (int)L.k1[m], n3 = (int)L.n3[m], n3p = (int)L.n3p[m];
+        const uint32_t w1sz = 64u * (uint32_t)K1, lead_hi = L.mlp_off[m], lead_lo = lead_hi + L.lead_blk[m], chunk0 = lead_hi + 2 * L.lead_blk[m];
+        auto layer1 = [&](int c, uint32_t hi, uint32_t lo) {       // layer-1 rows of chunk c (hidden units 32c..), pair columns 128..128+K1; c >= 16: zeros
+            J = PackJob{mw.w0, 256, c * 32, 128, c < 16 ? 32 : 0, 32, K1, hi, lo};
+        };
+        if (i < 2) layer1(i, lead_hi + i * w1sz, lead_lo + i * w1sz);
+        else if (i < 34) {
+            const int c = (i - 2) >> 1;
+            const uint32_t ba = chunk0 + (uint32_t)(2 * c) * L.mlp_blk[m], bb = ba + L.mlp_blk[m];
+            if (!((i - 2) & 1)) J = PackJob{mw.w1, 512, 0, c * 32, 256, 256, 32, ba, bb};
+            else layer1(c + 2, ba + 16384, bb + 16384);
+        } else {
+            const int p = i - 34;
+            const uint32_t pc = L.l3_off[m] + (uint32_t)(p >> 2) * L.l3_blk[m] + (uint32_t)(p & 3) * n3p * 128;
+            J = PackJob{mw.w2, 256, 0, p * 32, n3, n3p, 32, pc, pc + (uint32_t)n3p * 64};
+        }
+        return J;
+    }
+    j -= 4 * PACK_JOBS_MLP;
+    if (j < 16) {
+        const int g = j >> 3, kb = j & 7;
+        const sttode_decompose_weights& w = g ? w1 : w0;
+        const uint32_t blk = L.gru_off[g] + (uint32_t)kb * TC_GRU_BLK;
+        if (kb < 2) J = PackJob{w.gru_w_ih, 32, 0, kb * 16, 288, 288, 16, blk, blk + 9216};
+        else        J = PackJob{w.gru_w_hh, 96, 0, (kb - 2) * 16, 288, 288, 16, blk, blk + 9216};
+        return J;
+    }
+    j -= 16;
+    if (j < 88) {   // row kernel: tile t = (product p = t/2, columns (t&1)*256..): K slabs over [pf 0..127 | state 160..255] (p < 2) or pf only
+        int t, ks;
+        if (j < 56) { t = j / 14; ks = j - t * 14; } else { t = 4 + (j - 56) / 8; ks = (j - 56) & 7; }
+        const int p = t >> 1, nb = t & 1;
+        const sttode_mlp3_weights& mw = p == 0 ? w0.dec_x : p == 1 ? w0.dec_y : p == 2 ? w1.dec_y : w1.dec_x;
+        const uint32_t blk = L.rowp_off + (uint32_t)j * 16384;
+        J = PackJob{mw.w0, 256, nb * 256, ks < 8 ? ks * 16 : 160 + (ks - 8) * 16, 256, 256, 16, blk, blk + 8192};
+        return J;
+    }
+    J.K = 0;            // last job: clear the 256-byte status tail
+    return J;
+}
+
+__global__ void k_pack_all(sttode_decompose_weights w0, sttode_decompose_weights w1, const __grid_constant__ DecPackLayout L, unsigned char* __restrict__ pk) {
+    const int j = blockIdx.y;
+    const PackJob J = pack_job(j, w0, w1, L);
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (J.K == 0) {
+        if (idx < 64) reinterpret_cast<uint32_t*>(pk + L.total)[idx] = 0u;
+        return;
+    }
+    if (idx >= (J.K >> 3) * J.nrows) return;
+    const int kc = idx / J.nrows, r = idx - kc * J.nrows;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = r < J.nvalid ? __ldg(J.W + (size_t)(J.row0 + r) * J.ldw + J.col0 + kc * 8 + i) : 0.f;
+    tc::store_split8(pk + J.hi, pk + J.lo, J.nrows, r, kc, v);
+}
+void launch_pack_all(const sttode_decompose_weights& w0, const sttode_decompose_weights& w1, const DecPackLayout& L, unsigned char* pk, cudaStream_t st) {
+    k_pack_all<<<dim3(8, PACK_JOBS), 128, 0, st>>>(w0, w1, L, pk);      // largest image: 4 k-chunks x 256 rows = 1024 threads
+}
+
 // ------------------------------------------------------------------------------------------------
 // Warp-specialised tile kernel (576 threads):
 //   warps 0..15 epilogue : TMEM -> registers -> bias/ReLU/gates -> fp16 hi/lo operand images in shared memory, outputs

@@ -78,6 +78,7 @@ struct DecPackLayout {               // byte offsets inside the packed weight bu
 DecPackLayout dec_pack_layout(int Tp, int Tf);
 __global__ void k_pack_image(const float* W, int ldw, int row0, int col0, int nvalid, int nrows, int K, unsigned char* hi,
                              unsigned char* lo);
+void launch_pack_all(const sttode_decompose_weights& w0, const sttode_decompose_weights& w1, const DecPackLayout& L, unsigned char* pk, cudaStream_t st);
 __global__ void k_dec_pair_tc(const float* traj_norm, const float* z, unsigned long long seed, unsigned long long pair_base, const unsigned long long* rng_state,
                               const float* rowpre,
                               const int* row_scene, const float* origin, int rows, int K, int rpt, int Tp, int Tf,
@@ -90,6 +91,7 @@ size_t dec_pair_tc_smem_bytes(int Tp, int Tf);
 int dec_pair_tc_threads();
 
 __global__ void k_bump_counter(unsigned long long* p);
+__global__ void k_latent_draw(unsigned long long seed, unsigned long long pair_base, const unsigned long long* rng_state, size_t n_pairs, float* z);
 
 // metrics.cu
 __global__ void k_min_ade_fde(const float* pred, const float* gt, int gt_layout, int rows, int K, int Tf, double* sums);

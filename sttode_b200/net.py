@@ -310,23 +310,35 @@ def _decompose_struct(blk):
 
 
 class _PackedDecoder:
-    """fp16 hi/lo operand images of the decoder weights for the tcgen05 kernel, rebuilt whenever a parameter changes."""
+    """fp16 hi/lo operand images of the decoder weights for the tcgen05 kernels.
+
+    ONE buffer per (device, horizon), allocated once and rewritten in place (a single `k_pack_all` launch) whenever the weights
+    changed, so a pointer baked into a CUDA graph (ForecastGraph, GraphedTrainStep) stays valid for the life of the model and always
+    sees the newest pack.  Staleness is detected by (data_ptr, _version) of every decoder parameter — torch optimizers,
+    `load_state_dict` and in-place tensor ops all bump `_version` — plus an explicit `invalidate()` for updates that do not:
+    CUDA-graph replays of an optimizer step and the library's fused all-reduce + Adam kernel (parallel.py call it)."""
 
     def __init__(self):
-        self.key, self.buf = None, None
+        self.key, self.buf, self.shape = None, None, None
+        self.packs = 0                      # number of pack launches issued (tests)
+
+    def invalidate(self):
+        self.key = None
 
     def get(self, decoder, past_length, future_length):
         params = [p for blk in decoder.decompose for p in blk.parameters()]
-        key = tuple((p.data_ptr(), p._version) for p in params) + (past_length, future_length)
-        if key != self.key:
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        shape = (past_length, future_length, params[0].device)
+        if key != self.key or shape != self.shape:
             lib = _lib.lib()
-            dev = params[0].device
-            buf = torch.empty(lib.sttode_decoder_pack_bytes(past_length, future_length), dtype=torch.uint8, device=dev)
+            if self.buf is None or shape != self.shape:
+                self.buf = torch.empty(lib.sttode_decoder_pack_bytes(past_length, future_length), dtype=torch.uint8, device=params[0].device)
             mw = _lib.ModelWeights()
             mw.past_length, mw.future_length = past_length, future_length
             mw.dec[0], mw.dec[1] = _decompose_struct(decoder.decompose[0]), _decompose_struct(decoder.decompose[1])
-            _lib.check(lib.sttode_decoder_pack(C.byref(mw), _lib.dptr(buf), buf.numel(), _lib.stream_ptr()))
-            self.key, self.buf = key, buf
+            _lib.check(lib.sttode_decoder_pack(C.byref(mw), _lib.dptr(self.buf), self.buf.numel(), _lib.stream_ptr()))
+            self.key, self.shape = key, shape
+            self.packs += 1
         return self.buf
 
     def status(self, past_length, future_length):
@@ -371,7 +383,9 @@ class Decoder(nn.Module):
         zz = _f32c(z, "z").reshape(-1, 32)
         pairs = pf.shape[0]
         traj = _f32c(past_traj, "past_traj").repeat_interleave(sample_num, dim=0)
-        if not torch.equal(cur_location.reshape(-1, 2), past_traj[:, -1].reshape(-1, 2)):
+        # the library adds past_traj[:, -1] itself (every reference call site passes exactly that as cur_location); only the shape is checked
+        # here — comparing values would force a device->host sync (the class of hidden sync SURVEY K1 removes) and break graph capture
+        if cur_location.reshape(-1, 2).shape[0] != past_traj.shape[0]:
             raise NotImplementedError("Decoder on B200: cur_location must be past_traj[:, -1] (as at every reference call site)")
         mw = _lib.ModelWeights()
         mw.past_length, mw.future_length = self.past_length, self.future_length
@@ -509,6 +523,7 @@ class ForecastGraph:
         mw = self.model._weights()
         mw.rng_state = self.rng_state.data_ptr()
         self._mw = mw
+        self._packed_ptr = mw.dec_packed
         _lib.check(_lib.lib().sttode_forecast(_lib.dptr(self.traj), self.layout, _lib.dptr(self.scene_ptr), _lib.dptr(self.row_scene),
                                               self.n_scenes, self.rows, self.L, self.agents, None, self.seed, self.K, C.byref(mw),
                                               _lib.dptr(self.pred), _lib.dptr(self.past_feature), _lib.dptr(self.traj_norm),
@@ -528,6 +543,11 @@ class ForecastGraph:
 
     @torch.no_grad()
     def __call__(self, traj, scene_ptr=None):
+        if self.model.decoder.use_tensor_cores:
+            # the graph holds the pointer of the model's persistent pack buffer: refresh its contents (in place) if the weights changed since
+            buf = self.model.decoder._packed.get(self.model.decoder, self.model.args.past_length, self.model.args.future_length)
+            if buf.data_ptr() != self._packed_ptr:
+                raise _lib.SttodeError("ForecastGraph: the model's packed-weight buffer moved (model moved to another device?); capture again")
         self.traj.copy_(traj.reshape(self.traj.shape), non_blocking=True)
         if self.n_scenes:
             sp = scene_ptr.to(device=self.traj.device, dtype=torch.int32)
@@ -571,6 +591,11 @@ class STTODENet(nn.Module):
         if self.decoder.use_tensor_cores:
             mw.dec_packed = _lib.dptr(self.decoder._packed.get(self.decoder, self.args.past_length, self.args.future_length))
         return mw
+
+    def invalidate_packed(self):
+        """Call after changing decoder weights in a way torch cannot see (writes through raw pointers, CUDA-graph replays of an update):
+        the next forecast re-splits the weights into the tensor-core operand images."""
+        self.decoder._packed.invalidate()
 
     def tc_status(self):
         return self.decoder._packed.status(self.args.past_length, self.args.future_length)

@@ -82,9 +82,21 @@ class FlatGradReducer:
                 raise RuntimeError(f"{n}.grad no longer aliases the flat buffer (use reducer.zero(), not zero_grad(set_to_none=True))")
         w = self.world()
         if w > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-            self.flat.mul_(1.0 / w)
+            if dist.get_backend(self.group) == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)        # 1/world applied inside the collective: one pass
+            else:                                                                        # gloo (CPU tests) has no AVG
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+                self.flat.mul_(1.0 / w)
         return self.flat
+
+
+def describe_reduce(reducer, graphed):
+    """One line for bench.py's config: how the gradients of this run are exchanged."""
+    w = reducer.world()
+    if w == 1:
+        return "single GPU: no exchange; whole step (stage .. Adam) is one CUDA-graph replay" if graphed else "single GPU: no exchange"
+    how = "between a forward+backward graph and an Adam graph" if graphed else "eager"
+    return f"one NCCL all-reduce(SUM) of the flat {reducer.nbytes} B gradient buffer per step ({how}), pz_layer excluded, 1/world folded into the same pass"
 
 
 def make_optimizer(module, lr=1e-4, decay_step=10, decay_gamma=0.5, capturable=False):
@@ -137,6 +149,8 @@ class GraphedTrainStep:
                 self._update()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        from . import _lib
+        l0 = _lib.launch_count()
         self.graph = torch.cuda.CUDAGraph()
         if not self.split:
             with torch.cuda.graph(self.graph):
@@ -149,8 +163,12 @@ class GraphedTrainStep:
             self.graph_update = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_update, pool=self.graph.pool()):
                 self._update()
+        self.library_launches = _lib.launch_count() - l0       # libsttode_sm100 kernels recorded into the graph(s) = per replayed step
 
     def _forward_backward(self):
+        # the decoder's fp16 hi/lo weight images must be rebuilt from the CURRENT weights inside every replay: drop the cache key so the
+        # first decoder pass of the step issues (and the capture records) the pack; the second pass of the same step reuses it
+        self.model.decoder._packed.invalidate()
         self.model.set_data_nba(self.static)
         total, parts = self.model.objective()
         self.reducer.zero()
@@ -167,4 +185,10 @@ class GraphedTrainStep:
         if self.split:
             self.reducer.reduce()             # eager NCCL all-reduce of the flat gradient buffer on the current stream
             self.graph_update.replay()
+        # a replayed optimizer step changes the weights without bumping their version counters: the next eager forecast must repack
+        self.model.decoder._packed.invalidate()
         return self.losses
+
+    @property
+    def graph_replays_per_step(self):
+        return 2 if self.split else 1

@@ -1,0 +1,251 @@
+"""GPU parity, round 2: the paths bench.py actually times.
+
+ * the latent drawn IN the decoder kernels (Philox + Box-Muller) — its statistics, its independence across (pair, dim), and a full
+   oracle parity check of the un-injected path (the oracle is fed exactly the z the kernel drew, read back via sttode_latent_draw);
+ * several NBA attention groups (L = S = 128) in ONE sttode_forecast call against the oracle, group by group;
+ * the headline shape (scenes of 10..60 agents, in-batch) with a PER-AGENT max-norm, not a global one;
+ * weight-image cache invalidation (CUDA-graph replays / raw-pointer updates do not bump torch's version counters).
+Tolerance per north_star: <= 1e-4 relative."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sttode_oracle as O
+from sttode_b200 import synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def build_model(dataset, tp, tf, seed, dev, tensor_cores=True):
+    from oracle.ref_shim import make_args
+    from sttode_b200.net import STTODENet
+    sd = O.make_state_dict(seed, tp, tf)
+    m = STTODENet(make_args(dataset, tp, tf), dev)
+    m.load_state_dict(sd, strict=True)
+    m.set_device(dev)
+    m.decoder.use_tensor_cores = tensor_cores
+    return m.eval(), sd
+
+
+def rel_rows(got, ref, scale_floor=0.05):
+    """Per-agent max-norm: max over agents of (max |got - ref| over that agent's K x T x 2 block) / (max |ref| over the same block).
+    `scale_floor` (metres) keeps an agent that barely moves from dividing by ~0; displacements here are O(0.1 .. 10)."""
+    got, ref = got.detach().cpu().double(), ref.detach().cpu().double()
+    assert got.shape == ref.shape
+    r = got.shape[0]
+    err = (got - ref).abs().reshape(r, -1).max(dim=1)[0]
+    scl = ref.abs().reshape(r, -1).max(dim=1)[0].clamp_min(scale_floor)
+    return float((err / scl).max())
+
+
+def draw_latent(dev, seed, pair_base, n_pairs, rng_state=None):
+    import sttode_b200._lib as L
+    z = torch.empty(n_pairs, 32, device=dev)
+    L.check(L.lib().sttode_latent_draw(seed, pair_base, rng_state.data_ptr() if rng_state is not None else None, n_pairs, L.dptr(z), L.stream_ptr()))
+    return z
+
+
+# ------------------------------------------------------------------ the in-kernel latent draw
+def test_latent_draw_moments_and_ks(dev):
+    """>= 10^6 draws: mean, variance, skewness, kurtosis and a Kolmogorov-Smirnov statistic against N(0, 1)."""
+    n_pairs = 65536                                                    # 2 097 152 normals
+    z = draw_latent(dev, 0x1234_5678_9ABC, 0, n_pairs).double().flatten()
+    n = z.numel()
+    assert torch.isfinite(z).all()
+    mean, var = float(z.mean()), float(z.var())
+    skew = float(((z - mean) ** 3).mean() / var ** 1.5)
+    kurt = float(((z - mean) ** 4).mean() / var ** 2)
+    # standard errors at n = 2.1e6: mean 6.9e-4, var 9.8e-4, skew 1.7e-3, kurt 3.4e-3 -> 5 sigma bounds
+    assert abs(mean) < 3.5e-3 and abs(var - 1) < 5e-3 and abs(skew) < 8.5e-3 and abs(kurt - 3) < 1.7e-2, (mean, var, skew, kurt)
+    zs = torch.sort(z)[0]
+    cdf = 0.5 * (1 + torch.erf(zs / math.sqrt(2)))
+    i = torch.arange(1, n + 1, device=dev, dtype=torch.float64)
+    ks = float(torch.maximum((i / n - cdf).abs().max(), (cdf - (i - 1) / n).abs().max()))
+    assert ks < 1.95 / math.sqrt(n), ks                                # alpha ~ 0.001 critical value
+    assert float(z.abs().max()) > 4.5                                  # tails present (P(|z| > 4.5 somewhere in 2.1e6 draws) ~ 1)
+    assert float(z.abs().max()) < 7.0
+
+
+def test_latent_draw_independence(dev):
+    """No correlation across the 32 latent dims of a pair, across neighbouring pairs, across seeds; distinct pairs / seeds / rng_state give
+    distinct streams; pair_base shifts the stream exactly."""
+    n_pairs = 32768
+    z = draw_latent(dev, 99, 0, n_pairs).double()
+    zc = z - z.mean(0)
+    corr = (zc.T @ zc) / n_pairs / (zc.std(0)[:, None] * zc.std(0)[None, :])
+    off = corr - torch.diag(torch.diag(corr))
+    assert float(off.abs().max()) < 5.0 / math.sqrt(n_pairs), float(off.abs().max())          # 5 sigma of a sample correlation
+    lag = float((zc[:-1] * zc[1:]).mean() / zc.var())
+    assert abs(lag) < 5.0 / math.sqrt(n_pairs * 32)
+    z2 = draw_latent(dev, 100, 0, n_pairs).double()
+    cross = float(((z2 - z2.mean()) * zc).mean() / zc.std() / z2.std())
+    assert abs(cross) < 5.0 / math.sqrt(n_pairs * 32)
+    # keyed by (seed, batch-global pair index): a shifted window reads the same stream
+    zs = draw_latent(dev, 99, 1000, 4096)
+    assert torch.equal(zs.double(), z[1000:1000 + 4096])
+    # the device counter is added to the seed (CUDA-graph replays draw fresh z)
+    ctr = torch.tensor([1], dtype=torch.int64, device=dev)
+    assert torch.equal(draw_latent(dev, 99, 0, 4096, rng_state=ctr), draw_latent(dev, 100, 0, 4096))
+    assert len(torch.unique(z.flatten())) > 0.99 * z.numel()
+
+
+@pytest.mark.parametrize("tcores", [True, False])
+def test_uninjected_path_equals_injected_and_oracle(dev, tcores):
+    """The path bench.py times draws z in-kernel.  (i) forecast(z = NULL, seed) is BIT-identical to forecast(z = sttode_latent_draw(seed));
+    (ii) the oracle fed that same z agrees within 1e-4 per agent."""
+    import sttode_b200._lib as L
+    m, sd = build_model("eth", 8, 12, 1, dev, tensor_cores=tcores)
+    scenes = synth.eth_scenes(12, cycle=(10, 20, 30, 40, 50, 60), start=40)
+    counts = [o.shape[0] for o, _ in scenes]
+    obs = torch.cat([o for o, _ in scenes]).contiguous().to(dev)
+    sp = torch.tensor(np.concatenate([[0], np.cumsum(counts)]), dtype=torch.int32, device=dev)
+    rows = obs.shape[0]
+    rs = torch.repeat_interleave(torch.arange(len(counts), device=dev, dtype=torch.int32), (sp[1:] - sp[:-1]).long()).contiguous()
+    seed = 0xDEADBEEF
+    z = draw_latent(dev, seed, 0, rows * 20)
+    lib, mw = L.lib(), m._weights()
+    ws = L.workspace(lib.sttode_forecast_workspace_bytes(rows, 1, 20, 8), dev)
+    out = []
+    for zz, sd_ in ((None, seed), (z, 0)):
+        pred = torch.empty(rows, 20, 12, 2, device=dev)
+        L.check(lib.sttode_forecast(L.dptr(obs), 1, L.dptr(sp), L.dptr(rs), len(counts), rows, 1, 1, L.dptr(zz), sd_, 20, C.byref(mw), L.dptr(pred),
+                                    None, None, None, L.dptr(ws), ws.numel(), L.stream_ptr()))
+        out.append(pred.cpu())
+    assert torch.equal(out[0], out[1])
+    zc, r0 = z.cpu(), 0
+    for (o, _), n in zip(scenes, counts):
+        past, orig = O.eth_scene_normalise(o)
+        ref = O.inference(sd, past, 1, n, zc[r0 * 20:(r0 + n) * 20], scene_orig=orig, fast=True).permute(1, 0, 2, 3)
+        cur = (past[:, -1] + orig)[:, None, None, :]
+        assert rel_rows(out[0][r0:r0 + n] - cur, ref - cur) < TOL
+        r0 += n
+    assert m.tc_status() == 0
+
+
+# ------------------------------------------------------------------ the shapes bench.py times
+def test_nba_multi_group_launch_vs_oracle(dev):
+    """bench.py's NBA leg: several reference batches (attention groups of L = S = 128 scenes x 11 agents) in ONE sttode_forecast call.
+    Every group must equal the oracle run on that batch alone (groups never attend to each other)."""
+    import sttode_b200._lib as L
+    B, N, tp, tf, groups = 128, 11, 10, 20, 5
+    m, sd = build_model("nba", tp, tf, 2, dev)
+    batches = [synth.nba_batch(40 + i, B, N, tp, tf) for i in range(groups)]
+    past = torch.stack([b["past_traj"] for b in batches]).contiguous()             # [groups, B, N, tp, 2]
+    rows = groups * B * N
+    seed = 4242
+    z = draw_latent(dev, seed, 0, rows * 20)                                        # the latent the timed path draws
+    lib, mw = L.lib(), m._weights()
+    ws = L.workspace(lib.sttode_forecast_workspace_bytes(rows, B, 20, tp), dev)
+    pred = torch.empty(rows, 20, tf, 2, device=dev)
+    pf = torch.empty(rows, 128, device=dev)
+    pd = past.view(rows, tp, 2).to(dev)
+    L.check(lib.sttode_forecast(L.dptr(pd), 0, None, None, 0, rows, B, N, None, seed, 20, C.byref(mw), L.dptr(pred), L.dptr(pf), None, None,
+                                L.dptr(ws), ws.numel(), L.stream_ptr()))
+    pred, pf, zc = pred.cpu(), pf.cpu(), z.cpu()
+    R = B * N
+    for g in range(groups):
+        p = batches[g]["past_traj"].view(R, tp, 2)
+        dump = {}
+        ref = O.inference(sd, p, B, N, zc[g * R * 20:(g + 1) * R * 20], dump=dump, fast=True).permute(1, 0, 2, 3)      # [R, K, tf, 2]
+        assert rel_rows(pf[g * R:(g + 1) * R, 64:], dump["past_feature"][:, 64:], scale_floor=1e-3) < TOL               # ODE output: the sensitive quantity
+        cur = p[:, -1][:, None, None, :]
+        assert rel_rows(pred[g * R:(g + 1) * R] - cur, ref - cur) < TOL
+    assert m.tc_status() == 0
+
+
+def test_headline_shape_in_batch_vs_oracle(dev):
+    """bench.py's headline shape: scenes of N in {10..60} agents, >= 96 scenes in one launch, per-agent max-norm on the displacement,
+    on past_feature, and on min-ADE / min-FDE."""
+    m, sd = build_model("eth", 8, 12, 1, dev)
+    n_scenes = 96
+    scenes = synth.eth_scenes(n_scenes, cycle=(10, 20, 30, 40, 50, 60), start=0)
+    counts = [o.shape[0] for o, _ in scenes]
+    obs = torch.cat([o for o, _ in scenes])
+    gt = torch.cat([g for _, g in scenes])
+    sp = torch.tensor(np.concatenate([[0], np.cumsum(counts)]), dtype=torch.int32)
+    rows = obs.shape[0]
+    z = draw_latent(dev, 31337, 0, rows * 20)
+    m.z_override = z
+    pred = m.forecast_scenes(obs.to(dev), sp).cpu()
+    pf = m.past_feature.cpu()
+    m.z_override = None
+    zc, r0 = z.cpu(), 0
+    refs = []
+    for (o, _), n in zip(scenes, counts):
+        past, orig = O.eth_scene_normalise(o)
+        dump = {}
+        ref = O.inference(sd, past, 1, n, zc[r0 * 20:(r0 + n) * 20], scene_orig=orig, dump=dump, fast=True).permute(1, 0, 2, 3)
+        cur = (past[:, -1] + orig)[:, None, None, :]
+        assert rel_rows(pred[r0:r0 + n] - cur, ref - cur) < TOL, f"scene at row {r0}"
+        assert rel_rows(pf[r0:r0 + n, 64:], dump["past_feature"][:, 64:], scale_floor=1e-3) < TOL
+        refs.append(ref)
+        r0 += n
+    a0, f0 = O.min_ade_fde(torch.cat(refs), gt.permute(0, 2, 1))
+    a1, f1 = O.min_ade_fde(pred, gt.permute(0, 2, 1))
+    assert abs(a0 - a1) <= TOL * a0 and abs(f0 - f1) <= TOL * f0
+    assert m.tc_status() == 0
+
+
+# ------------------------------------------------------------------ weight-image cache
+def test_packed_weights_follow_unversioned_updates(dev):
+    """Weights changed behind torch's back (raw-pointer writes, graph replays) + invalidate_packed(): the tensor-core decoder must use the new
+    weights, in the SAME buffer (CUDA graphs hold its pointer), and agree with the FP32-FFMA decoder which reads the weights directly."""
+    m, _ = build_model("eth", 8, 12, 1, dev)
+    obs, _ = synth.eth_scene(3, 20)
+    sp = torch.tensor([0, 20], dtype=torch.int32)
+    m.z_override = synth.latent(20, seed=3)
+    a = m.forecast_scenes(obs.to(dev), sp).clone()
+    ptr0, packs0 = m.decoder._packed.buf.data_ptr(), m.decoder._packed.packs
+    m.forecast_scenes(obs.to(dev), sp)
+    assert m.decoder._packed.packs == packs0                                       # cache hit
+    w = m.decoder.decompose[1].decoder_y.layers[1].weight
+    # an update torch's version counter does not see (what a replayed optimizer graph does)
+    v0 = w._version
+    w.data.mul_(1.5)
+    assert w._version == v0
+    m.invalidate_packed()
+    b = m.forecast_scenes(obs.to(dev), sp).clone()
+    assert m.decoder._packed.buf.data_ptr() == ptr0 and m.decoder._packed.packs == packs0 + 1
+    assert not torch.equal(a, b)
+    m.decoder.use_tensor_cores = False
+    c = m.forecast_scenes(obs.to(dev), sp)
+    cur = obs[:, :, -1].to(dev)[:, None, None, :]
+    assert rel_rows(b - cur, c - cur) < TOL
+    m.decoder.use_tensor_cores = True
+    # a versioned update (optimizer.step / load_state_dict / in-place op) is picked up without any call
+    with torch.no_grad():
+        w.mul_(1.0 / 1.5)
+    d = m.forecast_scenes(obs.to(dev), sp)
+    assert rel_rows(d - cur, a - cur) < TOL
+    m.z_override = None
+
+
+def test_forecast_graph_sees_weight_updates(dev):
+    """ForecastGraph bakes the packed-weight pointer into the graph: after load_state_dict of other weights a replay must produce the
+    forecasts of the NEW weights (in-place repack before the replay), never read freed memory."""
+    m, _ = build_model("eth", 8, 12, 1, dev)
+    obs, _ = synth.eth_scene(5, 7)
+    obs, sp = obs.to(dev), torch.tensor([0, 7], dtype=torch.int32, device=dev)
+    g = m.capture_forecast(rows=7, L=1, agents=1, n_scenes=1)
+    g(obs, sp)
+    sd2 = O.make_state_dict(9, 8, 12)
+    m.load_state_dict(sd2, strict=True)
+    junk = [torch.empty(1 << 22, device=dev).normal_() for _ in range(4)]        # churn the allocator
+    g.rng_state.zero_()
+    got = g(obs, sp).clone()
+    m2, _ = build_model("eth", 8, 12, 9, dev)
+    z = draw_latent(dev, g.seed, 0, 7 * 20)
+    m2.z_override = z
+    want = m2.forecast_scenes(obs, sp)
+    assert torch.equal(got, want)
+    del junk
