@@ -655,7 +655,21 @@ def run_ours(args):
         torch.cuda.empty_cache()
         others[other], states[other] = inference_leg(ctx, other, args, max(3, args.steps // 2), 3)
         torch.cuda.empty_cache()
-        others["train"], states["train"] = train_leg(ctx, args, max(5, args.steps), 3)
+        # The training leg is secondary: it must never cost the headline line.  Every rank arms a dead-man timer; if the leg has not finished
+        # in time (a stuck collective), rank 0 prints the line without it and every rank leaves with status 0 instead of waiting for the NCCL watchdog.
+        def give_up():
+            if rank == 0:
+                others["train"] = {"error": f"training leg did not finish within {args.train_timeout:.0f} s; skipped"}
+                line["cpu_baseline"], line["configs"] = None, others
+                print(json.dumps(line), flush=True)
+            os._exit(0)
+        timer = threading.Timer(args.train_timeout, give_up)
+        timer.daemon = True
+        timer.start()
+        try:
+            others["train"], states["train"] = train_leg(ctx, args, max(5, args.steps), 3)
+        finally:
+            timer.cancel()
     ctx.close()                                                   # the last collective is done: no rank waits on another from here on
     if rank != 0:
         return
@@ -666,10 +680,11 @@ def run_ours(args):
         line["ade_fde_delta_vs_reference"] = parity_leg(state, dev)
         if not args.no_extra:
             for k in ("eth", "nba"):
-                if k in others:
+                if k in others and "error" not in others[k]:
                     others[k]["cpu_baseline"] = cpu_baseline_leg(states[k], max(4.0, args.cpu_seconds / 2))
                     others[k]["ade_fde_delta_vs_reference"] = parity_leg(states[k], dev)
-            others["train"]["cpu_baseline"] = train_cpu_baseline(states["train"])
+            if "train" in states:
+                others["train"]["cpu_baseline"] = train_cpu_baseline(states["train"])
             try:
                 line["gpu_eager_baseline"] = gpu_eager_baseline_leg(state, dev, 6.0)
             except Exception as e:                                 # secondary context only
@@ -697,6 +712,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="headline config only: skip the other configs, the training leg and the latency extras")
     ap.add_argument("--train", action="store_true", help="time only the data-parallel training step (configs[4])")
     ap.add_argument("--train-eager", action="store_true", help="training step launch by launch instead of CUDA-graph replay")
+    ap.add_argument("--train-timeout", type=float, default=150.0, help="dead-man timer of the secondary training leg (seconds)")
     ap.add_argument("--train-batch", type=int, default=32, help="scenes per GPU per training step (train.py:24)")
     ap.add_argument("--ffma", action="store_true", help="use the FP32-FFMA decoder tile instead of the tcgen05 one")
     args = ap.parse_args()
