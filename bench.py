@@ -296,7 +296,7 @@ def inference_leg(ctx, name, args, steps, warmup):
     model.load_state_dict(sd, strict=True)
     model.set_device(dev)
     model.eval()
-    model.decoder.use_tensor_cores = not args.ffma
+    model.set_tensor_cores(not args.ffma)
     mw = model._weights()
 
     if name == "eth":

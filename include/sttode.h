@@ -69,6 +69,9 @@ typedef struct sttode_ode_weights {
     const float *lin1_w, *lin1_b;               /* linear1 [1024,64],[1024]                         */
     const float *lin2_w, *lin2_b;               /* linear2 [64,1024],[64]                           */
     const float *norm1_g, *norm1_b, *norm2_g, *norm2_b; /* LayerNorm(64), eps 1e-5                  */
+    const void *packed;                         /* optional: buffer filled by sttode_ode_pack (fp16 hi/lo operand images of the
+                                                   weights above) -> forward runs on the tensor cores (k_qkv_tc, k_ode_tail_tc);
+                                                   NULL -> FP32-FFMA kernels.  Forward entry points only; ignored by *_bwd       */
 } sttode_ode_weights;
 
 /* PastEncoder / FutureEncoder front end (model/STTODE.py:179-197) */
@@ -125,6 +128,11 @@ int sttode_umma_bench(int n, int reps, long long *cycles2_dev, void *stream);
  * 2 / 3: only the N=192 / N=96 triples; 4: identical operands) with B images of b_rows rows; same outputs as sttode_umma_bench.
  * poll_mode > 0 adds 16 bystander warps waiting on an mbarrier meanwhile (1: every lane polls, 2: one lane per warp, 3: one lane + nanosleep). */
 int sttode_umma_pattern(int mode, int b_rows, int reps, int poll_mode, long long *cycles2_dev, void *stream);
+
+/* Tensor-core operand images of one ODE block's weights (tcgen05 3xFP16 path): call once per weight version, then put the buffer
+ * in sttode_ode_weights.packed.  One launch, graph-capturable. */
+size_t sttode_ode_pack_bytes(void);
+int sttode_ode_pack(const sttode_ode_weights *w, void *packed, size_t packed_bytes, void *stream);
 
 /* ---- MHGSA: replaces Hyp_mhsa.forward -> hyp_mhsa (hyptransformerlib.py:403-454 -> :29-311) ------
  * query [L,bsz,E], key/value [S,bsz,E] (key==value==query pointer for self-attention), out [L,bsz,E],

@@ -19,7 +19,7 @@ class MhgsaWeights(C.Structure):
 class OdeWeights(C.Structure):
     _fields_ = [("attn", MhgsaWeights)] + [(n, C.c_void_p) for n in (
         "info_w", "info_b", "gate_w", "gate_b", "lin1_w", "lin1_b", "lin2_w", "lin2_b",
-        "norm1_g", "norm1_b", "norm2_g", "norm2_b")]
+        "norm1_g", "norm1_b", "norm2_g", "norm2_b", "packed")]
 
 
 class MhgsaGrads(C.Structure):
@@ -73,6 +73,8 @@ SIGNATURES = {
     "sttode_umma_selftest": (_I, [_V, _V, _V, _I, _I, _I, _I, _V, _V]),
     "sttode_umma_bench": (_I, [_I, _I, _V, _V]),
     "sttode_umma_pattern": (_I, [_I, _I, _I, _I, _V, _V]),
+    "sttode_ode_pack_bytes": (_Z, []),
+    "sttode_ode_pack": (_I, [C.POINTER(OdeWeights), _V, _Z, _V]),
     "sttode_mhgsa_workspace_bytes": (_Z, [_I, _I, _I]),
     "sttode_mhgsa_fwd": (_I, [_V, _V, _V, C.POINTER(MhgsaWeights), _V, _V, _I, _I, _I, _I, _I, _I, _F, _F, _V, _Z, _V]),
     "sttode_linear64": (_I, [_V, _V, _V, _V, _I, _I, _V]),

@@ -95,7 +95,7 @@ struct AttnBufs { float *q, *k, *v; int ldq, ldk; };   // where run_attention le
 // self-attention layout: one [rows,192] buffer (q^|k^|v).  nb = number of independent (L x bsz) batches.
 int run_attention(const float* xq, const float* xk, const float* xv, bool self_attn, const sttode_mhgsa_weights& w, int L,
                   int S, int bsz, int nb, int score_mode, float clamp_eps, float curv, Carver& ws, float** o_out,
-                  float* attn_weights, cudaStream_t st, float* norms = nullptr, AttnBufs* bufs = nullptr) {
+                  float* attn_weights, cudaStream_t st, float* norms = nullptr, AttnBufs* bufs = nullptr, const void* packed = nullptr) {
     const int rows_q = nb * L * bsz, rows_k = nb * S * bsz;
     float *qb, *kb, *vb;
     int ldq, ldk;
@@ -105,22 +105,34 @@ int run_attention(const float* xq, const float* xk, const float* xv, bool self_a
     if (self_attn) {
         float* qkv = ws.take<float>((size_t)rows_q * 192);
         if (!qkv) return fail(STTODE_EWORKSPACE, "workspace too small for qkv");
+        int* flags = nullptr;
+        if (packed && !norms && score_mode == STTODE_SCORE_OBLIQUE_ACOS) {
+            // tensor-core in-projection (tcgen05 3xFP16); a tile whose operands leave the fp16 range (or hold NaN) raises its flag and is
+            // recomputed by the FP32 kernel right after (a CTA of the redo launch exits at once when its flag is clear)
+            const int tiles = ceil_div(rows_q, BM);
+            flags = ws.take<int>(tiles);
+            if (!flags) return fail(STTODE_EWORKSPACE, "workspace too small for the in-projection tile flags");
+            if ((rc = set_smem(k_qkv_tc, qkv_tc_smem_bytes(), "k_qkv_tc"))) return rc;
+            CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int) * tiles, st));
+            k_qkv_tc<<<tiles, ode_tail_tc_threads(), qkv_tc_smem_bytes(), st>>>(xq, 64, rows_q, w.in_proj_b, scale, (const unsigned char*)packed, qkv, 192, flags);
+            LAUNCH_CHECK("k_qkv_tc");
+        }
         k_proj<<<ceil_div(rows_q, BM), NTHREADS, proj_smem_bytes(), st>>>(xq, 64, rows_q, w.in_proj_w, w.in_proj_b, 3, qkv, 192,
-                                                                        0x1u, 0x3u, scale, score_mode, curv, norms, 16);
-        LAUNCH_CHECK("k_proj");
+                                                                        0x1u, 0x3u, scale, score_mode, curv, norms, 16, flags);
+        LAUNCH_CHECK(flags ? "k_proj(redo)" : "k_proj");
         qb = qkv; kb = qkv + 64; vb = qkv + 128; ldq = ldk = 192;
     } else {
         float* qq = ws.take<float>((size_t)rows_q * 64);
         float* kv = ws.take<float>((size_t)rows_k * 128);
         if (!qq || !kv) return fail(STTODE_EWORKSPACE, "workspace too small for q/kv");
         k_proj<<<ceil_div(rows_q, BM), NTHREADS, proj_smem_bytes(), st>>>(xq, 64, rows_q, w.in_proj_w, w.in_proj_b, 1, qq, 64,
-                                                                        0x1u, 0x1u, scale, score_mode, curv, norms, 8);
+                                                                        0x1u, 0x1u, scale, score_mode, curv, norms, 8, nullptr);
         LAUNCH_CHECK("k_proj(q)");
         k_proj<<<ceil_div(rows_k, BM), NTHREADS, proj_smem_bytes(), st>>>(xk, 64, rows_k, w.in_proj_w + 64 * 64, w.in_proj_b + 64, 1,
-                                                                        kv, 128, 0x0u, 0x1u, 1.f, score_mode, curv, norms ? norms + (size_t)rows_q * 8 : nullptr, 8);
+                                                                        kv, 128, 0x0u, 0x1u, 1.f, score_mode, curv, norms ? norms + (size_t)rows_q * 8 : nullptr, 8, nullptr);
         LAUNCH_CHECK("k_proj(k)");
         k_proj<<<ceil_div(rows_k, BM), NTHREADS, proj_smem_bytes(), st>>>(xv, 64, rows_k, w.in_proj_w + 128 * 64, w.in_proj_b + 128, 1,
-                                                                        kv + 64, 128, 0x0u, 0x0u, 1.f, score_mode, curv, nullptr, 0);
+                                                                        kv + 64, 128, 0x0u, 0x0u, 1.f, score_mode, curv, nullptr, 0, nullptr);
         LAUNCH_CHECK("k_proj(v)");
         qb = qq; ldq = 64; kb = kv; vb = kv + 64; ldk = 128;
     }
@@ -152,6 +164,28 @@ int check_ptrs_mhgsa(const sttode_mhgsa_weights* w) {
     return 0;
 }
 
+// ODE right-hand-side tail: tensor-core kernel when the weights come with their packed operand images, FP32-FFMA otherwise
+// (and for the tiles the tensor-core kernel flags: operands outside the fp16 range, NaN rows)
+int launch_ode_tail(const float* x, int ldx, const float* o, int ldo, const float* base, int ldb, float coef, int relu, float* out, int ldout,
+                    int rows, const sttode_ode_weights& w, int gate_only, Carver& ws, cudaStream_t st) {
+    int rc;
+    int* flags = nullptr;
+    const int tiles = ceil_div(rows, BM);
+    if (w.packed && !gate_only) {
+        flags = ws.take<int>(tiles);
+        if (!flags) return fail(STTODE_EWORKSPACE, "workspace too small for the ODE tile flags");
+        if ((rc = set_smem(k_ode_tail_tc, ode_tail_tc_smem_bytes(), "k_ode_tail_tc"))) return rc;
+        CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int) * tiles, st));
+        k_ode_tail_tc<<<tiles, ode_tail_tc_threads(), ode_tail_tc_smem_bytes(), st>>>(x, ldx, o, ldo, base, ldb, coef, relu, out, ldout, rows, w,
+                                                                                    (const unsigned char*)w.packed, flags);
+        LAUNCH_CHECK("k_ode_tail_tc");
+    }
+    if ((rc = set_smem(k_ode_tail, ode_tail_smem_bytes(), "k_ode_tail"))) return rc;
+    k_ode_tail<<<tiles, NTHREADS, ode_tail_smem_bytes(), st>>>(x, ldx, o, ldo, base, ldb, coef, relu, out, ldout, rows, w, gate_only, flags);
+    LAUNCH_CHECK(flags ? "k_ode_tail(redo)" : "k_ode_tail");
+    return 0;
+}
+
 // f = rhs(x) for nb batches of [L, bsz, 64]; out = act(base + coef*f)
 int run_rhs(const float* x, int L, int bsz, int nb, const sttode_ode_weights& w, const float* base, int ldb, float coef, int relu,
             float* out, int ldout, Carver ws /* by value: scratch is reusable after the call */, cudaStream_t st, int gate_only = 0) {
@@ -159,15 +193,16 @@ int run_rhs(const float* x, int L, int bsz, int nb, const sttode_ode_weights& w,
     float* o = nullptr;
     int rc;
     if (L > 1) {
-        if ((rc = run_attention(x, x, x, true, w.attn, L, L, bsz, nb, STTODE_SCORE_OBLIQUE_ACOS, 1e-4f, 1.f, ws, &o, nullptr, st))) return rc;
+        if ((rc = run_attention(x, x, x, true, w.attn, L, L, bsz, nb, STTODE_SCORE_OBLIQUE_ACOS, 1e-4f, 1.f, ws, &o, nullptr, st, nullptr, nullptr,
+                                gate_only ? nullptr : w.packed))) return rc;
     }
-    if ((rc = set_smem(k_ode_tail, ode_tail_smem_bytes(), "k_ode_tail"))) return rc;
-    k_ode_tail<<<ceil_div(rows, BM), NTHREADS, ode_tail_smem_bytes(), st>>>(x, 64, o, 64, base, ldb, coef, relu, out, ldout, rows, w, gate_only);
-    LAUNCH_CHECK("k_ode_tail");
-    return 0;
+    return launch_ode_tail(x, 64, o, 64, base, ldb, coef, relu, out, ldout, rows, w, gate_only, ws, st);
 }
 
-size_t rhs_ws_bytes(int rows, int L) { return L > 1 ? align_up((size_t)rows * 192 * 4) + align_up((size_t)rows * 64 * 4) : 0; }
+size_t rhs_ws_bytes(int rows, int L) {
+    const size_t flags = 2 * align_up((size_t)ceil_div(rows, BM) * 4);         // tensor-core tile flags (in-projection, tail)
+    return flags + (L > 1 ? align_up((size_t)rows * 192 * 4) + align_up((size_t)rows * 64 * 4) : 0);
+}
 
 int run_ode_block(const float* x, int L, int bsz, int nb, const sttode_ode_weights& w, int n_steps, float h, int method,
                   int final_relu, float* y, int ldy, Carver ws, cudaStream_t st) {
@@ -670,13 +705,7 @@ int run_encoder(const float* traj, int layout, const int* scene_ptr, const int* 
     const int bsz = scene_ptr ? 1 : agents;
     // ODE block on x0 = past_feature[:, 0:64] (ld 128) -> past_feature[:, 64:128]
     // k_ode_tail / k_proj read x with ld 64 only through run_rhs: stage x0 contiguously when L > 1
-    if (L == 1) {
-        if ((rc = set_smem(k_ode_tail, ode_tail_smem_bytes(), "k_ode_tail"))) return rc;
-        k_ode_tail<<<ceil_div(rows, BM), NTHREADS, ode_tail_smem_bytes(), st>>>(past_feature, 128, nullptr, 0, past_feature, 128, 12.f, 1,
-                                                                                past_feature + 64, 128, rows, ew.ode, 0);
-        LAUNCH_CHECK("k_ode_tail");
-        return 0;
-    }
+    if (L == 1) return launch_ode_tail(past_feature, 128, nullptr, 0, past_feature, 128, 12.f, 1, past_feature + 64, 128, rows, ew.ode, 0, ws, st);
     float* x0 = ws.take<float>((size_t)rows * 64);
     if (!x0) return fail(STTODE_EWORKSPACE, "workspace too small for x0");
     CUDA_TRY(cudaMemcpy2DAsync(x0, 64 * 4, past_feature, 128 * 4, 64 * 4, rows, cudaMemcpyDeviceToDevice, st));
@@ -887,6 +916,19 @@ int sttode_device_check(void) {
     return 0;
 }
 
+size_t sttode_ode_pack_bytes(void) { return ode_pack_bytes(); }
+
+int sttode_ode_pack(const sttode_ode_weights* w, void* packed, size_t packed_bytes, void* stream) {
+    int rc;
+    if (!w || !packed) return fail(STTODE_EINVAL, "null pointer");
+    if ((rc = check_ptrs_mhgsa(&w->attn))) return rc;
+    if (!w->info_w || !w->gate_w || !w->lin1_w || !w->lin2_w) return fail(STTODE_EINVAL, "ODE weights: null pointer");
+    if (packed_bytes < ode_pack_bytes()) return fail(STTODE_EWORKSPACE, "packed buffer too small: %zu < %zu", packed_bytes, ode_pack_bytes());
+    launch_pack_ode(*w, (unsigned char*)packed, (cudaStream_t)stream);
+    LAUNCH_CHECK("k_pack_ode");
+    return 0;
+}
+
 size_t sttode_mhgsa_workspace_bytes(int L, int S, int bsz) {
     return 4 * attn_ws_floats(L, S, bsz, false, true) + 4 * attn_ws_floats(L, S, bsz, true, true) + 1024;
 }
@@ -908,7 +950,7 @@ int sttode_mhgsa_fwd(const float* query, const float* key, const float* value, c
     float* o = nullptr;
     if ((rc = run_attention(query, key, value, self_attn, *w, L, S, bsz, 1, score_mode, clamp_eps, curvature, ws, &o, attn_weights, st))) return rc;
     // out_proj (hyptransformerlib.py:305): reuse k_proj with a single unscaled, un-normalised block
-    k_proj<<<ceil_div(L * bsz, BM), NTHREADS, proj_smem_bytes(), st>>>(o, 64, L * bsz, w->out_proj_w, w->out_proj_b, 1, out, 64, 0u, 0u, 1.f, 0, 1.f, nullptr, 0);
+    k_proj<<<ceil_div(L * bsz, BM), NTHREADS, proj_smem_bytes(), st>>>(o, 64, L * bsz, w->out_proj_w, w->out_proj_b, 1, out, 64, 0u, 0u, 1.f, 0, 1.f, nullptr, 0, nullptr);
     LAUNCH_CHECK("k_proj(out)");
     return 0;
 }
@@ -918,7 +960,7 @@ int sttode_linear64(const float* x, const float* weight, const float* bias, floa
     if (!x || !weight || !bias || !out || rows < 1) return fail(STTODE_EINVAL, "linear64: bad argument");
     if (out_features < 64 || out_features % 64 != 0 || out_features > 64 * 32) return fail(STTODE_EUNSUPPORTED, "linear64: out_features must be a multiple of 64 (<= 2048)");
     if ((rc = set_smem(k_proj, proj_smem_bytes(), "k_proj"))) return rc;
-    k_proj<<<ceil_div(rows, BM), NTHREADS, proj_smem_bytes(), (cudaStream_t)stream>>>(x, 64, rows, weight, bias, out_features / 64, out, out_features, 0u, 0u, 1.f, 0, 1.f, nullptr, 0);
+    k_proj<<<ceil_div(rows, BM), NTHREADS, proj_smem_bytes(), (cudaStream_t)stream>>>(x, 64, rows, weight, bias, out_features / 64, out, out_features, 0u, 0u, 1.f, 0, 1.f, nullptr, 0, nullptr);
     LAUNCH_CHECK("k_proj(linear64)");
     return 0;
 }

@@ -194,7 +194,8 @@ __device__ __forceinline__ float group8_sum(float v) {
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_proj(const float* __restrict__ X, int ldx, int rows, const float* __restrict__ W, const float* __restrict__ b, int nblk,
        float* __restrict__ out, int ldo, unsigned scale_mask, unsigned norm_mask, float scale, int score_mode, float curv,
-       float* __restrict__ norms, int ldn) {
+       float* __restrict__ norms, int ldn, const int* __restrict__ only_flagged) {
+    if (only_flagged && !only_flagged[blockIdx.x]) return;      // redo pass after k_qkv_tc: only tiles whose operands left the fp16 range
     extern __shared__ __align__(16) float smem[];
     float* xs = smem;                      // [BM][68]
     float* wbuf = xs + BM * LDS64;         // [2][64][68]
@@ -350,7 +351,9 @@ k_attn_weights(const float* __restrict__ rowop, int ldr, const float* __restrict
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_ode_tail(const float* __restrict__ x, int ldx, const float* __restrict__ attn_o, int ldo, const float* __restrict__ base,
-           int ldb, float coef, int relu, float* __restrict__ out, int ldout, int rows, sttode_ode_weights w, int gate_only) {
+           int ldb, float coef, int relu, float* __restrict__ out, int ldout, int rows, sttode_ode_weights w, int gate_only,
+           const int* __restrict__ only_flagged) {
+    if (only_flagged && !only_flagged[blockIdx.x]) return;      // redo pass after k_ode_tail_tc: only tiles whose operands left the fp16 range
     extern __shared__ __align__(16) float smem[];
     float* xs = smem;                       // [BM][68]
     float* As = xs + BM * LDS64;            // [BM][68]

@@ -10,13 +10,14 @@ __global__ void k_scene_origin(const float* traj, int layout, const int* scene_p
 __global__ void k_prologue(const float* traj, int layout, const int* scene_ptr, const int* row_scene, const float* origin,
                            int rows, int agents, int T, sttode_encoder_weights w, float* x0, int ldx0, float* traj_norm);
 __global__ void k_proj(const float* X, int ldx, int rows, const float* W, const float* b, int nblk, float* out, int ldo,
-                       unsigned scale_mask, unsigned norm_mask, float scale, int score_mode, float curv, float* norms, int ldn);
+                       unsigned scale_mask, unsigned norm_mask, float scale, int score_mode, float curv, float* norms, int ldn,
+                       const int* only_flagged);
 __global__ void k_geo_attn(const float* rowop, int ldr, const float* colop, int ldc, const float* vals, int ldv, float* out,
                            int ldo, float* denom, int Lr, int Lc, int bsz, int score_mode, float lo, float hi, float curv);
 __global__ void k_attn_weights(const float* rowop, int ldr, const float* colop, int ldc, const float* denom, float* wout,
                                int Lr, int Lc, int bsz, int score_mode, float lo, float hi, float curv);
 __global__ void k_ode_tail(const float* x, int ldx, const float* attn_o, int ldo, const float* base, int ldb, float coef,
-                           int relu, float* out, int ldout, int rows, sttode_ode_weights w, int gate_only);
+                           int relu, float* out, int ldout, int rows, sttode_ode_weights w, int gate_only, const int* only_flagged);
 __global__ void k_lincomb(const float* base, int ldb, const float* k0, const float* k1, const float* k2, const float* k3,
                           float c0, float c1, float c2, float c3, int relu, float* out, int ldout, int rows);
 __global__ void k_linear(const float* X, int rows, int K, const float* W, const float* b, int N, int relu, float* Y);
@@ -24,6 +25,17 @@ size_t linear_smem_bytes(int K);
 size_t prologue_smem_bytes(int T);
 size_t proj_smem_bytes();
 size_t ode_tail_smem_bytes();
+
+// encoder_tc.cu — tensor-core (tcgen05) in-projection and ODE right-hand side + weight packing
+size_t ode_pack_bytes();
+void launch_pack_ode(const sttode_ode_weights& w, unsigned char* pk, cudaStream_t st);
+__global__ void k_ode_tail_tc(const float* x, int ldx, const float* attn_o, int ldo, const float* base, int ldb, float coef, int relu, float* out,
+                              int ldout, int rows, sttode_ode_weights w, const unsigned char* packed, int* tile_flags);
+__global__ void k_qkv_tc(const float* x, int ldx, int rows, const float* in_b, float scale, const unsigned char* packed, float* out, int ldo,
+                         int* tile_flags);
+size_t ode_tail_tc_smem_bytes();
+size_t qkv_tc_smem_bytes();
+int ode_tail_tc_threads();
 
 // backward.cu
 __global__ void k_gemm(int M, int N, int K, const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C, long ldc,

@@ -48,9 +48,43 @@ def _ode_struct_from(tensors, cls=_lib.OdeWeights):
     return s
 
 
-def _ode_struct(layer):
-    """sttode_ode_weights for a TransformerEncoderLayer (or just its Hypattention when `layer` is one)."""
-    return _ode_struct_from(_ode_params(layer))
+def _ode_struct(layer, tensor_cores=None):
+    """sttode_ode_weights for a TransformerEncoderLayer (or just its Hypattention when `layer` is one).  With tensor_cores (default: the
+    layer is in eval mode and `use_tensor_cores` is set) the struct carries the fp16 hi/lo operand images of the weights and the forward
+    runs on the tcgen05 kernels."""
+    s = _ode_struct_from(_ode_params(layer))
+    if tensor_cores is None:
+        tensor_cores = isinstance(layer, TransformerEncoderLayer) and layer.use_tensor_cores and not layer.training
+    if tensor_cores:
+        s.packed = _lib.dptr(layer._packed.get(layer))
+    return s
+
+
+class _PackedOde:
+    """fp16 hi/lo operand images of one ODE block's weights for k_qkv_tc / k_ode_tail_tc (sttode_ode_pack): one persistent buffer,
+    rewritten in place when the weights change (same staleness rules as net._PackedDecoder)."""
+
+    def __init__(self):
+        self.key, self.buf, self.packs = None, None, 0
+
+    def invalidate(self):
+        self.key = None
+
+    def __deepcopy__(self, memo):
+        return _PackedOde()
+
+    def get(self, layer):
+        params = _ode_params(layer)
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if key != self.key:
+            lib = _lib.lib()
+            if self.buf is None or self.buf.device != params[0].device:
+                self.buf = torch.empty(lib.sttode_ode_pack_bytes(), dtype=torch.uint8, device=params[0].device)
+            st = _ode_struct_from(params)
+            _lib.check(lib.sttode_ode_pack(C.byref(st), _lib.dptr(self.buf), self.buf.numel(), _lib.stream_ptr()))
+            self.key = key
+            self.packs += 1
+        return self.buf
 
 
 class _OdeRhsFn(torch.autograd.Function):
@@ -58,13 +92,14 @@ class _OdeRhsFn(torch.autograd.Function):
     (sttode_ode_rhs_fwd / sttode_hypattention_fwd / sttode_ode_rhs_bwd).  x [L, bsz, 64]."""
 
     @staticmethod
-    def forward(ctx, x, gate_only, *params):
+    def forward(ctx, x, gate_only, packed, *params):
         L, bsz = x.shape[0], x.shape[1]
         params = [_f32c(p, "parameter") for p in params]
         out = torch.empty_like(x)
         lib = _lib.lib()
         ws = _lib.workspace(lib.sttode_ode_block_workspace_bytes(L, bsz, ODE_EULER), x.device)
         st = _ode_struct_from(params)
+        st.packed = _lib.dptr(packed)               # tensor-core operand images (eval mode) or None -> FP32 kernels
         fn = lib.sttode_hypattention_fwd if gate_only else lib.sttode_ode_rhs_fwd
         _lib.check(fn(_lib.dptr(x), C.byref(st), _lib.dptr(out), L, bsz, _lib.dptr(ws), ws.numel(), _lib.stream_ptr()))
         ctx.save_for_backward(x, *params)
@@ -83,7 +118,7 @@ class _OdeRhsFn(torch.autograd.Function):
         st, gs = _ode_struct_from(params), _ode_struct_from(grads, _lib.OdeGrads)
         _lib.check(lib.sttode_ode_rhs_bwd(_lib.dptr(x), _lib.dptr(df), C.byref(st), _lib.dptr(dx), C.byref(gs), L, bsz, int(ctx.gate_only),
                                           _lib.dptr(ws), ws.numel(), _lib.stream_ptr()))
-        return (dx, None, *grads)
+        return (dx, None, None, *grads)
 
 
 class _OdeBlockFn(torch.autograd.Function):
@@ -92,13 +127,14 @@ class _OdeBlockFn(torch.autograd.Function):
     solver states and runs the discrete adjoint of the same grid.  x [L, bsz, 64]."""
 
     @staticmethod
-    def forward(ctx, x, n_steps, h, method, final_relu, *params):
+    def forward(ctx, x, n_steps, h, method, final_relu, packed, *params):
         L, bsz = x.shape[0], x.shape[1]
         params = [_f32c(p, "parameter") for p in params]
         y = torch.empty_like(x)
         lib = _lib.lib()
         ws = _lib.workspace(lib.sttode_ode_block_workspace_bytes(L, bsz, method), x.device)
         st = _ode_struct_from(params)
+        st.packed = _lib.dptr(packed)
         _lib.check(lib.sttode_ode_block_fwd(_lib.dptr(x), C.byref(st), _lib.dptr(y), 64, L, bsz, n_steps, h, method, int(final_relu),
                                             _lib.dptr(ws), ws.numel(), _lib.stream_ptr()))
         ctx.save_for_backward(x, *params)
@@ -118,7 +154,7 @@ class _OdeBlockFn(torch.autograd.Function):
         st, gs = _ode_struct_from(params), _ode_struct_from(grads, _lib.OdeGrads)
         _lib.check(lib.sttode_ode_block_bwd(_lib.dptr(x), _lib.dptr(dy), 64, C.byref(st), _lib.dptr(dx), C.byref(gs), L, bsz, n_steps, h, method,
                                             int(final_relu), _lib.dptr(ws), ws.numel(), _lib.stream_ptr()))
-        return (dx, None, None, None, None, *grads)
+        return (dx, None, None, None, None, None, *grads)
 
 
 def _grad_view(t, name):
@@ -153,7 +189,7 @@ class Hypattention(nn.Module):
         _check_eval_dropout(self.temporal_attention_before.dropout, self.training, "Hypattention")
         T, N, sn, D = query.shape
         x = _grad_view(query, "query").reshape(T, N * sn, D)
-        out = _OdeRhsFn.apply(x, True, *_ode_params(self))
+        out = _OdeRhsFn.apply(x, True, None, *_ode_params(self))
         weights = None
         if need_weights:
             weights = self.temporal_attention_before(x, x, x, need_weights=True)[1]
@@ -175,12 +211,18 @@ class TransformerEncoderLayer(nn.Module):
         self.norm2 = nn.LayerNorm(d_model)
         self.dropout1 = nn.Dropout(dropout)
         self.dropout2 = nn.Dropout(dropout)
+        # eval-mode forwards run the in-projection / out-proj / gate / FFN on the tcgen05 tensor cores (3xFP16 split); False -> FP32 FFMA
+        self.use_tensor_cores = True
+        self._packed = _PackedOde()
+
+    def _packed_or_none(self):
+        return self._packed.get(self) if (self.use_tensor_cores and not self.training and self.linear1.weight.is_cuda) else None
 
     def forward(self, src, src_mask=None, src_key_padding_mask=None):
         _check_eval_dropout(self.dropout.p, self.training, "TransformerEncoderLayer")
         shape = src.shape
         x = _grad_view(src, "src").reshape(shape[0], -1, shape[-1])
-        out = _OdeRhsFn.apply(x, False, *_ode_params(self))
+        out = _OdeRhsFn.apply(x, False, self._packed_or_none(), *_ode_params(self))
         return out.reshape(shape)
 
 
@@ -228,7 +270,7 @@ class ODEblock_en(nn.Module):
         xs = _grad_view(x, "x").reshape(shape[0], -1, shape[-1])
         span = float(self.t[-1]) - float(self.t[0])
         method = _METHODS[self.method]
-        y = _OdeBlockFn.apply(xs, self.n_steps, span / self.n_steps, method, bool(final_relu), *_ode_params(layer))
+        y = _OdeBlockFn.apply(xs, self.n_steps, span / self.n_steps, method, bool(final_relu), layer._packed_or_none(), *_ode_params(layer))
         return y.reshape(shape)
 
     def forward(self, x):

@@ -523,7 +523,7 @@ class ForecastGraph:
         mw = self.model._weights()
         mw.rng_state = self.rng_state.data_ptr()
         self._mw = mw
-        self._packed_ptr = mw.dec_packed
+        self._packed_ptrs = (mw.dec_packed, mw.past.ode.packed)
         _lib.check(_lib.lib().sttode_forecast(_lib.dptr(self.traj), self.layout, _lib.dptr(self.scene_ptr), _lib.dptr(self.row_scene),
                                               self.n_scenes, self.rows, self.L, self.agents, None, self.seed, self.K, C.byref(mw),
                                               _lib.dptr(self.pred), _lib.dptr(self.past_feature), _lib.dptr(self.traj_norm),
@@ -543,11 +543,9 @@ class ForecastGraph:
 
     @torch.no_grad()
     def __call__(self, traj, scene_ptr=None):
-        if self.model.decoder.use_tensor_cores:
-            # the graph holds the pointer of the model's persistent pack buffer: refresh its contents (in place) if the weights changed since
-            buf = self.model.decoder._packed.get(self.model.decoder, self.model.args.past_length, self.model.args.future_length)
-            if buf.data_ptr() != self._packed_ptr:
-                raise _lib.SttodeError("ForecastGraph: the model's packed-weight buffer moved (model moved to another device?); capture again")
+        # the graph holds the pointers of the model's persistent pack buffers: refresh their contents (in place) if the weights changed since
+        if self.model._refresh_packed() != self._packed_ptrs:
+            raise _lib.SttodeError("ForecastGraph: the model's packed-weight buffers moved or the tensor-core switches changed; capture again")
         self.traj.copy_(traj.reshape(self.traj.shape), non_blocking=True)
         if self.n_scenes:
             sp = scene_ptr.to(device=self.traj.device, dtype=torch.int32)
@@ -592,10 +590,28 @@ class STTODENet(nn.Module):
             mw.dec_packed = _lib.dptr(self.decoder._packed.get(self.decoder, self.args.past_length, self.args.future_length))
         return mw
 
+    def _refresh_packed(self):
+        """Bring the tensor-core operand images used by `inference` up to date; -> (decoder pack ptr, past-encoder ODE pack ptr), None = FFMA."""
+        dec = self.decoder
+        d = dec._packed.get(dec, self.args.past_length, self.args.future_length).data_ptr() if dec.use_tensor_cores else None
+        layer = self.past_encoder.ODE_Encoder.odeblock.odefunc.layers[0]
+        pk = layer._packed_or_none()
+        return (d, pk.data_ptr() if pk is not None else None)
+
+    def set_tensor_cores(self, on):
+        """Select the tcgen05 tensor-core kernels (default) or the FP32-FFMA kernels for the decoder and both ODE blocks."""
+        self.decoder.use_tensor_cores = bool(on) and 2 * max(self.args.past_length, self.args.future_length) <= 48
+        for m in self.modules():
+            if isinstance(m, TransformerEncoderLayer):
+                m.use_tensor_cores = bool(on)
+
     def invalidate_packed(self):
-        """Call after changing decoder weights in a way torch cannot see (writes through raw pointers, CUDA-graph replays of an update):
-        the next forecast re-splits the weights into the tensor-core operand images."""
-        self.decoder._packed.invalidate()
+        """Call after changing weights in a way torch cannot see (writes through raw pointers, CUDA-graph replays of an update):
+        the next forward re-splits them into the tensor-core operand images (decoder and both ODE blocks)."""
+        for m in self.modules():
+            pk = getattr(m, "_packed", None)
+            if pk is not None:
+                pk.invalidate()
 
     def tc_status(self):
         return self.decoder._packed.status(self.args.past_length, self.args.future_length)

@@ -186,7 +186,7 @@ class GraphedTrainStep:
             self.reducer.reduce()             # eager NCCL all-reduce of the flat gradient buffer on the current stream
             self.graph_update.replay()
         # a replayed optimizer step changes the weights without bumping their version counters: the next eager forecast must repack
-        self.model.decoder._packed.invalidate()
+        self.model.invalidate_packed()
         return self.losses
 
     @property

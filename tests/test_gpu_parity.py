@@ -34,7 +34,7 @@ def build_model(dataset, tp, tf, seed, dev, tensor_cores=True):
     m = STTODENet(make_args(dataset, tp, tf), dev)
     m.load_state_dict(sd, strict=True)
     m.set_device(dev)
-    m.decoder.use_tensor_cores = tensor_cores
+    m.set_tensor_cores(tensor_cores)
     return m.eval(), sd
 
 

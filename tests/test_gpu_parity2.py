@@ -33,7 +33,7 @@ def build_model(dataset, tp, tf, seed, dev, tensor_cores=True):
     m = STTODENet(make_args(dataset, tp, tf), dev)
     m.load_state_dict(sd, strict=True)
     m.set_device(dev)
-    m.decoder.use_tensor_cores = tensor_cores
+    m.set_tensor_cores(tensor_cores)
     return m.eval(), sd
 
 
@@ -249,3 +249,61 @@ def test_forecast_graph_sees_weight_updates(dev):
     want = m2.forecast_scenes(obs, sp)
     assert torch.equal(got, want)
     del junk
+
+
+# ------------------------------------------------------------------ tensor-core MHGSA in-projection + ODE right-hand side
+LAYER = "past_encoder.ODE_Encoder.odeblock.odefunc.layers.0."
+
+
+def _ode_encoder(sd, dev, tensor_cores):
+    from sttode_b200.layers import ODEG_Encoder, TransformerEncoderLayer
+    enc = ODEG_Encoder(TransformerEncoderLayer(64, 8, 1024, 0.0), 1, 12.0).to(dev).eval()
+    enc.load_state_dict({k[len("past_encoder.ODE_Encoder."):]: v for k, v in sd.items() if k.startswith("past_encoder.ODE_Encoder.")})
+    enc.odeblock.odefunc.layers[0].use_tensor_cores = tensor_cores
+    return enc
+
+
+@pytest.mark.parametrize("L,bsz", [(1, 300), (5, 11), (128, 11), (33, 7), (256, 3)])
+def test_ode_block_tensor_cores_vs_oracle(dev, L, bsz):
+    """ODEG_Encoder (one Euler step, h = 12, final relu) on the tcgen05 kernels (k_qkv_tc for L > 1, k_ode_tail_tc) against the float64 oracle
+    and against the FP32-FFMA kernels; per-row max-norm.  L = 1 is the ETH/SDD shape (value projection inside the tail kernel)."""
+    sd = O.make_state_dict(1, 8, 12)
+    g = torch.Generator().manual_seed(L * 1000 + bsz)
+    x = torch.randn(L, bsz, 1, 64, generator=g)
+    sd64 = O.cast_state_dict(sd, torch.float64)
+    ref = O.ode_encoder(x.double(), sd64, "past_encoder.").reshape(L * bsz, 64)
+    y_tc = _ode_encoder(sd, dev, True)(x.to(dev)).reshape(L * bsz, 64)
+    y_ff = _ode_encoder(sd, dev, False)(x.to(dev)).reshape(L * bsz, 64)
+    assert rel_rows(y_tc, ref, scale_floor=1e-2) < TOL
+    assert rel_rows(y_ff, ref, scale_floor=1e-2) < TOL
+    assert rel_rows(y_tc, y_ff, scale_floor=1e-2) < TOL
+
+
+def test_ode_block_tensor_cores_clamp_nan_and_range(dev):
+    """Edge rows on the tensor-core path: k = +-q rows (both acos clamps), a zero row (NaN exactly where the reference gives NaN, and only
+    there), and activations beyond the fp16 range (the flagged tile is recomputed by the FP32 kernel: still within tolerance)."""
+    sd = O.make_state_dict(1, 8, 12)
+    L, bsz = 40, 6
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(L, bsz, 1, 64, generator=g)
+    x[3] = x[2]                      # identical rows: Gram = 1 -> upper clamp
+    x[5] = -x[4]
+    x[7, 2] = 0.0                    # in_proj bias is non-zero in the synthetic weights, so make a true zero q/k row via the weights below
+    sd = dict(sd)
+    att = LAYER + "self_attn.temporal_attention_before."
+    sd[att + "in_proj_bias"] = torch.zeros(192)
+    ref = O.ode_encoder(x, sd, "past_encoder.").reshape(L, bsz, 64)
+    y = _ode_encoder(sd, dev, True)(x.to(dev)).reshape(L, bsz, 64).cpu()
+    nan_ref, nan_got = torch.isnan(ref), torch.isnan(y)
+    assert nan_ref.any() and torch.equal(nan_ref, nan_got)
+    ok = ~nan_ref
+    err = ((y - ref).abs()[ok]).max() / ref[ok].abs().max()
+    assert float(err) < TOL
+    # beyond the fp16 range: |x| ~ 1e5 (LayerNorm brings the scale back, so the reference output is finite)
+    xb = torch.randn(1, 260, 1, 64, generator=g)
+    xb[0, 17] *= 1.0e5
+    xb[0, 200] *= 3.0e5
+    refb = O.ode_encoder(xb.double(), O.cast_state_dict(O.make_state_dict(1, 8, 12), torch.float64), "past_encoder.").reshape(260, 64)
+    yb = _ode_encoder(O.make_state_dict(1, 8, 12), dev, True)(xb.to(dev)).reshape(260, 64)
+    assert torch.isfinite(yb).all()
+    assert rel_rows(yb, refb, scale_floor=1e-2) < TOL

@@ -33,14 +33,14 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_header():
     import ctypes as C
     assert C.sizeof(L.MhgsaWeights) == 4 * 8
-    assert C.sizeof(L.OdeWeights) == 16 * 8
-    assert C.sizeof(L.EncoderWeights) == (9 + 16) * 8
+    assert C.sizeof(L.OdeWeights) == 17 * 8                      # 16 tensors + the optional packed tensor-core images
+    assert C.sizeof(L.EncoderWeights) == (9 + 17) * 8
     assert C.sizeof(L.DecomposeWeights) == (6 + 12) * 8
-    assert C.sizeof(L.ModelWeights) == 8 + (25 + 36 + 2) * 8
+    assert C.sizeof(L.ModelWeights) == 8 + (26 + 36 + 2) * 8
     # gradient structs mirror the weight structs field for field (include/sttode.h)
-    assert C.sizeof(L.MhgsaGrads) == C.sizeof(L.MhgsaWeights) and C.sizeof(L.OdeGrads) == C.sizeof(L.OdeWeights)
+    assert C.sizeof(L.MhgsaGrads) == C.sizeof(L.MhgsaWeights) and C.sizeof(L.OdeGrads) == C.sizeof(L.OdeWeights) - 8
     assert C.sizeof(L.DecomposeGrads) == C.sizeof(L.DecomposeWeights) and C.sizeof(L.Mlp3Grads) == C.sizeof(L.Mlp3Weights)
-    assert [f[0] for f in L.OdeGrads._fields_] == [f[0] for f in L.OdeWeights._fields_]
+    assert [f[0] for f in L.OdeGrads._fields_] == [f[0] for f in L.OdeWeights._fields_ if f[0] != "packed"]
     assert [f[0] for f in L.DecomposeGrads._fields_] == [f[0] for f in L.DecomposeWeights._fields_]
 
 
