@@ -82,6 +82,9 @@ typedef struct sttode_encoder_weights {
     const float *fc2_w, *fc2_b;                 /* input_fc2 [64,64*T],[64]                         */
     const float *fc3_w, *fc3_b;                 /* input_fc3 [64,67],[64]                           */
     sttode_ode_weights ode;                     /* ODE_Encoder.odeblock.odefunc.layers.0.*          */
+    const float *folded;                        /* optional: table filled by sttode_encoder_fold (the eval-mode front end — a chain of
+                                                   Linear layers — collapsed to one affine map of the 4 T input features).  With it AND
+                                                   ode.packed the tensor-core kernels compute x0 in their input staging; NULL -> k_prologue */
 } sttode_encoder_weights;
 
 /* one DecomposeBlock (model/STTODE.py:16-38) */
@@ -133,6 +136,11 @@ int sttode_umma_pattern(int mode, int b_rows, int reps, int poll_mode, long long
  * in sttode_ode_weights.packed.  One launch, graph-capturable. */
 size_t sttode_ode_pack_bytes(void);
 int sttode_ode_pack(const sttode_ode_weights *w, void *packed, size_t packed_bytes, void *stream);
+
+/* Eval-mode encoder front end (model/STTODE.py:214-223 without the PE dropout) folded into one affine map; T = the encoder's sequence
+ * length (past_length for PastEncoder, future_length for FutureEncoder).  Call once per weight version.  One launch, graph-capturable. */
+size_t sttode_encoder_fold_bytes(int T);
+int sttode_encoder_fold(const sttode_encoder_weights *w, int T, float *folded, size_t folded_bytes, void *stream);
 
 /* ---- MHGSA: replaces Hyp_mhsa.forward -> hyp_mhsa (hyptransformerlib.py:403-454 -> :29-311) ------
  * query [L,bsz,E], key/value [S,bsz,E] (key==value==query pointer for self-attention), out [L,bsz,E],

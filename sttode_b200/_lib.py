@@ -33,7 +33,7 @@ class OdeGrads(C.Structure):
 
 
 class EncoderWeights(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("fc_w", "fc_b", "pe", "pefc_w", "pefc_b", "fc2_w", "fc2_b", "fc3_w", "fc3_b")] + [("ode", OdeWeights)]
+    _fields_ = [(n, C.c_void_p) for n in ("fc_w", "fc_b", "pe", "pefc_w", "pefc_b", "fc2_w", "fc2_b", "fc3_w", "fc3_b")] + [("ode", OdeWeights), ("folded", C.c_void_p)]
 
 
 class Mlp3Weights(C.Structure):
@@ -75,6 +75,8 @@ SIGNATURES = {
     "sttode_umma_pattern": (_I, [_I, _I, _I, _I, _V, _V]),
     "sttode_ode_pack_bytes": (_Z, []),
     "sttode_ode_pack": (_I, [C.POINTER(OdeWeights), _V, _Z, _V]),
+    "sttode_encoder_fold_bytes": (_Z, [_I]),
+    "sttode_encoder_fold": (_I, [C.POINTER(EncoderWeights), _I, _V, _Z, _V]),
     "sttode_mhgsa_workspace_bytes": (_Z, [_I, _I, _I]),
     "sttode_mhgsa_fwd": (_I, [_V, _V, _V, C.POINTER(MhgsaWeights), _V, _V, _I, _I, _I, _I, _I, _I, _F, _F, _V, _Z, _V]),
     "sttode_linear64": (_I, [_V, _V, _V, _V, _I, _I, _V]),

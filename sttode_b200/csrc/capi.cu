@@ -1,5 +1,6 @@
 // extern "C" entry points of libsttode_sm100.so (see include/sttode.h for the contract).
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <atomic>
@@ -95,7 +96,8 @@ struct AttnBufs { float *q, *k, *v; int ldq, ldk; };   // where run_attention le
 // self-attention layout: one [rows,192] buffer (q^|k^|v).  nb = number of independent (L x bsz) batches.
 int run_attention(const float* xq, const float* xk, const float* xv, bool self_attn, const sttode_mhgsa_weights& w, int L,
                   int S, int bsz, int nb, int score_mode, float clamp_eps, float curv, Carver& ws, float** o_out,
-                  float* attn_weights, cudaStream_t st, float* norms = nullptr, AttnBufs* bufs = nullptr, const void* packed = nullptr) {
+                  float* attn_weights, cudaStream_t st, float* norms = nullptr, AttnBufs* bufs = nullptr, const void* packed = nullptr,
+                  int ldx = 64, const FoldedIn* fold = nullptr) {
     const int rows_q = nb * L * bsz, rows_k = nb * S * bsz;
     float *qb, *kb, *vb;
     int ldq, ldk;
@@ -112,12 +114,14 @@ int run_attention(const float* xq, const float* xk, const float* xv, bool self_a
             const int tiles = ceil_div(rows_q, BM);
             flags = ws.take<int>(tiles);
             if (!flags) return fail(STTODE_EWORKSPACE, "workspace too small for the in-projection tile flags");
-            if ((rc = set_smem(k_qkv_tc, qkv_tc_smem_bytes(), "k_qkv_tc"))) return rc;
+            const size_t smq = qkv_tc_smem_bytes(fold ? fold->T : 0);
+            if ((rc = set_smem(k_qkv_tc, smq, "k_qkv_tc"))) return rc;
             CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int) * tiles, st));
-            k_qkv_tc<<<tiles, ode_tail_tc_threads(), qkv_tc_smem_bytes(), st>>>(xq, 64, rows_q, w.in_proj_b, scale, (const unsigned char*)packed, qkv, 192, flags);
+            k_qkv_tc<<<tiles, ode_tail_tc_threads(), smq, st>>>(xq, ldx, rows_q, w.in_proj_b, scale, (const unsigned char*)packed, qkv, 192, flags,
+                                                               fold ? *fold : FoldedIn{});
             LAUNCH_CHECK("k_qkv_tc");
-        }
-        k_proj<<<ceil_div(rows_q, BM), NTHREADS, proj_smem_bytes(), st>>>(xq, 64, rows_q, w.in_proj_w, w.in_proj_b, 3, qkv, 192,
+        } else if (fold || ldx != 64) return fail(STTODE_EINVAL, "internal: folded front end without the tensor-core in-projection");
+        k_proj<<<ceil_div(rows_q, BM), NTHREADS, proj_smem_bytes(), st>>>(xq, ldx, rows_q, w.in_proj_w, w.in_proj_b, 3, qkv, 192,
                                                                         0x1u, 0x3u, scale, score_mode, curv, norms, 16, flags);
         LAUNCH_CHECK(flags ? "k_proj(redo)" : "k_proj");
         qb = qkv; kb = qkv + 64; vb = qkv + 128; ldq = ldk = 192;
@@ -167,19 +171,20 @@ int check_ptrs_mhgsa(const sttode_mhgsa_weights* w) {
 // ODE right-hand-side tail: tensor-core kernel when the weights come with their packed operand images, FP32-FFMA otherwise
 // (and for the tiles the tensor-core kernel flags: operands outside the fp16 range, NaN rows)
 int launch_ode_tail(const float* x, int ldx, const float* o, int ldo, const float* base, int ldb, float coef, int relu, float* out, int ldout,
-                    int rows, const sttode_ode_weights& w, int gate_only, Carver& ws, cudaStream_t st) {
+                    int rows, const sttode_ode_weights& w, int gate_only, Carver& ws, cudaStream_t st, const FoldedIn* fold = nullptr) {
     int rc;
     int* flags = nullptr;
     const int tiles = ceil_div(rows, BM);
     if (w.packed && !gate_only) {
         flags = ws.take<int>(tiles);
         if (!flags) return fail(STTODE_EWORKSPACE, "workspace too small for the ODE tile flags");
-        if ((rc = set_smem(k_ode_tail_tc, ode_tail_tc_smem_bytes(), "k_ode_tail_tc"))) return rc;
+        const size_t smt = ode_tail_tc_smem_bytes(fold ? fold->T : 0);
+        if ((rc = set_smem(k_ode_tail_tc, smt, "k_ode_tail_tc"))) return rc;
         CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int) * tiles, st));
-        k_ode_tail_tc<<<tiles, ode_tail_tc_threads(), ode_tail_tc_smem_bytes(), st>>>(x, ldx, o, ldo, base, ldb, coef, relu, out, ldout, rows, w,
-                                                                                    (const unsigned char*)w.packed, flags);
+        k_ode_tail_tc<<<tiles, ode_tail_tc_threads(), smt, st>>>(x, ldx, o, ldo, base, ldb, coef, relu, out, ldout, rows, w,
+                                                               (const unsigned char*)w.packed, flags, fold ? *fold : FoldedIn{});
         LAUNCH_CHECK("k_ode_tail_tc");
-    }
+    } else if (fold) return fail(STTODE_EINVAL, "internal: folded front end without the tensor-core ODE kernel");
     if ((rc = set_smem(k_ode_tail, ode_tail_smem_bytes(), "k_ode_tail"))) return rc;
     k_ode_tail<<<tiles, NTHREADS, ode_tail_smem_bytes(), st>>>(x, ldx, o, ldo, base, ldb, coef, relu, out, ldout, rows, w, gate_only, flags);
     LAUNCH_CHECK(flags ? "k_ode_tail(redo)" : "k_ode_tail");
@@ -524,7 +529,9 @@ int check_model(const sttode_model_weights* w, bool need_enc = true, bool need_d
     if (w->past_length < 2 || w->future_length < 1) return fail(STTODE_EINVAL, "past_length must be >= 2 and future_length >= 1");
     if (w->past_length > 200) return fail(STTODE_EINVAL, "past_length exceeds the positional table (200)");
     const void* const* p = (const void* const*)&w->past;
-    for (size_t i = 0; need_enc && i < sizeof(w->past) / sizeof(void*); ++i) if (!p[i]) return fail(STTODE_EINVAL, "past-encoder weight pointer %zu is null", i);
+    const size_t opt = offsetof(sttode_encoder_weights, ode.packed) / sizeof(void*), opt2 = offsetof(sttode_encoder_weights, folded) / sizeof(void*);
+    for (size_t i = 0; need_enc && i < sizeof(w->past) / sizeof(void*); ++i)       // the two optional members: NULL selects the FP32 kernels
+        if (!p[i] && i != opt && i != opt2) return fail(STTODE_EINVAL, "past-encoder weight pointer %zu is null", i);
     p = (const void* const*)&w->dec[0];
     for (size_t i = 0; need_dec && i < 2 * sizeof(w->dec[0]) / sizeof(void*); ++i) if (!p[i]) return fail(STTODE_EINVAL, "decoder weight pointer %zu is null", i);
     return 0;
@@ -697,12 +704,22 @@ int run_encoder(const float* traj, int layout, const int* scene_ptr, const int* 
     } else {
         if (L < 1 || agents < 1 || rows % (L * agents) != 0) return fail(STTODE_EINVAL, "rows (%d) must be a multiple of L*agents (%d*%d)", rows, L, agents);
     }
+    const int nb = scene_ptr ? rows : rows / (L * agents);
+    const int bsz = scene_ptr ? 1 : agents;
+    if (ew.folded && ew.ode.packed && T <= 32) {
+        // Tensor-core encoder: x0 comes out of the input staging of the first tcgen05 kernel (folded front end), so the raw trajectory is the
+        // only HBM input; past_feature[:, 0:64] = x0 and traj_norm are written by that kernel.  L = 1: one launch for the whole encoder.
+        const FoldedIn f{ew.folded, traj, layout, scene_ptr, row_scene, origin, agents, T, past_feature, traj_norm};
+        if (L == 1) return launch_ode_tail(past_feature, 128, nullptr, 0, past_feature, 128, 12.f, 1, past_feature + 64, 128, rows, ew.ode, 0, ws, st, &f);
+        float* o = nullptr;
+        if ((rc = run_attention(past_feature, past_feature, past_feature, true, ew.ode.attn, L, L, bsz, nb, STTODE_SCORE_OBLIQUE_ACOS, 1e-4f, 1.f, ws, &o,
+                                nullptr, st, nullptr, nullptr, ew.ode.packed, 128, &f))) return rc;
+        return launch_ode_tail(past_feature, 128, o, 64, past_feature, 128, 12.f, 1, past_feature + 64, 128, rows, ew.ode, 0, ws, st);
+    }
     const size_t sm = prologue_smem_bytes(T);
     if ((rc = set_smem(k_prologue, sm, "k_prologue"))) return rc;
     k_prologue<<<ceil_div(rows, BM), NTHREADS, sm, st>>>(traj, layout, scene_ptr, row_scene, origin, rows, agents, T, ew, past_feature, 128, traj_norm);
     LAUNCH_CHECK("k_prologue");
-    const int nb = scene_ptr ? rows : rows / (L * agents);
-    const int bsz = scene_ptr ? 1 : agents;
     // ODE block on x0 = past_feature[:, 0:64] (ld 128) -> past_feature[:, 64:128]
     // k_ode_tail / k_proj read x with ld 64 only through run_rhs: stage x0 contiguously when L > 1
     if (L == 1) return launch_ode_tail(past_feature, 128, nullptr, 0, past_feature, 128, 12.f, 1, past_feature + 64, 128, rows, ew.ode, 0, ws, st);
@@ -916,6 +933,19 @@ int sttode_device_check(void) {
     return 0;
 }
 
+size_t sttode_encoder_fold_bytes(int T) { return T > 0 ? fold_table_bytes(T) : 0; }
+
+int sttode_encoder_fold(const sttode_encoder_weights* w, int T, float* folded, size_t folded_bytes, void* stream) {
+    if (!w || !folded) return fail(STTODE_EINVAL, "null pointer");
+    if (T < 2 || T > 200) return fail(STTODE_EINVAL, "encoder_fold: T must be in [2, 200]");
+    if (!w->fc_w || !w->fc_b || !w->pe || !w->pefc_w || !w->pefc_b || !w->fc2_w || !w->fc2_b || !w->fc3_w || !w->fc3_b)
+        return fail(STTODE_EINVAL, "encoder_fold: null front-end weight");
+    if (folded_bytes < fold_table_bytes(T)) return fail(STTODE_EWORKSPACE, "folded buffer too small: %zu < %zu", folded_bytes, fold_table_bytes(T));
+    launch_fold_prologue(*w, T, folded, (cudaStream_t)stream);
+    LAUNCH_CHECK("k_fold_prologue");
+    return 0;
+}
+
 size_t sttode_ode_pack_bytes(void) { return ode_pack_bytes(); }
 
 int sttode_ode_pack(const sttode_ode_weights* w, void* packed, size_t packed_bytes, void* stream) {
@@ -1058,7 +1088,9 @@ int sttode_encoder_fwd(const float* feat4, int rows, int L, int agents, int T, c
     if (!feat4 || !w || !feature) return fail(STTODE_EINVAL, "null pointer");
     if (T < 1 || T > 200) return fail(STTODE_EINVAL, "T must be in [1, 200]");
     const void* const* p = (const void* const*)w;
-    for (size_t i = 0; i < sizeof(*w) / sizeof(void*); ++i) if (!p[i]) return fail(STTODE_EINVAL, "encoder weight pointer %zu is null", i);
+    for (size_t i = 0; i < sizeof(*w) / sizeof(void*); ++i)
+        if (!p[i] && i != offsetof(sttode_encoder_weights, ode.packed) / sizeof(void*) && i != offsetof(sttode_encoder_weights, folded) / sizeof(void*))
+            return fail(STTODE_EINVAL, "encoder weight pointer %zu is null", i);
     return run_encoder(feat4, STTODE_FEAT_RT4, nullptr, nullptr, 0, rows, L, agents, T, *w, feature, nullptr, nullptr, Carver(workspace, workspace_bytes),
                        (cudaStream_t)stream);
 }

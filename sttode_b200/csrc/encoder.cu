@@ -439,7 +439,7 @@ k_ode_tail(const float* __restrict__ x, int ldx, const float* __restrict__ attn_
         for (int j = 0; j < 4; ++j) {
             float v = __fmul_rn(coef, Bs[m * LDS64 + col[j]]);          // dt * f, then + y0: two roundings like the reference
             if (base) v = __fadd_rn(base[(size_t)r * ldb + col[j]], v);
-            out[(size_t)r * ldout + col[j]] = relu ? fmaxf(v, 0.f) : v;
+            out[(size_t)r * ldout + col[j]] = (relu && v < 0.f) ? 0.f : v;          // torch.relu keeps NaN (fmaxf would drop it)
         }
     }
 }
@@ -493,7 +493,7 @@ __global__ void k_lincomb(const float* __restrict__ base, int ldb, const float* 
     if (k1) v += c1 * k1[idx];
     if (k2) v += c2 * k2[idx];
     if (k3) v += c3 * k3[idx];
-    out[(size_t)r * ldout + n] = relu ? fmaxf(v, 0.f) : v;
+    out[(size_t)r * ldout + n] = (relu && v < 0.f) ? 0.f : v;
 }
 
 }  // namespace sttode

@@ -55,6 +55,118 @@ __global__ void k_pack_ode(sttode_ode_weights w, unsigned char* __restrict__ pk)
 size_t ode_pack_bytes() { return ODE_PACK_BYTES; }
 void launch_pack_ode(const sttode_ode_weights& w, unsigned char* pk, cudaStream_t st) { k_pack_ode<<<dim3(12, ODE_UNITS + 1), 128, 0, st>>>(w, pk); }
 
+// ---- folded encoder front end ------------------------------------------------------------------------------------------------------
+// In eval mode (PE dropout off) PastEncoder.forward up to the ODE block (model/STTODE.py:214-223) is a chain of Linear layers with no
+// nonlinearity in between — input_fc (4 -> 64), pos_encoder.fc on [. | pe_t] (128 -> 64), input_fc2 over the flattened time axis
+// (64 T -> 64), input_fc3 on [. | category] (67 -> 64) — i.e. ONE affine map of the 4 T input features:
+//     x0 = sum_t G_t in_t + g0 + flag * w3f ,   G_t = W3a W2_t Wpe1 Wfc  [64 x 4],
+//     g0 = W3a (sum_t W2_t (Wpe1 b_fc + Wpe2 pe_t + b_pe) + b_2) + b_3 ,   w3f = W3[:, 66].
+// k_fold_prologue builds the table [(4 T + 2), 64] = [G (k-major) | g0 | w3f] once per weight version, accumulating in float64 (so the
+// folded map is at least as accurate as the reference's fp32 chain); the tensor-core kernels then compute x0 in their input staging
+// (1024 FMAs per thread at T = 8) and the raw trajectory is the only HBM input of the encoder.  209 kFLOP/row -> 4 kFLOP/row.
+__global__ void __launch_bounds__(320) k_fold_prologue(sttode_encoder_weights w, int T, float* __restrict__ out) {
+    __shared__ double P1[64][5], U[64][5], V[64], acc4[64];
+    const int tid = threadIdx.x, n = tid / 5, c = tid - n * 5;
+    {   // P1[:, 0..3] = Wpe1 Wfc ; P1[:, 4] = Wpe1 b_fc + b_pe
+        double a = c == 4 ? (double)w.pefc_b[n] : 0.0;
+        for (int k = 0; k < 64; ++k) a += (double)w.pefc_w[n * 128 + k] * (c < 4 ? (double)w.fc_w[k * 4 + c] : (double)w.fc_b[k]);
+        P1[n][c] = a;
+    }
+    if (tid < 64) acc4[tid] = 0.0;
+    __syncthreads();
+    for (int t = 0; t < T; ++t) {
+        if (tid < 64) {
+            double a = P1[tid][4];
+            for (int k = 0; k < 64; ++k) a += (double)w.pefc_w[tid * 128 + 64 + k] * (double)w.pe[t * 64 + k];
+            V[tid] = a;
+        }
+        __syncthreads();
+        {
+            double a = 0.0;
+            for (int k = 0; k < 64; ++k) a += (double)w.fc2_w[(size_t)n * 64 * T + t * 64 + k] * (c < 4 ? P1[k][c] : V[k]);
+            U[n][c] = a;
+        }
+        __syncthreads();
+        if (c < 4) {
+            double a = 0.0;
+            for (int k = 0; k < 64; ++k) a += (double)w.fc3_w[n * 67 + k] * U[k][c];
+            out[(size_t)(t * 4 + c) * 64 + n] = (float)a;
+        } else {
+            acc4[n] += U[n][4];
+        }
+        __syncthreads();
+    }
+    if (tid < 64) {
+        double a = (double)w.fc3_b[tid];
+        for (int k = 0; k < 64; ++k) a += (double)w.fc3_w[tid * 67 + k] * (acc4[k] + (double)w.fc2_b[k]);
+        out[(size_t)(4 * T) * 64 + tid] = (float)a;
+        out[(size_t)(4 * T + 1) * 64 + tid] = w.fc3_w[tid * 67 + 66];
+    }
+}
+size_t fold_table_bytes(int T) { return (size_t)(4 * T + 2) * 64 * sizeof(float); }
+void launch_fold_prologue(const sttode_encoder_weights& w, int T, float* out, cudaStream_t st) { k_fold_prologue<<<1, 320, 0, st>>>(w, T, out); }
+
+// columns 32*half .. of x0 for row r from the raw trajectory (scene-centred positions + velocities, first step duplicated:
+// model/STTODE.py:417,429,582-596) or from explicit [x, y, vx, vy] features; tab_s = the folded table in shared memory
+__device__ __forceinline__ void folded_x0(const FoldedIn& f, const float* tab_s, int r, bool live, int half, bool write_norm, float (&v)[32]) {
+    const int T = f.T;
+    float flag = 0.f, ox = 0.f, oy = 0.f;
+    if (live) {
+        if (f.scene_ptr) {
+            const int sidx = f.row_scene[r];
+            flag = (r == f.scene_ptr[sidx + 1] - 1) ? 1.f : 0.f;
+            ox = f.origin[sidx * 2]; oy = f.origin[sidx * 2 + 1];
+        } else {
+            flag = ((r % f.agents) == f.agents - 1) ? 1.f : 0.f;
+        }
+    }
+    const float* g0 = tab_s + (size_t)(4 * T) * 64 + half * 32;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaf(flag, g0[64 + i], g0[i]);
+    if (!live) return;
+    const float* p = f.traj + (size_t)r * T * (f.layout == STTODE_FEAT_RT4 ? 4 : 2);
+    float ppx = 0.f, ppy = 0.f;                     // previous normalised position
+#pragma unroll 1
+    for (int t = 0; t < T; ++t) {
+        float in4[4];
+        if (f.layout == STTODE_FEAT_RT4) {
+            const float4 q = *reinterpret_cast<const float4*>(p + t * 4);
+            in4[0] = q.x; in4[1] = q.y; in4[2] = q.z; in4[3] = q.w;
+        } else {
+            auto pos = [&](int tt, float& x_, float& y_) {
+                if (f.layout == STTODE_TRAJ_RT2) { x_ = p[tt * 2] - ox; y_ = p[tt * 2 + 1] - oy; }
+                else                             { x_ = p[tt] - ox;     y_ = p[T + tt] - oy; }
+            };
+            float px, py;
+            pos(t, px, py);
+            if (t == 0) {                           // velocity of the first step duplicates the second
+                float qx, qy;
+                pos(1, qx, qy);
+                in4[2] = qx - px; in4[3] = qy - py;
+            } else {
+                in4[2] = px - ppx; in4[3] = py - ppy;
+            }
+            in4[0] = px; in4[1] = py;
+            ppx = px; ppy = py;
+            if (write_norm && f.traj_norm) *reinterpret_cast<float2*>(f.traj_norm + ((size_t)r * T + t) * 2) = make_float2(px, py);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float4* row = reinterpret_cast<const float4*>(tab_s + (size_t)(t * 4 + c) * 64 + half * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 m4 = row[q];
+                v[4 * q] = fmaf(in4[c], m4.x, v[4 * q]); v[4 * q + 1] = fmaf(in4[c], m4.y, v[4 * q + 1]);
+                v[4 * q + 2] = fmaf(in4[c], m4.z, v[4 * q + 2]); v[4 * q + 3] = fmaf(in4[c], m4.w, v[4 * q + 3]);
+            }
+        }
+    }
+}
+__device__ __forceinline__ void store_row32(float* p, const float (&v)[32]) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(p + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+
 // ---- shared pieces ----------------------------------------------------------------------------------------------------------------
 namespace otc {
 constexpr int THREADS = 320, EPI_WARPS = 8, ISSUER = 8, PRODUCER = 9;
@@ -63,6 +175,7 @@ constexpr int SM_A = 0;                          // A operand image, 128 rows x 
 constexpr int SM_H = 32768;                      // 2 x (hi 16 KB | lo 16 KB): staged FFN chunk operand
 constexpr int SM_RING = SM_H + 65536;
 constexpr int SM_BARS = SM_RING + NST * STAGE;   // 196608
+constexpr int SM_FOLD = SM_BARS + 256;           // folded front-end table [(4T+2), 64] fp32 (optional)
 constexpr int COL_D0 = 0, COL_DG = 64, COL_D1 = 192, COL_D2 = 320;
 enum { B_WFULL = 0, B_WFREE = 3, B_AFULL = 6, B_DFULL = 7, B_D1FULL = 8, B_HFULL = 10, B_HFREE = 12, B_D2FULL = 14, B_COUNT = 15 };
 constexpr float FP16_SAFE = 60000.f;
@@ -88,10 +201,11 @@ __device__ __forceinline__ void signal(uint64_t* bars, int bar) {
 }
 template <int N>
 __device__ __forceinline__ void track(const float (&v)[N], int& ovf) {
-    float mx = 0.f;
+    // integer max over |v| bit patterns: monotonic for finite values, and NaN patterns sort above inf (fmaxf would silently drop a NaN)
+    uint32_t mx = 0u;
 #pragma unroll
-    for (int i = 0; i < N; ++i) mx = fmaxf(mx, fabsf(v[i]));
-    ovf |= !(mx <= FP16_SAFE);                      // also true for NaN / inf
+    for (int i = 0; i < N; ++i) mx = max(mx, __float_as_uint(v[i]) & 0x7fffffffu);
+    ovf |= mx > __float_as_uint(FP16_SAFE);
 }
 // 32 consecutive-k values of row m (k chunks kc0 .. kc0+3) -> the 128-row operand image at `img` (hi) / img + 16384 (lo)
 __device__ __forceinline__ void stage32(unsigned char* img, int m, int kc0, const float (&v)[32], int& ovf) {
@@ -133,11 +247,14 @@ __device__ __forceinline__ void layernorm64(float (&s)[64], const float* __restr
 __global__ void __launch_bounds__(otc::THREADS, 1)
 k_ode_tail_tc(const float* __restrict__ x, int ldx, const float* __restrict__ attn_o, int ldo, const float* __restrict__ base, int ldb, float coef,
               int relu, float* __restrict__ out, int ldout, int rows, sttode_ode_weights w, const unsigned char* __restrict__ packed,
-              int* __restrict__ tile_flags) {
+              int* __restrict__ tile_flags, const FoldedIn fold) {
     using namespace otc;
     extern __shared__ __align__(128) unsigned char sm[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM_BARS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
+    float* tab_s = reinterpret_cast<float*>(sm + SM_FOLD);
+    if (fold.table)                                 // folded front end: x (= fold.x0_out, ld ldx) is produced by this kernel's input staging
+        for (int i = threadIdx.x; i < (4 * fold.T + 2) * 16; i += THREADS) reinterpret_cast<float4*>(tab_s)[i] = __ldg(reinterpret_cast<const float4*>(fold.table) + i);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wq = warp & 3, half = (warp >> 2) & 1;
     const int m = wq * 32 + lane, r = blockIdx.x * BM + m;
     const bool live = r < rows;
@@ -220,12 +337,16 @@ k_ode_tail_tc(const float* __restrict__ x, int ldx, const float* __restrict__ at
         uint32_t n_d = 0;
         float v[32];
         // input operand: x (value projection follows) or the attention output, columns 32*half .. of row m
-        {
+        if (fold.table) {                           // x0 from the raw trajectory; also this kernel's x / base (re-read below through L2)
+            folded_x0(fold, tab_s, r, live, half, half == 0, v);
+            if (live) store_row32(fold.x0_out + (size_t)r * ldx + half * 32, v);
+        }
+        if (!fold.table || !vproj) {
             const float* src = vproj ? x + (size_t)r * ldx : attn_o + (size_t)r * ldo;
             load_row32(v, live ? src + half * 32 : nullptr);
-            stage32(A, m, half * 4, v, ovf);
-            signal(bars, B_AFULL);
         }
+        stage32(A, m, half * 4, v, ovf);
+        signal(bars, B_AFULL);
         if (vproj) {                                // v = x.W_v^T + b_v
             wait(bars, B_DFULL, n_d++ & 1); tc::tc_fence_after();
             tc::tmem_ld32(tmem + lane_base + COL_D0 + half * 32, v);
@@ -252,7 +373,7 @@ k_ode_tail_tc(const float* __restrict__ x, int ldx, const float* __restrict__ at
                 tc::tmem_ld16(tmem + lane_base + COL_DG + 64 + q * 16, ug);
 #pragma unroll
                 for (int i4 = 0; i4 < 4; ++i4) {
-                    const float4 xr = live ? __ldg(reinterpret_cast<const float4*>(x + (size_t)r * ldx + q * 16) + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 xr = live ? __ldcg(reinterpret_cast<const float4*>(x + (size_t)r * ldx + q * 16) + i4) : make_float4(0.f, 0.f, 0.f, 0.f);   // L2: x may have been written by this CTA
                     const float xv[4] = {xr.x, xr.y, xr.z, xr.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -299,8 +420,8 @@ k_ode_tail_tc(const float* __restrict__ x, int ldx, const float* __restrict__ at
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         float t = __fmul_rn(coef, s[q * 4 + i]);          // dt * f, then + y0: two roundings like the reference
-                        if (base) t = __fadd_rn(__ldg(base + (size_t)r * ldb + q * 4 + i), t);
-                        o4[i] = relu ? fmaxf(t, 0.f) : t;
+                        if (base) t = __fadd_rn(__ldcg(base + (size_t)r * ldb + q * 4 + i), t);
+                        o4[i] = (relu && t < 0.f) ? 0.f : t;
                     }
                     *reinterpret_cast<float4*>(out + (size_t)r * ldout + q * 4) = make_float4(o4[0], o4[1], o4[2], o4[3]);
                 }
@@ -312,7 +433,7 @@ k_ode_tail_tc(const float* __restrict__ x, int ldx, const float* __restrict__ at
     __syncthreads();
     if (warp == ISSUER) tc::tmem_dealloc(tmem, 512);
 }
-size_t ode_tail_tc_smem_bytes() { return (size_t)otc::SM_BARS + otc::B_COUNT * 8 + 16; }
+size_t ode_tail_tc_smem_bytes(int fold_T) { return (size_t)otc::SM_FOLD + (fold_T > 0 ? fold_table_bytes(fold_T) : 0); }
 int ode_tail_tc_threads() { return otc::THREADS; }
 
 // =====================================================================================================================================
@@ -320,16 +441,19 @@ int ode_tail_tc_threads() { return otc::THREADS; }
 // Oblique manifold per head: p / |p|, no epsilon — a zero row yields NaN exactly as the reference does).  One N = 192 MMA group.
 // =====================================================================================================================================
 namespace qtc {
-constexpr int SM_A = 0, SM_W = 32768, SM_BARS = SM_W + 2 * ODE_QKV_IMG;      // 32 KB + 48 KB
+constexpr int SM_A = 0, SM_W = 32768, SM_BARS = SM_W + 2 * ODE_QKV_IMG, SM_FOLD = SM_BARS + 64;      // 32 KB + 48 KB (+ folded table)
 enum { B_W = 0, B_A = 1, B_D = 2, B_COUNT = 3 };
 }
 __global__ void __launch_bounds__(otc::THREADS, 1)
 k_qkv_tc(const float* __restrict__ x, int ldx, int rows, const float* __restrict__ in_b, float scale, const unsigned char* __restrict__ packed,
-         float* __restrict__ out, int ldo_, int* __restrict__ tile_flags) {
+         float* __restrict__ out, int ldo_, int* __restrict__ tile_flags, const FoldedIn fold) {
     using namespace otc;
     extern __shared__ __align__(128) unsigned char sm[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + qtc::SM_BARS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + qtc::B_COUNT);
+    float* tab_s = reinterpret_cast<float*>(sm + qtc::SM_FOLD);
+    if (fold.table)
+        for (int i = threadIdx.x; i < (4 * fold.T + 2) * 16; i += THREADS) reinterpret_cast<float4*>(tab_s)[i] = __ldg(reinterpret_cast<const float4*>(fold.table) + i);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wq = warp & 3, half = (warp >> 2) & 1;
     const int m = wq * 32 + lane, r = blockIdx.x * BM + m;
     const bool live = r < rows;
@@ -364,7 +488,12 @@ k_qkv_tc(const float* __restrict__ x, int ldx, int rows, const float* __restrict
     } else {
         const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
         float v[32];
-        load_row32(v, live ? x + (size_t)r * ldx + half * 32 : nullptr);
+        if (fold.table) {
+            folded_x0(fold, tab_s, r, live, half, half == 0, v);
+            if (live) store_row32(fold.x0_out + (size_t)r * ldx + half * 32, v);
+        } else {
+            load_row32(v, live ? x + (size_t)r * ldx + half * 32 : nullptr);
+        }
         stage32(sm + qtc::SM_A, m, half * 4, v, ovf);
         signal(bars, qtc::B_A);
         if (!tc::mbar_wait(bars + qtc::B_D, 0)) { printf("k_qkv_tc: MMA never completed\n"); __trap(); }
@@ -402,6 +531,6 @@ k_qkv_tc(const float* __restrict__ x, int ldx, int rows, const float* __restrict
     __syncthreads();
     if (warp == ISSUER) tc::tmem_dealloc(tmem, 256);
 }
-size_t qkv_tc_smem_bytes() { return (size_t)qtc::SM_BARS + qtc::B_COUNT * 8 + 16; }
+size_t qkv_tc_smem_bytes(int fold_T) { return (size_t)qtc::SM_FOLD + (fold_T > 0 ? fold_table_bytes(fold_T) : 0); }
 
 }  // namespace sttode

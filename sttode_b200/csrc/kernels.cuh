@@ -29,12 +29,21 @@ size_t ode_tail_smem_bytes();
 // encoder_tc.cu — tensor-core (tcgen05) in-projection and ODE right-hand side + weight packing
 size_t ode_pack_bytes();
 void launch_pack_ode(const sttode_ode_weights& w, unsigned char* pk, cudaStream_t st);
+// folded encoder front end (k_fold_prologue): when `table` is set, the tensor-core kernels compute x0 from the raw trajectory in their input
+// staging and write it to x0_out (the kernel's `x` with its ld) and the scene-normalised positions to traj_norm
+struct FoldedIn {
+    const float* table;         // [(4 T + 2), 64] from k_fold_prologue, or nullptr
+    const float* traj; int layout; const int* scene_ptr; const int* row_scene; const float* origin; int agents; int T;
+    float* x0_out; float* traj_norm;
+};
+size_t fold_table_bytes(int T);
+void launch_fold_prologue(const sttode_encoder_weights& w, int T, float* out, cudaStream_t st);
 __global__ void k_ode_tail_tc(const float* x, int ldx, const float* attn_o, int ldo, const float* base, int ldb, float coef, int relu, float* out,
-                              int ldout, int rows, sttode_ode_weights w, const unsigned char* packed, int* tile_flags);
+                              int ldout, int rows, sttode_ode_weights w, const unsigned char* packed, int* tile_flags, const FoldedIn fold);
 __global__ void k_qkv_tc(const float* x, int ldx, int rows, const float* in_b, float scale, const unsigned char* packed, float* out, int ldo,
-                         int* tile_flags);
-size_t ode_tail_tc_smem_bytes();
-size_t qkv_tc_smem_bytes();
+                         int* tile_flags, const FoldedIn fold);
+size_t ode_tail_tc_smem_bytes(int fold_T);
+size_t qkv_tc_smem_bytes(int fold_T);
 int ode_tail_tc_threads();
 
 // backward.cu

@@ -112,14 +112,52 @@ class PositionalAgentEncoding(nn.Module):
         self.register_buffer("pe", pe)
 
 
-def _encoder_struct(enc):
+class _FoldedFrontEnd:
+    """The eval-mode encoder front end (input_fc, pos_encoder.fc, input_fc2, input_fc3: Linear layers with nothing nonlinear between them)
+    collapsed to one affine map of the 4 T input features (sttode_encoder_fold, float64 accumulation).  One persistent buffer, rebuilt in
+    place when a front-end weight changes (same staleness rules as _PackedDecoder)."""
+
+    def __init__(self):
+        self.key, self.buf, self.packs = None, None, 0
+
+    def invalidate(self):
+        self.key = None
+
+    def __deepcopy__(self, memo):
+        return _FoldedFrontEnd()
+
+    def get(self, enc, T):
+        params = [enc.input_fc.weight, enc.input_fc.bias, enc.pos_encoder.pe, enc.pos_encoder.fc.weight, enc.pos_encoder.fc.bias,
+                  enc.input_fc2.weight, enc.input_fc2.bias, enc.input_fc3.weight, enc.input_fc3.bias]
+        key = tuple((p.data_ptr(), p._version) for p in params) + (T,)
+        if key != self.key:
+            lib = _lib.lib()
+            nbytes = lib.sttode_encoder_fold_bytes(T)
+            if self.buf is None or self.buf.device != params[0].device or self.buf.numel() * 4 != nbytes:
+                self.buf = torch.empty(nbytes // 4, dtype=torch.float32, device=params[0].device)
+            st = _encoder_struct(enc, tensor_cores=False)
+            _lib.check(lib.sttode_encoder_fold(C.byref(st), T, _lib.dptr(self.buf), nbytes, _lib.stream_ptr()))
+            self.key = key
+            self.packs += 1
+        return self.buf
+
+
+def _encoder_struct(enc, tensor_cores=None):
+    """sttode_encoder_weights of a Past/FutureEncoder.  tensor_cores (default: eval mode, `use_tensor_cores` set, sequence length <= 32): the
+    struct also carries the ODE block's tensor-core operand images and the folded front-end table, which selects the tcgen05 encoder kernels."""
     s = _lib.EncoderWeights()
     s.fc_w, s.fc_b = _lib.dptr(enc.input_fc.weight), _lib.dptr(enc.input_fc.bias)
     s.pe = _lib.dptr(enc.pos_encoder.pe)
     s.pefc_w, s.pefc_b = _lib.dptr(enc.pos_encoder.fc.weight), _lib.dptr(enc.pos_encoder.fc.bias)
     s.fc2_w, s.fc2_b = _lib.dptr(enc.input_fc2.weight), _lib.dptr(enc.input_fc2.bias)
     s.fc3_w, s.fc3_b = _lib.dptr(enc.input_fc3.weight), _lib.dptr(enc.input_fc3.bias)
-    s.ode = _ode_struct(enc.ODE_Encoder.odeblock.odefunc.layers[0])
+    layer = enc.ODE_Encoder.odeblock.odefunc.layers[0]
+    if tensor_cores is None:
+        tensor_cores = not enc.training and layer.use_tensor_cores
+    s.ode = _ode_struct(layer, tensor_cores=bool(tensor_cores))
+    T = enc.input_fc2.weight.shape[1] // 64
+    if tensor_cores and getattr(enc, "fold_front_end", True) and T <= 32:
+        s.folded = _lib.dptr(enc._packed.get(enc, T))
     return s
 
 
@@ -133,6 +171,8 @@ class _EncoderBase(nn.Module):
         self.input_fc = nn.Linear(in_dim, self.model_dim)
         self.input_fc2 = nn.Linear(self.model_dim * length, self.model_dim)
         self.input_fc3 = nn.Linear(self.model_dim + 3, self.model_dim)
+        self.fold_front_end = True                # eval mode: front end folded into one affine map inside the tensor-core kernels
+        self._packed = _FoldedFrontEnd()
         self.nhead, self.ff_dim, self.dropout, self.nlayer = 8, 1024, 0., 1
         self.ODE_Encoder = ODEG_Encoder(TransformerEncoderLayer(self.model_dim, self.nhead, self.ff_dim, self.dropout), self.nlayer, 12)
         self.pos_encoder = PositionalAgentEncoding(self.model_dim, 0.1, concat=True)
@@ -523,7 +563,7 @@ class ForecastGraph:
         mw = self.model._weights()
         mw.rng_state = self.rng_state.data_ptr()
         self._mw = mw
-        self._packed_ptrs = (mw.dec_packed, mw.past.ode.packed)
+        self._packed_ptrs = (mw.dec_packed, mw.past.ode.packed, mw.past.folded)
         _lib.check(_lib.lib().sttode_forecast(_lib.dptr(self.traj), self.layout, _lib.dptr(self.scene_ptr), _lib.dptr(self.row_scene),
                                               self.n_scenes, self.rows, self.L, self.agents, None, self.seed, self.K, C.byref(mw),
                                               _lib.dptr(self.pred), _lib.dptr(self.past_feature), _lib.dptr(self.traj_norm),
@@ -596,7 +636,9 @@ class STTODENet(nn.Module):
         d = dec._packed.get(dec, self.args.past_length, self.args.future_length).data_ptr() if dec.use_tensor_cores else None
         layer = self.past_encoder.ODE_Encoder.odeblock.odefunc.layers[0]
         pk = layer._packed_or_none()
-        return (d, pk.data_ptr() if pk is not None else None)
+        enc = self.past_encoder
+        fd = enc._packed.get(enc, self.args.past_length).data_ptr() if (pk is not None and enc.fold_front_end and self.args.past_length <= 32) else None
+        return (d, pk.data_ptr() if pk is not None else None, fd)
 
     def set_tensor_cores(self, on):
         """Select the tcgen05 tensor-core kernels (default) or the FP32-FFMA kernels for the decoder and both ODE blocks."""

@@ -188,6 +188,7 @@ def test_headline_shape_in_batch_vs_oracle(dev):
         cur = (past[:, -1] + orig)[:, None, None, :]
         assert rel_rows(pred[r0:r0 + n] - cur, ref - cur) < TOL, f"scene at row {r0}"
         assert rel_rows(pf[r0:r0 + n, 64:], dump["past_feature"][:, 64:], scale_floor=1e-3) < TOL
+        assert rel_rows(pf[r0:r0 + n, :64], dump["past_feature"][:, :64], scale_floor=1e-2) < TOL     # x0: the folded front end
         refs.append(ref)
         r0 += n
     a0, f0 = O.min_ade_fde(torch.cat(refs), gt.permute(0, 2, 1))
@@ -307,3 +308,45 @@ def test_ode_block_tensor_cores_clamp_nan_and_range(dev):
     yb = _ode_encoder(O.make_state_dict(1, 8, 12), dev, True)(xb.to(dev)).reshape(260, 64)
     assert torch.isfinite(yb).all()
     assert rel_rows(yb, refb, scale_floor=1e-2) < TOL
+
+
+@pytest.mark.parametrize("dataset,tp,tf,B,N", [("eth", 8, 12, 1, 37), ("nba", 10, 20, 24, 11), ("nba", 5, 10, 130, 11)])
+def test_folded_front_end_vs_layer_by_layer(dev, dataset, tp, tf, B, N):
+    """The eval-mode front end folded into one affine map (sttode_encoder_fold, inside the tensor-core kernels' input staging) against the
+    layer-by-layer FP32 prologue kernel and the float64 oracle: past_feature (x0 | ODE output), traj_norm, and the FutureEncoder eval path
+    (explicit [x, y, vx, vy] features, T = future_length)."""
+    m, sd = build_model(dataset, tp, tf, 5, dev)
+    if dataset == "eth":
+        obs, gt = synth.eth_scene(11, N)
+        sp = torch.tensor([0, N], dtype=torch.int32)
+        run = lambda: (m.forecast_scenes(obs.to(dev), sp), m.past_feature.clone(), m.past_traj.clone())
+        past, orig = O.eth_scene_normalise(obs)
+    else:
+        data = synth.nba_batch(8, B, N, tp, tf)
+        run = lambda: (m.inference(data), m.past_feature.clone(), m.past_traj.clone())
+        past = data["past_traj"].view(B * N, tp, 2)
+    m.z_override = synth.latent(B * N, seed=2)
+    _, pf_fold, tn_fold = run()
+    assert m.past_encoder._packed.packs == 1
+    m.past_encoder.fold_front_end = False
+    _, pf_layers, tn_layers = run()
+    m.past_encoder.fold_front_end = True
+    m.set_tensor_cores(False)
+    _, pf_ffma, _ = run()
+    m.set_tensor_cores(True)
+    m.z_override = None
+    ref = O.past_encoder(O.velocity_features(past.double()), B, N, O.cast_state_dict(sd, torch.float64))
+    for got in (pf_fold, pf_layers, pf_ffma):
+        assert rel_rows(got[:, :64], ref[:, :64], scale_floor=1e-2) < TOL
+        assert rel_rows(got[:, 64:], ref[:, 64:], scale_floor=1e-2) < TOL
+    assert torch.equal(tn_fold, tn_layers)                          # scene-normalised positions: same arithmetic in both kernels
+    assert rel_rows(tn_fold, past, scale_floor=1e-3) < 1e-6
+    # FutureEncoder, eval mode: explicit features through sttode_encoder_fwd
+    fut = (synth.eth_scene(11, B * N, tp, tf)[1].permute(0, 2, 1) if dataset == "eth" else data["future_traj"].view(B * N, tf, 2)).contiguous()
+    feats = O.posterior_inputs(past, fut - (orig if dataset == "eth" else 0)).to(dev)
+    q_fold = m.future_encoder(feats, B, N, pf_fold)
+    m.future_encoder.fold_front_end = False
+    q_layers = m.future_encoder(feats, B, N, pf_fold)
+    m.future_encoder.fold_front_end = True
+    q_ref = O.future_encoder(feats.cpu().double(), B, N, ref, O.cast_state_dict(sd, torch.float64))
+    assert rel_rows(q_fold, q_ref, scale_floor=1e-2) < TOL and rel_rows(q_layers, q_ref, scale_floor=1e-2) < TOL

@@ -11,8 +11,9 @@ from training_common import assert_grad_close, grad_sample_index, training_draws
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
 # gradients of the sampler pass through exp(-|y_i - y_j|^2) of the diversity term and the whole decoder; two fp32 evaluations of that chain
-# (reference on CPU, this on GPU) agree to ~1e-4 in L2, so the gradient bound is 3e-4 (losses and predictions stay at 1e-4)
-GRAD_TOL = 3e-4
+# (reference on CPU, this on GPU) agree to ~1e-4 .. 4e-4 in L2 (the frozen net's encoders and decoder run on the 3xFP16 tensor-core kernels,
+# whose ~5e-7 forward rounding this chain amplifies ~1e3 times), so the gradient bound is 6e-4 (losses and predictions stay at 1e-4)
+GRAD_TOL = 6e-4
 
 
 def sampler_args(dataset, tp, tf):
