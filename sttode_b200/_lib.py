@@ -186,3 +186,28 @@ def workspace(nbytes, device):
 
 def launch_count():
     return int(load().sttode_launch_count())
+
+
+# ---- direct gradient sinks -------------------------------------------------------------------------------------------------------------
+# The library's backward kernels ACCUMULATE parameter gradients (+=).  When the parameters' `.grad` tensors already exist (parallel.FlatGradReducer
+# makes them views into one flat buffer) the autograd nodes let the kernels write straight into them and return no parameter gradient, instead of
+# filling a zero tensor per parameter and having autograd add it to `.grad` afterwards (two extra launches per parameter per node).
+DIRECT_GRAD_SINKS = False
+
+
+def grad_sinks(params):
+    """The `.grad` tensors of `params` if every one is a preallocated contiguous fp32 CUDA tensor of the parameter's shape (and sinks are enabled)."""
+    if not DIRECT_GRAD_SINKS:
+        return None
+    sinks = []
+    for p in params:
+        g = getattr(p, "grad", None)
+        if g is None or not g.is_cuda or g.dtype != torch.float32 or g.shape != p.shape or not g.is_contiguous() or not p.requires_grad:
+            return None
+        sinks.append(g)
+    return sinks
+
+
+def sinks_still_valid(params, sinks):
+    """True if every parameter's `.grad` is still the tensor recorded at forward time (zero_grad(set_to_none=True) would break the link)."""
+    return sinks is not None and all(p.grad is not None and p.grad.data_ptr() == s.data_ptr() for p, s in zip(params, sinks))

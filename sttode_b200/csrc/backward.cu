@@ -451,6 +451,130 @@ __global__ void k_gru_step_bwd(const float* __restrict__ dh, const float* __rest
     hp[u] = dr; hp[96 + u] = dz; hp[192 + u] = dn * r;
     dh_prev[idx] = d * z;
 }
+// ---- GRU through time, one launch per direction ---------------------------------------------------------------------------------
+// The recurrence is row-local (h_t of a row depends only on that row's h_{t-1}), so a CTA owns GRU_R rows for ALL T steps with W_hh
+// resident in shared memory: one launch replaces the T x (GEMM + gate kernel) launches of the step-by-step form.
+// Thread (u = tid % 96, rg = tid / 96) owns hidden unit u (forward) / state column k = u (backward) of rows rg*8 .. rg*8+7.
+constexpr int GRU_R = 32, GRU_THREADS = 384, GRU_LDH = 100, GRU_LDG = 292;
+
+// forward: gi [P, T, 288] (row stride ldgi, input projections incl. b_ih), h [T+1, P, 96] (h[0] given), saves rzn [T, P, 288], ghn [T, P, 96]
+__global__ void __launch_bounds__(GRU_THREADS, 1)
+k_gru_seq_fwd(const float* __restrict__ gi, long ldgi, const float* __restrict__ w_hh, const float* __restrict__ b_hh, int P, int T,
+              float* __restrict__ h, float* __restrict__ rzn, float* __restrict__ ghn) {
+    extern __shared__ __align__(16) float smem[];
+    float* Wt = smem;                               // [96][288]: Wt[k][n] = W_hh[n][k]
+    float* hs = Wt + 96 * 288;                      // [GRU_R][GRU_LDH]
+    const int tid = threadIdx.x, u = tid % 96, rg = tid / 96, row0 = blockIdx.x * GRU_R;
+    for (int i = tid; i < 288 * 96; i += GRU_THREADS) { const int n = i / 96, k = i - n * 96; Wt[k * 288 + n] = __ldg(w_hh + i); }
+    for (int i = tid; i < GRU_R * 96; i += GRU_THREADS) {
+        const int rr = i / 96, c = i - rr * 96, p = row0 + rr;
+        hs[rr * GRU_LDH + c] = p < P ? h[(size_t)p * 96 + c] : 0.f;
+    }
+    const float br = __ldg(b_hh + u), bz = __ldg(b_hh + 96 + u), bn = __ldg(b_hh + 192 + u);
+    __syncthreads();
+    for (int t = 0; t < T; ++t) {
+        float acc[8][3];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = 0.f;
+#pragma unroll 2
+        for (int k = 0; k < 96; k += 4) {
+            float w[3][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int g = 0; g < 3; ++g) w[g][j] = Wt[(k + j) * 288 + g * 96 + u];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 h4 = *reinterpret_cast<const float4*>(hs + (rg * 8 + i) * GRU_LDH + k);
+#pragma unroll
+                for (int g = 0; g < 3; ++g) {
+                    acc[i][g] = fmaf(h4.x, w[g][0], acc[i][g]); acc[i][g] = fmaf(h4.y, w[g][1], acc[i][g]);
+                    acc[i][g] = fmaf(h4.z, w[g][2], acc[i][g]); acc[i][g] = fmaf(h4.w, w[g][3], acc[i][g]);
+                }
+            }
+        }
+        __syncthreads();                            // every dot product has read the old state
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int rr = rg * 8 + i, p = row0 + rr;
+            if (p >= P) continue;
+            const float* gip = gi + (size_t)p * ldgi + (size_t)t * 288;
+            const float r = sigmoidf_(gip[u] + acc[i][0] + br), z = sigmoidf_(gip[96 + u] + acc[i][1] + bz);
+            const float gn = acc[i][2] + bn;
+            const float n = tanhf(gip[192 + u] + r * gn);
+            const float hn = (1.f - z) * n + z * hs[rr * GRU_LDH + u];
+            float* rz = rzn + ((size_t)t * P + p) * 288;
+            rz[u] = r; rz[96 + u] = z; rz[192 + u] = n;
+            ghn[((size_t)t * P + p) * 96 + u] = gn;
+            h[((size_t)(t + 1) * P + p) * 96 + u] = hn;
+            hs[rr * GRU_LDH + u] = hn;
+        }
+        __syncthreads();
+    }
+}
+
+// backward (BPTT): dh_T [P, 96] (row stride lddh) -> d gi [P, T, 288] (row stride lddgi), d gh [T, P, 288]; dh_0 is discarded (h_0 = 0 is a constant)
+__global__ void __launch_bounds__(GRU_THREADS, 1)
+k_gru_seq_bwd(const float* __restrict__ dh_T, long lddh, const float* __restrict__ w_hh, const float* __restrict__ rzn, const float* __restrict__ ghn,
+              const float* __restrict__ h, int P, int T, float* __restrict__ dgi, long lddgi, float* __restrict__ dgh) {
+    extern __shared__ __align__(16) float smem[];
+    float* W = smem;                                // [288][96] as stored
+    float* gs = W + 288 * 96;                       // [GRU_R][GRU_LDG]: d gh of the current step
+    float* ds = gs + GRU_R * GRU_LDG;               // [GRU_R][GRU_LDH]: running dh
+    const int tid = threadIdx.x, u = tid % 96, rg = tid / 96, row0 = blockIdx.x * GRU_R;
+    for (int i = tid; i < 288 * 96; i += GRU_THREADS) W[i] = __ldg(w_hh + i);
+    for (int i = tid; i < GRU_R * 96; i += GRU_THREADS) {
+        const int rr = i / 96, c = i - rr * 96, p = row0 + rr;
+        ds[rr * GRU_LDH + c] = p < P ? dh_T[(size_t)p * lddh + c] : 0.f;
+    }
+    __syncthreads();
+    for (int t = T - 1; t >= 0; --t) {
+        float carry[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int rr = rg * 8 + i, p = row0 + rr;
+            float dr = 0.f, dz = 0.f, dn = 0.f, dnr = 0.f;
+            carry[i] = 0.f;
+            if (p < P) {
+                const float* rz = rzn + ((size_t)t * P + p) * 288;
+                const float r = rz[u], z = rz[96 + u], n = rz[192 + u];
+                const float d = ds[rr * GRU_LDH + u], gn = ghn[((size_t)t * P + p) * 96 + u];
+                dn = d * (1.f - z) * (1.f - n * n);         // through tanh
+                dz = d * (h[((size_t)t * P + p) * 96 + u] - n) * z * (1.f - z);
+                dr = dn * gn * r * (1.f - r);
+                dnr = dn * r;
+                carry[i] = d * z;
+                float* gp = dgi + (size_t)p * lddgi + (size_t)t * 288;
+                gp[u] = dr; gp[96 + u] = dz; gp[192 + u] = dn;
+                float* hp = dgh + ((size_t)t * P + p) * 288;
+                hp[u] = dr; hp[96 + u] = dz; hp[192 + u] = dnr;
+            }
+            gs[rr * GRU_LDG + u] = dr; gs[rr * GRU_LDG + 96 + u] = dz; gs[rr * GRU_LDG + 192 + u] = dnr;
+        }
+        __syncthreads();
+        if (t == 0) break;                          // dh_0 is not needed
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll 2
+        for (int n = 0; n < 288; n += 4) {
+            const float w0 = W[n * 96 + u], w1 = W[(n + 1) * 96 + u], w2 = W[(n + 2) * 96 + u], w3 = W[(n + 3) * 96 + u];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 g4 = *reinterpret_cast<const float4*>(gs + (rg * 8 + i) * GRU_LDG + n);
+                acc[i] = fmaf(g4.x, w0, acc[i]); acc[i] = fmaf(g4.y, w1, acc[i]); acc[i] = fmaf(g4.z, w2, acc[i]); acc[i] = fmaf(g4.w, w3, acc[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ds[(rg * 8 + i) * GRU_LDH + u] = carry[i] + acc[i];      // own (row, column) element: no other thread reads ds before the sync
+        __syncthreads();
+    }
+}
+size_t gru_seq_fwd_smem_bytes() { return sizeof(float) * ((size_t)96 * 288 + GRU_R * GRU_LDH); }
+size_t gru_seq_bwd_smem_bytes() { return sizeof(float) * ((size_t)288 * 96 + GRU_R * GRU_LDG + GRU_R * GRU_LDH); }
+int gru_seq_rows() { return GRU_R; }
+int gru_seq_threads() { return GRU_THREADS; }
+
 // dst[r, 0:n] = src[r, 0:n]   (row strides in floats)
 __global__ void k_rows_copy(const float* __restrict__ src, long lds, float* __restrict__ dst, long ldd, int rows, int n) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -600,13 +600,12 @@ int dec_block_fwd(cudaStream_t st, int P, int Tp, const sttode_decompose_weights
     if ((rc = gemm_nt(st, PT, 32, 6, b.col, 6, w.conv_w, w.conv_b, b.c, 32, 1))) return rc;
     if ((rc = gemm_nt(st, PT, 288, 32, b.c, 32, w.gru_w_ih, w.gru_b_ih, b.gi, 288))) return rc;
     CUDA_TRY(cudaMemsetAsync(b.h, 0, (size_t)P * 96 * 4, st));
-    for (int t = 0; t < Tp; ++t) {
-        const float* ht = b.h + (size_t)t * P * 96;
-        if ((rc = gemm_nt(st, P, 288, 96, ht, 96, w.gru_w_hh, w.gru_b_hh, gh, 288))) return rc;
-        k_gru_step_fwd<<<ceil_div(P * 96, 256), 256, 0, st>>>(b.gi + (size_t)t * 288, (long)Tp * 288, gh, ht, P, b.rzn + (size_t)t * P * 288,
-                                                              b.ghn + (size_t)t * P * 96, b.h + (size_t)(t + 1) * P * 96);
-        LAUNCH_CHECK("k_gru_step_fwd");
-    }
+    // the whole recurrence in one launch: a CTA owns 32 rows for all T_p steps, W_hh resident in shared memory (saves r|z|n, W_hn h + b and h_t)
+    (void)gh;
+    if ((rc = set_smem(k_gru_seq_fwd, gru_seq_fwd_smem_bytes(), "k_gru_seq_fwd"))) return rc;
+    k_gru_seq_fwd<<<ceil_div(P, gru_seq_rows()), gru_seq_threads(), gru_seq_fwd_smem_bytes(), st>>>(b.gi, (long)Tp * 288, w.gru_w_hh, w.gru_b_hh, P, Tp, b.h,
+                                                                                                 b.rzn, b.ghn);
+    LAUNCH_CHECK("k_gru_seq_fwd");
     k_rows_copy<<<ceil_div(P * 128, 256), 256, 0, st>>>(pf, 128, b.feat, 256, P, 128);
     LAUNCH_CHECK("k_rows_copy");
     k_rows_copy<<<ceil_div(P * 32, 256), 256, 0, st>>>(z, 32, b.feat + 128, 256, P, 32);
@@ -621,16 +620,12 @@ int dec_block_bwd(cudaStream_t st, int P, int Tp, const sttode_decompose_weights
                   const float* dfeat, float* dh, float* dh2, float* dgi, float* dgh, float* dc, float* dcol, float* splitk) {
     int rc;
     const int PT = P * Tp;
-    k_rows_copy<<<ceil_div(P * 96, 256), 256, 0, st>>>(dfeat + 160, 256, dh, 96, P, 96);
-    LAUNCH_CHECK("k_rows_copy");
-    for (int t = Tp - 1; t >= 0; --t) {
-        float* dght = dgh + (size_t)t * P * 288;
-        k_gru_step_bwd<<<ceil_div(P * 96, 256), 256, 0, st>>>(dh, b.rzn + (size_t)t * P * 288, b.ghn + (size_t)t * P * 96, b.h + (size_t)t * P * 96, P,
-                                                              dgi + (size_t)t * 288, (long)Tp * 288, dght, dh2);
-        LAUNCH_CHECK("k_gru_step_bwd");
-        if ((rc = gemm_nn(st, P, 96, 288, dght, 288, w.gru_w_hh, dh2, 96, nullptr, 0, nullptr, 0, 1, splitk))) return rc;      // += d gh W_hh
-        std::swap(dh, dh2);
-    }
+    // BPTT in one launch (row-local recurrence, W_hh resident in shared memory): d gi and d gh of every step, starting from dfeat[:, 160:256] = d h_T
+    (void)dh; (void)dh2;
+    if ((rc = set_smem(k_gru_seq_bwd, gru_seq_bwd_smem_bytes(), "k_gru_seq_bwd"))) return rc;
+    k_gru_seq_bwd<<<ceil_div(P, gru_seq_rows()), gru_seq_threads(), gru_seq_bwd_smem_bytes(), st>>>(dfeat + 160, 256, w.gru_w_hh, b.rzn, b.ghn, b.h, P, Tp, dgi,
+                                                                                                 (long)Tp * 288, dgh);
+    LAUNCH_CHECK("k_gru_seq_bwd");
     // h_0 .. h_{T-1} and d gh_0 .. d gh_{T-1} are contiguous [T*P, .] stacks: one product for the recurrent weight
     if ((rc = weight_grad(st, Tp * P, 288, 96, dgh, 288, b.h, 96, g.gru_w_hh, g.gru_b_hh, splitk))) return rc;
     if ((rc = weight_grad(st, PT, 288, 32, dgi, 288, b.c, 32, g.gru_w_ih, g.gru_b_ih, splitk))) return rc;

@@ -70,6 +70,13 @@ __global__ void k_conv_col2im_neg(const float* dcol, const float* base, int P, i
 __global__ void k_gru_step_fwd(const float* gi, long ldgi, const float* gh, const float* h, int P, float* rzn, float* ghn, float* hout);
 __global__ void k_gru_step_bwd(const float* dh, const float* rzn, const float* ghn, const float* hprev, int P, float* dgi, long lddgi, float* dgh,
                                float* dh_prev);
+__global__ void k_gru_seq_fwd(const float* gi, long ldgi, const float* w_hh, const float* b_hh, int P, int T, float* h, float* rzn, float* ghn);
+__global__ void k_gru_seq_bwd(const float* dh_T, long lddh, const float* w_hh, const float* rzn, const float* ghn, const float* h, int P, int T,
+                              float* dgi, long lddgi, float* dgh);
+size_t gru_seq_fwd_smem_bytes();
+size_t gru_seq_bwd_smem_bytes();
+int gru_seq_rows();
+int gru_seq_threads();
 __global__ void k_rows_copy(const float* src, long lds, float* dst, long ldd, int rows, int n);
 __global__ void k_rows_add(const float* a, long lda, const float* b, long ldb, float* out, long ldo, int rows, int n);
 

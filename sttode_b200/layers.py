@@ -94,12 +94,14 @@ class _OdeRhsFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gate_only, packed, *params):
         L, bsz = x.shape[0], x.shape[1]
+        params_in = params
         params = [_f32c(p, "parameter") for p in params]
         out = torch.empty_like(x)
         lib = _lib.lib()
         ws = _lib.workspace(lib.sttode_ode_block_workspace_bytes(L, bsz, ODE_EULER), x.device)
         st = _ode_struct_from(params)
         st.packed = _lib.dptr(packed)               # tensor-core operand images (eval mode) or None -> FP32 kernels
+        ctx.params_in, ctx.sinks = params_in, _lib.grad_sinks(params_in)
         fn = lib.sttode_hypattention_fwd if gate_only else lib.sttode_ode_rhs_fwd
         _lib.check(fn(_lib.dptr(x), C.byref(st), _lib.dptr(out), L, bsz, _lib.dptr(ws), ws.numel(), _lib.stream_ptr()))
         ctx.save_for_backward(x, *params)
@@ -112,13 +114,14 @@ class _OdeRhsFn(torch.autograd.Function):
         L, bsz = x.shape[0], x.shape[1]
         df = _f32c(df, "grad_output")
         dx = torch.empty_like(x)
-        grads = [torch.zeros_like(p) for p in params]                # the library accumulates (+=)
+        direct = _lib.sinks_still_valid(ctx.params_in, ctx.sinks)
+        grads = ctx.sinks if direct else [torch.zeros_like(p) for p in params]                # the library accumulates (+=)
         lib = _lib.lib()
         ws = _lib.workspace(lib.sttode_ode_rhs_bwd_workspace_bytes(L, bsz), x.device)
         st, gs = _ode_struct_from(params), _ode_struct_from(grads, _lib.OdeGrads)
         _lib.check(lib.sttode_ode_rhs_bwd(_lib.dptr(x), _lib.dptr(df), C.byref(st), _lib.dptr(dx), C.byref(gs), L, bsz, int(ctx.gate_only),
                                           _lib.dptr(ws), ws.numel(), _lib.stream_ptr()))
-        return (dx, None, None, *grads)
+        return (dx, None, None, *([None] * len(grads) if direct else grads))
 
 
 class _OdeBlockFn(torch.autograd.Function):
@@ -129,6 +132,7 @@ class _OdeBlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, n_steps, h, method, final_relu, packed, *params):
         L, bsz = x.shape[0], x.shape[1]
+        ctx.params_in, ctx.sinks = params, _lib.grad_sinks(params)
         params = [_f32c(p, "parameter") for p in params]
         y = torch.empty_like(x)
         lib = _lib.lib()
@@ -148,13 +152,14 @@ class _OdeBlockFn(torch.autograd.Function):
         L, bsz = x.shape[0], x.shape[1]
         dy = _f32c(dy, "grad_output")
         dx = torch.empty_like(x)
-        grads = [torch.zeros_like(p) for p in params]
+        direct = _lib.sinks_still_valid(ctx.params_in, ctx.sinks)
+        grads = ctx.sinks if direct else [torch.zeros_like(p) for p in params]
         lib = _lib.lib()
         ws = _lib.workspace(lib.sttode_ode_block_bwd_workspace_bytes(L, bsz, n_steps), x.device)
         st, gs = _ode_struct_from(params), _ode_struct_from(grads, _lib.OdeGrads)
         _lib.check(lib.sttode_ode_block_bwd(_lib.dptr(x), _lib.dptr(dy), 64, C.byref(st), _lib.dptr(dx), C.byref(gs), L, bsz, n_steps, h, method,
                                             int(final_relu), _lib.dptr(ws), ws.numel(), _lib.stream_ptr()))
-        return (dx, None, None, None, None, None, *grads)
+        return (dx, None, None, None, None, None, *([None] * len(grads) if direct else grads))
 
 
 def _grad_view(t, name):

@@ -226,6 +226,7 @@ class _DenseFn(torch.autograd.Function):
         _lib.check(_lib.lib().sttode_dense_fwd(_lib.dptr(xs), K, _lib.dptr(w), _lib.dptr(b), _lib.dptr(y), rows, K, N, int(relu), _lib.stream_ptr()))
         ctx.save_for_backward(xs, w, y if relu else None)
         ctx.meta = (x.shape, bool(relu), ctx.needs_input_grad[0])
+        ctx.params_in, ctx.sinks = (weight, bias), _lib.grad_sinks((weight, bias))
         return y.view(*x.shape[:-1], N)
 
     @staticmethod
@@ -236,10 +237,14 @@ class _DenseFn(torch.autograd.Function):
         dy = dy.reshape(rows, N)
         dy = (dy * (y > 0)).contiguous() if relu else _f32c(dy, "grad_output")
         dx = torch.empty_like(xs) if need_dx else None
-        dw, db = torch.zeros_like(w), torch.zeros(N, device=w.device, dtype=torch.float32)          # the library accumulates (+=)
+        direct = _lib.sinks_still_valid(ctx.params_in, ctx.sinks)
+        if direct:                                  # the kernels accumulate straight into the parameters' .grad (flat gradient buffer)
+            dw, db = ctx.sinks
+        else:
+            dw, db = torch.zeros_like(w), torch.zeros(N, device=w.device, dtype=torch.float32)      # the library accumulates (+=)
         _lib.check(_lib.lib().sttode_dense_bwd(_lib.dptr(xs), K, _lib.dptr(w), _lib.dptr(dy), _lib.dptr(dx), K, _lib.dptr(dw), _lib.dptr(db), rows, K, N,
                                                _lib.stream_ptr()))
-        return (dx.view(shape) if need_dx else None), dw, db, None
+        return (dx.view(shape) if need_dx else None), (None if direct else dw), (None if direct else db), None
 
 
 def _dense(x, layer, relu=False):
@@ -472,6 +477,7 @@ class _DecoderTrainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, past_feature, z, traj, Tp, Tf, packed, *params):
         pf, zz, tj = _f32c(past_feature, "past_feature"), _f32c(z, "z"), _f32c(traj, "past_traj")
+        ctx.params_in, ctx.sinks = params, _lib.grad_sinks(params)
         params = [_f32c(p, "parameter") for p in params]
         P = pf.shape[0]
         mw = _lib.ModelWeights()
@@ -498,14 +504,15 @@ class _DecoderTrainFn(torch.autograd.Function):
         mw = _lib.ModelWeights()
         mw.past_length, mw.future_length = Tp, Tf
         mw.dec[0], mw.dec[1] = _decompose_struct_from(params[:18], _lib.DecomposeWeights), _decompose_struct_from(params[18:], _lib.DecomposeWeights)
-        grads = [torch.zeros_like(p) for p in params]                                  # the library accumulates (+=)
+        direct = _lib.sinks_still_valid(ctx.params_in, ctx.sinks)
+        grads = ctx.sinks if direct else [torch.zeros_like(p) for p in params]         # the library accumulates (+=)
         gs = (_lib.DecomposeGrads * 2)(_decompose_struct_from(grads[:18], _lib.DecomposeGrads), _decompose_struct_from(grads[18:], _lib.DecomposeGrads))
         d_pf, d_z = torch.empty_like(pf), torch.empty_like(zz)
         lib = _lib.lib()
         ws = _lib.workspace(lib.sttode_decoder_bwd_workspace_bytes(P, Tp, Tf), pf.device)
         _lib.check(lib.sttode_decoder_bwd(_lib.dptr(pf), _lib.dptr(zz), _lib.dptr(tj), _lib.dptr(d_pred), _lib.dptr(d_recon), P, C.byref(mw), gs,
                                           _lib.dptr(d_pf), _lib.dptr(d_z), _lib.dptr(ws), ws.numel(), _lib.stream_ptr()))
-        return (d_pf, d_z, None, None, None, None, *grads)
+        return (d_pf, d_z, None, None, None, None, *([None] * len(grads) if direct else grads))
 
 
 def _decoder_forward_train(self, past_feature, z, past_traj, cur_location, sample_num, mode):

@@ -63,6 +63,9 @@ class FlatGradReducer:
         for _, p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
+        # the library's backward kernels accumulate (+=) straight into these views: no zero-fill + add per parameter per autograd node
+        from . import _lib
+        _lib.DIRECT_GRAD_SINKS = True
 
     @property
     def nbytes(self):

@@ -34,9 +34,9 @@ def test_struct_sizes_match_header():
     import ctypes as C
     assert C.sizeof(L.MhgsaWeights) == 4 * 8
     assert C.sizeof(L.OdeWeights) == 17 * 8                      # 16 tensors + the optional packed tensor-core images
-    assert C.sizeof(L.EncoderWeights) == (9 + 17) * 8
+    assert C.sizeof(L.EncoderWeights) == (9 + 17 + 1) * 8        # + the optional folded front-end table
     assert C.sizeof(L.DecomposeWeights) == (6 + 12) * 8
-    assert C.sizeof(L.ModelWeights) == 8 + (26 + 36 + 2) * 8
+    assert C.sizeof(L.ModelWeights) == 8 + (27 + 36 + 2) * 8
     # gradient structs mirror the weight structs field for field (include/sttode.h)
     assert C.sizeof(L.MhgsaGrads) == C.sizeof(L.MhgsaWeights) and C.sizeof(L.OdeGrads) == C.sizeof(L.OdeWeights) - 8
     assert C.sizeof(L.DecomposeGrads) == C.sizeof(L.DecomposeWeights) and C.sizeof(L.Mlp3Grads) == C.sizeof(L.Mlp3Weights)
