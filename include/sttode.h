@@ -300,6 +300,22 @@ void sttode_release_host_arena(void);
 int sttode_latent_draw(unsigned long long seed, unsigned long long pair_base, const unsigned long long *rng_state_or_null,
                        size_t n_pairs, float *z, void *stream);
 
+/* ---- data-parallel training (BASELINE.json configs[4]; the reference itself is single-GPU, train.py:55-98,122-123) -----------------------
+ * Gradient all-reduce fused with the Adam update over NVLink / NVSwitch peer memory, one process per GPU of one node, no NCCL call:
+ * every rank owns an arena [n_floats gradients | flag words] (sttode_peer_alloc), exports it through CUDA IPC (the 64-byte handle travels by any
+ * host channel, e.g. torch.distributed.all_gather_object) and maps its peers' arenas (sttode_peer_open).  sttode_dp_adam_step enqueues
+ *   barrier -> [sum of all ranks' gradients in rank order, * 1/world, torch.optim.Adam update of param / exp_avg / exp_avg_sq] -> barrier
+ * on `stream`: plain kernels, capturable into a CUDA graph together with the forward and backward.  grads_of_dev / flags_of_dev: DEVICE arrays of
+ * `world` pointers (rank r's arena and arena + n_floats*4).  lr_dev: device scalar.  The step count lives in the arena (replay-safe).
+ * A peer that never arrives raises the arena's error word after ~3 s (sttode_peer_status) instead of hanging the GPU. */
+int sttode_peer_alloc(size_t n_floats, void **arena, void *ipc_handle_64_bytes);
+int sttode_peer_open(const void *ipc_handle_64_bytes, void **arena);
+int sttode_peer_close(void *arena);
+int sttode_peer_free(void *arena);
+int sttode_dp_adam_step(const void *grads_of_dev, const void *flags_of_dev, int world, int rank, float *param, float *exp_avg, float *exp_avg_sq,
+                        float *grad_avg_or_null, size_t n_floats, const float *lr_dev, float beta1, float beta2, float eps, void *stream);
+int sttode_peer_status(const void *arena, size_t n_floats, unsigned *err_host, unsigned *step_host);
+
 /* ---- min-over-K ADE/FDE on device (utils/metrics.py:7-26; test.py:204-208): sums[0] += sum_agents minADE,
  * sums[1] += sum_agents minFDE, sums[2] += rows  (double[3], device; AverageMeter numerators). */
 int sttode_min_ade_fde(const float *pred, const float *gt, int gt_layout, int rows, int sample_k, int future_length,

@@ -108,6 +108,12 @@ SIGNATURES = {
     "sttode_forecast": (_I, [_V, _I, _V, _V, _I, _I, _I, _I, _V, _U64, _I, C.POINTER(ModelWeights), _V, _V, _V, _V, _V, _Z, _V]),
     "sttode_forecast_host": (_I, [_V, _I, _V, _I, _I, _I, _I, _U64, _I, C.POINTER(ModelWeights), _V, _V]),
     "sttode_release_host_arena": (None, []),
+    "sttode_peer_alloc": (_I, [_Z, C.POINTER(C.c_void_p), _V]),
+    "sttode_peer_open": (_I, [_V, C.POINTER(C.c_void_p)]),
+    "sttode_peer_close": (_I, [_V]),
+    "sttode_peer_free": (_I, [_V]),
+    "sttode_dp_adam_step": (_I, [_V, _V, _I, _I, _V, _V, _V, _V, _Z, _V, _F, _F, _F, _V]),
+    "sttode_peer_status": (_I, [_V, _Z, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]),
     "sttode_latent_draw": (_I, [_U64, _U64, _V, _Z, _V, _V]),
     "sttode_min_ade_fde": (_I, [_V, _V, _I, _I, _I, _I, _V, _V]),
     "sttode_oblique_proj": (_I, [_V, _V, _I, _I, _V]),

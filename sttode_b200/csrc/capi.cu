@@ -701,7 +701,7 @@ int run_encoder(const float* traj, int layout, const int* scene_ptr, const int* 
     }
     const int nb = scene_ptr ? rows : rows / (L * agents);
     const int bsz = scene_ptr ? 1 : agents;
-    if (ew.folded && ew.ode.packed && T <= 32) {
+    if (ew.folded && ew.ode.packed && T <= 30) {          // the folded table must fit next to the weight ring in shared memory
         // Tensor-core encoder: x0 comes out of the input staging of the first tcgen05 kernel (folded front end), so the raw trajectory is the
         // only HBM input; past_feature[:, 0:64] = x0 and traj_norm are written by that kernel.  L = 1: one launch for the whole encoder.
         const FoldedIn f{ew.folded, traj, layout, scene_ptr, row_scene, origin, agents, T, past_feature, traj_norm};
@@ -1282,6 +1282,54 @@ int sttode_latent_draw(unsigned long long seed, unsigned long long pair_base, co
     return 0;
 }
 
+// ---- data-parallel exchange over NVLink peer memory (comm.cu) -----------------------------------------------------------------------
+int sttode_peer_alloc(size_t n_floats, void** arena, void* ipc_handle64) {
+    if (!arena || !ipc_handle64 || n_floats == 0 || (n_floats & 3)) return fail(STTODE_EINVAL, "peer_alloc: n_floats must be a positive multiple of 4");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void* p = nullptr;
+    const size_t bytes = n_floats * sizeof(float) + PEER_FLAG_WORDS * sizeof(unsigned);
+    CUDA_TRY(cudaMalloc(&p, bytes));                // plain cudaMalloc: exportable through CUDA IPC (the caching allocator's blocks are not ours to export)
+    CUDA_TRY(cudaMemset(p, 0, bytes));
+    CUDA_TRY(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)ipc_handle64, p));
+    CUDA_TRY(cudaDeviceSynchronize());
+    *arena = p;
+    return 0;
+}
+int sttode_peer_open(const void* ipc_handle64, void** arena) {
+    if (!ipc_handle64 || !arena) return fail(STTODE_EINVAL, "null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle64, sizeof(h));
+    CUDA_TRY(cudaIpcOpenMemHandle(arena, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+int sttode_peer_close(void* arena) { if (arena) CUDA_TRY(cudaIpcCloseMemHandle(arena)); return 0; }
+int sttode_peer_free(void* arena) { if (arena) CUDA_TRY(cudaFree(arena)); return 0; }
+
+int sttode_dp_adam_step(const void* grads_of_dev, const void* flags_of_dev, int world, int rank, float* param, float* exp_avg, float* exp_avg_sq,
+                        float* grad_avg, size_t n_floats, const float* lr_dev, float beta1, float beta2, float eps, void* stream) {
+    if (!grads_of_dev || !flags_of_dev || !param || !exp_avg || !exp_avg_sq || !lr_dev) return fail(STTODE_EINVAL, "null pointer");
+    if (world < 1 || world > PEER_MAX_WORLD || rank < 0 || rank >= world || (n_floats & 3)) return fail(STTODE_EINVAL, "dp_adam_step: bad world / rank / size");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned* const* flags_of = (unsigned* const*)flags_of_dev;
+    const float* const* grads_of = (const float* const*)grads_of_dev;
+    // the local flag words live right behind this rank's gradient buffer; the kernels find them through the same table the barrier uses
+    launch_peer_barrier(flags_of, world, rank, 0, st);                       // every rank's gradients are complete
+    LAUNCH_CHECK("k_peer_barrier");
+    launch_allreduce_adam(grads_of, world, rank, flags_of, param, exp_avg, exp_avg_sq, grad_avg, n_floats / 4, lr_dev, beta1, beta2, eps, st);
+    LAUNCH_CHECK("k_allreduce_adam");
+    launch_peer_barrier(flags_of, world, rank, 1, st);                       // every peer has read my gradients; step counter += 1
+    LAUNCH_CHECK("k_peer_barrier");
+    return 0;
+}
+int sttode_peer_status(const void* arena, size_t n_floats, unsigned* err_host, unsigned* step_host) {
+    if (!arena) return fail(STTODE_EINVAL, "null pointer");
+    unsigned w[PEER_FLAG_WORDS];
+    CUDA_TRY(cudaMemcpy(w, (const char*)arena + n_floats * sizeof(float), sizeof(w), cudaMemcpyDeviceToHost));
+    if (err_host) *err_host = w[PEER_ERR];
+    if (step_host) *step_host = w[PEER_STEP];
+    return 0;
+}
+
 void sttode_release_host_arena(void) {
     std::lock_guard<std::mutex> lock(g_arena.mu);
     if (g_arena.pin_in) cudaFreeHost(g_arena.pin_in);
@@ -1300,7 +1348,7 @@ void sttode_release_host_arena(void) {
 int sttode_min_ade_fde(const float* pred, const float* gt, int gt_layout, int rows, int sample_k, int future_length, double* sums,
                        void* stream) {
     if (!pred || !gt || !sums || rows <= 0 || sample_k < 1 || future_length < 1) return fail(STTODE_EINVAL, "bad argument");
-    k_min_ade_fde<<<ceil_div(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(pred, gt, gt_layout, rows, sample_k, future_length, sums);
+    k_min_ade_fde<<<ceil_div(rows, 32), 1024, 0, (cudaStream_t)stream>>>(pred, gt, gt_layout, rows, sample_k, future_length, sums);
     LAUNCH_CHECK("k_min_ade_fde");
     return 0;
 }

@@ -106,9 +106,9 @@ __global__ void __launch_bounds__(320) k_fold_prologue(sttode_encoder_weights w,
 size_t fold_table_bytes(int T) { return (size_t)(4 * T + 2) * 64 * sizeof(float); }
 void launch_fold_prologue(const sttode_encoder_weights& w, int T, float* out, cudaStream_t st) { k_fold_prologue<<<1, 320, 0, st>>>(w, T, out); }
 
-// columns 32*half .. of x0 for row r from the raw trajectory (scene-centred positions + velocities, first step duplicated:
+// columns 16*cq .. 16*cq+15 of x0 for row r from the raw trajectory (scene-centred positions + velocities, first step duplicated:
 // model/STTODE.py:417,429,582-596) or from explicit [x, y, vx, vy] features; tab_s = the folded table in shared memory
-__device__ __forceinline__ void folded_x0(const FoldedIn& f, const float* tab_s, int r, bool live, int half, bool write_norm, float (&v)[32]) {
+__device__ __forceinline__ void folded_x0(const FoldedIn& f, const float* tab_s, int r, bool live, int cq, bool write_norm, float (&v)[16]) {
     const int T = f.T;
     float flag = 0.f, ox = 0.f, oy = 0.f;
     if (live) {
@@ -120,9 +120,9 @@ __device__ __forceinline__ void folded_x0(const FoldedIn& f, const float* tab_s,
             flag = ((r % f.agents) == f.agents - 1) ? 1.f : 0.f;
         }
     }
-    const float* g0 = tab_s + (size_t)(4 * T) * 64 + half * 32;
+    const float* g0 = tab_s + (size_t)(4 * T) * 64 + cq * 16;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = fmaf(flag, g0[64 + i], g0[i]);
+    for (int i = 0; i < 16; ++i) v[i] = fmaf(flag, g0[64 + i], g0[i]);
     if (!live) return;
     const float* p = f.traj + (size_t)r * T * (f.layout == STTODE_FEAT_RT4 ? 4 : 2);
     float ppx = 0.f, ppy = 0.f;                     // previous normalised position
@@ -152,9 +152,9 @@ __device__ __forceinline__ void folded_x0(const FoldedIn& f, const float* tab_s,
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const float4* row = reinterpret_cast<const float4*>(tab_s + (size_t)(t * 4 + c) * 64 + half * 32);
+            const float4* row = reinterpret_cast<const float4*>(tab_s + (size_t)(t * 4 + c) * 64 + cq * 16);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
+            for (int q = 0; q < 4; ++q) {
                 const float4 m4 = row[q];
                 v[4 * q] = fmaf(in4[c], m4.x, v[4 * q]); v[4 * q + 1] = fmaf(in4[c], m4.y, v[4 * q + 1]);
                 v[4 * q + 2] = fmaf(in4[c], m4.z, v[4 * q + 2]); v[4 * q + 3] = fmaf(in4[c], m4.w, v[4 * q + 3]);
@@ -162,20 +162,21 @@ __device__ __forceinline__ void folded_x0(const FoldedIn& f, const float* tab_s,
         }
     }
 }
-__device__ __forceinline__ void store_row32(float* p, const float (&v)[32]) {
+__device__ __forceinline__ void store_row16(float* p, const float (&v)[16]) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(p + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(p + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
 
 // ---- shared pieces ----------------------------------------------------------------------------------------------------------------
 namespace otc {
-constexpr int THREADS = 320, EPI_WARPS = 8, ISSUER = 8, PRODUCER = 9;
+constexpr int THREADS = 576, EPI_WARPS = 16, EPI_THREADS = 512, ISSUER = 16, PRODUCER = 17;
 constexpr int STAGE = 2 * ODE_UNIT, NST = 3, NBLK = ODE_UNITS / 2;          // 18 ring blocks of two units
 constexpr int SM_A = 0;                          // A operand image, 128 rows x K 64: hi 16 KB | lo 16 KB
 constexpr int SM_H = 32768;                      // 2 x (hi 16 KB | lo 16 KB): staged FFN chunk operand
 constexpr int SM_RING = SM_H + 65536;
 constexpr int SM_BARS = SM_RING + NST * STAGE;   // 196608
-constexpr int SM_FOLD = SM_BARS + 256;           // folded front-end table [(4T+2), 64] fp32 (optional)
+constexpr int SM_RED = SM_BARS + 256;            // LayerNorm partial sums: 2 x [128 rows][4 column quarters] fp32
+constexpr int SM_FOLD = SM_RED + 4096;           // folded front-end table [(4T+2), 64] fp32 (optional)
 constexpr int COL_D0 = 0, COL_DG = 64, COL_D1 = 192, COL_D2 = 320;
 enum { B_WFULL = 0, B_WFREE = 3, B_AFULL = 6, B_DFULL = 7, B_D1FULL = 8, B_HFULL = 10, B_HFREE = 12, B_D2FULL = 14, B_COUNT = 15 };
 constexpr float FP16_SAFE = 60000.f;
@@ -192,6 +193,7 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\tselp.u32 %0, 1, 0, px;\n\t}" : "=r"(pred));
     return pred != 0;
 }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 512;" ::: "memory"); }      // the 16 epilogue warps only
 // epilogue warp: publish generic-proxy smem writes + finished TMEM reads, one arrival per warp
 __device__ __forceinline__ void signal(uint64_t* bars, int bar) {
     tc::fence_proxy_async();
@@ -207,42 +209,62 @@ __device__ __forceinline__ void track(const float (&v)[N], int& ovf) {
     for (int i = 0; i < N; ++i) mx = max(mx, __float_as_uint(v[i]) & 0x7fffffffu);
     ovf |= mx > __float_as_uint(FP16_SAFE);
 }
-// 32 consecutive-k values of row m (k chunks kc0 .. kc0+3) -> the 128-row operand image at `img` (hi) / img + 16384 (lo)
-__device__ __forceinline__ void stage32(unsigned char* img, int m, int kc0, const float (&v)[32], int& ovf) {
+// 16 consecutive-k values of row m (k chunks kc0, kc0+1) -> the 128-row operand image at `img` (hi) / img + 16384 (lo)
+__device__ __forceinline__ void stage16(unsigned char* img, int m, int kc0, const float (&v)[16], int& ovf) {
     track(v, ovf);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < 2; ++q) {
         float t8[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) t8[i] = v[q * 8 + i];
         tc::store_split8(img, img + 16384, 128, m, kc0 + q, t8);
     }
 }
-__device__ __forceinline__ void load_row32(float (&v)[32], const float* __restrict__ p) {      // 128 contiguous bytes; p == nullptr -> zeros
+__device__ __forceinline__ void load_row16(float (&v)[16], const float* __restrict__ p) {      // 64 contiguous bytes through L2; p == nullptr -> zeros
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const float4 r = p ? __ldg(reinterpret_cast<const float4*>(p) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < 4; ++q) {
+        const float4 r = p ? __ldcg(reinterpret_cast<const float4*>(p) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
         v[4 * q] = r.x; v[4 * q + 1] = r.y; v[4 * q + 2] = r.z; v[4 * q + 3] = r.w;
     }
 }
-// LayerNorm over the 64 values of one row held by one thread (biased variance, eps inside the sqrt: torch native_layer_norm)
-__device__ __forceinline__ void layernorm64(float (&s)[64], const float* __restrict__ gamma, const float* __restrict__ beta) {
-    float mean = 0.f;
+__device__ __forceinline__ void add_bias16(float (&v)[16], const float* __restrict__ b) {
 #pragma unroll
-    for (int i = 0; i < 64; ++i) mean += s[i];
-    mean *= (1.f / 64.f);
+    for (int q = 0; q < 4; ++q) {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(b) + q);
+        v[4 * q] += r.x; v[4 * q + 1] += r.y; v[4 * q + 2] += r.z; v[4 * q + 3] += r.w;
+    }
+}
+// LayerNorm over the 64 features of a row held 16 per thread by the four threads (m, cq = 0..3) — they sit in different warps, so the two
+// row statistics travel through shared memory (biased variance about the mean, eps inside the sqrt: torch native_layer_norm).
+__device__ __forceinline__ void layernorm_rows16(float (&s)[16], float* red, int m, int cq, const float* __restrict__ gamma, const float* __restrict__ beta) {
+    float part = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) part += s[i];
+    red[m * 4 + cq] = part;
+    epi_barrier();
+    const float4 a = *reinterpret_cast<const float4*>(red + m * 4);
+    const float mean = (a.x + a.y + a.z + a.w) * (1.f / 64.f);
     float var = 0.f;
 #pragma unroll
-    for (int i = 0; i < 64; ++i) { s[i] -= mean; var = fmaf(s[i], s[i], var); }
-    const float rstd = 1.f / sqrtf(var * (1.f / 64.f) + 1e-5f);
+    for (int i = 0; i < 16; ++i) { s[i] -= mean; var = fmaf(s[i], s[i], var); }
+    red[512 + m * 4 + cq] = var;
+    epi_barrier();
+    const float4 b = *reinterpret_cast<const float4*>(red + 512 + m * 4);
+    const float rstd = 1.f / sqrtf((b.x + b.y + b.z + b.w) * (1.f / 64.f) + 1e-5f);
 #pragma unroll
-    for (int i = 0; i < 64; ++i) s[i] = s[i] * rstd * __ldg(gamma + i) + __ldg(beta + i);
+    for (int q = 0; q < 4; ++q) {
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + cq * 16) + q), b4 = __ldg(reinterpret_cast<const float4*>(beta + cq * 16) + q);
+        s[4 * q] = s[4 * q] * rstd * g4.x + b4.x; s[4 * q + 1] = s[4 * q + 1] * rstd * g4.y + b4.y;
+        s[4 * q + 2] = s[4 * q + 2] * rstd * g4.z + b4.z; s[4 * q + 3] = s[4 * q + 3] * rstd * g4.w + b4.w;
+    }
 }
 }  // namespace otc
 
 // =====================================================================================================================================
 // ODE right-hand side tail + solver update for a 128-row tile (see k_ode_tail for the algebra).  attn_o == nullptr: attention axis of
 // length 1 (softmax over one key is 1), the attention output is the value projection of x itself.
+// Epilogue thread (m = 32*(warp & 3) + lane, cq = warp >> 2) owns columns 16*cq .. 16*cq+15 of row m: four warps per scheduler hide the
+// TMEM / shared-memory latencies of one another (two per scheduler left the tensor pipe 11 % busy).
 // =====================================================================================================================================
 __global__ void __launch_bounds__(otc::THREADS, 1)
 k_ode_tail_tc(const float* __restrict__ x, int ldx, const float* __restrict__ attn_o, int ldo, const float* __restrict__ base, int ldb, float coef,
@@ -252,10 +274,11 @@ k_ode_tail_tc(const float* __restrict__ x, int ldx, const float* __restrict__ at
     extern __shared__ __align__(128) unsigned char sm[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM_BARS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
+    float* red = reinterpret_cast<float*>(sm + SM_RED);
     float* tab_s = reinterpret_cast<float*>(sm + SM_FOLD);
     if (fold.table)                                 // folded front end: x (= fold.x0_out, ld ldx) is produced by this kernel's input staging
         for (int i = threadIdx.x; i < (4 * fold.T + 2) * 16; i += THREADS) reinterpret_cast<float4*>(tab_s)[i] = __ldg(reinterpret_cast<const float4*>(fold.table) + i);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wq = warp & 3, half = (warp >> 2) & 1;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wq = warp & 3, cq = (warp >> 2) & 3;
     const int m = wq * 32 + lane, r = blockIdx.x * BM + m;
     const bool live = r < rows;
     int ovf = 0;
@@ -335,97 +358,81 @@ k_ode_tail_tc(const float* __restrict__ x, int ldx, const float* __restrict__ at
         const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
         unsigned char* A = sm + SM_A;
         uint32_t n_d = 0;
-        float v[32];
-        // input operand: x (value projection follows) or the attention output, columns 32*half .. of row m
+        float v[16];
+        // input operand: x (value projection follows) or the attention output, columns 16*cq .. of row m
         if (fold.table) {                           // x0 from the raw trajectory; also this kernel's x / base (re-read below through L2)
-            folded_x0(fold, tab_s, r, live, half, half == 0, v);
-            if (live) store_row32(fold.x0_out + (size_t)r * ldx + half * 32, v);
+            folded_x0(fold, tab_s, r, live, cq, cq == 0, v);
+            if (live) store_row16(fold.x0_out + (size_t)r * ldx + cq * 16, v);
         }
         if (!fold.table || !vproj) {
             const float* src = vproj ? x + (size_t)r * ldx : attn_o + (size_t)r * ldo;
-            load_row32(v, live ? src + half * 32 : nullptr);
+            load_row16(v, live ? src + cq * 16 : nullptr);
         }
-        stage32(A, m, half * 4, v, ovf);
+        stage16(A, m, cq * 2, v, ovf);
         signal(bars, B_AFULL);
         if (vproj) {                                // v = x.W_v^T + b_v
             wait(bars, B_DFULL, n_d++ & 1); tc::tc_fence_after();
-            tc::tmem_ld32(tmem + lane_base + COL_D0 + half * 32, v);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += __ldg(w.attn.in_proj_b + 128 + half * 32 + i);
-            stage32(A, m, half * 4, v, ovf);
+            tc::tmem_ld16(tmem + lane_base + COL_D0 + cq * 16, v);
+            add_bias16(v, w.attn.in_proj_b + 128 + cq * 16);
+            stage16(A, m, cq * 2, v, ovf);
             signal(bars, B_AFULL);
         }
         // m = o.W_o^T + b_o
         wait(bars, B_DFULL, n_d++ & 1); tc::tc_fence_after();
-        tc::tmem_ld32(tmem + lane_base + COL_D0 + half * 32, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += __ldg(w.attn.out_proj_b + half * 32 + i);
-        stage32(A, m, half * 4, v, ovf);
+        tc::tmem_ld16(tmem + lane_base + COL_D0 + cq * 16, v);
+        add_bias16(v, w.attn.out_proj_b + cq * 16);
+        stage16(A, m, cq * 2, v, ovf);
         signal(bars, B_AFULL);
-        // gate + residual + LN1: thread = row (warps 0..3 hold all 64 features of their row; s stays in registers for the second residual)
-        float s[64];
+        // gate + residual + LN1; s (this thread's 16 features) stays in registers for the second residual
+        float s[16];
         wait(bars, B_DFULL, n_d++ & 1); tc::tc_fence_after();
-        if (half == 0) {
+        {
+            float ui[16], ug[16];
+            tc::tmem_ld16(tmem + lane_base + COL_DG + cq * 16, ui);
+            tc::tmem_ld16(tmem + lane_base + COL_DG + 64 + cq * 16, ug);
+            add_bias16(ui, w.info_b + cq * 16);
+            add_bias16(ug, w.gate_b + cq * 16);
+            load_row16(s, live ? x + (size_t)r * ldx + cq * 16 : nullptr);          // through L2: x may have been written by this CTA (folded front end)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {           // 16 columns at a time keeps the live register set small (s[64] stays resident)
-                float ui[16], ug[16];
-                tc::tmem_ld16(tmem + lane_base + COL_DG + q * 16, ui);
-                tc::tmem_ld16(tmem + lane_base + COL_DG + 64 + q * 16, ug);
-#pragma unroll
-                for (int i4 = 0; i4 < 4; ++i4) {
-                    const float4 xr = live ? __ldcg(reinterpret_cast<const float4*>(x + (size_t)r * ldx + q * 16) + i4) : make_float4(0.f, 0.f, 0.f, 0.f);   // L2: x may have been written by this CTA
-                    const float xv[4] = {xr.x, xr.y, xr.z, xr.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int i = i4 * 4 + e, n = q * 16 + i;
-                        s[n] = xv[e] + tanhf(ui[i] + __ldg(w.info_b + n)) * sigmoidf_(ug[i] + __ldg(w.gate_b + n));
-                    }
-                }
-            }
-            layernorm64(s, w.norm1_g, w.norm1_b);
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = s[q * 32 + i];
-                stage32(A, m, q * 4, v, ovf);
-            }
+            for (int i = 0; i < 16; ++i) s[i] += tanhf(ui[i]) * sigmoidf_(ug[i]);
         }
+        layernorm_rows16(s, red, m, cq, w.norm1_g, w.norm1_b);
+        stage16(A, m, cq * 2, s, ovf);
         signal(bars, B_AFULL);
-        // FFN chunk epilogue: H[c&1] = relu(D1(c) + b1[64c..]), this thread: columns 32*half .. of row m
+        // FFN chunk epilogue: H[c&1] = relu(D1(c) + b1[64c..]), this thread: columns 16*cq .. of row m
 #pragma unroll 1
         for (int c = 0; c < 16; ++c) {
             const int b = c & 1;
-            wait(bars, B_D1FULL + b, (uint32_t)((c >> 1) & 1)); tc::tc_fence_after();
-            tc::tmem_ld32(tmem + lane_base + COL_D1 + b * 64 + half * 32, v);
+            float4 bq[4];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + __ldg(w.lin1_b + c * 64 + half * 32 + i), 0.f);
+            for (int q = 0; q < 4; ++q) bq[q] = __ldg(reinterpret_cast<const float4*>(w.lin1_b + c * 64 + cq * 16) + q);      // before the wait: off the critical path
+            wait(bars, B_D1FULL + b, (uint32_t)((c >> 1) & 1)); tc::tc_fence_after();
+            tc::tmem_ld16(tmem + lane_base + COL_D1 + b * 64 + cq * 16, v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                v[4 * q] = fmaxf(v[4 * q] + bq[q].x, 0.f); v[4 * q + 1] = fmaxf(v[4 * q + 1] + bq[q].y, 0.f);
+                v[4 * q + 2] = fmaxf(v[4 * q + 2] + bq[q].z, 0.f); v[4 * q + 3] = fmaxf(v[4 * q + 3] + bq[q].w, 0.f);
+            }
             if (c >= 2) wait(bars, B_HFREE + b, (uint32_t)(((c >> 1) - 1) & 1));       // layer 2 of chunk c-2 has read H[b]
-            stage32(sm + SM_H + b * 32768, m, half * 4, v, ovf);
+            stage16(sm + SM_H + b * 32768, m, cq * 2, v, ovf);
             signal(bars, B_HFULL + b);
         }
         // second residual + LN2 + solver update: out = act(base + coef * f)
-        if (half == 0) {
-            wait(bars, B_D2FULL, 0); tc::tc_fence_after();
+        wait(bars, B_D2FULL, 0); tc::tc_fence_after();
+        tc::tmem_ld16(tmem + lane_base + COL_D2 + cq * 16, v);
+        add_bias16(v, w.lin2_b + cq * 16);
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                tc::tmem_ld32(tmem + lane_base + COL_D2 + q * 32, v);
+        for (int i = 0; i < 16; ++i) s[i] += v[i];
+        layernorm_rows16(s, red, m, cq, w.norm2_g, w.norm2_b);
+        if (live) {
+            if (base) load_row16(v, base + (size_t)r * ldb + cq * 16);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) s[q * 32 + i] += v[i] + __ldg(w.lin2_b + q * 32 + i);
+            for (int i = 0; i < 16; ++i) {
+                float t = __fmul_rn(coef, s[i]);                                // dt * f, then + y0: two roundings like the reference
+                if (base) t = __fadd_rn(v[i], t);
+                v[i] = (relu && t < 0.f) ? 0.f : t;                              // torch.relu keeps NaN
             }
-            layernorm64(s, w.norm2_g, w.norm2_b);
-            if (live) {
-#pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    float o4[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float t = __fmul_rn(coef, s[q * 4 + i]);          // dt * f, then + y0: two roundings like the reference
-                        if (base) t = __fadd_rn(__ldcg(base + (size_t)r * ldb + q * 4 + i), t);
-                        o4[i] = (relu && t < 0.f) ? 0.f : t;
-                    }
-                    *reinterpret_cast<float4*>(out + (size_t)r * ldout + q * 4) = make_float4(o4[0], o4[1], o4[2], o4[3]);
-                }
-            }
+            store_row16(out + (size_t)r * ldout + cq * 16, v);
         }
     }
     if (ovf && tile_flags) tile_flags[blockIdx.x] = 1;
@@ -454,7 +461,7 @@ k_qkv_tc(const float* __restrict__ x, int ldx, int rows, const float* __restrict
     float* tab_s = reinterpret_cast<float*>(sm + qtc::SM_FOLD);
     if (fold.table)
         for (int i = threadIdx.x; i < (4 * fold.T + 2) * 16; i += THREADS) reinterpret_cast<float4*>(tab_s)[i] = __ldg(reinterpret_cast<const float4*>(fold.table) + i);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wq = warp & 3, half = (warp >> 2) & 1;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wq = warp & 3, cq = (warp >> 2) & 3;
     const int m = wq * 32 + lane, r = blockIdx.x * BM + m;
     const bool live = r < rows;
     int ovf = 0;
@@ -487,30 +494,29 @@ k_qkv_tc(const float* __restrict__ x, int ldx, int rows, const float* __restrict
         __syncwarp();
     } else {
         const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
-        float v[32];
+        float v[16];
         if (fold.table) {
-            folded_x0(fold, tab_s, r, live, half, half == 0, v);
-            if (live) store_row32(fold.x0_out + (size_t)r * ldx + half * 32, v);
+            folded_x0(fold, tab_s, r, live, cq, cq == 0, v);
+            if (live) store_row16(fold.x0_out + (size_t)r * ldx + cq * 16, v);
         } else {
-            load_row32(v, live ? x + (size_t)r * ldx + half * 32 : nullptr);
+            load_row16(v, live ? x + (size_t)r * ldx + cq * 16 : nullptr);
         }
-        stage32(sm + qtc::SM_A, m, half * 4, v, ovf);
+        stage16(sm + qtc::SM_A, m, cq * 2, v, ovf);
         signal(bars, qtc::B_A);
         if (!tc::mbar_wait(bars + qtc::B_D, 0)) { printf("k_qkv_tc: MMA never completed\n"); __trap(); }
         tc::tc_fence_after();
-        // six 32-column groups (4 heads each): groups 0,1 = q, 2,3 = k, 4,5 = v; warps of `half` take groups g with (g & 1) == half
+        // twelve 16-column groups (2 heads each): groups 0..3 = q, 4..7 = k, 8..11 = v; the warps of column quarter cq take groups cq, cq+4, cq+8
 #pragma unroll 1
-        for (int g = half; g < 6; g += 2) {
-            tc::tmem_ld32(tmem + lane_base + g * 32, v);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += __ldg(in_b + g * 32 + i);
-            if (g < 2) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] *= scale;
-            }
+        for (int g = cq; g < 12; g += 4) {
+            tc::tmem_ld16(tmem + lane_base + g * 16, v);
+            add_bias16(v, in_b + g * 16);
             if (g < 4) {
 #pragma unroll
-                for (int h = 0; h < 4; ++h) {
+                for (int i = 0; i < 16; ++i) v[i] *= scale;
+            }
+            if (g < 8) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
                     float n2 = 0.f;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) n2 = fmaf(v[h * 8 + i], v[h * 8 + i], n2);
@@ -519,11 +525,7 @@ k_qkv_tc(const float* __restrict__ x, int ldx, int rows, const float* __restrict
                     for (int i = 0; i < 8; ++i) v[h * 8 + i] = v[h * 8 + i] / nrm;          // oblique.py:16, no epsilon
                 }
             }
-            if (live) {
-#pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    *reinterpret_cast<float4*>(out + (size_t)r * ldo_ + g * 32 + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            }
+            if (live) store_row16(out + (size_t)r * ldo_ + g * 16, v);
         }
     }
     if (ovf && tile_flags) tile_flags[blockIdx.x] = 1;

@@ -121,6 +121,12 @@ int dec_pair_tc_threads();
 __global__ void k_bump_counter(unsigned long long* p);
 __global__ void k_latent_draw(unsigned long long seed, unsigned long long pair_base, const unsigned long long* rng_state, size_t n_pairs, float* z);
 
+// comm.cu — gradient all-reduce fused with Adam over NVLink peer memory
+constexpr int PEER_MAX_WORLD = 16, PEER_EPOCH = 16, PEER_ERR = 17, PEER_STEP = 18, PEER_FLAG_WORDS = 64;
+void launch_peer_barrier(unsigned* const* flags_of, int world, int rank, int bump_step, cudaStream_t st);
+void launch_allreduce_adam(const float* const* grads_of, int world, int rank, unsigned* const* flags_of, float* param, float* exp_avg, float* exp_avg_sq,
+                           float* grad_avg, size_t n4, const float* lr_dev, float beta1, float beta2, float eps, cudaStream_t st);
+
 // metrics.cu
 __global__ void k_min_ade_fde(const float* pred, const float* gt, int gt_layout, int rows, int K, int Tf, double* sums);
 

@@ -237,34 +237,45 @@ void launch_pmath_elem(int op, const float* x, float* out, size_t n, float clamp
 // ------------------------------------------------------------------------------------------------
 // min-over-K ADE / FDE (utils/metrics.py:7-26): one warp per agent row, lanes over samples.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_min_ade_fde(const float* __restrict__ pred, const float* __restrict__ gt, int gt_layout, int rows, int K,
-                              int Tf, double* __restrict__ sums) {
-    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (row >= rows) return;
+// One warp per agent row, lanes over samples; a block of 32 warps reduces its rows in shared memory (fixed order) and issues ONE
+// atomic triple — 3 double atomics per row on the same three addresses serialised the whole launch (0.27 ms at 53 760 rows, round 1).
+__global__ void __launch_bounds__(1024) k_min_ade_fde(const float* __restrict__ pred, const float* __restrict__ gt, int gt_layout, int rows, int K,
+                                                     int Tf, double* __restrict__ sums) {
+    __shared__ float s_ade[32], s_fde[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 32 + warp;
     float best_ade = INFINITY, best_fde = INFINITY;
-    for (int k = lane; k < K; k += 32) {
-        const float* p = pred + ((size_t)row * K + k) * Tf * 2;
-        float s = 0.f, last = 0.f;
-        for (int t = 0; t < Tf; ++t) {
-            float gx, gy;
-            if (gt_layout == STTODE_TRAJ_RT2) { gx = gt[((size_t)row * Tf + t) * 2]; gy = gt[((size_t)row * Tf + t) * 2 + 1]; }
-            else                              { gx = gt[(size_t)row * 2 * Tf + t];   gy = gt[(size_t)row * 2 * Tf + Tf + t]; }
-            const float dx = p[t * 2] - gx, dy = p[t * 2 + 1] - gy;
-            last = sqrtf(dx * dx + dy * dy);
-            s += last;
+    if (row < rows) {
+        for (int k = lane; k < K; k += 32) {
+            const float2* p = reinterpret_cast<const float2*>(pred + ((size_t)row * K + k) * Tf * 2);
+            float s = 0.f, last = 0.f;
+            for (int t = 0; t < Tf; ++t) {
+                float gx, gy;
+                if (gt_layout == STTODE_TRAJ_RT2) { gx = gt[((size_t)row * Tf + t) * 2]; gy = gt[((size_t)row * Tf + t) * 2 + 1]; }
+                else                              { gx = gt[(size_t)row * 2 * Tf + t];   gy = gt[(size_t)row * 2 * Tf + Tf + t]; }
+                const float2 q = __ldg(p + t);
+                const float dx = q.x - gx, dy = q.y - gy;
+                last = sqrtf(dx * dx + dy * dy);
+                s += last;
+            }
+            best_ade = fminf(best_ade, s / (float)Tf);
+            best_fde = fminf(best_fde, last);
         }
-        best_ade = fminf(best_ade, s / (float)Tf);
-        best_fde = fminf(best_fde, last);
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        best_ade = fminf(best_ade, __shfl_xor_sync(0xffffffffu, best_ade, o));
-        best_fde = fminf(best_fde, __shfl_xor_sync(0xffffffffu, best_fde, o));
+        for (int o = 16; o > 0; o >>= 1) {
+            best_ade = fminf(best_ade, __shfl_xor_sync(0xffffffffu, best_ade, o));
+            best_fde = fminf(best_fde, __shfl_xor_sync(0xffffffffu, best_fde, o));
+        }
     }
-    if (lane == 0) {
-        atomicAdd(sums, (double)best_ade);
-        atomicAdd(sums + 1, (double)best_fde);
-        atomicAdd(sums + 2, 1.0);
+    if (lane == 0) { s_ade[warp] = row < rows ? best_ade : 0.f; s_fde[warp] = row < rows ? best_fde : 0.f; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, f = 0.0;
+        const int n = min(32, rows - blockIdx.x * 32);
+        for (int i = 0; i < n; ++i) { a += (double)s_ade[i]; f += (double)s_fde[i]; }
+        atomicAdd(sums, a);
+        atomicAdd(sums + 1, f);
+        atomicAdd(sums + 2, (double)n);
     }
 }
 

@@ -143,7 +143,7 @@ class _FoldedFrontEnd:
 
 
 def _encoder_struct(enc, tensor_cores=None):
-    """sttode_encoder_weights of a Past/FutureEncoder.  tensor_cores (default: eval mode, `use_tensor_cores` set, sequence length <= 32): the
+    """sttode_encoder_weights of a Past/FutureEncoder.  tensor_cores (default: eval mode, `use_tensor_cores` set, sequence length <= 30): the
     struct also carries the ODE block's tensor-core operand images and the folded front-end table, which selects the tcgen05 encoder kernels."""
     s = _lib.EncoderWeights()
     s.fc_w, s.fc_b = _lib.dptr(enc.input_fc.weight), _lib.dptr(enc.input_fc.bias)
@@ -156,7 +156,7 @@ def _encoder_struct(enc, tensor_cores=None):
         tensor_cores = not enc.training and layer.use_tensor_cores
     s.ode = _ode_struct(layer, tensor_cores=bool(tensor_cores))
     T = enc.input_fc2.weight.shape[1] // 64
-    if tensor_cores and getattr(enc, "fold_front_end", True) and T <= 32:
+    if tensor_cores and getattr(enc, "fold_front_end", True) and T <= 30:
         s.folded = _lib.dptr(enc._packed.get(enc, T))
     return s
 
@@ -644,7 +644,7 @@ class STTODENet(nn.Module):
         layer = self.past_encoder.ODE_Encoder.odeblock.odefunc.layers[0]
         pk = layer._packed_or_none()
         enc = self.past_encoder
-        fd = enc._packed.get(enc, self.args.past_length).data_ptr() if (pk is not None and enc.fold_front_end and self.args.past_length <= 32) else None
+        fd = enc._packed.get(enc, self.args.past_length).data_ptr() if (pk is not None and enc.fold_front_end and self.args.past_length <= 30) else None
         return (d, pk.data_ptr() if pk is not None else None, fd)
 
     def set_tensor_cores(self, on):
