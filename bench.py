@@ -557,9 +557,13 @@ def train_leg(ctx, args, steps, warmup):
     model = STTODENet(synth.make_args("nba", tp, tf), torch.device("cpu"))
     model.set_device(dev)
     model.train()
-    reducer = parallel.FlatGradReducer(model)
     graph = not args.train_eager
-    opt, sched = parallel.make_optimizer(model, capturable=graph)
+    fused = args.train_exchange == "fused"
+    if fused:                                                    # gradient exchange over NVLink peer memory fused with Adam: no NCCL on the step
+        reducer, opt = parallel.FusedDPAdam(model, lr=1e-4), None
+    else:
+        reducer = parallel.FlatGradReducer(model)
+        opt, sched = parallel.make_optimizer(model, capturable=graph)
     torch.manual_seed(1000 + rank)                               # per-rank dropout / rsample streams
     batches = [{k: v.to(dev) for k, v in synth.nba_batch(100 + rank * 64 + i, B, N, tp, tf).items()} for i in range(8)]
     it = [0]
@@ -588,14 +592,17 @@ def train_leg(ctx, args, steps, warmup):
     e1.record()
     ctx.barrier()
     ms = ctx.max_over_ranks(e0.elapsed_time(e1)) / steps
-    # gradient-equality check across ranks after the reduce: every rank must hold the same flat buffer
-    spread = 0.0
+    # replica-equality check across ranks: after the exchange every rank must hold the same averaged gradient (NCCL path) / the same weights
+    # (fused path: all ranks sum the buffers in the same order, so the replicas stay bit-identical)
+    spread, exch_err = 0.0, 0
     if world > 1:
-        g = reducer.flat.detach().clone()
+        g = (reducer.flat_param if fused else reducer.flat).detach().clone()
         gmax, gmin = g.clone(), g.clone()
         ctx.dist.all_reduce(gmax, op=ctx.dist.ReduceOp.MAX)
         ctx.dist.all_reduce(gmin, op=ctx.dist.ReduceOp.MIN)
         spread = float((gmax - gmin).abs().max().item())
+    if fused:
+        exch_err, _ = reducer.status()
     loss = float(out[0].detach()) if not torch.is_tensor(out) else float(out[0])
     line = {"metric": "training scenes/sec (DP, forward+backward+Adam)", "value": B * world / (ms * 1e-3), "unit": "scenes/s", "n_gpus": world,
             "steps": steps, "warmup": max(warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "dtype": "f32", "data": "synthetic",
@@ -603,9 +610,12 @@ def train_leg(ctx, args, steps, warmup):
                        "parallelism": f"dp{world}: {parallel.describe_reduce(reducer, graph)}"},
             "gpu_launches": int(L.launch_count() - l0) if not graph else f"{getattr(graphed, 'graph_replays_per_step', 1)} CUDA-graph replay(s) per step",
             "library_kernels_per_step": getattr(graphed, "library_launches", None) if graph else int(L.launch_count() - l0) // steps,
-            "cuda_graph": graph, "last_loss": loss, "grad_spread_across_ranks": spread,
+            "cuda_graph": graph, "last_loss": loss, "replica_spread_across_ranks": spread, "exchange": args.train_exchange, "exchange_error_word": exch_err,
             "note": "every layer forward+backward in libsttode_sm100 (ODE blocks, dense layers, decoder incl. GRU through time)"}
     state = {"model": model, "B": B, "N": N, "tp": tp, "tf": tf}
+    if fused:
+        ctx.barrier()                                            # nobody unmaps an arena a peer may still read
+        reducer.close()
     return line, state
 
 
@@ -713,6 +723,9 @@ def main():
     ap.add_argument("--train", action="store_true", help="time only the data-parallel training step (configs[4])")
     ap.add_argument("--train-eager", action="store_true", help="training step launch by launch instead of CUDA-graph replay")
     ap.add_argument("--train-timeout", type=float, default=150.0, help="dead-man timer of the secondary training leg (seconds)")
+    ap.add_argument("--train-exchange", default="fused", choices=["fused", "nccl"],
+                    help="DP gradient exchange: fused = sttode_dp_adam_step over NVLink peer memory (all-reduce + Adam in one kernel, whole step one CUDA graph); "
+                         "nccl = one NCCL all-reduce between a forward+backward graph and an Adam graph")
     ap.add_argument("--train-batch", type=int, default=32, help="scenes per GPU per training step (train.py:24)")
     ap.add_argument("--ffma", action="store_true", help="use the FP32-FFMA decoder tile instead of the tcgen05 one")
     args = ap.parse_args()

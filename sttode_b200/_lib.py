@@ -203,7 +203,7 @@ DIRECT_GRAD_SINKS = False
 
 def grad_sinks(params):
     """The `.grad` tensors of `params` if every one is a preallocated contiguous fp32 CUDA tensor of the parameter's shape (and sinks are enabled)."""
-    if not DIRECT_GRAD_SINKS:
+    if not DIRECT_GRAD_SINKS or os.environ.get("STTODE_NO_GRAD_SINKS"):
         return None
     sinks = []
     for p in params:

@@ -93,9 +93,124 @@ class FlatGradReducer:
         return self.flat
 
 
+class _DevMem:
+    """Zero-copy torch view of library-owned device memory (torch.as_tensor reads __cuda_array_interface__)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+class FusedDPAdam(FlatGradReducer):
+    """Data-parallel Adam whose gradient exchange runs over NVLink / NVSwitch peer memory inside the update kernel (csrc/comm.cu,
+    sttode_dp_adam_step): barrier -> every rank sums all ranks' flat gradient buffers in rank order, scales by 1/world and applies
+    torch.optim.Adam's update to its weight replica -> barrier.  No NCCL call and no host synchronisation, so the WHOLE step (stage,
+    forward, backward, exchange, update) is one CUDA graph at any world size.  Reference: train.py:122 (Adam, lr 1e-4), :64-66.
+
+    Parameters become views into one flat fp32 buffer (so do their `.grad`, inherited from FlatGradReducer; `pz_layer` never receives a
+    gradient and stays outside, as torch's Adam would skip it).  The gradient buffer lives in a cudaMalloc'ed arena exported through CUDA
+    IPC; the 64-byte handles travel through torch.distributed (any backend) once, at construction.  `step()` does not bump the parameters'
+    version counters: call `model.invalidate_packed()` before the next eval forecast (train_step / GraphedTrainStep do)."""
+
+    def __init__(self, module, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, exclude=("pz_layer",), group=None):
+        import ctypes as C
+        from . import _lib
+        self._lib, self.module, self.group = _lib, module, group
+        lib = _lib.lib()
+        params = [(n, p) for n, p in module.named_parameters() if p.requires_grad and not any(n.startswith(e) or ("." + e) in n for e in exclude)]
+        self.params = params
+        self.excluded = [n for n, p in module.named_parameters() if p.requires_grad and all(p is not q for _, q in params)]
+        dev = params[0][1].device
+        if any(p.dtype != torch.float32 or p.device != dev for _, p in params) or dev.type != "cuda":
+            raise ValueError("FusedDPAdam: all parameters must be float32 on one CUDA device")
+        total = sum(p.numel() for _, p in params)
+        self.n = (total + 3) // 4 * 4
+        self.world_size = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world_size > 1 else 0
+        arena, handle = C.c_void_p(), (C.c_ubyte * 64)()
+        _lib.check(lib.sttode_peer_alloc(self.n, C.byref(arena), handle))
+        self.arena = arena.value
+        self.flat = torch.as_tensor(_DevMem(self.arena, self.n), device=dev)              # the flat gradient buffer, in the exported arena
+        self.flat_param = torch.zeros(self.n, device=dev)
+        self.exp_avg, self.exp_avg_sq = torch.zeros(self.n, device=dev), torch.zeros(self.n, device=dev)
+        off = 0
+        with torch.no_grad():
+            for _, p in params:
+                k = p.numel()
+                self.flat_param[off:off + k].copy_(p.detach().reshape(-1))
+                p.data = self.flat_param[off:off + k].view_as(p)
+                p.grad = self.flat[off:off + k].view_as(p)
+                off += k
+        self.lr = torch.full((1,), float(lr), device=dev)
+        self.betas, self.eps = betas, eps
+        arenas = [self.arena] * self.world_size
+        self._opened = []
+        if self.world_size > 1:
+            handles = [None] * self.world_size
+            dist.all_gather_object(handles, bytes(handle), group=group)
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    continue
+                ptr = C.c_void_p()
+                _lib.check(lib.sttode_peer_open((C.c_ubyte * 64).from_buffer_copy(h), C.byref(ptr)))
+                arenas[r] = ptr.value
+                self._opened.append(ptr.value)
+        self.grads_of = torch.tensor(arenas, dtype=torch.int64, device=dev)
+        self.flags_of = torch.tensor([a + self.n * 4 for a in arenas], dtype=torch.int64, device=dev)
+        torch.cuda.synchronize(dev)
+        if self.world_size > 1:
+            dist.barrier(group=group)               # every arena is mapped everywhere before the first step touches a peer
+        _lib.DIRECT_GRAD_SINKS = True
+
+    def world(self):
+        return self.world_size
+
+    def reduce(self):
+        raise RuntimeError("FusedDPAdam exchanges the gradients inside step(); there is no separate reduce()")
+
+    def zero_grad(self, set_to_none=False):
+        self.zero()
+
+    def set_lr(self, lr):
+        """StepLR (train.py:123) changes the rate between epochs: a device scalar, so captured steps see it."""
+        self.lr.fill_(float(lr))
+
+    def step(self, grad_avg=None):
+        """Exchange + update on the current stream.  grad_avg (optional flat tensor) receives the averaged gradient (tests / diagnostics)."""
+        L = self._lib
+        L.check(L.lib().sttode_dp_adam_step(self.grads_of.data_ptr(), self.flags_of.data_ptr(), self.world_size, self.rank, L.dptr(self.flat_param),
+                                            L.dptr(self.exp_avg), L.dptr(self.exp_avg_sq), L.dptr(grad_avg), self.n, L.dptr(self.lr),
+                                            self.betas[0], self.betas[1], self.eps, L.stream_ptr()))
+
+    def status(self):
+        """(error word, steps taken); synchronises.  error != 0: a peer never arrived at a barrier (the step's result is invalid)."""
+        import ctypes as C
+        err, step = C.c_uint(), C.c_uint()
+        torch.cuda.synchronize()
+        self._lib.check(self._lib.lib().sttode_peer_status(self.arena, self.n, C.byref(err), C.byref(step)))
+        return err.value, step.value
+
+    def close(self):
+        """Unmap the peers' arenas and free this rank's (call on every rank after a collective barrier; the parameters keep their flat storage,
+        their .grad views die with the arena)."""
+        lib = self._lib.lib()
+        torch.cuda.synchronize()
+        for _, p in self.params:
+            p.grad = None
+        self.flat = None
+        for a in self._opened:
+            lib.sttode_peer_close(a)
+        self._opened = []
+        if self.arena:
+            lib.sttode_peer_free(self.arena)
+            self.arena = None
+
+
 def describe_reduce(reducer, graphed):
     """One line for bench.py's config: how the gradients of this run are exchanged."""
     w = reducer.world()
+    if isinstance(reducer, FusedDPAdam):
+        return (f"gradient all-reduce fused with Adam over NVLink peer memory (sttode_dp_adam_step: barrier, every rank sums the {w} flat {reducer.nbytes} B "
+                f"buffers in rank order and updates its replica, barrier); no NCCL call; whole step = {'one CUDA-graph replay' if graphed else 'eager launches'}")
     if w == 1:
         return "single GPU: no exchange; whole step (stage .. Adam) is one CUDA-graph replay" if graphed else "single GPU: no exchange"
     how = "between a forward+backward graph and an Adam graph" if graphed else "eager"
@@ -115,8 +230,12 @@ def train_step(model, optimizer, reducer, stage):
     out = model.forward()
     reducer.zero()
     out[0].backward()
-    reducer.reduce()
-    optimizer.step()
+    if isinstance(reducer, FusedDPAdam):            # exchange + update in one kernel sequence over peer memory (optimizer is the reducer itself)
+        reducer.step()
+        model.invalidate_packed()
+    else:
+        reducer.reduce()
+        optimizer.step()
     return out
 
 
@@ -142,13 +261,15 @@ class GraphedTrainStep:
         dev = batch["past_traj"].device
         self.static = {k: batch[k].detach().clone().contiguous() for k in ("past_traj", "future_traj")}
         self.losses = torch.zeros(5, device=dev)
-        self.split = reducer.world() > 1
+        self.fused = isinstance(reducer, FusedDPAdam)
+        self.split = reducer.world() > 1 and not self.fused       # NCCL stays outside the graphs; the peer-memory exchange is captured with the rest
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(warmup):
                 self._forward_backward()
-                self.reducer.reduce()
+                if not self.fused:
+                    self.reducer.reduce()
                 self._update()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
@@ -179,7 +300,10 @@ class GraphedTrainStep:
         self.losses.copy_(torch.cat((total.detach().reshape(1), parts)))
 
     def _update(self):
-        self.optimizer.step()
+        if self.fused:
+            self.reducer.step()
+        else:
+            self.optimizer.step()
 
     def __call__(self, batch):
         for k, v in self.static.items():

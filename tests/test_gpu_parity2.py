@@ -350,3 +350,74 @@ def test_folded_front_end_vs_layer_by_layer(dev, dataset, tp, tf, B, N):
     m.future_encoder.fold_front_end = True
     q_ref = O.future_encoder(feats.cpu().double(), B, N, ref, O.cast_state_dict(sd, torch.float64))
     assert rel_rows(q_fold, q_ref, scale_floor=1e-2) < TOL and rel_rows(q_layers, q_ref, scale_floor=1e-2) < TOL
+
+
+# ------------------------------------------------------------------ pmath: backward rules and the remaining helpers (pmath.py:76-493)
+@pytest.mark.parametrize("c", [1.0, 0.5])
+def test_pmath_backward_vs_oracle_autograd(dev, c):
+    """Every pmath drop-in is differentiable like the reference's torch code: gradients w.r.t. all tensor arguments against torch autograd over
+    the float64 oracle (which carries the reference's Artanh / Arsinh gradient rules), points well inside the ball plus rows past the
+    projection radius (project's where-branch)."""
+    from oracle import pmath_oracle as PO
+    from sttode_b200 import pmath as P
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(37, 16, generator=g) * 0.15
+    y = torch.randn(37, 16, generator=g) * 0.15
+    xo = x.clone()
+    xo[5] *= 12.0                                   # outside the ball: project's rescaling branch
+    mat = torch.randn(24, 16, generator=g) * 0.3
+    w = torch.randn(37, 24, generator=g)
+
+    def run(fn_ours, fn_ref, args, proj=True):
+        outs = []
+        for lib_, dt, dv in ((P, torch.float32, dev), (PO, torch.float64, "cpu")):
+            ins = [a.to(dv, dt).requires_grad_(True) for a in args]
+            pts = [lib_.project(a, c=c) if (proj and a.shape[-1] == 16 and a.dim() == 2 and a.shape[0] == 37) else a for a in ins]
+            out = (fn_ours if lib_ is P else fn_ref)(*pts)
+            seed = torch.linspace(0.5, 1.5, out.numel()).reshape(out.shape).to(dv, dt)
+            out.backward(seed)
+            outs.append([a.grad.detach().cpu().double() for a in ins])
+        for got, ref in zip(*outs):
+            assert float((got - ref).abs().max() / ref.abs().max().clamp_min(1e-12)) < 2e-4
+
+    run(lambda a: P.project(a, c=c), lambda a: PO.project(a, c), [xo], proj=False)
+    run(lambda a: P.lambda_x(a, c=c), lambda a: PO.lambda_x(a, c), [x])
+    run(lambda a, b: P.mobius_add(a, b, c=c), lambda a, b: PO.mobius_add(a, b, c), [x, y])
+    run(lambda a, b: P.dist(a, b, c=c), lambda a, b: PO.dist(a, b, c), [x * 0.5, y * 0.5])
+    run(lambda a: P.dist0(a, c=c), lambda a: PO.dist0(a, c), [x * 0.5])
+    run(lambda a: P.expmap0(a, c=c), lambda a: PO.expmap0(a, c), [x], proj=False)
+    run(lambda a: P.logmap0(a, c=c), lambda a: PO.logmap0(a, c), [x * 0.5])
+    run(lambda a, b: P.expmap(a, b, c=c), lambda a, b: PO.expmap(a, b, c), [x * 0.5, y])
+    run(lambda a, b: P.logmap(a, b, c=c), lambda a, b: PO.logmap(a, b, c), [x * 0.5, y * 0.5])
+    run(lambda m_, a: P.mobius_matvec(m_, a, c=c), lambda m_, a: PO.mobius_matvec(m_, a, c), [mat, x * 0.5])
+    run(lambda a, b: P.dist_matrix(a, b, c=c), lambda a, b: PO.dist_matrix(a, b, c), [x * 0.5, y * 0.5])
+    run(lambda a, b: (P._mobius_addition_batch(a, b, c) * w.to(a.device, a.dtype)[:, :1, None]).sum(1),
+        lambda a, b: (PO.mobius_addition_batch(a, b, c) * w.to(a.device, a.dtype)[:, :1, None]).sum(1), [x * 0.5, y * 0.5])
+
+
+def test_pmath_remaining_helpers(dev):
+    """poincare_mean against the golden generated from the reference (tests/golden/pmath.npz), p2k / k2p round trip, _mobius_addition_batch
+    against the row-wise mobius_add kernel, _hyperbolic_softmax against its float64 restatement."""
+    import os
+    from oracle import pmath_oracle as PO
+    from sttode_b200 import pmath as P
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "pmath.npz"))
+    x = torch.from_numpy(g["x"]).to(dev)
+    for c in (1.0, 0.5):
+        px = P.project(x, c=c)
+        np.testing.assert_allclose(P.poincare_mean(px, dim=0, c=c).cpu().numpy(), g[f"poincare_mean_c{c}"], rtol=2e-4, atol=2e-6)
+        np.testing.assert_allclose(P.k2p(P.p2k(px, c), c).cpu().numpy(), px.cpu().numpy(), rtol=1e-4, atol=1e-6)
+        y = P.project(torch.from_numpy(g["y"]).to(dev), c=c)
+        mab = P._mobius_addition_batch(px, y, c)
+        for j in (0, y.shape[0] - 1):
+            np.testing.assert_allclose(mab[:, j].cpu().numpy(), P.mobius_add(px, y[j].expand_as(px), c=c).cpu().numpy(), rtol=2e-4, atol=2e-6)
+    gen = torch.Generator().manual_seed(1)
+    X, A, Pp = torch.randn(9, 8, generator=gen) * 0.2, torch.randn(5, 8, generator=gen), torch.randn(5, 8, generator=gen) * 0.2
+    got = P._hyperbolic_softmax(X.to(dev), A.to(dev), Pp.to(dev), 1.0).cpu().double()
+    Xd, Ad, Pd = X.double(), A.double(), Pp.double()
+    lam = 2 / (1 - (Pd * Pd).sum(1))
+    ma = PO.mobius_addition_batch(-Pd, Xd, 1.0)
+    num = 2 * (ma * Ad.unsqueeze(1)).sum(-1)
+    den = Ad.norm(dim=1, keepdim=True) * (1 - (ma * ma).sum(2))
+    ref = ((lam * Ad.norm(dim=1)).unsqueeze(1) * torch.asinh(num / den)).permute(1, 0)
+    assert float((got - ref).abs().max() / ref.abs().max()) < 1e-4

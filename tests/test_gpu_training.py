@@ -154,3 +154,50 @@ def test_cuda_graph_training_step_equals_eager(dev):
     for k in wa:
         if wa[k].is_floating_point():
             assert float((wa[k] - wb[k]).abs().mean()) < 2e-5, k
+
+
+def test_fused_dp_adam_matches_torch_adam(dev):
+    """parallel.FusedDPAdam (sttode_dp_adam_step: gradient exchange over peer memory fused with the update; world 1 here, so the exchange is
+    the identity) against torch.optim.Adam on the same model, same batches, every random draw injected: same losses, same weights after three
+    steps, eager and as ONE CUDA graph (stage .. update); the flat parameter / gradient views stay attached; the step count lives on the device."""
+    from sttode_b200 import parallel
+    dataset, tp, tf, B, N = "nba", 10, 20, 8, 11
+    d = training_draws(B * N, tp, tf, seed=31)
+    batches = [{k: v.to(dev) for k, v in synth.nba_batch(30 + i, B, N, tp, tf).items()} for i in range(3)]
+    results = []
+    for mode in ("torch", "fused", "fused-graph"):
+        m, _ = build(dataset, tp, tf, dev, seed=7)
+        m.train()
+        m.past_encoder.dropout_mask_override, m.future_encoder.dropout_mask_override = d["mask_past"].to(dev), d["mask_future"].to(dev)
+        m.eps_override = (d["eps_q"].to(dev), d["eps_p"].to(dev))
+        losses = []
+        if mode == "torch":
+            red = parallel.FlatGradReducer(m)
+            opt, _ = parallel.make_optimizer(m, lr=1e-3)
+        else:
+            red, opt = parallel.FusedDPAdam(m, lr=1e-3), None
+            assert all(p.data_ptr() >= red.flat_param.data_ptr() and p.data_ptr() < red.flat_param.data_ptr() + red.n * 4 for _, p in red.params)
+        if mode == "fused-graph":
+            step = parallel.GraphedTrainStep(m, opt, red, batches[0], warmup=1)
+            assert step.graph_replays_per_step == 1
+            losses.append(step.losses.clone())
+            for b in batches[1:]:
+                losses.append(step(b).clone())
+        else:
+            for b in batches:
+                out = parallel.train_step(m, opt, red, lambda: m.set_data_nba(b))
+                losses.append(torch.tensor([float(out[0].detach()), *out[1:]], device=dev))
+        torch.cuda.synchronize()
+        if mode != "torch":
+            err, steps = red.status()
+            assert err == 0 and steps == 3
+        results.append((torch.stack(losses).cpu(), {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}))
+        if mode != "torch":
+            red.close()
+    (la, wa), (lb, wb), (lc, wc) = results
+    assert torch.allclose(la, lb, rtol=1e-4, atol=0), (la, lb)
+    assert torch.allclose(lb, lc, rtol=1e-5, atol=0), (lb, lc)
+    for k in wa:
+        if wa[k].is_floating_point():
+            assert float((wa[k] - wb[k]).abs().mean()) < 2e-5, k
+            assert float((wb[k] - wc[k]).abs().mean()) < 2e-6, k
