@@ -275,17 +275,21 @@ class GraphedTrainStep:
         torch.cuda.synchronize(dev)
         from . import _lib
         l0 = _lib.launch_count()
+        # Capture on the SAME stream the warm-up ran on: the parameters' AccumulateGrad nodes were created there and outlive the warm-up
+        # graph (the model's cached stage tensors keep it alive); autograd closes backward() by making the caller's stream wait on every
+        # leaf stream, which is only legal under capture when that stream is the capturing one (with direct gradient sinks nothing else
+        # would pull a foreign leaf stream into the capture first).
         self.graph = torch.cuda.CUDAGraph()
         if not self.split:
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, stream=side):
                 self._forward_backward()
                 self._update()
             self.graph_update = None
         else:
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, stream=side):
                 self._forward_backward()
             self.graph_update = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_update, pool=self.graph.pool()):
+            with torch.cuda.graph(self.graph_update, pool=self.graph.pool(), stream=side):
                 self._update()
         self.library_launches = _lib.launch_count() - l0       # libsttode_sm100 kernels recorded into the graph(s) = per replayed step
 
