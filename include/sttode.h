@@ -246,8 +246,11 @@ int sttode_decoder_fwd(const float *past_feature, const float *traj_norm, const 
  *   bwd: dx[rows,K] = dy . W (dx nullable, row stride lddx);  dW[N,K] += dy^T . x;  db[N] += column sums of dy   (dW / db nullable).
  * The caller masks dy with the ReLU derivative beforehand when the forward used one.  Deterministic summation order. */
 int sttode_dense_fwd(const float *x, int ldx, const float *weight, const float *bias, float *y, int rows, int K, int N, int relu, void *stream);
+/* workspace (nullable): scratch for the split-K form of the weight / bias gradients — with a few thousand rows and a 64-wide layer the
+ * reduction runs over the rows, so without it one CTA walks the whole batch (0.2 ms per layer at 7040 rows); sttode_dense_bwd_workspace_bytes(). */
+size_t sttode_dense_bwd_workspace_bytes(void);
 int sttode_dense_bwd(const float *x, int ldx, const float *weight, const float *dy, float *dx, int lddx, float *dweight, float *dbias, int rows,
-                     int K, int N, void *stream);
+                     int K, int N, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- backward of Decoder.forward in 'train' mode (model/STTODE.py:320-347, both DecomposeBlocks :51-77); the reference gets it from
  * torch autograd (train.py:65).  One row per (agent, sample) pair: past_feature [pairs,128], z [pairs,32], traj_norm [pairs,T_p,2] (x_true,

@@ -97,7 +97,8 @@ SIGNATURES = {
     "sttode_decoder_workspace_bytes": (_Z, [_I, _I]),
     "sttode_decoder_fwd": (_I, [_V, _V, _V, _U64, _V, _V, _I, _I, C.POINTER(ModelWeights), _V, _V, _V, _Z, _V]),
     "sttode_dense_fwd": (_I, [_V, _I, _V, _V, _V, _I, _I, _I, _I, _V]),
-    "sttode_dense_bwd": (_I, [_V, _I, _V, _V, _V, _I, _V, _V, _I, _I, _I, _V]),
+    "sttode_dense_bwd_workspace_bytes": (_Z, []),
+    "sttode_dense_bwd": (_I, [_V, _I, _V, _V, _V, _I, _V, _V, _I, _I, _I, _V, _Z, _V]),
     "sttode_decoder_bwd_workspace_bytes": (_Z, [_I, _I, _I]),
     "sttode_decoder_bwd": (_I, [_V, _V, _V, _V, _V, _I, C.POINTER(ModelWeights), C.POINTER(DecomposeGrads), _V, _V, _V, _Z, _V]),
     "sttode_decoder_pack_bytes": (_Z, [_I, _I]),
@@ -188,6 +189,20 @@ def stream_ptr():
 
 def workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+_scratch = {}
+
+
+def scratch(nbytes, device, tag="default"):
+    """A per-(device, tag) scratch buffer that only grows: kernels that need a fixed-size workspace on every call (split-K partial sums) share it, and
+    its pointer stays valid across CUDA-graph replays.  Single-stream use only (the library's calls are stream-ordered)."""
+    key = (str(device), tag)
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _scratch[key] = buf
+    return buf
 
 
 def launch_count():

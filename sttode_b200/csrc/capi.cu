@@ -1118,12 +1118,16 @@ int sttode_dense_fwd(const float* x, int ldx, const float* weight, const float* 
     return gemm_nt((cudaStream_t)stream, rows, N, K, x, ldx, weight, bias, y, N, relu ? 1 : 0);
 }
 
+size_t sttode_dense_bwd_workspace_bytes(void) { return align_up(SPLITK_FLOATS * 4) + 256; }
+
 int sttode_dense_bwd(const float* x, int ldx, const float* weight, const float* dy, float* dx, int lddx, float* dweight, float* dbias, int rows, int K,
-                     int N, void* stream) {
+                     int N, void* workspace, size_t workspace_bytes, void* stream) {
     int rc;
     if (!x || !weight || !dy || rows < 1 || K < 1 || N < 1 || ldx < K || (dx && lddx < K)) return fail(STTODE_EINVAL, "dense_bwd: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
-    if ((rc = weight_grad(st, rows, N, K, dy, N, x, ldx, dweight, dbias))) return rc;
+    float* splitk = nullptr;
+    if (workspace && workspace_bytes >= SPLITK_FLOATS * 4) splitk = (float*)workspace;       // rows split over gridDim.z, slices summed in order (deterministic)
+    if ((rc = weight_grad(st, rows, N, K, dy, N, x, ldx, dweight, dbias, splitk))) return rc;
     if (dx && (rc = gemm_nn(st, rows, K, N, dy, N, weight, dx, lddx))) return rc;
     return 0;
 }

@@ -495,10 +495,8 @@ __device__ void epi_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, const 
         for (int q = 0; q < 3; ++q) {
             const int u = u0 + q * 8;
             float gr[8], gz[8], gni[8], gnh[8];
-            tc::tmem_ld8(tmem + lane_base + COL_GR + u, gr);
-            tc::tmem_ld8(tmem + lane_base + COL_GR + 96 + u, gz);
-            tc::tmem_ld8(tmem + lane_base + COL_GNI + u, gni);
-            tc::tmem_ld8(tmem + lane_base + COL_GNH + u, gnh);
+            tc::tmem_ld8x4(tmem + lane_base + COL_GR + u, tmem + lane_base + COL_GR + 96 + u, tmem + lane_base + COL_GNI + u, tmem + lane_base + COL_GNH + u,
+                           gr, gz, gni, gnh);          // four loads in flight, one wait
             float v[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {

@@ -93,6 +93,23 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+// four 8-column loads in flight, ONE wait: the GRU gate epilogue reads r, z, W_in x and W_hn h of the same 8 units from four column ranges
+__device__ __forceinline__ void tmem_ld8x4(uint32_t t0, uint32_t t1, uint32_t t2, uint32_t t3, float (&a)[8], float (&b)[8], float (&c)[8], float (&d)[8]) {
+    uint32_t r[32];
+#define STTODE_LD8(T, O)                                                                                                          \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                                         \
+                 : "=r"(r[O]), "=r"(r[O + 1]), "=r"(r[O + 2]), "=r"(r[O + 3]), "=r"(r[O + 4]), "=r"(r[O + 5]), "=r"(r[O + 6]), "=r"(r[O + 7]) \
+                 : "r"(T)                                                                                                          \
+                 : "memory")
+    STTODE_LD8(t0, 0);
+    STTODE_LD8(t1, 8);
+    STTODE_LD8(t2, 16);
+    STTODE_LD8(t3, 24);
+#undef STTODE_LD8
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[8 + i]); c[i] = __uint_as_float(r[16 + i]); d[i] = __uint_as_float(r[24 + i]); }
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
     asm volatile(

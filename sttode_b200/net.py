@@ -242,8 +242,10 @@ class _DenseFn(torch.autograd.Function):
             dw, db = ctx.sinks
         else:
             dw, db = torch.zeros_like(w), torch.zeros(N, device=w.device, dtype=torch.float32)      # the library accumulates (+=)
-        _lib.check(_lib.lib().sttode_dense_bwd(_lib.dptr(xs), K, _lib.dptr(w), _lib.dptr(dy), _lib.dptr(dx), K, _lib.dptr(dw), _lib.dptr(db), rows, K, N,
-                                               _lib.stream_ptr()))
+        lib = _lib.lib()
+        ws = _lib.scratch(lib.sttode_dense_bwd_workspace_bytes(), xs.device, "splitk")
+        _lib.check(lib.sttode_dense_bwd(_lib.dptr(xs), K, _lib.dptr(w), _lib.dptr(dy), _lib.dptr(dx), K, _lib.dptr(dw), _lib.dptr(db), rows, K, N,
+                                        _lib.dptr(ws), ws.numel(), _lib.stream_ptr()))
         return (dx.view(shape) if need_dx else None), (None if direct else dw), (None if direct else db), None
 
 
