@@ -57,8 +57,14 @@ DecPackLayout dec_pack_layout(int Tp, int Tf) {
 // ---- all weight images of one pack in ONE launch ------------------------------------------------------------------------------
 // Job j (blockIdx.y) is one operand image; the job list is a closed-form function of the layout, so nothing but the weight pointers
 // and the layout travels to the device (round 1 issued 264 single-image launches + 8 memsets per pack).
-struct PackJob { const float* W; int ldw, row0, col0, nvalid, nrows, K; uint32_t hi, lo; };
-constexpr int PACK_JOBS_MLP = 42, PACK_JOBS = 4 * PACK_JOBS_MLP + 16 + 88 + 1;
+struct PackJob { const float* W; int ldw, row0, col0, nvalid, nrows, K; uint32_t hi, lo; int perm; };      // perm: 0 rows as stored, 1 / 2 GRU half A / B
+constexpr int PACK_JOBS_MLP = 42, PACK_JOBS = 4 * PACK_JOBS_MLP + 32 + 88 + 1;
+// GRU weight rows are stored [r 96 | z 96 | n 96]; half A (units 0..63) and half B (units 64..95) get their own images [r | z | n]
+__device__ __forceinline__ int gru_perm_row(int perm, int i) {
+    if (perm == 1) return i < 64 ? i : i < 128 ? 96 + (i - 64) : 192 + (i - 128);
+    if (perm == 2) return i < 32 ? 64 + i : i < 64 ? 96 + 64 + (i - 32) : 192 + 64 + (i - 64);
+    return i;
+}
 
 __device__ __forceinline__ PackJob pack_job(int j, const sttode_decompose_weights& w0, const sttode_decompose_weights& w1, const DecPackLayout& L) {
     PackJob J{};
@@ -84,15 +90,16 @@ __device__ __forceinline__ PackJob pack_job(int j, const sttode_decompose_weight
         return J;
     }
     j -= 4 * PACK_JOBS_MLP;
-    if (j < 16) {
-        const int g = j >> 3, kb = j & 7;
+    if (j < 32) {
+        const int g = j >> 4, half = (j >> 3) & 1, kb = j & 7;
         const sttode_decompose_weights& w = g ? w1 : w0;
-        const uint32_t blk = L.gru_off[g] + (uint32_t)kb * TC_GRU_BLK;
-        if (kb < 2) J = PackJob{w.gru_w_ih, 32, 0, kb * 16, 288, 288, 16, blk, blk + 9216};
-        else        J = PackJob{w.gru_w_hh, 96, 0, (kb - 2) * 16, 288, 288, 16, blk, blk + 9216};
+        const uint32_t blk = L.gru_off[g] + (half ? 8u * TC_GRU_A + (uint32_t)kb * TC_GRU_B : (uint32_t)kb * TC_GRU_A);
+        const int nrows = half ? 96 : 192;
+        if (kb < 2) J = PackJob{w.gru_w_ih, 32, 0, kb * 16, nrows, nrows, 16, blk, blk + (uint32_t)nrows * 32, 1 + half};
+        else        J = PackJob{w.gru_w_hh, 96, 0, (kb - 2) * 16, nrows, nrows, 16, blk, blk + (uint32_t)nrows * 32, 1 + half};
         return J;
     }
-    j -= 16;
+    j -= 32;
     if (j < 88) {   // row kernel: tile t = (product p = t/2, columns (t&1)*256..): K slabs over [pf 0..127 | state 160..255] (p < 2) or pf only
         int t, ks;
         if (j < 56) { t = j / 14; ks = j - t * 14; } else { t = 4 + (j - 56) / 8; ks = (j - 56) & 7; }
@@ -118,7 +125,7 @@ __global__ void k_pack_all(sttode_decompose_weights w0, sttode_decompose_weights
     const int kc = idx / J.nrows, r = idx - kc * J.nrows;
     float v[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = r < J.nvalid ? __ldg(J.W + (size_t)(J.row0 + r) * J.ldw + J.col0 + kc * 8 + i) : 0.f;
+    for (int i = 0; i < 8; ++i) v[i] = r < J.nvalid ? __ldg(J.W + (size_t)(J.row0 + gru_perm_row(J.perm, r)) * J.ldw + J.col0 + kc * 8 + i) : 0.f;
     tc::store_split8(pk + J.hi, pk + J.lo, J.nrows, r, kc, v);
 }
 void launch_pack_all(const sttode_decompose_weights& w0, const sttode_decompose_weights& w1, const DecPackLayout& L, unsigned char* pk, cudaStream_t st) {
@@ -141,8 +148,10 @@ constexpr int SM_H = 65536;                      // 2 x [hi 8 KB | lo 8 KB] (MLP
 constexpr int SM_RING = SM_H + 32768;
 constexpr int SM_XY = SM_RING + TC_NST * TC_STAGE;
 constexpr int COL_D2 = 0, COL_D1 = 256, COL_D3 = 384;     // TMEM columns, MLP phases (D1: 4 x 32; D3 <= 128 columns)
-constexpr int COL_GR = 0, COL_GNI = 192, COL_GNH = 288;   // GRU phase (r|z contiguous at 0..191); overlaps D2/D1, not D3
-constexpr int B_WFULL = 0, B_WFREE = 4, B_D1FULL = 8, B_HFULL = 12, B_HFREE = 14, B_ACC = 16, B_XFULL = 17, B_D3FREE = 18, B_COUNT = 19;
+// GRU phase accumulators (overlap D2 / D1, not D3).  A step runs as two N-halves so the gate epilogue of half A overlaps the MMAs of half B:
+//   half A (units 0..63):  r 0..63 | z 64..127 | W_in x 128..191 | W_hn h 192..255        half B (units 64..95): r 256..287 | z 288..319 | W_in x 320..351 | W_hn h 352..383
+constexpr int COL_GA = 0, COL_GA_NI = 128, COL_GA_NH = 192, COL_GB = 256, COL_GB_NI = 320, COL_GB_NH = 352;
+constexpr int B_WFULL = 0, B_WFREE = 4, B_D1FULL = 8, B_HFULL = 12, B_HFREE = 14, B_ACC = 16, B_XFULL = 17, B_D3FREE = 18, B_ACC2 = 19, B_COUNT = 20;      // B_ACC2: GRU half B complete
 
 // debug timeline: absolute clock64 stamps into the status tail (CTA 0 only, when status[1] == 2)
 // compiled in only with -DSTTODE_TC_TIMELINE (scripts/tc_timing.py); the release build has no trace of it
@@ -176,15 +185,20 @@ __device__ __forceinline__ void epi_signal(uint64_t* bars, int bar) {
     if ((threadIdx.x & 31) == 0) mbar_arrive(bars + bar);
 }
 
-// global block sequence: [mlp x0: 36 blocks] [gru1: 8*Tp] [mlp y0: 36] [mlp y1: 36] [mlp x1: 36 when recon]
+// global block sequence: [mlp x0: 36 blocks] [gru1: 16*Tp] [mlp y0: 36] [mlp y1: 36] [mlp x1: 36 when recon]
 // one MLP = lead pair, 32 chunk blocks, layer-3 pair
 __device__ __forceinline__ void block_src(const DecPackLayout& lay, int Tp, int i, uint32_t& off, uint32_t& bytes) {
     int m;
     if (i < TC_MLP_BLOCKS) m = 0;
     else {
         i -= TC_MLP_BLOCKS;
-        if (i < 8 * Tp) { off = lay.gru_off[1] + (uint32_t)(i & 7) * TC_GRU_BLK; bytes = TC_GRU_BLK; return; }
-        i -= 8 * Tp;
+        if (i < 16 * Tp) {                          // per step: A-blocks of the 8 K-slabs, then their B-blocks
+            const int j = i & 15;
+            if (j < 8) { off = lay.gru_off[1] + (uint32_t)j * TC_GRU_A; bytes = TC_GRU_A; }
+            else       { off = lay.gru_off[1] + 8u * TC_GRU_A + (uint32_t)(j - 8) * TC_GRU_B; bytes = TC_GRU_B; }
+            return;
+        }
+        i -= 16 * Tp;
         if (i < TC_MLP_BLOCKS) m = 1;
         else if (i < 2 * TC_MLP_BLOCKS) { m = 2; i -= TC_MLP_BLOCKS; }
         else { m = 3; i -= 2 * TC_MLP_BLOCKS; }
@@ -294,7 +308,7 @@ __device__ void issuer_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int
 
 __device__ void issuer_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, int blk0, int T, uint32_t n_d3, uint32_t& n_x) {
     const uint32_t a1 = tc::smem_u32(sm + SM_A1), xh = tc::smem_u32(sm + SM_H), ring0 = tc::smem_u32(sm + SM_RING);
-    const uint32_t idesc_rz = tc::make_idesc_f16(192), idesc_n = tc::make_idesc_f16(96);
+    const uint32_t idesc128 = tc::make_idesc_f16(128), idesc64 = tc::make_idesc_f16(64), idesc32 = tc::make_idesc_f16(32);
     (void)n_d3;                                     // the gate accumulators (columns 0..383) overlap D2 / D1 (all read out), not D3
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
@@ -304,26 +318,37 @@ __device__ void issuer_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, int
         ++n_x;
         tc::tc_fence_after();
         TLOG(tl, 21);
-        // one elected lane issues the whole step (8 K = 16 slabs of [W_ih | W_hh], 288 rows each): no reconvergence between slabs
+        // one elected lane issues the whole step: half A (units 0..63) over the 8 K = 16 slabs of [W_ih | W_hh], commit, then half B (units 64..95):
+        // the epilogue works on half A's gates while the tensor pipe runs half B
         if (elect_one()) {
 #pragma unroll
-            for (int kb = 0; kb < 8; ++kb) {
-                const int bi = blk0 + t * 8 + kb;
-                const uint32_t st = ring0 + (uint32_t)(bi & 3) * TC_STAGE;
-                if (!(kb & 1)) {                    // blk0 is even: the pair's barrier covers slab kb + 1 too
-                    tc_wait(bars, B_WFULL + ((bi >> 1) & 1), (uint32_t)((bi >> 2) & 1));
-                    tc::tc_fence_after();
+            for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                for (int kb = 0; kb < 8; ++kb) {
+                    const int bi = blk0 + t * 16 + half * 8 + kb;
+                    const uint32_t st = ring0 + (uint32_t)(bi & 3) * TC_STAGE;
+                    if (!(kb & 1)) {                // blk0 is even: the pair's barrier covers slab kb + 1 too
+                        tc_wait(bars, B_WFULL + ((bi >> 1) & 1), (uint32_t)((bi >> 2) & 1));
+                        tc::tc_fence_after();
+                    }
+                    // A operand slab: kb < 2 -> conv image (k chunks 2kb, 2kb+1); else state h (A1 k chunks 4 + 2(kb-2) ..)
+                    const uint32_t a_off = kb < 2 ? xh + kb * 4096 : a1 + 4 * 2048 + (kb - 2) * 4096;
+                    const uint32_t a_lo_off = kb < 2 ? a_off + 8192 : a_off + 32768;
+                    const uint64_t ah = tc::op_desc(a_off, 128), al = tc::op_desc(a_lo_off, 128);
+                    if (half == 0) {                // image rows [r 64 | z 64 | n 64], lo image 6144 B behind the hi image
+                        tc::mma_split3_d(tmem + COL_GA, ah, al, 0, tc::op_desc(st, 192), tc::op_desc(st + 6144, 192), 0, idesc128, 1, kb > 0);
+                        const uint64_t bnh = tc::op_desc(st + 128 * 16, 192), bnl = tc::op_desc(st + 6144 + 128 * 16, 192);
+                        if (kb < 2) tc::mma_split3_d(tmem + COL_GA_NI, ah, al, 0, bnh, bnl, 0, idesc64, 1, kb > 0);
+                        else        tc::mma_split3_d(tmem + COL_GA_NH, ah, al, 0, bnh, bnl, 0, idesc64, 1, kb > 2);
+                    } else {                        // image rows [r 32 | z 32 | n 32], lo image 3072 B behind the hi image
+                        tc::mma_split3_d(tmem + COL_GB, ah, al, 0, tc::op_desc(st, 96), tc::op_desc(st + 3072, 96), 0, idesc64, 1, kb > 0);
+                        const uint64_t bnh = tc::op_desc(st + 64 * 16, 96), bnl = tc::op_desc(st + 3072 + 64 * 16, 96);
+                        if (kb < 2) tc::mma_split3_d(tmem + COL_GB_NI, ah, al, 0, bnh, bnl, 0, idesc32, 1, kb > 0);
+                        else        tc::mma_split3_d(tmem + COL_GB_NH, ah, al, 0, bnh, bnl, 0, idesc32, 1, kb > 2);
+                    }
+                    if (kb & 1) tc::mma_commit(bars + B_WFREE + ((bi >> 1) & 1));
+                    if (kb == 7) tc::mma_commit(bars + (half ? B_ACC2 : B_ACC));      // half A -> B_ACC, half B -> B_ACC2 (one completion each per step)
                 }
-                // A operand slab: kb < 2 -> conv image (k chunks 2kb, 2kb+1); else state h (A1 k chunks 4 + 2(kb-2) ..)
-                const uint32_t a_off = kb < 2 ? xh + kb * 4096 : a1 + 4 * 2048 + (kb - 2) * 4096;
-                const uint32_t a_lo_off = kb < 2 ? a_off + 8192 : a_off + 32768;
-                const uint64_t ah = tc::op_desc(a_off, 128), al = tc::op_desc(a_lo_off, 128);
-                tc::mma_split3_d(tmem + COL_GR, ah, al, 0, tc::op_desc(st, 288), tc::op_desc(st + 9216, 288), 0, idesc_rz, 1, kb > 0);
-                const uint64_t bnh = tc::op_desc(st + 192 * 16, 288), bnl = tc::op_desc(st + 9216 + 192 * 16, 288);
-                if (kb < 2) tc::mma_split3_d(tmem + COL_GNI, ah, al, 0, bnh, bnl, 0, idesc_n, 1, kb > 0);
-                else        tc::mma_split3_d(tmem + COL_GNH, ah, al, 0, bnh, bnl, 0, idesc_n, 1, kb > 2);
-                if (kb & 1) tc::mma_commit(bars + B_WFREE + ((bi >> 1) & 1));
-                if (kb == 7) tc::mma_commit(bars + B_ACC);
             }
         }
         __syncwarp();
@@ -455,10 +480,9 @@ __device__ void epi_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, const 
         const int img = i / (12 * 128), r = i - img * 12 * 128;
         *reinterpret_cast<uint4*>(sm + SM_A1 + img * 32768 + 4 * 2048 + r * 16) = make_uint4(0, 0, 0, 0);
     }
-    float hreg[24];                                 // this thread's 24 hidden units (sub*24 ..) of row m, fp32 across the recurrence
+    float hreg[24];                                 // this thread's 24 hidden units of row m (chunks 2*sub, 2*sub+1, 8+sub), fp32 across the recurrence
 #pragma unroll
     for (int i = 0; i < 24; ++i) hreg[i] = 0.f;
-    const int u0 = sub * 24;
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
         // conv channels sub*8 .. +8 of row m at time t -> k chunk `sub` of the conv image (H[0])
@@ -487,17 +511,25 @@ __device__ void epi_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, const 
         TLOG(tl, 0);
         epi_signal(bars, B_XFULL);                  // conv image t (+ state h_t written at the end of step t-1)
         TLOG(tl, 1);
-        tc_wait(bars, B_ACC, n_acc & 1);
-        ++n_acc;
-        tc::tc_fence_after();
-        TLOG(tl, 2);
+        // this thread's three 8-unit chunks of row m: chunks 2*sub, 2*sub+1 (half A, units 0..63) and 8+sub (half B, units 64..95).  The new
+        // state is computed per half as soon as that half's accumulators are complete, but h is staged only after BOTH halves' MMAs have
+        // finished reading the old state image.
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-            const int u = u0 + q * 8;
+            if (q == 0) {                           // half A complete
+                tc_wait(bars, B_ACC, n_acc & 1);
+                ++n_acc;
+                tc::tc_fence_after();
+                TLOG(tl, 2);
+            } else if (q == 2) {                    // half B complete (its own barrier: a waiter never falls two phases behind)
+                tc_wait(bars, B_ACC2, (uint32_t)(t & 1));
+                tc::tc_fence_after();
+            }
+            const int chunk = q < 2 ? sub * 2 + q : 8 + sub, u = chunk * 8;
+            const uint32_t cr = q < 2 ? COL_GA + u : COL_GB + (u - 64), cz = q < 2 ? COL_GA + 64 + u : COL_GB + 32 + (u - 64);
+            const uint32_t cni = q < 2 ? COL_GA_NI + u : COL_GB_NI + (u - 64), cnh = q < 2 ? COL_GA_NH + u : COL_GB_NH + (u - 64);
             float gr[8], gz[8], gni[8], gnh[8];
-            tc::tmem_ld8x4(tmem + lane_base + COL_GR + u, tmem + lane_base + COL_GR + 96 + u, tmem + lane_base + COL_GNI + u, tmem + lane_base + COL_GNH + u,
-                           gr, gz, gni, gnh);          // four loads in flight, one wait
-            float v[8];
+            tc::tmem_ld8x4(tmem + lane_base + cr, tmem + lane_base + cz, tmem + lane_base + cni, tmem + lane_base + cnh, gr, gz, gni, gnh);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 // r = 1/(1+ea), z = 1/(1+eb) with one reciprocal of the product (pre-activations clamped so it stays finite)
@@ -507,9 +539,15 @@ __device__ void epi_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, const 
                 const float r = inv * db, zg = inv * da;
                 const float n = fast_tanh((gni[i] + bin[u + i]) + r * (gnh[i] + bhn[u + i]));
                 const float hp = hreg[q * 8 + i];
-                v[i] = hreg[q * 8 + i] = (hp - n) * zg + n;
+                hreg[q * 8 + i] = (hp - n) * zg + n;
             }
-            tc::store_split8(a1_hi_p, a1_lo_p, 128, m, 4 + (u >> 3), v);
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            float t8[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t8[i] = hreg[q * 8 + i];
+            tc::store_split8(a1_hi_p, a1_lo_p, 128, m, 4 + (q < 2 ? sub * 2 + q : 8 + sub), t8);
         }
         TLOG(tl, 3);
     }
@@ -540,8 +578,8 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
     const size_t pair0 = (size_t)row0 * K;
     int ovf = 0;                                    // set when a staged fp16 operand would leave the fp16 range
     if (rng_state) seed += *rng_state;
-    const int total_blocks = TC_MLP_BLOCKS * 3 + 8 * Tp + (recon ? TC_MLP_BLOCKS : 0);
-    const int by0 = TC_MLP_BLOCKS + 8 * Tp;
+    const int total_blocks = TC_MLP_BLOCKS * 3 + 16 * Tp + (recon ? TC_MLP_BLOCKS : 0);
+    const int by0 = TC_MLP_BLOCKS + 16 * Tp;
 #ifdef STTODE_TC_TIMELINE
     if (blockIdx.x == 0 && tid == 0) g_tl = status[1] == 2 ? reinterpret_cast<long long*>(status + 2) : nullptr;
 #endif
@@ -659,8 +697,13 @@ constexpr int SMR_PFLO = SM_RING + TC_NST * TC_STAGE;     // past_feature image 
 constexpr int SMR_BARS = SMR_PFLO + 32768;
 
 __device__ __forceinline__ void row_block_src(const DecPackLayout& lay, int Tp, int i, uint32_t& off, uint32_t& bytes) {
-    if (i < 8 * Tp) { off = lay.gru_off[0] + (uint32_t)(i & 7) * TC_GRU_BLK; bytes = TC_GRU_BLK; return; }
-    off = lay.rowp_off + (uint32_t)(i - 8 * Tp) * 16384;
+    if (i < 16 * Tp) {
+        const int j = i & 15;
+        if (j < 8) { off = lay.gru_off[0] + (uint32_t)j * TC_GRU_A; bytes = TC_GRU_A; }
+        else       { off = lay.gru_off[0] + 8u * TC_GRU_A + (uint32_t)(j - 8) * TC_GRU_B; bytes = TC_GRU_B; }
+        return;
+    }
+    off = lay.rowp_off + (uint32_t)(i - 16 * Tp) * 16384;
     bytes = 16384;
 }
 
@@ -677,7 +720,7 @@ k_dec_row_tc(const float* __restrict__ past_feature, const float* __restrict__ t
     const int m = wq * 32 + lane;
     const int row0 = blockIdx.x * BM;
     const int nrow = min(BM, rows - row0);
-    const int total_blocks = 8 * Tp + 88;
+    const int total_blocks = 16 * Tp + 88;
 
     if (tid == 0) {
         for (int i = 0; i < B_COUNT; ++i) tc::mbar_init(bars + i, (i == B_HFULL || i == B_HFULL + 1 || i == B_XFULL || i == B_D3FREE) ? 16 : 1);
@@ -710,7 +753,7 @@ k_dec_row_tc(const float* __restrict__ past_feature, const float* __restrict__ t
         const uint32_t pf_hi = tc::smem_u32(sm + SMR_PFHI), pf_lo = tc::smem_u32(sm + SMR_PFLO);
         const uint32_t st_hi = tc::smem_u32(sm + SM_A1) + 4 * 2048, st_lo = st_hi + 32768;
         const uint32_t idesc = tc::make_idesc_f16(256);
-        int blk = 8 * Tp;
+        int blk = 16 * Tp;
 #pragma unroll 1
         for (int j = 0; j < 8; ++j) {               // output tile j: product p = j/2, columns (j&1)*256 ..
             const int b = j & 1, nks = j < 4 ? 14 : 8;
