@@ -504,43 +504,77 @@ def parity_leg(state, dev):
             "note": "same scenes, same injected latent z; reference = PyTorch-CPU oracle port (pinned to the reference's outputs in tests/golden); tolerance 1e-4"}
 
 
-def latency_extras(model, dev):
-    """configs[0] and configs[3] (single process): one ETH scene per call the way test.py drives the model, and the SDD-shape sweep."""
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12        # FFMA: 148 SMs x 128 lanes x 2 FLOP at the 1965 MHz boost clock = 74.4 TFLOP/s
+
+
+def latency_extras(model, sd, dev, cpu_seconds):
+    """configs[0] and configs[3] (single process): one ETH scene per call the way test.py drives the model (test.py:164-208), and the SDD-shape
+    sweep — end to end with one scene of N agents per call, plus the Gram-tile stress on the MHGSA module alone.  Each entry is a full line
+    (metric / value / unit / roofline / cpu_baseline): at these sizes the bound is the latency of the dependent kernel chain, and the line says so."""
     from sttode_b200 import synth
-    tp = 8
-    extra = {}
+    tp, tf = 8, 12
+    out = {}
 
     def lat(fn, n=200):
         for _ in range(20):
             fn()
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         for _ in range(n):
             fn()
+        e1.record()
         torch.cuda.synchronize()
-        return 1e6 * (time.perf_counter() - t0) / n
+        return 1e3 * e0.elapsed_time(e1) / n                      # microseconds per call, device clock
+
+    def chain_roofline(n_agents, us):
+        fl = reference_flops_per_row(tp, tf) * n_agents
+        ach = fl / (us * 1e-6) / 1e12
+        return {"bound": "latency", "achieved": ach, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach / FP32_PEAK_TFLOPS, "traffic": None,
+                "flops_per_call_reference_oplist": fl, "kernels_per_call": 5,
+                "note": "one scene fills a fraction of one wave (rows / 128 tiles on 148 SMs): the call is the latency of a chain of dependent kernels "
+                        "(scene origin -> encoder [folded front end + ODE block] -> decoder row kernel -> decoder pair kernel, + FP32 redo launches that exit at "
+                        "once), replayed as ONE CUDA graph; peak = FP32 FFMA peak, shown only to document that no pipe is the limiter"}
+
     with torch.no_grad():
-        obs7, _ = synth.eth_scene(3, 7)
-        obs7 = obs7.to(dev)
+        obs7, gt7 = synth.eth_scene(3, 7)
+        obs7d = obs7.to(dev)
         sp7 = torch.tensor([0, 7], dtype=torch.int32, device=dev)
         g7 = model.capture_forecast(rows=7, L=1, agents=1, n_scenes=1)
-        extra["eth_single_scene_N7"] = {"workload": "BASELINE.json configs[0] shape: one ETH scene (N = 7) per call, like test.py:164-208",
-                                        "eager_us_per_call": lat(lambda: model.forecast_scenes(obs7, sp7)),
-                                        "cuda_graph_us_per_call": lat(lambda: g7(obs7, sp7)), "bound": "latency of the dependent kernel chain"}
+        us_graph, us_eager = lat(lambda: g7(obs7d, sp7)), lat(lambda: model.forecast_scenes(obs7d, sp7))
+        scenes7 = [synth.eth_scene(3 + i, 7) for i in range(400)]
+        cpu_port_eth(sd, scenes7[:3], host_threads())
+        done, sec = cpu_port_eth(sd, scenes7, host_threads(), budget_s=min(3.0, cpu_seconds))
+        out["eth_single_scene"] = {
+            "metric": "forecast scenes/sec (K=20 samples)", "value": 1e6 / us_graph, "unit": "scenes/s", "n_gpus": 1, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE.json configs[0] shape: ETH scene of N = 7 agents, ONE scene per call like test.py:164-208, obs 8 / pred 12, K=20",
+                       "api": "ForecastGraph (one CUDA-graph launch per scene, inputs already on the device)"},
+            "us_per_scene_cuda_graph": us_graph, "us_per_scene_eager_c_abi": us_eager, "roofline": chain_roofline(7, us_graph),
+            "cpu_baseline": {"value": done / sec, "unit": "scenes/s", "cores": host_threads(), "kind": "port",
+                             "sample": f"{done} scenes of N = 7, one per call, PyTorch-CPU oracle port, {sec:.1f} s ({1e3 * sec / done:.2f} ms per scene)"}}
         sweep = {}
         for n_ag in (16, 64, 256, 512):
             obs_n = (torch.rand(n_ag, 2, tp, generator=torch.Generator().manual_seed(n_ag)) * 30.0).to(dev)
             sp_n = torch.tensor([0, n_ag], dtype=torch.int32, device=dev)
             gn = model.capture_forecast(rows=n_ag, L=1, agents=1, n_scenes=1)
-            sweep[f"N{n_ag}"] = {"cuda_graph_us_per_scene": lat(lambda: gn(obs_n, sp_n), n=50)}
+            us = lat(lambda: gn(obs_n, sp_n), n=50)
+            sweep[f"N{n_ag}"] = {"us_per_scene_cuda_graph": us, "scenes_per_s": 1e6 / us, "agents_per_s": n_ag * 1e6 / us, "roofline": chain_roofline(n_ag, us)}
         attn = model.past_encoder.ODE_Encoder.odeblock.odefunc.layers[0].self_attn.temporal_attention_before
         for Lg in (128, 256, 512):
             xg = torch.randn(Lg, 64, 64, generator=torch.Generator().manual_seed(Lg)).to(dev)
             us_g = lat(lambda: attn(xg, xg, xg, need_weights=False), n=50)
-            pairs_g = 64 * 8 * Lg * Lg                       # (agent, head, i, j) score entries
-            sweep[f"mhgsa_L{Lg}_bsz64"] = {"us_per_call": us_g, "score_entries_per_s": pairs_g / (us_g * 1e-6)}
-        extra["sdd_sweep"] = dict(sweep, workload="BASELINE.json configs[3]: one scene of N agents per CUDA-graph launch; Gram-tile stress on the MHGSA module alone")
-    return extra
+            entries = 64 * 8 * Lg * Lg                          # (agent, head, i, j) score entries
+            fl = entries * 32 + Lg * 64 * 2 * 64 * 256           # Gram 16 + AV 16 FLOP per entry; in/out projections 2*64*(192+64) per row
+            ach = fl / (us_g * 1e-6) / 1e12
+            sweep[f"mhgsa_L{Lg}_bsz64"] = {"us_per_call": us_g, "score_entries_per_s": entries / (us_g * 1e-6),
+                                           "roofline": {"bound": "fp32+sfu", "achieved": ach, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach / FP32_PEAK_TFLOPS,
+                                                        "traffic": None, "note": "Hyp_mhsa module alone (k_proj -> k_geo_attn -> k_proj): per score entry 32 FFMA-FLOP plus one acos "
+                                                                                 "(polynomial, ~20 FP32 ops) and one exp (MUFU); the K = 8 Gram stays on FFMA by design"}}
+        out["sdd_sweep"] = {"metric": "forecast scenes/sec (K=20 samples)", "unit": "scenes/s", "n_gpus": 1, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+                            "config": {"workload": "BASELINE.json configs[3]: SDD-shape large-scene sweep, one scene of N in {16..512} agents per CUDA-graph launch "
+                                                   "(S stays 1: stresses rows); Gram-tile stress on the MHGSA module alone, L = S in {128, 256, 512}, bsz 64"},
+                            "value": sweep["N512"]["scenes_per_s"], "sweep": sweep}
+    return out
 
 
 # ---------------------------------------------------------------------------------- training leg (configs[4]) on all ranks
@@ -699,8 +733,8 @@ def run_ours(args):
                 line["gpu_eager_baseline"] = gpu_eager_baseline_leg(state, dev, 6.0)
             except Exception as e:                                 # secondary context only
                 line["gpu_eager_baseline"] = {"unavailable": repr(e)[:200]}
-            eth_model = state["model"] if args.config == "eth" else states["eth"]["model"]
-            line["extra"] = latency_extras(eth_model, dev)
+            eth_state = state if args.config == "eth" else states["eth"]
+            others.update(latency_extras(eth_state["model"], eth_state["sd"], dev, args.cpu_seconds))
     else:
         line["cpu_baseline"] = None
         line["cpu_baseline_note"] = "timed at N = 1 only (task contract); see the --impl reference arm for this N"

@@ -8,6 +8,6 @@ cat gpurun_out/summary.txt; tail -n 30 gpurun_out/t_all.log; tail -3 gpurun_out/
 import json
 d=json.load(open('gpurun_out/bench.json'))
 print('value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['value'],'kernel_ms',d['roofline']['kernel_ms'],'frac',d['roofline']['frac'])
-for k,v in d['configs'].items(): print(k, v['value'], v['ms_per_step'])
-print(d['extra']['eth_single_scene_N7'])
+for k,v in d['configs'].items(): print(k, v.get('value'), v.get('ms_per_step'))
+print({k: v for k, v in d["configs"]["eth_single_scene"].items() if k.startswith("us_")})
 PY

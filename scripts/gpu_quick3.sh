@@ -9,7 +9,7 @@ tail -n 6 gpurun_out/t_all.log | cut -c1-300; tail -3 gpurun_out/bench.err | cut
 import json
 d=json.load(open('gpurun_out/bench.json'))
 print('value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['value'],'kernel_ms',d['roofline']['kernel_ms'],'frac',d['roofline']['frac'])
-for k,v in d['configs'].items(): print(k, v['value'], v['ms_per_step'])
+for k,v in d['configs'].items(): print(k, v.get('value'), v.get('ms_per_step'))
 PY
 fi
 cat gpurun_out/summary.txt

@@ -13,7 +13,7 @@ for f in ("gpurun_out/scale_ref_n$N.json", "gpurun_out/scale_n$N.json"):
         d = json.loads(open(f).read().strip().splitlines()[-1])
         print(f, "value", d["value"], "e2e", d["e2e"]["value"], "ms", d["ms_per_step"])
         for k, v in d.get("configs", {}).items():
-            print("   ", k, v["value"], v["ms_per_step"], v.get("e2e", {}).get("value"), v.get("replica_spread_across_ranks"), v.get("exchange_error_word"))
+            print("   ", k, v.get("value"), v.get("ms_per_step"), v.get("e2e", {}).get("value"), v.get("replica_spread_across_ranks"), v.get("exchange_error_word"))
     except Exception as e:
         print(f, "unreadable", e)
 PY

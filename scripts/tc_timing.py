@@ -29,3 +29,4 @@ print("epi mlp ch5 grp1 [before d1full, d1full ok, tmem ld done, staged+signalle
 print("epi mlp ch4 stage_h32 from tmem-ld-done: [relu+range", d(12, 4), " wait hfree", d(4, 5), " split+store", d(5, 6), " fence+arrive", d(6, 7), "]")
 base = v[24]
 print("absolute (from phase start): epi ch4", [v[i] - base for i in range(10, 14)], " epi ch5", [v[i] - base for i in range(15, 19)], " stage ch4", [v[i] - base for i in range(4, 8)])
+print("y0 MLP from phase start (26): chunk loop done", d(26, 8), " D2 complete", d(26, 9), " pieces staged", d(26, 19), " D3 complete", d(26, 23), " read out + barrier", d(26, 30))

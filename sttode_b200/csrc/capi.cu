@@ -825,7 +825,7 @@ int run_decoder(const float* past_feature, const float* traj_norm, const float* 
     return 0;
 }
 
-constexpr int HOST_MAX_CHUNKS = 8;
+constexpr int HOST_MAX_CHUNKS = 16;      // the last slice's copy-out is the only one not hidden under compute: more, smaller slices shorten that tail
 
 // one forecast over `rows` agent rows; co != nullptr overlaps the copy-out of the predictions with the pair kernels
 int forecast_impl(const float* traj, int layout, const int* scene_ptr, const int* row_scene, int n_scenes, int rows, int L, int agents,
@@ -1262,10 +1262,10 @@ int sttode_forecast_host(const float* traj_host, int layout, const int* scene_pt
     const int* rs_d = scene_ptr_host ? (const int*)(d + align_up(traj_b) + sp_b) : nullptr;
     float* pred_d = (float*)(d + in_b);
     void* ws_d = d + in_b + align_up(pred_b);
-    // the pair kernels run in slices of whole tiles; the D2H copy of slice i overlaps the kernels of slice i+1 (one slice per ~12 MB of output,
+    // the pair kernels run in slices of whole tiles; the D2H copy of slice i overlaps the kernels of slice i+1 (one slice per ~6 MB of output, at most 16,
     // each slice a whole number of 148-SM waves is not required: slices are large)
     CopyOut co{out_pinned ? (char*)pred_host : g_arena.pin_out, g_arena.copy_stream, g_arena.done,
-               (int)std::max<size_t>(1, std::min<size_t>(HOST_MAX_CHUNKS, pred_b / (12u << 20)))};
+               (int)std::max<size_t>(1, std::min<size_t>(HOST_MAX_CHUNKS, pred_b / (6u << 20)))};
     if ((rc = forecast_impl(traj_d, layout, sp_d, rs_d, n_scenes, rows, L, agents, nullptr, seed, sample_k, w, pred_d, nullptr, nullptr, nullptr, ws_d, ws_b,
                             st, &co))) {
         cudaStreamSynchronize(st);                  // the H2D copies above read the shared arena: drain them before the lock is released

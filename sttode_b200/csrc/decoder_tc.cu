@@ -431,9 +431,12 @@ __device__ void epi_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int n3
         stage_h16(sm, bars, wh, half, m, v, first_mlp && ch < 2, (uint32_t)(((ch >> 1) + 1) & 1), ovf, tl && ch == 4);
         TLOG(tl, 10 + (ch - 4) * 5 + 3);
     }
+    const bool tl2 = !first_mlp && !accumulate && threadIdx.x == 0;      // timeline of the layer-2 / layer-3 tail (y0 phase, timeline build only)
+    TLOG(tl2, 8);
     tc_wait(bars, B_ACC, n_acc & 1);                // D2 complete
     ++n_acc;
     tc::tc_fence_after();
+    TLOG(tl2, 9);
 #pragma unroll 1
     for (int p = wh; p < 8; p += 2) {
         float v[16];
@@ -442,9 +445,11 @@ __device__ void epi_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int n3
         for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + __ldg(b1 + p * 32 + half * 16 + i), 0.f);
         stage_h16(sm, bars, wh, half, m, v, false, (uint32_t)(((p >> 1) + 1) & 1), ovf);        // fill 12k + 8 + p/2
     }
+    TLOG(tl2, 19);
     tc_wait(bars, B_ACC, n_acc & 1);                // D3 complete
     ++n_acc;
     tc::tc_fence_after();
+    TLOG(tl2, 23);
     for (int c0 = 0; c0 < n3p; c0 += 16) {
         if (((c0 >> 4) & 3) != sub) continue;       // warp-uniform: the four groups take 16-wide column groups in turn
         float v[16];
@@ -460,6 +465,7 @@ __device__ void epi_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int n3
     }
     epi_signal(bars, B_D3FREE);
     epi_barrier();
+    TLOG(tl2, 30);
 }
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
