@@ -651,7 +651,7 @@ def train_leg(ctx, args, steps, warmup):
                        "parallelism": f"dp{world}: {parallel.describe_reduce(reducer, graph)}"},
             "gpu_launches": int(L.launch_count() - l0) if not graph else f"{getattr(graphed, 'graph_replays_per_step', 1)} CUDA-graph replay(s) per step",
             "library_kernels_per_step": getattr(graphed, "library_launches", None) if graph else int(L.launch_count() - l0) // steps,
-            "cuda_graph": graph, "last_loss": loss, "replica_spread_across_ranks": spread, "exchange": args.train_exchange, "exchange_error_word": exch_err,
+            "cuda_graph": graph, "backward_gemm": args.train_gemm, "last_loss": loss, "replica_spread_across_ranks": spread, "exchange": args.train_exchange, "exchange_error_word": exch_err,
             "note": "every layer forward+backward in libsttode_sm100 (ODE blocks, dense layers, decoder incl. GRU through time)"}
     state = {"model": model, "B": B, "N": N, "tp": tp, "tf": tf}
     if fused:
@@ -767,9 +767,13 @@ def main():
     ap.add_argument("--train-exchange", default="fused", choices=["fused", "nccl"],
                     help="DP gradient exchange: fused = sttode_dp_adam_step over NVLink peer memory (all-reduce + Adam in one kernel, whole step one CUDA graph); "
                          "nccl = one NCCL all-reduce between a forward+backward graph and an Adam graph")
+    ap.add_argument("--train-gemm", default="ffma", choices=["ffma", "tc"],
+                    help="backward GEMMs: ffma = FP32 kernels (parity-grade, default); tc = tcgen05 bf16x3 kernels (STTODE_TC_GEMM=1: faster, ~2e-6 per product)")
     ap.add_argument("--train-batch", type=int, default=32, help="scenes per GPU per training step (train.py:24)")
     ap.add_argument("--ffma", action="store_true", help="use the FP32-FFMA decoder tile instead of the tcgen05 one")
     args = ap.parse_args()
+    if args.train_gemm == "tc":
+        os.environ["STTODE_TC_GEMM"] = "1"          # read once by the library at its first GEMM
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

@@ -246,6 +246,15 @@ int sttode_decoder_fwd(const float *past_feature, const float *traj_norm, const 
  *   bwd: dx[rows,K] = dy . W (dx nullable, row stride lddx);  dW[N,K] += dy^T . x;  db[N] += column sums of dy   (dW / db nullable).
  * The caller masks dy with the ReLU derivative beforehand when the forward used one.  Deterministic summation order. */
 int sttode_dense_fwd(const float *x, int ldx, const float *weight, const float *bias, float *y, int rows, int K, int N, int relu, void *stream);
+/* General strided product with the backward kernels' epilogue, exported for tests and for callers that keep their own layers:
+ *   C[m,n] = epi(sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn]),  epi: + bias[n], ReLU, zero where mask[m,n] <= 0, + res[m,n], + C[m,n] (accumulate).
+ * mode 0: FP32 FFMA (k_gemm: what the backward entry points use); 1: tensor cores (k_gemm_tc: tcgen05, bf16x3 split over the whole fp32 exponent
+ * range, ~2e-6 relative error at K = 256 because the tensor cores truncate when they accumulate — 9 % faster training step, but outside the
+ * 1e-4 gradient-parity bound at the end of the backward chain, hence opt-in); -1: as the environment says (STTODE_TC_GEMM=1 turns the tensor
+ * cores on for products of >= 4 M multiply-adds inside the backward entry points too).  workspace (nullable, sttode_dense_bwd_workspace_bytes()): split-K scratch. */
+int sttode_gemm(int M, int N, int K, const float *A, long sam, long sak, const float *B, long sbk, long sbn, float *C, long ldc,
+                const float *bias, const float *res, long ldres, const float *mask, long ldmask, int relu, int accumulate, int mode,
+                void *workspace, size_t workspace_bytes, void *stream);
 /* workspace (nullable): scratch for the split-K form of the weight / bias gradients — with a few thousand rows and a 64-wide layer the
  * reduction runs over the rows, so without it one CTA walks the whole batch (0.2 ms per layer at 7040 rows); sttode_dense_bwd_workspace_bytes(). */
 size_t sttode_dense_bwd_workspace_bytes(void);

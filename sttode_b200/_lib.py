@@ -97,6 +97,7 @@ SIGNATURES = {
     "sttode_decoder_workspace_bytes": (_Z, [_I, _I]),
     "sttode_decoder_fwd": (_I, [_V, _V, _V, _U64, _V, _V, _I, _I, C.POINTER(ModelWeights), _V, _V, _V, _Z, _V]),
     "sttode_dense_fwd": (_I, [_V, _I, _V, _V, _V, _I, _I, _I, _I, _V]),
+    "sttode_gemm": (_I, [_I, _I, _I, _V, C.c_long, C.c_long, _V, C.c_long, C.c_long, _V, C.c_long, _V, _V, C.c_long, _V, C.c_long, _I, _I, _I, _V, _Z, _V]),
     "sttode_dense_bwd_workspace_bytes": (_Z, []),
     "sttode_dense_bwd": (_I, [_V, _I, _V, _V, _V, _I, _V, _V, _I, _I, _I, _V, _Z, _V]),
     "sttode_decoder_bwd_workspace_bytes": (_Z, [_I, _I, _I]),

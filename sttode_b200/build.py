@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsttode_sm100.so")
-SOURCES = ["encoder.cu", "encoder_tc.cu", "backward.cu", "decoder.cu", "decoder_tc.cu", "pmath.cu", "tc_selftest.cu", "comm.cu", "capi.cu"]      # + new files: keep in sync with csrc/
+SOURCES = ["encoder.cu", "encoder_tc.cu", "backward.cu", "gemm_tc.cu", "decoder.cu", "decoder_tc.cu", "pmath.cu", "tc_selftest.cu", "comm.cu", "capi.cu"]      # + new files: keep in sync with csrc/
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "kernels.cuh"), os.path.join(CSRC, "tc.cuh"),
            os.path.join(os.path.dirname(HERE), "include", "sttode.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

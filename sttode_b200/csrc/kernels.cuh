@@ -50,6 +50,12 @@ int ode_tail_tc_threads();
 __global__ void k_gemm(int M, int N, int K, const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C, long ldc,
                        const float* bias, const float* res, long ldres, const float* mask, long ldmask, int relu, int accumulate, int kchunk,
                        long slice_stride);
+// gemm_tc.cu — the same product on the tcgen05 tensor cores (bf16x3 split, fp32-level accuracy, gradient-safe range); 128 x 128 tiles
+__global__ void k_gemm_tc(int M, int N, int K, const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C, long ldc,
+                          const float* bias, const float* res, long ldres, const float* mask, long ldmask, int relu, int accumulate, int kchunk,
+                          long slice_stride);
+size_t gemm_tc_smem_bytes();
+int gemm_tc_threads();
 __global__ void k_colsum_part(const float* X, long ldx, int rows, int N, int rchunk, float* part);
 __global__ void k_splitk_epilogue(const float* part, int slices, int M, int N, float* C, long ldc, const float* bias, const float* res, long ldres,
                                   const float* mask, long ldmask, int relu, int accumulate);
