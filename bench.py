@@ -719,6 +719,8 @@ def run_ours(args):
         timer.start()
         try:
             others["train"], states["train"] = train_leg(ctx, args, max(5, args.steps), 3)
+        except Exception as e:                                   # secondary leg: report, never lose the headline line (an asymmetric failure is caught by the timer)
+            others["train"] = {"error": repr(e)[:300]}
         finally:
             timer.cancel()
     ctx.close()                                                   # the last collective is done: no rank waits on another from here on
