@@ -465,7 +465,7 @@ k_gru_seq_fwd(const float* __restrict__ gi, long ldgi, const float* __restrict__
     float* Wt = smem;                               // [96][288]: Wt[k][n] = W_hh[n][k]
     float* hs = Wt + 96 * 288;                      // [GRU_R][GRU_LDH]
     const int tid = threadIdx.x, u = tid % 96, rg = tid / 96, row0 = blockIdx.x * GRU_R;
-    for (int i = tid; i < 288 * 96; i += GRU_THREADS) { const int n = i / 96, k = i - n * 96; Wt[k * 288 + n] = __ldg(w_hh + i); }
+    for (int i = tid; i < 288 * 96; i += GRU_THREADS) { const int k = i / 288, n = i - k * 288; Wt[i] = __ldg(w_hh + n * 96 + k); }      // conflict-free stores; the strided reads hit L1/L2
     for (int i = tid; i < GRU_R * 96; i += GRU_THREADS) {
         const int rr = i / 96, c = i - rr * 96, p = row0 + rr;
         hs[rr * GRU_LDH + c] = p < P ? h[(size_t)p * 96 + c] : 0.f;
@@ -473,9 +473,14 @@ k_gru_seq_fwd(const float* __restrict__ gi, long ldgi, const float* __restrict__
     const float br = __ldg(b_hh + u), bz = __ldg(b_hh + 96 + u), bn = __ldg(b_hh + 192 + u);
     __syncthreads();
     for (int t = 0; t < T; ++t) {
-        float acc[8][3];
+        float acc[8][3], gin[8][3];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = 0.f;
+        for (int i = 0; i < 8; ++i) {               // the step's input projections: issued now, consumed after the dot products (latency hidden)
+            const int p = row0 + rg * 8 + i;
+            const float* gip = gi + (size_t)(p < P ? p : 0) * ldgi + (size_t)t * 288;
+            gin[i][0] = p < P ? __ldg(gip + u) : 0.f; gin[i][1] = p < P ? __ldg(gip + 96 + u) : 0.f; gin[i][2] = p < P ? __ldg(gip + 192 + u) : 0.f;
+            acc[i][0] = acc[i][1] = acc[i][2] = 0.f;
+        }
 #pragma unroll 2
         for (int k = 0; k < 96; k += 4) {
             float w[3][4];
@@ -498,10 +503,9 @@ k_gru_seq_fwd(const float* __restrict__ gi, long ldgi, const float* __restrict__
         for (int i = 0; i < 8; ++i) {
             const int rr = rg * 8 + i, p = row0 + rr;
             if (p >= P) continue;
-            const float* gip = gi + (size_t)p * ldgi + (size_t)t * 288;
-            const float r = sigmoidf_(gip[u] + acc[i][0] + br), z = sigmoidf_(gip[96 + u] + acc[i][1] + bz);
+            const float r = sigmoidf_(gin[i][0] + acc[i][0] + br), z = sigmoidf_(gin[i][1] + acc[i][1] + bz);
             const float gn = acc[i][2] + bn;
-            const float n = tanhf(gip[192 + u] + r * gn);
+            const float n = tanhf(gin[i][2] + r * gn);
             const float hn = (1.f - z) * n + z * hs[rr * GRU_LDH + u];
             float* rz = rzn + ((size_t)t * P + p) * 288;
             rz[u] = r; rz[96 + u] = z; rz[192 + u] = n;
@@ -528,6 +532,20 @@ k_gru_seq_bwd(const float* __restrict__ dh_T, long lddh, const float* __restrict
         ds[rr * GRU_LDH + c] = p < P ? dh_T[(size_t)p * lddh + c] : 0.f;
     }
     __syncthreads();
+    float sv[8][5];                                 // saved (r, z, n, W_hn h + b, h_prev) of the step being differentiated, fetched one step ahead
+    auto fetch = [&](int t) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int p = row0 + rg * 8 + i;
+            if (p < P) {
+                const float* rz = rzn + ((size_t)t * P + p) * 288;
+                sv[i][0] = __ldg(rz + u); sv[i][1] = __ldg(rz + 96 + u); sv[i][2] = __ldg(rz + 192 + u);
+                sv[i][3] = __ldg(ghn + ((size_t)t * P + p) * 96 + u);
+                sv[i][4] = __ldg(h + ((size_t)t * P + p) * 96 + u);
+            }
+        }
+    };
+    fetch(T - 1);
     for (int t = T - 1; t >= 0; --t) {
         float carry[8];
 #pragma unroll
@@ -536,11 +554,10 @@ k_gru_seq_bwd(const float* __restrict__ dh_T, long lddh, const float* __restrict
             float dr = 0.f, dz = 0.f, dn = 0.f, dnr = 0.f;
             carry[i] = 0.f;
             if (p < P) {
-                const float* rz = rzn + ((size_t)t * P + p) * 288;
-                const float r = rz[u], z = rz[96 + u], n = rz[192 + u];
-                const float d = ds[rr * GRU_LDH + u], gn = ghn[((size_t)t * P + p) * 96 + u];
+                const float r = sv[i][0], z = sv[i][1], n = sv[i][2];
+                const float d = ds[rr * GRU_LDH + u], gn = sv[i][3];
                 dn = d * (1.f - z) * (1.f - n * n);         // through tanh
-                dz = d * (h[((size_t)t * P + p) * 96 + u] - n) * z * (1.f - z);
+                dz = d * (sv[i][4] - n) * z * (1.f - z);
                 dr = dn * gn * r * (1.f - r);
                 dnr = dn * r;
                 carry[i] = d * z;
@@ -553,6 +570,7 @@ k_gru_seq_bwd(const float* __restrict__ dh_T, long lddh, const float* __restrict
         }
         __syncthreads();
         if (t == 0) break;                          // dh_0 is not needed
+        fetch(t - 1);                               // in flight during the matvec below
         float acc[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;

@@ -856,8 +856,9 @@ int run_decoder(const float* past_feature, const float* traj_norm, const float* 
                 g_prof.used.push_back(ev);
             }
         }
-        k_dec_pair<<<t1 - t0, NTHREADS, sm_pair, st>>>(tn_c, z_c, seed, pb, rng, rp_c, rs_c, origin, nr, K, rpt, Tp, Tf, w->dec[0], w->dec[1], pred_c, recon_c,
-                                                       tcores ? flags + row_tiles + t0 : nullptr);
+        k_dec_pair<<<tcores ? std::min(t1 - t0, 2 * sms) : t1 - t0, NTHREADS, sm_pair, st>>>(tn_c, z_c, seed, pb, rng, rp_c, rs_c, origin, nr, K, rpt, Tp, Tf,
+                                                                                          w->dec[0], w->dec[1], pred_c, recon_c,
+                                                                                          tcores ? flags + row_tiles + t0 : nullptr, t1 - t0);
         LAUNCH_CHECK(tcores ? "k_dec_pair(redo)" : "k_dec_pair");
         if (co) {
             CUDA_TRY(cudaEventRecord(co->done[c], st));

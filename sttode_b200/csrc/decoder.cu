@@ -268,9 +268,8 @@ k_dec_pair(const float* __restrict__ traj_norm, const float* __restrict__ z, uns
            const unsigned long long* __restrict__ rng_state,
            const float* __restrict__ rowpre, const int* __restrict__ row_scene, const float* __restrict__ origin, int rows,
            int K, int rpt, int Tp, int Tf, sttode_decompose_weights w0, sttode_decompose_weights w1,
-           float* __restrict__ pred, float* __restrict__ recon, const int* __restrict__ only_flagged) {
+           float* __restrict__ pred, float* __restrict__ recon, const int* __restrict__ only_flagged, int ntiles) {
     extern __shared__ __align__(16) float smem[];
-    if (only_flagged && !only_flagged[blockIdx.x]) return;
     const int Tm = Tp > Tf ? Tp : Tf;
     const int ldxy = 2 * Tm + 1;
     float* zA = smem;                               // [BM][LDZ]: z | block-1 GRU state
@@ -286,7 +285,11 @@ k_dec_pair(const float* __restrict__ traj_norm, const float* __restrict__ z, uns
 
     const int tid = threadIdx.x;
     if (rng_state) seed += *rng_state;
-    const int row0 = blockIdx.x * rpt;
+    // One tile per CTA when this is the decoder itself (gridDim.x == ntiles).  As the FP32 redo pass behind the tensor-core kernel it is launched
+    // with a SMALL grid that walks the tile flags: launching one CTA per tile just to see a clear flag cost ~25 us per 8 960-tile forecast.
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if (only_flagged && !only_flagged[tile]) continue;
+    const int row0 = tile * rpt;
     const int nrow = min(rpt, rows - row0);
     const int np = nrow * K;                        // valid pairs in this tile
     if (tid < BM) prow_s[tid] = tid < np ? row0 + tid / K : -1;
@@ -337,6 +340,8 @@ k_dec_pair(const float* __restrict__ traj_norm, const float* __restrict__ z, uns
             const int m = idx / (2 * Tp), e = idx - m * 2 * Tp;
             recon[(pair0 + m) * 2 * Tp + e] += xy_s[m * ldxy + e];
         }
+    }
+    __syncthreads();                                // the next tile of this CTA reuses every shared buffer
     }
 }
 

@@ -93,7 +93,7 @@ __global__ void k_dec_row(const float* past_feature, const float* traj_norm, int
 __global__ void k_dec_pair(const float* traj_norm, const float* z, unsigned long long seed, unsigned long long pair_base, const unsigned long long* rng_state,
                            const float* rowpre,
                            const int* row_scene, const float* origin, int rows, int K, int rpt, int Tp, int Tf,
-                           sttode_decompose_weights w0, sttode_decompose_weights w1, float* pred, float* recon, const int* only_flagged);
+                           sttode_decompose_weights w0, sttode_decompose_weights w1, float* pred, float* recon, const int* only_flagged, int ntiles);
 size_t dec_row_smem_bytes(int Tp);
 size_t dec_pair_smem_bytes(int Tp, int Tf);
 

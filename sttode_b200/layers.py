@@ -218,10 +218,14 @@ class TransformerEncoderLayer(nn.Module):
         self.dropout2 = nn.Dropout(dropout)
         # eval-mode forwards run the in-projection / out-proj / gate / FFN on the tcgen05 tensor cores (3xFP16 split); False -> FP32 FFMA
         self.use_tensor_cores = True
+        self.tensor_cores_in_training = True        # train-mode forward of the ODE block on the tensor cores as well (its backward stays FP32)
         self._packed = _PackedOde()
 
     def _packed_or_none(self):
-        return self._packed.get(self) if (self.use_tensor_cores and not self.training and self.linear1.weight.is_cuda) else None
+        """The tensor-core operand images when this forward should run on the tcgen05 kernels: always in eval mode; in train mode too when
+        `tensor_cores_in_training` is set (the weights change every step, so every training forward re-splits them: one 4 us launch)."""
+        on = self.use_tensor_cores and self.linear1.weight.is_cuda and (not self.training or self.tensor_cores_in_training)
+        return self._packed.get(self) if on else None
 
     def forward(self, src, src_mask=None, src_key_padding_mask=None):
         _check_eval_dropout(self.dropout.p, self.training, "TransformerEncoderLayer")

@@ -294,9 +294,9 @@ class GraphedTrainStep:
         self.library_launches = _lib.launch_count() - l0       # libsttode_sm100 kernels recorded into the graph(s) = per replayed step
 
     def _forward_backward(self):
-        # the decoder's fp16 hi/lo weight images must be rebuilt from the CURRENT weights inside every replay: drop the cache key so the
-        # first decoder pass of the step issues (and the capture records) the pack; the second pass of the same step reuses it
-        self.model.decoder._packed.invalidate()
+        # the tensor-core weight images (decoder, ODE blocks) must be rebuilt from the CURRENT weights inside every replay: drop the cache keys so
+        # the first use in the step issues (and the capture records) each pack; later uses in the same step reuse it
+        self.model.invalidate_packed()
         self.model.set_data_nba(self.static)
         total, parts = self.model.objective()
         self.reducer.zero()

@@ -141,3 +141,25 @@ def test_header_is_plain_c(tmp_path):
                     f"-Wl,-rpath,{libdir}"], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     assert int(out[0]) == len(names) and int(out[1]) == 100
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` under a multi-rank launch: rank 0 alone runs and prints ONE JSON line carrying the contract's keys; the other
+    ranks exit 0 without output (the driver launches the arm with torchrun for N > 1)."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+    env["RANK"] = env["LOCAL_RANK"] = "0"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--ref-scenes", "4"],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "scenes/s" and d["n_gpus"] == 2 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["value"] > 0 and "workload" in d["config"]
