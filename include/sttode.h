@@ -9,8 +9,9 @@
  *   - plain C: pointers + sizes only.  All `const float*` / `float*` are DEVICE pointers to contiguous fp32
  *     unless the name ends in `_host`.  `stream` is a cudaStream_t passed as void* (NULL = default stream).
  *   - ownership: the caller owns every buffer including the workspace; the library never allocates or frees
- *     device memory on these calls and keeps no pointer after return (exception: *_host entry points own a
- *     cached pinned/device staging arena, released by sttode_release_host_arena()).
+ *     device memory on these calls and keeps no pointer after return (exceptions: *_host entry points own a
+ *     cached pinned/device staging arena, released by sttode_release_host_arena(); sttode_peer_alloc returns a
+ *     cudaMalloc'ed arena because only such memory can be exported through CUDA IPC, freed by sttode_peer_free()).
  *   - errors: return 0 on success, negative STTODE_E* otherwise; text via sttode_last_error() (thread local).
  *     Unsupported shapes/options are errors, never fallbacks.  There is no CPU path.
  *   - work is only enqueued on `stream`; no implicit synchronisation; safe under CUDA-graph capture
