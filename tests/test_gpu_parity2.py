@@ -426,3 +426,54 @@ def test_pmath_remaining_helpers(dev):
     den = Ad.norm(dim=1, keepdim=True) * (1 - (ma * ma).sum(2))
     ref = ((lam * Ad.norm(dim=1)).unsqueeze(1) * torch.asinh(num / den)).permute(1, 0)
     assert float((got - ref).abs().max() / ref.abs().max()) < 1e-4
+
+
+def test_round2_entry_points_error_paths(dev):
+    """Bad arguments to the round-2 entry points are error codes with a message (never a launch, never a fallback); the malformed-CSR case of
+    sttode_forecast_host (an interior offset beyond `rows` used to write past the pinned arena) is rejected before anything is written."""
+    import sttode_b200._lib as L
+    from sttode_b200.layers import _ode_struct
+    from sttode_b200.net import _encoder_struct
+    m, _ = build_model("eth", 8, 12, 1, dev)
+    lib = L.lib()
+    enc = _encoder_struct(m.past_encoder, tensor_cores=False)
+    buf = torch.empty(1 << 16, device=dev)
+    assert lib.sttode_encoder_fold(C.byref(enc), 1, L.dptr(buf), buf.numel() * 4, L.stream_ptr()) == -1 and b"T must" in lib.sttode_last_error()
+    assert lib.sttode_encoder_fold(C.byref(enc), 8, L.dptr(buf), 16, L.stream_ptr()) == -3
+    assert lib.sttode_encoder_fold(C.byref(enc), 8, None, 0, L.stream_ptr()) == -1
+    ode = _ode_struct(m.past_encoder.ODE_Encoder.odeblock.odefunc.layers[0], tensor_cores=False)
+    assert lib.sttode_ode_pack(C.byref(ode), L.dptr(buf), 1024, L.stream_ptr()) == -3
+    assert lib.sttode_latent_draw(1, 0, None, 0, L.dptr(buf), L.stream_ptr()) == -1
+    assert lib.sttode_latent_draw(1, 0, None, 16, None, L.stream_ptr()) == -1
+    a = torch.randn(8, 8, device=dev)
+    assert lib.sttode_gemm(8, 8, 8, L.dptr(a), 8, 1, L.dptr(a), 1, 8, L.dptr(a), 8, None, None, 0, None, 0, 0, 0, 7, None, 0, L.stream_ptr()) == -1
+    assert lib.sttode_gemm(0, 8, 8, L.dptr(a), 8, 1, L.dptr(a), 1, 8, L.dptr(a), 8, None, None, 0, None, 0, 0, 0, 0, None, 0, L.stream_ptr()) == -1
+    assert lib.sttode_dp_adam_step(L.dptr(a), L.dptr(a), 99, 0, L.dptr(a), L.dptr(a), L.dptr(a), None, 64, L.dptr(a), 0.9, 0.999, 1e-8, L.stream_ptr()) == -1
+    assert lib.sttode_peer_alloc(7, C.byref(C.c_void_p()), (C.c_ubyte * 64)()) == -1
+    # malformed CSR: interior offset above rows
+    obs = torch.randn(10, 2, 8)
+    sp = torch.tensor([0, 1000, 10], dtype=torch.int32)
+    pred = torch.empty(10, 20, 12, 2)
+    mw = m._weights()
+    rc = lib.sttode_forecast_host(obs.data_ptr(), 1, sp.data_ptr(), 2, 10, 1, 1, 1, 20, C.byref(mw), pred.data_ptr(), L.stream_ptr())
+    assert rc == -1 and b"scene_ptr" in lib.sttode_last_error()
+    sp_ok = torch.tensor([0, 4, 10], dtype=torch.int32)
+    L.check(lib.sttode_forecast_host(obs.data_ptr(), 1, sp_ok.data_ptr(), 2, 10, 1, 1, 1, 20, C.byref(mw), pred.data_ptr(), L.stream_ptr()))
+    assert torch.isfinite(pred).all()
+
+
+def test_fold_falls_back_beyond_the_shared_memory_budget(dev):
+    """Sequence lengths whose folded table does not fit next to the weight ring (T > 30) use the layer-by-layer prologue with the tensor-core ODE
+    kernel behind it: same result as the all-FP32 path within tolerance."""
+    m, sd = build_model("nba", 36, 4, 6, dev)
+    data = synth.nba_batch(1, 6, 11, 36, 4)
+    m.z_override = synth.latent(66, seed=4)
+    a = m.inference(data).clone()
+    pf_tc = m.past_feature.clone()
+    assert m.past_encoder._packed.packs == 0                       # no fold for T = 36
+    m.set_tensor_cores(False)
+    b = m.inference(data)
+    cur = data["past_traj"].view(66, 36, 2)[:, -1].to(dev)[None, :, None, :]
+    assert rel_rows((a - cur).permute(1, 0, 2, 3), (b - cur).permute(1, 0, 2, 3)) < TOL
+    assert rel_rows(pf_tc, m.past_feature, scale_floor=1e-2) < TOL
+    m.z_override = None
