@@ -286,10 +286,10 @@ constexpr size_t SPLITK_FLOATS = (size_t)SPLITK_MAX * 512 * 256;
 int g_gemm_mode = -1;          // -1: per the environment; 0: FP32 FFMA only; 1: tensor cores whenever the shape allows (sttode_gemm, tests)
 bool tc_gemm_wanted(long M, long N, long K) {
     static const bool env_on = [] { const char* e = getenv("STTODE_TC_GEMM"); return e && e[0] == '1'; }();
-    if (g_gemm_mode == 0 || (g_gemm_mode < 0 && !env_on)) return false;
+    if (g_gemm_mode == 0 || (g_gemm_mode < 0 && !env_on)) return false;            // mode 2 (scoped, re-materialisation): size rule below
     if (K < 16 || N < 8) return false;
     if (g_gemm_mode == 1) return true;
-    return M * N * K >= (4l << 20) && K >= 32;      // below ~4 M MACs the FFMA kernel's smaller tiles fill the GPU better
+    return M * N * K >= (64l << 20) && K >= 32;     // the big decoder products only: below that the FFMA kernel's smaller tiles fill the GPU better
 }
 
 int gemm(cudaStream_t st, int M, int N, int K, const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C, long ldc,
@@ -702,13 +702,20 @@ int run_decoder_bwd(const float* pf, const float* z, const float* x_true, const 
     float* dxh0 = ws.take<float>((size_t)P * 2 * Tp);
     float* splitk = ws.take<float>(SPLITK_FLOATS);
     if (!ws.ok() || !dxh0 || !splitk) return fail(STTODE_EWORKSPACE, "workspace too small for the decoder backward (%zu B given)", ws.size);
-    // ---- forward re-materialisation (model/STTODE.py:336-339)
+    // ---- forward re-materialisation (model/STTODE.py:336-339).  The forward itself ran on the tensor cores (3xFP16, ~5e-7); re-creating its
+    // activations with the bf16x3 tensor-core GEMM (~2e-6) is within that noise, unlike running the GRADIENT products there (k_gemm_tc header),
+    // so the big re-materialisation products (7 040 rows at K = 20) may use it: STTODE_TC_RECOMPUTE=0 turns that off.
+    static const bool tc_recompute = [] { const char* e = getenv("STTODE_TC_RECOMPUTE"); return !(e && e[0] == '0'); }();
+    struct ModeGuard { int saved; ModeGuard(bool on) : saved(g_gemm_mode) { if (on && g_gemm_mode < 0) g_gemm_mode = 2; } ~ModeGuard() { g_gemm_mode = saved; } };
+    {
+    ModeGuard guard(tc_recompute);
     if ((rc = dec_block_fwd(st, P, Tp, w->dec[0], pf, z, x_true, nullptr, gh, b0))) return rc;
     if ((rc = mlp3_fwd(st, P, w->dec[0].dec_x, 2 * Tp, b0.feat, b0.ax1, b0.ax2, b0.xh, splitk))) return rc;
     if ((rc = mlp3_fwd(st, P, w->dec[0].dec_y, 2 * Tf, b0.feat, b0.ay1, b0.ay2, nullptr, splitk))) return rc;
     if ((rc = dec_block_fwd(st, P, Tp, w->dec[1], pf, z, x_true, b0.xh, gh, b1))) return rc;
     if ((rc = mlp3_fwd(st, P, w->dec[1].dec_y, 2 * Tf, b1.feat, b1.ay1, b1.ay2, nullptr, splitk))) return rc;
     if (d_recon && (rc = mlp3_fwd(st, P, w->dec[1].dec_x, 2 * Tp, b1.feat, b1.ax1, b1.ax2, nullptr, splitk))) return rc;
+    }
     // ---- block 1: prediction += y_hat1, reconstruction += x_hat1 (train mode)
     if ((rc = mlp3_bwd(st, P, w->dec[1].dec_y, g[1].dec_y, 2 * Tf, d_pred, b1.feat, b1.ay1, b1.ay2, da1, da2, dfeat1, 0, splitk))) return rc;
     if (d_recon && (rc = mlp3_bwd(st, P, w->dec[1].dec_x, g[1].dec_x, 2 * Tp, d_recon, b1.feat, b1.ax1, b1.ax2, da1, da2, dfeat1, 1, splitk))) return rc;
