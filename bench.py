@@ -45,8 +45,8 @@ CONFIGS = {
             "workload": "NBA-shape inference (BASELINE.json configs[2]): 11 agents, obs 10 / pred 20, K=20, reference batches of 128 scenes "
                         "(MHGSA L = S = 128 across the scenes of a batch), sharded by whole batches"},
 }
-# dram read+write of k_dec_pair_tc per (agent, sample) pair from `ncu --set full` (profiles/*_ncu_full_k_dec_pair_tc.md); None = not captured
-DRAM_BYTES_PER_PAIR = {"eth": 97.0e6 / 268800, "nba": None}
+# dram read+write of k_dec_pair_tc per (agent, sample) pair from `ncu --set full` (one launch of 268 800 / 225 280 pairs)
+DRAM_BYTES_PER_PAIR = {"eth": (85.92e6 + 10.88e6) / 268800, "nba": (72.69e6 + 12.36e6) / 225280}      # profiles/r02_ncu_full_{eth,nba}.md
 
 
 # ---------------------------------------------------------------------------------- FLOP accounting
