@@ -41,7 +41,7 @@ def grad_errors(got, ref, ref_max=None):
 def assert_grad_close(got, ref, tol, what, ref_max=None):
     """Gradient tolerance.  The loss is piecewise smooth: every ReLU (4.7 M of them per NBA step at B = 8), the best-of-20 min,
     the KL clamp and the acos clamp is a discrete decision, and a pre-activation within fp32 rounding of its threshold is decided
-    differently by two correct fp32 evaluations (the CPU fp32 oracle shows the same against float64, scripts/dbg_train_grads.py).
+    differently by two correct fp32 evaluations (the CPU fp32 oracle shows the same against float64).
     One such flip moves one row of one weight gradient by a few 1e-4 of the tensor's max.  So: L2-relative error <= tol (a flip
     barely registers), max-norm error <= 10 * tol."""
     l2, mx = grad_errors(got, ref, ref_max)
