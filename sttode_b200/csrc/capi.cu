@@ -793,7 +793,9 @@ int run_decoder(const float* past_feature, const float* traj_norm, const float* 
     int rc;
     if (K < 1 || K > BM) return fail(STTODE_EINVAL, "sample_k must be in [1, %d]", BM);
     const int Tp = w->past_length, Tf = w->future_length;
-    const int rpt = BM / K, row_tiles = ceil_div(rows, BM), pair_tiles = ceil_div(rows, rpt);
+    // pair tiles are 128 consecutive (agent, sample) pairs of the batch, NOT whole agents: at K = 20 that is 6.25 % fewer tiles than 6 agents per tile
+    const size_t n_pairs = (size_t)rows * K;
+    const int row_tiles = ceil_div(rows, BM), pair_tiles = (int)((n_pairs + BM - 1) / BM);
     float* rowpre = ws.take<float>((size_t)rows * ROWPRE_LD);
     if (!rowpre) return fail(STTODE_EWORKSPACE, "workspace too small for decoder row precompute");
     const size_t sm_row = dec_row_smem_bytes(Tp), sm_pair = dec_pair_smem_bytes(Tp, Tf);
@@ -825,7 +827,6 @@ int run_decoder(const float* past_feature, const float* traj_norm, const float* 
     }
     // ---- pair tiles, in nch slices of whole tiles (one slice unless the caller overlaps the copy-out)
     const int nch = co ? std::max(1, std::min(co->nch, pair_tiles)) : 1;
-    const size_t row_out = (size_t)K * Tf * 2;      // floats of pred per agent row
     std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
     if (tcores && g_prof.on) {
         std::lock_guard<std::mutex> lock(g_prof.mu);
@@ -844,17 +845,10 @@ int run_decoder(const float* past_feature, const float* traj_norm, const float* 
     for (int c = 0; c < nch; ++c) {
         const int t0 = std::min(pair_tiles, c * slice_tiles), t1 = std::min(pair_tiles, (c + 1) * slice_tiles);
         if (t1 <= t0) continue;
-        const int r0 = t0 * rpt, nr = std::min(rows, t1 * rpt) - r0;
-        const float* tn_c = traj_norm + (size_t)r0 * Tp * 2;
-        const float* z_c = z ? z + (size_t)r0 * K * 32 : nullptr;
-        const float* rp_c = rowpre + (size_t)r0 * ROWPRE_LD;
-        const int* rs_c = rs ? rs + r0 : nullptr;
-        float* pred_c = pred + (size_t)r0 * row_out;
-        float* recon_c = recon ? recon + (size_t)r0 * K * Tp * 2 : nullptr;
-        const unsigned long long pb = (unsigned long long)r0 * K;       // the latent draw is keyed by the pair's index in the whole batch
+        // the kernels index the whole batch (pair = tile * 128 + m, agent row = pair / K): every slice gets the base pointers and its first tile
         if (tcores) {
-            k_dec_pair_tc<<<t1 - t0, dec_pair_tc_threads(), dec_pair_tc_smem_bytes(Tp, Tf), st>>>(tn_c, z_c, seed, pb, rng, rp_c, rs_c, origin, nr, K, rpt, Tp, Tf,
-                                                                                               w->dec[0], w->dec[1], pk, lay, pred_c, recon_c,
+            k_dec_pair_tc<<<t1 - t0, dec_pair_tc_threads(), dec_pair_tc_smem_bytes(Tp, Tf), st>>>(traj_norm, z, seed, 0ull, rng, rowpre, rs, origin, rows, K, t0, Tp, Tf,
+                                                                                               w->dec[0], w->dec[1], pk, lay, pred, recon,
                                                                                                (int*)(pk + lay.total), flags + row_tiles + t0);
             LAUNCH_CHECK("k_dec_pair_tc");
             if (c == nch - 1 && ev.first) {
@@ -863,14 +857,15 @@ int run_decoder(const float* past_feature, const float* traj_norm, const float* 
                 g_prof.used.push_back(ev);
             }
         }
-        k_dec_pair<<<tcores ? std::min(t1 - t0, 2 * sms) : t1 - t0, NTHREADS, sm_pair, st>>>(tn_c, z_c, seed, pb, rng, rp_c, rs_c, origin, nr, K, rpt, Tp, Tf,
-                                                                                          w->dec[0], w->dec[1], pred_c, recon_c,
+        k_dec_pair<<<tcores ? std::min(t1 - t0, 2 * sms) : t1 - t0, NTHREADS, sm_pair, st>>>(traj_norm, z, seed, 0ull, rng, rowpre, rs, origin, rows, K, t0, Tp, Tf,
+                                                                                          w->dec[0], w->dec[1], pred, recon,
                                                                                           tcores ? flags + row_tiles + t0 : nullptr, t1 - t0);
         LAUNCH_CHECK(tcores ? "k_dec_pair(redo)" : "k_dec_pair");
         if (co) {
+            const size_t p0 = (size_t)t0 * BM, p1 = std::min(n_pairs, (size_t)t1 * BM), pair_out = (size_t)Tf * 2;      // this slice's pairs: one contiguous span of pred
             CUDA_TRY(cudaEventRecord(co->done[c], st));
             CUDA_TRY(cudaStreamWaitEvent(co->stream, co->done[c], 0));
-            CUDA_TRY(cudaMemcpyAsync(co->host + (size_t)r0 * row_out * 4, pred_c, (size_t)nr * row_out * 4, cudaMemcpyDeviceToHost, co->stream));
+            CUDA_TRY(cudaMemcpyAsync(co->host + p0 * pair_out * 4, pred + p0 * pair_out, (p1 - p0) * pair_out * 4, cudaMemcpyDeviceToHost, co->stream));
         }
     }
     if (rng) {

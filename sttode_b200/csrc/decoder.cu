@@ -289,16 +289,17 @@ k_dec_pair(const float* __restrict__ traj_norm, const float* __restrict__ z, uns
     // with a SMALL grid that walks the tile flags: launching one CTA per tile just to see a clear flag cost ~25 us per 8 960-tile forecast.
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     if (only_flagged && !only_flagged[tile]) continue;
-    const int row0 = tile * rpt;
-    const int nrow = min(rpt, rows - row0);
-    const int np = nrow * K;                        // valid pairs in this tile
-    if (tid < BM) prow_s[tid] = tid < np ? row0 + tid / K : -1;
+    // a tile is 128 consecutive (agent, sample) pairs of the whole batch (same cut as k_dec_pair_tc); `rpt` = index of this launch's first tile
+    const size_t pair0 = ((size_t)rpt + tile) * BM;
+    const size_t P = (size_t)rows * K;
+    const int np = (int)min((size_t)BM, P - pair0);          // valid pairs in this tile
+    if (tid < BM) prow_s[tid] = tid < np ? (int)((pair0 + tid) / K) : -1;
     // latent z: one float4 per (pair, q)
     for (int idx = tid; idx < BM * 8; idx += NTHREADS) {
         const int m = idx >> 3, q = idx & 7;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (m < np) {
-            const size_t pair = (size_t)row0 * K + m;
+            const size_t pair = pair0 + m;
             v = z ? *reinterpret_cast<const float4*>(z + pair * 32 + q * 4) : latent_normal4(seed, pair_base + pair, q);      // pair_base: index of this launch's first pair in the caller's batch
         }
         *reinterpret_cast<float4*>(zA + m * LDZ + q * 4) = v;
@@ -307,7 +308,6 @@ k_dec_pair(const float* __restrict__ traj_norm, const float* __restrict__ z, uns
 
     // ---- block 0 decoder_x -> x_hat0
     mlp_phase<32>(zA, LDZ, w0.dec_x, rowpre + 0, prow_s, 2 * Tp, xy_s, ldxy, false, h1c, w2c, w1c);
-    const size_t pair0 = (size_t)row0 * K;
     if (recon)
         for (int idx = tid; idx < np * 2 * Tp; idx += NTHREADS) {
             const int m = idx / (2 * Tp), e = idx - m * 2 * Tp;

@@ -577,11 +577,12 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wq = warp & 3, sub = (warp >> 2) & 3;
     const int m = wq * 32 + lane;
-    const int row0 = blockIdx.x * rpt;
-    const int nrow = min(rpt, rows - row0);
-    const int np = nrow * K;
-    const int prow = m < np ? row0 + m / K : -1;
-    const size_t pair0 = (size_t)row0 * K;
+    // A tile is 128 CONSECUTIVE (agent, sample) pairs of the whole batch (pair p = agent row p / K, sample p % K): tiles cut on agent
+    // boundaries would leave 128 - 6*20 = 8 of 128 MMA rows idle at K = 20.  `rpt` carries the index of this launch's first tile.
+    const size_t pair0 = ((size_t)rpt + blockIdx.x) * BM;
+    const size_t P = (size_t)rows * K;
+    const int np = (int)min((size_t)BM, P - pair0);
+    const int prow = m < np ? (int)((pair0 + m) / K) : -1;
     int ovf = 0;                                    // set when a staged fp16 operand would leave the fp16 range
     if (rng_state) seed += *rng_state;
     const int total_blocks = TC_MLP_BLOCKS * 3 + 16 * Tp + (recon ? TC_MLP_BLOCKS : 0);
@@ -658,7 +659,7 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
             }
         for (int idx = tid; idx < BM * 2 * Tp; idx += EPI_THREADS) {      // conv input of block 1: x_true - x_hat0
             const int mm = idx / (2 * Tp), e = idx - mm * 2 * Tp;
-            const int r = mm < np ? row0 + mm / K : -1;
+            const int r = mm < np ? (int)((pair0 + mm) / K) : -1;
             xy_s[mm * ldxy + e] = r >= 0 ? traj_norm[(size_t)r * 2 * Tp + e] - xy_s[mm * ldxy + e] : 0.f;
         }
         epi_barrier();
@@ -671,7 +672,7 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
         TLOG(tid == 0, 28);
         for (int idx = tid; idx < np * 2 * Tf; idx += EPI_THREADS) {
             const int mm = idx / (2 * Tf), e = idx - mm * 2 * Tf, cc = e & 1;
-            const int r = row0 + mm / K;
+            const int r = (int)((pair0 + mm) / K);
             float v = xy_s[mm * ldxy + e] + traj_norm[((size_t)r * Tp + Tp - 1) * 2 + cc];
             if (origin) v += origin[row_scene[r] * 2 + cc];
             pred[(pair0 + mm) * 2 * Tf + e] = v;
