@@ -440,9 +440,15 @@ __device__ void epi_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int n3
 #pragma unroll 1
     for (int p = wh; p < 8; p += 2) {
         float v[16];
+        float4 bq[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) bq[q] = __ldg(reinterpret_cast<const float4*>(b1 + p * 32 + half * 16) + q);      // four 16-byte loads, in flight under the TMEM load
         tc::tmem_ld16(tmem + lane_base + COL_D2 + p * 32 + half * 16, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + __ldg(b1 + p * 32 + half * 16 + i), 0.f);
+        for (int q = 0; q < 4; ++q) {
+            v[4 * q] = fmaxf(v[4 * q] + bq[q].x, 0.f); v[4 * q + 1] = fmaxf(v[4 * q + 1] + bq[q].y, 0.f);
+            v[4 * q + 2] = fmaxf(v[4 * q + 2] + bq[q].z, 0.f); v[4 * q + 3] = fmaxf(v[4 * q + 3] + bq[q].w, 0.f);
+        }
         stage_h16(sm, bars, wh, half, m, v, false, (uint32_t)(((p >> 1) + 1) & 1), ovf);        // fill 12k + 8 + p/2
     }
     TLOG(tl2, 19);
