@@ -26,7 +26,7 @@ print("gru step t=2, epilogue thread 0: conv image", d(0, 1), " wait for gates (
 print("gru step t=2, issuer lane 0: wait xfull", d(20, 21), " issue 8 slabs", d(21, 22))
 print("epi mlp ch4 grp0 [before d1full, d1full ok, tmem ld done, staged+signalled]:", [d(10, 10 + i) for i in range(1, 4)])
 print("epi mlp ch5 grp1 [before d1full, d1full ok, tmem ld done, staged+signalled]:", [d(15, 15 + i) for i in range(1, 4)])
-print("epi mlp ch4 stage_h32 from tmem-ld-done: [relu+range", d(12, 4), " wait hfree", d(4, 5), " split+store", d(5, 6), " fence+arrive", d(6, 7), "]")
+print("GRU phase from the end of x0 (25): conv input built", d(25, 4), " h zeroed / loop start", d(25, 5), " 8 steps done", d(25, 6), " final signal", d(25, 7), " y0 starts", d(25, 26))
 base = v[24]
-print("absolute (from phase start): epi ch4", [v[i] - base for i in range(10, 14)], " epi ch5", [v[i] - base for i in range(15, 19)], " stage ch4", [v[i] - base for i in range(4, 8)])
+print("absolute (from phase start): epi ch4", [v[i] - base for i in range(10, 14)], " epi ch5", [v[i] - base for i in range(15, 19)])
 print("y0 MLP from phase start (26): chunk loop done", d(26, 8), " D2 complete", d(26, 9), " pieces staged", d(26, 19), " D3 complete", d(26, 23), " read out + barrier", d(26, 30))

@@ -375,9 +375,7 @@ __device__ __forceinline__ void track_range(const float (&v)[N], int& ovf) {
 __device__ __forceinline__ void stage_h16(unsigned char* sm, uint64_t* bars, int b, int half, int m, const float (&v)[16], bool first,
                                           uint32_t prev_parity, int& ovf, bool tl = false) {
     track_range(v, ovf);
-    TLOG(tl, 4);
     if (!first) tc_wait(bars, B_HFREE + b, prev_parity);
-    TLOG(tl, 5);
     unsigned char* hb = sm + SM_H + b * 16384;
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -386,9 +384,7 @@ __device__ __forceinline__ void stage_h16(unsigned char* sm, uint64_t* bars, int
         for (int i = 0; i < 8; ++i) t8[i] = v[q * 8 + i];
         tc::store_split8(hb, hb + 8192, 128, m, half * 2 + q, t8);
     }
-    TLOG(tl, 6);
     epi_signal(bars, B_HFULL + b);
-    TLOG(tl, 7);
 }
 
 __device__ __forceinline__ void load_rowbias16(float (&rb)[16], const float* __restrict__ rowpre, int prow, int col) {
@@ -495,6 +491,7 @@ __device__ void epi_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, const 
     float hreg[24];                                 // this thread's 24 hidden units of row m (chunks 2*sub, 2*sub+1, 8+sub), fp32 across the recurrence
 #pragma unroll
     for (int i = 0; i < 24; ++i) hreg[i] = 0.f;
+    TLOG(tid == 0 && ldxy != 2 * T, 5);            // pair kernel only (the row kernel passes ldxy = 2 T)
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
         // conv channels sub*8 .. +8 of row m at time t -> k chunk `sub` of the conv image (H[0])
@@ -545,8 +542,8 @@ __device__ void epi_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, const 
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 // r = 1/(1+ea), z = 1/(1+eb) with one reciprocal of the product (pre-activations clamped so it stays finite)
-                const float da = 1.f + __expf(-fminf(fmaxf(gr[i] + brz[u + i], -30.f), 30.f));
-                const float db = 1.f + __expf(-fminf(fmaxf(gz[i] + brz[96 + u + i], -30.f), 30.f));
+                const float da = 1.f + __expf(-fmaxf(gr[i] + brz[u + i], -30.f));          // lower clamp keeps da * db finite; large positive x gives e^-x -> 0
+                const float db = 1.f + __expf(-fmaxf(gz[i] + brz[96 + u + i], -30.f));
                 const float inv = __fdividef(1.f, da * db);
                 const float r = inv * db, zg = inv * da;
                 const float n = fast_tanh((gni[i] + bin[u + i]) + r * (gnh[i] + bhn[u + i]));
@@ -563,6 +560,7 @@ __device__ void epi_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, const 
         }
         TLOG(tl, 3);
     }
+    TLOG(tid == 0 && ldxy != 2 * T, 6);
     epi_signal(bars, B_XFULL);                      // final state staged, gate accumulators read out
 }
 
@@ -643,6 +641,7 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
         if (sub == 0) {
             float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (prow >= 0) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(traj_norm + (size_t)prow * 2 * Tp));       // the row the conv-input build reads after the x0 MLP
                 const float2 tn = *reinterpret_cast<const float2*>(traj_norm + ((size_t)prow * Tp + Tp - 1) * 2);
                 c4.x = tn.x; c4.y = tn.y;
                 if (origin) { const int sc = row_scene[prow]; c4.z = origin[sc * 2]; c4.w = origin[sc * 2 + 1]; }
@@ -676,13 +675,17 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
                 const int mm = idx / (2 * Tp), e = idx - mm * 2 * Tp;
                 recon[(pair0 + mm) * 2 * Tp + e] = xy_s[mm * ldxy + e];
             }
-        for (int idx = tid; idx < BM * 2 * Tp; idx += EPI_THREADS) {      // conv input of block 1: x_true - x_hat0
-            const int mm = idx / (2 * Tp), e = idx - mm * 2 * Tp;
-            const int r = mm < np ? (int)((pair0 + mm) / K) : -1;
-            xy_s[mm * ldxy + e] = r >= 0 ? traj_norm[(size_t)r * 2 * Tp + e] - xy_s[mm * ldxy + e] : 0.f;
+        {   // conv input of block 1: x_true - x_hat0.  Thread (m, sub) owns a quarter of row m's 2 T_p values: no index division, the
+            // agent row is already known (prow), independent loads of a line the prologue prefetched (this loop cost 3.8 k cycles per tile)
+            const int per = (2 * Tp + 3) >> 2, e0 = sub * per, e1 = min(2 * Tp, e0 + per);
+            const float* tn = traj_norm + (size_t)(prow >= 0 ? prow : 0) * 2 * Tp;
+#pragma unroll 4
+            for (int e = e0; e < e1; ++e) xy_s[m * ldxy + e] = prow >= 0 ? __ldg(tn + e) - xy_s[m * ldxy + e] : 0.f;
         }
         epi_barrier();
+        TLOG(tid == 0, 4);
         epi_gru(sm, bars, tmem, gb, xy_s, ldxy, BM, Tp, n_acc, ovf);
+        TLOG(tid == 0, 7);
         epi_barrier();                              // every thread is done reading the conv input before y0 overwrites xy_s
         TLOG(tid == 0, 26);
         epi_mlp(sm, bars, tmem, 2 * Tf, (int)lay.n3p[1], false, rowpre + 512, prow, w0.dec_y.b1, w0.dec_y.b2, xy_s, ldxy, false, n_acc, ovf);
