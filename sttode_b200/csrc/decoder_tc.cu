@@ -332,7 +332,7 @@ __device__ void issuer_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, int
                         tc::tc_fence_after();
                     }
                     // A operand slab: kb < 2 -> conv image (k chunks 2kb, 2kb+1); else state h (A1 k chunks 4 + 2(kb-2) ..)
-                    const uint32_t a_off = kb < 2 ? xh + kb * 4096 : a1 + 4 * 2048 + (kb - 2) * 4096;
+                    const uint32_t a_off = kb < 2 ? xh + (uint32_t)(t & 1) * 16384 + kb * 4096 : a1 + 4 * 2048 + (kb - 2) * 4096;      // conv image of step t lives in H[t & 1]
                     const uint32_t a_lo_off = kb < 2 ? a_off + 8192 : a_off + 32768;
                     const uint64_t ah = tc::op_desc(a_off, 128), al = tc::op_desc(a_lo_off, 128);
                     if (half == 0) {                // image rows [r 64 | z 64 | n 64], lo image 6144 B behind the hi image
@@ -492,9 +492,9 @@ __device__ void epi_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, const 
 #pragma unroll
     for (int i = 0; i < 24; ++i) hreg[i] = 0.f;
     TLOG(tid == 0 && ldxy != 2 * T, 5);            // pair kernel only (the row kernel passes ldxy = 2 T)
-#pragma unroll 1
-    for (int t = 0; t < T; ++t) {
-        // conv channels sub*8 .. +8 of row m at time t -> k chunk `sub` of the conv image (H[0])
+    // conv channels sub*8 .. +8 of row m at time t -> k chunk `sub` of the conv image of step t, H[t & 1]: the images alternate between the two
+    // H buffers so that step t+1's image is computed while the tensor pipe works on step t (it does not depend on the state)
+    auto stage_conv = [&](int t) {
         float d[6];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -503,23 +503,27 @@ __device__ void epi_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, const 
             d[k] = in ? xy_s[m * ldxy + tt * 2] : 0.f;
             d[3 + k] = in ? xy_s[m * ldxy + tt * 2 + 1] : 0.f;
         }
-        {
-            float v[8];
+        float v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int chn = sub * 8 + i;
-                float a = cb[chn];
+        for (int i = 0; i < 8; ++i) {
+            const int chn = sub * 8 + i;
+            float a = cb[chn];
 #pragma unroll
-                for (int e = 0; e < 6; ++e) a = fmaf(cw[chn * 6 + e], d[e], a);
-                v[i] = fmaxf(a, 0.f);
-            }
-            track_range(v, ovf);
-            tc::store_split8(sm + SM_H, sm + SM_H + 8192, 128, m, sub, v);
+            for (int e = 0; e < 6; ++e) a = fmaf(cw[chn * 6 + e], d[e], a);
+            v[i] = fmaxf(a, 0.f);
         }
+        track_range(v, ovf);
+        unsigned char* img = sm + SM_H + (t & 1) * 16384;
+        tc::store_split8(img, img + 8192, 128, m, sub, v);
+    };
+    stage_conv(0);
+#pragma unroll 1
+    for (int t = 0; t < T; ++t) {
         const bool tl = (t == 2 && tid == 0);
         TLOG(tl, 0);
-        epi_signal(bars, B_XFULL);                  // conv image t (+ state h_t written at the end of step t-1)
+        epi_signal(bars, B_XFULL);                  // conv image t (staged during step t-1) + state h_t (written at the end of step t-1)
         TLOG(tl, 1);
+        if (t + 1 < T) stage_conv(t + 1);           // H[(t+1) & 1] held the image of step t-1, whose MMAs completed before the last B_ACC2 wait
         // this thread's three 8-unit chunks of row m: chunks 2*sub, 2*sub+1 (half A, units 0..63) and 8+sub (half B, units 64..95).  The new
         // state is computed per half as soon as that half's accumulators are complete, but h is staged only after BOTH halves' MMAs have
         // finished reading the old state image.
@@ -675,6 +679,7 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
                 const int mm = idx / (2 * Tp), e = idx - mm * 2 * Tp;
                 recon[(pair0 + mm) * 2 * Tp + e] = xy_s[mm * ldxy + e];
             }
+        if (recon) epi_barrier();                   // the copy above and the build below map threads to elements differently
         {   // conv input of block 1: x_true - x_hat0.  Thread (m, sub) owns a quarter of row m's 2 T_p values: no index division, the
             // agent row is already known (prow), independent loads of a line the prologue prefetched (this loop cost 3.8 k cycles per tile)
             const int per = (2 * Tp + 3) >> 2, e0 = sub * per, e1 = min(2 * Tp, e0 + per);
