@@ -14,6 +14,7 @@
 #include "kernels.cuh"
 #include "tc.cuh"
 #include <cstdio>
+#include <type_traits>
 
 namespace sttode {
 
@@ -59,11 +60,23 @@ DecPackLayout dec_pack_layout(int Tp, int Tf) {
 // and the layout travels to the device (round 1 issued 264 single-image launches + 8 memsets per pack).
 struct PackJob { const float* W; int ldw, row0, col0, nvalid, nrows, K; uint32_t hi, lo; int perm; };      // perm: 0 rows as stored, 1 / 2 GRU half A / B
 constexpr int PACK_JOBS_MLP = 42, PACK_JOBS = 4 * PACK_JOBS_MLP + 32 + 88 + 1;
-// GRU weight rows are stored [r 96 | z 96 | n 96]; half A (units 0..63) and half B (units 64..95) get their own images [r | z | n]
+// GRU weight rows are stored [r 96 | z 96 | n 96]; half A (units 0..63) and half B (units 64..95) get their own images.  h-slabs (W_hh) are in
+// gate order [r | z | n] (perm 1 / 2), x-slabs (W_ih) in [n | r | z] (perm 3 / 4): with the accumulator columns laid out [W_in x | r | z | W_hn h]
+// both kinds of slab feed ONE contiguous column range (x: first three quarters, h: last three), i.e. one MMA per split product.
 __device__ __forceinline__ int gru_perm_row(int perm, int i) {
     if (perm == 1) return i < 64 ? i : i < 128 ? 96 + (i - 64) : 192 + (i - 128);
     if (perm == 2) return i < 32 ? 64 + i : i < 64 ? 96 + 64 + (i - 32) : 192 + 64 + (i - 64);
+    if (perm == 3) return i < 64 ? 192 + i : i < 128 ? (i - 64) : 96 + (i - 128);
+    if (perm == 4) return i < 32 ? 192 + 64 + i : i < 64 ? 64 + (i - 32) : 96 + 64 + (i - 64);
     return i;
+}
+// byte offset (inside one GRU's image area) and size of ring block j of a step (TC_GRU_STEP_BLOCKS per step; the same 8 blocks every step)
+__host__ __device__ __forceinline__ void gru_block(int j, uint32_t& off, uint32_t& bytes) {
+    // slab-pair index: x0x1 -> 0, h0h1 -> 1, h2h3 -> 2, h4h5 -> 3;   order: A0 B0 | B1 B2 A1 A2 | A3 B3
+    const bool isA = j == 0 || (j >= 4 && j <= 6);
+    const int pi = j == 0 ? 0 : j == 1 ? 0 : j == 2 ? 1 : j == 3 ? 2 : j == 4 ? 1 : j == 5 ? 2 : 3;
+    if (isA) { off = (uint32_t)pi * 2u * TC_GRU_A; bytes = 2u * TC_GRU_A; }
+    else     { off = 8u * TC_GRU_A + (uint32_t)pi * 2u * TC_GRU_B; bytes = 2u * TC_GRU_B; }
 }
 
 __device__ __forceinline__ PackJob pack_job(int j, const sttode_decompose_weights& w0, const sttode_decompose_weights& w1, const DecPackLayout& L) {
@@ -93,9 +106,11 @@ __device__ __forceinline__ PackJob pack_job(int j, const sttode_decompose_weight
     if (j < 32) {
         const int g = j >> 4, half = (j >> 3) & 1, kb = j & 7;
         const sttode_decompose_weights& w = g ? w1 : w0;
-        const uint32_t blk = L.gru_off[g] + (half ? 8u * TC_GRU_A + (uint32_t)kb * TC_GRU_B : (uint32_t)kb * TC_GRU_A);
+        // slab kb lives in slab-pair block kb >> 1 of its half, slot kb & 1
+        const uint32_t blk = L.gru_off[g] + (half ? 8u * TC_GRU_A + (uint32_t)(kb >> 1) * 2u * TC_GRU_B + (uint32_t)(kb & 1) * TC_GRU_B
+                                                  : (uint32_t)(kb >> 1) * 2u * TC_GRU_A + (uint32_t)(kb & 1) * TC_GRU_A);
         const int nrows = half ? 96 : 192;
-        if (kb < 2) J = PackJob{w.gru_w_ih, 32, 0, kb * 16, nrows, nrows, 16, blk, blk + (uint32_t)nrows * 32, 1 + half};
+        if (kb < 2) J = PackJob{w.gru_w_ih, 32, 0, kb * 16, nrows, nrows, 16, blk, blk + (uint32_t)nrows * 32, 3 + half};
         else        J = PackJob{w.gru_w_hh, 96, 0, (kb - 2) * 16, nrows, nrows, 16, blk, blk + (uint32_t)nrows * 32, 1 + half};
         return J;
     }
@@ -148,10 +163,13 @@ constexpr int SM_H = 65536;                      // 2 x [hi 8 KB | lo 8 KB] (MLP
 constexpr int SM_RING = SM_H + 32768;
 constexpr int SM_XY = SM_RING + TC_NST * TC_STAGE;
 constexpr int COL_D2 = 0, COL_D1 = 256, COL_D3 = 384;     // TMEM columns, MLP phases (D1: 4 x 32; D3 <= 128 columns)
-// GRU phase accumulators (overlap D2 / D1, not D3).  A step runs as two N-halves so the gate epilogue of half A overlaps the MMAs of half B:
-//   half A (units 0..63):  r 0..63 | z 64..127 | W_in x 128..191 | W_hn h 192..255        half B (units 64..95): r 256..287 | z 288..319 | W_in x 320..351 | W_hn h 352..383
-constexpr int COL_GA = 0, COL_GA_NI = 128, COL_GA_NH = 192, COL_GB = 256, COL_GB_NI = 320, COL_GB_NH = 352;
-constexpr int B_WFULL = 0, B_WFREE = 4, B_D1FULL = 8, B_HFULL = 12, B_HFREE = 14, B_ACC = 16, B_XFULL = 17, B_D3FREE = 18, B_ACC2 = 19, B_COUNT = 20;      // B_ACC2: GRU half B complete
+// GRU phase accumulators (the MLP accumulators are all read out by then).  A step runs as two N-halves, each [W_in x | r | z | W_hn h]:
+//   half A (units 0..63): columns 0..255        half B (units 64..95): columns 256..383 (even steps) / 384..511 (odd steps)
+// Half B alternates between two buffers and half A is read out first, so the MMAs of step t+1 run UNDER the gate math of step t: the x-slabs as soon
+// as half A's accumulators are in registers, h-slabs 0..3 once units 0..63 of h(t+1) are staged; only h-slabs 4..5 wait for the whole state.
+constexpr int COL_GA = 0, COL_GB = 256;
+constexpr int B_WFULL = 0, B_WFREE = 4, B_D1FULL = 8, B_HFULL = 12, B_HFREE = 14, B_ACC = 16, B_XFULL = 17, B_D3FREE = 18, B_ACC2 = 19,      // B_ACC2: GRU half B complete
+              B_GREAD = 20, B_HA = 21, B_HB = 22, B_COUNT = 23;    // GRU: half-A accumulators read + next conv image staged / units 0..63 / units 64..95 of the new state staged
 
 // debug timeline: absolute clock64 stamps into the status tail (CTA 0 only, when status[1] == 2)
 // compiled in only with -DSTTODE_TC_TIMELINE (scripts/tc_timing.py); the release build has no trace of it
@@ -185,20 +203,19 @@ __device__ __forceinline__ void epi_signal(uint64_t* bars, int bar) {
     if ((threadIdx.x & 31) == 0) mbar_arrive(bars + bar);
 }
 
-// global block sequence: [mlp x0: 36 blocks] [gru1: 16*Tp] [mlp y0: 36] [mlp y1: 36] [mlp x1: 36 when recon]
+// global block sequence: [mlp x0: 36 blocks] [gru1: 8*Tp] [mlp y0: 36] [mlp y1: 36] [mlp x1: 36 when recon]
 // one MLP = lead pair, 32 chunk blocks, layer-3 pair
 __device__ __forceinline__ void block_src(const DecPackLayout& lay, int Tp, int i, uint32_t& off, uint32_t& bytes) {
     int m;
     if (i < TC_MLP_BLOCKS) m = 0;
     else {
         i -= TC_MLP_BLOCKS;
-        if (i < 16 * Tp) {                          // per step: A-blocks of the 8 K-slabs, then their B-blocks
-            const int j = i & 15;
-            if (j < 8) { off = lay.gru_off[1] + (uint32_t)j * TC_GRU_A; bytes = TC_GRU_A; }
-            else       { off = lay.gru_off[1] + 8u * TC_GRU_A + (uint32_t)(j - 8) * TC_GRU_B; bytes = TC_GRU_B; }
+        if (i < TC_GRU_STEP_BLOCKS * Tp) {          // the same 8 blocks every step
+            gru_block(i & 7, off, bytes);
+            off += lay.gru_off[1];
             return;
         }
-        i -= 16 * Tp;
+        i -= TC_GRU_STEP_BLOCKS * Tp;
         if (i < TC_MLP_BLOCKS) m = 1;
         else if (i < 2 * TC_MLP_BLOCKS) { m = 2; i -= TC_MLP_BLOCKS; }
         else { m = 3; i -= 2 * TC_MLP_BLOCKS; }
@@ -233,6 +250,7 @@ __device__ void producer_loop(unsigned char* sm, uint64_t* bars, const unsigned 
     }
 }
 static_assert(TC_NST == 4, "ring index arithmetic assumes 4 stages");
+static_assert(2 * TC_GRU_A <= TC_STAGE && (TC_GRU_STEP_BLOCKS & 1) == 0, "a GRU slab pair fills at most one ring stage");
 
 // ================================================================ issuer warp ==============================
 __device__ __forceinline__ uint32_t ring_wait(unsigned char* sm, uint64_t* bars, int i) {      // block i resident -> stage address
@@ -306,56 +324,106 @@ __device__ void issuer_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int
     ++n_d3;
 }
 
-__device__ void issuer_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, int blk0, int T, uint32_t n_d3, uint32_t& n_x) {
+// GRU issue schedule of step t (one elected lane; every wait is on the completion index t of its barrier: index 0 is the epilogue's prologue,
+// index t >= 1 comes from the gate epilogue of step t-1):
+//   B_GREAD : conv image t staged, half-A accumulators of step t-1 in registers        -> x-slabs of both halves
+//   B_HA    : units 0..63 of h(t) staged (every MMA of step t-1 has completed)          -> h-slabs 0..3 (half B first: it frees the ring pair sooner)
+//   B_HB    : units 64..95 staged, half-B accumulators of step t-1 read                  -> h-slabs 4, 5; commit half A, then half B
+__device__ void issuer_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, int blk0, int T) {
     const uint32_t a1 = tc::smem_u32(sm + SM_A1), xh = tc::smem_u32(sm + SM_H), ring0 = tc::smem_u32(sm + SM_RING);
-    const uint32_t idesc128 = tc::make_idesc_f16(128), idesc64 = tc::make_idesc_f16(64), idesc32 = tc::make_idesc_f16(32);
-    (void)n_d3;                                     // the gate accumulators (columns 0..383) overlap D2 / D1 (all read out), not D3
+    const uint32_t idesc192 = tc::make_idesc_f16(192), idesc128 = tc::make_idesc_f16(128), idesc96 = tc::make_idesc_f16(96),
+                   idesc64 = tc::make_idesc_f16(64), idesc32 = tc::make_idesc_f16(32);
+    if (elect_one()) {
 #pragma unroll 1
-    for (int t = 0; t < T; ++t) {
-        const bool tl = (t == 2 && (threadIdx.x & 31) == 0);
-        TLOG(tl, 20);
-        tc_wait(bars, B_XFULL, n_x & 1);            // conv image of step t and state h_t are staged
-        ++n_x;
-        tc::tc_fence_after();
-        TLOG(tl, 21);
-        // one elected lane issues the whole step: half A (units 0..63) over the 8 K = 16 slabs of [W_ih | W_hh], commit, then half B (units 64..95):
-        // the epilogue works on half A's gates while the tensor pipe runs half B
-        if (elect_one()) {
+        for (int t = 0; t < T; ++t) {
+            const bool tl = t == 2;
+            const uint32_t par = (uint32_t)(t & 1);
+            const uint32_t colA = tmem + COL_GA, colB = tmem + COL_GB + (uint32_t)(t & 1) * 128u;
+            const int bi = blk0 + t * TC_GRU_STEP_BLOCKS;          // even
+            auto ring_pair = [&](int i) {                          // blocks i, i + 1 resident
+                tc_wait(bars, B_WFULL + ((i >> 1) & 1), (uint32_t)((i >> 2) & 1));
+                tc::tc_fence_after();
+            };
+            auto stage = [&](int i) { return ring0 + (uint32_t)(i & 3) * TC_STAGE; };
+            // state slab j (units 16j..16j+15): A1 k chunks 4 + 2j, 5 + 2j; lo image 32 KB behind the hi image
+            auto h_slab = [&](int j, uint64_t& ah, uint64_t& al) {
+                const uint32_t a = a1 + 4 * 2048 + (uint32_t)j * 4096;
+                ah = tc::op_desc(a, 128); al = tc::op_desc(a + 32768, 128);
+            };
+            // h-slab into half A (s = image inside the ring stage): r|z|nh = columns 64..255; the FIRST h-slab must not accumulate into nh
+            auto mma_hA = [&](uint32_t s, uint64_t ah, uint64_t al, bool first) {
+                if (first) {
+                    tc::mma_split3_d(colA + 64, ah, al, 0, tc::op_desc(s, 192), tc::op_desc(s + 6144, 192), 0, idesc128, 1, true);
+                    tc::mma_split3_d(colA + 192, ah, al, 0, tc::op_desc(s + 128 * 16, 192), tc::op_desc(s + 6144 + 128 * 16, 192), 0, idesc64, 1, false);
+                } else tc::mma_split3_d(colA + 64, ah, al, 0, tc::op_desc(s, 192), tc::op_desc(s + 6144, 192), 0, idesc192, 1, true);
+            };
+            auto mma_hB = [&](uint32_t s, uint64_t ah, uint64_t al, bool first) {
+                if (first) {
+                    tc::mma_split3_d(colB + 32, ah, al, 0, tc::op_desc(s, 96), tc::op_desc(s + 3072, 96), 0, idesc64, 1, true);
+                    tc::mma_split3_d(colB + 96, ah, al, 0, tc::op_desc(s + 64 * 16, 96), tc::op_desc(s + 3072 + 64 * 16, 96), 0, idesc32, 1, false);
+                } else tc::mma_split3_d(colB + 32, ah, al, 0, tc::op_desc(s, 96), tc::op_desc(s + 3072, 96), 0, idesc96, 1, true);
+            };
+            // ---- x-slabs: conv image of step t (H[t & 1], k chunks 0..3) . W_ih^T -> [ni | r | z] of both halves
+            TLOG(tl, 20);
+            tc_wait(bars, B_GREAD, par);
+            tc::tc_fence_after();
+            TLOG(tl, 21);
+            ring_pair(bi);
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-#pragma unroll
-                for (int kb = 0; kb < 8; ++kb) {
-                    const int bi = blk0 + t * 16 + half * 8 + kb;
-                    const uint32_t st = ring0 + (uint32_t)(bi & 3) * TC_STAGE;
-                    if (!(kb & 1)) {                // blk0 is even: the pair's barrier covers slab kb + 1 too
-                        tc_wait(bars, B_WFULL + ((bi >> 1) & 1), (uint32_t)((bi >> 2) & 1));
-                        tc::tc_fence_after();
-                    }
-                    // A operand slab: kb < 2 -> conv image (k chunks 2kb, 2kb+1); else state h (A1 k chunks 4 + 2(kb-2) ..)
-                    const uint32_t a_off = kb < 2 ? xh + (uint32_t)(t & 1) * 16384 + kb * 4096 : a1 + 4 * 2048 + (kb - 2) * 4096;      // conv image of step t lives in H[t & 1]
-                    const uint32_t a_lo_off = kb < 2 ? a_off + 8192 : a_off + 32768;
-                    const uint64_t ah = tc::op_desc(a_off, 128), al = tc::op_desc(a_lo_off, 128);
-                    if (half == 0) {                // image rows [r 64 | z 64 | n 64], lo image 6144 B behind the hi image
-                        tc::mma_split3_d(tmem + COL_GA, ah, al, 0, tc::op_desc(st, 192), tc::op_desc(st + 6144, 192), 0, idesc128, 1, kb > 0);
-                        const uint64_t bnh = tc::op_desc(st + 128 * 16, 192), bnl = tc::op_desc(st + 6144 + 128 * 16, 192);
-                        if (kb < 2) tc::mma_split3_d(tmem + COL_GA_NI, ah, al, 0, bnh, bnl, 0, idesc64, 1, kb > 0);
-                        else        tc::mma_split3_d(tmem + COL_GA_NH, ah, al, 0, bnh, bnl, 0, idesc64, 1, kb > 2);
-                    } else {                        // image rows [r 32 | z 32 | n 32], lo image 3072 B behind the hi image
-                        tc::mma_split3_d(tmem + COL_GB, ah, al, 0, tc::op_desc(st, 96), tc::op_desc(st + 3072, 96), 0, idesc64, 1, kb > 0);
-                        const uint64_t bnh = tc::op_desc(st + 64 * 16, 96), bnl = tc::op_desc(st + 3072 + 64 * 16, 96);
-                        if (kb < 2) tc::mma_split3_d(tmem + COL_GB_NI, ah, al, 0, bnh, bnl, 0, idesc32, 1, kb > 0);
-                        else        tc::mma_split3_d(tmem + COL_GB_NH, ah, al, 0, bnh, bnl, 0, idesc32, 1, kb > 2);
-                    }
-                    if (kb & 1) tc::mma_commit(bars + B_WFREE + ((bi >> 1) & 1));
-                    if (kb == 7) tc::mma_commit(bars + (half ? B_ACC2 : B_ACC));      // half A -> B_ACC, half B -> B_ACC2 (one completion each per step)
-                }
+            for (int kb = 0; kb < 2; ++kb) {
+                const uint32_t xa = xh + (uint32_t)(t & 1) * 16384 + kb * 4096;
+                const uint64_t ah = tc::op_desc(xa, 128), al = tc::op_desc(xa + 8192, 128);
+                const uint32_t sa = stage(bi) + kb * TC_GRU_A, sb = stage(bi + 1) + kb * TC_GRU_B;
+                tc::mma_split3_d(colA, ah, al, 0, tc::op_desc(sa, 192), tc::op_desc(sa + 6144, 192), 0, idesc192, 1, kb > 0);
+                tc::mma_split3_d(colB, ah, al, 0, tc::op_desc(sb, 96), tc::op_desc(sb + 3072, 96), 0, idesc96, 1, kb > 0);
             }
+            tc::mma_commit(bars + B_WFREE + ((bi >> 1) & 1));
+            // ---- h-slabs 0..3
+            tc_wait(bars, B_HA, par);
+            tc::tc_fence_after();
+            TLOG(tl, 22);
+            ring_pair(bi + 2);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint64_t ah, al;
+                h_slab(j, ah, al);
+                mma_hB(stage(bi + 2 + (j >> 1)) + (j & 1) * TC_GRU_B, ah, al, j == 0);
+            }
+            tc::mma_commit(bars + B_WFREE + (((bi + 2) >> 1) & 1));
+            ring_pair(bi + 4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint64_t ah, al;
+                h_slab(j, ah, al);
+                mma_hA(stage(bi + 4 + (j >> 1)) + (j & 1) * TC_GRU_A, ah, al, j == 0);
+            }
+            tc::mma_commit(bars + B_WFREE + (((bi + 4) >> 1) & 1));
+            // ---- h-slabs 4, 5: the only MMAs on the recurrence's critical path
+            tc_wait(bars, B_HB, par);
+            tc::tc_fence_after();
+            TLOG(tl, 14);
+            ring_pair(bi + 6);
+#pragma unroll
+            for (int j = 4; j < 6; ++j) {
+                uint64_t ah, al;
+                h_slab(j, ah, al);
+                mma_hA(stage(bi + 6) + (j & 1) * TC_GRU_A, ah, al, false);
+            }
+            tc::mma_commit(bars + B_ACC);
+#pragma unroll
+            for (int j = 4; j < 6; ++j) {
+                uint64_t ah, al;
+                h_slab(j, ah, al);
+                mma_hB(stage(bi + 7) + (j & 1) * TC_GRU_B, ah, al, false);
+            }
+            tc::mma_commit(bars + B_ACC2);
+            tc::mma_commit(bars + B_WFREE + (((bi + 6) >> 1) & 1));
         }
-        __syncwarp();
-        TLOG(tl, 22);
+        // final state staged and every gate accumulator read out (completion index T)
+        tc_wait(bars, B_HA, (uint32_t)(T & 1));
+        tc_wait(bars, B_HB, (uint32_t)(T & 1));
     }
-    tc_wait(bars, B_XFULL, n_x & 1);                // final state staged and the last gate read-out finished
-    ++n_x;
+    __syncwarp();
     tc::tc_fence_after();
 }
 
@@ -517,55 +585,67 @@ __device__ void epi_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, const 
         tc::store_split8(img, img + 8192, 128, m, sub, v);
     };
     stage_conv(0);
+    // completion index 0 of the three hand-off barriers: conv image 0 + zero state staged, nothing to read out yet
+    epi_signal(bars, B_GREAD);
+    epi_signal(bars, B_HA);
+    epi_signal(bars, B_HB);
+    // this thread's three 8-unit chunks of row m: chunks 2*sub, 2*sub+1 (half A, units 0..63) and 8+sub (half B, units 64..95)
+    constexpr std::integral_constant<int, 0> Q0{};
+    constexpr std::integral_constant<int, 1> Q1{};
+    constexpr std::integral_constant<int, 2> Q2{};
+    auto gates = [&](auto qc, int t) {
+        constexpr int q = decltype(qc)::value;
+        const int chunk = q < 2 ? sub * 2 + q : 8 + sub, u = chunk * 8;
+        // accumulator columns of a half: [W_in x | r | z | W_hn h], each `w` wide
+        const uint32_t base = tmem + lane_base + (q < 2 ? COL_GA + u : COL_GB + (uint32_t)(t & 1) * 128u + (u - 64)), w = q < 2 ? 64u : 32u;
+        float gr[8], gz[8], gni[8], gnh[8];
+        tc::tmem_ld8x4(base + w, base + 2 * w, base, base + 3 * w, gr, gz, gni, gnh);
+        if (q == 1) epi_signal(bars, B_GREAD);      // half A is in registers (q = 0 was read before) and conv image t+1 is staged: x-slabs of step t+1 may run
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            // r = 1/(1+ea), z = 1/(1+eb) with one reciprocal of the product (pre-activations clamped so it stays finite)
+            const float da = 1.f + __expf(-fmaxf(gr[i] + brz[u + i], -30.f));          // lower clamp keeps da * db finite; large positive x gives e^-x -> 0
+            const float db = 1.f + __expf(-fmaxf(gz[i] + brz[96 + u + i], -30.f));
+            const float inv = __fdividef(1.f, da * db);
+            const float r = inv * db, zg = inv * da;
+            const float n = fast_tanh((gni[i] + bin[u + i]) + r * (gnh[i] + bhn[u + i]));
+            const float hp = hreg[q * 8 + i];
+            hreg[q * 8 + i] = (hp - n) * zg + n;
+        }
+    };
+    auto stage_h = [&](auto qc) {
+        constexpr int q = decltype(qc)::value;
+        float t8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t8[i] = hreg[q * 8 + i];
+        tc::store_split8(a1_hi_p, a1_lo_p, 128, m, 4 + (q < 2 ? sub * 2 + q : 8 + sub), t8);
+    };
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
         const bool tl = (t == 2 && tid == 0);
         TLOG(tl, 0);
-        epi_signal(bars, B_XFULL);                  // conv image t (staged during step t-1) + state h_t (written at the end of step t-1)
+        // H[(t+1) & 1] held the image of step t-1, whose MMAs completed before the half-A completion this warp waited for in the last iteration;
+        // the image is published by the B_GREAD arrival below.  It is built while the tensor pipe runs the last two h-slabs of step t.
+        if (t + 1 < T) stage_conv(t + 1);
         TLOG(tl, 1);
-        if (t + 1 < T) stage_conv(t + 1);           // H[(t+1) & 1] held the image of step t-1, whose MMAs completed before the last B_ACC2 wait
-        // this thread's three 8-unit chunks of row m: chunks 2*sub, 2*sub+1 (half A, units 0..63) and 8+sub (half B, units 64..95).  The new
-        // state is computed per half as soon as that half's accumulators are complete, but h is staged only after BOTH halves' MMAs have
-        // finished reading the old state image.
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            if (q == 0) {                           // half A complete
-                tc_wait(bars, B_ACC, n_acc & 1);
-                ++n_acc;
-                tc::tc_fence_after();
-                TLOG(tl, 2);
-            } else if (q == 2) {                    // half B complete (its own barrier: a waiter never falls two phases behind)
-                tc_wait(bars, B_ACC2, (uint32_t)(t & 1));
-                tc::tc_fence_after();
-            }
-            const int chunk = q < 2 ? sub * 2 + q : 8 + sub, u = chunk * 8;
-            const uint32_t cr = q < 2 ? COL_GA + u : COL_GB + (u - 64), cz = q < 2 ? COL_GA + 64 + u : COL_GB + 32 + (u - 64);
-            const uint32_t cni = q < 2 ? COL_GA_NI + u : COL_GB_NI + (u - 64), cnh = q < 2 ? COL_GA_NH + u : COL_GB_NH + (u - 64);
-            float gr[8], gz[8], gni[8], gnh[8];
-            tc::tmem_ld8x4(tmem + lane_base + cr, tmem + lane_base + cz, tmem + lane_base + cni, tmem + lane_base + cnh, gr, gz, gni, gnh);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                // r = 1/(1+ea), z = 1/(1+eb) with one reciprocal of the product (pre-activations clamped so it stays finite)
-                const float da = 1.f + __expf(-fmaxf(gr[i] + brz[u + i], -30.f));          // lower clamp keeps da * db finite; large positive x gives e^-x -> 0
-                const float db = 1.f + __expf(-fmaxf(gz[i] + brz[96 + u + i], -30.f));
-                const float inv = __fdividef(1.f, da * db);
-                const float r = inv * db, zg = inv * da;
-                const float n = fast_tanh((gni[i] + bin[u + i]) + r * (gnh[i] + bhn[u + i]));
-                const float hp = hreg[q * 8 + i];
-                hreg[q * 8 + i] = (hp - n) * zg + n;
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            float t8[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) t8[i] = hreg[q * 8 + i];
-            tc::store_split8(a1_hi_p, a1_lo_p, 128, m, 4 + (q < 2 ? sub * 2 + q : 8 + sub), t8);
-        }
+        tc_wait(bars, B_ACC, n_acc & 1);            // half A of step t complete
+        ++n_acc;
+        tc::tc_fence_after();
+        TLOG(tl, 2);
+        gates(Q0, t);
+        gates(Q1, t);
+        // the old state image is read by the MMAs of BOTH halves: wait for half B too (complete long ago) before overwriting it
+        tc_wait(bars, B_ACC2, (uint32_t)(t & 1));
+        tc::tc_fence_after();
+        stage_h(Q0);
+        stage_h(Q1);
+        epi_signal(bars, B_HA);                     // units 0..63 of h(t+1): h-slabs 0..3 of step t+1 run under the gate math of half B
         TLOG(tl, 3);
+        gates(Q2, t);
+        stage_h(Q2);
+        epi_signal(bars, B_HB);                     // units 64..95 staged, half-B accumulators read
     }
     TLOG(tid == 0 && ldxy != 2 * T, 6);
-    epi_signal(bars, B_XFULL);                      // final state staged, gate accumulators read out
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -594,15 +674,15 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
     const int prow = m < np ? (int)((pair0 + m) / K) : -1;
     int ovf = 0;                                    // set when a staged fp16 operand would leave the fp16 range
     if (rng_state) seed += *rng_state;
-    const int total_blocks = TC_MLP_BLOCKS * 3 + 16 * Tp + (recon ? TC_MLP_BLOCKS : 0);
-    const int by0 = TC_MLP_BLOCKS + 16 * Tp;
+    const int total_blocks = TC_MLP_BLOCKS * 3 + TC_GRU_STEP_BLOCKS * Tp + (recon ? TC_MLP_BLOCKS : 0);
+    const int by0 = TC_MLP_BLOCKS + TC_GRU_STEP_BLOCKS * Tp;
 #ifdef STTODE_TC_TIMELINE
     if (blockIdx.x == 0 && tid == 0) g_tl = status[1] == 2 ? reinterpret_cast<long long*>(status + 2) : nullptr;
 #endif
 
     if (tid == 0) {
         for (int i = 0; i < B_COUNT; ++i) {
-            const int cnt = (i == B_HFULL || i == B_HFULL + 1) ? 8 : (i == B_XFULL || i == B_D3FREE) ? 16 : 1;     // arrivals: one per epilogue warp
+            const int cnt = (i == B_HFULL || i == B_HFULL + 1) ? 8 : (i == B_XFULL || i == B_D3FREE || i == B_GREAD || i == B_HA || i == B_HB) ? 16 : 1;     // arrivals: one per epilogue warp
             tc::mbar_init(bars + i, cnt);
         }
         tc::fence_mbar_init();
@@ -663,9 +743,9 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
     if (warp == PRODUCER_WARP) {                    // ---------------- producer
         producer_loop(sm, bars, packed, total_blocks, status[1] == 3, [&](int i, uint32_t& off, uint32_t& bytes) { block_src(lay, Tp, i, off, bytes); });
     } else if (warp == ISSUER_WARP) {               // ---------------- issuer
-        uint32_t n_d3 = 0, n_x = 0;
+        uint32_t n_d3 = 0;
         issuer_mlp(sm, bars, tmem, 32, (int)lay.n3p[0], 0, n_d3);
-        issuer_gru(sm, bars, tmem, TC_MLP_BLOCKS, Tp, n_d3, n_x);
+        issuer_gru(sm, bars, tmem, TC_MLP_BLOCKS, Tp);
         issuer_mlp(sm, bars, tmem, 32, (int)lay.n3p[1], by0, n_d3);
         issuer_mlp(sm, bars, tmem, 128, (int)lay.n3p[2], by0 + TC_MLP_BLOCKS, n_d3);
         if (recon) issuer_mlp(sm, bars, tmem, 128, (int)lay.n3p[3], by0 + 2 * TC_MLP_BLOCKS, n_d3);
@@ -730,13 +810,12 @@ constexpr int SMR_PFLO = SM_RING + TC_NST * TC_STAGE;     // past_feature image 
 constexpr int SMR_BARS = SMR_PFLO + 32768;
 
 __device__ __forceinline__ void row_block_src(const DecPackLayout& lay, int Tp, int i, uint32_t& off, uint32_t& bytes) {
-    if (i < 16 * Tp) {
-        const int j = i & 15;
-        if (j < 8) { off = lay.gru_off[0] + (uint32_t)j * TC_GRU_A; bytes = TC_GRU_A; }
-        else       { off = lay.gru_off[0] + 8u * TC_GRU_A + (uint32_t)(j - 8) * TC_GRU_B; bytes = TC_GRU_B; }
+    if (i < TC_GRU_STEP_BLOCKS * Tp) {
+        gru_block(i & 7, off, bytes);
+        off += lay.gru_off[0];
         return;
     }
-    off = lay.rowp_off + (uint32_t)(i - 16 * Tp) * 16384;
+    off = lay.rowp_off + (uint32_t)(i - TC_GRU_STEP_BLOCKS * Tp) * 16384;
     bytes = 16384;
 }
 
@@ -753,10 +832,11 @@ k_dec_row_tc(const float* __restrict__ past_feature, const float* __restrict__ t
     const int m = wq * 32 + lane;
     const int row0 = blockIdx.x * BM;
     const int nrow = min(BM, rows - row0);
-    const int total_blocks = 16 * Tp + 88;
+    const int total_blocks = TC_GRU_STEP_BLOCKS * Tp + 88;
 
     if (tid == 0) {
-        for (int i = 0; i < B_COUNT; ++i) tc::mbar_init(bars + i, (i == B_HFULL || i == B_HFULL + 1 || i == B_XFULL || i == B_D3FREE) ? 16 : 1);
+        for (int i = 0; i < B_COUNT; ++i)
+            tc::mbar_init(bars + i, (i == B_HFULL || i == B_HFULL + 1 || i == B_XFULL || i == B_D3FREE || i == B_GREAD || i == B_HA || i == B_HB) ? 16 : 1);
         tc::fence_mbar_init();
     }
     if (warp == ISSUER_WARP) tc::tmem_alloc(tmem_slot, 512);
@@ -779,14 +859,13 @@ k_dec_row_tc(const float* __restrict__ past_feature, const float* __restrict__ t
     if (warp == PRODUCER_WARP) {                    // ---------------- producer
         producer_loop(sm, bars, packed, total_blocks, 0, [&](int i, uint32_t& off, uint32_t& bytes) { row_block_src(lay, Tp, i, off, bytes); });
     } else if (warp == ISSUER_WARP) {               // ---------------- issuer
-        uint32_t n_x = 0;
-        issuer_gru(sm, bars, tmem, 0, Tp, 0, n_x);
-        tc_wait(bars, B_XFULL, n_x & 1);            // past_feature images staged
+        issuer_gru(sm, bars, tmem, 0, Tp);
+        tc_wait(bars, B_XFULL, 0);                  // past_feature images staged
         tc::tc_fence_after();
         const uint32_t pf_hi = tc::smem_u32(sm + SMR_PFHI), pf_lo = tc::smem_u32(sm + SMR_PFLO);
         const uint32_t st_hi = tc::smem_u32(sm + SM_A1) + 4 * 2048, st_lo = st_hi + 32768;
         const uint32_t idesc = tc::make_idesc_f16(256);
-        int blk = 16 * Tp;
+        int blk = TC_GRU_STEP_BLOCKS * Tp;
 #pragma unroll 1
         for (int j = 0; j < 8; ++j) {               // output tile j: product p = j/2, columns (j&1)*256 ..
             const int b = j & 1, nks = j < 4 ? 14 : 8;
