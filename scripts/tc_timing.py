@@ -22,8 +22,8 @@ L.check(lib.sttode_decoder_timing(L.dptr(buf), 8, 12, 0, out))
 v = list(out)
 d = lambda a, b: (v[b] - v[a]) if v[a] and v[b] else None
 print("epilogue phases (cycles): x0", d(24, 25), " prep+gru", d(25, 26), " y0", d(26, 27), " y1", d(27, 28), " output", d(28, 29), " total", d(24, 29))
-print("gru step t=2, epilogue thread 0: conv image", d(0, 1), " wait for gates (MMA)", d(1, 2), " gate math + restage", d(2, 3))
-print("gru step t=2, issuer lane 0: wait xfull", d(20, 21), " issue 8 slabs", d(21, 22))
+print("gru step t=2, epilogue thread 0: conv image t+1", d(0, 1), " wait half A", d(1, 2), " gates A + stage (-> HA signalled)", d(2, 3))
+print("gru step t=2, issuer (relative to the epilogue's iteration start): before GREAD wait", d(0, 20), " GREAD ok", d(0, 21), " HA ok", d(0, 22), " HB ok", d(0, 14))
 print("epi mlp ch4 grp0 [before d1full, d1full ok, tmem ld done, staged+signalled]:", [d(10, 10 + i) for i in range(1, 4)])
 print("epi mlp ch5 grp1 [before d1full, d1full ok, tmem ld done, staged+signalled]:", [d(15, 15 + i) for i in range(1, 4)])
 print("GRU phase from the end of x0 (25): conv input built", d(25, 4), " h zeroed / loop start", d(25, 5), " 8 steps done", d(25, 6), " final signal", d(25, 7), " y0 starts", d(25, 26))

@@ -538,11 +538,20 @@ __device__ void epi_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int n3
     TLOG(tl2, 30);
 }
 
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
+constexpr float LOG2E = 1.4426950408889634f;
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// GRU constants in shared memory, biases pre-scaled for the ex2-based gates of epi_gru: [-log2e (b_ir+b_hr | b_iz+b_hz) 192 | 2 log2e b_in 96 | 2 log2e b_hn 96 | conv_w 192 | conv_b 32]
+__device__ __forceinline__ float gru_const(const sttode_decompose_weights& w, int i) {
+    if (i < 192) return -LOG2E * (w.gru_b_ih[i] + w.gru_b_hh[i]);
+    if (i < 288) return 2.f * LOG2E * w.gru_b_ih[i];
+    if (i < 384) return 2.f * LOG2E * w.gru_b_hh[i - 96];
+    if (i < 576) return w.conv_w[i - 384];
+    return w.conv_b[i - 576];
+}
 
 // Conv1d+ReLU -> GRU over T steps; conv input d = xy_s; final state left in A1 k 32..127 (fp16 hi/lo images).
-// gb: shared-memory constants [brz 192 | bin 96 | bhn 96 | conv_w 192 | conv_b 32]
+// gb: shared-memory constants of gru_const()
 __device__ void epi_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, const float* gb, const float* xy_s, int ldxy, int valid_rows, int T,
                         uint32_t& n_acc, int& ovf) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wq = warp & 3, sub = warp >> 2;
@@ -603,14 +612,18 @@ __device__ void epi_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, const 
         if (q == 1) epi_signal(bars, B_GREAD);      // half A is in registers (q = 0 was read before) and conv image t+1 is staged: x-slabs of step t+1 may run
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            // r = 1/(1+ea), z = 1/(1+eb) with one reciprocal of the product (pre-activations clamped so it stays finite)
-            const float da = 1.f + __expf(-fmaxf(gr[i] + brz[u + i], -30.f));          // lower clamp keeps da * db finite; large positive x gives e^-x -> 0
-            const float db = 1.f + __expf(-fmaxf(gz[i] + brz[96 + u + i], -30.f));
-            const float inv = __fdividef(1.f, da * db);
+            // r = 1/(1+ea), z = 1/(1+eb) with one reciprocal of the product.  The biases are pre-scaled by -log2(e) (r, z) and 2 log2(e) (n), so a
+            // pre-activation is ONE fma away from the ex2 argument; the clamp (pre-activation >= -30) keeps da * db finite, large positive x gives 2^-x -> 0.
+            // ex2 / rcp in their .ftz forms: no operand here is denormal, and the non-ftz forms cost three extra instructions each.
+            const float da = 1.f + ex2_ftz(fminf(fmaf(gr[i], -LOG2E, brz[u + i]), 30.f * LOG2E));
+            const float db = 1.f + ex2_ftz(fminf(fmaf(gz[i], -LOG2E, brz[96 + u + i]), 30.f * LOG2E));
+            const float inv = rcp_ftz(da * db);
             const float r = inv * db, zg = inv * da;
-            const float n = fast_tanh((gni[i] + bin[u + i]) + r * (gnh[i] + bhn[u + i]));
+            // tanh(y) = 1 - 2 / (1 + e^(2y));  e^(2y) = inf gives 1, 0 gives -1
+            const float ec = ex2_ftz(fmaf(r, fmaf(gnh[i], 2.f * LOG2E, bhn[u + i]), fmaf(gni[i], 2.f * LOG2E, bin[u + i])));
+            const float n = fmaf(-2.f, rcp_ftz(1.f + ec), 1.f);
             const float hp = hreg[q * 8 + i];
-            hreg[q * 8 + i] = (hp - n) * zg + n;
+            hreg[q * 8 + i] = fmaf(hp - n, zg, n);
         }
     };
     auto stage_h = [&](auto qc) {
@@ -689,15 +702,7 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
     }
     if (warp == ISSUER_WARP) tc::tmem_alloc(tmem_slot, 512);
     if (warp < ISSUER_WARP) {
-        for (int i = tid; i < 608; i += EPI_THREADS) {
-            float v;
-            if (i < 192) v = w1.gru_b_ih[i] + w1.gru_b_hh[i];
-            else if (i < 288) v = w1.gru_b_ih[i];                      // b_in
-            else if (i < 384) v = w1.gru_b_hh[i - 96];                 // b_hn
-            else if (i < 576) v = w1.conv_w[i - 384];
-            else v = w1.conv_b[i - 576];
-            gb[i] = v;
-        }
+        for (int i = tid; i < 608; i += EPI_THREADS) gb[i] = gru_const(w1, i);
         // latent z -> A1 k chunks 0..3 (this thread: chunk `sub` of row m)
         {
             const int kc = sub;
@@ -841,15 +846,7 @@ k_dec_row_tc(const float* __restrict__ past_feature, const float* __restrict__ t
     }
     if (warp == ISSUER_WARP) tc::tmem_alloc(tmem_slot, 512);
     if (warp < ISSUER_WARP)
-        for (int i = tid; i < 608; i += EPI_THREADS) {
-            float v;
-            if (i < 192) v = w0.gru_b_ih[i] + w0.gru_b_hh[i];
-            else if (i < 288) v = w0.gru_b_ih[i];
-            else if (i < 384) v = w0.gru_b_hh[i - 96];
-            else if (i < 576) v = w0.conv_w[i - 384];
-            else v = w0.conv_b[i - 576];
-            gb[i] = v;
-        }
+        for (int i = tid; i < 608; i += EPI_THREADS) gb[i] = gru_const(w0, i);
     tc::fence_proxy_async();
     tc::tc_fence_before();
     __syncthreads();
