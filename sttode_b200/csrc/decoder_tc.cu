@@ -38,12 +38,15 @@ DecPackLayout dec_pack_layout(int Tp, int Tf) {
         L.k1[m] = k1[m];
         L.n3[m] = n3[m];
         L.n3p[m] = (n3[m] + 15) / 16 * 16;
-        // stream of one MLP: lead pair [W1 rows of chunk 0 | chunk 1] (hi block, lo block), then per chunk c a (hi, lo) pair of
-        // [W2 chunk c image (256 rows x 32 k) | W1 chunk c+2 image (32 rows x K1)]: layer 1 runs two chunks ahead of layer 2
-        L.lead_blk[m] = 2 * 64 * k1[m];
-        L.mlp_blk[m] = 16384 + 64 * k1[m];
+        // Layer 1 runs per GROUP of 128 hidden units (four 32-unit chunks: one N = 128 MMA per split product instead of four N = 32 ones at the
+        // small-N issue floor).  Stream of one MLP: lead = W1 rows of group 0 as two K halves [hi, lo, hi, lo] + the first K slice of group 1
+        // [hi, lo]; then per chunk c a (hi, lo) pair of [W2 chunk c image (256 rows x 32 k) | K slice (c+1) & 3 of W1 group ((c+1) >> 2) + 1]:
+        // a group's layer 1 is complete one chunk before its first chunk is consumed.  K1 = 128: four slices of 32 k; K1 = 32: two of 16 k.
+        L.lead_blk[m] = 128 * k1[m];            // 128 rows x K1/2 halves
+        L.slice_blk[m] = 128 * 2 * (k1[m] == 32 ? 16 : k1[m] / 4);
+        L.mlp_blk[m] = 16384 + L.slice_blk[m];
         L.mlp_off[m] = off;
-        off += 2 * L.lead_blk[m] + TC_NCH * L.mlp_blk[m];
+        off += 4 * L.lead_blk[m] + 2 * L.slice_blk[m] + TC_NCH * L.mlp_blk[m];
         L.l3_blk[m] = L.n3p[m] * 512;           // 4 pieces of [hi n3p x 32 | lo n3p x 32]
         L.l3_off[m] = off;
         off += 2 * L.l3_blk[m];
@@ -59,7 +62,7 @@ DecPackLayout dec_pack_layout(int Tp, int Tf) {
 // Job j (blockIdx.y) is one operand image; the job list is a closed-form function of the layout, so nothing but the weight pointers
 // and the layout travels to the device (round 1 issued 264 single-image launches + 8 memsets per pack).
 struct PackJob { const float* W; int ldw, row0, col0, nvalid, nrows, K; uint32_t hi, lo; int perm; };      // perm: 0 rows as stored, 1 / 2 GRU half A / B
-constexpr int PACK_JOBS_MLP = 42, PACK_JOBS = 4 * PACK_JOBS_MLP + 32 + 88 + 1;
+constexpr int PACK_JOBS_MLP = 2 + 12 + 16 + 8, PACK_JOBS = 4 * PACK_JOBS_MLP + 32 + 88 + 1;
 // GRU weight rows are stored [r 96 | z 96 | n 96]; half A (units 0..63) and half B (units 64..95) get their own images.  h-slabs (W_hh) are in
 // gate order [r | z | n] (perm 1 / 2), x-slabs (W_ih) in [n | r | z] (perm 3 / 4): with the accumulator columns laid out [W_in x | r | z | W_hn h]
 // both kinds of slab feed ONE contiguous column range (x: first three quarters, h: last three), i.e. one MMA per split product.
@@ -85,18 +88,24 @@ __device__ __forceinline__ PackJob pack_job(int j, const sttode_decompose_weight
         const int m = j / PACK_JOBS_MLP, i = j - m * PACK_JOBS_MLP;
         const sttode_mlp3_weights& mw = m == 0 ? w0.dec_x : m == 1 ? w0.dec_y : m == 2 ? w1.dec_y : w1.dec_x;
         const int K1 = (int)L.k1[m], n3 = (int)L.n3[m], n3p = (int)L.n3p[m];
-        const uint32_t w1sz = 64u * (uint32_t)K1, lead_hi = L.mlp_off[m], lead_lo = lead_hi + L.lead_blk[m], chunk0 = lead_hi + 2 * L.lead_blk[m];
-        auto layer1 = [&](int c, uint32_t hi, uint32_t lo) {       // layer-1 rows of chunk c (hidden units 32c..), pair columns 128..128+K1; c >= 16: zeros
-            J = PackJob{mw.w0, 256, c * 32, 128, c < 16 ? 32 : 0, 32, K1, hi, lo};
-        };
-        if (i < 2) layer1(i, lead_hi + i * w1sz, lead_lo + i * w1sz);
-        else if (i < 34) {
-            const int c = (i - 2) >> 1;
-            const uint32_t ba = chunk0 + (uint32_t)(2 * c) * L.mlp_blk[m], bb = ba + L.mlp_blk[m];
-            if (!((i - 2) & 1)) J = PackJob{mw.w1, 512, 0, c * 32, 256, 256, 32, ba, bb};
-            else layer1(c + 2, ba + 16384, bb + 16384);
+        const uint32_t lead = L.mlp_off[m], SB = L.slice_blk[m], chunk0 = lead + 4 * L.lead_blk[m] + 2 * SB;
+        const int nsl = K1 == 32 ? 2 : 4, ksl = K1 / nsl;
+        if (i < 2) {                    // group 0, K half i: hidden rows 0..127, pair columns 128 + i K1/2 ..
+            J = PackJob{mw.w0, 256, 0, 128 + i * (K1 / 2), 128, 128, K1 / 2, lead + (uint32_t)(2 * i) * L.lead_blk[m], lead + (uint32_t)(2 * i + 1) * L.lead_blk[m]};
+        } else if (i < 14) {            // group g = 1..3, K slice s: rides in the lead (g = 1, s = 0) or behind W2 of chunk 4 (g - 1) + s - 1
+            const int g = 1 + (i - 2) / 4, sl = (i - 2) & 3, cp = 4 * (g - 1) + sl;
+            if (sl >= nsl) J = PackJob{mw.w0, 256, 0, 0, 0, 0, 8, 0, 0};          // no such slice: empty job
+            else if (cp == 0) J = PackJob{mw.w0, 256, g * 128, 128 + sl * ksl, 128, 128, ksl, lead + 4 * L.lead_blk[m], lead + 4 * L.lead_blk[m] + SB};
+            else {
+                const uint32_t ba = chunk0 + (uint32_t)(2 * (cp - 1)) * L.mlp_blk[m] + 16384;
+                J = PackJob{mw.w0, 256, g * 128, 128 + sl * ksl, 128, 128, ksl, ba, ba + L.mlp_blk[m]};
+            }
+        } else if (i < 30) {
+            const int c = i - 14;
+            const uint32_t ba = chunk0 + (uint32_t)(2 * c) * L.mlp_blk[m];
+            J = PackJob{mw.w1, 512, 0, c * 32, 256, 256, 32, ba, ba + L.mlp_blk[m]};
         } else {
-            const int p = i - 34;
+            const int p = i - 30;
             const uint32_t pc = L.l3_off[m] + (uint32_t)(p >> 2) * L.l3_blk[m] + (uint32_t)(p & 3) * n3p * 128;
             J = PackJob{mw.w2, 256, 0, p * 32, n3, n3p, 32, pc, pc + (uint32_t)n3p * 64};
         }
@@ -162,7 +171,7 @@ constexpr int SM_A1 = 0;                         // [hi 32 KB | lo 32 KB]   A1 =
 constexpr int SM_H = 65536;                      // 2 x [hi 8 KB | lo 8 KB] (MLP 32-wide chunk operand)  /  GRU: conv image in H[0]
 constexpr int SM_RING = SM_H + 32768;
 constexpr int SM_XY = SM_RING + TC_NST * TC_STAGE;
-constexpr int COL_D2 = 0, COL_D1 = 256, COL_D3 = 384;     // TMEM columns, MLP phases (D1: 4 x 32; D3 <= 128 columns)
+constexpr int COL_D2 = 0, COL_D1 = 256, COL_D3 = 384;     // TMEM columns, MLP phases (D1: 2 buffers of 128 = one 4-chunk hidden group each; D3 <= 128 columns aliases the second)
 // GRU phase accumulators (the MLP accumulators are all read out by then).  A step runs as two N-halves, each [W_in x | r | z | W_hn h]:
 //   half A (units 0..63): columns 0..255        half B (units 64..95): columns 256..383 (even steps) / 384..511 (odd steps)
 // Half B alternates between two buffers and half A is read out first, so the MMAs of step t+1 run UNDER the gate math of step t: the x-slabs as soon
@@ -203,8 +212,8 @@ __device__ __forceinline__ void epi_signal(uint64_t* bars, int bar) {
     if ((threadIdx.x & 31) == 0) mbar_arrive(bars + bar);
 }
 
-// global block sequence: [mlp x0: 36 blocks] [gru1: 8*Tp] [mlp y0: 36] [mlp y1: 36] [mlp x1: 36 when recon]
-// one MLP = lead pair, 32 chunk blocks, layer-3 pair
+// global block sequence: [mlp x0: 40 blocks] [gru1: 8*Tp] [mlp y0: 40] [mlp y1: 40] [mlp x1: 40 when recon]
+// one MLP = 6 lead blocks, 32 chunk blocks, layer-3 pair
 __device__ __forceinline__ void block_src(const DecPackLayout& lay, int Tp, int i, uint32_t& off, uint32_t& bytes) {
     int m;
     if (i < TC_MLP_BLOCKS) m = 0;
@@ -220,9 +229,10 @@ __device__ __forceinline__ void block_src(const DecPackLayout& lay, int Tp, int 
         else if (i < 2 * TC_MLP_BLOCKS) { m = 2; i -= TC_MLP_BLOCKS; }
         else { m = 3; i -= 2 * TC_MLP_BLOCKS; }
     }
-    if (i < 2) { off = lay.mlp_off[m] + (uint32_t)i * lay.lead_blk[m]; bytes = lay.lead_blk[m]; }
-    else if (i < 2 + TC_NCH) { off = lay.mlp_off[m] + 2 * lay.lead_blk[m] + (uint32_t)(i - 2) * lay.mlp_blk[m]; bytes = lay.mlp_blk[m]; }
-    else { off = lay.l3_off[m] + (uint32_t)(i - 2 - TC_NCH) * lay.l3_blk[m]; bytes = lay.l3_blk[m]; }
+    if (i < 4) { off = lay.mlp_off[m] + (uint32_t)i * lay.lead_blk[m]; bytes = lay.lead_blk[m]; }
+    else if (i < TC_LEAD) { off = lay.mlp_off[m] + 4 * lay.lead_blk[m] + (uint32_t)(i - 4) * lay.slice_blk[m]; bytes = lay.slice_blk[m]; }
+    else if (i < TC_LEAD + TC_NCH) { off = lay.mlp_off[m] + 4 * lay.lead_blk[m] + 2 * lay.slice_blk[m] + (uint32_t)(i - TC_LEAD) * lay.mlp_blk[m]; bytes = lay.mlp_blk[m]; }
+    else { off = lay.l3_off[m] + (uint32_t)(i - TC_LEAD - TC_NCH) * lay.l3_blk[m]; bytes = lay.l3_blk[m]; }
 }
 
 // ================================================================ producer warp ============================
@@ -259,58 +269,68 @@ __device__ __forceinline__ uint32_t ring_wait(unsigned char* sm, uint64_t* bars,
 }
 
 // n_d3 is a running count kept by the caller (uniform across the warp).
-// Layer 1 runs TWO chunks ahead of layer 2: L1(ch+2) is issued before the issuer waits for the staged operand of chunk ch, so
-// the two epilogue groups always have a finished D1 to work on while the tensor pipe runs layer 2 (4 D1 buffers in TMEM; the
-// weight stream carries W1 of chunk ch+2 next to W2 of chunk ch, so both operands of an iteration arrive in one ring pair).
+// Layer 1 runs per group of 128 hidden units (chunks 4g..4g+3) into one of two 128-column D1 buffers, and well ahead of layer 2: group 0 from the
+// lead blocks, group g >= 1 in K slices that ride behind W2 of chunks 4(g-1)-1 .. (complete at least one chunk before chunk 4g is consumed), so the
+// epilogue always has a finished D1 to work on while the tensor pipe runs layer 2.  D3 aliases the second D1 buffer (free once chunk 15 is staged).
 __device__ void issuer_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int K1, int n3p, int blk0, uint32_t& n_d3) {
-    const uint32_t h_base = tc::smem_u32(sm + SM_H);
-    const uint64_t a1_hi = tc::op_desc(tc::smem_u32(sm + SM_A1), 128), a1_lo = tc::op_desc(tc::smem_u32(sm + SM_A1) + 32768, 128);
-    const uint32_t idesc1 = tc::make_idesc_f16(32), idesc2 = tc::make_idesc_f16(256), idesc3 = tc::make_idesc_f16(n3p);
-    const int nk1 = K1 >> 4;
-    const uint32_t w1sz = 64u * (uint32_t)K1;
-    {   // lead pair: layer 1 of chunks 0 and 1 (D1[0], D1[1]: their previous readers finished phases ago)
-        const uint32_t sa = ring_wait(sm, bars, blk0), sb = ring_wait(sm, bars, blk0 + 1);
+    const uint32_t h_base = tc::smem_u32(sm + SM_H), a1 = tc::smem_u32(sm + SM_A1);
+    const uint32_t idesc1 = tc::make_idesc_f16(128), idesc2 = tc::make_idesc_f16(256), idesc3 = tc::make_idesc_f16(n3p);
+    const int nsl = K1 == 32 ? 2 : 4, nks = (K1 >> 4) / nsl;              // K slices per group, K = 16 steps per slice
+    // A operand of slice / half starting at pair column k0: A1 k chunk k0 / 8 (2048 B per chunk), lo image 32 KB behind
+    auto a_hi = [&](int k0) { return tc::op_desc(a1 + (uint32_t)(k0 >> 3) * 2048u, 128); };
+    auto a_lo = [&](int k0) { return tc::op_desc(a1 + 32768u + (uint32_t)(k0 >> 3) * 2048u, 128); };
+    auto stage = [&](int i) { return tc::smem_u32(sm + SM_RING + (i & 3) * TC_STAGE); };
+    auto ring_pair = [&](int i) {                                          // blocks i, i + 1 (i even) resident
+        tc_wait(bars, B_WFULL + ((i >> 1) & 1), (uint32_t)((i >> 2) & 1));
         tc::tc_fence_after();
-        if (elect_one()) {
-            tc::mma_split3_d(tmem + COL_D1, a1_hi, a1_lo, 256, tc::op_desc(sa, 32), tc::op_desc(sb, 32), 64, idesc1, nk1, false);
-            tc::mma_commit(bars + B_D1FULL);
-            tc::mma_split3_d(tmem + COL_D1 + 32, a1_hi, a1_lo, 256, tc::op_desc(sa + w1sz, 32), tc::op_desc(sb + w1sz, 32), 64, idesc1, nk1, false);
-            tc::mma_commit(bars + B_D1FULL + 1);
-            tc::mma_commit(bars + B_WFREE + ((blk0 >> 1) & 1));
-        }
-        __syncwarp();
-    }
-    // one elected lane runs the whole chunk loop (waits included): no reconvergence between the layer-1 and layer-2 groups
+    };
+    // one elected lane runs the whole phase (waits included): no reconvergence between the MMA groups
     if (elect_one()) {
+        // lead: layer 1 of group 0 (D1 buffer 0: its previous readers finished phases ago), one K half per ring pair
+#pragma unroll 1
+        for (int kh = 0; kh < 2; ++kh) {
+            const int i = blk0 + 2 * kh;
+            ring_pair(i);
+            tc::mma_split3_d(tmem + COL_D1, a_hi(kh * (K1 >> 1)), a_lo(kh * (K1 >> 1)), 256, tc::op_desc(stage(i), 128), tc::op_desc(stage(i + 1), 128), 256,
+                             idesc1, K1 >> 5, kh > 0);
+            if (kh == 1) tc::mma_commit(bars + B_D1FULL);
+            tc::mma_commit(bars + B_WFREE + ((i >> 1) & 1));
+        }
+        {   // first K slice of group 1 -> D1 buffer 1 = D3 of the previous MLP: its read-out precedes the epilogue's first staged chunk, so this wait
+            // ends about a thousand cycles before the first layer-2 MMA can go
+            const int i = blk0 + 4;
+            ring_pair(i);
+            if (n_d3 >= 1) { tc_wait(bars, B_D3FREE, (n_d3 - 1) & 1); tc::tc_fence_after(); }
+            tc::mma_split3_d(tmem + COL_D1 + 128, a_hi(0), a_lo(0), 256, tc::op_desc(stage(i), 128), tc::op_desc(stage(i + 1), 128), 256, idesc1, nks, false);
+            tc::mma_commit(bars + B_WFREE + ((i >> 1) & 1));
+        }
 #pragma unroll 1
         for (int ch = 0; ch < 16; ++ch) {
-            const int i0 = blk0 + 2 + 2 * ch, b = ch & 1;
-            tc_wait(bars, B_WFULL + ((i0 >> 1) & 1), (uint32_t)((i0 >> 2) & 1));      // the pair's barrier covers block i0 + 1 too
-            const uint32_t sa = tc::smem_u32(sm + SM_RING + (i0 & 3) * TC_STAGE), sb = tc::smem_u32(sm + SM_RING + ((i0 + 1) & 3) * TC_STAGE);
-            tc::tc_fence_after();
-            if (ch < 14) {          // layer 1 of chunk ch+2 into D1[(ch+2)&3] (chunk ch-2 was read out before HFULL(ch-2), waited two iterations ago)
-                tc::mma_split3_d(tmem + COL_D1 + ((ch + 2) & 3) * 32, a1_hi, a1_lo, 256, tc::op_desc(sa + 16384, 32), tc::op_desc(sb + 16384, 32), 64,
-                                 idesc1, nk1, false);
-                tc::mma_commit(bars + B_D1FULL + ((ch + 2) & 3));
-            }
+            const int i0 = blk0 + TC_LEAD + 2 * ch, b = ch & 1;
+            ring_pair(i0);
+            const uint32_t sa = stage(i0), sb = stage(i0 + 1);
             tc_wait(bars, B_HFULL + b, (uint32_t)((ch >> 1) & 1));          // relu(D1(ch) + rowpre) staged as the A operand
             tc::tc_fence_after();
             tc::mma_split3_d(tmem + COL_D2, tc::op_desc(h_base + b * 16384, 128), tc::op_desc(h_base + b * 16384 + 8192, 128), 256,
                              tc::op_desc(sa, 256), tc::op_desc(sb, 256), 512, idesc2, 2, ch > 0);
-            tc::mma_commit(bars + B_WFREE + ((i0 >> 1) & 1));
             tc::mma_commit(bars + B_HFREE + b);
             if (ch == 15) tc::mma_commit(bars + B_ACC);            // D2 complete
+            // K slice (ch+1) & 3 of group ((ch+1) >> 2) + 1: its D1 buffer held group g-2, whose last chunk 4g-5 <= ch was staged before the HFULL above
+            const int cp = ch + 1, g = (cp >> 2) + 1, sl = cp & 3;
+            if (g < 4 && sl < nsl) {
+                const int k0 = sl * (K1 / nsl);
+                tc::mma_split3_d(tmem + COL_D1 + (g & 1) * 128, a_hi(k0), a_lo(k0), 256, tc::op_desc(sa + 16384, 128), tc::op_desc(sb + 16384, 128), 256, idesc1,
+                                 nks, sl > 0);
+                if (sl == nsl - 1) tc::mma_commit(bars + B_D1FULL + (g & 1));
+            }
+            tc::mma_commit(bars + B_WFREE + ((i0 >> 1) & 1));
         }
-    }
-    __syncwarp();
-    // layer 3: D3 must have been read out by the previous phase's epilogue
-    if (elect_one()) {
-        if (n_d3 >= 1) tc_wait(bars, B_D3FREE, (n_d3 - 1) & 1);
+        // layer 3 (D3 = D1 buffer 1: group 3 was staged before HFULL(15))
 #pragma unroll 1
         for (int p = 0; p < 8; ++p) {
-            const int b = p & 1, blk = blk0 + 2 + TC_NCH + (p >> 2);
-            if (!(p & 3)) tc_wait(bars, B_WFULL + ((blk >> 1) & 1), (uint32_t)((blk >> 2) & 1));     // the pair's barrier covers both layer-3 blocks
-            const uint32_t st = tc::smem_u32(sm + SM_RING + (blk & 3) * TC_STAGE) + (uint32_t)(p & 3) * n3p * 128;
+            const int b = p & 1, blk = blk0 + TC_LEAD + TC_NCH + (p >> 2);
+            if (!(p & 3)) ring_pair(blk0 + TC_LEAD + TC_NCH);                // the pair's barrier covers both layer-3 blocks (re-waiting a completed phase is free)
+            const uint32_t st = stage(blk) + (uint32_t)(p & 3) * n3p * 128;
             tc_wait(bars, B_HFULL + b, (uint32_t)((p >> 1) & 1));          // 8 layer-2 fills per buffer precede: parity unchanged
             tc::tc_fence_after();
             tc::mma_split3_d(tmem + COL_D3, tc::op_desc(h_base + b * 16384, 128), tc::op_desc(h_base + b * 16384 + 8192, 128), 256,
@@ -401,7 +421,7 @@ __device__ void issuer_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, int
             // ---- h-slabs 4, 5: the only MMAs on the recurrence's critical path
             tc_wait(bars, B_HB, par);
             tc::tc_fence_after();
-            TLOG(tl, 14);
+            TLOG(tl, 7);
             ring_pair(bi + 6);
 #pragma unroll
             for (int j = 4; j < 6; ++j) {
@@ -480,20 +500,15 @@ __device__ void epi_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int n3
     float rb[16];
 #pragma unroll 1
     for (int ch = wh; ch < 16; ch += 2) {
-        const bool tl = (!first_mlp && !accumulate && n3 != 0 && (ch == 4 || ch == 5) && lane == 0 && wq == 0 && half == 0 && n_acc >= 8);
         load_rowbias16(rb, rowpre, prow, ch * 32 + half * 16);
-        TLOG(tl, 10 + (ch - 4) * 5 + 0);
-        tc_wait(bars, B_D1FULL + (ch & 3), (uint32_t)((ch >> 2) & 1));      // 4 completions per buffer per MLP: parity restarts at 0
+        tc_wait(bars, B_D1FULL + ((ch >> 2) & 1), (uint32_t)((ch >> 3) & 1));      // group ch / 4 in D1 buffer (ch / 4) & 1; 2 completions per buffer per MLP: parity restarts at 0
         tc::tc_fence_after();
-        TLOG(tl, 10 + (ch - 4) * 5 + 1);
         float v[16];
-        tc::tmem_ld16(tmem + lane_base + COL_D1 + (ch & 3) * 32 + half * 16, v);
-        TLOG(tl, 10 + (ch - 4) * 5 + 2);
+        tc::tmem_ld16(tmem + lane_base + COL_D1 + ((ch >> 2) & 1) * 128 + (ch & 3) * 32 + half * 16, v);
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + rb[i], 0.f);
         // fill j = 12*k + ch/2 of H[wh]: wait for the reader of fill j-1
-        stage_h16(sm, bars, wh, half, m, v, first_mlp && ch < 2, (uint32_t)(((ch >> 1) + 1) & 1), ovf, tl && ch == 4);
-        TLOG(tl, 10 + (ch - 4) * 5 + 3);
+        stage_h16(sm, bars, wh, half, m, v, first_mlp && ch < 2, (uint32_t)(((ch >> 1) + 1) & 1), ovf);
     }
     const bool tl2 = !first_mlp && !accumulate && threadIdx.x == 0;      // timeline of the layer-2 / layer-3 tail (y0 phase, timeline build only)
     TLOG(tl2, 8);
@@ -609,6 +624,7 @@ __device__ void epi_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, const 
         const uint32_t base = tmem + lane_base + (q < 2 ? COL_GA + u : COL_GB + (uint32_t)(t & 1) * 128u + (u - 64)), w = q < 2 ? 64u : 32u;
         float gr[8], gz[8], gni[8], gnh[8];
         tc::tmem_ld8x4(base + w, base + 2 * w, base, base + 3 * w, gr, gz, gni, gnh);
+        TLOG(t == 2 && tid == 0, 10 + 2 * q);
         if (q == 1) epi_signal(bars, B_GREAD);      // half A is in registers (q = 0 was read before) and conv image t+1 is staged: x-slabs of step t+1 may run
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -625,6 +641,7 @@ __device__ void epi_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, const 
             const float hp = hreg[q * 8 + i];
             hreg[q * 8 + i] = fmaf(hp - n, zg, n);
         }
+        TLOG(t == 2 && tid == 0, 11 + 2 * q);
     };
     auto stage_h = [&](auto qc) {
         constexpr int q = decltype(qc)::value;
@@ -650,13 +667,16 @@ __device__ void epi_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, const 
         // the old state image is read by the MMAs of BOTH halves: wait for half B too (complete long ago) before overwriting it
         tc_wait(bars, B_ACC2, (uint32_t)(t & 1));
         tc::tc_fence_after();
+        TLOG(tl, 16);
         stage_h(Q0);
         stage_h(Q1);
+        TLOG(tl, 17);
         epi_signal(bars, B_HA);                     // units 0..63 of h(t+1): h-slabs 0..3 of step t+1 run under the gate math of half B
         TLOG(tl, 3);
         gates(Q2, t);
         stage_h(Q2);
         epi_signal(bars, B_HB);                     // units 64..95 staged, half-B accumulators read
+        TLOG(tl, 18);
     }
     TLOG(tid == 0 && ldxy != 2 * T, 6);
 }
@@ -775,7 +795,6 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
         epi_barrier();
         TLOG(tid == 0, 4);
         epi_gru(sm, bars, tmem, gb, xy_s, ldxy, BM, Tp, n_acc, ovf);
-        TLOG(tid == 0, 7);
         epi_barrier();                              // every thread is done reading the conv input before y0 overwrites xy_s
         TLOG(tid == 0, 26);
         epi_mlp(sm, bars, tmem, 2 * Tf, (int)lay.n3p[1], false, rowpre + 512, prow, w0.dec_y.b1, w0.dec_y.b2, xy_s, ldxy, false, n_acc, ovf);

@@ -101,13 +101,14 @@ size_t dec_pair_smem_bytes(int Tp, int Tf);
 constexpr int TC_NST = 4;            // weight ring stages
 constexpr int TC_STAGE = 24576;      // bytes per ring stage
 constexpr int TC_NCH = 32;           // ring blocks per MLP layer-1/2 sweep: 16 chunks of 32 hidden units x (hi block, lo block)
-constexpr int TC_MLP_BLOCKS = 36;    // per MLP: lead pair (layer-1 rows of chunks 0, 1) + TC_NCH chunk blocks + layer-3 pair
+constexpr int TC_LEAD = 6;           // lead blocks of an MLP: layer-1 rows of hidden group 0 as two K halves (hi, lo each) + the first K slice of group 1 (hi, lo)
+constexpr int TC_MLP_BLOCKS = TC_LEAD + TC_NCH + 2;    // per MLP: lead blocks + TC_NCH chunk blocks + layer-3 pair
 constexpr int TC_GRU_BLK = 18432;    // one K = 16 slab of [W_ih | W_hh]: 288 rows (hi + lo), split into an A image (units 0..63) and a B image (units 64..95)
 constexpr int TC_GRU_A = 12288;      //   A slab image: 192 rows (hi 6144 B | lo 6144 B); x-slabs (conv input) in row order [n | r | z], h-slabs in [r | z | n]
 constexpr int TC_GRU_B = 6144;       //   B slab image:  96 rows (hi 3072 B | lo 3072 B), same row orders
 constexpr int TC_GRU_STEP_BLOCKS = 8;   // ring blocks per GRU step, two slabs each, in issue order: A x0x1, B x0x1 | B h0h1, B h2h3, A h0h1, A h2h3 | A h4h5, B h4h5
 struct DecPackLayout {               // byte offsets inside the packed weight buffer; MLP order: x0, y0, y1, x1
-    uint32_t mlp_off[4], lead_blk[4], mlp_blk[4], l3_off[4], l3_blk[4], n3p[4], n3[4], k1[4];
+    uint32_t mlp_off[4], lead_blk[4], slice_blk[4], mlp_blk[4], l3_off[4], l3_blk[4], n3p[4], n3[4], k1[4];
     uint32_t gru_off[2];             // decompose[0], decompose[1]: 4 A-blocks (2 slabs, 2 * TC_GRU_A each) followed by 4 B-blocks (2 * TC_GRU_B each)
     uint32_t rowp_off;               // k_dec_row_tc layer-1 partial-product slabs
     uint32_t total;                  // bytes of images; a 256-byte status tail follows
