@@ -123,7 +123,8 @@ int sttode_profile_enable(int on);
 int sttode_profile_read(double *total_ms, unsigned long long *launches);
 
 /* tcgen05 building-block check: c[128,n] = a[128,k] . b[n,k]^T on the tensor cores, passes = 1 (fp16 inputs) or
- * 3 (fp16 hi/lo split, fp32-accurate).  status (device int) is set to 1 if the MMA never completed. */
+ * 3 (fp16 hi/lo split, fp32-accurate).  swap_lbo_sbo: 0 = the library's descriptor convention, 1 = the swapped one (must fail), 2 = A operand
+ * staged in tensor memory instead of shared memory.  status (device int) is set to 1 if the MMA never completed. */
 int sttode_umma_selftest(const float *a, const float *b, float *c, int n, int k, int passes, int swap_lbo_sbo, int *status, void *stream);
 /* Diagnostic: issue `reps` back-to-back tcgen05.mma (M = 128, K = 16, kind::f16, width n) on resident operands; cycles2_dev[0] = clock64 cycles from
  * first issue to completion, [1] = cycles spent in the issue loop (device pointer to two long long). */

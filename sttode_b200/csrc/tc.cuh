@@ -123,6 +123,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// registers -> TMEM: thread t of warp w writes lane 32*(w%4)+t, columns [col, col+N)
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]),
+                 "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ---- descriptors + MMA -----------------------------------------------------------------------------------
 // K-major, no swizzle.  lbo/sbo in bytes (multiples of 16).
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
@@ -185,6 +196,28 @@ __device__ __forceinline__ void mma_split3_d(uint32_t d_tmem, uint64_t a_hi, uin
         a_hi += a_step; a_lo += a_step; b_hi += b_step; b_lo += b_step;
     }
 }
+// A operand in TENSOR MEMORY (".ts" form): row r of A = TMEM lane r, element k of a K = 16 step = half (k & 1) of 32-bit column a_tmem + k / 2
+// (8 columns per step), K-major only.  B from shared memory as above.
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate));
+}
+// three split products with A = (a_hi, a_lo) column blocks in TMEM, advancing 8 columns per K = 16 step
+__device__ __forceinline__ void mma_split3_ts(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint64_t b_hi, uint64_t b_lo, uint32_t b_step, uint32_t idesc,
+                                              int nk, bool accumulate_first) {
+    uint32_t acc = accumulate_first ? 1u : 0u;
+#pragma unroll 2
+    for (int k = 0; k < nk; ++k) {
+        mma_f16_ts(d_tmem, a_lo, b_hi, idesc, acc);      // small terms first
+        mma_f16_ts(d_tmem, a_hi, b_lo, idesc, 1u);
+        mma_f16_ts(d_tmem, a_hi, b_hi, idesc, 1u);
+        acc = 1u;
+        a_hi += 8; a_lo += 8; b_hi += b_step; b_lo += b_step;
+    }
+}
 // descriptor of an R-row operand image starting at shared-window address `addr`
 __device__ __forceinline__ uint64_t op_desc(uint32_t addr, int rows) { return make_desc(addr, (uint32_t)rows * 16, 128); }
 
@@ -216,6 +249,16 @@ __device__ __forceinline__ void store_split8(unsigned char* hi_base, unsigned ch
     const size_t off = (size_t)kchunk * rows * 16 + (size_t)row * 16;
     *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
     *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+}
+
+// 8 consecutive-k values of one row -> 4 packed hi words and 4 packed lo words (same roundings as store_split8), for a TMEM-resident A operand
+__device__ __forceinline__ void split8_packed(const float (&v)[8], uint32_t (&hw)[4], uint32_t (&lw)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        hw[i] = cvt_f16x2(v[2 * i], v[2 * i + 1]);
+        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
+        lw[i] = cvt_f16x2(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+    }
 }
 
 }  // namespace tc

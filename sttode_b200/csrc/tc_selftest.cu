@@ -32,13 +32,30 @@ k_umma_selftest(const float* __restrict__ A, const float* __restrict__ B, float*
             tc::store_split8(b_hi, b_lo, N, r, kc, vb);
         }
     }
-    if (warp == 0) tc::tmem_alloc(tmem_slot, 256);
+    if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
     if (tid == 0) { tc::mbar_init(bar, 1); tc::fence_mbar_init(); }
     tc::fence_proxy_async();
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    const bool ts = swap_lbo_sbo == 2;              // A operand from tensor memory: hi image in columns 256.., lo image in columns 320..
+    if (ts) {
+        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        for (int kc = 0; kc < K / 8; ++kc) {
+            float va[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) va[i] = A[(size_t)tid * K + kc * 8 + i];
+            uint32_t hw[4], lw[4];
+            tc::split8_packed(va, hw, lw);
+            tc::tmem_st4(tmem + lane_base + 256 + kc * 4, hw);
+            tc::tmem_st4(tmem + lane_base + 320 + kc * 4, lw);
+        }
+        tc::tmem_st_wait();
+        tc::tc_fence_before();
+        __syncthreads();
+        tc::tc_fence_after();
+    }
     if (tid == 0) {
         const uint32_t idesc = tc::make_idesc_f16(N);
         const uint32_t a_k = 128 * 16, b_k = (uint32_t)N * 16;          // byte stride between 8-wide k chunks
@@ -48,6 +65,17 @@ k_umma_selftest(const float* __restrict__ A, const float* __restrict__ B, float*
             auto D = [&](unsigned char* base, uint32_t off, uint32_t kstride) {
                 return swap_lbo_sbo ? tc::make_desc(tc::smem_u32(base) + off, 128, kstride) : tc::make_desc(tc::smem_u32(base) + off, kstride, 128);
             };
+            if (ts) {
+                const uint32_t th = tmem + 256 + (k >> 1), tl = tmem + 320 + (k >> 1);
+                if (passes == 3) {
+                    tc::mma_f16_ts(tmem, tl, tc::make_desc(tc::smem_u32(b_hi) + bo, b_k, 128), idesc, acc ? 1u : 0u);
+                    tc::mma_f16_ts(tmem, th, tc::make_desc(tc::smem_u32(b_lo) + bo, b_k, 128), idesc, 1u);
+                    acc = true;
+                }
+                tc::mma_f16_ts(tmem, th, tc::make_desc(tc::smem_u32(b_hi) + bo, b_k, 128), idesc, acc ? 1u : 0u);
+                acc = true;
+                continue;
+            }
             if (passes == 3) {
                 tc::mma_f16(tmem, D(a_lo, ao, a_k), D(b_hi, bo, b_k), idesc, acc);
                 tc::mma_f16(tmem, D(a_hi, ao, a_k), D(b_lo, bo, b_k), idesc, true);
@@ -73,7 +101,7 @@ k_umma_selftest(const float* __restrict__ A, const float* __restrict__ B, float*
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, 256);
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
 // Issue-rate probe: `reps` back-to-back tcgen05.mma (M = 128, K = 16, kind::f16) of width N on resident zero operands, timed with

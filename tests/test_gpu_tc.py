@@ -25,6 +25,26 @@ def test_umma_selftest(N, K):
         assert err < tol, (passes, err)
 
 
+@pytest.mark.parametrize("N,K", [(16, 16), (256, 32), (32, 128), (96, 64)])
+def test_umma_selftest_a_from_tmem(N, K):
+    """tcgen05.mma with the A operand in tensor memory (lane = row, two consecutive-k halves per 32-bit column, written with tcgen05.st): the
+    form the decoder's layer 2 / layer 3 use so that relu(D + b) never leaves TMEM."""
+    dev = torch.device("cuda:0")
+    lib = L.lib()
+    g = torch.Generator().manual_seed(N * 1000 + K + 7)
+    A, B = torch.randn(128, K, generator=g), torch.randn(N, K, generator=g) * 0.1
+    Ad, Bd = A.to(dev), B.to(dev)
+    for passes, tol in ((1, 2e-6), (3, 2e-6)):
+        C = torch.full((128, N), float("nan"), device=dev)
+        st = torch.zeros(1, dtype=torch.int32, device=dev)
+        L.check(lib.sttode_umma_selftest(L.dptr(Ad), L.dptr(Bd), L.dptr(C), N, K, passes, 2, L.dptr(st), L.stream_ptr()))
+        torch.cuda.synchronize()
+        assert int(st.item()) == 0, "tcgen05.mma never completed"
+        ref = (A.half().double() @ B.half().double().T) if passes == 1 else (A.double() @ B.double().T)
+        err = ((C.cpu().double() - ref).abs().max() / ref.abs().max()).item()
+        assert err < tol, (passes, err)
+
+
 # ------------------------------------------------------------------ k_gemm_tc: the training backward's GEMM on the tensor cores (bf16x3 split)
 @pytest.mark.parametrize("M,N,K,form", [(7040, 512, 256, "nt"), (7040, 256, 512, "nn"), (512, 256, 7040, "tn"), (352, 1024, 64, "nt"), (130, 24, 257, "nt"),
                                         (64, 640, 3520, "tn"), (1000, 96, 100, "nn")])
