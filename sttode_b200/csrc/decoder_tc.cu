@@ -177,8 +177,9 @@ constexpr int COL_D2 = 0, COL_D1 = 256, COL_D3 = 384;     // TMEM columns, MLP p
 // Half B alternates between two buffers and half A is read out first, so the MMAs of step t+1 run UNDER the gate math of step t: the x-slabs as soon
 // as half A's accumulators are in registers, h-slabs 0..3 once units 0..63 of h(t+1) are staged; only h-slabs 4..5 wait for the whole state.
 constexpr int COL_GA = 0, COL_GB = 256;
-constexpr int B_WFULL = 0, B_WFREE = 4, B_D1FULL = 8, B_HFULL = 12, B_HFREE = 14, B_ACC = 16, B_XFULL = 17, B_D3FREE = 18, B_ACC2 = 19,      // B_ACC2: GRU half B complete
-              B_GREAD = 20, B_HA = 21, B_HB = 22, B_COUNT = 23;    // GRU: half-A accumulators read + next conv image staged / units 0..63 / units 64..95 of the new state staged
+constexpr int B_WFULL = 0, B_WFREE = 4, B_D1FULL = 8, B_HFULL = 12, B_ACC = 16, B_XFULL = 17, B_D3FREE = 18, B_ACC2 = 19,      // B_ACC2: GRU half B complete
+              B_GREAD = 20, B_HA = 21, B_HB = 22, B_CFULL = 23, B_L3RDY = 31, B_COUNT = 33;    // GRU: half-A accumulators read + next conv image staged / units 0..63 / units 64..95 of the new state staged
+// B_CFULL + (ch & 7): hidden chunk ch converted in place to an A operand in TMEM (8 arrivals); B_L3RDY + s: half s of relu(D2 + b1) converted (16 arrivals)
 
 // debug timeline: absolute clock64 stamps into the status tail (CTA 0 only, when status[1] == 2)
 // compiled in only with -DSTTODE_TC_TIMELINE (scripts/tc_timing.py); the release build has no trace of it
@@ -273,7 +274,7 @@ __device__ __forceinline__ uint32_t ring_wait(unsigned char* sm, uint64_t* bars,
 // lead blocks, group g >= 1 in K slices that ride behind W2 of chunks 4(g-1)-1 .. (complete at least one chunk before chunk 4g is consumed), so the
 // epilogue always has a finished D1 to work on while the tensor pipe runs layer 2.  D3 aliases the second D1 buffer (free once chunk 15 is staged).
 __device__ void issuer_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int K1, int n3p, int blk0, uint32_t& n_d3) {
-    const uint32_t h_base = tc::smem_u32(sm + SM_H), a1 = tc::smem_u32(sm + SM_A1);
+    const uint32_t a1 = tc::smem_u32(sm + SM_A1);
     const uint32_t idesc1 = tc::make_idesc_f16(128), idesc2 = tc::make_idesc_f16(256), idesc3 = tc::make_idesc_f16(n3p);
     const int nsl = K1 == 32 ? 2 : 4, nks = (K1 >> 4) / nsl;              // K slices per group, K = 16 steps per slice
     // A operand of slice / half starting at pair column k0: A1 k chunk k0 / 8 (2048 B per chunk), lo image 32 KB behind
@@ -306,16 +307,15 @@ __device__ void issuer_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int
         }
 #pragma unroll 1
         for (int ch = 0; ch < 16; ++ch) {
-            const int i0 = blk0 + TC_LEAD + 2 * ch, b = ch & 1;
+            const int i0 = blk0 + TC_LEAD + 2 * ch;
             ring_pair(i0);
             const uint32_t sa = stage(i0), sb = stage(i0 + 1);
-            tc_wait(bars, B_HFULL + b, (uint32_t)((ch >> 1) & 1));          // relu(D1(ch) + rowpre) staged as the A operand
+            tc_wait(bars, B_CFULL + (ch & 7), (uint32_t)((ch >> 3) & 1));   // relu(D1(ch) + rowpre) converted in place: per K = 16 step [hi 8 columns | lo 8 columns]
             tc::tc_fence_after();
-            tc::mma_split3_d(tmem + COL_D2, tc::op_desc(h_base + b * 16384, 128), tc::op_desc(h_base + b * 16384 + 8192, 128), 256,
-                             tc::op_desc(sa, 256), tc::op_desc(sb, 256), 512, idesc2, 2, ch > 0);
-            tc::mma_commit(bars + B_HFREE + b);
+            const uint32_t ac = tmem + COL_D1 + (uint32_t)((ch >> 2) & 1) * 128u + (uint32_t)(ch & 3) * 32u;
+            tc::mma_split3_ts(tmem + COL_D2, ac, ac + 8, 16, tc::op_desc(sa, 256), tc::op_desc(sb, 256), 512, idesc2, 2, ch > 0);
             if (ch == 15) tc::mma_commit(bars + B_ACC);            // D2 complete
-            // K slice (ch+1) & 3 of group ((ch+1) >> 2) + 1: its D1 buffer held group g-2, whose last chunk 4g-5 <= ch was staged before the HFULL above
+            // K slice (ch+1) & 3 of group ((ch+1) >> 2) + 1: its D1 buffer held group g-2, whose last chunk 4g-5 <= ch was converted before the wait above and read by the layer-2 MMAs issued before this one (the tensor pipe runs them in order)
             const int cp = ch + 1, g = (cp >> 2) + 1, sl = cp & 3;
             if (g < 4 && sl < nsl) {
                 const int k0 = sl * (K1 / nsl);
@@ -325,19 +325,24 @@ __device__ void issuer_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int
             }
             tc::mma_commit(bars + B_WFREE + ((i0 >> 1) & 1));
         }
-        // layer 3 (D3 = D1 buffer 1: group 3 was staged before HFULL(15))
+        // layer 3: A = relu(D2 + b1) converted in place (column block 16 s = K step s: [hi 8 | lo 8]), two halves of 8 steps; D3 = D1 buffer 1, whose last
+        // reader (layer 2 of chunks 12..15) precedes these MMAs in the pipe
+        {
+            const int blk = blk0 + TC_LEAD + TC_NCH;
+            ring_pair(blk);
 #pragma unroll 1
-        for (int p = 0; p < 8; ++p) {
-            const int b = p & 1, blk = blk0 + TC_LEAD + TC_NCH + (p >> 2);
-            if (!(p & 3)) ring_pair(blk0 + TC_LEAD + TC_NCH);                // the pair's barrier covers both layer-3 blocks (re-waiting a completed phase is free)
-            const uint32_t st = stage(blk) + (uint32_t)(p & 3) * n3p * 128;
-            tc_wait(bars, B_HFULL + b, (uint32_t)((p >> 1) & 1));          // 8 layer-2 fills per buffer precede: parity unchanged
-            tc::tc_fence_after();
-            tc::mma_split3_d(tmem + COL_D3, tc::op_desc(h_base + b * 16384, 128), tc::op_desc(h_base + b * 16384 + 8192, 128), 256,
-                             tc::op_desc(st, n3p), tc::op_desc(st + n3p * 64, n3p), 2 * n3p, idesc3, 2, p > 0);
-            tc::mma_commit(bars + B_HFREE + b);
-            if (p == 7) tc::mma_commit(bars + B_WFREE + ((blk >> 1) & 1));
-            if (p == 7) tc::mma_commit(bars + B_ACC);                  // D3 complete
+            for (int hf = 0; hf < 2; ++hf) {
+                tc_wait(bars, B_L3RDY + hf, n_d3 & 1);
+                tc::tc_fence_after();
+#pragma unroll 1
+                for (int p = 4 * hf; p < 4 * hf + 4; ++p) {            // 32-wide K piece p: image [hi n3p x 32 | lo n3p x 32] inside block p >> 2
+                    const uint32_t st = stage(blk + (p >> 2)) + (uint32_t)(p & 3) * n3p * 128;
+                    const uint32_t ac = tmem + COL_D2 + (uint32_t)p * 32u;
+                    tc::mma_split3_ts(tmem + COL_D3, ac, ac + 8, 16, tc::op_desc(st, n3p), tc::op_desc(st + n3p * 64, n3p), 2 * n3p, idesc3, 2, p > 0);
+                }
+            }
+            tc::mma_commit(bars + B_WFREE + ((blk >> 1) & 1));
+            tc::mma_commit(bars + B_ACC);                              // D3 complete
         }
     }
     __syncwarp();
@@ -458,23 +463,6 @@ __device__ __forceinline__ void track_range(const float (&v)[N], int& ovf) {
     ovf |= !(mx <= FP16_SAFE);                      // also true for NaN/inf
 }
 
-// stage 16 values (k chunks 2*half, 2*half+1) of one row of the chunk operand H[b]; prev_parity = phase of the MMA that read
-// the previous contents of H[b]
-__device__ __forceinline__ void stage_h16(unsigned char* sm, uint64_t* bars, int b, int half, int m, const float (&v)[16], bool first,
-                                          uint32_t prev_parity, int& ovf, bool tl = false) {
-    track_range(v, ovf);
-    if (!first) tc_wait(bars, B_HFREE + b, prev_parity);
-    unsigned char* hb = sm + SM_H + b * 16384;
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        float t8[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) t8[i] = v[q * 8 + i];
-        tc::store_split8(hb, hb + 8192, 128, m, half * 2 + q, t8);
-    }
-    epi_signal(bars, B_HFULL + b);
-}
-
 __device__ __forceinline__ void load_rowbias16(float (&rb)[16], const float* __restrict__ rowpre, int prow, int col) {
     if (prow >= 0) {
         const float4* p = reinterpret_cast<const float4*>(rowpre + (size_t)prow * ROWPRE_LD + col);
@@ -489,14 +477,42 @@ __device__ __forceinline__ void load_rowbias16(float (&rb)[16], const float* __r
     }
 }
 
-// Epilogue warp groups: sub = warp >> 2.  wh = sub & 1 owns the chunks / pieces of index parity wh (one of the double buffers),
-// half = sub >> 1 owns columns 16*half..16*half+15 of each 32-wide chunk, so two chunks are in flight and each is staged by 8 warps.
+// 16 accumulator columns of one row -> relu -> fp16 hi/lo -> written back IN PLACE as the A operand of the next layer's MMA (tensor-memory A):
+// the 16 fp32 columns of a K = 16 step become [hi: 8 columns of packed pairs | lo: 8 columns], so a thread only overwrites columns it has read itself
+__device__ __forceinline__ void convert_in_place16(uint32_t taddr, const float (&v)[16], int& ovf) {
+    track_range(v, ovf);
+    uint32_t hw[8], lw[8];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        float t8[8];
+        uint32_t h4[4], l4[4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t8[i] = v[q * 8 + i];
+        tc::split8_packed(t8, h4, l4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { hw[q * 4 + i] = h4[i]; lw[q * 4 + i] = l4[i]; }
+    }
+    tc::tmem_st8(taddr, hw);
+    tc::tmem_st8(taddr + 8, lw);
+}
+// epilogue warp: finished TMEM writes (and reads) published to the issuer, one arrival per warp
+__device__ __forceinline__ void epi_signal_tmem(uint64_t* bars, int bar) {
+    tc::tmem_st_wait();
+    tc::tc_fence_before();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bars + bar);
+}
+
+// Epilogue warp groups: sub = warp >> 2.  wh = sub & 1 owns the chunks of index parity wh, half = sub >> 1 owns columns 16*half..16*half+15 (one K = 16
+// step) of each 32-wide chunk, so each chunk is converted by 8 warps.  Nothing here waits for the tensor pipe except the layer-1 completion of a
+// 4-chunk group: the conversions run up to 7 chunks ahead of layer 2 (8 chunk barriers).
 __device__ void epi_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int n3, int n3p, bool first_mlp, const float* __restrict__ rowpre,
                         int prow, const float* __restrict__ b1, const float* __restrict__ b2, float* xy_s, int ldxy, bool accumulate,
                         uint32_t& n_acc, int& ovf) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wq = warp & 3, sub = warp >> 2, wh = sub & 1, half = sub >> 1;
     const int m = wq * 32 + lane;
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+    (void)sm;
     float rb[16];
 #pragma unroll 1
     for (int ch = wh; ch < 16; ch += 2) {
@@ -504,11 +520,12 @@ __device__ void epi_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int n3
         tc_wait(bars, B_D1FULL + ((ch >> 2) & 1), (uint32_t)((ch >> 3) & 1));      // group ch / 4 in D1 buffer (ch / 4) & 1; 2 completions per buffer per MLP: parity restarts at 0
         tc::tc_fence_after();
         float v[16];
-        tc::tmem_ld16(tmem + lane_base + COL_D1 + ((ch >> 2) & 1) * 128 + (ch & 3) * 32 + half * 16, v);
+        const uint32_t col = tmem + lane_base + COL_D1 + ((ch >> 2) & 1) * 128 + (ch & 3) * 32 + half * 16;
+        tc::tmem_ld16(col, v);
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + rb[i], 0.f);
-        // fill j = 12*k + ch/2 of H[wh]: wait for the reader of fill j-1
-        stage_h16(sm, bars, wh, half, m, v, first_mlp && ch < 2, (uint32_t)(((ch >> 1) + 1) & 1), ovf);
+        convert_in_place16(col, v, ovf);
+        epi_signal_tmem(bars, B_CFULL + (ch & 7));
     }
     const bool tl2 = !first_mlp && !accumulate && threadIdx.x == 0;      // timeline of the layer-2 / layer-3 tail (y0 phase, timeline build only)
     TLOG(tl2, 8);
@@ -516,19 +533,26 @@ __device__ void epi_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int n3
     ++n_acc;
     tc::tc_fence_after();
     TLOG(tl2, 9);
+    // relu(D2 + b1) in place; this thread converts K steps sub, sub + 4 (first half) and sub + 8, sub + 12 (second half) of its row
 #pragma unroll 1
-    for (int p = wh; p < 8; p += 2) {
-        float v[16];
-        float4 bq[4];
+    for (int hf = 0; hf < 2; ++hf) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) bq[q] = __ldg(reinterpret_cast<const float4*>(b1 + p * 32 + half * 16) + q);      // four 16-byte loads, in flight under the TMEM load
-        tc::tmem_ld16(tmem + lane_base + COL_D2 + p * 32 + half * 16, v);
+        for (int j = 0; j < 2; ++j) {
+            const int s = hf * 8 + j * 4 + sub;
+            float v[16];
+            float4 bq[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            v[4 * q] = fmaxf(v[4 * q] + bq[q].x, 0.f); v[4 * q + 1] = fmaxf(v[4 * q + 1] + bq[q].y, 0.f);
-            v[4 * q + 2] = fmaxf(v[4 * q + 2] + bq[q].z, 0.f); v[4 * q + 3] = fmaxf(v[4 * q + 3] + bq[q].w, 0.f);
+            for (int q = 0; q < 4; ++q) bq[q] = __ldg(reinterpret_cast<const float4*>(b1 + s * 16) + q);      // four 16-byte loads, in flight under the TMEM load
+            const uint32_t col = tmem + lane_base + COL_D2 + s * 16;
+            tc::tmem_ld16(col, v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                v[4 * q] = fmaxf(v[4 * q] + bq[q].x, 0.f); v[4 * q + 1] = fmaxf(v[4 * q + 1] + bq[q].y, 0.f);
+                v[4 * q + 2] = fmaxf(v[4 * q + 2] + bq[q].z, 0.f); v[4 * q + 3] = fmaxf(v[4 * q + 3] + bq[q].w, 0.f);
+            }
+            convert_in_place16(col, v, ovf);
         }
-        stage_h16(sm, bars, wh, half, m, v, false, (uint32_t)(((p >> 1) + 1) & 1), ovf);        // fill 12k + 8 + p/2
+        epi_signal_tmem(bars, B_L3RDY + hf);
     }
     TLOG(tl2, 19);
     tc_wait(bars, B_ACC, n_acc & 1);                // D3 complete
@@ -715,7 +739,7 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
 
     if (tid == 0) {
         for (int i = 0; i < B_COUNT; ++i) {
-            const int cnt = (i == B_HFULL || i == B_HFULL + 1) ? 8 : (i == B_XFULL || i == B_D3FREE || i == B_GREAD || i == B_HA || i == B_HB) ? 16 : 1;     // arrivals: one per epilogue warp
+            const int cnt = (i == B_HFULL || i == B_HFULL + 1) ? 8 : (i >= B_CFULL && i < B_CFULL + 8) ? 8 : (i == B_XFULL || i == B_D3FREE || i == B_GREAD || i == B_HA || i == B_HB || i == B_L3RDY || i == B_L3RDY + 1) ? 16 : 1;     // arrivals: one per epilogue warp
             tc::mbar_init(bars + i, cnt);
         }
         tc::fence_mbar_init();

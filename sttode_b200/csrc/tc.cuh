@@ -205,9 +205,9 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uin
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate));
 }
-// three split products with A = (a_hi, a_lo) column blocks in TMEM, advancing 8 columns per K = 16 step
-__device__ __forceinline__ void mma_split3_ts(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint64_t b_hi, uint64_t b_lo, uint32_t b_step, uint32_t idesc,
-                                              int nk, bool accumulate_first) {
+// three split products with A = (a_hi, a_lo) column blocks in TMEM (8 columns each per K = 16 step), advancing `a_step` columns per step
+__device__ __forceinline__ void mma_split3_ts(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t a_step, uint64_t b_hi, uint64_t b_lo, uint32_t b_step,
+                                              uint32_t idesc, int nk, bool accumulate_first) {
     uint32_t acc = accumulate_first ? 1u : 0u;
 #pragma unroll 2
     for (int k = 0; k < nk; ++k) {
@@ -215,7 +215,7 @@ __device__ __forceinline__ void mma_split3_ts(uint32_t d_tmem, uint32_t a_hi, ui
         mma_f16_ts(d_tmem, a_hi, b_lo, idesc, 1u);
         mma_f16_ts(d_tmem, a_hi, b_hi, idesc, 1u);
         acc = 1u;
-        a_hi += 8; a_lo += 8; b_hi += b_step; b_lo += b_step;
+        a_hi += a_step; a_lo += a_step; b_hi += b_step; b_lo += b_step;
     }
 }
 // descriptor of an R-row operand image starting at shared-window address `addr`
