@@ -53,7 +53,7 @@ def build(force=False, verbose=False):
     if not force and not is_stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    extra = ["-DSTTODE_TC_TIMELINE"] if os.environ.get("STTODE_TC_TIMELINE") else []
+    extra = ["-DSTTODE_TC_TIMELINE=" + os.environ["STTODE_TC_TIMELINE"]] if os.environ.get("STTODE_TC_TIMELINE") else []
     cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

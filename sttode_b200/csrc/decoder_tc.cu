@@ -39,8 +39,9 @@ DecPackLayout dec_pack_layout(int Tp, int Tf) {
         L.n3[m] = n3[m];
         L.n3p[m] = (n3[m] + 15) / 16 * 16;
         // Layer 1 runs per GROUP of 128 hidden units (four 32-unit chunks: one N = 128 MMA per split product instead of four N = 32 ones at the
-        // small-N issue floor).  Stream of one MLP: lead = W1 rows of group 0 as two K halves [hi, lo, hi, lo] + the first K slice of group 1
-        // [hi, lo]; then per chunk c a (hi, lo) pair of [W2 chunk c image (256 rows x 32 k) | K slice (c+1) & 3 of W1 group ((c+1) >> 2) + 1]:
+        // small-N issue floor).  Stream of one MLP: lead = two ring pairs: W1 rows of group 0, first K half [hi, lo], then [second K half | first K slice
+        // of group 1] [hi, lo] (a ring pair costs one L2 round trip whatever its size: three small lead pairs were three serial round trips per MLP);
+        // then per chunk c a (hi, lo) pair of [W2 chunk c image (256 rows x 32 k) | K slice (c+1) & 3 of W1 group ((c+1) >> 2) + 1]:
         // a group's layer 1 is complete one chunk before its first chunk is consumed.  K1 = 128: four slices of 32 k; K1 = 32: two of 16 k.
         L.lead_blk[m] = 128 * k1[m];            // 128 rows x K1/2 halves
         L.slice_blk[m] = 128 * 2 * (k1[m] == 32 ? 16 : k1[m] / 4);
@@ -90,12 +91,13 @@ __device__ __forceinline__ PackJob pack_job(int j, const sttode_decompose_weight
         const int K1 = (int)L.k1[m], n3 = (int)L.n3[m], n3p = (int)L.n3p[m];
         const uint32_t lead = L.mlp_off[m], SB = L.slice_blk[m], chunk0 = lead + 4 * L.lead_blk[m] + 2 * SB;
         const int nsl = K1 == 32 ? 2 : 4, ksl = K1 / nsl;
-        if (i < 2) {                    // group 0, K half i: hidden rows 0..127, pair columns 128 + i K1/2 ..
-            J = PackJob{mw.w0, 256, 0, 128 + i * (K1 / 2), 128, 128, K1 / 2, lead + (uint32_t)(2 * i) * L.lead_blk[m], lead + (uint32_t)(2 * i + 1) * L.lead_blk[m]};
+        if (i < 2) {                    // group 0, K half i: hidden rows 0..127, pair columns 128 + i K1/2 ..  (lead area: [h0 hi | h0 lo | h1 hi | slice hi | h1 lo | slice lo])
+            const uint32_t LB = L.lead_blk[m];
+            J = PackJob{mw.w0, 256, 0, 128 + i * (K1 / 2), 128, 128, K1 / 2, lead + (i ? 2 * LB : 0u), lead + (i ? 3 * LB + SB : LB)};
         } else if (i < 14) {            // group g = 1..3, K slice s: rides in the lead (g = 1, s = 0) or behind W2 of chunk 4 (g - 1) + s - 1
             const int g = 1 + (i - 2) / 4, sl = (i - 2) & 3, cp = 4 * (g - 1) + sl;
             if (sl >= nsl) J = PackJob{mw.w0, 256, 0, 0, 0, 0, 8, 0, 0};          // no such slice: empty job
-            else if (cp == 0) J = PackJob{mw.w0, 256, g * 128, 128 + sl * ksl, 128, 128, ksl, lead + 4 * L.lead_blk[m], lead + 4 * L.lead_blk[m] + SB};
+            else if (cp == 0) J = PackJob{mw.w0, 256, g * 128, 128 + sl * ksl, 128, 128, ksl, lead + 3 * L.lead_blk[m], lead + 4 * L.lead_blk[m] + SB};
             else {
                 const uint32_t ba = chunk0 + (uint32_t)(2 * (cp - 1)) * L.mlp_blk[m] + 16384;
                 J = PackJob{mw.w0, 256, g * 128, 128 + sl * ksl, 128, 128, ksl, ba, ba + L.mlp_blk[m]};
@@ -183,11 +185,29 @@ constexpr int B_WFULL = 0, B_WFREE = 4, B_D1FULL = 8, B_HFULL = 12, B_ACC = 16, 
 
 // debug timeline: absolute clock64 stamps into the status tail (CTA 0 only, when status[1] == 2)
 // compiled in only with -DSTTODE_TC_TIMELINE (scripts/tc_timing.py); the release build has no trace of it
+// STTODE_TC_TIMELINE=1: phase / GRU-step stamps (TLOG); =2: issuer and epilogue stamps of the y0 MLP (TLOG2, TACC2 accumulates a duration)
 #ifdef STTODE_TC_TIMELINE
 __device__ long long* g_tl = nullptr;
+#endif
+#if defined(STTODE_TC_TIMELINE) && STTODE_TC_TIMELINE == 1
 #define TLOG(cond, slot) do { if (g_tl && blockIdx.x == 0 && (cond)) g_tl[slot] = clock64(); } while (0)
 #else
 #define TLOG(cond, slot) do { (void)(cond); } while (0)
+#endif
+// =3: whole-tile accounting incl. the prologue and the hand-over of the SM to the next CTA (TLOG3)
+#if defined(STTODE_TC_TIMELINE) && STTODE_TC_TIMELINE == 3
+#define TLOG3(cond, slot) do { if (g_tl && blockIdx.x == 0 && (cond)) g_tl[slot] = clock64(); } while (0)
+#else
+#define TLOG3(cond, slot) do { (void)(cond); } while (0)
+#endif
+#if defined(STTODE_TC_TIMELINE) && STTODE_TC_TIMELINE == 2
+#define TLOG2(cond, slot) do { if (g_tl && blockIdx.x == 0 && (cond)) g_tl[slot] = clock64(); } while (0)
+#define TACC2(cond, slot, t0) do { if (g_tl && blockIdx.x == 0 && (cond)) g_tl[slot] += clock64() - (t0); } while (0)
+#define TNOW() clock64()
+#else
+#define TLOG2(cond, slot) do { (void)(cond); } while (0)
+#define TACC2(cond, slot, t0) do { (void)(cond); (void)(t0); } while (0)
+#define TNOW() 0LL
 #endif
 
 __device__ __forceinline__ void tc_wait(uint64_t* bars, int bar, uint32_t parity) {
@@ -214,7 +234,7 @@ __device__ __forceinline__ void epi_signal(uint64_t* bars, int bar) {
 }
 
 // global block sequence: [mlp x0: 40 blocks] [gru1: 8*Tp] [mlp y0: 40] [mlp y1: 40] [mlp x1: 40 when recon]
-// one MLP = 6 lead blocks, 32 chunk blocks, layer-3 pair
+// one MLP = 4 lead blocks, 32 chunk blocks, layer-3 pair
 __device__ __forceinline__ void block_src(const DecPackLayout& lay, int Tp, int i, uint32_t& off, uint32_t& bytes) {
     int m;
     if (i < TC_MLP_BLOCKS) m = 0;
@@ -230,8 +250,8 @@ __device__ __forceinline__ void block_src(const DecPackLayout& lay, int Tp, int 
         else if (i < 2 * TC_MLP_BLOCKS) { m = 2; i -= TC_MLP_BLOCKS; }
         else { m = 3; i -= 2 * TC_MLP_BLOCKS; }
     }
-    if (i < 4) { off = lay.mlp_off[m] + (uint32_t)i * lay.lead_blk[m]; bytes = lay.lead_blk[m]; }
-    else if (i < TC_LEAD) { off = lay.mlp_off[m] + 4 * lay.lead_blk[m] + (uint32_t)(i - 4) * lay.slice_blk[m]; bytes = lay.slice_blk[m]; }
+    if (i < 2) { off = lay.mlp_off[m] + (uint32_t)i * lay.lead_blk[m]; bytes = lay.lead_blk[m]; }
+    else if (i < TC_LEAD) { bytes = lay.lead_blk[m] + lay.slice_blk[m]; off = lay.mlp_off[m] + 2 * lay.lead_blk[m] + (uint32_t)(i - 2) * bytes; }
     else if (i < TC_LEAD + TC_NCH) { off = lay.mlp_off[m] + 4 * lay.lead_blk[m] + 2 * lay.slice_blk[m] + (uint32_t)(i - TC_LEAD) * lay.mlp_blk[m]; bytes = lay.mlp_blk[m]; }
     else { off = lay.l3_off[m] + (uint32_t)(i - TC_LEAD - TC_NCH) * lay.l3_blk[m]; bytes = lay.l3_blk[m]; }
 }
@@ -286,7 +306,9 @@ __device__ void issuer_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int
         tc::tc_fence_after();
     };
     // one elected lane runs the whole phase (waits included): no reconvergence between the MMA groups
+    const bool tl = K1 == 32 && blk0 != 0;          // y0 MLP (timeline build 2 only)
     if (elect_one()) {
+        TLOG2(tl, 19);
         // lead: layer 1 of group 0 (D1 buffer 0: its previous readers finished phases ago), one K half per ring pair
 #pragma unroll 1
         for (int kh = 0; kh < 2; ++kh) {
@@ -294,24 +316,31 @@ __device__ void issuer_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int
             ring_pair(i);
             tc::mma_split3_d(tmem + COL_D1, a_hi(kh * (K1 >> 1)), a_lo(kh * (K1 >> 1)), 256, tc::op_desc(stage(i), 128), tc::op_desc(stage(i + 1), 128), 256,
                              idesc1, K1 >> 5, kh > 0);
-            if (kh == 1) tc::mma_commit(bars + B_D1FULL);
-            tc::mma_commit(bars + B_WFREE + ((i >> 1) & 1));
-        }
-        {   // first K slice of group 1 -> D1 buffer 1 = D3 of the previous MLP: its read-out precedes the epilogue's first staged chunk, so this wait
-            // ends about a thousand cycles before the first layer-2 MMA can go
-            const int i = blk0 + 4;
-            ring_pair(i);
-            if (n_d3 >= 1) { tc_wait(bars, B_D3FREE, (n_d3 - 1) & 1); tc::tc_fence_after(); }
-            tc::mma_split3_d(tmem + COL_D1 + 128, a_hi(0), a_lo(0), 256, tc::op_desc(stage(i), 128), tc::op_desc(stage(i + 1), 128), 256, idesc1, nks, false);
+            if (kh == 1) {
+                tc::mma_commit(bars + B_D1FULL);
+                // first K slice of group 1 (behind the second K half in the same ring pair) -> D1 buffer 1 = D3 of the previous MLP: its read-out precedes
+                // the epilogue's first staged chunk, so this wait ends about a thousand cycles before the first layer-2 MMA can go
+                const uint32_t LB = 128u * (uint32_t)K1;
+                if (n_d3 >= 1) { tc_wait(bars, B_D3FREE, (n_d3 - 1) & 1); tc::tc_fence_after(); }
+                tc::mma_split3_d(tmem + COL_D1 + 128, a_hi(0), a_lo(0), 256, tc::op_desc(stage(i) + LB, 128), tc::op_desc(stage(i + 1) + LB, 128), 256, idesc1, nks,
+                                 false);
+            }
             tc::mma_commit(bars + B_WFREE + ((i >> 1) & 1));
         }
 #pragma unroll 1
         for (int ch = 0; ch < 16; ++ch) {
             const int i0 = blk0 + TC_LEAD + 2 * ch;
+            if (ch == 0) TLOG2(tl, 20);
+            const long long tq0 = TNOW();
             ring_pair(i0);
+            TACC2(tl, 16, tq0);
+            const long long tq1 = TNOW();
             const uint32_t sa = stage(i0), sb = stage(i0 + 1);
             tc_wait(bars, B_CFULL + (ch & 7), (uint32_t)((ch >> 3) & 1));   // relu(D1(ch) + rowpre) converted in place: per K = 16 step [hi 8 columns | lo 8 columns]
             tc::tc_fence_after();
+            TACC2(tl, 17, tq1);
+            TLOG2(tl, ch);
+            const long long tq2 = TNOW();
             const uint32_t ac = tmem + COL_D1 + (uint32_t)((ch >> 2) & 1) * 128u + (uint32_t)(ch & 3) * 32u;
             tc::mma_split3_ts(tmem + COL_D2, ac, ac + 8, 16, tc::op_desc(sa, 256), tc::op_desc(sb, 256), 512, idesc2, 2, ch > 0);
             if (ch == 15) tc::mma_commit(bars + B_ACC);            // D2 complete
@@ -324,6 +353,7 @@ __device__ void issuer_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int
                 if (sl == nsl - 1) tc::mma_commit(bars + B_D1FULL + (g & 1));
             }
             tc::mma_commit(bars + B_WFREE + ((i0 >> 1) & 1));
+            TACC2(tl, 18, tq2);
         }
         // layer 3: A = relu(D2 + b1) converted in place (column block 16 s = K step s: [hi 8 | lo 8]), two halves of 8 steps; D3 = D1 buffer 1, whose last
         // reader (layer 2 of chunks 12..15) precedes these MMAs in the pipe
@@ -334,6 +364,7 @@ __device__ void issuer_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int
             for (int hf = 0; hf < 2; ++hf) {
                 tc_wait(bars, B_L3RDY + hf, n_d3 & 1);
                 tc::tc_fence_after();
+                TLOG2(tl, 21 + hf);
 #pragma unroll 1
                 for (int p = 4 * hf; p < 4 * hf + 4; ++p) {            // 32-wide K piece p: image [hi n3p x 32 | lo n3p x 32] inside block p >> 2
                     const uint32_t st = stage(blk + (p >> 2)) + (uint32_t)(p & 3) * n3p * 128;
@@ -343,6 +374,7 @@ __device__ void issuer_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int
             }
             tc::mma_commit(bars + B_WFREE + ((blk >> 1) & 1));
             tc::mma_commit(bars + B_ACC);                              // D3 complete
+            TLOG2(tl, 23);
         }
     }
     __syncwarp();
@@ -514,11 +546,14 @@ __device__ void epi_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int n3
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
     (void)sm;
     float rb[16];
+    const bool tl2 = !first_mlp && !accumulate && threadIdx.x == 0;      // timeline of the y0 phase (timeline builds only)
+    TLOG2(tl2, 24);
 #pragma unroll 1
     for (int ch = wh; ch < 16; ch += 2) {
         load_rowbias16(rb, rowpre, prow, ch * 32 + half * 16);
         tc_wait(bars, B_D1FULL + ((ch >> 2) & 1), (uint32_t)((ch >> 3) & 1));      // group ch / 4 in D1 buffer (ch / 4) & 1; 2 completions per buffer per MLP: parity restarts at 0
         tc::tc_fence_after();
+        if (ch == 0) TLOG2(tl2, 25);
         float v[16];
         const uint32_t col = tmem + lane_base + COL_D1 + ((ch >> 2) & 1) * 128 + (ch & 3) * 32 + half * 16;
         tc::tmem_ld16(col, v);
@@ -526,13 +561,15 @@ __device__ void epi_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int n3
         for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + rb[i], 0.f);
         convert_in_place16(col, v, ovf);
         epi_signal_tmem(bars, B_CFULL + (ch & 7));
+        if (ch == 0) TLOG2(tl2, 26);
     }
-    const bool tl2 = !first_mlp && !accumulate && threadIdx.x == 0;      // timeline of the layer-2 / layer-3 tail (y0 phase, timeline build only)
     TLOG(tl2, 8);
+    TLOG2(tl2, 27);
     tc_wait(bars, B_ACC, n_acc & 1);                // D2 complete
     ++n_acc;
     tc::tc_fence_after();
     TLOG(tl2, 9);
+    TLOG2(tl2, 28);
     // relu(D2 + b1) in place; this thread converts K steps sub, sub + 4 (first half) and sub + 8, sub + 12 (second half) of its row
 #pragma unroll 1
     for (int hf = 0; hf < 2; ++hf) {
@@ -555,10 +592,12 @@ __device__ void epi_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int n3
         epi_signal_tmem(bars, B_L3RDY + hf);
     }
     TLOG(tl2, 19);
+    TLOG2(tl2, 29);
     tc_wait(bars, B_ACC, n_acc & 1);                // D3 complete
     ++n_acc;
     tc::tc_fence_after();
     TLOG(tl2, 23);
+    TLOG2(tl2, 30);
     for (int c0 = 0; c0 < n3p; c0 += 16) {
         if (((c0 >> 4) & 3) != sub) continue;       // warp-uniform: the four groups take 16-wide column groups in turn
         float v[16];
@@ -580,6 +619,14 @@ __device__ void epi_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int n3
 constexpr float LOG2E = 1.4426950408889634f;
 __device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// 1 / x for x in [1, 2^65] on the FMA pipe (bit-trick seed, relative error 5 %, three Newton steps in residual form: <= 6e-8, the class of rcp.approx).
+// The gate math is bound by the 16-lane XU pipe (3 ex2 + 2 rcp per unit); this moves one of the five to the 128-lane pipes.
+__device__ __forceinline__ float rcp_newton(float x) {
+    float r = __int_as_float(0x7EF311C7 - __float_as_int(x));
+#pragma unroll
+    for (int i = 0; i < 3; ++i) r = fmaf(r, fmaf(-x, r, 1.f), r);
+    return r;
+}
 // GRU constants in shared memory, biases pre-scaled for the ex2-based gates of epi_gru: [-log2e (b_ir+b_hr | b_iz+b_hz) 192 | 2 log2e b_in 96 | 2 log2e b_hn 96 | conv_w 192 | conv_b 32]
 __device__ __forceinline__ float gru_const(const sttode_decompose_weights& w, int i) {
     if (i < 192) return -LOG2E * (w.gru_b_ih[i] + w.gru_b_hh[i]);
@@ -659,9 +706,9 @@ __device__ void epi_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, const 
             const float db = 1.f + ex2_ftz(fminf(fmaf(gz[i], -LOG2E, brz[96 + u + i]), 30.f * LOG2E));
             const float inv = rcp_ftz(da * db);
             const float r = inv * db, zg = inv * da;
-            // tanh(y) = 1 - 2 / (1 + e^(2y));  e^(2y) = inf gives 1, 0 gives -1
-            const float ec = ex2_ftz(fmaf(r, fmaf(gnh[i], 2.f * LOG2E, bhn[u + i]), fmaf(gni[i], 2.f * LOG2E, bin[u + i])));
-            const float n = fmaf(-2.f, rcp_ftz(1.f + ec), 1.f);
+            // tanh(y) = 1 - 2 / (1 + e^(2y));  the exponent is clamped at 64 (tanh = 1 to fp32 long before) so that 1 + e^(2y) stays in rcp_newton's range; 0 gives -1
+            const float ec = ex2_ftz(fminf(fmaf(r, fmaf(gnh[i], 2.f * LOG2E, bhn[u + i]), fmaf(gni[i], 2.f * LOG2E, bin[u + i])), 64.f));
+            const float n = fmaf(-2.f, rcp_newton(1.f + ec), 1.f);
             const float hp = hreg[q * 8 + i];
             hreg[q * 8 + i] = fmaf(hp - n, zg, n);
         }
@@ -735,6 +782,15 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
     const int by0 = TC_MLP_BLOCKS + TC_GRU_STEP_BLOCKS * Tp;
 #ifdef STTODE_TC_TIMELINE
     if (blockIdx.x == 0 && tid == 0) g_tl = status[1] == 2 ? reinterpret_cast<long long*>(status + 2) : nullptr;
+#if STTODE_TC_TIMELINE == 3
+    if (tid == 0 && status[1] == 2) {              // slot 0: entry of CTA 0, slot 9: its SM + 1, slot 8: entry of the next CTA that lands on that SM (same clock)
+        long long* tl = reinterpret_cast<long long*>(status + 2);
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (blockIdx.x == 0) { tl[0] = clock64(); tl[9] = (long long)smid + 1; __threadfence(); }
+        else if (blockIdx.x >= 148 && *reinterpret_cast<volatile long long*>(tl + 9) == (long long)smid + 1 && *reinterpret_cast<volatile long long*>(tl + 8) == 0) tl[8] = clock64();
+    }
+#endif
 #endif
 
     if (tid == 0) {
@@ -788,6 +844,7 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    TLOG3(tid == 0, 1);
 
     if (warp == PRODUCER_WARP) {                    // ---------------- producer
         producer_loop(sm, bars, packed, total_blocks, status[1] == 3, [&](int i, uint32_t& off, uint32_t& bytes) { block_src(lay, Tp, i, off, bytes); });
@@ -801,8 +858,10 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
     } else {                                        // ---------------- epilogue warps
         uint32_t n_acc = 0;
         TLOG(tid == 0, 24);
+        TLOG3(tid == 0, 2);
         epi_mlp(sm, bars, tmem, 2 * Tp, (int)lay.n3p[0], true, rowpre + 0, prow, w0.dec_x.b1, w0.dec_x.b2, xy_s, ldxy, false, n_acc, ovf);
         TLOG(tid == 0, 25);
+        TLOG3(tid == 0, 3);
         if (recon)
             for (int idx = tid; idx < np * 2 * Tp; idx += EPI_THREADS) {
                 const int mm = idx / (2 * Tp), e = idx - mm * 2 * Tp;
@@ -821,15 +880,34 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
         epi_gru(sm, bars, tmem, gb, xy_s, ldxy, BM, Tp, n_acc, ovf);
         epi_barrier();                              // every thread is done reading the conv input before y0 overwrites xy_s
         TLOG(tid == 0, 26);
+        TLOG3(tid == 0, 4);
         epi_mlp(sm, bars, tmem, 2 * Tf, (int)lay.n3p[1], false, rowpre + 512, prow, w0.dec_y.b1, w0.dec_y.b2, xy_s, ldxy, false, n_acc, ovf);
         TLOG(tid == 0, 27);
+        TLOG3(tid == 0, 5);
         epi_mlp(sm, bars, tmem, 2 * Tf, (int)lay.n3p[2], false, rowpre + 1024, prow, w1.dec_y.b1, w1.dec_y.b2, xy_s, ldxy, true, n_acc, ovf);
         TLOG(tid == 0, 28);
-        for (int idx = tid; idx < np * 2 * Tf; idx += EPI_THREADS) {
-            const int mm = idx / (2 * Tf), e = idx - mm * 2 * Tf, cc = e & 1;
-            float v = xy_s[mm * ldxy + e] + cur_s[mm * 4 + cc];
-            if (origin) v += cur_s[mm * 4 + 2 + cc];
-            pred[(pair0 + mm) * 2 * Tf + e] = v;
+        TLOG3(tid == 0, 6);
+        if (!(Tf & 1) && !(reinterpret_cast<uintptr_t>(pred) & 15)) {
+            // thread (row tid / 4, c = tid % 4) writes the 16-byte pieces c, c + 4, .. of its row (8 T_f bytes, contiguous with its neighbours): no index division
+            const int mm = tid >> 2;
+            if (mm < np) {
+                const float cx = cur_s[mm * 4], cy = cur_s[mm * 4 + 1], ox = cur_s[mm * 4 + 2], oy = cur_s[mm * 4 + 3];
+                const float* src = xy_s + mm * ldxy;
+                float4* dst = reinterpret_cast<float4*>(pred + (pair0 + mm) * 2 * Tf);
+#pragma unroll 2
+                for (int j = tid & 3; j < (Tf >> 1); j += 4) {
+                    float4 o = make_float4(src[4 * j] + cx, src[4 * j + 1] + cy, src[4 * j + 2] + cx, src[4 * j + 3] + cy);
+                    if (origin) { o.x += ox; o.y += oy; o.z += ox; o.w += oy; }
+                    dst[j] = o;
+                }
+            }
+        } else {
+            for (int idx = tid; idx < np * 2 * Tf; idx += EPI_THREADS) {
+                const int mm = idx / (2 * Tf), e = idx - mm * 2 * Tf, cc = e & 1;
+                float v = xy_s[mm * ldxy + e] + cur_s[mm * 4 + cc];
+                if (origin) v += cur_s[mm * 4 + 2 + cc];
+                pred[(pair0 + mm) * 2 * Tf + e] = v;
+            }
         }
         if (recon) {
             epi_barrier();
@@ -842,9 +920,11 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
     }
     if (ovf) tile_flags[blockIdx.x] = 1;
     TLOG(tid == 0, 29);
+    TLOG3(tid == 0, 7);
     tc::tc_fence_before();
     __syncthreads();
     if (warp == ISSUER_WARP) tc::tmem_dealloc(tmem, 512);
+    TLOG3(tid == 0 || tid == ISSUER_WARP * 32, tid == 0 ? 10 : 11);
 }
 
 

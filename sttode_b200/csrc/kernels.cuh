@@ -101,7 +101,7 @@ size_t dec_pair_smem_bytes(int Tp, int Tf);
 constexpr int TC_NST = 4;            // weight ring stages
 constexpr int TC_STAGE = 24576;      // bytes per ring stage
 constexpr int TC_NCH = 32;           // ring blocks per MLP layer-1/2 sweep: 16 chunks of 32 hidden units x (hi block, lo block)
-constexpr int TC_LEAD = 6;           // lead blocks of an MLP: layer-1 rows of hidden group 0 as two K halves (hi, lo each) + the first K slice of group 1 (hi, lo)
+constexpr int TC_LEAD = 4;           // lead blocks of an MLP: layer-1 rows of hidden group 0, first K half (hi, lo), then [second K half | first K slice of group 1] (hi, lo)
 constexpr int TC_MLP_BLOCKS = TC_LEAD + TC_NCH + 2;    // per MLP: lead blocks + TC_NCH chunk blocks + layer-3 pair
 constexpr int TC_GRU_BLK = 18432;    // one K = 16 slab of [W_ih | W_hh]: 288 rows (hi + lo), split into an A image (units 0..63) and a B image (units 64..95)
 constexpr int TC_GRU_A = 12288;      //   A slab image: 192 rows (hi 6144 B | lo 6144 B); x-slabs (conv input) in row order [n | r | z], h-slabs in [r | z | n]
