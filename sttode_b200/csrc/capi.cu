@@ -585,7 +585,8 @@ int check_model(const sttode_model_weights* w, bool need_enc = true, bool need_d
 }
 
 size_t past_encoder_ws(int rows, int L) { return ode_ws_bytes(rows, L, STTODE_ODE_EULER); }
-size_t decoder_ws(int rows) { return align_up((size_t)rows * ROWPRE_LD * 4) + align_up(((size_t)rows / 1 + 256) * 4); }
+constexpr int MAX_SLICES = 32;      // copy-overlap slices of the pair tiles (each slice launch of the persistent pair kernel owns one tile counter)
+size_t decoder_ws(int rows) { return align_up((size_t)rows * ROWPRE_LD * 4) + align_up(((size_t)rows / 1 + 256 + MAX_SLICES) * 4); }
 
 int run_encoder(const float* traj, int layout, const int* scene_ptr, const int* row_scene, int n_scenes, int rows, int L, int agents, int T,
                 const sttode_encoder_weights& ew, float* past_feature, float* traj_norm, float* origin, Carver ws, cudaStream_t st);
@@ -817,16 +818,16 @@ int run_decoder(const float* past_feature, const float* traj_norm, const float* 
         const size_t sm_tc = dec_pair_tc_smem_bytes(Tp, Tf), sm_rtc = dec_row_tc_smem_bytes();
         if ((rc = set_smem(k_dec_row_tc, sm_rtc, "k_dec_row_tc"))) return rc;
         if ((rc = set_smem(k_dec_pair_tc, sm_tc, "k_dec_pair_tc"))) return rc;
-        flags = ws.take<int>((size_t)row_tiles + pair_tiles);
+        flags = ws.take<int>((size_t)row_tiles + pair_tiles + MAX_SLICES);      // + one tile counter per slice launch of the persistent pair kernel
         if (!flags) return fail(STTODE_EWORKSPACE, "workspace too small for decoder tile flags");
-        CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int) * ((size_t)row_tiles + pair_tiles), st));
+        CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int) * ((size_t)row_tiles + pair_tiles + MAX_SLICES), st));
         k_dec_row_tc<<<row_tiles, dec_pair_tc_threads(), sm_rtc, st>>>(past_feature, traj_norm, rows, Tp, w->dec[0], w->dec[1], pk, lay, rowpre, flags);
         LAUNCH_CHECK("k_dec_row_tc");
         k_dec_row<<<row_tiles, NTHREADS, sm_row, st>>>(past_feature, traj_norm, rows, Tp, w->dec[0], w->dec[1], rowpre, flags);
         LAUNCH_CHECK("k_dec_row(redo)");
     }
     // ---- pair tiles, in nch slices of whole tiles (one slice unless the caller overlaps the copy-out)
-    const int nch = co ? std::max(1, std::min(co->nch, pair_tiles)) : 1;
+    const int nch = co ? std::max(1, std::min(std::min(co->nch, MAX_SLICES), pair_tiles)) : 1;
     std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
     if (tcores && g_prof.on) {
         std::lock_guard<std::mutex> lock(g_prof.mu);
@@ -836,7 +837,7 @@ int run_decoder(const float* past_feature, const float* traj_norm, const float* 
     }
     // slices are whole waves of one CTA per SM, so only the last slice ends on a partial wave (as the unsliced launch does)
     int sms = 148;
-    if (nch > 1) {
+    {
         int dev = 0;
         CUDA_TRY(cudaGetDevice(&dev));
         CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -847,9 +848,11 @@ int run_decoder(const float* past_feature, const float* traj_norm, const float* 
         if (t1 <= t0) continue;
         // the kernels index the whole batch (pair = tile * 128 + m, agent row = pair / K): every slice gets the base pointers and its first tile
         if (tcores) {
-            k_dec_pair_tc<<<t1 - t0, dec_pair_tc_threads(), dec_pair_tc_smem_bytes(Tp, Tf), st>>>(traj_norm, z, seed, 0ull, rng, rowpre, rs, origin, rows, K, t0, Tp, Tf,
-                                                                                               w->dec[0], w->dec[1], pk, lay, pred, recon,
-                                                                                               (int*)(pk + lay.total), flags + row_tiles + t0);
+            // persistent: one CTA per SM walks the slice's tiles
+            k_dec_pair_tc<<<std::min(t1 - t0, sms), dec_pair_tc_threads(), dec_pair_tc_smem_bytes(Tp, Tf), st>>>(traj_norm, z, seed, 0ull, rng, rowpre, rs, origin, rows, K,
+                                                                                                              t0, Tp, Tf, w->dec[0], w->dec[1], pk, lay, pred, recon,
+                                                                                                              (int*)(pk + lay.total), flags + row_tiles + t0, t1 - t0,
+                                                                                                              flags + row_tiles + pair_tiles + c);
             LAUNCH_CHECK("k_dec_pair_tc");
             if (c == nch - 1 && ev.first) {
                 std::lock_guard<std::mutex> lock(g_prof.mu);

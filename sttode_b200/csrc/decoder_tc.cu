@@ -638,8 +638,11 @@ __device__ __forceinline__ float gru_const(const sttode_decompose_weights& w, in
 
 // Conv1d+ReLU -> GRU over T steps; conv input d = xy_s; final state left in A1 k 32..127 (fp16 hi/lo images).
 // gb: shared-memory constants of gru_const()
+// last_step_work(): run once in the slot where the last step has no next conv image to build (the tensor pipe is busy with h-slabs 4, 5 then):
+// the pair kernel stages the NEXT tile's latent there, into the conv buffer H[T & 1] that is free from that point on
+template <typename LastStepWork>
 __device__ void epi_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, const float* gb, const float* xy_s, int ldxy, int valid_rows, int T,
-                        uint32_t& n_acc, int& ovf) {
+                        uint32_t& n_acc, int& ovf, LastStepWork last_step_work) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wq = warp & 3, sub = warp >> 2;
     const int m = wq * 32 + lane;
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
@@ -728,6 +731,7 @@ __device__ void epi_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, const 
         // H[(t+1) & 1] held the image of step t-1, whose MMAs completed before the half-A completion this warp waited for in the last iteration;
         // the image is published by the B_GREAD arrival below.  It is built while the tensor pipe runs the last two h-slabs of step t.
         if (t + 1 < T) stage_conv(t + 1);
+        else last_step_work();
         TLOG(tl, 1);
         tc_wait(bars, B_ACC, n_acc & 1);            // half A of step t complete
         ++n_acc;
@@ -758,7 +762,7 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
               const float* __restrict__ rowpre, const int* __restrict__ row_scene, const float* __restrict__ origin, int rows, int K,
               int rpt, int Tp, int Tf, sttode_decompose_weights w0, sttode_decompose_weights w1,
               const unsigned char* __restrict__ packed, const __grid_constant__ DecPackLayout lay, float* __restrict__ pred,
-              float* __restrict__ recon, int* __restrict__ status, int* __restrict__ tile_flags) {
+              float* __restrict__ recon, int* __restrict__ status, int* __restrict__ tile_flags, int ntiles, int* __restrict__ tile_counter) {
     extern __shared__ __align__(128) unsigned char sm[];
     const int Tm = Tp > Tf ? Tp : Tf;
     const int ldxy = 2 * Tm + 1;
@@ -766,78 +770,101 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM_XY + ((BM * ldxy * 4 + 15) / 16) * 16);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT + 1);
     float* gb = reinterpret_cast<float*>(bars + B_COUNT + 3);          // GRU/conv constants of block 1 (608 floats)
-    float* cur_s = gb + 608;                                           // [BM][4]: current position (x, y) and scene origin (x, y) of every pair's agent
+    float* cur_base = gb + 608;                                        // 2 x [BM][4]: current position (x, y) and scene origin (x, y) of every pair's agent (this tile / next tile)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wq = warp & 3, sub = (warp >> 2) & 3;
     const int m = wq * 32 + lane;
-    // A tile is 128 CONSECUTIVE (agent, sample) pairs of the whole batch (pair p = agent row p / K, sample p % K): tiles cut on agent
-    // boundaries would leave 128 - 6*20 = 8 of 128 MMA rows idle at K = 20.  `rpt` carries the index of this launch's first tile.
-    const size_t pair0 = ((size_t)rpt + blockIdx.x) * BM;
     const size_t P = (size_t)rows * K;
-    const int np = (int)min((size_t)BM, P - pair0);
-    const int prow = m < np ? (int)((pair0 + m) / K) : -1;
-    int ovf = 0;                                    // set when a staged fp16 operand would leave the fp16 range
     if (rng_state) seed += *rng_state;
     const int total_blocks = TC_MLP_BLOCKS * 3 + TC_GRU_STEP_BLOCKS * Tp + (recon ? TC_MLP_BLOCKS : 0);
     const int by0 = TC_MLP_BLOCKS + TC_GRU_STEP_BLOCKS * Tp;
 #ifdef STTODE_TC_TIMELINE
     if (blockIdx.x == 0 && tid == 0) g_tl = status[1] == 2 ? reinterpret_cast<long long*>(status + 2) : nullptr;
-#if STTODE_TC_TIMELINE == 3
-    if (tid == 0 && status[1] == 2) {              // slot 0: entry of CTA 0, slot 9: its SM + 1, slot 8: entry of the next CTA that lands on that SM (same clock)
-        long long* tl = reinterpret_cast<long long*>(status + 2);
-        unsigned smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        if (blockIdx.x == 0) { tl[0] = clock64(); tl[9] = (long long)smid + 1; __threadfence(); }
-        else if (blockIdx.x >= 148 && *reinterpret_cast<volatile long long*>(tl + 9) == (long long)smid + 1 && *reinterpret_cast<volatile long long*>(tl + 8) == 0) tl[8] = clock64();
-    }
 #endif
+    // Persistent CTA (one per SM): tensor memory, the GRU constants and the CTA itself are set up once (a tile costs ~160 k cycles, a CTA hand-over
+    // + set-up ~8 k).  Tiles are claimed from a counter one tile ahead (tile_s[it & 1] = this tile, tile_s[(it + 1) & 1] = the next one): the SMs do
+    // not run at the same speed (distance to the L2 slices), and a static split of equal tiles lost ~3 % to the slowest SM.
+    int* tile_s = reinterpret_cast<int*>(cur_base + 2 * BM * 4);
+    if (tid == PRODUCER_WARP * 32) tile_s[0] = atomicAdd(tile_counter, 1);
+    __syncthreads();
+    if (warp == ISSUER_WARP) tc::tmem_alloc(tmem_slot, 512);
+    if (warp < ISSUER_WARP)
+        for (int i = tid; i < 608; i += EPI_THREADS) gb[i] = gru_const(w1, i);
+    int ovf_next = 0, it = 0;
+    // latent z of pair tile `t` -> fp16 hi/lo image of 128 rows x 32 k (this thread: k chunk `sub` of row m), plus the current position / scene origin of
+    // the pairs' agents (dependent global loads: row_scene -> origin) for the output phase
+    auto stage_tile_inputs = [&](int t, unsigned char* img_hi, unsigned char* img_lo, float* cur_dst, int& ovf_t) {
+        const size_t t_pair0 = ((size_t)rpt + t) * BM;
+        const int t_np = (int)min((size_t)BM, P - t_pair0);
+        const int t_prow = m < t_np ? (int)((t_pair0 + m) / K) : -1;
+        float v[8];
+        if (m < t_np) {
+            const size_t pair = t_pair0 + m;
+            float4 lo4, hi4;
+            if (z) {
+                lo4 = *reinterpret_cast<const float4*>(z + pair * 32 + sub * 8);
+                hi4 = *reinterpret_cast<const float4*>(z + pair * 32 + sub * 8 + 4);
+            } else {
+                lo4 = latent_normal4(seed, pair_base + pair, sub * 2);
+                hi4 = latent_normal4(seed, pair_base + pair, sub * 2 + 1);
+            }
+            v[0] = lo4.x; v[1] = lo4.y; v[2] = lo4.z; v[3] = lo4.w; v[4] = hi4.x; v[5] = hi4.y; v[6] = hi4.z; v[7] = hi4.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        }
+        track_range(v, ovf_t);
+        tc::store_split8(img_hi, img_lo, 128, m, sub, v);
+        if (sub == 0) {
+            float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t_prow >= 0) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(traj_norm + (size_t)t_prow * 2 * Tp));       // the row the conv-input build reads after the x0 MLP
+                const float2 tn = *reinterpret_cast<const float2*>(traj_norm + ((size_t)t_prow * Tp + Tp - 1) * 2);
+                c4.x = tn.x; c4.y = tn.y;
+                if (origin) { const int sc = row_scene[t_prow]; c4.z = origin[sc * 2]; c4.w = origin[sc * 2 + 1]; }
+            }
+            *reinterpret_cast<float2*>(cur_dst + m * 4) = make_float2(c4.x, c4.y);          // 8-byte aligned (it follows the mbarriers)
+            *reinterpret_cast<float2*>(cur_dst + m * 4 + 2) = make_float2(c4.z, c4.w);
+        }
+    };
+#pragma unroll 1
+    for (;; ++it) {
+    const int tile = tile_s[it & 1];
+    if (tile >= ntiles) break;
+    float* cur_s = cur_base + (it & 1) * BM * 4;
+    unsigned char* znext = sm + SM_H + (Tp & 1) * 16384;           // [hi 8 KB | lo 8 KB]: the conv buffer the last GRU step leaves free
+    // A tile is 128 CONSECUTIVE (agent, sample) pairs of the whole batch (pair p = agent row p / K, sample p % K): tiles cut on agent
+    // boundaries would leave 128 - 6*20 = 8 of 128 MMA rows idle at K = 20.  `rpt` carries the index of this launch's first tile.
+    const size_t pair0 = ((size_t)rpt + tile) * BM;
+    const int np = (int)min((size_t)BM, P - pair0);
+    const int prow = m < np ? (int)((pair0 + m) / K) : -1;
+    int ovf = ovf_next;                             // set when a staged fp16 operand would leave the fp16 range (the latent was staged one tile ahead)
+    ovf_next = 0;
+#if defined(STTODE_TC_TIMELINE) && STTODE_TC_TIMELINE == 3
+    if (g_tl && blockIdx.x == 0 && tid == 0) { g_tl[8] = g_tl[0]; g_tl[0] = clock64(); }      // slot 0: start of this tile, slot 8: start of the previous one
 #endif
 
-    if (tid == 0) {
+    // every phase parity below is a closed-form function of the loop indices of ONE tile: the barriers are re-created per tile.  All their users are
+    // past the barrier that ends the previous tile, and the issuer has waited for the last asynchronous arrivals (tcgen05.commit on the ring barriers).
+    if (tid == PRODUCER_WARP * 32) {                // the producer warp is idle here (ONE thread: inval / init of many barriers by the lanes of a warp at once lost phases on the GPU)
+        tile_s[(it + 1) & 1] = atomicAdd(tile_counter, 1);      // published by the barrier below; its previous value was last read a whole tile ago
         for (int i = 0; i < B_COUNT; ++i) {
             const int cnt = (i == B_HFULL || i == B_HFULL + 1) ? 8 : (i >= B_CFULL && i < B_CFULL + 8) ? 8 : (i == B_XFULL || i == B_D3FREE || i == B_GREAD || i == B_HA || i == B_HB || i == B_L3RDY || i == B_L3RDY + 1) ? 16 : 1;     // arrivals: one per epilogue warp
+            if (it) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(bars + i)) : "memory");
             tc::mbar_init(bars + i, cnt);
         }
         tc::fence_mbar_init();
     }
-    if (warp == ISSUER_WARP) tc::tmem_alloc(tmem_slot, 512);
     if (warp < ISSUER_WARP) {
-        for (int i = tid; i < 608; i += EPI_THREADS) gb[i] = gru_const(w1, i);
-        // latent z -> A1 k chunks 0..3 (this thread: chunk `sub` of row m)
-        {
-            const int kc = sub;
-            float v[8];
-            if (m < np) {
-                const size_t pair = pair0 + m;
-                float4 lo4, hi4;
-                if (z) {
-                    lo4 = *reinterpret_cast<const float4*>(z + pair * 32 + kc * 8);
-                    hi4 = *reinterpret_cast<const float4*>(z + pair * 32 + kc * 8 + 4);
-                } else {
-                    lo4 = latent_normal4(seed, pair_base + pair, kc * 2);
-                    hi4 = latent_normal4(seed, pair_base + pair, kc * 2 + 1);
-                }
-                v[0] = lo4.x; v[1] = lo4.y; v[2] = lo4.z; v[3] = lo4.w; v[4] = hi4.x; v[5] = hi4.y; v[6] = hi4.z; v[7] = hi4.w;
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        // latent z -> A1 k chunks 0..3, current positions -> cur_s: generated here for the CTA's first tile; every later tile finds them staged by the
+        // previous tile's GRU phase (z images in the spare conv buffer: two 8 KB copies)
+        if (it == 0) stage_tile_inputs(tile, sm + SM_A1, sm + SM_A1 + 32768, cur_s, ovf);
+        else
+            for (int i = tid; i < 1024; i += EPI_THREADS) {
+                const int img = i >> 9, o = (i & 511) * 16;
+                *reinterpret_cast<uint4*>(sm + SM_A1 + img * 32768 + o) = *reinterpret_cast<const uint4*>(znext + img * 8192 + o);
             }
-            track_range(v, ovf);
-            tc::store_split8(sm + SM_A1, sm + SM_A1 + 32768, 128, m, kc, v);
-        }
-        // the output phase adds the agent's current position (and the scene origin): fetched now, so the dependent global loads
-        // (row_scene -> origin) are off the tail of the tile (they cost 6.6 k cycles per tile there)
-        if (sub == 0) {
-            float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (prow >= 0) {
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(traj_norm + (size_t)prow * 2 * Tp));       // the row the conv-input build reads after the x0 MLP
-                const float2 tn = *reinterpret_cast<const float2*>(traj_norm + ((size_t)prow * Tp + Tp - 1) * 2);
-                c4.x = tn.x; c4.y = tn.y;
-                if (origin) { const int sc = row_scene[prow]; c4.z = origin[sc * 2]; c4.w = origin[sc * 2 + 1]; }
-            }
-            *reinterpret_cast<float2*>(cur_s + m * 4) = make_float2(c4.x, c4.y);          // cur_s is 8-byte aligned (it follows the mbarriers)
-            *reinterpret_cast<float2*>(cur_s + m * 4 + 2) = make_float2(c4.z, c4.w);
-        }
+        if (sub == 1 && prow >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(traj_norm + (size_t)prow * 2 * Tp));
     }
     tc::fence_proxy_async();
     tc::tc_fence_before();
@@ -855,6 +882,8 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
         issuer_mlp(sm, bars, tmem, 32, (int)lay.n3p[1], by0, n_d3);
         issuer_mlp(sm, bars, tmem, 128, (int)lay.n3p[2], by0 + TC_MLP_BLOCKS, n_d3);
         if (recon) issuer_mlp(sm, bars, tmem, 128, (int)lay.n3p[3], by0 + 2 * TC_MLP_BLOCKS, n_d3);
+        // the commits on the ring's free barriers of the last two pairs have no other waiter: they must have arrived before the barriers are re-created
+        for (int j = (total_blocks >> 1) - 2; j < (total_blocks >> 1); ++j) tc_wait(bars, B_WFREE + (j & 1), (uint32_t)((j >> 1) & 1));
     } else {                                        // ---------------- epilogue warps
         uint32_t n_acc = 0;
         TLOG(tid == 0, 24);
@@ -877,7 +906,10 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
         }
         epi_barrier();
         TLOG(tid == 0, 4);
-        epi_gru(sm, bars, tmem, gb, xy_s, ldxy, BM, Tp, n_acc, ovf);
+        epi_gru(sm, bars, tmem, gb, xy_s, ldxy, BM, Tp, n_acc, ovf, [&] {
+            const int nt = tile_s[(it + 1) & 1];
+            if (nt < ntiles) stage_tile_inputs(nt, znext, znext + 8192, cur_base + ((it + 1) & 1) * BM * 4, ovf_next);
+        });
         epi_barrier();                              // every thread is done reading the conv input before y0 overwrites xy_s
         TLOG(tid == 0, 26);
         TLOG3(tid == 0, 4);
@@ -918,13 +950,15 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
             }
         }
     }
-    if (ovf) tile_flags[blockIdx.x] = 1;
+    if (ovf) tile_flags[tile] = 1;
     TLOG(tid == 0, 29);
     TLOG3(tid == 0, 7);
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == ISSUER_WARP) tc::tmem_dealloc(tmem, 512);
-    TLOG3(tid == 0 || tid == ISSUER_WARP * 32, tid == 0 ? 10 : 11);
+    TLOG3(tid == 0, 10);
+    }   // tile loop
+    tc::tc_fence_after();
+    if (warp == ISSUER_WARP) tc::tmem_dealloc(*tmem_slot, 512);
 }
 
 
@@ -1007,7 +1041,7 @@ k_dec_row_tc(const float* __restrict__ past_feature, const float* __restrict__ t
         }
     } else {                                        // ---------------- epilogue warps
         uint32_t n_acc = 0;
-        epi_gru(sm, bars, tmem, gb, traj_norm + (size_t)row0 * 2 * Tp, 2 * Tp, nrow, Tp, n_acc, ovf);
+        epi_gru(sm, bars, tmem, gb, traj_norm + (size_t)row0 * 2 * Tp, 2 * Tp, nrow, Tp, n_acc, ovf, [] {});
         // past_feature tile -> fp16 hi/lo images (k chunks 4*sub .. 4*sub+3 of row m); safe: every GRU MMA has completed
         {
             const int r = row0 + m;
@@ -1063,7 +1097,7 @@ size_t dec_row_tc_smem_bytes() { return (size_t)SMR_BARS + (B_COUNT + 3) * 8 + 6
 
 size_t dec_pair_tc_smem_bytes(int Tp, int Tf) {
     const int Tm = Tp > Tf ? Tp : Tf;
-    return (size_t)SM_XY + ((size_t)(BM * (2 * Tm + 1) * 4 + 15) / 16) * 16 + (B_COUNT + 3) * 8 + 608 * 4 + BM * 4 * 4;
+    return (size_t)SM_XY + ((size_t)(BM * (2 * Tm + 1) * 4 + 15) / 16) * 16 + (B_COUNT + 3) * 8 + 608 * 4 + 2 * BM * 4 * 4 + 16;
 }
 int dec_pair_tc_threads() { return TC_THREADS; }
 
