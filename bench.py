@@ -364,17 +364,24 @@ def inference_leg(ctx, name, args, steps, warmup):
     ms_max = ctx.max_over_ranks(ms)
 
     # ---- end-to-end leg (host buffers through the C ABI) ------------------------------------------------
-    for i in range(max(1, warmup // 2)):
-        step_host(200 + i)
-    ctx.barrier()
-    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    h0.record()                                                        # device clock on the stream the call uses; the call blocks until its D2H landed
-    for i in range(steps):
-        step_host(2000 + i)
-    h1.record()
-    torch.cuda.synchronize()
-    e2e_s = ctx.max_over_ranks(h0.elapsed_time(h1) * 1e-3)
-    ctx.barrier()
+    # timed in the library's default output mode (that is the headline e2e) and, for the record, in the other one
+    # (sttode_host_output_mode: 0 = sliced D2H copies overlapped with the kernels, 1 = kernels store into the page-locked buffer)
+    default_mode = lib.sttode_host_output_mode(-1)
+    e2e_modes = {}
+    for mode in (1 - default_mode, default_mode):
+        lib.sttode_host_output_mode(mode)
+        for i in range(max(1, warmup // 2)):
+            step_host(200 + i)
+        ctx.barrier()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()                                                    # device clock on the stream the call uses; the call blocks until the predictions are in host memory
+        for i in range(steps):
+            step_host(2000 + i)
+        h1.record()
+        torch.cuda.synchronize()
+        e2e_modes["direct" if mode else "copy"] = ctx.max_over_ranks(h0.elapsed_time(h1) * 1e-3)
+        ctx.barrier()
+    e2e_s = e2e_modes["direct" if default_mode else "copy"]
     lib.sttode_release_host_arena()
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------------
@@ -426,6 +433,8 @@ def inference_leg(ctx, name, args, steps, warmup):
                 "h2d_bytes_per_step": int(traj_h.numel() * 4 + (sp_h.numel() * 4 + rows * 4 if name == "eth" else 0)),
                 "d2h_bytes_per_step": int(pred_h.numel() * 4), "ms_per_step": 1e3 * e2e_s / steps,
                 "api": "sttode_forecast_host (host trajectories in, host predictions out)",
+                "output_mode": "direct" if default_mode else "copy",
+                "ms_per_step_by_output_mode": {k: 1e3 * v / steps for k, v in e2e_modes.items()},
                 "limiter": "host-side D2H: every rank streams its predictions to one host's memory; the device-resident value shows the GPU-side scaling" if world > 1 else None},
         "gpu_launches": int(launches),
         "roofline": roofline,

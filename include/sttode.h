@@ -306,6 +306,10 @@ int sttode_forecast_host(const float *traj_host, int layout, const int *scene_pt
                          int L, int agents, unsigned long long seed, int sample_k, const sttode_model_weights *w,
                          float *pred_host, void *stream);
 void sttode_release_host_arena(void);
+/* How sttode_forecast_host returns the predictions: 0 = device buffer + device-to-host copies of slices overlapped with the decoder kernels,
+ * 1 = the decoder kernels store into the page-locked host buffer directly (host-mapped memory; a pageable `pred_host` goes through the pinned
+ * arena either way).  Returns the previous mode; any other argument only queries.  Initial mode: STTODE_HOST_OUTPUT=copy|direct, else the default. */
+int sttode_host_output_mode(int mode);
 
 /* The latent the decoder kernels draw when `z` is NULL (the reference's `torch.randn_like`, model/STTODE.py:609-616), written out:
  * z[n_pairs, 32] for pairs pair_base .. pair_base + n_pairs - 1 of a batch, seed as passed to sttode_forecast / sttode_decoder_fwd

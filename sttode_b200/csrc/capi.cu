@@ -11,6 +11,10 @@
 #include <algorithm>
 #include "kernels.cuh"
 
+#ifndef STTODE_HOST_OUTPUT_DEFAULT
+#define STTODE_HOST_OUTPUT_DEFAULT 1        // sttode_forecast_host: 0 = sliced D2H copies, 1 = kernels write the page-locked buffer (sttode_host_output_mode)
+#endif
+
 namespace sttode {
 void launch_pmath_rows(int op, const float* x, const float* y, float* out, int rows, int d, float c, cudaStream_t st);
 void launch_pmath_matvec(const float* m, const float* x, float* out, int rows, int d, int dout, float c, cudaStream_t st);
@@ -1271,6 +1275,24 @@ int sttode_forecast(const float* traj, int layout, const int* scene_ptr, const i
                          origin_out, workspace, workspace_bytes, (cudaStream_t)stream, nullptr);
 }
 
+// Where sttode_forecast_host's predictions travel: 0 = device buffer + D2H copies of slices overlapped with the pair kernels, 1 = the kernels write the
+// page-locked host buffer directly (host-mapped memory over PCIe: no slices, no copy stream).  Default from STTODE_HOST_OUTPUT=copy|direct.
+static std::atomic<int> g_host_out_mode{-1};
+static int host_out_mode() {
+    int m = g_host_out_mode.load();
+    if (m < 0) {
+        const char* e = getenv("STTODE_HOST_OUTPUT");
+        m = (e && !strcmp(e, "copy")) ? 0 : (e && !strcmp(e, "direct")) ? 1 : STTODE_HOST_OUTPUT_DEFAULT;
+        g_host_out_mode.store(m);
+    }
+    return m;
+}
+int sttode_host_output_mode(int mode) {
+    const int prev = host_out_mode();
+    if (mode == 0 || mode == 1) g_host_out_mode.store(mode);
+    return prev;
+}
+
 int sttode_forecast_host(const float* traj_host, int layout, const int* scene_ptr_host, int n_scenes, int rows, int L, int agents,
                          unsigned long long seed, int sample_k, const sttode_model_weights* w, float* pred_host, void* stream) {
     int rc;
@@ -1328,6 +1350,16 @@ int sttode_forecast_host(const float* traj_host, int layout, const int* scene_pt
     const int* rs_d = scene_ptr_host ? (const int*)(d + align_up(traj_b) + sp_b) : nullptr;
     float* pred_d = (float*)(d + in_b);
     void* ws_d = d + in_b + align_up(pred_b);
+    if (host_out_mode() == 1) {
+        // direct: the decoder kernels store into the page-locked buffer itself (one launch of the persistent pair kernel, nothing to copy afterwards)
+        void* alias = nullptr;
+        CUDA_TRY(cudaHostGetDevicePointer(&alias, out_pinned ? (void*)pred_host : (void*)g_arena.pin_out, 0));
+        rc = forecast_impl(traj_d, layout, sp_d, rs_d, n_scenes, rows, L, agents, nullptr, seed, sample_k, w, (float*)alias, nullptr, nullptr, nullptr, ws_d, ws_b, st, nullptr);
+        CUDA_TRY(cudaStreamSynchronize(st));        // also on error: the H2D copies above read the shared arena
+        if (rc) return rc;
+        if (!out_pinned) memcpy(pred_host, g_arena.pin_out, pred_b);
+        return 0;
+    }
     // the pair kernels run in slices of whole tiles; the D2H copy of slice i overlaps the kernels of slice i+1 (one slice per ~6 MB of output, at most 16,
     // each slice a whole number of 148-SM waves is not required: slices are large)
     CopyOut co{out_pinned ? (char*)pred_host : g_arena.pin_out, g_arena.copy_stream, g_arena.done,

@@ -920,18 +920,18 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
         TLOG(tid == 0, 28);
         TLOG3(tid == 0, 6);
         if (!(Tf & 1) && !(reinterpret_cast<uintptr_t>(pred) & 15)) {
-            // thread (row tid / 4, c = tid % 4) writes the 16-byte pieces c, c + 4, .. of its row (8 T_f bytes, contiguous with its neighbours): no index division
-            const int mm = tid >> 2;
-            if (mm < np) {
-                const float cx = cur_s[mm * 4], cy = cur_s[mm * 4 + 1], ox = cur_s[mm * 4 + 2], oy = cur_s[mm * 4 + 3];
-                const float* src = xy_s + mm * ldxy;
-                float4* dst = reinterpret_cast<float4*>(pred + (pair0 + mm) * 2 * Tf);
+            // the tile's predictions are ONE contiguous span of np * 8 T_f bytes: consecutive threads write consecutive 16-byte pieces, so every store instruction of a
+            // warp covers 512 contiguous bytes (whole 128-byte lines: this also keeps a host-mapped `pred`, written over PCIe, efficient)
+            const int hp = Tf >> 1;
+            float4* dst = reinterpret_cast<float4*>(pred + pair0 * 2 * Tf);
 #pragma unroll 2
-                for (int j = tid & 3; j < (Tf >> 1); j += 4) {
-                    float4 o = make_float4(src[4 * j] + cx, src[4 * j + 1] + cy, src[4 * j + 2] + cx, src[4 * j + 3] + cy);
-                    if (origin) { o.x += ox; o.y += oy; o.z += ox; o.w += oy; }
-                    dst[j] = o;
-                }
+            for (int idx = tid; idx < np * hp; idx += EPI_THREADS) {
+                const int mm = idx / hp, j = idx - mm * hp;
+                const float* src = xy_s + mm * ldxy + 4 * j;
+                const float cx = cur_s[mm * 4], cy = cur_s[mm * 4 + 1];
+                float4 o = make_float4(src[0] + cx, src[1] + cy, src[2] + cx, src[3] + cy);
+                if (origin) { const float ox = cur_s[mm * 4 + 2], oy = cur_s[mm * 4 + 3]; o.x += ox; o.y += oy; o.z += ox; o.w += oy; }
+                dst[idx] = o;
             }
         } else {
             for (int idx = tid; idx < np * 2 * Tf; idx += EPI_THREADS) {

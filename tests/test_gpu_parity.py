@@ -368,10 +368,17 @@ def test_host_entry_point_chunked_copy_overlap(dev):
     mw = m._weights()
     m._seed = lambda: 77
     want = m.forecast_scenes(obs.to(dev), sp).cpu()
-    for pinned in (False, True):
-        pred_h = torch.empty(rows, 20, 12, 2).pin_memory() if pinned else torch.empty(rows, 20, 12, 2)
-        L.check(L.lib().sttode_forecast_host(obs.data_ptr(), 1, sp.data_ptr(), len(counts), rows, 1, 1, 77, 20, C.byref(mw), pred_h.data_ptr(), L.stream_ptr()))
-        assert torch.equal(pred_h, want)
+    # both output modes (sttode_host_output_mode): sliced D2H copies and decoder kernels storing into the page-locked buffer itself
+    prev = L.lib().sttode_host_output_mode(-1)
+    try:
+        for mode in (0, 1):
+            assert L.lib().sttode_host_output_mode(mode) in (0, 1) and L.lib().sttode_host_output_mode(-1) == mode
+            for pinned in (False, True):
+                pred_h = torch.full((rows, 20, 12, 2), float("nan")).pin_memory() if pinned else torch.full((rows, 20, 12, 2), float("nan"))
+                L.check(L.lib().sttode_forecast_host(obs.data_ptr(), 1, sp.data_ptr(), len(counts), rows, 1, 1, 77, 20, C.byref(mw), pred_h.data_ptr(), L.stream_ptr()))
+                assert torch.equal(pred_h, want), (mode, pinned)
+    finally:
+        L.lib().sttode_host_output_mode(prev)
     # NBA mode: 48 groups of (L = 16 scenes x 11 agents), 10/20 frames
     mn, _ = build_model("nba", 10, 20, 2, dev)
     Lg, groups = 16, 48
