@@ -21,6 +21,6 @@ for rep in range(2):
     L.check(lib.sttode_decoder_timing(L.dptr(buf), 8, 12, 0, out))
     v = list(out)
     t0 = v[0]
-    print("last tile of CTA 0, cycles from the tile's start: prologue done", v[1] - t0, " epilogue: x0 starts", v[2] - t0, " x0 done", v[3] - t0, " gru done", v[4] - t0,
+    print("sixth tile of CTA 0, cycles from the tile's start: prologue done", v[1] - t0, " epilogue: x0 starts", v[2] - t0, " x0 done", v[3] - t0, " gru done", v[4] - t0,
           " y0 done", v[5] - t0, " y1 done", v[6] - t0, " output written", v[7] - t0, " after the tile's last barrier", v[10] - t0,
-          " | tile period (start of the previous tile -> start of this one)", (v[0] - v[8]) if v[8] else None)
+          " | tile period (start of this tile -> start of the next one)", (v[8] - v[0]) if v[8] else None)

@@ -590,7 +590,7 @@ int check_model(const sttode_model_weights* w, bool need_enc = true, bool need_d
 
 size_t past_encoder_ws(int rows, int L) { return ode_ws_bytes(rows, L, STTODE_ODE_EULER); }
 constexpr int MAX_SLICES = 32;      // copy-overlap slices of the pair tiles (each slice launch of the persistent pair kernel owns one tile counter)
-size_t decoder_ws(int rows) { return align_up((size_t)rows * ROWPRE_LD * 4) + align_up(((size_t)rows / 1 + 256 + MAX_SLICES) * 4); }
+size_t decoder_ws(int rows) { return align_up(rowpre_floats(rows) * 4) + align_up(((size_t)rows / 1 + 256 + MAX_SLICES) * 4); }
 
 int run_encoder(const float* traj, int layout, const int* scene_ptr, const int* row_scene, int n_scenes, int rows, int L, int agents, int T,
                 const sttode_encoder_weights& ew, float* past_feature, float* traj_norm, float* origin, Carver ws, cudaStream_t st);
@@ -801,7 +801,7 @@ int run_decoder(const float* past_feature, const float* traj_norm, const float* 
     // pair tiles are 128 consecutive (agent, sample) pairs of the batch, NOT whole agents: at K = 20 that is 6.25 % fewer tiles than 6 agents per tile
     const size_t n_pairs = (size_t)rows * K;
     const int row_tiles = ceil_div(rows, BM), pair_tiles = (int)((n_pairs + BM - 1) / BM);
-    float* rowpre = ws.take<float>((size_t)rows * ROWPRE_LD);
+    float* rowpre = ws.take<float>(rowpre_floats(rows));
     if (!rowpre) return fail(STTODE_EWORKSPACE, "workspace too small for decoder row precompute");
     const size_t sm_row = dec_row_smem_bytes(Tp), sm_pair = dec_pair_smem_bytes(Tp, Tf);
     if ((rc = set_smem(k_dec_row, sm_row, "k_dec_row"))) return rc;

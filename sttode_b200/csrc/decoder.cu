@@ -165,7 +165,7 @@ k_dec_row(const float* __restrict__ past_feature, const float* __restrict__ traj
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int n = nb * 64 + j * 16 + tx;
-                    rowpre[(size_t)r * ROWPRE_LD + p * 512 + n] = acc[i][j] + __ldg(Bv[p] + n);
+                    rowpre[rowpre_off(r, p * 512 + n)] = acc[i][j] + __ldg(Bv[p] + n);
                 }
             }
         }
@@ -217,7 +217,7 @@ __device__ void mlp_phase(const float* A1, int lda, const sttode_mlp3_weights& w
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int n = hc * 32 + j * 16 + tx;
-                const float rb = prow[i] >= 0 ? __ldg(rowpre + (size_t)prow[i] * ROWPRE_LD + n) : 0.f;
+                const float rb = prow[i] >= 0 ? __ldg(rowpre + rowpre_off(prow[i], n)) : 0.f;
                 h1c[m * LDX + j * 16 + tx] = fmaxf(acc1[i][j] + rb, 0.f);
             }
         }
@@ -323,8 +323,8 @@ k_dec_pair(const float* __restrict__ traj_norm, const float* __restrict__ z, uns
     // ---- block 1 Conv1d+GRU -> state1 in zA[:, 32:128]
     gru_phase(xy_s, ldxy, Tp, w1, zA + 32, LDZ, hB, LDH, xt_s, wch);
     // ---- decoder_y of both blocks, summed (prediction += y_hat, model/STTODE.py:338)
-    mlp_phase<32>(zA, LDZ, w0.dec_y, rowpre + 512, prow_s, 2 * Tf, xy_s, ldxy, false, h1c, w2c, w1c);
-    mlp_phase<128>(zA, LDZ, w1.dec_y, rowpre + 1024, prow_s, 2 * Tf, xy_s, ldxy, true, h1c, w2c, w1c);
+    mlp_phase<32>(zA, LDZ, w0.dec_y, rowpre + rowpre_col(512), prow_s, 2 * Tf, xy_s, ldxy, false, h1c, w2c, w1c);
+    mlp_phase<128>(zA, LDZ, w1.dec_y, rowpre + rowpre_col(1024), prow_s, 2 * Tf, xy_s, ldxy, true, h1c, w2c, w1c);
     // pred = (y0 + y1) + cur_location (+ scene origin); the tile is one contiguous span of pred
     for (int idx = tid; idx < np * 2 * Tf; idx += NTHREADS) {
         const int m = idx / (2 * Tf), e = idx - m * 2 * Tf, c = e & 1;
@@ -335,7 +335,7 @@ k_dec_pair(const float* __restrict__ traj_norm, const float* __restrict__ z, uns
     }
     if (recon) {    // reconstruction += block-1 decoder_x (only when the caller wants recover_pre_seq)
         __syncthreads();
-        mlp_phase<128>(zA, LDZ, w1.dec_x, rowpre + 1536, prow_s, 2 * Tp, xy_s, ldxy, false, h1c, w2c, w1c);
+        mlp_phase<128>(zA, LDZ, w1.dec_x, rowpre + rowpre_col(1536), prow_s, 2 * Tp, xy_s, ldxy, false, h1c, w2c, w1c);
         for (int idx = tid; idx < np * 2 * Tp; idx += NTHREADS) {
             const int m = idx / (2 * Tp), e = idx - m * 2 * Tp;
             recon[(pair0 + m) * 2 * Tp + e] += xy_s[m * ldxy + e];

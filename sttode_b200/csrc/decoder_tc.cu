@@ -190,19 +190,19 @@ constexpr int B_WFULL = 0, B_WFREE = 4, B_D1FULL = 8, B_HFULL = 12, B_ACC = 16, 
 __device__ long long* g_tl = nullptr;
 #endif
 #if defined(STTODE_TC_TIMELINE) && STTODE_TC_TIMELINE == 1
-#define TLOG(cond, slot) do { if (g_tl && blockIdx.x == 0 && (cond)) g_tl[slot] = clock64(); } while (0)
+#define TLOG(cond, slot) do { if (blockIdx.x == 0 && (cond)) { long long* tl_ = *const_cast<long long* volatile*>(&g_tl); if (tl_) tl_[slot] = clock64(); } } while (0)
 #else
 #define TLOG(cond, slot) do { (void)(cond); } while (0)
 #endif
 // =3: whole-tile accounting incl. the prologue and the hand-over of the SM to the next CTA (TLOG3)
 #if defined(STTODE_TC_TIMELINE) && STTODE_TC_TIMELINE == 3
-#define TLOG3(cond, slot) do { if (g_tl && blockIdx.x == 0 && (cond)) g_tl[slot] = clock64(); } while (0)
+#define TLOG3(cond, slot) do { if (blockIdx.x == 0 && (cond)) { long long* tl_ = *const_cast<long long* volatile*>(&g_tl); if (tl_) tl_[slot] = clock64(); } } while (0)
 #else
 #define TLOG3(cond, slot) do { (void)(cond); } while (0)
 #endif
 #if defined(STTODE_TC_TIMELINE) && STTODE_TC_TIMELINE == 2
-#define TLOG2(cond, slot) do { if (g_tl && blockIdx.x == 0 && (cond)) g_tl[slot] = clock64(); } while (0)
-#define TACC2(cond, slot, t0) do { if (g_tl && blockIdx.x == 0 && (cond)) g_tl[slot] += clock64() - (t0); } while (0)
+#define TLOG2(cond, slot) do { if (blockIdx.x == 0 && (cond)) { long long* tl_ = *const_cast<long long* volatile*>(&g_tl); if (tl_) tl_[slot] = clock64(); } } while (0)
+#define TACC2(cond, slot, t0) do { if (blockIdx.x == 0 && (cond)) { long long* tl_ = *const_cast<long long* volatile*>(&g_tl); if (tl_) tl_[slot] += clock64() - (t0); } } while (0)
 #define TNOW() clock64()
 #else
 #define TLOG2(cond, slot) do { (void)(cond); } while (0)
@@ -497,10 +497,10 @@ __device__ __forceinline__ void track_range(const float (&v)[N], int& ovf) {
 
 __device__ __forceinline__ void load_rowbias16(float (&rb)[16], const float* __restrict__ rowpre, int prow, int col) {
     if (prow >= 0) {
-        const float4* p = reinterpret_cast<const float4*>(rowpre + (size_t)prow * ROWPRE_LD + col);
+        const float4* p = reinterpret_cast<const float4*>(rowpre + rowpre_off(prow, col));
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float4 r = __ldg(p + q);
+            const float4 r = __ldg(p + q * 128);            // next 4-column group of the same row: 512 floats on
             rb[4 * q] = r.x; rb[4 * q + 1] = r.y; rb[4 * q + 2] = r.z; rb[4 * q + 3] = r.w;
         }
     } else {
@@ -778,9 +778,6 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
     if (rng_state) seed += *rng_state;
     const int total_blocks = TC_MLP_BLOCKS * 3 + TC_GRU_STEP_BLOCKS * Tp + (recon ? TC_MLP_BLOCKS : 0);
     const int by0 = TC_MLP_BLOCKS + TC_GRU_STEP_BLOCKS * Tp;
-#ifdef STTODE_TC_TIMELINE
-    if (blockIdx.x == 0 && tid == 0) g_tl = status[1] == 2 ? reinterpret_cast<long long*>(status + 2) : nullptr;
-#endif
     // Persistent CTA (one per SM): tensor memory, the GRU constants and the CTA itself are set up once (a tile costs ~160 k cycles, a CTA hand-over
     // + set-up ~8 k).  Tiles are claimed from a counter one tile ahead (tile_s[it & 1] = this tile, tile_s[(it + 1) & 1] = the next one): the SMs do
     // not run at the same speed (distance to the L2 slices), and a static split of equal tiles lost ~3 % to the slowest SM.
@@ -840,8 +837,15 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
     const int prow = m < np ? (int)((pair0 + m) / K) : -1;
     int ovf = ovf_next;                             // set when a staged fp16 operand would leave the fp16 range (the latent was staged one tile ahead)
     ovf_next = 0;
-#if defined(STTODE_TC_TIMELINE) && STTODE_TC_TIMELINE == 3
-    if (g_tl && blockIdx.x == 0 && tid == 0) { g_tl[8] = g_tl[0]; g_tl[0] = clock64(); }      // slot 0: start of this tile, slot 8: start of the previous one
+#ifdef STTODE_TC_TIMELINE
+    if (blockIdx.x == 0 && tid == 0) {              // the stamps are taken on CTA 0's SIXTH tile (every SM busy); published to the CTA by the prologue's barrier
+        long long* tl = reinterpret_cast<long long*>(status + 2);
+        const bool on = status[1] == 2;
+        g_tl = on && it == 5 ? tl : nullptr;
+#if STTODE_TC_TIMELINE == 3
+        if (on && (it == 5 || it == 6)) tl[it == 5 ? 0 : 8] = clock64();      // slot 0: start of the stamped tile, slot 8: start of the next one
+#endif
+    }
 #endif
 
     // every phase parity below is a closed-form function of the loop indices of ONE tile: the barriers are re-created per tile.  All their users are
@@ -913,10 +917,10 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
         epi_barrier();                              // every thread is done reading the conv input before y0 overwrites xy_s
         TLOG(tid == 0, 26);
         TLOG3(tid == 0, 4);
-        epi_mlp(sm, bars, tmem, 2 * Tf, (int)lay.n3p[1], false, rowpre + 512, prow, w0.dec_y.b1, w0.dec_y.b2, xy_s, ldxy, false, n_acc, ovf);
+        epi_mlp(sm, bars, tmem, 2 * Tf, (int)lay.n3p[1], false, rowpre + rowpre_col(512), prow, w0.dec_y.b1, w0.dec_y.b2, xy_s, ldxy, false, n_acc, ovf);
         TLOG(tid == 0, 27);
         TLOG3(tid == 0, 5);
-        epi_mlp(sm, bars, tmem, 2 * Tf, (int)lay.n3p[2], false, rowpre + 1024, prow, w1.dec_y.b1, w1.dec_y.b2, xy_s, ldxy, true, n_acc, ovf);
+        epi_mlp(sm, bars, tmem, 2 * Tf, (int)lay.n3p[2], false, rowpre + rowpre_col(1024), prow, w1.dec_y.b1, w1.dec_y.b2, xy_s, ldxy, true, n_acc, ovf);
         TLOG(tid == 0, 28);
         TLOG3(tid == 0, 6);
         if (!(Tf & 1) && !(reinterpret_cast<uintptr_t>(pred) & 15)) {
@@ -943,7 +947,7 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
         }
         if (recon) {
             epi_barrier();
-            epi_mlp(sm, bars, tmem, 2 * Tp, (int)lay.n3p[3], false, rowpre + 1536, prow, w1.dec_x.b1, w1.dec_x.b2, xy_s, ldxy, false, n_acc, ovf);
+            epi_mlp(sm, bars, tmem, 2 * Tp, (int)lay.n3p[3], false, rowpre + rowpre_col(1536), prow, w1.dec_x.b1, w1.dec_x.b2, xy_s, ldxy, false, n_acc, ovf);
             for (int idx = tid; idx < np * 2 * Tp; idx += EPI_THREADS) {
                 const int mm = idx / (2 * Tp), e = idx - mm * 2 * Tp;
                 recon[(pair0 + mm) * 2 * Tp + e] += xy_s[mm * ldxy + e];
@@ -1069,17 +1073,18 @@ k_dec_row_tc(const float* __restrict__ past_feature, const float* __restrict__ t
             const int b = j & 1, p = j >> 1, nb = j & 1;
             tc_wait(bars, B_D1FULL + b, (uint32_t)((j >> 1) & 1));
             tc::tc_fence_after();
-            const float* bp = bias[p] + nb * 256 + sub * 64;
-            float* dst = rowpre + (size_t)(row0 + m) * ROWPRE_LD + p * 512 + nb * 256 + sub * 64;
+            const float4* bp = reinterpret_cast<const float4*>(bias[p] + nb * 256 + sub * 64);
+            float4* dst = reinterpret_cast<float4*>(rowpre + rowpre_off(row0 + m, p * 512 + nb * 256 + sub * 64));      // + 128 per 4-column group; lanes = consecutive rows: 512 contiguous bytes per store
 #pragma unroll 1
             for (int c0 = 0; c0 < 64; c0 += 32) {
                 float v[32];
                 tc::tmem_ld32(tmem + lane_base + b * 256 + sub * 64 + c0, v);
                 if (m < nrow) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        *reinterpret_cast<float4*>(dst + c0 + q * 4) = make_float4(v[q * 4] + __ldg(bp + c0 + q * 4), v[q * 4 + 1] + __ldg(bp + c0 + q * 4 + 1),
-                                                                                   v[q * 4 + 2] + __ldg(bp + c0 + q * 4 + 2), v[q * 4 + 3] + __ldg(bp + c0 + q * 4 + 3));
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 bq = __ldg(bp + (c0 >> 2) + q);
+                        dst[((c0 >> 2) + q) * 128] = make_float4(v[q * 4] + bq.x, v[q * 4 + 1] + bq.y, v[q * 4 + 2] + bq.z, v[q * 4 + 3] + bq.w);
+                    }
                 }
             }
             tc::tc_fence_before();

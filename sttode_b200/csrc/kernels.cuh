@@ -88,6 +88,14 @@ __global__ void k_rows_add(const float* a, long lda, const float* b, long ldb, f
 
 // decoder.cu
 constexpr int ROWPRE_LD = 2048;     // per-row layer-1 partial sums: [P0x | P0y | P1y | P1x], 512 each
+// rowpre lives in HBM in tiles of 128 rows, [tile][column / 4][row % 128][4 floats]: the row kernels hold one row per thread, so a warp's 16-byte stores
+// of one column group land in 512 contiguous bytes (row-major [R][2048] made every store instruction touch 32 half-used sectors: the tensor-core row
+// kernel was bound by the store queue), and the pair kernels' 16-byte loads of neighbouring agents share sectors.  Rows are padded to a multiple of 128.
+__host__ __device__ __forceinline__ size_t rowpre_off(int row, int col) {
+    return (size_t)(row >> 7) * (128 * ROWPRE_LD) + (size_t)(col >> 2) * 512 + (size_t)(row & 127) * 4 + (col & 3);
+}
+__host__ __device__ constexpr size_t rowpre_col(int col0) { return (size_t)(col0 >> 2) * 512; }      // pointer offset of column col0 (a multiple of 4): rowpre_off is linear in it
+inline size_t rowpre_floats(int rows) { return (size_t)((rows + 127) / 128) * 128 * ROWPRE_LD; }
 __global__ void k_dec_row(const float* past_feature, const float* traj_norm, int rows, int Tp, sttode_decompose_weights w0,
                           sttode_decompose_weights w1, float* rowpre, const int* only_flagged);
 __global__ void k_dec_pair(const float* traj_norm, const float* z, unsigned long long seed, unsigned long long pair_base, const unsigned long long* rng_state,
