@@ -128,7 +128,7 @@ int sttode_profile_read(double *total_ms, unsigned long long *launches);
 int sttode_umma_selftest(const float *a, const float *b, float *c, int n, int k, int passes, int swap_lbo_sbo, int *status, void *stream);
 /* Diagnostic: issue `reps` back-to-back tcgen05.mma (M = 128, K = 16, kind::f16, width n) on resident operands; cycles2_dev[0] = clock64 cycles from
  * first issue to completion, [1] = cycles spent in the issue loop (device pointer to two long long). */
-int sttode_umma_bench(int n, int reps, long long *cycles2_dev, void *stream);
+int sttode_umma_bench(int n, int reps, long long *cycles2_dev, void *stream);   /* n | 0x1000: A operand from tensor memory; n | 0x2000: bystander warps on tcgen05.ld / st */
 /* Diagnostic: `reps` GRU-slab-like groups of MMAs (mode 0: 3 x N=192 then 3 x N=96 with distinct hi/lo images, the decoder's order; 1: interleaved;
  * 2 / 3: only the N=192 / N=96 triples; 4: identical operands) with B images of b_rows rows; same outputs as sttode_umma_bench.
  * poll_mode > 0 adds 16 bystander warps waiting on an mbarrier meanwhile (1: every lane polls, 2: one lane per warp, 3: one lane + nanosleep). */

@@ -22,4 +22,4 @@ def run(mode):
     L.check(lib.sttode_decoder_timing(L.dptr(buf), 8, 12, 0, None))
     return ms.value / n.value
 print("normal  k_dec_pair_tc ms:", run(0))
-print("no-copy k_dec_pair_tc ms:", run(3))
+print("no-copy k_dec_pair_tc ms:", run(4))

@@ -15,15 +15,18 @@ torch.cuda.synchronize()
 buf = m.decoder._packed.buf
 lib = L.lib()
 out = (C.c_longlong * 31)()
-L.check(lib.sttode_decoder_timing(L.dptr(buf), 8, 12, 2, None))
-m.forecast_scenes(obs, sp); torch.cuda.synchronize()
-L.check(lib.sttode_decoder_timing(L.dptr(buf), 8, 12, 0, out))
-v = list(out)
-t0 = v[19]
-print("y0 MLP, issuer lane, cycles from the issuer's phase start:")
-print("  chunk loop starts", v[20] - t0, " layer-2 of chunk ch issued at:", [v[c] - t0 for c in range(16)])
-print("  gaps between chunk issues:", [v[c + 1] - v[c] for c in range(15)])
-print("  sums over the 16 chunks: ring wait", v[16], " CFULL wait", v[17], " issue", v[18])
-print("  L3RDY half 0 ok", v[21] - t0, " half 1 ok", v[22] - t0, " all issued", v[23] - t0)
-print("y0 MLP, epilogue thread 0 (same origin): phase start", v[24] - t0, " D1FULL(group 0) ok", v[25] - t0, " chunk 0 converted + signalled", v[26] - t0,
-      " own chunks done", v[27] - t0, " D2 complete", v[28] - t0, " L3RDY signalled", v[29] - t0, " D3 complete", v[30] - t0)
+import sys as _s
+for flag, name in ((2, "with the weight stream"), (6, "weight copies skipped (results invalid)")):
+  L.check(lib.sttode_decoder_timing(L.dptr(buf), 8, 12, flag, None))
+  m.forecast_scenes(obs, sp); torch.cuda.synchronize()
+  L.check(lib.sttode_decoder_timing(L.dptr(buf), 8, 12, 0, out))
+  v = list(out)
+  print("==", name)
+  t0 = v[19]
+  print("y0 MLP, issuer lane, cycles from the issuer's phase start:")
+  print("  chunk loop starts", v[20] - t0, " layer-2 of chunk ch issued at:", [v[c] - t0 for c in range(16)])
+  print("  gaps between chunk issues:", [v[c + 1] - v[c] for c in range(15)])
+  print("  sums over the 16 chunks: ring wait", v[16], " CFULL wait", v[17], " issue", v[18])
+  print("  L3RDY half 0 ok", v[21] - t0, " half 1 ok", v[22] - t0, " all issued", v[23] - t0)
+  print("y0 MLP, epilogue thread 0 (same origin): phase start", v[24] - t0, " D1FULL(group 0) ok", v[25] - t0, " chunk 0 converted + signalled", v[26] - t0,
+        " own chunks done", v[27] - t0, " D2 complete", v[28] - t0, " L3RDY signalled", v[29] - t0, " D3 complete", v[30] - t0)

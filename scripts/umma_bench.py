@@ -11,6 +11,12 @@ for n in (16, 32, 48, 64, 96, 128, 192, 256):
         torch.cuda.synchronize()
         tot, iss = out.tolist()
         print(f"N={n:3d} reps={reps:3d}: total {tot:7d} cyc = {tot / reps:6.1f}/mma   issue loop {iss:7d} = {iss / reps:6.1f}/mma   (ideal {n / 2:.0f})")
+for mode, name in ((0x1000, "A from tensor memory (.ts)"), (0x2000, "A from shared memory, 3 warps on tcgen05.ld/st"), (0x3000, ".ts, 3 warps on tcgen05.ld/st")):
+    for n in (128, 256):
+        L.check(lib.sttode_umma_bench(n | mode, 256, out.data_ptr(), L.stream_ptr()))
+        torch.cuda.synchronize()
+        tot, iss = out.tolist()
+        print(f"{name:48s} N={n:3d}: total {tot / 256:6.1f}/mma   issue loop {iss / 256:6.1f}/mma")
 print("GRU-slab pattern probe (cycles per slab group of 3 x N=192 + 3 x N=96; 448 expected from the per-N rates):")
 for poll, pname in ((0, "no bystanders"), (1, "16 warps, every lane polls an mbarrier"), (2, "16 warps, one lane polls"), (3, "16 warps, one lane polls with nanosleep(100)")):
     for mode, name in ((0, "rz rz rz n n n"), (1, "rz n rz n rz n")):

@@ -21,7 +21,7 @@ void launch_pmath_matvec(const float* m, const float* x, float* out, int rows, i
 void launch_pmath_dist_matrix(const float* x, const float* y, float* out, int b, int n, int d, float c, cudaStream_t st);
 void launch_pmath_elem(int op, const float* x, float* out, size_t n, float clampv, cudaStream_t st);
 int launch_umma_selftest(const float* A, const float* B, float* C, int N, int K, int passes, int swap, int* status, cudaStream_t st);
-int launch_umma_bench(int N, int reps, long long* cycles, cudaStream_t st);
+int launch_umma_bench(int N, int reps, long long* cycles, int mode, cudaStream_t st);
 int launch_umma_pattern(int mode, int brows, int reps, long long* cycles, cudaStream_t st, int poll_mode);
 void launch_oblique_proj(const float* x, float* out, int rows, int d, cudaStream_t st);
 void launch_oblique_dist(const float* p1, const float* p2, float* out, int batch, int n1, int n2, int d, float lo, float hi, cudaStream_t st);
@@ -960,8 +960,11 @@ int sttode_umma_selftest(const float* a, const float* b, float* c, int n, int k,
 }
 
 int sttode_umma_bench(int n, int reps, long long* cycles2_dev, void* stream) {
+    // bits 12, 13 of n select the probe's mode (0x1000: A operand from tensor memory, 0x2000: bystander warps on tcgen05.ld / st)
+    const int mode = (n >> 12) & 3;
+    n &= 0xfff;
     if (!cycles2_dev || n < 16 || n > 256 || n % 16 || reps < 1) return fail(STTODE_EINVAL, "umma_bench: N in [16,256] %%16, reps >= 1");
-    int e = launch_umma_bench(n, reps, cycles2_dev, (cudaStream_t)stream);
+    int e = launch_umma_bench(n, reps, cycles2_dev, mode, (cudaStream_t)stream);
     g_launches.fetch_add(1);
     if (e) return fail(STTODE_ECUDA, "umma_bench launch: %s", cudaGetErrorString((cudaError_t)e));
     return 0;

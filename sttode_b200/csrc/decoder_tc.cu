@@ -840,7 +840,7 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
 #ifdef STTODE_TC_TIMELINE
     if (blockIdx.x == 0 && tid == 0) {              // the stamps are taken on CTA 0's SIXTH tile (every SM busy); published to the CTA by the prologue's barrier
         long long* tl = reinterpret_cast<long long*>(status + 2);
-        const bool on = status[1] == 2;
+        const bool on = (status[1] & 3) == 2;
         g_tl = on && it == 5 ? tl : nullptr;
 #if STTODE_TC_TIMELINE == 3
         if (on && (it == 5 || it == 6)) tl[it == 5 ? 0 : 8] = clock64();      // slot 0: start of the stamped tile, slot 8: start of the next one
@@ -878,7 +878,7 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
     TLOG3(tid == 0, 1);
 
     if (warp == PRODUCER_WARP) {                    // ---------------- producer
-        producer_loop(sm, bars, packed, total_blocks, status[1] == 3, [&](int i, uint32_t& off, uint32_t& bytes) { block_src(lay, Tp, i, off, bytes); });
+        producer_loop(sm, bars, packed, total_blocks, (status[1] & 4) != 0, [&](int i, uint32_t& off, uint32_t& bytes) { block_src(lay, Tp, i, off, bytes); });
     } else if (warp == ISSUER_WARP) {               // ---------------- issuer
         uint32_t n_d3 = 0;
         issuer_mlp(sm, bars, tmem, 32, (int)lay.n3p[0], 0, n_d3);

@@ -106,14 +106,17 @@ k_umma_selftest(const float* __restrict__ A, const float* __restrict__ B, float*
 
 // Issue-rate probe: `reps` back-to-back tcgen05.mma (M = 128, K = 16, kind::f16) of width N on resident zero operands, timed with
 // clock64 from the first issue to the mbarrier completion of the trailing commit.  cycles[0] = total, cycles[1] = issue loop only.
-__global__ void __launch_bounds__(128, 1) k_umma_bench(int N, int reps, long long* __restrict__ cycles) {
+// mode bit 0: A operand from tensor memory (the `.ts` form the decoder's MLP layers 2 / 3 use); bit 1: warps 1..3 read / write other tensor-memory
+// columns (tcgen05.ld / st) for the whole run, as the decoder's epilogue warps do while the MMAs execute.
+__global__ void __launch_bounds__(128, 1) k_umma_bench(int N, int reps, long long* __restrict__ cycles, int mode) {
     extern __shared__ __align__(128) unsigned char sm[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm + (128 + 256) * 32);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    volatile int* stop = reinterpret_cast<volatile int*>(bar + 2);
     const int tid = threadIdx.x, warp = tid >> 5;
     for (int i = tid; i < (128 + 256) * 32 / 4; i += 128) reinterpret_cast<uint32_t*>(sm)[i] = 0;
-    if (warp == 0) tc::tmem_alloc(tmem_slot, 256);
-    if (tid == 0) { tc::mbar_init(bar, 1); tc::fence_mbar_init(); }
+    if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
+    if (tid == 0) { tc::mbar_init(bar, 1); tc::fence_mbar_init(); *stop = 0; }
     tc::fence_proxy_async();
     tc::tc_fence_before();
     __syncthreads();
@@ -123,17 +126,30 @@ __global__ void __launch_bounds__(128, 1) k_umma_bench(int N, int reps, long lon
         const uint32_t idesc = tc::make_idesc_f16(N);
         const uint64_t da = tc::op_desc(tc::smem_u32(sm), 128), db = tc::op_desc(tc::smem_u32(sm) + 128 * 32, N);
         const long long t0 = clock64();
-        for (int i = 0; i < reps; ++i) tc::mma_f16_nc(tmem, da, db, idesc, 1u);
+        if (mode & 1) for (int i = 0; i < reps; ++i) tc::mma_f16_ts(tmem, tmem + 256, db, idesc, 1u);
+        else          for (int i = 0; i < reps; ++i) tc::mma_f16_nc(tmem, da, db, idesc, 1u);
         const long long t1 = clock64();
         tc::mma_commit(bar);
         tc::mbar_wait(bar, 0);
         const long long t2 = clock64();
         cycles[0] = t2 - t0;
         cycles[1] = t1 - t0;
+        *stop = 1;
+    } else if ((mode & 2) && warp >= 1) {
+        const uint32_t col = tmem + ((uint32_t)(warp * 32) << 16) + 320 + (uint32_t)warp * 32;      // own lanes, columns no MMA touches
+        float v[16];
+        uint32_t w8[8];
+        while (!*stop) {
+            tc::tmem_ld16(col, v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w8[i] = __float_as_uint(v[i] + v[8 + i]);
+            tc::tmem_st8(col, w8);
+            tc::tmem_st_wait();
+        }
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, 256);
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
 // Pattern probe: `reps` GRU-like slabs of 6 MMAs (3 x N = 192 into D0, 3 x N = 96 into D1) with distinct hi/lo operand images, B images of
@@ -201,9 +217,9 @@ int launch_umma_pattern(int mode, int brows, int reps, long long* cycles, cudaSt
     return (int)cudaGetLastError();
 }
 
-int launch_umma_bench(int N, int reps, long long* cycles, cudaStream_t st) {
+int launch_umma_bench(int N, int reps, long long* cycles, int mode, cudaStream_t st) {
     const size_t smem = (128 + 256) * 32 + 64;
-    k_umma_bench<<<1, 128, smem, st>>>(N, reps, cycles);
+    k_umma_bench<<<1, 128, smem, st>>>(N, reps, cycles, mode);
     return (int)cudaGetLastError();
 }
 
