@@ -812,6 +812,7 @@ int run_decoder(const float* past_feature, const float* traj_norm, const float* 
     DecPackLayout lay{};
     const unsigned char* pk = (const unsigned char*)w->dec_packed;
     int* flags = nullptr;
+    int y_first = 0;
     if (!tcores) {                                  // FP32-FFMA decoder
         k_dec_row<<<row_tiles, NTHREADS, sm_row, st>>>(past_feature, traj_norm, rows, Tp, w->dec[0], w->dec[1], rowpre, nullptr);
         LAUNCH_CHECK("k_dec_row");
@@ -819,7 +820,10 @@ int run_decoder(const float* past_feature, const float* traj_norm, const float* 
         // Tensor-core decoder.  Its fp16 hi/lo operands cover |v| < 65504; a tile that stages anything larger raises its flag and is
         // recomputed by the FP32 kernel right after (a CTA of the redo launch exits at once when its flag is clear).
         lay = dec_pack_layout(Tp, Tf);
-        const size_t sm_tc = dec_pair_tc_smem_bytes(Tp, Tf), sm_rtc = dec_row_tc_smem_bytes();
+        // phase order x0, y0, GRU, y1 with a third ring slot (decoder_tc.cu) when y0's own output buffer fits the 227 KB; STTODE_DEC_Y_FIRST=0 forces the other order
+        static const bool y_first_allowed = [] { const char* e = getenv("STTODE_DEC_Y_FIRST"); return !(e && e[0] == '0'); }();
+        y_first = y_first_allowed && dec_pair_tc_smem_bytes(Tp, Tf, 1) <= 227 * 1024 ? 1 : 0;
+        const size_t sm_tc = dec_pair_tc_smem_bytes(Tp, Tf, y_first), sm_rtc = dec_row_tc_smem_bytes();
         if ((rc = set_smem(k_dec_row_tc, sm_rtc, "k_dec_row_tc"))) return rc;
         if ((rc = set_smem(k_dec_pair_tc, sm_tc, "k_dec_pair_tc"))) return rc;
         flags = ws.take<int>((size_t)row_tiles + pair_tiles + MAX_SLICES);      // + one tile counter per slice launch of the persistent pair kernel
@@ -853,10 +857,10 @@ int run_decoder(const float* past_feature, const float* traj_norm, const float* 
         // the kernels index the whole batch (pair = tile * 128 + m, agent row = pair / K): every slice gets the base pointers and its first tile
         if (tcores) {
             // persistent: one CTA per SM walks the slice's tiles
-            k_dec_pair_tc<<<std::min(t1 - t0, sms), dec_pair_tc_threads(), dec_pair_tc_smem_bytes(Tp, Tf), st>>>(traj_norm, z, seed, 0ull, rng, rowpre, rs, origin, rows, K,
+            k_dec_pair_tc<<<std::min(t1 - t0, sms), dec_pair_tc_threads(), dec_pair_tc_smem_bytes(Tp, Tf, y_first), st>>>(traj_norm, z, seed, 0ull, rng, rowpre, rs, origin, rows, K,
                                                                                                               t0, Tp, Tf, w->dec[0], w->dec[1], pk, lay, pred, recon,
                                                                                                               (int*)(pk + lay.total), flags + row_tiles + t0, t1 - t0,
-                                                                                                              flags + row_tiles + pair_tiles + c);
+                                                                                                              flags + row_tiles + pair_tiles + c, y_first);
             LAUNCH_CHECK("k_dec_pair_tc");
             if (c == nch - 1 && ev.first) {
                 std::lock_guard<std::mutex> lock(g_prof.mu);

@@ -183,6 +183,21 @@ constexpr int B_WFULL = 0, B_WFREE = 4, B_D1FULL = 8, B_HFULL = 12, B_ACC = 16, 
               B_GREAD = 20, B_HA = 21, B_HB = 22, B_CFULL = 23, B_L3RDY = 31, B_COUNT = 33;    // GRU: half-A accumulators read + next conv image staged / units 0..63 / units 64..95 of the new state staged
 // B_CFULL + (ch & 7): hidden chunk ch converted in place to an A operand in TMEM (8 arrivals); B_L3RDY + s: half s of relu(D2 + b1) converted (16 arrivals)
 
+// Weight ring.  Blocks travel in PAIRS (2 stages of TC_STAGE bytes, one full / one free mbarrier per slot).  Pairs [0, n3) of a tile rotate over THREE
+// slots, every later pair alternates over slots 0 and 1: the third slot is the state half of A1 (k chunks 4..15 of the hi and of the lo image, 24 KB each),
+// which is idle while the two K1 = 32 MLPs run before the GRU (phase order x0, y0, GRU, y1).  A pair is requested when the previous occupant of its slot
+// has been consumed, and a 40 KB pair takes ~2 k cycles from L2 against 0.87 k of MMA work per chunk: with two slots every chunk waited for its weights.
+// n3 = 0 is the plain two-slot ring (row kernel; pair kernel when the separate y buffer does not fit).  slot / use index are closed forms of the pair index.
+// The issuing thread runs these between its waits and its MMAs, one dependent instruction every ~5 cycles: no divisions (a first version with p / 3 and
+// (n3 - slot + 2) / 3 in here cost 4 % of the kernel).
+struct RingCfg { int n3, c30, c31; };               // c3s = uses of slot s by the three-slot pairs = (n3 - s + 2) / 3
+__host__ __device__ __forceinline__ RingCfg make_ring_cfg(int n3) { return RingCfg{n3, (n3 + 2) / 3, (n3 + 1) / 3}; }
+__device__ __forceinline__ void ring_slot(const RingCfg& rc, int p, int& slot, int& use) {
+    if (p < rc.n3) { use = (p * 0xAAAB) >> 17; slot = p - 3 * use; }                    // p / 3, p % 3 for p < 32768
+    else { const int q = p - rc.n3; slot = q & 1; use = (slot ? rc.c31 : rc.c30) + (q >> 1); }
+}
+__device__ __forceinline__ int ring_stage_off(int slot, int half) { return slot < 2 ? SM_RING + (2 * slot + half) * TC_STAGE : SM_A1 + 8192 + half * 32768; }
+
 // debug timeline: absolute clock64 stamps into the status tail (CTA 0 only, when status[1] == 2)
 // compiled in only with -DSTTODE_TC_TIMELINE (scripts/tc_timing.py); the release build has no trace of it
 // STTODE_TC_TIMELINE=1: phase / GRU-step stamps (TLOG); =2: issuer and epilogue stamps of the y0 MLP (TLOG2, TACC2 accumulates a duration)
@@ -233,22 +248,20 @@ __device__ __forceinline__ void epi_signal(uint64_t* bars, int bar) {
     if ((threadIdx.x & 31) == 0) mbar_arrive(bars + bar);
 }
 
-// global block sequence: [mlp x0: 40 blocks] [gru1: 8*Tp] [mlp y0: 40] [mlp y1: 40] [mlp x1: 40 when recon]
+// global block sequence: [mlp x0: 38 blocks] [mlp y0: 38 when y_first] [gru1: 8*Tp] [mlp y0: 38 otherwise] [mlp y1: 38] [mlp x1: 38 when recon]
 // one MLP = 4 lead blocks, 32 chunk blocks, layer-3 pair
-__device__ __forceinline__ void block_src(const DecPackLayout& lay, int Tp, int i, uint32_t& off, uint32_t& bytes) {
+__device__ __forceinline__ void block_src(const DecPackLayout& lay, int Tp, int y_first, int i, uint32_t& off, uint32_t& bytes) {
     int m;
-    if (i < TC_MLP_BLOCKS) m = 0;
-    else {
-        i -= TC_MLP_BLOCKS;
-        if (i < TC_GRU_STEP_BLOCKS * Tp) {          // the same 8 blocks every step
-            gru_block(i & 7, off, bytes);
-            off += lay.gru_off[1];
-            return;
-        }
-        i -= TC_GRU_STEP_BLOCKS * Tp;
-        if (i < TC_MLP_BLOCKS) m = 1;
-        else if (i < 2 * TC_MLP_BLOCKS) { m = 2; i -= TC_MLP_BLOCKS; }
-        else { m = 3; i -= 2 * TC_MLP_BLOCKS; }
+    const int gru0 = y_first ? 2 * TC_MLP_BLOCKS : TC_MLP_BLOCKS, ngru = TC_GRU_STEP_BLOCKS * Tp;
+    if (i < gru0) { m = i < TC_MLP_BLOCKS ? 0 : 1; if (m) i -= TC_MLP_BLOCKS; }
+    else if (i < gru0 + ngru) {                     // the same 8 blocks every step
+        gru_block((i - gru0) & 7, off, bytes);
+        off += lay.gru_off[1];
+        return;
+    } else {
+        i -= gru0 + ngru;
+        m = y_first ? 2 : 1;                        // MLPs after the GRU: (y0,) y1, x1
+        while (i >= TC_MLP_BLOCKS) { i -= TC_MLP_BLOCKS; ++m; }
     }
     if (i < 2) { off = lay.mlp_off[m] + (uint32_t)i * lay.lead_blk[m]; bytes = lay.lead_blk[m]; }
     else if (i < TC_LEAD) { bytes = lay.lead_blk[m] + lay.slice_blk[m]; off = lay.mlp_off[m] + 2 * lay.lead_blk[m] + (uint32_t)(i - 2) * bytes; }
@@ -260,21 +273,22 @@ __device__ __forceinline__ void block_src(const DecPackLayout& lay, int Tp, int 
 // The ring is managed in PAIRS of stages (every phase starts at an even block index and uses blocks two at a time):
 // one full / one free mbarrier per pair halves the number of barrier hand-offs on the issuer's critical path.
 template <typename SrcFn>
-__device__ void producer_loop(unsigned char* sm, uint64_t* bars, const unsigned char* __restrict__ packed, int total_blocks, int dbg_nocopy,
+__device__ void producer_loop(unsigned char* sm, uint64_t* bars, const unsigned char* __restrict__ packed, int total_blocks, int dbg_nocopy, const RingCfg rc,
                               SrcFn src_of) {
 #pragma unroll 1
     for (int j = 0; j < (total_blocks >> 1); ++j) {
-        const int d = j & 1;
+        int slot, use;
+        ring_slot(rc, j, slot, use);
         uint32_t off0, bytes0, off1, bytes1;
         src_of(2 * j, off0, bytes0);                // address arithmetic first: nothing but the copies follows the wait
         src_of(2 * j + 1, off1, bytes1);
-        if (j >= 2) tc_wait(bars, B_WFREE + d, (uint32_t)(((j >> 1) - 1) & 1));
+        if (use >= 1) tc_wait(bars, B_WFREE + slot, (uint32_t)((use - 1) & 1));      // the slot's previous occupant has been consumed
         if (elect_one()) {
-            if (dbg_nocopy) mbar_arrive(bars + B_WFULL + d);          // debug: timing without the weight stream (results invalid)
+            if (dbg_nocopy) mbar_arrive(bars + B_WFULL + slot);       // debug: timing without the weight stream (results invalid)
             else {
-                tc::mbar_arrive_expect_tx(bars + B_WFULL + d, bytes0 + bytes1);
-                tc::bulk_g2s(sm + SM_RING + (2 * d) * TC_STAGE, packed + off0, bytes0, bars + B_WFULL + d);
-                tc::bulk_g2s(sm + SM_RING + (2 * d + 1) * TC_STAGE, packed + off1, bytes1, bars + B_WFULL + d);
+                tc::mbar_arrive_expect_tx(bars + B_WFULL + slot, bytes0 + bytes1);
+                tc::bulk_g2s(sm + ring_stage_off(slot, 0), packed + off0, bytes0, bars + B_WFULL + slot);
+                tc::bulk_g2s(sm + ring_stage_off(slot, 1), packed + off1, bytes1, bars + B_WFULL + slot);
             }
         }
         __syncwarp();
@@ -293,17 +307,28 @@ __device__ __forceinline__ uint32_t ring_wait(unsigned char* sm, uint64_t* bars,
 // Layer 1 runs per group of 128 hidden units (chunks 4g..4g+3) into one of two 128-column D1 buffers, and well ahead of layer 2: group 0 from the
 // lead blocks, group g >= 1 in K slices that ride behind W2 of chunks 4(g-1)-1 .. (complete at least one chunk before chunk 4g is consumed), so the
 // epilogue always has a finished D1 to work on while the tensor pipe runs layer 2.  D3 aliases the second D1 buffer (free once chunk 15 is staged).
-__device__ void issuer_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int K1, int n3p, int blk0, uint32_t& n_d3) {
+template <int K1>
+__device__ void issuer_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int n3p, int blk0, uint32_t& n_d3, const RingCfg rc) {
     const uint32_t a1 = tc::smem_u32(sm + SM_A1);
     const uint32_t idesc1 = tc::make_idesc_f16(128), idesc2 = tc::make_idesc_f16(256), idesc3 = tc::make_idesc_f16(n3p);
-    const int nsl = K1 == 32 ? 2 : 4, nks = (K1 >> 4) / nsl;              // K slices per group, K = 16 steps per slice
+    constexpr int nsl = K1 == 32 ? 2 : 4, nks = (K1 >> 4) / nsl;          // K slices per group, K = 16 steps per slice
     // A operand of slice / half starting at pair column k0: A1 k chunk k0 / 8 (2048 B per chunk), lo image 32 KB behind
     auto a_hi = [&](int k0) { return tc::op_desc(a1 + (uint32_t)(k0 >> 3) * 2048u, 128); };
     auto a_lo = [&](int k0) { return tc::op_desc(a1 + 32768u + (uint32_t)(k0 >> 3) * 2048u, 128); };
-    auto stage = [&](int i) { return tc::smem_u32(sm + SM_RING + (i & 3) * TC_STAGE); };
-    auto ring_pair = [&](int i) {                                          // blocks i, i + 1 (i even) resident
-        tc_wait(bars, B_WFULL + ((i >> 1) & 1), (uint32_t)((i >> 2) & 1));
+    const uint32_t sm0 = tc::smem_u32(sm);
+    auto st = [&](int slot, int half) { return sm0 + (uint32_t)ring_stage_off(slot, half); };      // stage address of a slot
+    // Ring cursor: the 19 pairs of an MLP are consecutive and lie in ONE regime (three- or two-slot rotation), so slot and use index advance by a compare and an
+    // add per pair.  The issuing thread runs one dependent instruction every ~5 cycles and is what paces the tensor pipe whenever it is not back-pressured:
+    // everything it executes between a wait and its MMAs is kept to a minimum.
+    int cslot, cuse;
+    ring_slot(rc, blk0 >> 1, cslot, cuse);
+    const int cns = (blk0 >> 1) < rc.n3 ? 3 : 2;
+    auto ring_pair = [&]() {                                               // next pair resident -> its slot; the cursor moves on
+        const int slot = cslot;
+        tc_wait(bars, B_WFULL + slot, (uint32_t)(cuse & 1));
         tc::tc_fence_after();
+        if (++cslot == cns) { cslot = 0; ++cuse; }
+        return slot;
     };
     // one elected lane runs the whole phase (waits included): no reconvergence between the MMA groups
     const bool tl = K1 == 32 && blk0 != 0;          // y0 MLP (timeline build 2 only)
@@ -312,9 +337,8 @@ __device__ void issuer_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int
         // lead: layer 1 of group 0 (D1 buffer 0: its previous readers finished phases ago), one K half per ring pair
 #pragma unroll 1
         for (int kh = 0; kh < 2; ++kh) {
-            const int i = blk0 + 2 * kh;
-            ring_pair(i);
-            tc::mma_split3_d(tmem + COL_D1, a_hi(kh * (K1 >> 1)), a_lo(kh * (K1 >> 1)), 256, tc::op_desc(stage(i), 128), tc::op_desc(stage(i + 1), 128), 256,
+            const int sl_ = ring_pair();
+            tc::mma_split3_d(tmem + COL_D1, a_hi(kh * (K1 >> 1)), a_lo(kh * (K1 >> 1)), 256, tc::op_desc(st(sl_, 0), 128), tc::op_desc(st(sl_, 1), 128), 256,
                              idesc1, K1 >> 5, kh > 0);
             if (kh == 1) {
                 tc::mma_commit(bars + B_D1FULL);
@@ -322,20 +346,19 @@ __device__ void issuer_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int
                 // the epilogue's first staged chunk, so this wait ends about a thousand cycles before the first layer-2 MMA can go
                 const uint32_t LB = 128u * (uint32_t)K1;
                 if (n_d3 >= 1) { tc_wait(bars, B_D3FREE, (n_d3 - 1) & 1); tc::tc_fence_after(); }
-                tc::mma_split3_d(tmem + COL_D1 + 128, a_hi(0), a_lo(0), 256, tc::op_desc(stage(i) + LB, 128), tc::op_desc(stage(i + 1) + LB, 128), 256, idesc1, nks,
+                tc::mma_split3_d(tmem + COL_D1 + 128, a_hi(0), a_lo(0), 256, tc::op_desc(st(sl_, 0) + LB, 128), tc::op_desc(st(sl_, 1) + LB, 128), 256, idesc1, nks,
                                  false);
             }
-            tc::mma_commit(bars + B_WFREE + ((i >> 1) & 1));
+            tc::mma_commit(bars + B_WFREE + sl_);
         }
 #pragma unroll 1
         for (int ch = 0; ch < 16; ++ch) {
-            const int i0 = blk0 + TC_LEAD + 2 * ch;
             if (ch == 0) TLOG2(tl, 20);
             const long long tq0 = TNOW();
-            ring_pair(i0);
+            const int sl_ = ring_pair();
             TACC2(tl, 16, tq0);
             const long long tq1 = TNOW();
-            const uint32_t sa = stage(i0), sb = stage(i0 + 1);
+            const uint32_t sa = st(sl_, 0), sb = st(sl_, 1);
             tc_wait(bars, B_CFULL + (ch & 7), (uint32_t)((ch >> 3) & 1));   // relu(D1(ch) + rowpre) converted in place: per K = 16 step [hi 8 columns | lo 8 columns]
             tc::tc_fence_after();
             TACC2(tl, 17, tq1);
@@ -352,14 +375,13 @@ __device__ void issuer_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int
                                  nks, sl > 0);
                 if (sl == nsl - 1) tc::mma_commit(bars + B_D1FULL + (g & 1));
             }
-            tc::mma_commit(bars + B_WFREE + ((i0 >> 1) & 1));
+            tc::mma_commit(bars + B_WFREE + sl_);
             TACC2(tl, 18, tq2);
         }
         // layer 3: A = relu(D2 + b1) converted in place (column block 16 s = K step s: [hi 8 | lo 8]), two halves of 8 steps; D3 = D1 buffer 1, whose last
         // reader (layer 2 of chunks 12..15) precedes these MMAs in the pipe
         {
-            const int blk = blk0 + TC_LEAD + TC_NCH;
-            ring_pair(blk);
+            const int sl_ = ring_pair();
 #pragma unroll 1
             for (int hf = 0; hf < 2; ++hf) {
                 tc_wait(bars, B_L3RDY + hf, n_d3 & 1);
@@ -367,12 +389,12 @@ __device__ void issuer_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int
                 TLOG2(tl, 21 + hf);
 #pragma unroll 1
                 for (int p = 4 * hf; p < 4 * hf + 4; ++p) {            // 32-wide K piece p: image [hi n3p x 32 | lo n3p x 32] inside block p >> 2
-                    const uint32_t st = stage(blk + (p >> 2)) + (uint32_t)(p & 3) * n3p * 128;
+                    const uint32_t sp_ = st(sl_, p >> 2) + (uint32_t)(p & 3) * n3p * 128;
                     const uint32_t ac = tmem + COL_D2 + (uint32_t)p * 32u;
-                    tc::mma_split3_ts(tmem + COL_D3, ac, ac + 8, 16, tc::op_desc(st, n3p), tc::op_desc(st + n3p * 64, n3p), 2 * n3p, idesc3, 2, p > 0);
+                    tc::mma_split3_ts(tmem + COL_D3, ac, ac + 8, 16, tc::op_desc(sp_, n3p), tc::op_desc(sp_ + n3p * 64, n3p), 2 * n3p, idesc3, 2, p > 0);
                 }
             }
-            tc::mma_commit(bars + B_WFREE + ((blk >> 1) & 1));
+            tc::mma_commit(bars + B_WFREE + sl_);
             tc::mma_commit(bars + B_ACC);                              // D3 complete
             TLOG2(tl, 23);
         }
@@ -386,22 +408,26 @@ __device__ void issuer_mlp(unsigned char* sm, uint64_t* bars, uint32_t tmem, int
 //   B_GREAD : conv image t staged, half-A accumulators of step t-1 in registers        -> x-slabs of both halves
 //   B_HA    : units 0..63 of h(t) staged (every MMA of step t-1 has completed)          -> h-slabs 0..3 (half B first: it frees the ring pair sooner)
 //   B_HB    : units 64..95 staged, half-B accumulators of step t-1 read                  -> h-slabs 4, 5; commit half A, then half B
-__device__ void issuer_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, int blk0, int T) {
-    const uint32_t a1 = tc::smem_u32(sm + SM_A1), xh = tc::smem_u32(sm + SM_H), ring0 = tc::smem_u32(sm + SM_RING);
+__device__ void issuer_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, int blk0, int T, const RingCfg rc) {
+    const uint32_t sm0 = tc::smem_u32(sm), a1 = tc::smem_u32(sm + SM_A1), xh = tc::smem_u32(sm + SM_H);
     const uint32_t idesc192 = tc::make_idesc_f16(192), idesc128 = tc::make_idesc_f16(128), idesc96 = tc::make_idesc_f16(96),
                    idesc64 = tc::make_idesc_f16(64), idesc32 = tc::make_idesc_f16(32);
+    int gslot[4], gpar[4];                          // pair k of step 0: slot, parity of its use index (pair k of step t: use index + 2 t)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { int u; ring_slot(rc, (blk0 >> 1) + k, gslot[k], u); gpar[k] = u & 1; }
     if (elect_one()) {
 #pragma unroll 1
         for (int t = 0; t < T; ++t) {
             const bool tl = t == 2;
             const uint32_t par = (uint32_t)(t & 1);
             const uint32_t colA = tmem + COL_GA, colB = tmem + COL_GB + (uint32_t)(t & 1) * 128u;
-            const int bi = blk0 + t * TC_GRU_STEP_BLOCKS;          // even
-            auto ring_pair = [&](int i) {                          // blocks i, i + 1 resident
-                tc_wait(bars, B_WFULL + ((i >> 1) & 1), (uint32_t)((i >> 2) & 1));
+            // the step's four pairs sit in the two-slot regime, 4 pairs per step: slot and barrier parity of pair k are the same in every step
+            auto ring_pair = [&](int k) {                          // pair k of this step resident -> its slot
+                tc_wait(bars, B_WFULL + gslot[k], (uint32_t)gpar[k]);      // a slot is used twice per step: the parity of its use index does not change with t
                 tc::tc_fence_after();
+                return gslot[k];
             };
-            auto stage = [&](int i) { return ring0 + (uint32_t)(i & 3) * TC_STAGE; };
+            auto st = [&](int slot, int half) { return sm0 + (uint32_t)ring_stage_off(slot, half); };
             // state slab j (units 16j..16j+15): A1 k chunks 4 + 2j, 5 + 2j; lo image 32 KB behind the hi image
             auto h_slab = [&](int j, uint64_t& ah, uint64_t& al) {
                 const uint32_t a = a1 + 4 * 2048 + (uint32_t)j * 4096;
@@ -425,56 +451,56 @@ __device__ void issuer_gru(unsigned char* sm, uint64_t* bars, uint32_t tmem, int
             tc_wait(bars, B_GREAD, par);
             tc::tc_fence_after();
             TLOG(tl, 21);
-            ring_pair(bi);
+            const int s0 = ring_pair(0);
 #pragma unroll
             for (int kb = 0; kb < 2; ++kb) {
                 const uint32_t xa = xh + (uint32_t)(t & 1) * 16384 + kb * 4096;
                 const uint64_t ah = tc::op_desc(xa, 128), al = tc::op_desc(xa + 8192, 128);
-                const uint32_t sa = stage(bi) + kb * TC_GRU_A, sb = stage(bi + 1) + kb * TC_GRU_B;
+                const uint32_t sa = st(s0, 0) + kb * TC_GRU_A, sb = st(s0, 1) + kb * TC_GRU_B;
                 tc::mma_split3_d(colA, ah, al, 0, tc::op_desc(sa, 192), tc::op_desc(sa + 6144, 192), 0, idesc192, 1, kb > 0);
                 tc::mma_split3_d(colB, ah, al, 0, tc::op_desc(sb, 96), tc::op_desc(sb + 3072, 96), 0, idesc96, 1, kb > 0);
             }
-            tc::mma_commit(bars + B_WFREE + ((bi >> 1) & 1));
+            tc::mma_commit(bars + B_WFREE + s0);
             // ---- h-slabs 0..3
             tc_wait(bars, B_HA, par);
             tc::tc_fence_after();
             TLOG(tl, 22);
-            ring_pair(bi + 2);
+            const int s1 = ring_pair(1);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 uint64_t ah, al;
                 h_slab(j, ah, al);
-                mma_hB(stage(bi + 2 + (j >> 1)) + (j & 1) * TC_GRU_B, ah, al, j == 0);
+                mma_hB(st(s1, j >> 1) + (j & 1) * TC_GRU_B, ah, al, j == 0);
             }
-            tc::mma_commit(bars + B_WFREE + (((bi + 2) >> 1) & 1));
-            ring_pair(bi + 4);
+            tc::mma_commit(bars + B_WFREE + s1);
+            const int s2 = ring_pair(2);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 uint64_t ah, al;
                 h_slab(j, ah, al);
-                mma_hA(stage(bi + 4 + (j >> 1)) + (j & 1) * TC_GRU_A, ah, al, j == 0);
+                mma_hA(st(s2, j >> 1) + (j & 1) * TC_GRU_A, ah, al, j == 0);
             }
-            tc::mma_commit(bars + B_WFREE + (((bi + 4) >> 1) & 1));
+            tc::mma_commit(bars + B_WFREE + s2);
             // ---- h-slabs 4, 5: the only MMAs on the recurrence's critical path
             tc_wait(bars, B_HB, par);
             tc::tc_fence_after();
             TLOG(tl, 7);
-            ring_pair(bi + 6);
+            const int s3 = ring_pair(3);
 #pragma unroll
             for (int j = 4; j < 6; ++j) {
                 uint64_t ah, al;
                 h_slab(j, ah, al);
-                mma_hA(stage(bi + 6) + (j & 1) * TC_GRU_A, ah, al, false);
+                mma_hA(st(s3, 0) + (j & 1) * TC_GRU_A, ah, al, false);
             }
             tc::mma_commit(bars + B_ACC);
 #pragma unroll
             for (int j = 4; j < 6; ++j) {
                 uint64_t ah, al;
                 h_slab(j, ah, al);
-                mma_hB(stage(bi + 7) + (j & 1) * TC_GRU_B, ah, al, false);
+                mma_hB(st(s3, 1) + (j & 1) * TC_GRU_B, ah, al, false);
             }
             tc::mma_commit(bars + B_ACC2);
-            tc::mma_commit(bars + B_WFREE + (((bi + 6) >> 1) & 1));
+            tc::mma_commit(bars + B_WFREE + s3);
         }
         // final state staged and every gate accumulator read out (completion index T)
         tc_wait(bars, B_HA, (uint32_t)(T & 1));
@@ -762,12 +788,16 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
               const float* __restrict__ rowpre, const int* __restrict__ row_scene, const float* __restrict__ origin, int rows, int K,
               int rpt, int Tp, int Tf, sttode_decompose_weights w0, sttode_decompose_weights w1,
               const unsigned char* __restrict__ packed, const __grid_constant__ DecPackLayout lay, float* __restrict__ pred,
-              float* __restrict__ recon, int* __restrict__ status, int* __restrict__ tile_flags, int ntiles, int* __restrict__ tile_counter) {
+              float* __restrict__ recon, int* __restrict__ status, int* __restrict__ tile_flags, int ntiles, int* __restrict__ tile_counter, int y_first) {
     extern __shared__ __align__(128) unsigned char sm[];
+    // y_first: phase order x0, y0, GRU, y1 (y0 = decoder_y0 needs only the latent): both K1 = 32 MLPs then run while the state half of A1 is idle and serves
+    // as a third ring slot; y0's output must survive the GRU, so it gets its own buffer (set by the host when the extra shared memory fits).
+    // Otherwise x0, GRU, y0, y1 with one buffer for x and y.
     const int Tm = Tp > Tf ? Tp : Tf;
-    const int ldxy = 2 * Tm + 1;
+    const int ldxy = y_first ? 2 * Tp + 1 : 2 * Tm + 1, ldy = y_first ? 2 * Tf + 1 : ldxy;
     float* xy_s = reinterpret_cast<float*>(sm + SM_XY);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM_XY + ((BM * ldxy * 4 + 15) / 16) * 16);
+    float* y_s = y_first ? xy_s + BM * ldxy : xy_s;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM_XY + ((BM * (y_first ? ldxy + ldy : ldxy) * 4 + 15) / 16) * 16);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT + 1);
     float* gb = reinterpret_cast<float*>(bars + B_COUNT + 3);          // GRU/conv constants of block 1 (608 floats)
     float* cur_base = gb + 608;                                        // 2 x [BM][4]: current position (x, y) and scene origin (x, y) of every pair's agent (this tile / next tile)
@@ -777,7 +807,9 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
     const size_t P = (size_t)rows * K;
     if (rng_state) seed += *rng_state;
     const int total_blocks = TC_MLP_BLOCKS * 3 + TC_GRU_STEP_BLOCKS * Tp + (recon ? TC_MLP_BLOCKS : 0);
-    const int by0 = TC_MLP_BLOCKS + TC_GRU_STEP_BLOCKS * Tp;
+    const int blk_y0 = y_first ? TC_MLP_BLOCKS : TC_MLP_BLOCKS + TC_GRU_STEP_BLOCKS * Tp, blk_gru = y_first ? 2 * TC_MLP_BLOCKS : TC_MLP_BLOCKS,
+              blk_y1 = 2 * TC_MLP_BLOCKS + TC_GRU_STEP_BLOCKS * Tp;
+    const RingCfg rc = make_ring_cfg(y_first ? TC_MLP_BLOCKS : 0);      // pairs of x0 and y0 (2 x TC_MLP_BLOCKS / 2) rotate over three slots
     // Persistent CTA (one per SM): tensor memory, the GRU constants and the CTA itself are set up once (a tile costs ~160 k cycles, a CTA hand-over
     // + set-up ~8 k).  Tiles are claimed from a counter one tile ahead (tile_s[it & 1] = this tile, tile_s[(it + 1) & 1] = the next one): the SMs do
     // not run at the same speed (distance to the L2 slices), and a static split of equal tiles lost ~3 % to the slowest SM.
@@ -844,6 +876,7 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
         g_tl = on && it == 5 ? tl : nullptr;
 #if STTODE_TC_TIMELINE == 3
         if (on && (it == 5 || it == 6)) tl[it == 5 ? 0 : 8] = clock64();      // slot 0: start of the stamped tile, slot 8: start of the next one
+        if (on && it < 56 && (it % 10 == 5 || it % 10 == 6)) tl[12 + 2 * (it / 10) + (it % 10 - 5)] = clock64();      // slots 12..23: tile periods at it = 5, 15, .., 55
 #endif
     }
 #endif
@@ -878,16 +911,21 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
     TLOG3(tid == 0, 1);
 
     if (warp == PRODUCER_WARP) {                    // ---------------- producer
-        producer_loop(sm, bars, packed, total_blocks, (status[1] & 4) != 0, [&](int i, uint32_t& off, uint32_t& bytes) { block_src(lay, Tp, i, off, bytes); });
+        producer_loop(sm, bars, packed, total_blocks, (status[1] & 4) != 0, rc, [&](int i, uint32_t& off, uint32_t& bytes) { block_src(lay, Tp, y_first, i, off, bytes); });
     } else if (warp == ISSUER_WARP) {               // ---------------- issuer
         uint32_t n_d3 = 0;
-        issuer_mlp(sm, bars, tmem, 32, (int)lay.n3p[0], 0, n_d3);
-        issuer_gru(sm, bars, tmem, TC_MLP_BLOCKS, Tp);
-        issuer_mlp(sm, bars, tmem, 32, (int)lay.n3p[1], by0, n_d3);
-        issuer_mlp(sm, bars, tmem, 128, (int)lay.n3p[2], by0 + TC_MLP_BLOCKS, n_d3);
-        if (recon) issuer_mlp(sm, bars, tmem, 128, (int)lay.n3p[3], by0 + 2 * TC_MLP_BLOCKS, n_d3);
-        // the commits on the ring's free barriers of the last two pairs have no other waiter: they must have arrived before the barriers are re-created
-        for (int j = (total_blocks >> 1) - 2; j < (total_blocks >> 1); ++j) tc_wait(bars, B_WFREE + (j & 1), (uint32_t)((j >> 1) & 1));
+        issuer_mlp<32>(sm, bars, tmem, (int)lay.n3p[0], 0, n_d3, rc);
+        if (y_first) issuer_mlp<32>(sm, bars, tmem, (int)lay.n3p[1], blk_y0, n_d3, rc);
+        issuer_gru(sm, bars, tmem, blk_gru, Tp, rc);
+        if (!y_first) issuer_mlp<32>(sm, bars, tmem, (int)lay.n3p[1], blk_y0, n_d3, rc);
+        issuer_mlp<128>(sm, bars, tmem, (int)lay.n3p[2], blk_y1, n_d3, rc);
+        if (recon) issuer_mlp<128>(sm, bars, tmem, (int)lay.n3p[3], blk_y1 + TC_MLP_BLOCKS, n_d3, rc);
+        // the last commit on every slot's free barrier has no other waiter: it must have arrived before the barriers are re-created
+        {
+            const int np_ = total_blocks >> 1;
+            for (int j = np_ - 2; j < np_; ++j) { int slot, use; ring_slot(rc, j, slot, use); tc_wait(bars, B_WFREE + slot, (uint32_t)(use & 1)); }
+            if (rc.n3 >= 3) { const int j = rc.n3 - 1 - (rc.n3 % 3); int slot, use; ring_slot(rc, j, slot, use); tc_wait(bars, B_WFREE + slot, (uint32_t)(use & 1)); }   // last pair in slot 2
+        }
     } else {                                        // ---------------- epilogue warps
         uint32_t n_acc = 0;
         TLOG(tid == 0, 24);
@@ -900,7 +938,12 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
                 const int mm = idx / (2 * Tp), e = idx - mm * 2 * Tp;
                 recon[(pair0 + mm) * 2 * Tp + e] = xy_s[mm * ldxy + e];
             }
-        if (recon) epi_barrier();                   // the copy above and the build below map threads to elements differently
+        if (y_first) {                              // y0 right away (the issuer is already on its layer 1); the conv input is built after it
+            TLOG(tid == 0, 26);
+            epi_mlp(sm, bars, tmem, 2 * Tf, (int)lay.n3p[1], false, rowpre + rowpre_col(512), prow, w0.dec_y.b1, w0.dec_y.b2, y_s, ldy, false, n_acc, ovf);
+            TLOG(tid == 0, 27);
+            TLOG3(tid == 0, 5);
+        } else if (recon) epi_barrier();            // the copy above and the build below map threads to elements differently
         {   // conv input of block 1: x_true - x_hat0.  Thread (m, sub) owns a quarter of row m's 2 T_p values: no index division, the
             // agent row is already known (prow), independent loads of a line the prologue prefetched (this loop cost 3.8 k cycles per tile)
             const int per = (2 * Tp + 3) >> 2, e0 = sub * per, e1 = min(2 * Tp, e0 + per);
@@ -915,12 +958,14 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
             if (nt < ntiles) stage_tile_inputs(nt, znext, znext + 8192, cur_base + ((it + 1) & 1) * BM * 4, ovf_next);
         });
         epi_barrier();                              // every thread is done reading the conv input before y0 overwrites xy_s
-        TLOG(tid == 0, 26);
         TLOG3(tid == 0, 4);
-        epi_mlp(sm, bars, tmem, 2 * Tf, (int)lay.n3p[1], false, rowpre + rowpre_col(512), prow, w0.dec_y.b1, w0.dec_y.b2, xy_s, ldxy, false, n_acc, ovf);
-        TLOG(tid == 0, 27);
-        TLOG3(tid == 0, 5);
-        epi_mlp(sm, bars, tmem, 2 * Tf, (int)lay.n3p[2], false, rowpre + rowpre_col(1024), prow, w1.dec_y.b1, w1.dec_y.b2, xy_s, ldxy, true, n_acc, ovf);
+        if (!y_first) {
+            TLOG(tid == 0, 26);
+            epi_mlp(sm, bars, tmem, 2 * Tf, (int)lay.n3p[1], false, rowpre + rowpre_col(512), prow, w0.dec_y.b1, w0.dec_y.b2, y_s, ldy, false, n_acc, ovf);
+            TLOG(tid == 0, 27);
+            TLOG3(tid == 0, 5);
+        }
+        epi_mlp(sm, bars, tmem, 2 * Tf, (int)lay.n3p[2], false, rowpre + rowpre_col(1024), prow, w1.dec_y.b1, w1.dec_y.b2, y_s, ldy, true, n_acc, ovf);
         TLOG(tid == 0, 28);
         TLOG3(tid == 0, 6);
         if (!(Tf & 1) && !(reinterpret_cast<uintptr_t>(pred) & 15)) {
@@ -931,7 +976,7 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
 #pragma unroll 2
             for (int idx = tid; idx < np * hp; idx += EPI_THREADS) {
                 const int mm = idx / hp, j = idx - mm * hp;
-                const float* src = xy_s + mm * ldxy + 4 * j;
+                const float* src = y_s + mm * ldy + 4 * j;
                 const float cx = cur_s[mm * 4], cy = cur_s[mm * 4 + 1];
                 float4 o = make_float4(src[0] + cx, src[1] + cy, src[2] + cx, src[3] + cy);
                 if (origin) { const float ox = cur_s[mm * 4 + 2], oy = cur_s[mm * 4 + 3]; o.x += ox; o.y += oy; o.z += ox; o.w += oy; }
@@ -940,7 +985,7 @@ k_dec_pair_tc(const float* __restrict__ traj_norm, const float* __restrict__ z, 
         } else {
             for (int idx = tid; idx < np * 2 * Tf; idx += EPI_THREADS) {
                 const int mm = idx / (2 * Tf), e = idx - mm * 2 * Tf, cc = e & 1;
-                float v = xy_s[mm * ldxy + e] + cur_s[mm * 4 + cc];
+                float v = y_s[mm * ldy + e] + cur_s[mm * 4 + cc];
                 if (origin) v += cur_s[mm * 4 + 2 + cc];
                 pred[(pair0 + mm) * 2 * Tf + e] = v;
             }
@@ -1015,9 +1060,9 @@ k_dec_row_tc(const float* __restrict__ past_feature, const float* __restrict__ t
     const uint32_t tmem = *tmem_slot;
 
     if (warp == PRODUCER_WARP) {                    // ---------------- producer
-        producer_loop(sm, bars, packed, total_blocks, 0, [&](int i, uint32_t& off, uint32_t& bytes) { row_block_src(lay, Tp, i, off, bytes); });
+        producer_loop(sm, bars, packed, total_blocks, 0, make_ring_cfg(0), [&](int i, uint32_t& off, uint32_t& bytes) { row_block_src(lay, Tp, i, off, bytes); });
     } else if (warp == ISSUER_WARP) {               // ---------------- issuer
-        issuer_gru(sm, bars, tmem, 0, Tp);
+        issuer_gru(sm, bars, tmem, 0, Tp, make_ring_cfg(0));
         tc_wait(bars, B_XFULL, 0);                  // past_feature images staged
         tc::tc_fence_after();
         const uint32_t pf_hi = tc::smem_u32(sm + SMR_PFHI), pf_lo = tc::smem_u32(sm + SMR_PFLO);
@@ -1100,9 +1145,10 @@ k_dec_row_tc(const float* __restrict__ past_feature, const float* __restrict__ t
 
 size_t dec_row_tc_smem_bytes() { return (size_t)SMR_BARS + (B_COUNT + 3) * 8 + 608 * 4; }
 
-size_t dec_pair_tc_smem_bytes(int Tp, int Tf) {
+size_t dec_pair_tc_smem_bytes(int Tp, int Tf, int y_first) {
     const int Tm = Tp > Tf ? Tp : Tf;
-    return (size_t)SM_XY + ((size_t)(BM * (2 * Tm + 1) * 4 + 15) / 16) * 16 + (B_COUNT + 3) * 8 + 608 * 4 + 2 * BM * 4 * 4 + 16;
+    const int ld = y_first ? (2 * Tp + 1) + (2 * Tf + 1) : 2 * Tm + 1;
+    return (size_t)SM_XY + ((size_t)(BM * ld * 4 + 15) / 16) * 16 + (B_COUNT + 3) * 8 + 608 * 4 + 2 * BM * 4 * 4 + 16;
 }
 int dec_pair_tc_threads() { return TC_THREADS; }
 

@@ -129,11 +129,11 @@ __global__ void k_dec_pair_tc(const float* traj_norm, const float* z, unsigned l
                               const float* rowpre,
                               const int* row_scene, const float* origin, int rows, int K, int rpt, int Tp, int Tf,
                               sttode_decompose_weights w0, sttode_decompose_weights w1, const unsigned char* packed,
-                              const __grid_constant__ DecPackLayout lay, float* pred, float* recon, int* status, int* tile_flags, int ntiles, int* tile_counter);
+                              const __grid_constant__ DecPackLayout lay, float* pred, float* recon, int* status, int* tile_flags, int ntiles, int* tile_counter, int y_first);
 __global__ void k_dec_row_tc(const float* past_feature, const float* traj_norm, int rows, int Tp, sttode_decompose_weights w0,
                              sttode_decompose_weights w1, const unsigned char* packed, const __grid_constant__ DecPackLayout lay, float* rowpre, int* tile_flags);
 size_t dec_row_tc_smem_bytes();
-size_t dec_pair_tc_smem_bytes(int Tp, int Tf);
+size_t dec_pair_tc_smem_bytes(int Tp, int Tf, int y_first);
 int dec_pair_tc_threads();
 
 __global__ void k_bump_counter(unsigned long long* p);
