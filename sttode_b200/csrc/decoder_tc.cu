@@ -265,7 +265,14 @@ __device__ __forceinline__ void block_src(const DecPackLayout& lay, int Tp, int 
     }
     if (i < 2) { off = lay.mlp_off[m] + (uint32_t)i * lay.lead_blk[m]; bytes = lay.lead_blk[m]; }
     else if (i < TC_LEAD) { bytes = lay.lead_blk[m] + lay.slice_blk[m]; off = lay.mlp_off[m] + 2 * lay.lead_blk[m] + (uint32_t)(i - 2) * bytes; }
-    else if (i < TC_LEAD + TC_NCH) { off = lay.mlp_off[m] + 4 * lay.lead_blk[m] + 2 * lay.slice_blk[m] + (uint32_t)(i - TC_LEAD) * lay.mlp_blk[m]; bytes = lay.mlp_blk[m]; }
+    else if (i < TC_LEAD + TC_NCH) {
+        // chunk block (hi or lo) of chunk ch: W2 image (16 KB) + the layer-1 K slice that rides behind it, when there is one (slice (ch+1) & 3 of group ((ch+1) >> 2) + 1:
+        // groups 1..3, K1 = 32 has two slices per group): blocks without a slice copy 16 KB only (they used to drag 4..8 dead KB each: 8 % of the tile's L2 traffic)
+        const int ch = (i - TC_LEAD) >> 1, cp = ch + 1;
+        const bool has_slice = (cp >> 2) + 1 < 4 && (cp & 3) < (lay.k1[m] == 32 ? 2 : 4);
+        off = lay.mlp_off[m] + 4 * lay.lead_blk[m] + 2 * lay.slice_blk[m] + (uint32_t)(i - TC_LEAD) * lay.mlp_blk[m];
+        bytes = 16384 + (has_slice ? lay.slice_blk[m] : 0);
+    }
     else { off = lay.l3_off[m] + (uint32_t)(i - TC_LEAD - TC_NCH) * lay.l3_blk[m]; bytes = lay.l3_blk[m]; }
 }
 
