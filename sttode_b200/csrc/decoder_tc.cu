@@ -1,16 +1,19 @@
 // Tensor-core (tcgen05 / TMEM) version of the per-(agent,sample) decoder tile, sm_100a.
 //
-// Same algebra as k_dec_pair (decoder.cu): decoder_x0 -> Conv1d+GRU1 -> decoder_y0 + decoder_y1 -> pred, for a tile of
-// 128 pairs resident on one SM.  Every dense contraction runs as tcgen05.mma kind::f16 with the 3xFP16 split of
+// Same algebra as k_dec_pair (decoder.cu): decoder_x0 -> Conv1d+GRU1 -> decoder_y0 + decoder_y1 -> pred (model/STTODE.py:137-347), for tiles of 128
+// consecutive (agent, sample) pairs, one persistent CTA per SM.  Every dense contraction runs as tcgen05.mma kind::f16 with the 3xFP16 split of
 // tc.cuh (fp32-accurate), accumulators in TMEM:
-//   MLP layer 1 : D1[128x32]   = [z|state](K1) . W1c^T          per 32-unit hidden chunk (4 TMEM buffers, issued 2 chunks ahead)
-//   MLP layer 2 : D2[128x256] += relu(D1 + rowpre) . W2c^T      (the register epilogue of layer 1 re-stages the chunk as A)
-//   MLP layer 3 : D3[128xn3p] += relu(D2 + b1)[:,16p..] . W3p^T
-//   GRU step    : D_r|D_z|D_ni|D_nh [128x96 each] = conv(x)_t . W_ih^T (+) h . W_hh^T ; gates in the register epilogue
-// Weights are pre-split into fp16 hi/lo images in the canonical no-swizzle K-major layout by k_pack_image (once per
-// weight version) and streamed L2 -> shared memory with 1-D bulk copies (cp.async.bulk, UBLKCP) through a 4-stage ring
-// guarded by mbarriers; tcgen05.commit releases ring stages and activation buffers.  One thread issues the copies and
-// the MMAs; all 256 threads run the TMEM epilogues (warp w reads lanes 32*(w%4).., warps w and w+4 split the columns).
+//   MLP layer 1 : D1[128x128]  = [z|state](K1) . W1g^T          per GROUP of 128 hidden units (two 128-column D1 buffers; group g+1 in K slices behind group g's chunks)
+//   MLP layer 2 : D2[128x256] += relu(D1 + rowpre)[:, 32c..] . W2c^T     per 32-unit chunk c; the epilogue converts the chunk to fp16 hi/lo IN PLACE in tensor memory
+//                                                                (tcgen05.st) and the MMA reads it as a TMEM A operand: the hidden layer never touches shared memory
+//   MLP layer 3 : D3[128xn3p] += relu(D2 + b1)[:, 32p..] . W3p^T          (same in-place conversion of D2; D3 aliases the second D1 buffer)
+//   GRU step    : [W_in x | r | z | W_hn h] per N-half (units 0..63 / 64..95) = conv(x)_t . W_ih^T (+) h . W_hh^T ; gates in the register epilogue;
+//                 pipelined across steps (half B and the conv image double-buffered)
+// Phase order of a tile: x0-MLP, y0-MLP, Conv+GRU, y1-MLP, output (y0 needs only the latent; see RingCfg below for why it runs before the GRU).
+// Weights are pre-split into fp16 hi/lo images in the canonical no-swizzle K-major layout by k_pack_all (once per weight version) and streamed
+// L2 -> shared memory with 1-D bulk copies (cp.async.bulk, UBLKCP) through a ring of 2 or 3 slots guarded by mbarriers; tcgen05.commit releases ring
+// slots and accumulators.  Roles: 16 epilogue warps (TMEM -> registers -> bias / ReLU / gates -> operands), one issuer warp (one elected lane issues
+// every MMA), one producer warp (weight stream, barrier set-up, tile claiming).
 #include "kernels.cuh"
 #include "tc.cuh"
 #include <cstdio>
@@ -170,7 +173,7 @@ constexpr int ISSUER_WARP = 16, PRODUCER_WARP = 17;
 constexpr int TC_THREADS = 576;
 constexpr int EPI_THREADS = 512;
 constexpr int SM_A1 = 0;                         // [hi 32 KB | lo 32 KB]   A1 = [z (k 0..31) | state (k 32..127)]
-constexpr int SM_H = 65536;                      // 2 x [hi 8 KB | lo 8 KB] (MLP 32-wide chunk operand)  /  GRU: conv image in H[0]
+constexpr int SM_H = 65536;                      // 2 x [hi 8 KB | lo 8 KB]: conv image of GRU step t in H[t & 1]; the last step leaves H[T & 1] to the next tile's latent image
 constexpr int SM_RING = SM_H + 32768;
 constexpr int SM_XY = SM_RING + TC_NST * TC_STAGE;
 constexpr int COL_D2 = 0, COL_D1 = 256, COL_D3 = 384;     // TMEM columns, MLP phases (D1: 2 buffers of 128 = one 4-chunk hidden group each; D3 <= 128 columns aliases the second)
