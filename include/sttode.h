@@ -311,6 +311,15 @@ void sttode_release_host_arena(void);
  * arena either way).  Returns the previous mode; any other argument only queries.  Initial mode: STTODE_HOST_OUTPUT=copy|direct, else the default. */
 int sttode_host_output_mode(int mode);
 
+/* The whole loop body of test.py:171-208 for a batch of scenes, HOST buffers in, metrics out: H2D of the trajectories and of the ground truth
+ * (gt_layout 0 = [rows,T_f,2], 1 = [rows,2,T_f] as the ETH loader yields pred_traj_gt), set_data + inference (as sttode_forecast_host), then
+ * compute_ADE / compute_FDE with the min over the K samples (utils/metrics.py:7-26) ON THE DEVICE, and a device-to-host copy of only the three
+ * AverageMeter numerators (utils/utils.py:29-34): sums_host[0] = sum over agents of minADE, [1] = of minFDE, [2] = rows (overwritten, not accumulated).
+ * The K samples never leave HBM, so the call moves rows*(T_p+T_f)*8 bytes in and 24 bytes out instead of rows*K*T_f*8 bytes out. */
+int sttode_evaluate_host(const float *traj_host, const float *gt_host, int layout, int gt_layout, const int *scene_ptr_host, int n_scenes,
+                         int rows, int L, int agents, unsigned long long seed, int sample_k, const sttode_model_weights *w,
+                         double *sums_host, void *stream);
+
 /* The latent the decoder kernels draw when `z` is NULL (the reference's `torch.randn_like`, model/STTODE.py:609-616), written out:
  * z[n_pairs, 32] for pairs pair_base .. pair_base + n_pairs - 1 of a batch, seed as passed to sttode_forecast / sttode_decoder_fwd
  * (plus *rng_state when given).  Same device function as the decoder kernels, so the un-injected path is verifiable:

@@ -109,6 +109,7 @@ SIGNATURES = {
     "sttode_forecast_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "sttode_forecast": (_I, [_V, _I, _V, _V, _I, _I, _I, _I, _V, _U64, _I, C.POINTER(ModelWeights), _V, _V, _V, _V, _V, _Z, _V]),
     "sttode_forecast_host": (_I, [_V, _I, _V, _I, _I, _I, _I, _U64, _I, C.POINTER(ModelWeights), _V, _V]),
+    "sttode_evaluate_host": (_I, [_V, _V, _I, _I, _V, _I, _I, _I, _I, _U64, _I, C.POINTER(ModelWeights), C.POINTER(C.c_double), _V]),
     "sttode_release_host_arena": (None, []),
     "sttode_host_output_mode": (_I, [_I]),
     "sttode_peer_alloc": (_I, [_Z, C.POINTER(C.c_void_p), _V]),

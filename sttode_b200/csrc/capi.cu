@@ -1384,6 +1384,68 @@ int sttode_forecast_host(const float* traj_host, int layout, const int* scene_pt
     return 0;
 }
 
+// The loop body of test.py:171-208 for a batch of scenes with HOST buffers, metrics reduced on the device: H2D of the trajectories and the ground truth,
+// inference, min-over-K ADE/FDE (k_min_ade_fde), D2H of the three AverageMeter numerators.  The K samples stay in HBM.
+int sttode_evaluate_host(const float* traj_host, const float* gt_host, int layout, int gt_layout, const int* scene_ptr_host, int n_scenes, int rows, int L,
+                         int agents, unsigned long long seed, int sample_k, const sttode_model_weights* w, double* sums_host, void* stream) {
+    int rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = check_model(w))) return rc;
+    if (!traj_host || !gt_host || !sums_host || rows <= 0 || sample_k < 1) return fail(STTODE_EINVAL, "null pointer / empty batch");
+    if (gt_layout != 0 && gt_layout != 1) return fail(STTODE_EINVAL, "gt_layout must be 0 ([rows,T_f,2]) or 1 ([rows,2,T_f])");
+    std::lock_guard<std::mutex> lock(g_arena.mu);
+    const int Tp = w->past_length, Tf = w->future_length;
+    const size_t traj_b = (size_t)rows * Tp * 2 * 4, gt_b = (size_t)rows * Tf * 2 * 4, pred_b = (size_t)rows * sample_k * Tf * 2 * 4;
+    const size_t sp_b = scene_ptr_host ? align_up((size_t)(n_scenes + 1) * 4) : 0, rs_b = scene_ptr_host ? align_up((size_t)rows * 4) : 0;
+    // arena (pinned and device alike): [traj | scene_ptr | row_scene | gt | sums]; device only: [... | pred | workspace]
+    const size_t off_sp = align_up(traj_b), off_rs = off_sp + sp_b, off_gt = off_rs + rs_b, off_sums = off_gt + align_up(gt_b), in_b = off_sums + 256;
+    const size_t ws_b = sttode_forecast_workspace_bytes(rows, L, sample_k, Tp);
+    if ((rc = grow(&g_arena.pin_in, &g_arena.pin_in_sz, in_b, true))) return rc;
+    if ((rc = grow(&g_arena.dev, &g_arena.dev_sz, in_b + align_up(pred_b) + ws_b, false))) return rc;
+    char *pin = g_arena.pin_in, *d = g_arena.dev;
+    if (scene_ptr_host) {
+        int *sp_h = (int*)(pin + off_sp), *rs_h = (int*)(pin + off_rs);
+        memcpy(sp_h, scene_ptr_host, (size_t)(n_scenes + 1) * 4);
+        if (n_scenes <= 0 || sp_h[0] != 0 || sp_h[n_scenes] != rows) return fail(STTODE_EINVAL, "scene_ptr must start at 0 and end at rows");
+        for (int s = 0; s < n_scenes; ++s)                 // every offset is checked before rs_h is written (an interior offset above `rows` would overrun the arena)
+            if (sp_h[s] < 0 || sp_h[s + 1] <= sp_h[s] || sp_h[s + 1] > rows)
+                return fail(STTODE_EINVAL, "scene_ptr[%d..%d] = %d..%d is not strictly increasing within [0, rows = %d]", s, s + 1, sp_h[s], sp_h[s + 1], rows);
+        for (int s = 0; s < n_scenes; ++s)
+            for (int r = sp_h[s]; r < sp_h[s + 1]; ++r) rs_h[r] = s;
+    }
+    auto is_pinned = [](const void* p) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeHost;
+    };
+    // page-locked caller buffers are DMA sources as they are; pageable ones are staged through the pinned arena
+    const void *traj_src = traj_host, *gt_src = gt_host;
+    if (!is_pinned(traj_host)) { memcpy(pin, traj_host, traj_b); traj_src = pin; }
+    if (!is_pinned(gt_host)) { memcpy(pin + off_gt, gt_host, gt_b); gt_src = pin + off_gt; }
+    // from here on copies are in flight on `st`: every exit drains the stream before the arena lock is released
+    cudaError_t ce = cudaMemcpyAsync(d, traj_src, traj_b, cudaMemcpyHostToDevice, st);
+    if (ce == cudaSuccess && scene_ptr_host) ce = cudaMemcpyAsync(d + off_sp, pin + off_sp, sp_b + rs_b, cudaMemcpyHostToDevice, st);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(d + off_gt, gt_src, gt_b, cudaMemcpyHostToDevice, st);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(d + off_sums, 0, 3 * sizeof(double), st);
+    if (ce != cudaSuccess) {
+        cudaStreamSynchronize(st);
+        return fail(STTODE_ECUDA, "evaluate_host: staging failed: %s", cudaGetErrorString(ce));
+    }
+    const int* sp_d = scene_ptr_host ? (const int*)(d + off_sp) : nullptr;
+    const int* rs_d = scene_ptr_host ? (const int*)(d + off_rs) : nullptr;
+    float* pred_d = (float*)(d + in_b);
+    rc = forecast_impl((const float*)d, layout, sp_d, rs_d, n_scenes, rows, L, agents, nullptr, seed, sample_k, w, pred_d, nullptr, nullptr, nullptr,
+                       d + in_b + align_up(pred_b), ws_b, st, nullptr);
+    if (!rc) rc = sttode_min_ade_fde(pred_d, (const float*)(d + off_gt), gt_layout, rows, sample_k, Tf, (double*)(d + off_sums), stream);
+    if (!rc && (ce = cudaMemcpyAsync(pin + off_sums, d + off_sums, 3 * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+        rc = fail(STTODE_ECUDA, "evaluate_host: D2H of the sums failed: %s", cudaGetErrorString(ce));
+    ce = cudaStreamSynchronize(st);
+    if (rc) return rc;
+    if (ce != cudaSuccess) return fail(STTODE_ECUDA, "evaluate_host: %s", cudaGetErrorString(ce));
+    memcpy(sums_host, pin + off_sums, 3 * sizeof(double));
+    return 0;
+}
+
 int sttode_latent_draw(unsigned long long seed, unsigned long long pair_base, const unsigned long long* rng_state, size_t n_pairs, float* z, void* stream) {
     if (!z || n_pairs == 0) return fail(STTODE_EINVAL, "latent_draw: null pointer / no pairs");
     k_latent_draw<<<(unsigned)((n_pairs * 8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(seed, pair_base, rng_state, n_pairs, z);

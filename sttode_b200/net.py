@@ -785,6 +785,37 @@ class STTODENet(nn.Module):
             raise _lib.SttodeError("scene_ptr does not cover obs_traj")
         return self._forecast(obs, layout, sp, rs, n_scenes, rows, 1, 1, K)
 
+    @torch.no_grad()
+    def evaluate_host(self, obs_traj, gt_traj, scene_ptr=None, seed=None, sample_k=None):
+        """The body of the reference's evaluation loop (test.py:171-208 / :495-552) for a batch of scenes as ONE library call on HOST (CPU) tensors:
+        H2D, set_data + inference, min-over-K ADE/FDE on the device, three doubles back — the K samples never leave HBM (sttode_evaluate_host).
+        ETH/SDD: obs_traj [sum N_i, 2, T_p], gt_traj [sum N_i, 2, T_f] as the loader yields them, scene_ptr int32 [n_scenes+1] CSR offsets.
+        NBA (scene_ptr None): obs_traj [B, N, T_p, 2], gt_traj [B, N, T_f, 2], one reference batch (the B scenes attend to each other).
+        -> (sum of minADE over agents, sum of minFDE, agents): `ade_meter.update(sum / agents, n=agents)` reproduces test.py:204-208."""
+        K = self.args.sample_k if sample_k is None else sample_k
+        Tp, Tf = self.args.past_length, self.args.future_length
+        if obs_traj.is_cuda or gt_traj.is_cuda:
+            raise _lib.SttodeError("evaluate_host takes host tensors; for device tensors use forecast_scenes / inference + sttode_min_ade_fde")
+        obs = obs_traj.detach().to(torch.float32).contiguous()
+        gt = gt_traj.detach().to(torch.float32).contiguous()
+        if scene_ptr is not None:
+            sp = scene_ptr.detach().to(device="cpu", dtype=torch.int32).contiguous()
+            rows, n_scenes, L, agents, layout, gt_layout = obs.shape[0], sp.numel() - 1, 1, 1, TRAJ_R2T, 1
+            if tuple(obs.shape) != (rows, 2, Tp) or tuple(gt.shape) != (rows, 2, Tf):
+                raise _lib.SttodeError(f"evaluate_host: expected obs [rows,2,{Tp}] and gt [rows,2,{Tf}], got {tuple(obs.shape)} / {tuple(gt.shape)}")
+        else:
+            sp = None
+            B, N = obs.shape[0], obs.shape[1]
+            rows, n_scenes, L, agents, layout, gt_layout = B * N, 0, B, N, TRAJ_RT2, 0
+            if tuple(obs.shape) != (B, N, Tp, 2) or tuple(gt.shape) != (B, N, Tf, 2):
+                raise _lib.SttodeError(f"evaluate_host: expected obs [B,N,{Tp},2] and gt [B,N,{Tf},2], got {tuple(obs.shape)} / {tuple(gt.shape)}")
+        sums = (C.c_double * 3)()
+        mw = self._weights()
+        with torch.cuda.device(next(self.parameters()).device):
+            _lib.check(_lib.lib().sttode_evaluate_host(obs.data_ptr(), gt.data_ptr(), layout, gt_layout, sp.data_ptr() if sp is not None else None, n_scenes,
+                                                       rows, L, agents, self._seed() if seed is None else int(seed), K, C.byref(mw), sums, _lib.stream_ptr()))
+        return sums[0], sums[1], int(sums[2])
+
     def capture_forecast(self, rows, L, agents, n_scenes=0, layout=TRAJ_R2T, sample_k=None):
         """CUDA-graph version of `forecast_scenes` (n_scenes > 0, L = 1) or of NBA-style inference (n_scenes = 0) for a fixed shape."""
         return ForecastGraph(self, rows, L, agents, n_scenes, layout, sample_k).capture()
