@@ -914,6 +914,16 @@ struct HostArena {
     cudaEvent_t done[HOST_MAX_CHUNKS] = {}, copied = nullptr;
 } g_arena;
 
+// second stream + events of the arena (caller holds g_arena.mu)
+int ensure_copy_stream() {
+    if (!g_arena.copy_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&g_arena.copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < HOST_MAX_CHUNKS; ++i) CUDA_TRY(cudaEventCreateWithFlags(&g_arena.done[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&g_arena.copied, cudaEventDisableTiming));
+    }
+    return 0;
+}
+
 int grow(char** p, size_t* cur, size_t want, bool pinned) {
     if (*cur >= want) return 0;
     if (*p) { if (pinned) cudaFreeHost(*p); else cudaFree(*p); *p = nullptr; *cur = 0; }
@@ -1322,11 +1332,7 @@ int sttode_forecast_host(const float* traj_host, int layout, const int* scene_pt
     if ((rc = grow(&g_arena.pin_in, &g_arena.pin_in_sz, in_b, true))) return rc;
     if (!out_pinned && (rc = grow(&g_arena.pin_out, &g_arena.pin_out_sz, pred_b, true))) return rc;
     if ((rc = grow(&g_arena.dev, &g_arena.dev_sz, in_b + align_up(pred_b) + ws_b, false))) return rc;
-    if (!g_arena.copy_stream) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&g_arena.copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < HOST_MAX_CHUNKS; ++i) CUDA_TRY(cudaEventCreateWithFlags(&g_arena.done[i], cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&g_arena.copied, cudaEventDisableTiming));
-    }
+    if ((rc = ensure_copy_stream())) return rc;
     // inputs: a page-locked trajectory buffer is the DMA source as it is; a pageable one is staged through the pinned arena.
     // The CSR offsets and the row -> scene map (built here) always go through the arena.
     const bool in_pinned = is_pinned(traj_host);
@@ -1422,12 +1428,18 @@ int sttode_evaluate_host(const float* traj_host, const float* gt_host, int layou
     const void *traj_src = traj_host, *gt_src = gt_host;
     if (!is_pinned(traj_host)) { memcpy(pin, traj_host, traj_b); traj_src = pin; }
     if (!is_pinned(gt_host)) { memcpy(pin + off_gt, gt_host, gt_b); gt_src = pin + off_gt; }
-    // from here on copies are in flight on `st`: every exit drains the stream before the arena lock is released
-    cudaError_t ce = cudaMemcpyAsync(d, traj_src, traj_b, cudaMemcpyHostToDevice, st);
+    if ((rc = ensure_copy_stream())) return rc;
+    // from here on copies are in flight: every exit drains both streams before the arena lock is released.  The ground truth (60 % of the input bytes) is
+    // needed only by the metric kernel at the very end, so it travels on the arena's second stream underneath the forecast kernels; the previous call
+    // synchronised `st`, so nothing still reads the region it lands in.
+    cudaStream_t cs = g_arena.copy_stream;
+    cudaError_t ce = cudaMemcpyAsync(d + off_gt, gt_src, gt_b, cudaMemcpyHostToDevice, cs);
+    if (ce == cudaSuccess) ce = cudaEventRecord(g_arena.copied, cs);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(d, traj_src, traj_b, cudaMemcpyHostToDevice, st);
     if (ce == cudaSuccess && scene_ptr_host) ce = cudaMemcpyAsync(d + off_sp, pin + off_sp, sp_b + rs_b, cudaMemcpyHostToDevice, st);
-    if (ce == cudaSuccess) ce = cudaMemcpyAsync(d + off_gt, gt_src, gt_b, cudaMemcpyHostToDevice, st);
     if (ce == cudaSuccess) ce = cudaMemsetAsync(d + off_sums, 0, 3 * sizeof(double), st);
     if (ce != cudaSuccess) {
+        cudaStreamSynchronize(cs);
         cudaStreamSynchronize(st);
         return fail(STTODE_ECUDA, "evaluate_host: staging failed: %s", cudaGetErrorString(ce));
     }
@@ -1436,9 +1448,12 @@ int sttode_evaluate_host(const float* traj_host, const float* gt_host, int layou
     float* pred_d = (float*)(d + in_b);
     rc = forecast_impl((const float*)d, layout, sp_d, rs_d, n_scenes, rows, L, agents, nullptr, seed, sample_k, w, pred_d, nullptr, nullptr, nullptr,
                        d + in_b + align_up(pred_b), ws_b, st, nullptr);
+    if (!rc && (ce = cudaStreamWaitEvent(st, g_arena.copied, 0)) != cudaSuccess)                  // the metric kernel reads the ground truth
+        rc = fail(STTODE_ECUDA, "evaluate_host: %s", cudaGetErrorString(ce));
     if (!rc) rc = sttode_min_ade_fde(pred_d, (const float*)(d + off_gt), gt_layout, rows, sample_k, Tf, (double*)(d + off_sums), stream);
     if (!rc && (ce = cudaMemcpyAsync(pin + off_sums, d + off_sums, 3 * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess)
         rc = fail(STTODE_ECUDA, "evaluate_host: D2H of the sums failed: %s", cudaGetErrorString(ce));
+    if (rc) cudaStreamSynchronize(cs);                     // on success `st` waited for the copy stream's event already
     ce = cudaStreamSynchronize(st);
     if (rc) return rc;
     if (ce != cudaSuccess) return fail(STTODE_ECUDA, "evaluate_host: %s", cudaGetErrorString(ce));
