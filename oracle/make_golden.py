@@ -18,7 +18,7 @@ from oracle import ref_shim                      # noqa: E402
 from oracle import sttode_oracle as O            # noqa: E402
 from sttode_b200 import synth                    # noqa: E402
 
-OUT = os.path.join(ROOT, "tests", "golden")
+OUT = os.environ.get("STTODE_GOLDEN_OUT") or os.path.join(ROOT, "tests", "golden")      # override: tests/test_golden_reproducible.py
 
 
 def ref_model(ref, dataset, tp, tf, seed, dtype=torch.float32):
