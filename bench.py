@@ -13,7 +13,9 @@ N > 1: shards are independent (weak scaling, no data-path collective); one NCCL 
 timed region.
 
 Output: ONE JSON line on rank 0 (contract in the task statement): value = whole-job scenes/s with inputs resident in HBM; e2e = the
-same through sttode_forecast_host (host buffers, H2D + D2H inside the timed region); roofline for the dominant kernel from CUDA
+same through sttode_forecast_host (host buffers, H2D + D2H of every sample inside the timed region); e2e_metrics_only = the reference's
+evaluation loop body through sttode_evaluate_host (host trajectories + ground truth in, min-over-K ADE/FDE reduced on the device, 24 bytes
+out: secondary, shows the end-to-end scaling without the host-memory wall of the prediction copy); roofline for the dominant kernel from CUDA
 events; cpu_baseline = the oracle port of the reference timed on the host cores (N = 1 only).  The default run also measures the
 other inference config and the data-parallel training step (configs[4]) briefly and reports them under "configs".
 
