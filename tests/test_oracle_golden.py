@@ -223,3 +223,35 @@ def test_training_step_matches_reference(golden, name):
     out["total"].backward()
     losses = (out["total"], out["pred"], out["recover"], out["kl"], out["diverse"])
     check_against_golden(golden("training_step"), name, losses, [(k, sd[k].grad) for k in names], 2e-5)
+
+
+# ---------------------------------------------------------------- third-party solver restatement (torchdiffeq 0.2.3, un-vendored)
+def test_restated_euler_solver_known_answers():
+    """The one third-party routine on the path cannot be pinned against its own source (absent here: "parity unpinned"), so both
+    restatements — the reference-side shim `oracle.ref_shim._odeint` and the oracle's `ode_euler` — are held to the published contract of
+    `odeint(func, y0, t, method='euler')` with step_size=None: output[i] is the state at t[i], output[0] is y0, the user grid IS the step grid,
+    one RHS evaluation per interval at (t_i, y_i), increment (t_{i+1} - t_i) * f.  Known answers: dy/dt = a*y gives y_n = y0 * prod(1 + a*dt_i);
+    dy/dt = t gives the left Riemann sum."""
+    from oracle.ref_shim import _odeint
+    t = torch.tensor([0.0, 0.5, 0.75, 2.0], dtype=torch.float64)
+    y0 = torch.tensor([[1.0, -2.0], [0.25, 4.0]], dtype=torch.float64)
+    a, calls = -0.3, []
+
+    def f(ti, y):
+        calls.append(float(ti))
+        return a * y
+    out = _odeint(f, y0, t, method="euler")
+    assert out.shape == (4, 2, 2) and torch.equal(out[0], y0) and calls == [0.0, 0.5, 0.75]
+    want = y0.clone()
+    for i in range(3):
+        want = want * (1 + a * float(t[i + 1] - t[i]))
+        assert torch.allclose(out[i + 1], want, rtol=1e-15, atol=0)
+    assert torch.allclose(O.ode_euler(lambda ti, y: a * y, y0, t), out[-1], rtol=1e-15, atol=0)
+    riemann = _odeint(lambda ti, y: ti * torch.ones_like(y), torch.zeros(1, dtype=torch.float64), t)
+    assert torch.allclose(riemann[:, 0], torch.tensor([0.0, 0.0, 0.125, 0.125 + 0.75 * 1.25], dtype=torch.float64))
+    # the reference's call (ode_demo.py:186-190): t = [0, 12], result index 1 = y0 + 12 * f(0, y0): exactly one RHS evaluation
+    calls.clear()
+    out = _odeint(f, y0, torch.tensor([0.0, 12.0], dtype=torch.float64))
+    assert calls == [0.0] and torch.allclose(out[1], y0 + 12.0 * a * y0, rtol=1e-15, atol=0)
+    with pytest.raises(AssertionError):
+        _odeint(f, y0, t, method="dopri5")          # anything but the solver the reference asks for is refused, not approximated
