@@ -163,3 +163,38 @@ def test_bench_reference_arm_contract():
     assert d["impl"] == "reference" and d["unit"] == "scenes/s" and d["n_gpus"] == 2 and d["higher_is_better"] is True
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["e2e"]["h2d_bytes_per_step"] == 0
     assert d["value"] > 0 and "workload" in d["config"]
+
+
+def test_ctypes_signatures_match_header_prototypes():
+    """Every prototype of include/sttode.h against its ctypes signature in sttode_b200/_lib.py: same number of parameters, and per position the same
+    class (pointer / int / float / long / 64-bit unsigned = size_t and unsigned long long / unsigned / double), same for the return type.  ctypes
+    would silently marshal a wrong signature; this is the check that the Python mirror calls the ABI the header declares."""
+    import ctypes as C
+    text = open(os.path.join(ROOT, "include", "sttode.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = re.findall(r"([A-Za-z_][A-Za-z0-9_ \*]*?)\b(sttode_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", text, flags=re.S)
+    assert {n for _, n, _ in protos} == set(L.SIGNATURES)
+    scalars = {"int": "int", "float": "float", "size_t": "u64", "unsigned long long": "u64", "long": "long", "double": "double", "unsigned": "uint"}
+
+    def header_kind(decl, has_name):
+        d = " ".join(decl.replace("const ", " ").split())
+        if d in ("void", ""):
+            return None
+        if "*" in d:
+            return "ptr"
+        if has_name:
+            d = d.rsplit(" ", 1)[0]
+        return scalars[d]
+
+    def ctypes_kind(t):
+        if t is None:
+            return None
+        if t in (C.c_void_p, C.c_char_p) or (isinstance(t, type) and issubclass(t, C._Pointer)):
+            return "ptr"
+        return {C.c_int: "int", C.c_float: "float", C.c_size_t: "u64", C.c_ulonglong: "u64", C.c_long: "long", C.c_double: "double", C.c_uint: "uint"}[t]
+
+    for ret, name, params in protos:
+        want = [k for k in (header_kind(p, True) for p in params.split(",")) if k is not None]
+        res, args = L.SIGNATURES[name]
+        assert [ctypes_kind(a) for a in args] == want, name
+        assert ctypes_kind(res) == header_kind(ret, False), name
