@@ -198,3 +198,32 @@ def test_ctypes_signatures_match_header_prototypes():
         res, args = L.SIGNATURES[name]
         assert [ctypes_kind(a) for a in args] == want, name
         assert ctypes_kind(res) == header_kind(ret, False), name
+
+
+def test_ctypes_struct_fields_match_header_structs():
+    """Field names, order and nesting of every struct in include/sttode.h against the ctypes mirror (sizes alone would not catch two swapped pointers)."""
+    text = open(os.path.join(ROOT, "include", "sttode.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    mirror = {"sttode_mhgsa_weights": L.MhgsaWeights, "sttode_ode_weights": L.OdeWeights, "sttode_encoder_weights": L.EncoderWeights,
+              "sttode_mlp3_weights": L.Mlp3Weights, "sttode_decompose_weights": L.DecomposeWeights, "sttode_model_weights": L.ModelWeights,
+              "sttode_mhgsa_grads": L.MhgsaGrads, "sttode_ode_grads": L.OdeGrads, "sttode_mlp3_grads": L.Mlp3Grads, "sttode_decompose_grads": L.DecomposeGrads}
+    structs = re.findall(r"typedef struct (sttode_[a-z0-9_]+) \{(.*?)\} \1;", text, flags=re.S)
+    assert {n for n, _ in structs} == set(mirror)
+    for name, body in structs:
+        fields = []
+        for decl in body.split(";"):
+            decl = " ".join(decl.split())
+            if not decl:
+                continue
+            first, *more = [d.strip() for d in decl.split(",")]
+            toks = first.replace("*", " * ").split()
+            base = " ".join(t for t in toks[:-1] if t not in ("const", "*"))
+            for d in [toks[-1]] + [m.replace("*", "").strip() for m in more]:
+                m = re.fullmatch(r"([a-z0-9_]+)(?:\[(\d+)\])?", d)
+                fields.append((m.group(1), base if base.startswith("sttode_") else None, int(m.group(2)) if m.group(2) else None))
+        got = mirror[name]._fields_
+        assert [f[0] for f in got] == [f[0] for f in fields], name
+        for (fname, nested, count), (_, ctype) in zip(fields, got):
+            if nested:
+                want = mirror[nested] * count if count else mirror[nested]
+                assert ctype is want or (count and ctype._type_ is mirror[nested] and ctype._length_ == count), (name, fname)
