@@ -1,0 +1,41 @@
+"""bench.py's FLOP accounting — the numerator of `roofline.achieved` and of `flops_per_step_*` — checked on the CPU:
+the reference op-list formula equals torch's FlopCounterMode over the oracle's inference to the digit, the table of SURVEY §8d is
+reproduced, and the FLOPs the pair kernel issues after exact de-duplication are the documented 1 608 704 per (agent, sample) pair at 8/12 frames."""
+import os
+import sys
+
+import pytest
+import torch
+from torch.utils.flop_counter import FlopCounterMode
+
+from oracle import sttode_oracle as O
+from sttode_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench      # noqa: E402
+
+
+@pytest.mark.parametrize("tp,tf,B,N,mflop_per_scene", [(8, 12, 1, 7, 468.99), (8, 12, 1, 60, 4019.93), (10, 20, 32, 11, 807.35), (5, 10, 16, 11, None)])
+def test_reference_flop_formula_equals_flop_counter_on_the_oracle(tp, tf, B, N, mflop_per_scene):
+    sd = O.make_state_dict(1, tp, tf)
+    past = torch.randn(B * N, tp, 2, generator=torch.Generator().manual_seed(0))
+    with FlopCounterMode(display=False) as fc:
+        O.inference(sd, past, B, N, synth.latent(B * N, seed=9))
+    total = fc.get_total_flops()
+    assert total == bench.reference_flops_per_row(tp, tf, B) * B * N            # S = B: the attention axis is the scene-batch axis
+    if mflop_per_scene is not None:                                              # SURVEY.md §8d table, per scene
+        assert abs(total / B / 1e6 - mflop_per_scene) < 0.005
+
+
+def test_issued_flops_after_deduplication():
+    assert bench.issued_flops_dec_pair(8, 12) == 1_608_704
+    # pieces: x0-MLP and y0-MLP read the 32-dim latent slice only (K1 = 32: the 224 sample-independent layer-1 columns are in rowpre), y1-MLP the 96 + 32
+    # state/latent columns; GRU = conv (2*2*3*32) + input and hidden products per step
+    assert bench.flops_mlp(32, 16) + bench.flops_gru(8) + bench.flops_mlp(32, 24) + bench.flops_mlp(128, 24) == 1_608_704
+    assert bench.flops_gru(1) == 2 * 6 * 32 + 2 * 32 * 288 + 2 * 96 * 288
+    # whole step: issued / reference op list = 0.507 at 8/12 frames, K = 20
+    rows, K = 53760, 20
+    issued = bench.issued_flops_per_row(8, 1) * rows + bench.issued_flops_dec_pair(8, 12) * rows * K
+    ratio = issued / (bench.reference_flops_per_row(8, 12, 1) * rows)
+    assert 0.50 < ratio < 0.515, ratio
