@@ -39,3 +39,26 @@ def test_issued_flops_after_deduplication():
     issued = bench.issued_flops_per_row(8, 1) * rows + bench.issued_flops_dec_pair(8, 12) * rows * K
     ratio = issued / (bench.reference_flops_per_row(8, 12, 1) * rows)
     assert 0.50 < ratio < 0.515, ratio
+
+
+@pytest.mark.parametrize("name", ["r02_bench_final_eth.json", "r02_bench_final_nba.json", "r02_bench_n1.json", "r02_bench_n2.json", "r02_bench_n4.json", "r02_bench_n8.json"])
+def test_committed_bench_lines_are_self_consistent(name):
+    """The bench lines committed under profiles/ recompute: value from the shard size and the step time, the roofline from the issued FLOPs and the kernel's
+    measured duration, the kernel inside the step, the end-to-end number not above the device-resident one, clean clocks."""
+    import json
+    with open(os.path.join(ROOT, "profiles", name)) as f:                # multi-rank captures start with NCCL's version banner: the line is the last '{' line
+        d = json.loads([ln for ln in f.read().splitlines() if ln.startswith("{")][-1])
+    cfg, rf = d["config"], d["roofline"]
+    scenes = cfg["scenes_per_gpu_per_step"] * d["n_gpus"]
+    assert abs(d["value"] - scenes / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]
+    nba = "NBA" in cfg["workload"]
+    tp, tf = (10, 20) if nba else (8, 12)
+    per_launch = bench.issued_flops_dec_pair(tp, tf) * cfg["sample_pairs_per_gpu_per_step"]
+    assert rf["flops_per_launch_issued"] == per_launch
+    assert abs(rf["achieved"] - per_launch / (rf["kernel_ms"] * 1e-3) / 1e12) <= 1e-6 * rf["achieved"]
+    assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9 and rf["bound"] == "tensor" and rf["unit"] == "TFLOP/s"
+    assert 0.5 < rf["kernel_share_of_step"] < 1.0 and rf["kernel_ms"] < d["ms_per_step"]
+    assert rf["frac"] < 1 / 3                                          # three tensor-core MACs per algorithmic MAC: the ceiling of the 3xFP16 split
+    assert d["e2e"]["value"] <= d["value"] * 1.001 and d["e2e"]["d2h_bytes_per_step"] == cfg["sample_pairs_per_gpu_per_step"] * tf * 2 * 4
+    assert d["scaling"] == "weak" and d["unit"] == "scenes/s" and d["vs_baseline"] is None and d["tc_status"] == 0 and d["gpu_launches"] > 0
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
