@@ -48,7 +48,7 @@ CONFIGS = {
                         "(MHGSA L = S = 128 across the scenes of a batch), sharded by whole batches"},
 }
 # dram read+write of k_dec_pair_tc per (agent, sample) pair from `ncu --set full` (one launch of 268 800 / 225 280 pairs)
-DRAM_BYTES_PER_PAIR = {"eth": (86.35e6 + 11.50e6) / 268800, "nba": (72.69e6 + 12.36e6) / 225280}      # profiles/r02_ncu_full_{eth,nba}.md (eth: final persistent kernel)
+DRAM_BYTES_PER_PAIR = {"eth": (85.84e6 + 14.39e6) / 268800, "nba": (72.69e6 + 12.36e6) / 225280}      # profiles/r02_ncu_full_{eth,nba}.md (eth: final persistent kernel)
 
 
 # ---------------------------------------------------------------------------------- FLOP accounting
