@@ -144,22 +144,33 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         self.thr.join(timeout=2)
-        sm, smax, reasons = [], None, set()
-        t_mark = getattr(self, "t_mark", 0.0)
-        for ts, ln in self.lines:
-            if ts < t_mark:
-                continue
+        return self.summarise(self.lines, getattr(self, "t_mark", 0.0))
+
+    @staticmethod
+    def summarise(lines, t_mark):
+        """Median SM clock and throttle reasons of the samples taken inside the timed region.  A region shorter than the 20 ms sampling period may hold no
+        sample at all: then the nearest ones on either side are used (the one before was taken during the warm-up steps, i.e. under the same load) and
+        `window` says so."""
+        parsed = []
+        for ts, ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); smax = float(f[2])
+                parsed.append((ts, float(f[1]), float(f[2]), f[5:9]))
             except ValueError:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+        inside = [p for p in parsed if p[0] >= t_mark]
+        window = "timed region"
+        if not inside and parsed:
+            inside = parsed[-2:]
+            window = "nearest samples before the timed region (region shorter than the 20 ms sampling period)"
+        sm, smax, reasons = [p[1] for p in inside], (inside[-1][2] if inside else None), set()
+        for p in inside:
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ---------------------------------------------------------------------------------- CPU port of the reference (oracle/), timed legs only

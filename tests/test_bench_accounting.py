@@ -62,3 +62,19 @@ def test_committed_bench_lines_are_self_consistent(name):
     assert d["e2e"]["value"] <= d["value"] * 1.001 and d["e2e"]["d2h_bytes_per_step"] == cfg["sample_pairs_per_gpu_per_step"] * tf * 2 * 4
     assert d["scaling"] == "weak" and d["unit"] == "scenes/s" and d["vs_baseline"] is None and d["tc_status"] == 0 and d["gpu_launches"] > 0
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_clock_sampler_summary():
+    """bench.ClockSampler.summarise on synthetic nvidia-smi lines: only samples inside the timed region count; a region without any sample falls back to the
+    nearest earlier ones and says so; throttle reasons are collected."""
+    ok = "0, 1965, 1965, 700.0, 0x0, Not Active, Not Active, Not Active, Not Active"
+    cap = "0, 1800, 1965, 990.0, 0x4, Not Active, Not Active, Not Active, Active"
+    hot = "0, 1200, 1965, 990.0, 0x40, Not Active, Active, Not Active, Not Active"
+    lines = [(0.00, ok), (0.02, hot), (0.04, ok), (0.06, cap), (0.08, "garbage"), (0.10, ok)]
+    c = bench.ClockSampler.summarise(lines, 0.03)
+    assert c == {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": ["sw_power_cap"], "samples": 3, "window": "timed region"}
+    c = bench.ClockSampler.summarise(lines, 0.5)                      # nothing inside: the two nearest samples, flagged
+    assert c["samples"] == 2 and c["sm_mhz"] == (1800 + 1965) / 2 and c["reasons"] == ["sw_power_cap"] and c["window"].startswith("nearest")
+    c = bench.ClockSampler.summarise(lines, 0.0)
+    assert c["reasons"] == ["hw_thermal_slowdown", "sw_power_cap"] and c["samples"] == 5
+    assert bench.ClockSampler.summarise([], 0.0) == {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "window": "timed region"}
