@@ -1,0 +1,117 @@
+"""The oracle against the UNMODIFIED reference on fresh random inputs (build container only: /root/reference does not exist on the GPU box, where these
+tests skip).  The committed goldens pin a fixed set of shapes; here shapes, seeds and curvatures are drawn at random per run of the loop so the restatement is
+held to the reference beyond the fixtures: MHGSA (square, cross, one-scene), the tensor-ODE block, whole ETH and NBA inference with the latent injected, and
+every pmath function including points at and beyond the ball's margin.  Tolerance 2e-6 relative (fp32 rounding; identical op order gives exact equality)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pmath_oracle as PO
+from oracle import ref_shim
+from oracle import sttode_oracle as O
+from sttode_b200 import synth
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present (GPU box)")
+P = "past_encoder.ODE_Encoder.odeblock.odefunc.layers.0."
+A = P + "self_attn.temporal_attention_before."
+
+
+def rel(a, b):
+    a, b = a.detach().double(), b.detach().double()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def ref():
+    r = ref_shim.install()
+    saved = r.sttode.Normal.rsample
+    yield r
+    r.sttode.Normal.rsample = saved                     # the latent injection below patches the class: leave the reference as it was found
+
+
+def ref_model(ref, dataset, tp, tf, seed):
+    m = ref.sttode.STTODENet(ref_shim.make_args(dataset, tp, tf), torch.device("cpu")).eval()
+    sd = O.make_state_dict(seed, tp, tf)
+    m.load_state_dict(sd, strict=True)
+    return m, sd
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_mhgsa_and_ode_block_random_shapes(ref, seed):
+    rng = np.random.default_rng(100 + seed)
+    m, sd = ref_model(ref, "eth", 8, 12, seed=1 + seed % 2)
+    attn = m.past_encoder.ODE_Encoder.odeblock.odefunc.layers[0].self_attn.temporal_attention_before
+    g = torch.Generator().manual_seed(200 + seed)
+    L, bsz = int(rng.integers(1, 40)), int(rng.integers(1, 9))
+    S = L if seed % 2 == 0 else int(rng.integers(1, 40))
+    q = torch.randn(L, bsz, 64, generator=g) * float(rng.uniform(0.2, 3.0))
+    kv = q if S == L and seed % 2 == 0 else torch.randn(S, bsz, 64, generator=g)
+    with torch.no_grad():
+        out_r, w_r = attn(q, kv, kv)
+    out_o, w_o = O.hyp_mhsa(q, kv, kv, sd[A + "in_proj_weight"], sd[A + "in_proj_bias"], sd[A + "out_proj.weight"], sd[A + "out_proj.bias"])
+    assert rel(out_o, out_r) < 2e-6 and rel(w_o, w_r) < 2e-6, (L, S, bsz)
+    x = torch.randn(L, bsz, 1, 64, generator=g)
+    m.past_encoder.agent_mask = torch.zeros(1)
+    with torch.no_grad():
+        y_r = m.past_encoder.ODE_Encoder(x, mask=None, num_agent=bsz)
+    assert rel(O.ode_encoder(x, sd, "past_encoder."), y_r) < 2e-6, (L, bsz)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_inference_random_scenes(ref, seed):
+    rng = np.random.default_rng(300 + seed)
+    # ETH / SDD: one scene per call
+    n = int(rng.integers(1, 25))
+    m, sd = ref_model(ref, "eth", 8, 12, seed=1)
+    obs, gt = synth.eth_scene(500 + seed, n)
+    z = synth.latent(n, seed=40 + seed)
+    ref.sttode.Normal.rsample = lambda self: self.mu + z.to(self.mu.dtype) * self.sigma
+    with torch.no_grad():
+        m.set_data(None, obs, gt, torch.ones(n, 8), torch.ones(n, 12))
+        pred_r = m.inference(None)
+    past, orig = O.eth_scene_normalise(obs)
+    pred_o = O.inference(sd, past, 1, n, z, scene_orig=orig)
+    cur = obs[:, :, -1][None, :, None, :]
+    assert float((pred_o - pred_r).abs().max() / (pred_r - cur).abs().max()) < 2e-6, n          # relative to the displacement, not the coordinates
+    # NBA: B scenes attend to each other
+    B, (tp, tf) = int(rng.integers(2, 8)), [(10, 20), (5, 10)][seed % 2]
+    mn, sdn = ref_model(ref, "nba", tp, tf, seed=2)
+    data = synth.nba_batch(600 + seed, B, 11, tp, tf)
+    zn = synth.latent(B * 11, seed=50 + seed)
+    ref.sttode.Normal.rsample = lambda self: self.mu + zn.to(self.mu.dtype) * self.sigma
+    with torch.no_grad():
+        mn.set_data_nba(data)
+        pred_r = mn.inference(data)
+    past = data["past_traj"].view(B * 11, tp, 2)
+    pred_o = O.inference(sdn, past, B, 11, zn)
+    cur = past[:, -1][None, :, None, :]
+    assert float((pred_o - pred_r).abs().max() / (pred_r - cur).abs().max()) < 2e-6, (B, tp, tf)
+
+
+@pytest.mark.parametrize("c", [0.3, 1.0, 2.0])
+def test_pmath_random_points_incl_the_boundary(ref, c):
+    R = ref.pmath
+    g = torch.Generator().manual_seed(int(c * 100))
+    d = 16
+    x = torch.randn(64, d, generator=g) * 0.25 / c ** 0.5
+    y = torch.randn(64, d, generator=g) * 0.25 / c ** 0.5
+    u = torch.randn(64, d, generator=g)
+    x[0] = 0
+    y[1] = 0
+    x[2] = x[2] / x[2].norm() * (1 - 1e-3) / c ** 0.5                                # on the projection margin
+    x[3] = x[3] / x[3].norm() * 3.0 / c ** 0.5                                       # far outside the ball
+    x[4] = x[4] / x[4].norm() * (1 - 1e-6) / c ** 0.5                                # between the margin and the boundary
+    mat = torch.randn(7, d, generator=g) * 0.5
+    px, py = R.project(x, c=c), R.project(y, c=c)
+    assert torch.equal(PO.project(x, c), px)
+    pairs = [(PO.lambda_x(px, c), R.lambda_x(px, c=c)), (PO.mobius_add(px, py, c), R.mobius_add(px, py, c=c)), (PO.dist0(px, c), R.dist0(px, c=c)),
+             (PO.expmap0(u, c), R.expmap0(u, c=c)), (PO.logmap0(px, c), R.logmap0(px, c=c)), (PO.expmap(px, u * 0.3, c), R.expmap(px, u * 0.3, c=c)),
+             (PO.logmap(px, py, c), R.logmap(px, py, c=c)), (PO.mobius_matvec(mat, px, c), R.mobius_matvec(mat, px, c=c)),
+             (PO.dist_matrix(px[:9], py[:11], c), R.dist_matrix(px[:9], py[:11], c=c)), (PO.artanh(px * 0.9), R.artanh(px * 0.9)),
+             (PO.arsinh(u), R.arsinh(u)), (PO.tanh(u * 20), R.tanh(u * 20))]
+    for i, (a, b) in enumerate(pairs):
+        assert torch.allclose(a, b, rtol=2e-6, atol=1e-7, equal_nan=True), i
+    # dist near the boundary: compare through tanh(sqrt(c) d / 2) (the artanh argument), as tests/test_gpu_parity.py does for the device kernels
+    da, db = PO.dist(px, py, c), R.dist(px, py, c=c)
+    assert torch.allclose(torch.tanh(c ** 0.5 * da / 2), torch.tanh(c ** 0.5 * db / 2), rtol=2e-6, atol=1e-7)
