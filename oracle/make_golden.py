@@ -209,35 +209,42 @@ def grad_sample_index(numel, count=512):
     return torch.linspace(0, numel - 1, min(numel, count)).round().long()
 
 
+def reference_training_step(ref, dataset, tp, tf, B, N, draws_seed, batch_index):
+    """One training step of the reference itself in train() mode (train.py:61-65: set_data* -> forward -> backward) with every random draw injected.
+    Weights are the reference's own default init under torch.manual_seed(3).  -> (model after backward, loss tuple as 5 floats)."""
+    torch.manual_seed(3)
+    m = ref.sttode.STTODENet(ref_shim.make_args(dataset, tp, tf), torch.device("cpu")).train()
+    R = B * N
+    d = training_draws(R, tp, tf, seed=draws_seed)
+    m.past_encoder.pos_encoder.dropout = _MaskDropout(d["mask_past"])
+    m.future_encoder.pos_encoder.dropout = _MaskDropout(d["mask_future"])
+    queue = [d["eps_q"], d["eps_mid"], d["eps_p"]]
+    ref.sttode.Normal.rsample = lambda self: self.mu + queue.pop(0) * self.sigma
+    if dataset == "nba":
+        m.set_data_nba(synth.nba_batch(batch_index, B, N, tp, tf))
+    else:
+        obs, gt = synth.eth_scene(batch_index, N)
+        orig_rand = torch.rand
+        torch.rand = lambda *a, **k: d["theta_u"].clone()        # the uniform draw behind the rotation angle (model/STTODE.py:423)
+        try:
+            m.set_data(None, obs, gt, torch.ones(N, tp), torch.ones(N, tf))
+        finally:
+            torch.rand = orig_rand
+    m.zero_grad(set_to_none=True)
+    total, lp, lr, lk, ld = m.forward()
+    total.backward()
+    return m, [float(total.detach()), lp, lr, lk, ld]
+
+
 def training_golden():
-    """One training step of the reference itself in train() mode (train.py:61-65: set_data* -> forward -> backward) with every
-    random draw injected: loss tuple + the gradient of all parameters.  Weights are the reference's own default init under
-    torch.manual_seed(3) (sttode_b200.net.STTODENet reproduces it bit for bit, tests/test_host_logic.py)."""
+    """One training step of the reference itself in train() mode with every random draw injected: loss tuple + the gradient of all
+    parameters.  Weights are the reference's own default init under torch.manual_seed(3) (sttode_b200.net.STTODENet reproduces it
+    bit for bit, tests/test_host_logic.py)."""
     ref = ref_shim.install()
     rec = {}
     for name, dataset, tp, tf, B, N in (("nba", "nba", 10, 20, 8, 11), ("eth", "eth", 8, 12, 1, 7)):
-        torch.manual_seed(3)
-        m = ref.sttode.STTODENet(ref_shim.make_args(dataset, tp, tf), torch.device("cpu")).train()
-        R = B * N
-        d = training_draws(R, tp, tf, seed=40 + B)
-        m.past_encoder.pos_encoder.dropout = _MaskDropout(d["mask_past"])
-        m.future_encoder.pos_encoder.dropout = _MaskDropout(d["mask_future"])
-        queue = [d["eps_q"], d["eps_mid"], d["eps_p"]]
-        ref.sttode.Normal.rsample = lambda self: self.mu + queue.pop(0) * self.sigma
-        if dataset == "nba":
-            m.set_data_nba(synth.nba_batch(2, B, N, tp, tf))
-        else:
-            obs, gt = synth.eth_scene(3, N)
-            orig_rand = torch.rand
-            torch.rand = lambda *a, **k: d["theta_u"].clone()        # the uniform draw behind the rotation angle (model/STTODE.py:423)
-            try:
-                m.set_data(None, obs, gt, torch.ones(N, tp), torch.ones(N, tf))
-            finally:
-                torch.rand = orig_rand
-        m.zero_grad(set_to_none=True)
-        total, lp, lr, lk, ld = m.forward()
-        total.backward()
-        rec[f"{name}_losses"] = np.array([float(total), lp, lr, lk, ld], np.float64)
+        m, losses = reference_training_step(ref, dataset, tp, tf, B, N, draws_seed=40 + B, batch_index=2 if dataset == "nba" else 3)
+        rec[f"{name}_losses"] = np.array(losses, np.float64)
         for n, p_ in m.named_parameters():           # fixtures stay small: <= 512 evenly spaced entries + norm + max per tensor
             g_ = (p_.grad if p_.grad is not None else torch.zeros_like(p_)).detach().flatten()
             rec[f"{name}_g_{n}"] = np32(g_[grad_sample_index(g_.numel())])

@@ -115,3 +115,39 @@ def test_pmath_random_points_incl_the_boundary(ref, c):
     # dist near the boundary: compare through tanh(sqrt(c) d / 2) (the artanh argument), as tests/test_gpu_parity.py does for the device kernels
     da, db = PO.dist(px, py, c), R.dist(px, py, c=c)
     assert torch.allclose(torch.tanh(c ** 0.5 * da / 2), torch.tanh(c ** 0.5 * db / 2), rtol=2e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("dataset,tp,tf,B,N,draws_seed,batch_index", [("nba", 10, 20, 3, 11, 71, 9), ("nba", 5, 10, 5, 11, 72, 4), ("eth", 8, 12, 1, 4, 73, 21),
+                                                                   ("eth", 8, 12, 1, 13, 74, 22)])
+def test_training_step_random_batches(ref, dataset, tp, tf, B, N, draws_seed, batch_index):
+    """One train()-mode step of the reference (forward + backward, every draw injected: PE-dropout masks, rsample noise, rotation angle) against the oracle's
+    objective + torch autograd on batches and shapes the fixtures do not hold: loss tuple and the gradient of every parameter."""
+    import math
+    from oracle.make_golden import reference_training_step, training_draws
+    from training_common import assert_grad_close
+    m, losses_r = reference_training_step(ref, dataset, tp, tf, B, N, draws_seed, batch_index)
+    from sttode_b200.net import STTODENet
+    torch.manual_seed(3)
+    sd = {k: v.clone() for k, v in STTODENet(synth.make_args(dataset, tp, tf), torch.device("cpu")).state_dict().items()}
+    names = [k for k in sd if not k.endswith("pos_encoder.pe")]
+    for k in names:
+        sd[k].requires_grad_(True)
+    d = training_draws(B * N, tp, tf, seed=draws_seed)
+    if dataset == "nba":
+        data = synth.nba_batch(batch_index, B, N, tp, tf)
+        past, fut, feats = data["past_traj"].view(B * N, tp, 2), data["future_traj"].view(B * N, tf, 2), None
+    else:
+        obs, gt = synth.eth_scene(batch_index, N)
+        inputs, inputs_post, past, fut = O.eth_train_staging(obs, gt, d["theta_u"] * math.pi * 2)
+        feats = (inputs, inputs_post)
+    out = O.training_objective(sd, past, fut, B, N, d["eps_q"], d["eps_p"], masks=(d["mask_past"], d["mask_future"]), features=feats, tensors=True)
+    out["total"].backward()
+    for got, want, what in zip((out["total"], out["pred"], out["recover"], out["kl"], out["diverse"]), losses_r, ("total", "pred", "recover", "kl", "diverse")):
+        assert abs(float(got) - want) <= 2e-5 * abs(want), (what, float(got), want)
+    ref_grads = dict(m.named_parameters())
+    for k in names:
+        gr = ref_grads[k].grad
+        if gr is None:                                       # pz_layer: learn_prior = False
+            assert sd[k].grad is None or float(sd[k].grad.abs().max()) == 0.0, k
+            continue
+        assert_grad_close(sd[k].grad.double().flatten(), gr.double().flatten(), 2e-5, k)
