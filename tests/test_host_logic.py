@@ -227,3 +227,28 @@ def test_ctypes_struct_fields_match_header_structs():
             if nested:
                 want = mirror[nested] * count if count else mirror[nested]
                 assert ctype is want or (count and ctype._type_ is mirror[nested] and ctype._length_ == count), (name, fname)
+
+
+def test_model_level_calls_have_no_cpu_fallback():
+    """STTODENet on CPU tensors: inference, the batched forecast, the host-buffer evaluation and a train()-mode step all raise SttodeError (no device,
+    no silent PyTorch path); argument errors of evaluate_host are reported before the library is touched."""
+    from sttode_b200 import synth
+    from sttode_b200.net import STTODENet
+    m = STTODENet(make_args("eth"), torch.device("cpu")).eval()
+    obs, gt = synth.eth_scene(1, 5)
+    sp = torch.tensor([0, 5], dtype=torch.int32)
+    m.set_data(None, obs, gt, torch.ones(5, 8), torch.ones(5, 12))
+    for call in (lambda: m.inference(None), lambda: m.forecast_scenes(obs, sp), lambda: m.evaluate_host(obs, gt, sp), lambda: m.forward()):
+        with pytest.raises(L.SttodeError):
+            call()
+    with pytest.raises(L.SttodeError, match=r"expected obs \[rows,2,8\]"):
+        m.evaluate_host(obs[:, :, :5], gt, sp)
+    n = STTODENet(make_args("nba", 10, 20), torch.device("cpu")).eval()
+    d = synth.nba_batch(0, 3)
+    with pytest.raises(L.SttodeError, match=r"expected obs \[B,N,10,2\]"):
+        n.evaluate_host(d["past_traj"][:, :, :4], d["future_traj"])
+    with pytest.raises(L.SttodeError):
+        n.evaluate_host(d["past_traj"], d["future_traj"])
+    n.set_data_nba(d)
+    with pytest.raises(L.SttodeError):
+        n.train().forward()
