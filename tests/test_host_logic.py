@@ -252,3 +252,27 @@ def test_model_level_calls_have_no_cpu_fallback():
     n.set_data_nba(d)
     with pytest.raises(L.SttodeError):
         n.train().forward()
+
+
+def test_product_never_touches_the_oracle_or_the_reference_tree():
+    """The oracle is test infrastructure: no module of the package imports it (statically: AST of every file; dynamically: importing every module of the
+    package leaves no `oracle*` entry in sys.modules), nothing under sttode_b200/ or include/ names /root/reference, and the C sources link nothing from oracle/."""
+    import ast
+    import glob
+    import subprocess
+    import sys
+    pkg = os.path.join(ROOT, "sttode_b200")
+    for path in glob.glob(os.path.join(pkg, "**", "*.py"), recursive=True):
+        tree = ast.parse(open(path).read(), path)
+        for node in ast.walk(tree):
+            mods = [a.name for a in node.names] if isinstance(node, ast.Import) else [node.module or ""] if isinstance(node, ast.ImportFrom) else []
+            assert not any(m == "oracle" or m.startswith("oracle.") for m in mods), path
+    for path in glob.glob(os.path.join(pkg, "**", "*"), recursive=True) + glob.glob(os.path.join(ROOT, "include", "*")):
+        if os.path.isfile(path) and not path.endswith((".so", ".pyc", ".srchash")):
+            text = open(path, errors="replace").read()
+            assert "/root/reference" not in text and "oracle/_ref" not in text, path
+    code = ("import sys; sys.path.insert(0, %r); import sttode_b200, sttode_b200._lib, sttode_b200.net, sttode_b200.layers, sttode_b200.mhgsa, sttode_b200.pmath,"
+            "sttode_b200.sampler, sttode_b200.parallel, sttode_b200.io, sttode_b200.synth, sttode_b200.compat, sttode_b200.build; sttode_b200._lib.load();"
+            "bad = [m for m in sys.modules if m == 'oracle' or m.startswith('oracle.')]; print('BAD' if bad else 'CLEAN', bad)") % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0 and "CLEAN" in out.stdout, out.stdout + out.stderr
